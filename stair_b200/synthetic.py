@@ -1,0 +1,184 @@
+"""Synthetic AGQA2-shaped questions for the NMN hot path (tests, bench, golden fixtures).
+
+The reference trains/evaluates on AGQA2 pickles + TGIF-QA style h5 features that are not on
+the box, so every test and benchmark in this repo runs on seeded synthetic data of the same
+shape.  The *layouts* are real: ``TEMPLATES`` holds the NMN prefix-token lists
+(and original-program index lists) that the reference ``utils/program_parser.py:28-170``
+``parse_program`` emits for ten AGQA program strings; ``tests/test_layout_host.py`` re-derives
+them from the reference whenever ``/root/reference`` is mounted.
+
+Data dict schema follows ``video_nmn/dataset.py:189-233`` (producer) /
+``video_nmn/module_net.py:69-71`` (consumer).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+# name -> (AGQA program string, nmn token list, idx_list) ; token lists probed from the reference.
+TEMPLATES = {
+    'exists_while': (
+        "Exists(table, Iterate(Localize(while, [sitting on a bed]), Filter(frame, [objects])))",
+        ['Exists', 'table', 'Filter', 'Temporal', 'while', 'video', 'Localize', 'video', 'sitting_on_a_bed', 'objects'],
+        [0, 1, 2, 3, None, None, 4, None, 6, 10]),
+    'choose': (
+        "Choose(dish, food, Iterate(Localize(before, [opening a door]), Filter(frame, [relations, holding, objects])))",
+        ['Choose', 'dish', 'food', 'Filter', 'Temporal', 'before', 'video', 'Localize', 'video', 'opening_a_door', 'holding'],
+        [0, 1, 2, 3, 4, None, None, 5, None, 7, 12]),
+    'and': (
+        "AND(Exists(dish, Iterate(video, Filter(frame, [objects]))), Exists(food, Iterate(video, Filter(frame, [objects]))))",
+        ['And', 'Exists', 'dish', 'Filter', 'video', 'objects', 'Exists', 'food', 'Filter', 'video', 'objects'],
+        [0, 1, 2, 3, 4, 8, 9, 10, 11, 12, 16]),
+    'equals': (
+        "Equals(Query(class, OnlyItem(Iterate(video, Filter(frame, [relations, holding, objects])))), Query(class, OnlyItem(Iterate(video, Filter(frame, [relations, touching, objects])))))",
+        ['Equals', 'Filter', 'video', 'holding', 'Filter', 'video', 'touching'],
+        [0, 4, 5, 10, 15, 16, 21]),
+    'toaction': (
+        "ToAction(holding, Query(class, OnlyItem(Iterate(video, Filter(frame, [relations, holding, objects])))))",
+        ['ToAction', 'holding', 'Filter', 'video', 'holding'],
+        [0, 1, 5, 6, 11]),
+    'superlative': (
+        "Superlative(max, Filter(video, [actions]), Subtract(Query(end, action), Query(start, action)))",
+        ['Superlative', 'max', 'FilterFrame', 'video', 'actions', 'video'],
+        [0, 1, 2, 3, 5, None]),
+    'compare': (
+        "Compare([before, after], Exists(holding a dish, Iterate(Localize(temporal tag, [watching television]), Filter(frame, [actions]))))",
+        ['Compare', 'Exists', 'holding_a_dish', 'Filter', 'Temporal', 'before', 'video', 'Localize', 'video', 'watching_television', 'actions',
+         'Exists', 'holding_a_dish', 'Filter', 'Temporal', 'after', 'video', 'Localize', 'video', 'watching_television', 'actions'],
+        [0, 4, 5, 6, 7, None, None, 8, None, 10, 14, 4, 5, 6, 7, None, None, 8, None, 10, 14]),
+    'iterate_until': (
+        "Query(class, OnlyItem(IterateUntil(forward, Localize(after, [eating some food]), HasItem(Filter(frame, [relations, taking, objects])), Filter(frame, [relations, taking, objects]))))",
+        ['Filter', 'AttnVideo', 'Temporal', 'after', 'video', 'Localize', 'video', 'eating_some_food', 'Relate', 'forward', 'HasItem',
+         'FilterFrame', 'video', 'taking', 'taking'],
+        [3, None, 5, None, None, 6, None, 8, None, 4, 9, 10, 11, 14, 20]),
+    'iterate_until_exists': (
+        "Query(class, OnlyItem(IterateUntil(backward, video, Exists(dish, Filter(frame, [relations, holding, objects])), Filter(frame, [relations, holding, objects]))))",
+        ['Filter', 'AttnVideo', 'video', 'Relate', 'backward', 'ExistsFrame', 'dish', 'FilterFrame', 'video', 'holding', 'holding'],
+        [3, None, 5, None, 4, 6, 7, 8, 9, 12, 18]),
+    'xor_between': (
+        "XOR(Exists(food, Iterate(Localize(between, [A, B]), Filter(frame, [relation, holding, objects]))), Exists(Query(class, OnlyItem(Iterate(video, Filter(frame, [relations, opening, objects])))), Iterate(Localize(between, [A, B]), Filter(frame, [relation, holding, objects]))))",
+        ['Xor', 'Exists', 'food', 'Filter', 'Temporal', 'between', 'video', 'Localize', 'video', 'Array2', 'A', 'B', 'holding',
+         'Exists', 'Filter', 'video', 'opening', 'Filter', 'Temporal', 'between', 'video', 'Localize', 'video', 'Array2', 'A', 'B', 'holding'],
+        [0, 1, 2, 3, 4, None, None, 5, None, 6, 7, 8, 13, 15, 19, 20, 25, 27, 28, None, None, 29, None, 30, 31, 32, 37]),
+}
+
+# Extra hand-written layouts (valid for the reference interpreter, module_net.py:94-133) that reach the
+# operators / dynamic-typing cases the ten AGQA templates above do not: XorFrame, And on attention maps,
+# Superlative over an Array2 of keywords (min mode), FilterFrame with string keywords, Filter 'relations'.
+EXTRA_TEMPLATES = {
+    'xorframe': (
+        None,
+        ['Filter', 'AttnVideo', 'video', 'Relate', 'forward', 'XorFrame', 'ExistsFrame', 'dish', 'FilterFrame', 'video', 'holding',
+         'ExistsFrame', 'cup', 'FilterFrame', 'video', 'relations', 'touching'],
+        [0, None, 1, None, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14]),
+    'and_frames': (
+        None,
+        ['Filter', 'AttnVideo', 'video', 'Relate', 'backward', 'And', 'ExistsFrame', 'dish', 'FilterFrame', 'video', 'actions',
+         'HasItem', 'FilterFrame', 'video', 'holding', 'relations'],
+        [0, None, 1, None, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]),
+    'superlative_min': (
+        None,
+        ['Superlative', 'min', 'Array2', 'running', 'sitting_down', 'video'],
+        [0, 1, 2, 3, 4, None]),
+    'toaction_superlative': (
+        None,
+        ['Equals', 'ToAction', 'holding', 'Filter', 'video', 'cup', 'Superlative', 'max', 'Array2', 'running', 'sitting_down',
+         'Temporal', 'after', 'video', 'Localize', 'video', 'opening_a_door'],
+        [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, None, None, 12, None, 13]),
+}
+
+ALL_TEMPLATES = {**TEMPLATES, **EXTRA_TEMPLATES}
+
+# arity table (utils/program_parser.py:16-23) restricted to the tokens the interpreter dispatches on.
+MODULE_ARITY = {
+    'And': 2, 'AttnVideo': 2, 'Choose': 3, 'Compare': 2, 'Equals': 2, 'Exists': 2, 'ExistsFrame': 2, 'Filter': 2,
+    'FilterFrame': 2, 'HasItem': 1, 'Localize': 2, 'Relate': 2, 'Superlative': 3, 'Temporal': 3, 'ToAction': 2,
+    'Xor': 2, 'XorFrame': 2, 'Array2': 2,
+}
+# video_nmn/dataset.py:23 WORDS_TO_KEEP | module_net.py:23 type keywords
+WORDS_TO_KEEP = {'forward', 'backward', 'while', 'between', 'before', 'after', 'max', 'min', 'start', 'end', 'video',
+                 'actions', 'objects', 'relations'}
+
+CLASS_POOL = ['class_%02d' % i for i in range(64)]
+
+
+def _content_positions(tokens):
+    return [i for i, t in enumerate(tokens) if t not in MODULE_ARITY and t not in WORDS_TO_KEEP]
+
+
+def make_question(rng: np.random.Generator, template: str, T: int, V: int, text_size: int = 300,
+                  answer_vocab: int = 172, with_gold: bool = False, object_types: int = 256,
+                  qa_id: str | None = None):
+    """One reference-schema ``data`` dict (CPU fp32 tensors)."""
+    _, tokens, idx_list = ALL_TEMPLATES[template]
+    L = int(rng.integers(8, 25))
+    question = torch.from_numpy((rng.standard_normal((L, text_size)) * 0.4).astype(np.float32))
+    video = torch.from_numpy(np.abs(rng.standard_normal((T, V))).astype(np.float32))
+    spans = {}
+    for i in _content_positions(tokens):
+        w = int(rng.integers(1, 4))
+        s = int(rng.integers(0, L - w + 1))
+        spans[i] = (s, s + w)
+    data = {
+        'question': question, 'video_features': video, 'prog_str_to_question_tokens': spans,
+        'nmn_program_list': list(tokens), 'nmn_program_idx': list(idx_list),
+        'answer': torch.tensor(int(rng.integers(0, answer_vocab - 1))),
+        'qa_id': qa_id or 'syn-%s' % template, 'question_raw': ' '.join(tokens), 'template': template,
+    }
+    if with_gold:
+        data['sg_res_by_step'] = make_gold(rng, tokens, idx_list, T, text_size, object_types)
+    return data
+
+
+def make_gold(rng, tokens, idx_list, T, text_size, object_types):
+    """Random intermediate supervision with the value types ``CriterionByModule`` expects
+    (train_module.py:83-194): bool / (s,e) / [(s,e)..] / {name:(s,e)} / [(class, glove[n_w,text])...]."""
+    def interval():
+        s = float(rng.uniform(0, T - 1)); e = float(rng.uniform(s + 0.05, T)); return (s, e)
+    gold = {}
+    for i, (tok, idx) in enumerate(zip(tokens, idx_list)):
+        if idx is None or i == 0 or tok not in MODULE_ARITY:
+            continue
+        if tok in ('Exists', 'Xor', 'Equals'):
+            gold[idx] = bool(rng.integers(0, 2))
+        elif tok == 'Localize':
+            # K = 2 iff the keyword argument is an Array2 (token right after the feat argument subtree)
+            k = 2 if tokens[i + 1] == 'video' and tokens[i + 2] == 'Array2' else 1
+            gold[idx] = tuple(interval() for _ in range(k))
+        elif tok in ('Temporal', 'ExistsFrame'):
+            gold[idx] = interval()
+        elif tok == 'FilterFrame':
+            gold[idx] = {'obj_%d' % int(rng.integers(0, object_types)): interval()
+                         for _ in range(int(rng.integers(1, 3)))}
+        elif tok in ('Filter', 'ToAction', 'Superlative'):
+            names = rng.choice(len(CLASS_POOL), size=int(rng.integers(1, 3)), replace=False)
+            gold[idx] = [(CLASS_POOL[int(n)], class_embedding(int(n), text_size)) for n in names]
+    return gold
+
+
+def class_embedding(class_id: int, text_size: int):
+    """Deterministic stand-in GloVe phrase [n_w, text_size] for a class name (same name -> same tensor)."""
+    r = np.random.default_rng(10_000 + class_id)
+    n_w = 1 + class_id % 3
+    return torch.from_numpy((r.standard_normal((n_w, text_size)) * 0.4).astype(np.float32))
+
+
+def make_questions(n: int, T: int, V: int, seed: int = 1234, templates=None, text_size: int = 300,
+                   with_gold: bool = False, answer_vocab: int = 172, object_types: int = 256):
+    """``n`` questions cycling through ``templates`` (default: the ten AGQA templates)."""
+    rng = np.random.default_rng(seed)
+    names = list(templates or TEMPLATES.keys())
+    return [make_question(rng, names[i % len(names)], T, V, text_size, answer_vocab, with_gold, object_types,
+                          qa_id='syn-%d' % i) for i in range(n)]
+
+
+def model_config(T: int = 8, V: int = 4096, hidden: int = 512, text_size: int = 300, dropout: float = 0.0,
+                 answer_vocab: int = 172, object_types: int = 256):
+    """Mirrors the dict built at train_module.py:304-310."""
+    return {'hidden_size': hidden, 'video_size': V, 'text_size': text_size, 'dropout': dropout,
+            'answer_vocab_length': answer_vocab, 'max_video_length': T, 'init_method': 'default', 'layer_norm': 1,
+            'have_pretrain_head': True, 'object_types': object_types}
+
+
+PRETRAIN_MODULES = {'Exists', 'Xor', 'Equals', 'Filter', 'ToAction', 'FilterFrame', 'ExistsFrame', 'Superlative',
+                    'Localize', 'Temporal', 'decoder'}   # CriterionByModule.criterions keys, train_module.py:36-48

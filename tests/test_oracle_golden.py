@@ -1,0 +1,106 @@
+"""Pin the CPU oracle (oracle/nmn_oracle.py) to the golden fixtures produced by the unmodified reference."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import nmn_oracle as orc
+from tests import golden_util as gu
+
+FIXTURES = ['rx_small', 'i3d_small']
+TOL = dict(rtol=2e-5, atol=2e-6)
+
+
+@pytest.fixture(scope='module', params=FIXTURES)
+def fx(request):
+    return gu.load(request.param)
+
+
+def test_layout_helpers_match_reference():
+    lay = json.load(open(os.path.join(gu.GOLDEN_DIR, 'layouts.json')))
+    assert {k: v for k, v in orc.NARY.items()} == lay['nary']
+    for name, t in lay['templates'].items():
+        ch, pa = orc.children_and_parents(t['tokens'])
+        assert ch == t['children'], name
+        assert pa == t['parents'], name
+        assert orc.module_levels(t['tokens']) == t['levels'], name
+        assert orc.program_is_valid(t['tokens']) == t['valid'], name
+    for prog, res in zip(lay['invalid'], lay['invalid_results']):
+        assert orc.program_is_valid(prog) == res
+
+
+def test_forward_every_intermediate(fx):
+    cfg, weights, questions, meta, _ = fx
+    model = orc.OracleNMN(cfg, weights, meta['pretrain_modules'])
+    for data, ref, q in questions:
+        with torch.no_grad():
+            out = model(data, return_res_by_step=True, return_result_of_each_step=True)
+        torch.testing.assert_close(out['logits'], ref['logits'], **TOL)
+        assert int(out['logits'].argmax()) == int(ref['logits'].argmax())
+        assert len(out['result_of_each_step']) == len(ref['steps'])
+        for j, ((_, got), want) in enumerate(zip(out['result_of_each_step'], ref['steps'])):
+            if isinstance(want, str):
+                assert got == want
+            else:
+                torch.testing.assert_close(got, want, msg=lambda m: '%s step %d: %s' % (q['template'], j, m), **TOL)
+                if want.dim() >= 1 and want.size(-1) == cfg['max_video_length'] and want.numel() <= 2 * want.size(-1):
+                    assert torch.equal(got.argmax(-1), want.argmax(-1))       # attention argmax index
+        assert set(out['res_by_step']) == set(ref['res_by_step'])
+        for k, (m, t) in ref['res_by_step'].items():
+            assert out['res_by_step'][k][0] == m
+            torch.testing.assert_close(out['res_by_step'][k][1], t, **TOL)
+        for k, reps in ref['gold_reps'].items():
+            for (n, t), (n2, t2) in zip(reps, out['sg_res_by_step'][k]):
+                assert n == n2
+                torch.testing.assert_close(t2, t, **TOL)
+
+
+def test_span_to_attention(fx):
+    for case in fx[3]['span_to_attention']:
+        got = orc.span_to_attention(tuple(case['gold']), case['T'])
+        torch.testing.assert_close(got, torch.tensor(case['out']), rtol=1e-6, atol=1e-7)
+
+
+def test_window_loss_and_gradients(fx):
+    cfg, weights, questions, meta, grads = fx
+    w = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
+    for k in list(w):        # Superlative.localize_module.* aliases Localize.* (module_net.py:31-32)
+        if k.startswith('submodules.Superlative.localize_module.'):
+            w[k] = w[k.replace('Superlative.localize_module', 'Localize')]
+    model = orc.OracleNMN(cfg, w, meta['pretrain_modules'])
+    crit = orc.OracleCriterion({'obj_%d' % i: i for i in range(cfg['object_types'])})
+    batch = [d for d, _, _ in questions]
+    total, logs, outs = orc.window_loss(model, crit, batch)
+    assert abs(float(total) - meta['window']['loss']) < 2e-5 * abs(meta['window']['loss'])
+    for name, vals in meta['window']['logs'].items():
+        assert len(vals) == len(logs[name]), name
+        for a, b in zip(sorted(vals), sorted(logs[name])):
+            assert abs(a - b) <= 2e-5 * max(1.0, abs(a)), name
+    # FilterFrame criterion (excluded from training by default, args.py:62) checked separately
+    for it, step, val in meta['window']['filterframe_losses']:
+        res = outs[it]['res_by_step'][step][1]
+        got = float(crit('FilterFrame', res, outs[it]['sg_res_by_step'][step]))
+        assert abs(got - val) <= 2e-5 * max(1.0, abs(val))
+    total.backward()
+    for k, g in grads.items():
+        got = w[k].grad
+        assert got is not None, k
+        scale = max(float(g.abs().max()), 1e-6)
+        assert float((got - g).abs().max()) <= 1e-4 * scale + 1e-7, k
+    for k in meta['params_without_grad']:
+        if k in w and not k.startswith('submodules.Superlative.localize_module.'):
+            assert w[k].grad is None or float(w[k].grad.abs().max()) == 0.0, k
+
+
+def test_relate_scan_matches_reference_formula():
+    # modules.py:290-308 is dead code in the reference forward; restated and checked on a hand example.
+    a = torch.tensor([0.1, -0.2, 0.5, 0.0, 0.3])
+    torch.testing.assert_close(orc.OracleNMN.relate_scan(a, 'before'), torch.tensor([0.1, 0.1, 0.6, 0.6, 0.9]))
+    torch.testing.assert_close(orc.OracleNMN.relate_scan(a, 'after'), torch.tensor([0.9, 0.8, 0.8, 0.3, 0.3]))
+    ab = torch.stack([a, a.flip(0)])
+    got = orc.OracleNMN.relate_scan(ab, 'between')
+    b = torch.relu(a.flip(0))
+    want = torch.max(torch.min(torch.cumsum(torch.relu(a), 0), torch.cumsum(torch.relu(a).flip(0), 0).flip(0)),
+                     torch.min(torch.cumsum(b, 0), torch.cumsum(b.flip(0), 0).flip(0)))
+    torch.testing.assert_close(got, want)
