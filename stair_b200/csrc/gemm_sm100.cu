@@ -1,0 +1,446 @@
+// Dense contraction for the NMN hot path:  C[M,N] = act(row_scale[m] * (A[M,K] · W[N,K]^T) + bias[n])
+//
+// This is the only GEMM-shaped work on the path (nn.Linear in every module, the LSTM input/recurrent
+// projections, the decoder: video_nmn/modules.py passim, video_nmn/module_net.py:39-53).  Both operands are
+// K-major bf16 (activations row-major [M,K]; nn.Linear weights are already [N,K]), accumulation is fp32.
+//
+// sm_100a design: persistent warp-specialised kernel, one CTA per SM.
+//   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
+//   warp 1 lane 0 : tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16, fp32 accumulators in TMEM)
+//   warp 2        : TMEM allocator / deallocator
+//   warps 4..7    : epilogue (tcgen05.ld 32x32b -> registers -> row_scale/bias/ReLU -> global)
+// smem ring of STAGES {A 128x64, W BNx64} tiles; TMEM double-buffered (2 x BN columns) so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
+//
+// "Split" mode (nplanes = 3) evaluates an fp32-grade product from bf16 planes x = x0 + x1 + x2 (each bf16):
+// the six significant plane products are accumulated into the same TMEM tile by looping the K range six
+// times with different plane row-offsets.  It is the strict-parity mode.
+#include "stair_common.cuh"
+#include <cuda.h>
+
+namespace stair {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                         // 64 bf16 = 128 B = one SWIZZLE_128B atom row
+constexpr int A_STAGE_BYTES = BM * BK * 2;     // 16 KiB
+constexpr int GEMM_THREADS = 256;
+
+struct GemmParams {
+    int M, N, K;
+    int num_kb;            // ceil(K / 64)
+    int nseg;              // 1, or 6 in split mode
+    int a_plane_rows, w_plane_rows;
+    const float* bias;     // [N] or null
+    const float* row_scale;// [M] or null
+    void* C;
+    long long ldc;
+    int out_dtype, act, accumulate, vec_ok;
+    int* err_flag;
+};
+
+// plane pairs (a,b) of the 6-term bf16x3 product, smallest contributions first
+__device__ __constant__ int c_seg_a[6] = {2, 0, 1, 1, 0, 0};
+__device__ __constant__ int c_seg_b[6] = {0, 2, 1, 0, 1, 0};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU (4 s wall-clock limit).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3FFu) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) {
+                if (err_flag) atomicExch(err_flag, code);
+                __threadfence_system();
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor for a K-major, 128B-swizzled tile (rows of 128 B, 8-row atoms of 1024 B):
+// start>>4 | LBO(ignored for swizzled K-major)=1 | SBO = 1024>>4 | version=1 (sm_100) | layout=SWIZZLE_128B(2).
+__device__ __forceinline__ uint64_t make_umma_desc_kmajor_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// Instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int TILE_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int TOTAL = TILE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
+};
+
+// ------------------------------------------------------------------------------------------------
+// epilogue store of one 32-column chunk of one row
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int n, const uint32_t (&raw)[32]) {
+    const float rs = p.row_scale ? __ldg(p.row_scale + row) : 1.0f;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(raw[j]) * rs;
+        if (p.bias && n + j < p.N) x += __ldg(p.bias + n + j);
+        if (p.act == STAIR_ACT_RELU) x = fmaxf(x, 0.0f);
+        v[j] = x;
+    }
+    const bool full = p.vec_ok && (n + 32 <= p.N);
+    if (p.out_dtype == STAIR_BF16) {
+        bf16* out = reinterpret_cast<bf16*>(p.C) + static_cast<long long>(row) * p.ldc + n;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint4 r;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[j + 2 * i], v[j + 2 * i + 1]);
+                *reinterpret_cast<uint4*>(out + j) = r;
+            }
+        } else {
+            for (int j = 0; j < 32; ++j) if (n + j < p.N) out[j] = __float2bfloat16_rn(v[j]);
+        }
+    } else {
+        float* out = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + n;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 r = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.accumulate) {
+                    float4 o = *reinterpret_cast<const float4*>(out + j);
+                    r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+                }
+                *reinterpret_cast<float4*>(out + j) = r;
+            }
+        } else {
+            for (int j = 0; j < 32; ++j) if (n + j < p.N) out[j] = p.accumulate ? out[j] + v[j] : v[j];
+        }
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using S = GemmSmem<BN, STAGES>;
+    constexpr int B_STAGE_BYTES = S::B_STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // power of two by construction (BN in {64,128,256})
+    constexpr uint32_t IDESC = make_idesc_bf16(BM, BN);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = (p.N + BN - 1) / BN;
+    const int tiles_m = (p.M + BM - 1) / BM;
+    const int total_tiles = tiles_m * tiles_n;
+    const int kiters = p.nseg * p.num_kb;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int seg = 0; seg < p.nseg; ++seg) {
+                    const int a_row = m0 + (p.nseg > 1 ? c_seg_a[seg] * p.a_plane_rows : 0);
+                    const int b_row = n0 + (p.nseg > 1 ? c_seg_b[seg] * p.w_plane_rows : 0);
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 101);
+                        mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+                        tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, a_row);
+                        tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, b_row);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.err_flag, 102);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int it = 0; it < kiters; ++it) {
+                    mbar_wait(&full_bar[stage], phase, p.err_flag, 103);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = make_umma_desc_kmajor_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
+                    const uint64_t bdesc = make_umma_desc_kmajor_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // +32 B per UMMA_K=16 bf16 inside the swizzle atom -> +2 in the (addr>>4) field
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);                  // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int quarter = warp - 4;                          // TMEM lanes [32*quarter, 32*quarter+32)
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 104);
+            tcgen05_fence_after();
+            const int row = m0 + quarter * 32 + lane;
+            const uint32_t t_base = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= p.N) break;                     // warp-uniform
+                uint32_t v[32];
+                tmem_ld32(t_base + static_cast<uint32_t>(c0), v);
+                tmem_ld_wait();
+                if (row < p.M) epilogue_store(p, row, n0 + c0, v);
+            }
+            tcgen05_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plain CUDA-core kernel with identical semantics.  Debug aid only (selected with stair_set_gemm_impl(1));
+// it lets every other kernel be validated on the GPU independently of the tcgen05 path.
+// ------------------------------------------------------------------------------------------------
+__global__ void gemm_simt_kernel(const bf16* __restrict__ A, long long lda, const bf16* __restrict__ W, long long ldw, GemmParams p) {
+    __shared__ float sa[16][17], sb[16][17];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+    float acc = 0.f;
+    for (int seg = 0; seg < p.nseg; ++seg) {
+        const long long a_off = p.nseg > 1 ? static_cast<long long>(c_seg_a[seg]) * p.a_plane_rows : 0;
+        const long long b_off = p.nseg > 1 ? static_cast<long long>(c_seg_b[seg]) * p.w_plane_rows : 0;
+        for (int k0 = 0; k0 < p.K; k0 += 16) {
+            const int ar = blockIdx.y * 16 + ty, br = blockIdx.x * 16 + ty;
+            sa[ty][tx] = (ar < p.M && k0 + tx < p.K) ? __bfloat162float(A[(a_off + ar) * lda + k0 + tx]) : 0.f;
+            sb[ty][tx] = (br < p.N && k0 + tx < p.K) ? __bfloat162float(W[(b_off + br) * ldw + k0 + tx]) : 0.f;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sb[tx][k];
+            __syncthreads();
+        }
+    }
+    if (row < p.M && col < p.N) {
+        float x = acc * (p.row_scale ? p.row_scale[row] : 1.f);
+        if (p.bias) x += p.bias[col];
+        if (p.act == STAIR_ACT_RELU) x = fmaxf(x, 0.f);
+        if (p.out_dtype == STAIR_BF16) reinterpret_cast<bf16*>(p.C)[static_cast<long long>(row) * p.ldc + col] = __float2bfloat16_rn(x);
+        else {
+            float* o = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + col;
+            *o = p.accumulate ? *o + x : x;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+static int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t row_pitch_elems,
+                             uint32_t box_cols, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return STAIR_ERR_CUDA;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_pitch_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? STAIR_OK : STAIR_ERR_ARG;
+}
+
+static int g_gemm_impl = 0;      // 0 = tcgen05 (product), 1 = SIMT debug kernel
+static int* g_err_flag = nullptr;
+static int g_num_sms = 0;
+
+static int* err_flag_ptr() {
+    if (!g_err_flag) {
+        if (cudaMallocHost(reinterpret_cast<void**>(&g_err_flag), sizeof(int)) != cudaSuccess) return nullptr;   // pinned, device-visible
+        *g_err_flag = 0;
+    }
+    return g_err_flag;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    using S = GemmSmem<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+            return STAIR_ERR_CUDA;
+        configured = true;
+    }
+    const int tiles = ceil_div(p.M, BM) * ceil_div(p.N, BN);
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    gemm_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, p);
+    STAIR_CHECK_LAUNCH();
+    return STAIR_OK;
+}
+
+}  // namespace stair
+
+using namespace stair;
+
+extern "C" int stair_set_gemm_impl(int impl) { g_gemm_impl = impl; return STAIR_OK; }
+extern "C" int stair_get_gemm_impl() { return g_gemm_impl; }
+extern "C" int stair_gemm_error_flag() { return g_err_flag ? *g_err_flag : 0; }
+
+// C = act(row_scale * (A · W^T) + bias).  A: bf16 [nplanes][a_plane_rows, lda], W: bf16 [nplanes][w_plane_rows, ldw].
+extern "C" int stair_gemm_bf16(const void* A, long long lda, int a_plane_rows, const void* W, long long ldw, int w_plane_rows,
+                               int nplanes, const float* bias, const float* row_scale, void* C, long long ldc, int out_dtype,
+                               int M, int N, int K, int act, int accumulate, void* stream) {
+    if (M <= 0 || N <= 0) return STAIR_OK;
+    if (K <= 0 || (nplanes != 1 && nplanes != 3) || (lda % 8) || (ldw % 8)) return STAIR_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return STAIR_ERR_ARG;
+    if (accumulate && out_dtype != STAIR_F32) return STAIR_ERR_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.num_kb = ceil_div(K, BK); p.nseg = nplanes == 3 ? 6 : 1;
+    p.a_plane_rows = a_plane_rows; p.w_plane_rows = w_plane_rows;
+    p.bias = bias; p.row_scale = row_scale; p.C = C; p.ldc = ldc; p.out_dtype = out_dtype; p.act = act; p.accumulate = accumulate;
+    const int esz = out_dtype == STAIR_BF16 ? 2 : 4;
+    p.vec_ok = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * esz) % 16 == 0) ? 1 : 0;
+    p.err_flag = err_flag_ptr();
+
+    if (g_gemm_impl == 1) {
+        dim3 grid(ceil_div(N, 16), ceil_div(M, 16)), block(16, 16);
+        gemm_simt_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const bf16*>(A), lda, reinterpret_cast<const bf16*>(W), ldw, p);
+        STAIR_CHECK_LAUNCH();
+        return STAIR_OK;
+    }
+    if (!g_num_sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return STAIR_ERR_CUDA;
+        if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return STAIR_ERR_CUDA;
+    }
+    const uint64_t a_rows = static_cast<uint64_t>(nplanes - 1) * a_plane_rows + M;
+    const uint64_t w_rows = static_cast<uint64_t>(nplanes - 1) * w_plane_rows + N;
+    const int tiles128 = ceil_div(M, BM) * ceil_div(N, 128);
+    const int bn = N <= 64 ? 64 : ((N % 256 == 0 && tiles128 >= 2 * g_num_sms) ? 256 : 128);
+    CUtensorMap ta, tb;
+    int rc = make_tmap_bf16_2d(&ta, A, K, a_rows, lda, BK, BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tb, W, K, w_rows, ldw, BK, bn);
+    if (rc) return rc;
+    if (bn == 64) return launch_tc<64, 8>(ta, tb, p, st);
+    if (bn == 256) return launch_tc<256, 4>(ta, tb, p, st);
+    return launch_tc<128, 6>(ta, tb, p, st);
+}

@@ -1,0 +1,93 @@
+"""GPU: tcgen05/TMA GEMM (stair_gemm_bf16) against a torch fp32 reference of the same contraction."""
+import pytest
+import torch
+
+from stair_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(A, W, bias, row_scale, act):
+    y = A.float() @ W.float().t()
+    if row_scale is not None:
+        y = y * row_scale[:, None]
+    if bias is not None:
+        y = y + bias
+    return torch.relu(y) if act else y
+
+
+CASES = [
+    # M, N, K, out dtype, bias, relu, row_scale
+    (128, 128, 64, torch.float32, False, False, False),
+    (128, 128, 512, torch.float32, True, False, False),
+    (256, 512, 512, torch.bfloat16, True, True, False),
+    (1000, 512, 512, torch.bfloat16, True, True, True),
+    (4096, 2048, 4096, torch.bfloat16, True, False, False),
+    (300, 172, 1024, torch.float32, True, False, False),     # decoder head: ragged N
+    (333, 64, 192, torch.float32, True, True, False),        # small-config shapes (H=64)
+    (77, 2048, 300, torch.bfloat16, True, False, False),     # text projection: K=300 (row pitch 304)
+    (5000, 1024, 256, torch.float32, False, False, False),   # LSTM recurrent projection
+    (20000, 512, 1536, torch.bfloat16, True, True, False),
+]
+
+
+@pytest.mark.parametrize('impl', [0, 1], ids=['tc', 'simt'])
+@pytest.mark.parametrize('case', CASES)
+def test_gemm_matches_fp32_reference(case, impl):
+    M, N, K, odt, use_bias, relu, use_rs = case
+    if impl == 1 and M * N * K > 3e9:
+        pytest.skip('SIMT debug kernel: small cases only')
+    g = torch.Generator(device='cuda').manual_seed(M * 7 + N * 3 + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp, device='cuda', dtype=torch.bfloat16)
+    W = torch.zeros(N, Kp, device='cuda', dtype=torch.bfloat16)
+    A[:, :K] = torch.randn(M, K, device='cuda', generator=g).bfloat16()
+    W[:, :K] = (torch.randn(N, K, device='cuda', generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device='cuda', generator=g) if use_bias else None
+    rs = torch.rand(M, device='cuda', generator=g) if use_rs else None
+    L.lib().stair_set_gemm_impl(impl)
+    try:
+        out = L.gemm(A, W, bias=bias, out_dtype=odt, act=L.ACT_RELU if relu else L.ACT_NONE, row_scale=rs, K=K)
+        torch.cuda.synchronize()
+    finally:
+        L.lib().stair_set_gemm_impl(0)
+    ref = _ref(A[:, :K], W[:, :K], bias, rs, relu)
+    tol = 2e-2 if odt == torch.bfloat16 else 2e-4
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * max(scale, 1.0), 'max err %g (scale %g)' % (err, scale)
+
+
+def test_gemm_accumulate_and_strided_output():
+    M, N, K = 512, 256, 128
+    A = torch.randn(M, K, device='cuda').bfloat16()
+    W = torch.randn(N, K, device='cuda').bfloat16()
+    big = torch.ones(M, 2 * N, device='cuda')
+    L.gemm(A, W, out=big[:, N:], accumulate=True, ldc=2 * N)
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + 1
+    assert torch.equal(big[:, :N], torch.ones(M, N, device='cuda'))
+    assert (big[:, N:] - ref).abs().max().item() < 1e-3
+
+
+def test_gemm_split3_is_fp32_grade():
+    """bf16x3 planes: six plane products accumulate to an fp32-accurate contraction."""
+    M, N, K = 700, 512, 512
+    g = torch.Generator(device='cuda').manual_seed(5)
+    A = torch.randn(M, K, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g) * K ** -0.5
+
+    def split(x):
+        p0 = x.bfloat16(); r = x - p0.float()
+        p1 = r.bfloat16(); r = r - p1.float()
+        return torch.cat([p0, p1, r.bfloat16()], dim=0).contiguous()
+    for impl in (1, 0):
+        L.lib().stair_set_gemm_impl(impl)
+        try:
+            out = L.gemm(split(A), split(W), out_dtype=torch.float32, M=M, N=N, K=K, nplanes=3, a_plane_rows=M, w_plane_rows=N)
+            torch.cuda.synchronize()
+        finally:
+            L.lib().stair_set_gemm_impl(0)
+        ref = (A.double() @ W.double().t()).float()
+        err = (out - ref).abs().max().item()
+        assert err < 2e-5 * ref.abs().max().item() + 1e-6, 'impl %d err %g' % (impl, err)
