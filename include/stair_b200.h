@@ -1,0 +1,223 @@
+/* stair_b200 — C ABI of the B200 (sm_100a) implementation of STAIR's video_nmn ModuleNet hot path.
+ *
+ * The reference (yellow-binary-tree/STAIR) is pure Python/PyTorch and has no FFI layer: its boundary for this
+ * path is the nn.Module surface of video_nmn/module_net.py:11-176 and video_nmn/modules.py:7-465.  This header
+ * is the boundary *below* that surface: stair_b200/nmn.py (the drop-in `VideoNMN`) binds it with ctypes, and a
+ * maintainer of the reference would bind exactly these entry points (INTEGRATION.md shows the stub).
+ *
+ * Conventions: every function returns 0 (STAIR_OK) or a negative STAIR_ERR_* code; nothing throws, exits,
+ * allocates device memory or synchronises — the caller (PyTorch's caching allocator) owns every buffer and all
+ * work is enqueued on the `stream` argument (a cudaStream_t passed as void*).  Pointers are device pointers
+ * unless marked HOST, and must be 16-byte aligned.  sm_100a only; there is no CPU or library fallback.
+ */
+#ifndef STAIR_B200_H
+#define STAIR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STAIR_ABI_VERSION 3
+
+/* status codes */
+#define STAIR_OK 0
+#define STAIR_ERR_ARG (-1)
+#define STAIR_ERR_CUDA (-2)
+#define STAIR_ERR_CAPACITY (-3)
+#define STAIR_ERR_LAYOUT (-4)
+#define STAIR_ERR_UNSUPPORTED (-5)
+
+/* element types of activations / inputs */
+#define STAIR_BF16 0
+#define STAIR_F32 1
+
+#define STAIR_ACT_NONE 0
+#define STAIR_ACT_RELU 1
+
+/* Operator codes.  1..18 follow NAME_TO_MODULE order (video_nmn/modules.py:446-465); 0 is a content word
+ * (phrase embedding, video_nmn/module_net.py:126-131). */
+enum StairOp {
+    STAIR_OP_WORD = 0, STAIR_OP_AND, STAIR_OP_ATTNVIDEO, STAIR_OP_CHOOSE, STAIR_OP_COMPARE, STAIR_OP_EQUALS,
+    STAIR_OP_EXISTS, STAIR_OP_EXISTSFRAME, STAIR_OP_FILTER, STAIR_OP_FILTERFRAME, STAIR_OP_HASITEM,
+    STAIR_OP_LOCALIZE, STAIR_OP_RELATE, STAIR_OP_SUPERLATIVE, STAIR_OP_TEMPORAL, STAIR_OP_TOACTION, STAIR_OP_XOR,
+    STAIR_OP_XORFRAME, STAIR_OP_ARRAY2, STAIR_OP_COUNT
+};
+
+/* Weight table slots (StairModel.w[]).  *_W matrices are bf16 [nplanes][N, K_ld] (nplanes = 1, or 3 bf16 planes
+ * w = w0+w1+w2 in strict fp32 mode), row-major with K contiguous exactly like nn.Linear.weight; everything else
+ * is fp32.  Names follow the reference state_dict keys. */
+enum StairWeight {
+    /* video_encoder / text_encoder: nn.LSTM(bidirectional), module_net.py:39-47.  WIH = [fwd ; reverse] rows (2*4h),
+     * B = b_ih + b_hh for both directions (2*4h). */
+    STAIR_W_VENC_WIH = 0, STAIR_W_VENC_B, STAIR_W_VENC_WHH_F, STAIR_W_VENC_WHH_R,
+    STAIR_W_TENC_WIH, STAIR_W_TENC_B, STAIR_W_TENC_WHH_F, STAIR_W_TENC_WHH_R,
+    /* decoder.{0,3}, module_net.py:49-53 */
+    STAIR_W_DEC0_W, STAIR_W_DEC0_B, STAIR_W_DEC1_W, STAIR_W_DEC1_B,
+    /* Localize.video_linear.{0,3}, keyword_linear.0 (modules.py:185-192); shared by Superlative (module_net.py:31-32) */
+    STAIR_W_LOC_V0_W, STAIR_W_LOC_V0_B, STAIR_W_LOC_V1_W, STAIR_W_LOC_V1_B, STAIR_W_LOC_K_W, STAIR_W_LOC_K_B,
+    /* Temporal.dense.0, layer_norm, relate.{before,after,between}.{0,2,4} (modules.py:255-283) — relate params fp32 */
+    STAIR_W_TEMP_D_W, STAIR_W_TEMP_D_B, STAIR_W_TEMP_LN_G, STAIR_W_TEMP_LN_B,
+    STAIR_W_TEMP_REL_BEFORE,               /* 6 consecutive slots per mode: w0,b0,w1,b1,w2,b2 */
+    STAIR_W_TEMP_REL_AFTER = STAIR_W_TEMP_REL_BEFORE + 6,
+    STAIR_W_TEMP_REL_BETWEEN = STAIR_W_TEMP_REL_AFTER + 6,
+    /* Filter.param.{representation,actions,objects,relations}.{0,3}, dense.0 (modules.py:346-358):
+     * 4 consecutive slots per keyword kind: w0,b0,w1,b1 */
+    STAIR_W_FILT_REPR = STAIR_W_TEMP_REL_BETWEEN + 6,
+    STAIR_W_FILT_ACTIONS = STAIR_W_FILT_REPR + 4,
+    STAIR_W_FILT_OBJECTS = STAIR_W_FILT_ACTIONS + 4,
+    STAIR_W_FILT_RELATIONS = STAIR_W_FILT_OBJECTS + 4,
+    STAIR_W_FILT_D_W = STAIR_W_FILT_RELATIONS + 4, STAIR_W_FILT_D_B,
+    /* FilterFrame.param.{representation,relations,actions}, attention.0, dense.0, pretrain_head (modules.py:384-396) */
+    STAIR_W_FF_REPR, STAIR_W_FF_RELATIONS = STAIR_W_FF_REPR + 4, STAIR_W_FF_ACTIONS = STAIR_W_FF_RELATIONS + 4,
+    STAIR_W_FF_ATT_W = STAIR_W_FF_ACTIONS + 4, STAIR_W_FF_ATT_B, STAIR_W_FF_D_W, STAIR_W_FF_D_B,
+    STAIR_W_FF_HEAD_W, STAIR_W_FF_HEAD_B,
+    /* HasItem.param.{0,3} (modules.py:126-129); param.3 (Linear(H,1)) is fp32 */
+    STAIR_W_HAS0_W, STAIR_W_HAS0_B, STAIR_W_HAS1_W, STAIR_W_HAS1_B,
+    STAIR_W_REL_BETA,                      /* Relate.beta (modules.py:420) */
+    STAIR_W_SUP_D_W, STAIR_W_SUP_D_B,      /* Superlative.dense.0 (modules.py:228-230) */
+    STAIR_W_COMPARE_W, STAIR_W_COMPARE_B,  /* Compare.param.0 (modules.py:18) */
+    STAIR_W_EQUALS_W, STAIR_W_EQUALS_B, STAIR_W_EQUALS_HEAD_W, STAIR_W_EQUALS_HEAD_B,    /* modules.py:27-29; heads fp32 */
+    STAIR_W_XOR_W, STAIR_W_XOR_B, STAIR_W_XOR_HEAD_W, STAIR_W_XOR_HEAD_B,                /* modules.py:62-64 */
+    STAIR_W_EXISTS0_W, STAIR_W_EXISTS0_B, STAIR_W_EXISTS1_W, STAIR_W_EXISTS1_B,
+    STAIR_W_EXISTS_HEAD_W, STAIR_W_EXISTS_HEAD_B,                                        /* modules.py:144-150 */
+    STAIR_W_TOACT0_W, STAIR_W_TOACT0_B, STAIR_W_TOACT1_W, STAIR_W_TOACT1_B,              /* modules.py:105-108 */
+    STAIR_W_COUNT
+};
+
+/* Static model description (config dict of train_module.py:304-310 + packed weights). */
+typedef struct StairModel {
+    int32_t T_max;       /* config['max_video_length']; Temporal.relate is Linear(T_max,T_max) iff T_max <= 32 */
+    int32_t V, V_ld;     /* config['video_size'] and the row pitch of the packed W_ih (multiple of 8) */
+    int32_t H;           /* config['hidden_size'] (multiple of 16); LSTM hidden per direction is H/2 */
+    int32_t text_size, text_ld;
+    int32_t A;           /* config['answer_vocab_length'] */
+    int32_t O;           /* config['object_types'] */
+    int32_t conv_k;      /* Temporal Conv1d kernel size round(T_max/4) when T_max > 32, else 0 */
+    int32_t precision;   /* STAIR_BF16: bf16 storage, fp32 accumulate.  STAIR_F32: fp32 storage, bf16x3 split GEMMs */
+    const void* w[STAIR_W_COUNT];
+} StairModel;
+
+/* One (level, op, variant) group of module instances; groups are listed in schedule order (level-major). */
+typedef struct StairGroup {
+    int32_t op, variant, level;
+    int32_t count;       /* instances in the batch */
+    int32_t node_off;    /* first position of the group in the sorted node order (exclusive prefix of counts) */
+    int32_t out_base;    /* first output index in the op's arena (VID slot / VEC row / ATT row) */
+    int32_t out_mult;    /* arena units per instance (K rows for Localize, 2 for Array2, else 1) */
+    int32_t aux_base;    /* first auxiliary index: Temporal -> ATT row of the stashed related_attn; modules with a
+                            pretrain head -> row in the head buffer; -1 if unused */
+    int32_t head;        /* 1: also compute the module's pretrain_head for every instance (res_by_step / audit) */
+} StairGroup;
+
+/* One batch of questions, compiled by the host (stair_b200/layout.py) from reference-schema `data` dicts
+ * (video_nmn/dataset.py:189-233).  Node order is question-major, token order within a question. */
+typedef struct StairBatch {
+    int32_t B;                 /* questions */
+    int32_t T;                 /* frames per question (uniform within a batch) */
+    int32_t n_tok;             /* sum of question lengths */
+    int32_t L_max;             /* longest question */
+    int32_t n_nodes;
+    int32_t n_groups;
+    int32_t video_dtype;       /* STAIR_F32 | STAIR_BF16 */
+    int32_t question_dtype;
+    const void* video;         /* [B*T, V] (pitch V, must be a multiple of 8 elements when bf16) */
+    const void* question;      /* [n_tok, text_size] packed word embeddings */
+    const int32_t* q_off;      /* [B+1] token offsets */
+    const int32_t* node_gid;   /* [n_nodes] group id of every node */
+    const int32_t* node_q;     /* [n_nodes] question index */
+    const int32_t* node_arg;   /* [3][n_nodes] child node index | -1 unused | -2 'video' (encoded frames of own question) */
+    const int32_t* node_span;  /* [2][n_nodes] word span of content-word nodes; start = -1 => whole question */
+    const int32_t* root_node;  /* [B] node index of token 0 */
+    const StairGroup* groups;  /* HOST [n_groups] */
+    const int32_t* group_tab;  /* device [4][n_groups]: node_off, out_base, out_mult, aux_base (same as `groups`) */
+} StairBatch;
+
+/* Caller-owned output / scratch buffers. */
+typedef struct StairBuffers {
+    void* vid;  int64_t vid_slots;    /* [vid_slots][T][H] act dtype; slots 0..B-1 = encoded video (module_net.py:160-163) */
+    void* vec;  int64_t vec_rows;     /* [vec_rows][H] act dtype */
+    float* att; int64_t att_rows;     /* [att_rows][T] fp32 attention maps */
+    void* tokfeat;                    /* [n_tok][H] act dtype (token_feature) */
+    void* qfeat;                      /* [B][H] act dtype (question_feature) */
+    float* logits;                    /* [B][A] */
+    int32_t* answers;                 /* [B] argmax(logits) */
+    float* head_small;                /* [head_small_rows][2] Equals/Xor/Exists pretrain heads */
+    float* head_vec;                  /* [head_vec_rows][H] L2-normalised Filter/Superlative/ToAction heads */
+    float* head_ff;                   /* [head_ff_rows][T][O] FilterFrame head */
+    int32_t* itab; int64_t itab_ints; /* device int workspace, >= stair_itab_ints(n_nodes, n_groups) */
+    void* workspace; int64_t workspace_bytes;   /* >= stair_nmn_workspace_bytes(...) */
+    int32_t* status;                  /* device int[4]: [0] != 0 => layout grouping mismatch / device-side error code */
+} StairBuffers;
+
+/* Offsets (in int32 units) of the device tables the grouping step leaves in StairBuffers.itab. */
+typedef struct StairItabLayout {
+    int64_t perm;        /* [n_nodes] sorted position -> node */
+    int64_t out_slot;    /* [n_nodes] node -> output index in its arena */
+    int64_t aux_slot;    /* [n_nodes] node -> auxiliary index */
+    int64_t arg_slot;    /* [3][n_nodes] sorted position -> resolved argument index */
+    int64_t pos_q;       /* [n_nodes] sorted position -> question */
+    int64_t pos_span;    /* [2][n_nodes] sorted position -> word span */
+    int64_t group_off;   /* [n_groups+1] device-computed group offsets */
+    int64_t total;
+} StairItabLayout;
+
+int stair_version(void);
+
+/* ---- dense contraction (tcgen05 + TMA): C[M,N] = act(row_scale[m] * (A[M,K] . W[N,K]^T) + bias[n]) -------------
+ * Replaces every nn.Linear / LSTM projection call site (video_nmn/modules.py passim, module_net.py:39-53). */
+int stair_gemm_bf16(const void* A, long long lda, int a_plane_rows, const void* W, long long ldw, int w_plane_rows,
+                    int nplanes, const float* bias, const float* row_scale, void* C, long long ldc, int out_dtype,
+                    int M, int N, int K, int act, int accumulate, void* stream);
+/* Same contraction with A gathered from an arena of slots: row m = slot a_slots[m / slot_rows], frame m % slot_rows.
+ * Used for every module that reads [T,H] frame features of arbitrary questions (TMA 3-D boxes, no staging copy). */
+int stair_gemm_bf16_gather(const void* arena, long long ld, long long arena_slots, const int32_t* a_slots, int slot_rows,
+                           const void* W, long long ldw, const float* bias, const float* row_scale, void* C, long long ldc,
+                           int out_dtype, int M, int N, int K, int act, void* stream);
+int stair_set_gemm_impl(int impl);      /* 0 = tcgen05 (product); 1 = SIMT debug kernel used to cross-check in tests */
+int stair_get_gemm_impl(void);
+int stair_gemm_error_flag(void);
+
+/* ---- layout grouping (utils/program_parser.py:182-200,307-321 semantics, grouped on device) --------------------
+ * Stable counting sort of the batch's nodes by group id + output-slot assignment + argument resolution. */
+int64_t stair_itab_ints(int32_t n_nodes, int32_t n_groups);
+int stair_itab_layout(int32_t n_nodes, int32_t n_groups, StairItabLayout* out /*HOST*/);
+int stair_group_layouts(const StairBatch* batch /*HOST struct*/, int32_t* itab, int32_t* status, void* stream);
+
+/* ---- whole forward: VideoNMN.forward (video_nmn/module_net.py:65-145) for a batch ------------------------------ */
+int64_t stair_nmn_workspace_bytes(const StairModel* model /*HOST*/, const StairBatch* batch /*HOST*/);
+#define STAIR_FWD_ENCODE_VIDEO 1 /* BiLSTM video encoder (module_net.py:160-163) */
+#define STAIR_FWD_ENCODE_TEXT 2  /* BiLSTM text encoder (module_net.py:147-158) */
+#define STAIR_FWD_GROUP 4        /* device layout grouping */
+#define STAIR_FWD_MODULES 8      /* grouped module execution */
+#define STAIR_FWD_DECODE 16      /* decoder + argmax (module_net.py:135-138, train_module.py:252) */
+#define STAIR_FWD_ALL 31
+int stair_nmn_forward(const StairModel* model /*HOST*/, const StairBatch* batch /*HOST*/, const StairBuffers* buf /*HOST*/,
+                      int phases, void* stream);
+/* number of kernels stair_nmn_forward launched in its last call on this thread (bench.py's gpu_launches). */
+int64_t stair_last_launch_count(void);
+
+/* ---- single operators (memory-bound kernels), exported for unit parity tests ----------------------------------- */
+/* TemporalModule.relate_ (video_nmn/modules.py:290-308): cumsum before/after/between masks.  mode: 0 while, 1 before,
+ * 2 after, 3 between (att then holds two rows per instance).  att [n][K][T] fp32 -> out [n][T]. */
+int stair_relate_scan(const float* att, int mode, float* out, int n, int T, void* stream);
+/* attention = (cos(f_t, k_k) + 1) * 0.49 (modules.py:205-216, :170-177): f [n*T,H], k [n*K,H] -> att [n][K][T] */
+int stair_cos_attention(int dtype, const void* f, const void* k, int K, int T, int H, float* att, int n, void* stream);
+/* RelateModule (modules.py:417-435): softmax_T(att +/- beta) ; sign = +1 forward, -1 backward */
+int stair_relate(const float* att, const float* beta, int sign, float* out, int n, int T, void* stream);
+/* torch.argmax over the last dim (first maximal index) */
+int stair_argmax(const float* x, int32_t* out, int rows, int cols, void* stream);
+/* L2Normalize (module_net.py:211-216, F.normalize eps 1e-12) of n rows [H] -> fp32 */
+int stair_l2normalize(int dtype, const void* x, float* out, int n, int H, void* stream);
+/* LayerNorm over H (eps 1e-5, biased variance) */
+int stair_layernorm(int dtype, const void* x, const float* gamma, const float* beta, void* out, long long rows, int H, void* stream);
+/* fp32 -> bf16 rows, and fp32 -> three bf16 planes (x = p0 + p1 + p2) used by the strict mode */
+int stair_cast_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, void* stream);
+int stair_split3(const float* src, long long ld_src, void* dst, long long ld_dst, long long plane_rows, long long rows, int cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAIR_B200_H */

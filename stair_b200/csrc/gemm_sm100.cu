@@ -35,6 +35,9 @@ struct GemmParams {
     void* C;
     long long ldc;
     int out_dtype, act, accumulate, vec_ok;
+    const int* a_slots;    // gather mode (else null)
+    int slot_rows;         // rows per slot (divides BM)
+    int num_slots;         // ceil(M / slot_rows)
     int* err_flag;
 };
 
@@ -86,6 +89,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -226,21 +235,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===================== TMA producer =====================
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-                for (int seg = 0; seg < p.nseg; ++seg) {
-                    const int a_row = m0 + (p.nseg > 1 ? c_seg_a[seg] * p.a_plane_rows : 0);
-                    const int b_row = n0 + (p.nseg > 1 ? c_seg_b[seg] * p.w_plane_rows : 0);
-                    for (int kb = 0; kb < p.num_kb; ++kb) {
+        // ===================== TMA producer (whole warp: in gather mode lane j loads slot j of the tile) ==========
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            int my_slot = -1, nvalid = 0;
+            if (p.a_slots) {
+                const int s0 = m0 / p.slot_rows;
+                nvalid = min(BM / p.slot_rows, p.num_slots - s0);
+                if (lane < nvalid) my_slot = __ldg(p.a_slots + s0 + lane);
+            }
+            const uint32_t a_bytes = p.a_slots ? static_cast<uint32_t>(nvalid * p.slot_rows * BK * 2) : A_STAGE_BYTES;
+            for (int seg = 0; seg < p.nseg; ++seg) {
+                const int a_row = m0 + (p.nseg > 1 ? c_seg_a[seg] * p.a_plane_rows : 0);
+                const int b_row = n0 + (p.nseg > 1 ? c_seg_b[seg] * p.w_plane_rows : 0);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    if (lane == 0) {
                         mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 101);
-                        mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                        tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, a_row);
+                        mbar_arrive_expect_tx(&full_bar[stage], a_bytes + B_STAGE_BYTES);
                         tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, b_row);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (!p.a_slots) tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, a_row);
                     }
+                    if (p.a_slots) {
+                        __syncwarp();
+                        if (my_slot >= 0)
+                            tma_load_3d(sA + stage * A_STAGE_BYTES + lane * p.slot_rows * (BK * 2), &tmA, &full_bar[stage],
+                                        kb * BK, 0, my_slot);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -366,6 +388,20 @@ static int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t cols, u
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? STAIR_OK : STAIR_ERR_ARG;
 }
+// slot arena [slots][slot_rows][cols] with row pitch `row_pitch_elems`; one box = one slot x 64 columns
+static int make_tmap_bf16_slots(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t slot_rows, uint64_t slots,
+                                uint64_t row_pitch_elems) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return STAIR_ERR_CUDA;
+    cuuint64_t gdim[3] = {cols, slot_rows, slots};
+    cuuint64_t gstride[2] = {row_pitch_elems * 2, row_pitch_elems * 2 * slot_rows};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(slot_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? STAIR_OK : STAIR_ERR_ARG;
+}
 
 static int g_gemm_impl = 0;      // 0 = tcgen05 (product), 1 = SIMT debug kernel
 static int* g_err_flag = nullptr;
@@ -395,6 +431,51 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     return STAIR_OK;
 }
 
+thread_local long long g_launch_count = 0;
+
+int launch_gemm(const GemmArgs& a, cudaStream_t st) {
+    if (a.M <= 0 || a.N <= 0) return STAIR_OK;
+    if (a.K <= 0 || (a.nplanes != 1 && a.nplanes != 3) || (a.lda % 8) || (a.ldw % 8)) return STAIR_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.W) & 15)) return STAIR_ERR_ARG;
+    if (a.accumulate && a.out_dtype != STAIR_F32) return STAIR_ERR_ARG;
+    const bool gather = a.a_slots != nullptr;
+    if (gather && (a.nplanes != 1 || !gemm_gather_ok(a.slot_rows) || a.M % a.slot_rows)) return STAIR_ERR_ARG;
+    GemmParams p;
+    p.M = a.M; p.N = a.N; p.K = a.K; p.num_kb = ceil_div(a.K, BK); p.nseg = a.nplanes == 3 ? 6 : 1;
+    p.a_plane_rows = a.a_plane_rows; p.w_plane_rows = a.w_plane_rows;
+    p.bias = a.bias; p.row_scale = a.row_scale; p.C = a.C; p.ldc = a.ldc; p.out_dtype = a.out_dtype; p.act = a.act;
+    p.accumulate = a.accumulate;
+    const int esz = a.out_dtype == STAIR_BF16 ? 2 : 4;
+    p.vec_ok = ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.ldc * esz) % 16 == 0) ? 1 : 0;
+    p.a_slots = a.a_slots; p.slot_rows = gather ? a.slot_rows : BM; p.num_slots = gather ? a.M / a.slot_rows : 0;
+    p.err_flag = err_flag_ptr();
+
+    if (g_gemm_impl == 1 && !gather) {
+        dim3 grid(ceil_div(a.N, 16), ceil_div(a.M, 16)), block(16, 16);
+        gemm_simt_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const bf16*>(a.A), a.lda, reinterpret_cast<const bf16*>(a.W), a.ldw, p);
+        STAIR_CHECK_LAUNCH();
+        return STAIR_OK;
+    }
+    if (!g_num_sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return STAIR_ERR_CUDA;
+        if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return STAIR_ERR_CUDA;
+    }
+    const uint64_t a_rows = static_cast<uint64_t>(a.nplanes - 1) * a.a_plane_rows + a.M;
+    const uint64_t w_rows = static_cast<uint64_t>(a.nplanes - 1) * a.w_plane_rows + a.N;
+    const int tiles128 = ceil_div(a.M, BM) * ceil_div(a.N, 128);
+    const int bn = a.N <= 64 ? 64 : ((a.N % 256 == 0 && tiles128 >= 2 * g_num_sms) ? 256 : 128);
+    CUtensorMap ta, tb;
+    int rc = gather ? make_tmap_bf16_slots(&ta, a.A, a.K, a.slot_rows, a.arena_slots, a.lda)
+                    : make_tmap_bf16_2d(&ta, a.A, a.K, a_rows, a.lda, BK, BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tb, a.W, a.K, w_rows, a.ldw, BK, bn);
+    if (rc) return rc;
+    if (bn == 64) return launch_tc<64, 8>(ta, tb, p, st);
+    if (bn == 256) return launch_tc<256, 4>(ta, tb, p, st);
+    return launch_tc<128, 6>(ta, tb, p, st);
+}
+
 }  // namespace stair
 
 using namespace stair;
@@ -407,40 +488,18 @@ extern "C" int stair_gemm_error_flag() { return g_err_flag ? *g_err_flag : 0; }
 extern "C" int stair_gemm_bf16(const void* A, long long lda, int a_plane_rows, const void* W, long long ldw, int w_plane_rows,
                                int nplanes, const float* bias, const float* row_scale, void* C, long long ldc, int out_dtype,
                                int M, int N, int K, int act, int accumulate, void* stream) {
-    if (M <= 0 || N <= 0) return STAIR_OK;
-    if (K <= 0 || (nplanes != 1 && nplanes != 3) || (lda % 8) || (ldw % 8)) return STAIR_ERR_ARG;
-    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return STAIR_ERR_ARG;
-    if (accumulate && out_dtype != STAIR_F32) return STAIR_ERR_ARG;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    GemmParams p;
-    p.M = M; p.N = N; p.K = K; p.num_kb = ceil_div(K, BK); p.nseg = nplanes == 3 ? 6 : 1;
-    p.a_plane_rows = a_plane_rows; p.w_plane_rows = w_plane_rows;
-    p.bias = bias; p.row_scale = row_scale; p.C = C; p.ldc = ldc; p.out_dtype = out_dtype; p.act = act; p.accumulate = accumulate;
-    const int esz = out_dtype == STAIR_BF16 ? 2 : 4;
-    p.vec_ok = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * esz) % 16 == 0) ? 1 : 0;
-    p.err_flag = err_flag_ptr();
+    GemmArgs a;
+    a.A = A; a.lda = lda; a.a_plane_rows = a_plane_rows; a.W = W; a.ldw = ldw; a.w_plane_rows = w_plane_rows; a.nplanes = nplanes;
+    a.bias = bias; a.row_scale = row_scale; a.C = C; a.ldc = ldc; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K;
+    a.act = act; a.accumulate = accumulate;
+    return launch_gemm(a, reinterpret_cast<cudaStream_t>(stream));
+}
 
-    if (g_gemm_impl == 1) {
-        dim3 grid(ceil_div(N, 16), ceil_div(M, 16)), block(16, 16);
-        gemm_simt_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const bf16*>(A), lda, reinterpret_cast<const bf16*>(W), ldw, p);
-        STAIR_CHECK_LAUNCH();
-        return STAIR_OK;
-    }
-    if (!g_num_sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return STAIR_ERR_CUDA;
-        if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return STAIR_ERR_CUDA;
-    }
-    const uint64_t a_rows = static_cast<uint64_t>(nplanes - 1) * a_plane_rows + M;
-    const uint64_t w_rows = static_cast<uint64_t>(nplanes - 1) * w_plane_rows + N;
-    const int tiles128 = ceil_div(M, BM) * ceil_div(N, 128);
-    const int bn = N <= 64 ? 64 : ((N % 256 == 0 && tiles128 >= 2 * g_num_sms) ? 256 : 128);
-    CUtensorMap ta, tb;
-    int rc = make_tmap_bf16_2d(&ta, A, K, a_rows, lda, BK, BM);
-    if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tb, W, K, w_rows, ldw, BK, bn);
-    if (rc) return rc;
-    if (bn == 64) return launch_tc<64, 8>(ta, tb, p, st);
-    if (bn == 256) return launch_tc<256, 4>(ta, tb, p, st);
-    return launch_tc<128, 6>(ta, tb, p, st);
+extern "C" int stair_gemm_bf16_gather(const void* arena, long long ld, long long arena_slots, const int32_t* a_slots, int slot_rows,
+                                      const void* W, long long ldw, const float* bias, const float* row_scale, void* C, long long ldc,
+                                      int out_dtype, int M, int N, int K, int act, void* stream) {
+    GemmArgs a;
+    a.A = arena; a.lda = ld; a.arena_slots = arena_slots; a.a_slots = a_slots; a.slot_rows = slot_rows; a.W = W; a.ldw = ldw;
+    a.bias = bias; a.row_scale = row_scale; a.C = C; a.ldc = ldc; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K; a.act = act;
+    return launch_gemm(a, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -1,57 +1,76 @@
-// Internal launch API of the memory-bound NMN kernels (nmn_kernels.cu) used by the executor (executor.cu).
-// Every function enqueues on `st` and returns a STAIR_* status; nothing allocates or synchronises.
+// Internal launch API of the memory-bound NMN kernels (nmn_kernels.cu, lstm.cu, layout_group.cu) used by the
+// executor (executor.cu).  Every function enqueues on `st` and returns a STAIR_* status; nothing allocates or
+// synchronises.
 //
-// Arena conventions:  VID slot s -> vid + s*T*H ;  VEC row r -> vec + r*H ;
-// ATT row r -> att + r*T (fp32).  `dt` is the activation dtype of VID/VEC (STAIR_BF16 | STAIR_F32).
+// Arena conventions:  VID slot s -> vid + s*T*H ;  VEC row r -> vec + r*H ;  ATT row r -> att + r*T
+// (fp32).  `dt` is the activation dtype of VID/VEC (STAIR_BF16 | STAIR_F32).  Index arrays (`*_idx`) are in the
+// sorted (grouped) node order produced by layout_group.cu; outputs of a group are contiguous from `out_base`.
 #pragma once
 #include "stair_common.cuh"
 
 namespace stair {
 
-// utility
-int launch_cast_f32_to_bf16(const float* src, bf16* dst, long long rows, int cols, long long ld_src, long long ld_dst, cudaStream_t st);
-int launch_split3(const float* src, long long ld_src, bf16* dst, long long plane_rows, long long ld_dst, long long rows, int cols, cudaStream_t st);
-int launch_split3_from_bf16(const bf16* src, long long ld_src, bf16* dst, long long plane_rows, long long ld_dst, long long rows, int cols, cudaStream_t st);
-
-// gathers / elementwise
-int launch_gather_vid(int dt, const void* vid, const int* slot, void* dst, int n, int T, int H, cudaStream_t st);
-int launch_word_embed(int dt, const void* tokfeat, const int* q_off, const int* inst_q, const int* span, void* vec, const int* out_row,
-                      int n, int H, cudaStream_t st);
-int launch_cos_att(int dt, const void* f, const void* kmat, int K, int T, int H, float* att, const int* out_row, int n, cudaStream_t st);
-int launch_temporal_relate(const float* att, const int* arg_row, const int* arg_k, int mode, int conv_mode, int ksize,
-                           const float* const* params /*[6]: w0,b0,w1,b1,w2,b2*/, float* r_out, int n, int T, cudaStream_t st);
-int launch_layernorm(int dt, const void* x, const float* gamma, const float* beta, void* out, long long rows, int H, cudaStream_t st);
-int launch_sum_T(int dt, const void* x, void* out, int n, int T, int H, cudaStream_t st);
-int launch_ff_attn(int dt, void* x, const void* vec, const int* kw_row, const float* w, const float* b, int n, int T, int H, cudaStream_t st);
-int launch_attnvideo(int dt, const void* vid, const int* feat_slot, const float* att, const int* att_row, void* vid_out, const int* out_slot,
-                     int n, int T, int H, cudaStream_t st);
-int launch_relate(const float* att, const int* arg_row, const float* beta, int sign, float* att_out, const int* out_row, int n, int T, cudaStream_t st);
-int launch_rowdot_sigmoid(int dt, const void* x, const float* w, const float* b, float* att, const int* out_row, int n, int T, int H, cudaStream_t st);
-int launch_existsframe(int dt, const void* vid, const int* feat_slot, const void* vec, const int* kw_row, float* att, const int* out_row,
-                       int n, int T, int H, cudaStream_t st);
-// concat modes
+// ---- GEMM operand staging -------------------------------------------------------------------------------------
+// dst (bf16, `nplanes` planes of `plane_rows` rows, pitch ld_dst) <- rows of src (`sdt`, pitch ld_src), optionally
+// gathered: source row of destination row r is slots[r / rps] * unit + r % rps (VID slots: unit = rps = T; VEC rows:
+// unit = 1).  Columns [cols, ld_dst) are zeroed.
+int launch_stage_rows(int sdt, const void* src, long long ld_src, const int* slots, int rps, int unit, bf16* dst, long long ld_dst,
+                      long long plane_rows, int nplanes, long long rows, int cols, cudaStream_t st);
 #define STAIR_CAT_EXISTS 0   // [b | a | b*a]  with a = arg0 (keyword), b = arg1 (feat)      modules.py:158
 #define STAIR_CAT_XOR 1      // [|a-b| | a | b]                                             modules.py:72
 #define STAIR_CAT_PAIR 2     // [a | b]                                                     modules.py:21,37,119
-int launch_concat_vec(int dt, const void* vec, const int* a_row, const int* b_row, int mode, void* dst, int n, int H, cudaStream_t st);
-int launch_choose(int dt, void* vec, const int* k1, const int* k2, const int* q, const int* out_row, int n, int H, cudaStream_t st);
+int launch_concat_vec(int dt, const void* vec, const int* a_idx, const int* b_idx, int mode, bf16* dst, long long plane_rows,
+                      int nplanes, int n, int H, cudaStream_t st);
+// [root VEC row | question_feature]  (module_net.py:136)
+int launch_decoder_concat(int dt, const void* vec, const int* root_node, const int* out_slot, const void* qfeat, bf16* dst, long long plane_rows,
+                          int nplanes, int B, int H, cudaStream_t st);
+
+// ---- module kernels ---------------------------------------------------------------------------------------------
+int launch_word_embed(int dt, const void* tokfeat, const int* q_off, const int* pos_q, const int* span_s, const int* span_e,
+                      void* vec, int out_base, int n, int H, cudaStream_t st);
+// att[(out_base + i*K + k)*T + t] = (cos(f[i*T+t], kmat[i*K+k]) + 1) * 0.49
+int launch_cos_att(int dt, const void* f, const void* kmat, int K, int T, int H, float* att, long long out_base, int n, cudaStream_t st);
+int launch_existsframe(int dt, const void* vid, const int* feat_idx, const void* vec, const int* kw_idx, float* att, int out_base,
+                       int n, int T, int H, cudaStream_t st);
+// r[(aux_base+i)*T + t] = relate[mode](mean_k att[(att_idx[i]+k)*T + t]);  params = {w0,b0,w1,b1,w2,b2} (Linear [T,T] or conv [k])
+int launch_temporal_relate(const float* att, const int* att_idx, int K, int mode, int conv_k, const float* const* params,
+                           float* att_out, int aux_base, int n, int T, cudaStream_t st);
+int launch_layernorm(int dt, const void* x, const float* gamma, const float* beta, void* out, long long rows, int H, cudaStream_t st);
+int launch_sum_T(int dt, const void* x, void* out, int n, int T, int H, cudaStream_t st);
+// a[i*T+t] = sigmoid(w[0:H].x[i*T+t] + w[H:2H].vec[kw_idx[i]] + b)       (FilterFrame.attention, modules.py:407-409)
+int launch_ff_attn(int dt, const void* x, const void* vec, const int* kw_idx, const float* w, const float* b, float* a,
+                   int n, int T, int H, cudaStream_t st);
+int launch_attnvideo(int dt, void* vid, const int* feat_idx, const float* att, const int* att_idx, int out_base,
+                     int n, int T, int H, cudaStream_t st);
+int launch_relate(const float* att, const int* att_idx, const float* beta, int sign, float* att_out, int out_base, int n, int T, cudaStream_t st);
+// att[(out_base+i)*T+t] = sigmoid(w.x[i*T+t] + b)                          (HasItem tail, modules.py:128-129)
+int launch_rowdot_sigmoid(int dt, const void* x, const float* w, const float* b, float* att, int out_base, int n, int T, int H, cudaStream_t st);
+int launch_choose(int dt, void* vec, const int* k1, const int* k2, const int* q, int out_base, int n, int H, cudaStream_t st);
 #define STAIR_BIN_MIN 0
 #define STAIR_BIN_ABSDIFF 1
-int launch_binary_vec(int dt, void* vec, const int* a_row, const int* b_row, const int* out_row, int op, int n, int H, cudaStream_t st);
-int launch_binary_att(float* att, const int* a_row, const int* b_row, const int* out_row, int op, int n, int T, cudaStream_t st);
-int launch_array2(int dt, void* vec, const int* a_row, const int* b_row, const int* out_row, int n, int H, cudaStream_t st);
-int launch_super_weights(int dt, const float* att_scratch, int K, int T, int H, int is_min, const void* actions_base, const int* actions_idx,
-                         long long actions_stride /*elements between instances' index units*/, void* dst, int n, cudaStream_t st);
-int launch_small_head(int dt, const void* vec, const int* row, const float* w, const float* b, int nout, float* out, int n, int H, cudaStream_t st);
-int launch_l2norm(int dt, const void* vec, const int* row, float* out, int n, int H, cudaStream_t st);
-int launch_decoder_concat(int dt, const void* vec, const int* root_row, const void* qfeat, void* dst, int B, int H, cudaStream_t st);
-int launch_argmax(const float* logits, int* out, int B, int A, cudaStream_t st);
+// len = elements per instance (H for VEC rows, K*T for ATT rows); base arrays index units of `unit` elements
+int launch_binary(int dt, void* base, const int* a_idx, const int* b_idx, int out_base, int unit, int len, int op, int n, cudaStream_t st);
+int launch_array2(int dt, void* vec, const int* a_idx, const int* b_idx, int out_base, int n, int H, cudaStream_t st);
+// Superlative tail (modules.py:243-247): w = softmax_K(sum_t att[i][k][t]); min -> 1-w; dst[i] = sum_k w_k actions[i][k]
+// actions rows: base + (act_idx[i]*act_unit + k) * H
+int launch_super_mix(int dt, const float* att, int K, int T, int H, int is_min, const void* act_base, const int* act_idx, int act_unit,
+                     void* dst, int n, cudaStream_t st);
+int launch_small_head(int dt, const void* vec, int row_base, const float* w, const float* b, int nout, float* out, int out_base, int n, int H, cudaStream_t st);
+int launch_l2norm(int dt, const void* vec, int row_base, float* out, int out_base, int n, int H, cudaStream_t st);
+int launch_argmax(const float* logits, int* out, int rows, int cols, cudaStream_t st);
 int launch_relate_scan(const float* att, int mode, float* out, int n, int T, cudaStream_t st);
 
-// LSTM cells (gate order i,f,g,o; video_nmn/module_net.py:39-47)
-int launch_lstm_cell_video(int dt, const void* xproj, const float* hw_f, const float* hw_r, float* c /*[2][B][h]*/, void* out /*[B,T,2h]*/,
+// ---- LSTM cells (gate order i,f,g,o; nn.LSTM, video_nmn/module_net.py:39-47) -------------------------------------
+// xproj [rows, 8h] = W_ih x + b for both directions (fwd gates | reverse gates); g [2][B, 4h] = W_hh h_prev (fp32);
+// c [2][B,h] fp32; hstate bf16 [nplanes][2*B, h] (A operand of the next step; direction d at rows d*B..);
+// video: out[(b*T+t)*2h + d*h + j].
+int launch_lstm_cell_video(int xdt, const void* xproj, const float* g, float* c, bf16* hstate, int nplanes, int odt, void* out,
                            int B, int T, int h, int step, cudaStream_t st);
-int launch_lstm_cell_text(int dt, const void* xproj, const float* hw_f, const float* hw_r, float* c, void* tokfeat /*[sumL,2h]*/,
-                          void* hstate /*[B,2h]*/, const int* q_off, int B, int h, int step, cudaStream_t st);
+// text: ragged; direction 0 consumes token step, direction 1 token L-1-step; final h of both directions -> qfeat [B, 2h]
+int launch_lstm_cell_text(int xdt, const void* xproj, const float* g, float* c, bf16* hstate, int nplanes, int odt, void* tokfeat,
+                          void* qfeat, const int* q_off, int B, int h, int step, cudaStream_t st);
+
+// ---- layout grouping (layout_group.cu) ----------------------------------------------------------------------------
+int launch_group_layouts(const StairBatch& b, int32_t* itab, int32_t* status, cudaStream_t st);
 
 }  // namespace stair

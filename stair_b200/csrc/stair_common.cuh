@@ -4,25 +4,16 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
-#define STAIR_OK 0
-#define STAIR_ERR_ARG (-1)
-#define STAIR_ERR_CUDA (-2)
-#define STAIR_ERR_CAPACITY (-3)
-#define STAIR_ERR_LAYOUT (-4)
-#define STAIR_ERR_UNSUPPORTED (-5)
-
-#define STAIR_BF16 0
-#define STAIR_F32 1
-
-#define STAIR_ACT_NONE 0
-#define STAIR_ACT_RELU 1
+#include "stair_b200.h"
 
 namespace stair {
 
 typedef __nv_bfloat16 bf16;
 
 static inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? STAIR_OK : STAIR_ERR_CUDA; }
-#define STAIR_CHECK_LAUNCH() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return STAIR_ERR_CUDA; } while (0)
+extern thread_local long long g_launch_count;     // kernels launched by this thread (stair_last_launch_count)
+#define STAIR_CHECK_LAUNCH() do { ++::stair::g_launch_count; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return STAIR_ERR_CUDA; } while (0)
+#define STAIR_TRY(expr) do { int rc__ = (expr); if (rc__ != STAIR_OK) return rc__; } while (0)
 
 __host__ __device__ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -74,5 +65,30 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---- internal GEMM launch API (gemm_sm100.cu) ----------------------------------------------------
+struct GemmArgs {
+    const void* A = nullptr;        // bf16 [nplanes][a_plane_rows, lda]  (or the slot arena in gather mode)
+    long long lda = 0;
+    int a_plane_rows = 0;
+    const int* a_slots = nullptr;   // gather mode: row m comes from slot a_slots[m / slot_rows], row m % slot_rows
+    int slot_rows = 0;
+    long long arena_slots = 0;
+    const void* W = nullptr;        // bf16 [nplanes][w_plane_rows, ldw]
+    long long ldw = 0;
+    int w_plane_rows = 0;
+    int nplanes = 1;
+    const float* bias = nullptr;
+    const float* row_scale = nullptr;
+    void* C = nullptr;
+    long long ldc = 0;
+    int out_dtype = STAIR_BF16;
+    int M = 0, N = 0, K = 0;
+    int act = STAIR_ACT_NONE;
+    int accumulate = 0;
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t st);
+// true when the TMA slot-gather path can serve this (slot_rows, K) without a staging copy
+static inline bool gemm_gather_ok(int slot_rows) { return slot_rows >= 8 && slot_rows <= 128 && (128 % slot_rows) == 0; }
 
 }  // namespace stair

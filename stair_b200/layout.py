@@ -1,0 +1,413 @@
+"""Host-side layout compiler: NMN prefix-token programs -> typed node tables for the device executor.
+
+The reference interprets ``nmn_program_list`` with a dynamically-typed Python stack, one question at a time
+(video_nmn/module_net.py:94-133), with arities from ``nary_mappings`` (utils/program_parser.py:16-23).  Here every
+distinct token list is compiled ONCE into a typed DAG (``Layout``): node = module call or content word, keyword
+strings (``while``, ``forward``, ``objects`` ...) folded into the consuming module's *variant*, children/levels as in
+utils/program_parser.py:182-200 / :307-321.  ``collate`` concatenates the cached layouts of a batch into SoA int32
+tables; the stable grouping by (level, op, variant), output-slot assignment and argument resolution then happen on
+the device (csrc/layout_group.cu).  The host only histograms the group keys (``np.bincount``) so that launch
+dimensions are known without a device->host sync.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+# utils/program_parser.py:16-23 — arity of every module token
+NARY = {}
+for _n, _names in ((1, 'Array1 HasItem OnlyItem Query'),
+                   (2, 'Array2 AND XOR And Xor Compare Equals Exists Filter Iterate Localize ToAction Relate AttnVideo '
+                       'FilterFrame ExistsFrame XorFrame'),
+                   (3, 'Array3 Superlative Choose Temporal'), (4, 'IterateUntil')):
+    for _t in _names.split():
+        NARY[_t] = _n
+
+# video_nmn/modules.py:446-465 — the modules the interpreter dispatches on, in NAME_TO_MODULE order
+MODULE_NAMES = ['And', 'AttnVideo', 'Choose', 'Compare', 'Equals', 'Exists', 'ExistsFrame', 'Filter', 'FilterFrame', 'HasItem',
+                'Localize', 'Relate', 'Superlative', 'Temporal', 'ToAction', 'Xor', 'XorFrame', 'Array2']
+OP_OF = {name: L.OP[name.upper()] for name in MODULE_NAMES}
+OP_WORD = L.OP['WORD']
+OP_NAME = {v: k for k, v in OP_OF.items()}
+OP_NAME[OP_WORD] = '<word>'
+
+# video_nmn/dataset.py:23 | video_nmn/module_net.py:23-25
+WORDS_TO_KEEP = frozenset(['forward', 'backward', 'while', 'between', 'before', 'after', 'max', 'min', 'start', 'end', 'video',
+                           'actions', 'objects', 'relations'])
+
+TEMPORAL_MODES = {'while': 0, 'before': 1, 'after': 2, 'between': 3}
+FILTER_KINDS = {'actions': 1, 'objects': 2, 'relations': 3}                 # 0 = tensor keyword ('representation')
+FILTERFRAME_KINDS = {'relations': 1, 'actions': 2}                          # no 'objects' branch in the reference (KeyError)
+
+# value types on the interpreter stack
+STR, VID, ATT, VEC, VEC2 = 'str', 'vid', 'att', 'vec', 'vec2'
+ARENA_OF = {VID: 'vid', VEC: 'vec', VEC2: 'vec', ATT: 'att'}
+
+
+def children_and_parents(tokens):
+    """utils/program_parser.py:182-200 semantics (children in pop order, parent index per token)."""
+    children, parents, stack = [[] for _ in tokens], [0] * len(tokens), []
+    for i in range(len(tokens) - 1, -1, -1):
+        for _ in range(NARY.get(tokens[i], 0)):
+            children[i].append(stack.pop())
+        stack.append(i)
+    for i, ch in enumerate(children):
+        for c in ch:
+            parents[c] = i
+    return children, parents
+
+
+def module_levels(tokens):
+    """utils/program_parser.py:307-321 semantics: leaves 0, module = 1 + max(children)."""
+    lv, stack = [0] * len(tokens), []
+    for i in range(len(tokens) - 1, -1, -1):
+        n = NARY.get(tokens[i], 0)
+        if n:
+            args = [stack.pop() for _ in range(n)]
+            lv[i] = 1 + max(args)
+        stack.append(lv[i])
+    return lv
+
+
+def program_is_valid(tokens):
+    """utils/program_parser.py:324-333."""
+    depth = 0
+    for tok in reversed(tokens):
+        depth += 1 - NARY.get(tok, 0)
+        if depth < 1:
+            return False
+    return depth == 1
+
+
+class _Val:
+    __slots__ = ('type', 'node', 'K', 'text', 'level')
+
+    def __init__(self, type_, node=-1, K=1, text=None, level=0):
+        self.type, self.node, self.K, self.text, self.level = type_, node, K, text, level
+
+
+def _type_error(tok, what):
+    return TypeError('%s: %s (the reference interpreter fails on this layout too)' % (tok, what))
+
+
+class Layout:
+    """One compiled token list.  Node i = i-th token that is a module call or a content word (token order)."""
+
+    def __init__(self, tokens, submodules=MODULE_NAMES, words_to_keep=WORDS_TO_KEEP):
+        self.tokens = tuple(tokens)
+        n_tok = len(tokens)
+        node_of_token, n = [-1] * n_tok, 0
+        for i, tok in enumerate(tokens):
+            if tok in submodules or tok not in words_to_keep:
+                node_of_token[i] = n
+                n += 1
+        self.n = n
+        self.node_of_token = node_of_token
+        self.token_of_node = [i for i, x in enumerate(node_of_token) if x >= 0]
+        op = np.zeros(n, np.int32); variant = np.zeros(n, np.int32); level = np.zeros(n, np.int32)
+        args = np.full((3, n), -1, np.int32)
+        out_type = [None] * n; out_K = [1] * n
+        self.param_tokens = [[] for _ in range(n_tok)]          # token positions of each call's params (pop order)
+        stack = []
+        for i in range(n_tok - 1, -1, -1):
+            tok = tokens[i]
+            if tok in submodules:                                # module_net.py:100-106
+                ps = [stack.pop() for _ in range(NARY[tok])]     # IndexError on an empty stack, like the reference
+                self.param_tokens[i] = [p.text[1] if p.type == STR else self.token_of_node[p.node] for p in ps]
+                vals = [(_Val(VID, -2, level=0) if (p.type == STR and p.text[0] == 'video') else p) for p in ps]
+                nd = node_of_token[i]
+                v, a, t, K = self._resolve(tok, vals)
+                op[nd], variant[nd] = OP_OF[tok], v
+                for k, x in enumerate(a):
+                    args[k, nd] = x
+                lvl = 1 + max(p.level for p in ps)
+                level[nd] = lvl
+                out_type[nd], out_K[nd] = t, K
+                stack.append(_Val(t, nd, K, level=lvl))
+            elif tok in words_to_keep:                           # module_net.py:121-124
+                stack.append(_Val(STR, text=(tok, i)))
+            else:                                                # module_net.py:126-131: phrase embedding
+                nd = node_of_token[i]
+                op[nd] = OP_WORD
+                out_type[nd] = VEC
+                stack.append(_Val(VEC, nd))
+        assert len(stack) == 1                                   # module_net.py:135
+        root = stack[0]
+        if root.type != VEC:
+            raise _type_error(tokens[0], 'the program result must be a [hidden] vector for the decoder, got %s' % root.type)
+        self.root = root.node
+        self.op, self.variant, self.level, self.args = op, variant, level, args
+        self.out_type, self.out_K = out_type, out_K
+        self.key = (level.astype(np.int64) * 32 + op) * 8 + variant          # ascending key = schedule order
+        self.word_nodes = [nd for nd in range(n) if op[nd] == OP_WORD]
+        self.is_module = op != OP_WORD
+
+    @staticmethod
+    def _resolve(tok, p):
+        """-> (variant, arg nodes, out type, out K) with the reference's argument order (pop order)."""
+        ty = [x.type for x in p]
+
+        def need(cond, what):
+            if not cond:
+                raise _type_error(tok, what)
+        if tok in ('And', 'XorFrame'):                                           # modules.py:7-12, 75-80
+            need(ty[0] == ty[1] and ty[0] in (VEC, ATT) and p[0].K == p[1].K, 'operands must both be vectors or both attention maps')
+            return (0 if ty[0] == VEC else p[0].K), [p[0].node, p[1].node], ty[0], p[0].K
+        if tok == 'AttnVideo':                                                   # (feat, attn) modules.py:330-340
+            need(ty[0] == VID and ty[1] == ATT and p[1].K == 1, 'expects (frame features, [T] attention)')
+            return 0, [p[0].node, p[1].node], VID, 1
+        if tok == 'Choose':
+            need(ty == [VEC, VEC, VEC], 'expects three vectors')
+            return 0, [x.node for x in p], VEC, 1
+        if tok in ('Compare', 'Equals', 'Xor', 'ToAction', 'Exists'):
+            need(ty == [VEC, VEC], 'expects two vectors')
+            return 0, [p[0].node, p[1].node], VEC, 1
+        if tok == 'ExistsFrame':                                                 # (keyword, feat) modules.py:169
+            need(ty == [VEC, VID], 'expects (keyword vector, frame features)')
+            return 0, [p[0].node, p[1].node], ATT, 1
+        if tok == 'Filter':                                                      # (feat, keyword) modules.py:361
+            need(ty[0] == VID, 'expects frame features first')
+            if ty[1] == STR:
+                return FILTER_KINDS[p[1].text[0]], [p[0].node], VEC, 1           # KeyError on other strings, like param[keyword]
+            need(ty[1] == VEC, 'keyword must be a vector or a type word')
+            return 0, [p[0].node, p[1].node], VEC, 1
+        if tok == 'FilterFrame':                                                 # (feat, keyword) modules.py:398
+            need(ty[0] == VID, 'expects frame features first')
+            if ty[1] == STR:
+                return FILTERFRAME_KINDS[p[1].text[0]], [p[0].node], VID, 1      # 'objects' -> KeyError as in the reference
+            need(ty[1] == VEC, 'keyword must be a vector or a type word')
+            return 0, [p[0].node, p[1].node], VID, 1
+        if tok == 'HasItem':
+            need(ty[0] == VID, 'only frame features are supported (a [hidden] input yields an unusable 0-d tensor in the reference)')
+            return 0, [p[0].node], ATT, 1
+        if tok == 'Localize':                                                    # (feat, keyword) modules.py:194
+            need(ty[0] == VID and ty[1] in (VEC, VEC2), 'expects (frame features, keyword vector(s))')
+            K = 1 if ty[1] == VEC else 2
+            return K - 1, [p[0].node, p[1].node], ATT, K
+        if tok == 'Relate':                                                      # (mode, attn) modules.py:423
+            need(ty[0] == STR and ty[1] == ATT and p[1].K == 1, 'expects (direction word, [T] attention)')
+            return (0 if p[0].text[0] == 'forward' else 1), [p[1].node], ATT, 1
+        if tok == 'Superlative':                                                 # (mode, actions, feat) modules.py:233
+            need(ty[0] == STR and ty[1] in (VEC, VEC2, VID) and ty[2] == VID, 'expects (max|min, actions, frame features)')
+            kind = {VEC: 0, VEC2: 1, VID: 2}[ty[1]]
+            return (1 if p[0].text[0] == 'min' else 0) + 2 * kind, [p[1].node, p[2].node], VEC, 1
+        if tok == 'Temporal':                                                    # (mode, feat, attention) modules.py:310
+            need(ty[0] == STR and ty[1] == VID and ty[2] == ATT, 'expects (mode word, frame features, attention map)')
+            return TEMPORAL_MODES[p[0].text[0]] * 2 + (p[2].K - 1), [p[1].node, p[2].node], VID, 1
+        if tok == 'Array2':
+            need(ty == [VEC, VEC], 'expects two vectors')
+            return 0, [p[0].node, p[1].node], VEC2, 1
+        raise KeyError(tok)
+
+
+_LAYOUT_CACHE = {}
+
+
+def compile_layout(tokens) -> Layout:
+    key = tuple(tokens)
+    lay = _LAYOUT_CACHE.get(key)
+    if lay is None:
+        lay = _LAYOUT_CACHE[key] = Layout(key)
+    return lay
+
+
+def _out_units(op, variant, T):
+    """(arena, units per instance) of a group's outputs."""
+    name = OP_NAME[op]
+    if op == OP_WORD:
+        return 'vec', 1
+    if name in ('And', 'XorFrame'):
+        return ('vec', 1) if variant == 0 else ('att', variant)
+    if name in ('AttnVideo', 'FilterFrame', 'Temporal'):
+        return 'vid', 1
+    if name in ('ExistsFrame', 'HasItem', 'Relate'):
+        return 'att', 1
+    if name == 'Localize':
+        return 'att', variant + 1
+    if name == 'Array2':
+        return 'vec', 2
+    return 'vec', 1
+
+
+HEAD_KIND = {'Equals': 'small', 'Xor': 'small', 'Exists': 'small', 'Filter': 'vec', 'Superlative': 'vec', 'ToAction': 'vec',
+             'FilterFrame': 'ff'}
+
+
+class NMNBatch:
+    """A collated batch (host tensors, optionally pinned) + the device copies made by ``to``.
+
+    Host tensors: ``video`` [B,T,V], ``question`` [n_tok,text], ``itab_host`` (one packed int32 buffer holding q_off,
+    node_gid, node_q, node_arg, node_span, root_node).  Python-side metadata (layouts, node offsets, spans, program
+    index lists) is kept for rebuilding ``res_by_step`` / ``result_of_each_step`` in the reference's format.
+    """
+
+    def __init__(self):
+        self.device = None
+
+    # ---- offsets inside the packed int table
+    def _slices(self):
+        B, n = self.B, self.n_nodes
+        o, out = 0, {}
+        for name, size in (('q_off', B + 1), ('node_gid', n), ('node_q', n), ('node_arg', 3 * n), ('node_span', 2 * n),
+                           ('root_node', B)):
+            out[name] = (o, size)
+            o += (size + 3) // 4 * 4
+        out['_total'] = (0, o)
+        return out
+
+    def to(self, device, non_blocking=True):
+        """Upload (H2D) the batch: 3 copies (video, question, int tables)."""
+        self.device = torch.device(device)
+        if self.device.type == 'cuda' and self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.video_dev = self.video.to(self.device, non_blocking=non_blocking)
+        self.question_dev = self.question.to(self.device, non_blocking=non_blocking)
+        self.itab_dev = self.itab_host.to(self.device, non_blocking=non_blocking)
+        return self
+
+    def h2d_bytes(self):
+        return (self.video.numel() * self.video.element_size() + self.question.numel() * self.question.element_size()
+                + self.itab_host.numel() * 4)
+
+    def tab_ptr(self, name):
+        o, _ = self._slices()[name]
+        return self.itab_dev.data_ptr() + 4 * o
+
+    def host_tab(self, name):
+        o, size = self._slices()[name]
+        return self.itab_host[o:o + size]
+
+
+def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None) -> NMNBatch:
+    """Collate reference-schema ``data`` dicts (video_nmn/dataset.py:189-233) into one ``NMNBatch``.
+
+    Replaces the reference's ``collate_fn = examples[0]`` (video_nmn/dataset.py:463-464).  All questions of a batch
+    must have the same number of frames T.
+    """
+    if isinstance(examples, dict):
+        examples = [examples]
+    B = len(examples)
+    if B == 0:
+        raise ValueError('empty batch')
+    b = NMNBatch()
+    b.B = B
+    b.examples = examples
+    layouts = [compile_layout(e['nmn_program_list']) for e in examples]
+    b.layouts = layouts
+    v0 = examples[0]['video_features']
+    T, V = int(v0.shape[0]), int(v0.shape[1])
+    for e in examples:
+        if tuple(e['video_features'].shape) != (T, V):
+            raise ValueError('all questions of a batch must have the same [T, V] video features; bucket by length '
+                             '(got %s and %s)' % ((T, V), tuple(e['video_features'].shape)))
+    b.T, b.V = T, V
+    vdt = video_dtype or v0.dtype
+    video = torch.empty((B, T, V), dtype=vdt, pin_memory=pin_memory)
+    for i, e in enumerate(examples):
+        video[i].copy_(e['video_features'])
+    b.video = video
+    lens = np.array([int(e['question'].shape[0]) for e in examples], np.int64)
+    q_off = np.zeros(B + 1, np.int64)
+    np.cumsum(lens, out=q_off[1:])
+    b.n_tok, b.L_max = int(q_off[-1]), int(lens.max())
+    text = int(examples[0]['question'].shape[1])
+    qdt = question_dtype or examples[0]['question'].dtype
+    question = torch.empty((b.n_tok, text), dtype=qdt, pin_memory=pin_memory)
+    for i, e in enumerate(examples):
+        question[q_off[i]:q_off[i + 1]].copy_(e['question'])
+    b.question = question
+    b.text_size = text
+
+    sizes = np.array([lay.n for lay in layouts], np.int64)
+    node_start = np.zeros(B + 1, np.int64)
+    np.cumsum(sizes, out=node_start[1:])
+    n = int(node_start[-1])
+    b.n_nodes, b.node_start = n, node_start
+    node_key = np.empty(n, np.int64); node_q = np.empty(n, np.int32)
+    node_arg = np.full((3, n), -1, np.int32); node_span = np.full((2, n), -1, np.int32)
+    root = np.empty(B, np.int32)
+    # vectorised per distinct layout
+    by_layout = {}
+    for qi, lay in enumerate(layouts):
+        by_layout.setdefault(id(lay), (lay, []))[1].append(qi)
+    for lay, qs in by_layout.values():
+        qs = np.asarray(qs, np.int64)
+        starts = node_start[qs]
+        pos = (starts[:, None] + np.arange(lay.n)[None, :]).reshape(-1)
+        node_key[pos] = np.tile(lay.key, len(qs))
+        node_q[pos] = np.repeat(qs, lay.n).astype(np.int32)
+        for k in range(3):
+            a = lay.args[k]
+            glob = np.where(a[None, :] >= 0, a[None, :] + starts[:, None], a[None, :])
+            node_arg[k, pos] = glob.reshape(-1).astype(np.int32)
+        root[qs] = (starts + lay.root).astype(np.int32)
+    # word spans (per question data; module_net.py:128-129).  A missing entry raises KeyError like the reference.
+    for qi, (lay, e) in enumerate(zip(layouts, examples)):
+        if lay.word_nodes:
+            spans = e['prog_str_to_question_tokens']
+            base = node_start[qi]
+            for nd in lay.word_nodes:
+                s, t = spans[lay.token_of_node[nd]]
+                if s is None and t is None:
+                    s, t = -1, -1
+                elif s is None or t is None or s < 0 or t < 0:
+                    Lq = int(lens[qi])                            # python slice semantics of token_feature[s:t]
+                    s, t, _ = slice(s, t).indices(Lq)
+                node_span[0, base + nd], node_span[1, base + nd] = s, t
+    keys = np.unique(node_key)
+    gid = np.searchsorted(keys, node_key).astype(np.int32)
+    counts = np.bincount(gid, minlength=len(keys))
+    b.group_keys, b.group_counts = keys, counts
+    b.n_groups = len(keys)
+    b.node_gid_host = gid
+
+    sl = b._slices()
+    itab = torch.empty(sl['_total'][1], dtype=torch.int32, pin_memory=pin_memory)
+    it = itab.numpy()
+    for name, arr in (('q_off', q_off), ('node_gid', gid), ('node_q', node_q), ('node_arg', node_arg.reshape(-1)),
+                      ('node_span', node_span.reshape(-1)), ('root_node', root)):
+        o, size = sl[name]
+        it[o:o + size] = arr
+    b.itab_host = itab
+    b.answer = None
+    if all('answer' in e for e in examples):
+        b.answer = torch.tensor([int(e['answer']) for e in examples], dtype=torch.int64)
+    return b
+
+
+def build_groups(batch: NMNBatch, head_modules=frozenset()):
+    """Group table (host ``StairGroup`` array + the device [4][n_groups] int table) and arena sizes for this batch."""
+    ng = batch.n_groups
+    groups = (L.StairGroup * ng)()
+    tab = np.zeros((4, ng), np.int32)
+    next_free = {'vid': batch.B, 'vec': 0, 'att': 0, 'small': 0, 'hvec': 0, 'ff': 0}
+    off = 0
+    for g in range(ng):
+        key = int(batch.group_keys[g])
+        variant, op, level = key % 8, (key // 8) % 32, key // 256
+        cnt = int(batch.group_counts[g])
+        arena, mult = _out_units(op, variant, batch.T)
+        name = OP_NAME[op]
+        head = 1 if name in head_modules and name in HEAD_KIND else 0
+        aux = -1
+        if name == 'Temporal':                                   # stash of related_attn (modules.py:288,321-325)
+            aux = next_free['att']; next_free['att'] += cnt
+        elif head:
+            hk = {'small': 'small', 'vec': 'hvec', 'ff': 'ff'}[HEAD_KIND[name]]
+            aux = next_free[hk]; next_free[hk] += cnt
+        G = groups[g]
+        G.op, G.variant, G.level, G.count, G.node_off = op, variant, level, cnt, off
+        G.out_base, G.out_mult, G.aux_base, G.head = next_free[arena], mult, aux, head
+        tab[:, g] = (off, G.out_base, mult, aux)
+        next_free[arena] += cnt * mult
+        off += cnt
+    return groups, tab, next_free
+
+
+def host_grouping(batch: NMNBatch):
+    """Reference grouping computed on the host with numpy (stable argsort) — used by the tests to check the device
+    counting sort bit-exactly."""
+    perm = np.argsort(batch.node_gid_host, kind='stable').astype(np.int32)
+    return perm

@@ -1,0 +1,248 @@
+"""Parameter tree of the drop-in ``VideoNMN`` and its packing into the C-ABI weight table.
+
+The tree reproduces the reference ``state_dict`` exactly (119 keys such as
+``submodules.Localize.video_linear.{0,3}.weight``, ``submodules.Temporal.relate.before.{0,2,4}.*``,
+``submodules.video_encoder.weight_ih_l0_reverse``), so ``load_state_dict`` (evaluate.py:139) and pickled-module
+loading (train_module.py:296-298) work unchanged.  It is built from a compact spec instead of one class per module:
+the torch layers here are *parameter holders with the reference's default initialisation* — their ``forward`` is
+never used; all arithmetic runs in the CUDA library (csrc/).
+
+Reference for the layer shapes: video_nmn/modules.py:15-443 and video_nmn/module_net.py:39-53.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+
+class L2Normalize(nn.Module):
+    """``contrastive_head`` (video_nmn/module_net.py:211-216): x / max(|x|_2, 1e-12) over dim 0."""
+
+    def forward(self, feat):
+        L.require_cuda(feat, 'feat')
+        x = feat.detach().contiguous()
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        L.check(L.lib().stair_l2normalize(L.i32(L.dtype_code(x.dtype)), L.ptr(x), L.ptr(out), L.i32(1), L.i32(x.numel()),
+                                          L.stream_ptr()), 'stair_l2normalize')
+        return out
+
+
+def _seq(spec, p):
+    """spec: list of ('lin', in, out) | 'relu' | 'drop' | 'sigmoid' | 'softmax' -> nn.Sequential with reference indices."""
+    layers = []
+    for s in spec:
+        if isinstance(s, tuple):
+            layers.append(nn.Linear(s[1], s[2]))
+        elif s == 'relu':
+            layers.append(nn.ReLU())
+        elif s == 'drop':
+            layers.append(nn.Dropout(p))
+        elif s == 'sigmoid':
+            layers.append(nn.Sigmoid())
+        elif s == 'softmax':
+            layers.append(nn.Softmax(dim=None))
+    return nn.Sequential(*layers)
+
+
+class Operator(nn.Module):
+    """Parameter holder for one NMN module type.  Calling it directly is not supported: modules execute batched,
+    grouped by type, inside ``VideoNMN.forward`` (csrc/executor.cu)."""
+
+    def __init__(self, name):
+        super().__init__()
+        self.op_name = name
+
+    def forward(self, *params):
+        raise L.StairError('%s executes inside the batched CUDA interpreter; call VideoNMN.forward' % self.op_name)
+
+
+class TemporalOperator(Operator):
+    """Adds the reference's stateful head: ``pretrain_head()`` returns the related attention stashed by the last
+    forward that executed a Temporal module (video_nmn/modules.py:287-288, 321-325)."""
+
+    def __init__(self):
+        super().__init__('Temporal')
+        self.related_attn = None
+
+    def pretrain_head(self, *args):
+        return self.related_attn
+
+
+def build_submodules(config, contrastive_head):
+    """nn.ModuleDict in NAME_TO_MODULE order + encoders + decoder (module_net.py:27-53)."""
+    H, p, T = config['hidden_size'], config['dropout'], config['max_video_length']
+    head = config['have_pretrain_head']
+    mlp2 = lambda i: [('lin', i, H), 'relu', 'drop', ('lin', H, H), 'relu', 'drop']       # noqa: E731
+    sub = nn.ModuleDict()
+
+    def op(name, **children):
+        m = TemporalOperator() if name == 'Temporal' else Operator(name)
+        for k, v in children.items():
+            if v is not None:
+                setattr(m, k, v)
+        sub[name] = m
+        return m
+
+    op('And')
+    op('AttnVideo')
+    op('Choose')
+    op('Compare', param=_seq([('lin', 2 * H, H), 'relu'], p))
+    op('Equals', param=_seq([('lin', 2 * H, H), 'relu'], p), pretrain_head=nn.Linear(H, 1) if head else None)
+    op('Exists', param=_seq(mlp2(3 * H), p), pretrain_head=nn.Linear(H, 2) if head else None)
+    op('ExistsFrame', pretrain_head=nn.Identity() if head else None)
+    op('Filter', param=nn.ModuleDict({kw: _seq(mlp2(H), p) for kw in ['representation', 'actions', 'objects', 'relations']}),
+       attention=_seq([('lin', 2 * H, 1), 'softmax'], p), dense=_seq([('lin', H, H), 'relu'], p),
+       pretrain_head=contrastive_head if head else None)
+    op('FilterFrame', param=nn.ModuleDict({kw: _seq(mlp2(H), p) for kw in ['representation', 'relations', 'actions']}),
+       attention=_seq([('lin', 2 * H, 1), 'sigmoid'], p), dense=_seq([('lin', H, H), 'relu', 'drop'], p),
+       pretrain_head=nn.Linear(H, config['object_types']) if head else None)
+    op('HasItem', param=_seq([('lin', H, H), 'relu', 'drop', ('lin', H, 1), 'sigmoid', 'drop'], p),
+       pretrain_head=nn.Identity() if head else None)
+    loc = op('Localize', video_linear=_seq([('lin', H, H), 'relu', 'drop', ('lin', H, H)], p),
+             keyword_linear=_seq([('lin', H, H)], p), pretrain_head=nn.Identity() if head else None)
+    rel = op('Relate')
+    rel.beta = nn.Parameter(torch.rand(T))
+    op('Superlative', localize_module=loc, dense=_seq([('lin', H, H), 'relu'], p),
+       pretrain_head=contrastive_head if head else None)
+    if T > 32:                                                   # modules.py:255-266
+        k = round(T / 4)
+        relate = {m: nn.Sequential(nn.Conv1d(1, 1, k, padding='same'), nn.ReLU(), nn.Conv1d(1, 1, k, padding='same'), nn.ReLU(),
+                                   nn.Conv1d(1, 1, 2 * k + 1, padding='same'), nn.Sigmoid()) for m in ['before', 'after', 'between']}
+    else:                                                        # modules.py:267-277
+        relate = {m: _seq([('lin', T, T), 'relu', ('lin', T, T), 'relu', ('lin', T, T), 'sigmoid'], p)
+                  for m in ['before', 'after', 'between']}
+    relate = nn.ModuleDict(relate)
+    relate['while'] = nn.Identity()
+    op('Temporal', relate=relate, dense=_seq([('lin', H, H), 'relu', 'drop'], p), layer_norm=nn.LayerNorm(H))
+    op('ToAction', param=_seq([('lin', 2 * H, H), 'relu', 'drop', ('lin', H, H), 'relu'], p),
+       pretrain_head=contrastive_head if head else None)
+    op('Xor', param=_seq([('lin', 3 * H, H), 'relu'], p), pretrain_head=nn.Linear(H, 2) if head else None)
+    op('XorFrame')
+    sub['Array2'] = Operator('Array2')
+    sub['video_encoder'] = nn.LSTM(input_size=config['video_size'], hidden_size=H // 2, batch_first=True, bidirectional=True)
+    sub['text_encoder'] = nn.LSTM(input_size=config['text_size'], hidden_size=H // 2, batch_first=True, bidirectional=True)
+    sub['decoder'] = _seq([('lin', 2 * H, 2 * H), 'relu', 'drop', ('lin', 2 * H, config['answer_vocab_length'])], p)
+    return sub
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# packing: state_dict tensors -> the StairWeight table (include/stair_b200.h)
+# ---------------------------------------------------------------------------------------------------------------------
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def _matrix(w, nplanes):
+    """fp32 [N,K] -> bf16 [nplanes][N, K_ld] (K zero-padded to a multiple of 8; 3 planes = exact bf16x3 split)."""
+    N, K = w.shape
+    ld = _pad8(K)
+    x = torch.zeros((N, ld), device=w.device, dtype=torch.float32)
+    x[:, :K] = w.detach().float()
+    if nplanes == 1:
+        return x.to(torch.bfloat16).contiguous()
+    p0 = x.to(torch.bfloat16)
+    r = x - p0.float()
+    p1 = r.to(torch.bfloat16)
+    r = r - p1.float()
+    return torch.stack([p0, p1, r.to(torch.bfloat16)]).contiguous()
+
+
+def _vector(v):
+    return v.detach().float().contiguous().reshape(-1)
+
+
+def weight_sources(sub, config):
+    """{STAIR_W_* name: (kind, callable -> fp32 tensor)}; kind 'M' = GEMM matrix (bf16 planes), 'V' = fp32 vector."""
+    s = {}
+
+    def lin(prefix, layer, mat='M'):
+        s[prefix + '_W'] = (mat, lambda: layer.weight)
+        s[prefix + '_B'] = ('V', lambda: layer.bias)
+
+    def lstm(prefix, m):
+        s[prefix + '_WIH'] = ('M', lambda: torch.cat([m.weight_ih_l0, m.weight_ih_l0_reverse], 0))
+        s[prefix + '_B'] = ('V', lambda: torch.cat([m.bias_ih_l0 + m.bias_hh_l0, m.bias_ih_l0_reverse + m.bias_hh_l0_reverse]))
+        s[prefix + '_WHH_F'] = ('M', lambda: m.weight_hh_l0)
+        s[prefix + '_WHH_R'] = ('M', lambda: m.weight_hh_l0_reverse)
+
+    def mlp4(prefix, seq):                      # 4 consecutive slots w0,b0,w1,b1 (Sequential indices 0 and 3)
+        base = L.W[prefix]
+        for j, (kind, layer, attr) in enumerate((('M', seq[0], 'weight'), ('V', seq[0], 'bias'), ('M', seq[3], 'weight'), ('V', seq[3], 'bias'))):
+            s[base + j] = (kind, (lambda l=layer, a=attr: getattr(l, a)))
+
+    lstm('VENC', sub['video_encoder'])
+    lstm('TENC', sub['text_encoder'])
+    lin('DEC0', sub['decoder'][0]); lin('DEC1', sub['decoder'][3])
+    loc = sub['Localize']
+    lin('LOC_V0', loc.video_linear[0]); lin('LOC_V1', loc.video_linear[3]); lin('LOC_K', loc.keyword_linear[0])
+    tmp = sub['Temporal']
+    lin('TEMP_D', tmp.dense[0])
+    s['TEMP_LN_G'] = ('V', lambda: tmp.layer_norm.weight)
+    s['TEMP_LN_B'] = ('V', lambda: tmp.layer_norm.bias)
+    for mode in ('BEFORE', 'AFTER', 'BETWEEN'):
+        seq = tmp.relate[mode.lower()]
+        base = L.W['TEMP_REL_' + mode]
+        for j, layer in enumerate((seq[0], seq[2], seq[4])):
+            s[base + 2 * j] = ('V', (lambda l=layer: l.weight))
+            s[base + 2 * j + 1] = ('V', (lambda l=layer: l.bias))
+    flt = sub['Filter']
+    for kind, slot in (('representation', 'FILT_REPR'), ('actions', 'FILT_ACTIONS'), ('objects', 'FILT_OBJECTS'), ('relations', 'FILT_RELATIONS')):
+        mlp4(slot, flt.param[kind])
+    lin('FILT_D', flt.dense[0])
+    ff = sub['FilterFrame']
+    for kind, slot in (('representation', 'FF_REPR'), ('relations', 'FF_RELATIONS'), ('actions', 'FF_ACTIONS')):
+        mlp4(slot, ff.param[kind])
+    lin('FF_ATT', ff.attention[0], mat='V')
+    lin('FF_D', ff.dense[0])
+    if config['have_pretrain_head']:
+        lin('FF_HEAD', ff.pretrain_head)
+        lin('EQUALS_HEAD', sub['Equals'].pretrain_head, mat='V')
+        lin('XOR_HEAD', sub['Xor'].pretrain_head, mat='V')
+        lin('EXISTS_HEAD', sub['Exists'].pretrain_head, mat='V')
+    has = sub['HasItem']
+    lin('HAS0', has.param[0]); lin('HAS1', has.param[3], mat='V')
+    s['REL_BETA'] = ('V', lambda: sub['Relate'].beta)
+    lin('SUP_D', sub['Superlative'].dense[0])
+    lin('COMPARE', sub['Compare'].param[0])
+    lin('EQUALS', sub['Equals'].param[0])
+    lin('XOR', sub['Xor'].param[0])
+    lin('EXISTS0', sub['Exists'].param[0]); lin('EXISTS1', sub['Exists'].param[3])
+    lin('TOACT0', sub['ToAction'].param[0]); lin('TOACT1', sub['ToAction'].param[3])
+    return {(L.W[k] if isinstance(k, str) else k): v for k, v in s.items()}
+
+
+class PackedWeights:
+    """Device copies of the weights in the layout the kernels read, rebuilt when a parameter changes."""
+
+    def __init__(self):
+        self.signature = None
+        self.tensors = {}
+        self.model_struct = None
+
+    def refresh(self, sub, config, precision, device):
+        params = [p for p in sub.parameters()]
+        sig = (precision, str(device)) + tuple((p.data_ptr(), p._version) for p in params)
+        if sig == self.signature:
+            return self.model_struct
+        nplanes = 3 if precision == L.F32 else 1
+        srcs = weight_sources(sub, config)
+        tensors = {}
+        with torch.no_grad():
+            for wid, (kind, get) in srcs.items():
+                w = get()
+                if w.device != device:
+                    raise L.StairError('model parameters live on %s but the batch is on %s; call model.to(device)' % (w.device, device))
+                tensors[wid] = _matrix(w.reshape(w.shape[0], -1), nplanes) if kind == 'M' else _vector(w)
+        m = L.StairModel()
+        T = config['max_video_length']
+        m.T_max, m.V, m.V_ld, m.H = T, config['video_size'], _pad8(config['video_size']), config['hidden_size']
+        m.text_size, m.text_ld = config['text_size'], _pad8(config['text_size'])
+        m.A, m.O = config['answer_vocab_length'], config.get('object_types', 0) or 0
+        m.conv_k = round(T / 4) if T > 32 else 0
+        m.precision = precision
+        for wid in range(L.W_COUNT):
+            m.w[wid] = tensors[wid].data_ptr() if wid in tensors else None
+        self.tensors, self.model_struct, self.signature = tensors, m, sig
+        return m

@@ -1,0 +1,155 @@
+"""GPU parity of the batched CUDA forward (through the C ABI) against the committed golden fixtures produced by the
+unmodified reference, and against the CPU oracle on fresh seeded inputs.
+
+Bars (north star): layout grouping, argmax answers and attention argmax indices bit-exact; floating-point maps /
+logits within a stated tolerance:
+  * precision='fp32' (strict: fp32 storage, bf16x3 split contractions, fp32 accumulate): rtol 2e-4, atol 2e-5
+  * precision='bf16' (fast path: bf16 storage, fp32 accumulate): |err| <= 3e-2 * max|ref| + 2e-3 per tensor
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nmn_oracle as orc
+from stair_b200 import VideoNMN, collate, synthetic as syn
+from stair_b200 import layout as LY
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+STRICT = dict(rtol=2e-4, atol=2e-5)
+BF16_REL, BF16_ABS = 3e-2, 2e-3
+
+
+def _close(got, want, precision, what):
+    got = got.detach().float().cpu()
+    want = want.detach().float().cpu()
+    assert got.shape == want.shape, '%s: shape %s vs %s' % (what, tuple(got.shape), tuple(want.shape))
+    if precision == 'fp32':
+        torch.testing.assert_close(got, want, msg=lambda m: '%s: %s' % (what, m), **STRICT)
+    else:
+        scale = max(float(want.abs().max()), 1e-3)
+        err = float((got - want).abs().max())
+        assert err <= BF16_REL * scale + BF16_ABS, '%s: max err %g vs scale %g' % (what, err, scale)
+
+
+def _margin_ok(t, dim=-1):
+    """top-2 margin of a reference tensor along dim (argmax comparisons are only meaningful above the tolerance)."""
+    if t.size(dim) < 2:
+        return torch.ones(t.shape[:-1], dtype=torch.bool)
+    top = t.float().topk(2, dim=dim).values
+    return (top[..., 0] - top[..., 1]) > 2 * (BF16_REL * max(float(t.abs().max()), 1e-3) + BF16_ABS)
+
+
+def _model(cfg, weights, pretrain, precision):
+    m = VideoNMN(cfg, pretrain_modules=set(pretrain), precision=precision)
+    m.load_state_dict(weights)
+    return m.cuda().eval()
+
+
+@pytest.fixture(scope='module', params=['rx_small', 'i3d_small'])
+def fx(request):
+    return gu.load(request.param)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_golden_every_intermediate(fx, precision):
+    cfg, weights, questions, meta, _ = fx
+    model = _model(cfg, weights, meta['pretrain_modules'], precision)
+    datas = [d for d, _, _ in questions]
+    out = model(datas, return_res_by_step=True, return_result_of_each_step=True)
+    torch.cuda.synchronize()
+    T = cfg['max_video_length']
+    for qi, (data, ref, q) in enumerate(questions):
+        name = q['template']
+        _close(out['logits'][qi], ref['logits'], precision, '%s logits' % name)
+        if precision == 'fp32' or bool(_margin_ok(ref['logits'])):
+            assert int(out['answers'][qi]) == int(ref['logits'].argmax()), '%s answer' % name
+        steps = out['result_of_each_step'][qi]
+        assert len(steps) == len(ref['steps'])
+        for j, ((_, got), want) in enumerate(zip(steps, ref['steps'])):
+            if isinstance(want, str):
+                assert got == want
+                continue
+            _close(got, want, precision, '%s step %d (%s)' % (name, j, data['nmn_program_list'][j]))
+            if want.dim() >= 1 and want.size(-1) == T and want.numel() <= 2 * T:       # attention maps: argmax index
+                ok = _margin_ok(want) if precision == 'bf16' else torch.ones(want.shape[:-1], dtype=torch.bool)
+                g, w = got.float().cpu().argmax(-1), want.argmax(-1)
+                assert torch.equal(g[ok], w[ok]), '%s step %d attention argmax' % (name, j)
+        assert set(out['res_by_step'][qi]) == set(ref['res_by_step'])
+        for k, (mname, t) in ref['res_by_step'].items():
+            assert out['res_by_step'][qi][k][0] == mname
+            _close(out['res_by_step'][qi][k][1], t, precision, '%s res_by_step[%d] %s' % (name, k, mname))
+        for k, reps in ref['gold_reps'].items():
+            for (n1, t1), (n2, t2) in zip(reps, out['sg_res_by_step'][qi][k]):
+                assert n1 == n2
+                _close(t2, t1, precision, '%s gold rep %s' % (name, n1))
+
+
+def test_single_question_keeps_reference_shapes(fx):
+    cfg, weights, questions, meta, _ = fx
+    model = _model(cfg, weights, meta['pretrain_modules'], 'fp32')
+    data, ref, q = questions[0]
+    out = model(data, return_res_by_step=True, test_mode=True)
+    assert out['logits'].shape == ref['logits'].shape
+    assert 'sg_res_by_step' not in out
+    _close(out['logits'], ref['logits'], 'fp32', 'logits')
+    assert isinstance(out['res_by_step'], dict) and set(out['res_by_step']) == set(ref['res_by_step'])
+
+
+def test_device_grouping_is_bit_exact(fx):
+    """perm / group offsets computed by the device counting sort == numpy stable argsort on the host."""
+    cfg, weights, questions, meta, _ = fx
+    model = _model(cfg, weights, meta['pretrain_modules'], 'bf16')
+    datas = [d for d, _, _ in questions] * 40                    # > 1 chunk of 1024 nodes
+    rng = np.random.default_rng(0)
+    rng.shuffle(datas)
+    batch = collate(datas).to('cuda')
+    st = model.forward_batch(batch)
+    torch.cuda.synchronize()
+    model.check_status(st)
+    il = st.itab_layout
+    itab = st.itab.cpu().numpy()
+    n, ng = batch.n_nodes, batch.n_groups
+    perm = itab[il.perm:il.perm + n]
+    assert np.array_equal(perm, LY.host_grouping(batch))
+    off = itab[il.group_off:il.group_off + ng + 1]
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(batch.group_counts)]))
+    # levels/children used for the grouping agree with the oracle's restatement of program_parser.py
+    for d in datas[:14]:
+        lay = LY.compile_layout(d['nmn_program_list'])
+        lv = orc.module_levels(d['nmn_program_list'])
+        for nd in range(lay.n):
+            assert lay.level[nd] == lv[lay.token_of_node[nd]]
+
+
+@pytest.mark.parametrize('shape', ['rx', 'i3d'])
+def test_full_size_against_oracle(shape):
+    """Config-1 sized check at the real dimensions (H=512): 24 questions over all 14 layouts vs the CPU oracle."""
+    T, V = (8, 4096) if shape == 'rx' else (64, 1024)
+    cfg = syn.model_config(T=T, V=V)
+    torch.manual_seed(0)
+    ref_model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
+    weights = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
+    oracle = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES)
+    qs = syn.make_questions(24, T, V, seed=99, templates=list(syn.ALL_TEMPLATES))
+    with torch.no_grad():
+        want = [oracle(d, return_res_by_step=False, return_result_of_each_step=True, test_mode=True) for d in qs]
+    for precision in ('fp32', 'bf16'):
+        model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision=precision)
+        model.load_state_dict(weights)
+        model = model.cuda().eval()
+        out = model(qs, return_res_by_step=False, return_result_of_each_step=True, test_mode=True)
+        torch.cuda.synchronize()
+        n_checked = 0
+        for qi, w in enumerate(want):
+            _close(out['logits'][qi], w['logits'], precision, 'q%d logits' % qi)
+            if precision == 'fp32' or bool(_margin_ok(w['logits'])):
+                assert int(out['answers'][qi]) == int(w['logits'].argmax())
+                n_checked += 1
+            for j, ((_, got), (_, exp)) in enumerate(zip(out['result_of_each_step'][qi], w['result_of_each_step'])):
+                if isinstance(exp, str):
+                    assert got == exp
+                else:
+                    _close(got, exp, precision, 'q%d step %d %s' % (qi, j, qs[qi]['nmn_program_list'][j]))
+        assert n_checked >= (24 if precision == 'fp32' else 1)

@@ -91,3 +91,31 @@ def test_gemm_split3_is_fp32_grade():
         ref = (A.double() @ W.double().t()).float()
         err = (out - ref).abs().max().item()
         assert err < 2e-5 * ref.abs().max().item() + 1e-6, 'impl %d err %g' % (impl, err)
+
+
+def test_gemm_small_k():
+    """K < one 64-wide TMA box (LSTM recurrent projection of the H=64 fixtures: K = 32)."""
+    M, N, K = 300, 128, 32
+    g = torch.Generator(device='cuda').manual_seed(3)
+    A = torch.randn(M, K, device='cuda', generator=g).bfloat16()
+    W = torch.randn(N, K, device='cuda', generator=g).bfloat16()
+    out = L.gemm(A, W, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert (out - A.float() @ W.float().t()).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize('T', [8, 16, 64, 128])
+@pytest.mark.parametrize('H', [64, 512])
+def test_gemm_slot_gather(T, H):
+    """A rows gathered from a [slots, T, H] arena by TMA 3-D boxes == gather-then-GEMM."""
+    slots, n, N = 97, 211, 192
+    g = torch.Generator(device='cuda').manual_seed(T + H)
+    arena = torch.randn(slots, T, H, device='cuda', generator=g).bfloat16()
+    idx = torch.randint(0, slots, (n,), device='cuda', generator=g, dtype=torch.int32)
+    W = (torch.randn(N, H, device='cuda', generator=g) * H ** -0.5).bfloat16()
+    bias = torch.randn(N, device='cuda', generator=g)
+    rs = torch.rand(n * T, device='cuda', generator=g)
+    out = L.gemm_gather(arena, idx, T, W, bias=bias, out_dtype=torch.float32, act=L.ACT_RELU, row_scale=rs)
+    torch.cuda.synchronize()
+    ref = torch.relu((arena[idx.long()].reshape(n * T, H).float() @ W.float().t()) * rs[:, None] + bias)
+    assert (out - ref).abs().max().item() < 2e-3
