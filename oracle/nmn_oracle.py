@@ -148,7 +148,12 @@ class OracleNMN:
     (module_net.py:31-32) and is read from the ``Localize`` keys.
     """
 
-    def __init__(self, config: dict, weights: Dict[str, torch.Tensor], pretrain_modules=frozenset()):
+    def __init__(self, config: dict, weights: Dict[str, torch.Tensor], pretrain_modules=frozenset(), aten_lstm=False):
+        """``aten_lstm=True`` runs the two encoders through ``torch.nn.LSTM`` itself — the very ATen call the reference
+        makes (module_net.py:39-47,151-163; mkldnn/cuDNN kernels) — instead of the explicit per-step restatement.  Used by
+        the CPU-baseline timer so the baseline is not handicapped by a Python time loop; tested equal to the loop."""
+        self.aten_lstm = aten_lstm
+        self._lstm_cache = {}
         self.config = config
         self.W = weights
         self.pretrain_modules = set(pretrain_modules)
@@ -161,6 +166,17 @@ class OracleNMN:
 
     # ---- encoders (module_net.py:147-163) ---------------------------------------------------------
     def _bilstm(self, name, x):
+        if self.aten_lstm:
+            m = self._lstm_cache.get(name)
+            if m is None:
+                m = torch.nn.LSTM(input_size=x.size(1), hidden_size=self.p(name + '.weight_hh_l0').size(1), batch_first=True,
+                                  bidirectional=True)
+                with torch.no_grad():
+                    for k, v in m.named_parameters():
+                        v.copy_(self.p(name + '.' + k))
+                self._lstm_cache[name] = m
+            out, (hn, _) = m(x.unsqueeze(0))
+            return out[0], hn[:, 0, :].reshape(-1)
         f, hf = _lstm_dir(x, self.p(name + '.weight_ih_l0'), self.p(name + '.weight_hh_l0'),
                           self.p(name + '.bias_ih_l0'), self.p(name + '.bias_hh_l0'), False)
         b, hb = _lstm_dir(x, self.p(name + '.weight_ih_l0_reverse'), self.p(name + '.weight_hh_l0_reverse'),

@@ -39,6 +39,7 @@ struct GemmParams {
     int slot_rows;         // rows per slot (divides BM)
     int num_slots;         // ceil(M / slot_rows)
     int* err_flag;
+    unsigned long long* dbg;   // debug timeline of block 0 (globaltimer ns), null in production
 };
 
 // plane pairs (a,b) of the 6-term bf16x3 product, smallest contributions first
@@ -96,6 +97,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+__device__ __forceinline__ void dbg_stamp(const GemmParams& p, int slot) {
+    if (p.dbg && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.dbg[slot] = t;
+    }
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -213,6 +221,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) dbg_stamp(p, 0);
     const int tiles_n = (p.N + BN - 1) / BN;
     const int tiles_m = (p.M + BM - 1) / BM;
     const int total_tiles = tiles_m * tiles_n;
@@ -233,6 +242,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (threadIdx.x == 0) dbg_stamp(p, 1);
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp: in gather mode lane j loads slot j of the tile) ==========
@@ -278,6 +288,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int it = 0; it < kiters; ++it) {
                     mbar_wait(&full_bar[stage], phase, p.err_flag, 103);
                     tcgen05_fence_after();
+                    if (it == 0 && tile == blockIdx.x) dbg_stamp(p, 2);
                     const uint64_t adesc = make_umma_desc_kmajor_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
                     const uint64_t bdesc = make_umma_desc_kmajor_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
 #pragma unroll
@@ -300,6 +311,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 104);
             tcgen05_fence_after();
+            if (threadIdx.x == 128 && tile == blockIdx.x) dbg_stamp(p, 3);
             const int row = m0 + quarter * 32 + lane;
             const uint32_t t_base = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
@@ -315,8 +327,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
+    if (threadIdx.x == 128) dbg_stamp(p, 4);
     tcgen05_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) dbg_stamp(p, 5);
     if (warp == 2) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -406,6 +420,7 @@ static int make_tmap_bf16_slots(CUtensorMap* tm, const void* base, uint64_t cols
 static int g_gemm_impl = 0;      // 0 = tcgen05 (product), 1 = SIMT debug kernel
 static int* g_err_flag = nullptr;
 static int g_num_sms = 0;
+static unsigned long long* g_dbg = nullptr;
 
 static int* err_flag_ptr() {
     if (!g_err_flag) {
@@ -449,6 +464,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     p.vec_ok = ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.ldc * esz) % 16 == 0) ? 1 : 0;
     p.a_slots = a.a_slots; p.slot_rows = gather ? a.slot_rows : BM; p.num_slots = gather ? a.M / a.slot_rows : 0;
     p.err_flag = err_flag_ptr();
+    p.dbg = g_dbg;
 
     if (g_gemm_impl == 1 && !gather) {
         dim3 grid(ceil_div(a.N, 16), ceil_div(a.M, 16)), block(16, 16);
@@ -481,6 +497,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
 using namespace stair;
 
 extern "C" int stair_set_gemm_impl(int impl) { g_gemm_impl = impl; return STAIR_OK; }
+extern "C" int stair_gemm_debug_timeline(unsigned long long* dev_buf) { g_dbg = dev_buf; return STAIR_OK; }
 extern "C" int stair_get_gemm_impl() { return g_gemm_impl; }
 extern "C" int stair_gemm_error_flag() { return g_err_flag ? *g_err_flag : 0; }
 

@@ -1,0 +1,62 @@
+"""Question sharding across the GPUs of one box.
+
+Questions are independent in the forward (video_nmn/module_net.py:65-145 has no cross-question op), so the batch is
+split into contiguous slices, one per rank; weights are replicated; every rank groups and executes its own slice.  The
+only data-path collective of inference is the all-gather of the int32 answers (4 B/question), plus optionally the fp32
+logits.  One process per GPU, ``torch.distributed`` (NCCL over NVLink/NVSwitch; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous slice [lo, hi) of ``n`` questions owned by ``rank``; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard(items, rank=None, world=None):
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    lo, hi = shard_bounds(len(items), rank, world)
+    return items[lo:hi]
+
+
+def all_gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Concatenate per-rank row blocks (sizes given by ``shard_bounds``) into the full [n_total, ...] tensor on every
+    rank.  Ragged slices are padded to the largest slice for the collective and trimmed afterwards."""
+    world = dist.get_world_size(group)
+    sizes = [shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0] for r in range(world)]
+    mx = max(sizes)
+    if local.shape[0] != sizes[dist.get_rank(group)]:
+        raise ValueError('local block has %d rows, expected %d' % (local.shape[0], sizes[dist.get_rank(group)]))
+    pad = local
+    if local.shape[0] < mx:
+        pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+    out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    if all(s == mx for s in sizes):
+        return out
+    return torch.cat([out[r * mx:r * mx + sizes[r]] for r in range(world)])
+
+
+class ShardedNMN:
+    """Batch-sharded inference: ``model`` is a (replicated) ``stair_b200.VideoNMN`` on this rank's GPU."""
+
+    def __init__(self, model, group=None):
+        self.model, self.group = model, group
+
+    @torch.no_grad()
+    def answer(self, questions, gather_logits=False):
+        """questions: the FULL list of data dicts (every rank passes the same list).  Returns (answers [B] int32,
+        logits [B, A] or None) on every rank."""
+        n = len(questions)
+        mine = shard(questions, dist.get_rank(self.group), dist.get_world_size(self.group))
+        out = self.model(mine, return_res_by_step=False, test_mode=True)
+        answers = all_gather_rows(out['answers'], n, self.group)
+        logits = all_gather_rows(out['logits'], n, self.group) if gather_logits else None
+        return answers, logits

@@ -1,0 +1,118 @@
+"""CPU: host layout compiler (stair_b200/layout.py) against the reference's layout helpers recorded in
+tests/golden/layouts.json (parse_program / get_childrens_and_parents / stat_module_levels / program_is_valid outputs of the
+unmodified reference) and against the oracle restatement."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nmn_oracle as orc
+from stair_b200 import layout as LY, synthetic as syn
+from tests import golden_util as gu
+
+LAY = json.load(open(os.path.join(gu.GOLDEN_DIR, 'layouts.json')))
+
+
+def test_arity_table_matches_reference():
+    assert dict(LY.NARY) == LAY['nary']
+
+
+@pytest.mark.parametrize('name', sorted(LAY['templates']))
+def test_children_levels_validity(name):
+    t = LAY['templates'][name]
+    ch, pa = LY.children_and_parents(t['tokens'])
+    assert ch == t['children'] and pa == t['parents']
+    assert LY.module_levels(t['tokens']) == t['levels']
+    assert LY.program_is_valid(t['tokens']) == t['valid']
+
+
+def test_invalid_programs():
+    for prog, res in zip(LAY['invalid'], LAY['invalid_results']):
+        assert LY.program_is_valid(prog) == res
+
+
+@pytest.mark.parametrize('name', sorted(syn.ALL_TEMPLATES))
+def test_compiled_layout_is_consistent_with_reference_tree(name):
+    tokens = syn.ALL_TEMPLATES[name][1]
+    lay = LY.compile_layout(tokens)
+    ch, _ = orc.children_and_parents(tokens)
+    lv = orc.module_levels(tokens)
+    for nd in range(lay.n):
+        i = lay.token_of_node[nd]
+        assert lay.level[nd] == lv[i]
+        if tokens[i] in LY.OP_OF:
+            assert lay.op[nd] == LY.OP_OF[tokens[i]]
+            assert lay.param_tokens[i] == ch[i]                       # same children, same (pop) order
+            tensor_children = [c for c in ch[i] if tokens[c] == 'video' or lay.node_of_token[c] >= 0]
+            args = [a for a in lay.args[:, nd] if a != -1]
+            want = [-2 if tokens[c] == 'video' else lay.node_of_token[c] for c in tensor_children]
+            assert list(args) == want
+    assert lay.token_of_node[lay.root] == 0
+
+
+def test_interpreter_errors_mirror_reference():
+    with pytest.raises(IndexError):                                   # stack.pop() on an empty stack, module_net.py:102
+        LY.Layout(['Exists', 'table'])
+    with pytest.raises(AssertionError):                               # assert len(stack) == 1, module_net.py:135
+        LY.Layout(['table', 'Filter', 'video', 'objects'])
+    with pytest.raises(KeyError):                                     # FilterFrame has no 'objects' branch, modules.py:384
+        LY.Layout(['Filter', 'FilterFrame', 'video', 'objects', 'objects'])
+
+
+def test_collate_tables_and_grouping():
+    qs = syn.make_questions(64, 8, 32, seed=3, templates=list(syn.ALL_TEMPLATES))
+    b = LY.collate(qs)
+    assert b.B == 64 and b.n_nodes == sum(LY.compile_layout(q['nmn_program_list']).n for q in qs)
+    assert b.video.shape == (64, 8, 32) and b.question.shape[0] == b.n_tok
+    q_off = b.host_tab('q_off').numpy()
+    assert q_off[0] == 0 and q_off[-1] == b.n_tok and np.all(np.diff(q_off) == [q['question'].shape[0] for q in qs])
+    gid = b.host_tab('node_gid').numpy()
+    assert np.array_equal(np.bincount(gid, minlength=b.n_groups), b.group_counts)
+    node_q = b.host_tab('node_q').numpy()
+    node_arg = b.host_tab('node_arg').numpy().reshape(3, -1)
+    for k in range(3):                                                # argument edges stay inside the question
+        m = node_arg[k] >= 0
+        assert np.array_equal(node_q[node_arg[k][m]], node_q[m])
+    # children are always scheduled in an earlier group than their parent (level-synchronous execution is valid)
+    for k in range(3):
+        m = node_arg[k] >= 0
+        assert np.all(gid[node_arg[k][m]] < gid[m])
+    groups, tab, sizes = LY.build_groups(b, frozenset(syn.PRETRAIN_MODULES))
+    assert sum(g.count for g in groups) == b.n_nodes
+    assert [g.node_off for g in groups] == list(np.concatenate([[0], np.cumsum(b.group_counts)[:-1]]))
+    assert [g.level for g in groups] == sorted(g.level for g in groups)
+    # spans: every content word got its (start, end); None span = whole question
+    qs[0]['prog_str_to_question_tokens'] = {k: (None, None) for k in qs[0]['prog_str_to_question_tokens']}
+    b2 = LY.collate(qs[:1])
+    span = b2.host_tab('node_span').numpy().reshape(2, -1)
+    lay = b2.layouts[0]
+    assert all(span[0, nd] == -1 for nd in lay.word_nodes)
+    del qs[1]['prog_str_to_question_tokens'][next(iter(qs[1]['prog_str_to_question_tokens']))]
+    with pytest.raises(KeyError):                                     # module_net.py:128 KeyError on a missing span
+        LY.collate(qs[1:2])
+
+
+def test_state_dict_matches_reference_keys_and_shapes():
+    from stair_b200 import VideoNMN
+    for fixture in ('rx_small', 'i3d_small'):
+        cfg, weights, _, meta, _ = gu.load(fixture)
+        m = VideoNMN(cfg, pretrain_modules=set(meta['pretrain_modules']))
+        sd = m.state_dict()
+        assert set(sd) == set(weights)
+        for k, v in weights.items():
+            assert tuple(sd[k].shape) == tuple(v.shape), k
+        m.load_state_dict(weights)
+        # Superlative shares the Localize module (module_net.py:31-32)
+        assert m.submodules['Superlative'].localize_module is m.submodules['Localize']
+
+
+def test_product_path_fails_loudly_without_cuda():
+    from stair_b200 import VideoNMN, _lib
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    cfg, weights, questions, meta, _ = gu.load('rx_small')
+    m = VideoNMN(cfg)
+    with pytest.raises(_lib.StairError):
+        m(questions[0][0])

@@ -104,3 +104,16 @@ def test_relate_scan_matches_reference_formula():
     want = torch.max(torch.min(torch.cumsum(torch.relu(a), 0), torch.cumsum(torch.relu(a).flip(0), 0).flip(0)),
                      torch.min(torch.cumsum(b, 0), torch.cumsum(b.flip(0), 0).flip(0)))
     torch.testing.assert_close(got, want)
+
+
+def test_aten_lstm_variant_equals_loop(fx):
+    """The CPU-baseline variant (encoders through torch.nn.LSTM, the reference's own call) == the explicit restatement."""
+    cfg, weights, questions, meta, _ = fx
+    a = orc.OracleNMN(cfg, weights, meta['pretrain_modules'])
+    b = orc.OracleNMN(cfg, weights, meta['pretrain_modules'], aten_lstm=True)
+    for data, ref, _ in questions[:4]:
+        with torch.no_grad():
+            la = a(data, return_res_by_step=False, test_mode=True)['logits']
+            lb = b(data, return_res_by_step=False, test_mode=True)['logits']
+        torch.testing.assert_close(la, lb, **TOL)
+        torch.testing.assert_close(lb, ref['logits'], **TOL)

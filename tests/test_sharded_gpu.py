@@ -1,0 +1,53 @@
+"""GPU (>= 2 devices): question-sharded inference over NCCL == unsharded inference, answers bit-identical."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from stair_b200 import VideoNMN, synthetic as syn
+    from stair_b200.distributed import ShardedNMN
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        cfg = syn.model_config(T=8, V=256, hidden=128)
+        torch.manual_seed(0)
+        model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().eval()
+        qs = syn.make_questions(101, 8, 256, seed=5, templates=list(syn.ALL_TEMPLATES))
+        ans, logits = ShardedNMN(model).answer(qs, gather_logits=True)
+        full = model(qs, return_res_by_step=False, test_mode=True)
+        torch.cuda.synchronize()
+        ok = torch.equal(ans, full['answers']) and torch.equal(logits, full['logits'])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_equals_unsharded():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
