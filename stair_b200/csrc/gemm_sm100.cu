@@ -35,6 +35,7 @@ struct GemmParams {
     void* C;
     long long ldc;
     int out_dtype, act, accumulate, vec_ok;
+    int tma_store;         // epilogue stages tiles in shared memory and writes them with TMA (C aligned, no accumulate)
     const int* a_slots;    // gather mode (else null)
     int slot_rows;         // rows per slot (divides BM)
     int num_slots;         // ceil(M / slot_rows)
@@ -147,12 +148,75 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ---- epilogue helpers: swizzled staging + TMA store -------------------------------------------------
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// act(rs * acc + bias) for one 32-column TMEM chunk of this thread's row
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, int n, float rs, const uint32_t (&raw)[32], float (&v)[32]) {
+    if (p.bias && n + 32 <= p.N) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);     // n is a multiple of 32: 16-byte aligned
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] = fmaf(__uint_as_float(raw[4 * j]), rs, b.x);
+            v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), rs, b.y);
+            v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), rs, b.z);
+            v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), rs, b.w);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(raw[j]) * rs;
+            if (p.bias && n + j < p.N) x += __ldg(p.bias + n + j);
+            v[j] = x;
+        }
+    }
+    if (p.act == STAIR_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+    }
+}
+
+// write this thread's 32 values into the warp's staging buffer (row = lane, 128-byte rows, SWIZZLE_128B chunk order)
+__device__ __forceinline__ void stage_chunk(uint32_t buf, int lane, int half, int out_dtype, const float (&v)[32]) {
+    const uint32_t rowaddr = buf + static_cast<uint32_t>(lane) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    if (out_dtype == STAIR_BF16) {                  // 32 columns = 64 bytes = 16-byte chunks 4*half .. 4*half+3
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t ch = static_cast<uint32_t>(4 * half + c);
+            st_shared_v4(rowaddr + ((ch ^ sw) << 4), pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                         pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+        }
+    } else {                                        // 32 columns = 128 bytes = the whole row
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            st_shared_v4(rowaddr + ((static_cast<uint32_t>(c) ^ sw) << 4), __float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                         __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
+    }
+}
+
 template <int BN, int STAGES>
 struct GemmSmem {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int TILE_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+    static constexpr int STAGING_BYTES = 4 * 2 * 4096;            // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int TOTAL = TILE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
+    static constexpr int TOTAL = TILE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -203,7 +267,8 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     using S = GemmSmem<BN, STAGES>;
     constexpr int B_STAGE_BYTES = S::B_STAGE_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // power of two by construction (BN in {64,128,256})
@@ -214,7 +279,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES);
+    uint8_t* sStage = smem + S::TILE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES + S::STAGING_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -230,6 +296,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -307,6 +374,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ===================== epilogue =====================
         const int quarter = warp - 4;                          // TMEM lanes [32*quarter, 32*quarter+32)
         int acc = 0; uint32_t acc_phase = 0;
+        int sbuf = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 104);
@@ -314,6 +382,48 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (threadIdx.x == 128 && tile == blockIdx.x) dbg_stamp(p, 3);
             const int row = m0 + quarter * 32 + lane;
             const uint32_t t_base = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
+            if (p.tma_store) {
+                // TMEM -> registers (next chunk's tcgen05.ld in flight while this one is processed) -> swizzled smem -> TMA store
+                const float rs = (p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.0f;
+                const uint32_t stage0 = smem_u32(sStage) + static_cast<uint32_t>(quarter) * 8192u;
+                const int per_buf = p.out_dtype == STAIR_BF16 ? 2 : 1;          // TMEM chunks per 128-byte staging row
+                uint32_t ra[32], rb[32];
+                float v[32];
+                tmem_ld32(t_base, ra);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c += 2) {
+                    if (n0 + c * 32 >= p.N) break;                               // warp-uniform
+                    tmem_ld_wait();
+                    tmem_ld32(t_base + static_cast<uint32_t>((c + 1) * 32), rb);
+#pragma unroll
+                    for (int hsel = 0; hsel < 2; ++hsel) {
+                        const int cc = c + hsel;
+                        if (hsel == 1) {
+                            tmem_ld_wait();
+                            if (cc + 1 < BN / 32) tmem_ld32(t_base + static_cast<uint32_t>((cc + 1) * 32), ra);
+                        }
+                        const int n = n0 + cc * 32;
+                        const int half = per_buf == 2 ? hsel : 0;
+                        if (half == 0) {                                         // about to refill a staging buffer: it must be drained
+                            if (lane == 0) bulk_wait_read1();
+                            __syncwarp();
+                        }
+                        const uint32_t buf = stage0 + static_cast<uint32_t>(sbuf) * 4096u;
+                        if (n < p.N) {
+                            epilogue_math(p, n, rs, hsel == 0 ? ra : rb, v);
+                            stage_chunk(buf, lane, half, p.out_dtype, v);
+                        }
+                        if (half == per_buf - 1) {
+                            fence_async_smem();
+                            __syncwarp();
+                            const int nbox = n - (per_buf == 2 ? 32 : 0);
+                            if (lane == 0 && nbox < p.N) { tma_store_2d(&tmC, buf, nbox, m0 + quarter * 32); bulk_commit(); }
+                            sbuf ^= 1;
+                        }
+                    }
+                }
+                tmem_ld_wait();
+            } else {
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 if (n0 + c0 >= p.N) break;                     // warp-uniform
@@ -322,10 +432,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tmem_ld_wait();
                 if (row < p.M) epilogue_store(p, row, n0 + c0, v);
             }
+            }
             tcgen05_fence_before();
             mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.tma_store && lane == 0) bulk_wait_all();         // outstanding TMA stores must land before the CTA exits
     }
     if (threadIdx.x == 128) dbg_stamp(p, 4);
     tcgen05_fence_before();
@@ -417,7 +529,23 @@ static int make_tmap_bf16_slots(CUtensorMap* tm, const void* base, uint64_t cols
     return r == CUDA_SUCCESS ? STAIR_OK : STAIR_ERR_ARG;
 }
 
+// output tile map for the epilogue's TMA stores: box = 32 rows x 128 bytes, SWIZZLE_128B
+static int make_tmap_out(CUtensorMap* tm, const void* base, int out_dtype, uint64_t cols, uint64_t rows, uint64_t row_pitch_elems) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return STAIR_ERR_CUDA;
+    const uint64_t esz = out_dtype == STAIR_BF16 ? 2 : 4;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_pitch_elems * esz};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, out_dtype == STAIR_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? STAIR_OK : STAIR_ERR_ARG;
+}
+
 static int g_gemm_impl = 0;      // 0 = tcgen05 (product), 1 = SIMT debug kernel
+static int g_epilogue_impl = 0;  // 0 = staged TMA-store epilogue, 1 = direct per-row stores (debug / comparison)
 static int* g_err_flag = nullptr;
 static int g_num_sms = 0;
 static unsigned long long* g_dbg = nullptr;
@@ -431,7 +559,7 @@ static int* err_flag_ptr() {
 }
 
 template <int BN, int STAGES>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, cudaStream_t st) {
     using S = GemmSmem<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
@@ -441,7 +569,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     }
     const int tiles = ceil_div(p.M, BM) * ceil_div(p.N, BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, p);
+    gemm_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, tc, p);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -462,6 +590,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     p.accumulate = a.accumulate;
     const int esz = a.out_dtype == STAIR_BF16 ? 2 : 4;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.ldc * esz) % 16 == 0) ? 1 : 0;
+    p.tma_store = (!a.accumulate && p.vec_ok && g_epilogue_impl == 0) ? 1 : 0;
     p.a_slots = a.a_slots; p.slot_rows = gather ? a.slot_rows : BM; p.num_slots = gather ? a.M / a.slot_rows : 0;
     p.err_flag = err_flag_ptr();
     p.dbg = g_dbg;
@@ -487,9 +616,14 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tb, a.W, a.K, w_rows, a.ldw, BK, bn);
     if (rc) return rc;
-    if (bn == 64) return launch_tc<64, 8>(ta, tb, p, st);
-    if (bn == 256) return launch_tc<256, 4>(ta, tb, p, st);
-    return launch_tc<128, 6>(ta, tb, p, st);
+    CUtensorMap tc = tb;
+    if (p.tma_store) {
+        rc = make_tmap_out(&tc, a.C, a.out_dtype, a.N, a.M, a.ldc);
+        if (rc) return rc;
+    }
+    if (bn == 64) return launch_tc<64, 8>(ta, tb, tc, p, st);
+    if (bn == 256) return launch_tc<256, 4>(ta, tb, tc, p, st);
+    return launch_tc<128, 6>(ta, tb, tc, p, st);
 }
 
 }  // namespace stair
@@ -498,6 +632,7 @@ using namespace stair;
 
 extern "C" int stair_set_gemm_impl(int impl) { g_gemm_impl = impl; return STAIR_OK; }
 extern "C" int stair_gemm_debug_timeline(unsigned long long* dev_buf) { g_dbg = dev_buf; return STAIR_OK; }
+extern "C" int stair_set_gemm_epilogue(int impl) { g_epilogue_impl = impl; return STAIR_OK; }
 extern "C" int stair_get_gemm_impl() { return g_gemm_impl; }
 extern "C" int stair_gemm_error_flag() { return g_err_flag ? *g_err_flag : 0; }
 
