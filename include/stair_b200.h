@@ -84,6 +84,9 @@ enum StairWeight {
     STAIR_W_EXISTS0_W, STAIR_W_EXISTS0_B, STAIR_W_EXISTS1_W, STAIR_W_EXISTS1_B,
     STAIR_W_EXISTS_HEAD_W, STAIR_W_EXISTS_HEAD_B,                                        /* modules.py:144-150 */
     STAIR_W_TOACT0_W, STAIR_W_TOACT0_B, STAIR_W_TOACT1_W, STAIR_W_TOACT1_B,              /* modules.py:105-108 */
+    /* W_hh of the two encoders with rows re-ordered for the fused recurrence kernel (bf16, 1 plane, only when h % 64 == 0):
+     * row c*256 + g*64 + u  <-  W_hh row g*h + c*64 + u   (chunk c of 64 hidden units, gate g in i,f,g,o) */
+    STAIR_W_VENC_WHHI_F, STAIR_W_VENC_WHHI_R, STAIR_W_TENC_WHHI_F, STAIR_W_TENC_WHHI_R,
     STAIR_W_COUNT
 };
 

@@ -13,6 +13,7 @@ namespace stair {
 
 namespace {
 
+int g_lstm_impl = 0;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
 constexpr long long ROW_CAP = 65536;     // frame rows per chunk of a VID-typed group
 constexpr long long VEC_CAP = 16384;     // instances per chunk of a VEC-typed group / decoder chunk
 
@@ -50,7 +51,7 @@ void make_plan(const StairModel& m, const StairBatch& b, Plan* p) {
     p->xq_in = take(static_cast<long long>(np) * b.n_tok * m.text_ld * 2);
     p->xq = take(static_cast<long long>(b.n_tok) * 4 * H * esz);
     p->g = take(2 * B * 4 * h * 4);
-    p->c = take(2 * B * h * 4);
+    p->c = take(2 * 2 * B * h * 4);     // video + text cell states (the fused kernel runs both encoders at once)
     p->hs = take(np * 2 * B * h * 2);
     const long long enc_total = o;
     // module regions
@@ -156,7 +157,8 @@ int run_encoders(Ctx& c, int phases) {
         a.M = static_cast<int>(rows_v); a.N = 4 * H; a.K = m.V;
         STAIR_TRY(launch_gemm(a, c.st));
     }
-    if (phases & STAIR_FWD_ENCODE_VIDEO) {
+    const bool fused = lstm_fused_ok(m.precision, h) && g_lstm_impl == 0 && c.W(STAIR_W_VENC_WHHI_F) && c.W(STAIR_W_TENC_WHHI_F);
+    if ((phases & STAIR_FWD_ENCODE_VIDEO) && !fused) {
     if (cudaMemsetAsync(cs, 0, sizeof(float) * 2 * B * h, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
     for (int s = 0; s < T; ++s) {
         if (s > 0)
@@ -167,7 +169,12 @@ int run_encoders(Ctx& c, int phases) {
         STAIR_TRY(launch_lstm_cell_video(c.adt, c.at<void>(c.plan.xv), g, cs, hs, c.np, c.adt, c.buf.vid, B, T, h, s, c.st));
     }
     }
-    if (!(phases & STAIR_FWD_ENCODE_TEXT)) return STAIR_OK;
+    if (!(phases & STAIR_FWD_ENCODE_TEXT)) {
+        if (fused && (phases & STAIR_FWD_ENCODE_VIDEO))
+            return launch_lstm_fused(c.at<void>(c.plan.xv), c.buf.vid, T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R), nullptr,
+                                     nullptr, nullptr, nullptr, 0, nullptr, nullptr, cs, B, h, 1, 0, err_flag_ptr(), c.st);
+        return STAIR_OK;
+    }
     // text input projection over the packed tokens of all questions
     {
         bf16* in = c.at<bf16>(c.plan.xq_in);
@@ -179,6 +186,10 @@ int run_encoders(Ctx& c, int phases) {
         a.M = b.n_tok; a.N = 4 * H; a.K = m.text_size;
         STAIR_TRY(launch_gemm(a, c.st));
     }
+    if (fused)
+        return launch_lstm_fused(c.at<void>(c.plan.xv), c.buf.vid, T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R),
+                                 c.at<void>(c.plan.xq), c.buf.tokfeat, c.buf.qfeat, b.q_off, b.L_max, c.W(STAIR_W_TENC_WHHI_F),
+                                 c.W(STAIR_W_TENC_WHHI_R), cs, B, h, (phases & STAIR_FWD_ENCODE_VIDEO) ? 1 : 0, 1, err_flag_ptr(), c.st);
     if (cudaMemsetAsync(cs, 0, sizeof(float) * 2 * B * h, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
     for (int s = 0; s < b.L_max; ++s) {
         if (s > 0)
@@ -365,6 +376,7 @@ thread_local long long t_last_launches = 0;
 
 using namespace stair;
 
+extern "C" int stair_set_lstm_impl(int impl) { g_lstm_impl = impl; return STAIR_OK; }
 extern "C" int stair_version(void) { return STAIR_ABI_VERSION; }
 
 extern "C" int64_t stair_nmn_workspace_bytes(const StairModel* model, const StairBatch* batch) {

@@ -1,0 +1,327 @@
+// Persistent fused BiLSTM recurrence (bf16 path): the whole time loop of nn.LSTM (video_nmn/module_net.py:39-47,
+// 147-163) in ONE launch for both encoders and both directions.
+//
+// One CTA owns 128 questions of one (encoder, direction) for all T (or L) steps:
+//   h_{t-1} lives in shared memory as the bf16 A operand (128 x h, K-major, SWIZZLE_128B, double-buffered),
+//   W_hh (gate-interleaved so that a 256-column chunk = 64 hidden units x {i,f,g,o}) streams from L2 through a TMA ring,
+//   tcgen05.mma accumulates the 128 x 256 gate pre-activations of a chunk in TMEM (two chunks in flight),
+//   8 epilogue warps add the precomputed input projection (xproj), apply the cell non-linearities, update c (fp32, global,
+//   L2-resident), write h_t to the encoder output and straight back into the other shared-memory h buffer.
+// No per-step launches, no [B,4h] round trips: per step only xproj rows and h rows touch HBM.
+//
+// warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4..11: cell epilogue (2 warps per TMEM lane quarter)
+#include "nmn_kernels.cuh"
+#include "tc_ptx.cuh"
+
+namespace stair {
+
+namespace {
+
+constexpr int LF_THREADS = 384;
+constexpr int LF_ROWS = 128;
+constexpr int LF_KB_BYTES = LF_ROWS * 64 * 2;      // one 64-wide k-block of h: 16 KiB
+constexpr int LF_W_STAGE_BYTES = 256 * 64 * 2;     // one W tile (256 gate columns x 64 k): 32 KiB
+constexpr int LF_STAGES = 3;
+constexpr uint32_t LF_IDESC = make_idesc_bf16(128, 256);
+
+struct LstmSeq {
+    const bf16* xproj;      // [rows, 8h]: W_ih x + b for both directions (fwd gates | reverse gates)
+    float* c;               // [2][B][h] cell state scratch (fp32)
+    bf16* out;              // video: [B*T, 2h] (VID arena slots 0..B-1) ; text: token_feature [n_tok, 2h]
+    bf16* final_h;          // text: question_feature [B, 2h] (h_n of both directions) ; video: null
+    const int* q_off;       // text: [B+1] token offsets (ragged) ; video: null
+    int steps;              // video: T ; text: L_max
+    int B, h;
+};
+
+struct LstmFusedParams {
+    LstmSeq seq[2];
+    int* err_flag;
+    volatile unsigned int* dbg;   // debug progress words (pinned host memory), null in production
+};
+#define LF_DBG(slot, val) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { p.dbg[slot] = (val); __threadfence_system(); } } while (0)
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(hh[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+__global__ void __launch_bounds__(LF_THREADS, 1)
+lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
+                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, const LstmFusedParams p) {
+    const LstmSeq& sq = p.seq[blockIdx.z];
+    const int dir = blockIdx.y;
+    const int wsel = blockIdx.z * 2 + dir;          // which W_hh map (never form a runtime-selected pointer to a param-space map)
+    const int row0 = blockIdx.x * LF_ROWS;
+    if (row0 >= sq.B) return;
+    const int h = sq.h, NC = h / 64;              // chunks of 64 hidden units == k-blocks of h
+    const bool ragged = sq.q_off != nullptr;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    const int hbuf_bytes = NC * LF_KB_BYTES;
+    uint8_t* sH = smem;                                            // [2][NC][128 x 64] bf16
+    uint8_t* sW = smem + 2 * hbuf_bytes;                           // [LF_STAGES][256 x 64] bf16
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(sW + LF_STAGES * LF_W_STAGE_BYTES);
+    uint64_t* w_empty = w_full + LF_STAGES;
+    uint64_t* tmem_full = w_empty + LF_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint64_t* h_ready = tmem_empty + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(h_ready + 1);
+    int* s_steps = reinterpret_cast<int*>(tmem_ptr_smem + 1);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LF_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 256); }
+        mbar_init(h_ready, 256);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *s_steps = ragged ? 0 : sq.steps;
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr_smem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 2 * hbuf_bytes / 16; i += LF_THREADS) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (ragged && threadIdx.x < LF_ROWS) {                          // this CTA only runs as many steps as its longest question
+        const int r = row0 + threadIdx.x;
+        if (r < sq.B) atomicMax(s_steps, __ldg(sq.q_off + r + 1) - __ldg(sq.q_off + r));
+    }
+    fence_async_smem();                                            // zero-filled h buffers visible to the tensor core (async proxy)
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int S = *s_steps;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer: W_hh tiles, (chunk, k-block) order, every step after the first ==========
+            int stage = 0; uint32_t phase = 0;
+            for (int s = 1; s < S; ++s)
+                for (int c = 0; c < NC; ++c)
+                    for (int kb = 0; kb < NC; ++kb) {
+                        LF_DBG(0, 0x10000u + s * 256 + c * 16 + kb);
+                        mbar_wait(&w_empty[stage], phase ^ 1, p.err_flag, 201);
+                        mbar_arrive_expect_tx(&w_full[stage], LF_W_STAGE_BYTES);
+                        uint8_t* dst = sW + stage * LF_W_STAGE_BYTES;
+                        if (wsel == 0) tma_load_2d(dst, &tmW0, &w_full[stage], kb * 64, c * 256);
+                        else if (wsel == 1) tma_load_2d(dst, &tmW1, &w_full[stage], kb * 64, c * 256);
+                        else if (wsel == 2) tma_load_2d(dst, &tmW2, &w_full[stage], kb * 64, c * 256);
+                        else tma_load_2d(dst, &tmW3, &w_full[stage], kb * 64, c * 256);
+                        if (++stage == LF_STAGES) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer: gates[128, 256c..] = h_{s-1}[128, h] . W_hh[chunk]^T ============================
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int s = 1; s < S; ++s) {
+                LF_DBG(1, 0x20000u + s * 256);
+                mbar_wait(h_ready, static_cast<uint32_t>((s - 1) & 1), p.err_flag, 202);   // h_{s-1} fully written to sH[s & 1]
+                LF_DBG(1, 0x21000u + s * 256);
+                tcgen05_fence_after();
+                const uint32_t hb = smem_u32(sH + (s & 1) * hbuf_bytes);
+                for (int c = 0; c < NC; ++c) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.err_flag, 203);
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+                    for (int kb = 0; kb < NC; ++kb) {
+                        LF_DBG(1, 0x24000u + s * 256 + c * 16 + kb);
+                        mbar_wait(&w_full[stage], phase, p.err_flag, 204);
+                        tcgen05_fence_after();
+                        const uint64_t adesc = make_umma_desc_kmajor_sw128(hb + kb * LF_KB_BYTES);
+                        const uint64_t bdesc = make_umma_desc_kmajor_sw128(smem_u32(sW + stage * LF_W_STAGE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, LF_IDESC, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit(&w_empty[stage]);
+                        if (++stage == LF_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(&tmem_full[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== cell epilogue: 2 warps per TMEM lane quarter, each takes 32 of a chunk's 64 units =============
+        const int quarter = warp & 3, halfsel = (warp - 4) >> 2;
+        const int row = quarter * 32 + lane;
+        const int grow = row0 + row;
+        const bool valid = grow < sq.B;
+        int base = 0, L = sq.steps;
+        if (ragged) { base = valid ? __ldg(sq.q_off + grow) : 0; L = valid ? __ldg(sq.q_off + grow + 1) - base : 0; }
+        else base = grow * sq.steps;
+        float* crow = sq.c + (static_cast<long long>(dir) * sq.B + grow) * h;
+        const uint32_t sH0 = smem_u32(sH);
+        const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
+        const uint32_t sw = static_cast<uint32_t>(row & 7);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int s = 0; s < S; ++s) {
+            const bool active = valid && s < L;
+            const long long tokrow = static_cast<long long>(base) + (dir == 0 ? s : L - 1 - s);
+            const bf16* xrow = sq.xproj + tokrow * 8 * h + dir * 4 * h;
+            bf16* orow = sq.out + tokrow * 2 * h + dir * h;
+            const bool last = ragged && s == L - 1;
+            const uint32_t h_src = sH0 + static_cast<uint32_t>((s & 1) * hbuf_bytes);
+            const uint32_t h_dst = sH0 + static_cast<uint32_t>(((s + 1) & 1) * hbuf_bytes);
+            for (int c = 0; c < NC; ++c) {
+                if (s > 0) {
+                    if (lane == 0) LF_DBG(2 + (warp - 4), 0x50000u + s * 256 + c);
+                    mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 205);
+                    tcgen05_fence_after();
+                }
+#pragma unroll 1
+                for (int sb = 0; sb < 2; ++sb) {
+                    const int sub = 2 * halfsel + sb;                 // 16 hidden units u0 .. u0+15
+                    const int u0 = c * 64 + sub * 16;
+                    uint32_t gi[16], gf[16], gg[16], go[16];
+                    if (s > 0) {
+                        const uint32_t t = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256 + sub * 16);
+                        tmem_ld16(t, gi); tmem_ld16(t + 64, gf); tmem_ld16(t + 128, gg); tmem_ld16(t + 192, go);
+                    }
+                    const uint32_t ch0 = static_cast<uint32_t>(sub * 2);
+                    const uint32_t a0 = static_cast<uint32_t>(c) * LF_KB_BYTES + rowoff + (((ch0) ^ sw) << 4);
+                    const uint32_t a1 = static_cast<uint32_t>(c) * LF_KB_BYTES + rowoff + (((ch0 + 1) ^ sw) << 4);
+                    uint4 xi[2], xf[2], xg[2], xo[2];
+                    float cprev[16];
+                    if (active) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            xi[q] = __ldg(reinterpret_cast<const uint4*>(xrow + u0) + q);
+                            xf[q] = __ldg(reinterpret_cast<const uint4*>(xrow + h + u0) + q);
+                            xg[q] = __ldg(reinterpret_cast<const uint4*>(xrow + 2 * h + u0) + q);
+                            xo[q] = __ldg(reinterpret_cast<const uint4*>(xrow + 3 * h + u0) + q);
+                        }
+                        if (s > 0) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 t4 = *reinterpret_cast<const float4*>(crow + u0 + 4 * q);
+                                cprev[4 * q] = t4.x; cprev[4 * q + 1] = t4.y; cprev[4 * q + 2] = t4.z; cprev[4 * q + 3] = t4.w;
+                            }
+                        }
+                    }
+                    if (s > 0) {                                      // tcgen05.wait::ld is .sync.aligned: the whole warp, converged
+                        __syncwarp();
+                        tmem_ld_wait();
+                    }
+                    if (active) {
+                        float hn[16], cn[16];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            float fi[8], ff[8], fg[8], fo[8];
+                            unpack8(xi[q], fi); unpack8(xf[q], ff); unpack8(xg[q], fg); unpack8(xo[q], fo);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int e = 8 * q + j;
+                                float pi = fi[j], pf = ff[j], pg = fg[j], po = fo[j], cp = 0.0f;
+                                if (s > 0) {
+                                    pi += __uint_as_float(gi[e]); pf += __uint_as_float(gf[e]);
+                                    pg += __uint_as_float(gg[e]); po += __uint_as_float(go[e]);
+                                    cp = cprev[e];
+                                }
+                                const float cc = fast_sigmoid(pf) * cp + fast_sigmoid(pi) * fast_tanh(pg);
+                                cn[e] = cc;
+                                hn[e] = fast_sigmoid(po) * fast_tanh(cc);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<float4*>(crow + u0 + 4 * q) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
+                        uint4 o0, o1;
+                        o0.x = pack_bf16(hn[0], hn[1]); o0.y = pack_bf16(hn[2], hn[3]); o0.z = pack_bf16(hn[4], hn[5]); o0.w = pack_bf16(hn[6], hn[7]);
+                        o1.x = pack_bf16(hn[8], hn[9]); o1.y = pack_bf16(hn[10], hn[11]); o1.z = pack_bf16(hn[12], hn[13]); o1.w = pack_bf16(hn[14], hn[15]);
+                        reinterpret_cast<uint4*>(orow + u0)[0] = o0;
+                        reinterpret_cast<uint4*>(orow + u0)[1] = o1;
+                        if (last) {
+                            uint4* fh = reinterpret_cast<uint4*>(sq.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0);
+                            fh[0] = o0; fh[1] = o1;
+                        }
+                        st_shared_v4(h_dst + a0, o0.x, o0.y, o0.z, o0.w);
+                        st_shared_v4(h_dst + a1, o1.x, o1.y, o1.z, o1.w);
+                    } else {
+                        // finished (or padding) row: carry h forward unchanged so the next step's MMA reads a defined operand
+                        const uint4 p0 = ld_shared_v4(h_src + a0), p1 = ld_shared_v4(h_src + a1);
+                        st_shared_v4(h_dst + a0, p0.x, p0.y, p0.z, p0.w);
+                        st_shared_v4(h_dst + a1, p1.x, p1.y, p1.z, p1.w);
+                    }
+                }
+                if (s > 0) {
+                    tcgen05_fence_before();
+                    mbar_arrive(&tmem_empty[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+            fence_async_smem();                                     // h_s (generic-proxy stores) -> visible to tcgen05.mma
+            mbar_arrive(h_ready);
+            if (lane == 0) LF_DBG(2 + (warp - 4), 0x60000u + s * 256);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+}  // namespace
+
+static volatile unsigned int* g_lstm_dbg = nullptr;
+bool lstm_fused_ok(int precision, int h) { return precision == STAIR_BF16 && h >= 64 && h <= 256 && (h % 64) == 0; }
+
+// seq 0 = video (T steps), seq 1 = text (ragged, L_max steps); either may be disabled with steps = 0.
+int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh_v_f, const void* whh_v_r,
+                      const void* xproj_t, void* tokfeat, void* qfeat, const int* q_off, int L_max, const void* whh_t_f,
+                      const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st) {
+    if (B <= 0 || (!run_video && !run_text)) return STAIR_OK;
+    LstmFusedParams p;
+    p.err_flag = err_flag;
+    p.dbg = g_lstm_dbg;
+    LstmSeq v; v.xproj = reinterpret_cast<const bf16*>(xproj_v); v.c = c_scratch; v.out = reinterpret_cast<bf16*>(vid_out);
+    v.final_h = nullptr; v.q_off = nullptr; v.steps = T; v.B = B; v.h = h;
+    LstmSeq t; t.xproj = reinterpret_cast<const bf16*>(xproj_t); t.c = c_scratch + 2LL * B * h; t.out = reinterpret_cast<bf16*>(tokfeat);
+    t.final_h = reinterpret_cast<bf16*>(qfeat); t.q_off = q_off; t.steps = L_max; t.B = B; t.h = h;
+    const void* w[4];
+    int nseq = 0;
+    if (run_video) { p.seq[nseq] = v; w[2 * nseq] = whh_v_f; w[2 * nseq + 1] = whh_v_r; ++nseq; }
+    if (run_text) { p.seq[nseq] = t; w[2 * nseq] = whh_t_f; w[2 * nseq + 1] = whh_t_r; ++nseq; }
+    if (nseq == 1) { p.seq[1] = p.seq[0]; w[2] = w[0]; w[3] = w[1]; }
+    CUtensorMap tm[4];
+    for (int i = 0; i < 4; ++i) STAIR_TRY(make_tmap_bf16_2d(&tm[i], w[i], h, 4ULL * h, h, 64, 256));
+    const int smem = 2 * (h / 64) * LF_KB_BYTES + LF_STAGES * LF_W_STAGE_BYTES + 256 + 1024;
+    static int configured = 0;
+    if (configured < smem) {
+        if (cudaFuncSetAttribute(lstm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return STAIR_ERR_CUDA;
+        configured = smem;
+    }
+    dim3 grid((B + LF_ROWS - 1) / LF_ROWS, 2, nseq);
+    lstm_fused_kernel<<<grid, LF_THREADS, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
+    STAIR_CHECK_LAUNCH();
+    return STAIR_OK;
+}
+
+}  // namespace stair
+
+extern "C" int stair_lstm_debug(unsigned int* pinned_buf) { stair::g_lstm_dbg = pinned_buf; return STAIR_OK; }

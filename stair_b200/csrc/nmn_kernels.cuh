@@ -70,6 +70,12 @@ int launch_lstm_cell_video(int xdt, const void* xproj, const float* g, float* c,
 int launch_lstm_cell_text(int xdt, const void* xproj, const float* g, float* c, bf16* hstate, int nplanes, int odt, void* tokfeat,
                           void* qfeat, const int* q_off, int B, int h, int step, cudaStream_t st);
 
+// fused persistent recurrence for both encoders and both directions (lstm_fused.cu; bf16 path, h in {64,128,192,256})
+bool lstm_fused_ok(int precision, int h);
+int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh_v_f, const void* whh_v_r,
+                      const void* xproj_t, void* tokfeat, void* qfeat, const int* q_off, int L_max, const void* whh_t_f,
+                      const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st);
+
 // ---- layout grouping (layout_group.cu) ----------------------------------------------------------------------------
 int launch_group_layouts(const StairBatch& b, int32_t* itab, int32_t* status, cudaStream_t st);
 

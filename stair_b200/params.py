@@ -166,6 +166,11 @@ def weight_sources(sub, config):
         s[prefix + '_B'] = ('V', lambda: torch.cat([m.bias_ih_l0 + m.bias_hh_l0, m.bias_ih_l0_reverse + m.bias_hh_l0_reverse]))
         s[prefix + '_WHH_F'] = ('M', lambda: m.weight_hh_l0)
         s[prefix + '_WHH_R'] = ('M', lambda: m.weight_hh_l0_reverse)
+        hh = m.hidden_size
+        if hh % 64 == 0:                        # gate-interleaved copy for the fused recurrence kernel (csrc/lstm_fused.cu)
+            il = lambda w: w.reshape(4, hh // 64, 64, hh).permute(1, 0, 2, 3).reshape(4 * hh, hh)        # noqa: E731
+            s[prefix + '_WHHI_F'] = ('M1', lambda: il(m.weight_hh_l0))
+            s[prefix + '_WHHI_R'] = ('M1', lambda: il(m.weight_hh_l0_reverse))
 
     def mlp4(prefix, seq):                      # 4 consecutive slots w0,b0,w1,b1 (Sequential indices 0 and 3)
         base = L.W[prefix]
@@ -234,7 +239,12 @@ class PackedWeights:
                 w = get()
                 if w.device != device:
                     raise L.StairError('model parameters live on %s but the batch is on %s; call model.to(device)' % (w.device, device))
-                tensors[wid] = _matrix(w.reshape(w.shape[0], -1), nplanes) if kind == 'M' else _vector(w)
+                if kind == 'M':
+                    tensors[wid] = _matrix(w.reshape(w.shape[0], -1), nplanes)
+                elif kind == 'M1':
+                    tensors[wid] = _matrix(w.reshape(w.shape[0], -1), 1)
+                else:
+                    tensors[wid] = _vector(w)
         m = L.StairModel()
         T = config['max_video_length']
         m.T_max, m.V, m.V_ld, m.H = T, config['video_size'], _pad8(config['video_size']), config['hidden_size']

@@ -153,3 +153,40 @@ def test_full_size_against_oracle(shape):
                 else:
                     _close(got, exp, precision, 'q%d step %d %s' % (qi, j, qs[qi]['nmn_program_list'][j]))
         assert n_checked >= (24 if precision == 'fp32' else 1)
+
+
+@pytest.mark.parametrize('hidden,T', [(128, 8), (256, 16), (512, 8), (512, 64)])
+def test_fused_lstm_matches_stepwise(hidden, T):
+    """csrc/lstm_fused.cu (persistent fused recurrence) == per-step GEMM + cell kernels, and both ~ the oracle's encoders."""
+    from stair_b200 import _lib as L
+    V = 256
+    cfg = syn.model_config(T=T, V=V, hidden=hidden)
+    torch.manual_seed(1)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16')
+    weights = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().eval()
+    qs = syn.make_questions(300, T, V, seed=11)                 # 300 questions: 3 row blocks, the last one partial
+    outs = {}
+    for impl in (1, 0):
+        L.lib().stair_set_lstm_impl(impl)
+        try:
+            batch = collate(qs).to('cuda')
+            st = model.forward_batch(batch, phases=L.FWD_ENCODE_VIDEO | L.FWD_ENCODE_TEXT)
+            torch.cuda.synchronize()
+            B, H = batch.B, hidden
+            outs[impl] = (st.vid[:B * T * H].float().cpu().clone(), st.tokfeat[:batch.n_tok * H].float().cpu().clone(),
+                          st.qfeat[:B * H].float().cpu().clone())
+        finally:
+            L.lib().stair_set_lstm_impl(0)
+    for a, b, name in zip(outs[0], outs[1], ('video_feat', 'token_feature', 'question_feature')):
+        err = float((a - b).abs().max())
+        assert err <= 2e-2, '%s fused vs stepwise: %g' % (name, err)
+    oracle = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES, aten_lstm=True)
+    with torch.no_grad():
+        for qi in (0, 150, 299):
+            v = oracle.encode_video(qs[qi]['video_features'])
+            tok, sent = oracle.encode_question(qs[qi]['question'])
+            got_v = outs[0][0].view(-1, T, hidden)[qi]
+            got_s = outs[0][2].view(-1, hidden)[qi]
+            assert float((got_v - v).abs().max()) <= 3e-2 * float(v.abs().max()) + 2e-3
+            assert float((got_s - sent).abs().max()) <= 3e-2 * float(sent.abs().max()) + 2e-3
