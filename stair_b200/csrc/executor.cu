@@ -51,7 +51,7 @@ void make_plan(const StairModel& m, const StairBatch& b, Plan* p) {
     p->xq_in = take(static_cast<long long>(np) * b.n_tok * m.text_ld * 2);
     p->xq = take(static_cast<long long>(b.n_tok) * 4 * H * esz);
     p->g = take(2 * B * 4 * h * 4);
-    p->c = take(2 * 2 * B * h * 4);     // video + text cell states (the fused kernel runs both encoders at once)
+    p->c = take(2 * 2 * ((B + 127) / 128 * 128) * h * 4);     // video + text cell states (the fused kernel runs both encoders at once)
     p->hs = take(np * 2 * B * h * 2);
     const long long enc_total = o;
     // module regions

@@ -54,6 +54,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
@@ -173,7 +178,9 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
         int base = 0, L = sq.steps;
         if (ragged) { base = valid ? __ldg(sq.q_off + grow) : 0; L = valid ? __ldg(sq.q_off + grow + 1) - base : 0; }
         else base = grow * sq.steps;
-        float* crow = sq.c + (static_cast<long long>(dir) * sq.B + grow) * h;
+        // cell state scratch, private to this CTA, laid out [unit/4][row][4] so that a warp's float4 accesses are contiguous
+        const int nblk = (sq.B + LF_ROWS - 1) / LF_ROWS;
+        float* cblk = sq.c + (static_cast<long long>(dir) * nblk + blockIdx.x) * (static_cast<long long>(h) * LF_ROWS) + row * 4;
         const uint32_t sH0 = smem_u32(sH);
         const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
         const uint32_t sw = static_cast<uint32_t>(row & 7);
@@ -193,31 +200,27 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                     tcgen05_fence_after();
                 }
 #pragma unroll 1
-                for (int sb = 0; sb < 2; ++sb) {
-                    const int sub = 2 * halfsel + sb;                 // 16 hidden units u0 .. u0+15
-                    const int u0 = c * 64 + sub * 16;
-                    uint32_t gi[16], gf[16], gg[16], go[16];
+                for (int sb = 0; sb < 4; ++sb) {
+                    const int u0 = c * 64 + halfsel * 32 + sb * 8;    // 8 hidden units u0 .. u0+7 (one 16-byte chunk of the h row)
+                    uint32_t gi[8], gf[8], gg[8], go[8];
                     if (s > 0) {
-                        const uint32_t t = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256 + sub * 16);
-                        tmem_ld16(t, gi); tmem_ld16(t + 64, gf); tmem_ld16(t + 128, gg); tmem_ld16(t + 192, go);
+                        const uint32_t t = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                           static_cast<uint32_t>(acc * 256 + halfsel * 32 + sb * 8);
+                        tmem_ld8(t, gi); tmem_ld8(t + 64, gf); tmem_ld8(t + 128, gg); tmem_ld8(t + 192, go);
                     }
-                    const uint32_t ch0 = static_cast<uint32_t>(sub * 2);
-                    const uint32_t a0 = static_cast<uint32_t>(c) * LF_KB_BYTES + rowoff + (((ch0) ^ sw) << 4);
-                    const uint32_t a1 = static_cast<uint32_t>(c) * LF_KB_BYTES + rowoff + (((ch0 + 1) ^ sw) << 4);
-                    uint4 xi[2], xf[2], xg[2], xo[2];
-                    float cprev[16];
+                    const uint32_t ch = static_cast<uint32_t>(halfsel * 4 + sb);
+                    const uint32_t a0 = static_cast<uint32_t>(c) * LF_KB_BYTES + rowoff + ((ch ^ sw) << 4);
+                    uint4 xi, xf, xg, xo;
+                    float cprev[8];
                     if (active) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            xi[q] = __ldg(reinterpret_cast<const uint4*>(xrow + u0) + q);
-                            xf[q] = __ldg(reinterpret_cast<const uint4*>(xrow + h + u0) + q);
-                            xg[q] = __ldg(reinterpret_cast<const uint4*>(xrow + 2 * h + u0) + q);
-                            xo[q] = __ldg(reinterpret_cast<const uint4*>(xrow + 3 * h + u0) + q);
-                        }
+                        xi = __ldg(reinterpret_cast<const uint4*>(xrow + u0));
+                        xf = __ldg(reinterpret_cast<const uint4*>(xrow + h + u0));
+                        xg = __ldg(reinterpret_cast<const uint4*>(xrow + 2 * h + u0));
+                        xo = __ldg(reinterpret_cast<const uint4*>(xrow + 3 * h + u0));
                         if (s > 0) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 t4 = *reinterpret_cast<const float4*>(crow + u0 + 4 * q);
+                            for (int q = 0; q < 2; ++q) {
+                                const float4 t4 = *reinterpret_cast<const float4*>(cblk + (u0 / 4 + q) * (LF_ROWS * 4));
                                 cprev[4 * q] = t4.x; cprev[4 * q + 1] = t4.y; cprev[4 * q + 2] = t4.z; cprev[4 * q + 3] = t4.w;
                             }
                         }
@@ -227,44 +230,32 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                         tmem_ld_wait();
                     }
                     if (active) {
-                        float hn[16], cn[16];
+                        float fi[8], ff[8], fg[8], fo[8], hn[8], cn[8];
+                        unpack8(xi, fi); unpack8(xf, ff); unpack8(xg, fg); unpack8(xo, fo);
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            float fi[8], ff[8], fg[8], fo[8];
-                            unpack8(xi[q], fi); unpack8(xf[q], ff); unpack8(xg[q], fg); unpack8(xo[q], fo);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int e = 8 * q + j;
-                                float pi = fi[j], pf = ff[j], pg = fg[j], po = fo[j], cp = 0.0f;
-                                if (s > 0) {
-                                    pi += __uint_as_float(gi[e]); pf += __uint_as_float(gf[e]);
-                                    pg += __uint_as_float(gg[e]); po += __uint_as_float(go[e]);
-                                    cp = cprev[e];
-                                }
-                                const float cc = fast_sigmoid(pf) * cp + fast_sigmoid(pi) * fast_tanh(pg);
-                                cn[e] = cc;
-                                hn[e] = fast_sigmoid(po) * fast_tanh(cc);
+                        for (int j = 0; j < 8; ++j) {
+                            float pi = fi[j], pf = ff[j], pg = fg[j], po = fo[j], cp = 0.0f;
+                            if (s > 0) {
+                                pi += __uint_as_float(gi[j]); pf += __uint_as_float(gf[j]);
+                                pg += __uint_as_float(gg[j]); po += __uint_as_float(go[j]);
+                                cp = cprev[j];
                             }
+                            const float cc = fast_sigmoid(pf) * cp + fast_sigmoid(pi) * fast_tanh(pg);
+                            cn[j] = cc;
+                            hn[j] = fast_sigmoid(po) * fast_tanh(cc);
                         }
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<float4*>(crow + u0 + 4 * q) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
-                        uint4 o0, o1;
+                        for (int q = 0; q < 2; ++q)
+                            *reinterpret_cast<float4*>(cblk + (u0 / 4 + q) * (LF_ROWS * 4)) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
+                        uint4 o0;
                         o0.x = pack_bf16(hn[0], hn[1]); o0.y = pack_bf16(hn[2], hn[3]); o0.z = pack_bf16(hn[4], hn[5]); o0.w = pack_bf16(hn[6], hn[7]);
-                        o1.x = pack_bf16(hn[8], hn[9]); o1.y = pack_bf16(hn[10], hn[11]); o1.z = pack_bf16(hn[12], hn[13]); o1.w = pack_bf16(hn[14], hn[15]);
-                        reinterpret_cast<uint4*>(orow + u0)[0] = o0;
-                        reinterpret_cast<uint4*>(orow + u0)[1] = o1;
-                        if (last) {
-                            uint4* fh = reinterpret_cast<uint4*>(sq.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0);
-                            fh[0] = o0; fh[1] = o1;
-                        }
+                        *reinterpret_cast<uint4*>(orow + u0) = o0;
+                        if (last) *reinterpret_cast<uint4*>(sq.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0) = o0;
                         st_shared_v4(h_dst + a0, o0.x, o0.y, o0.z, o0.w);
-                        st_shared_v4(h_dst + a1, o1.x, o1.y, o1.z, o1.w);
                     } else {
                         // finished (or padding) row: carry h forward unchanged so the next step's MMA reads a defined operand
-                        const uint4 p0 = ld_shared_v4(h_src + a0), p1 = ld_shared_v4(h_src + a1);
+                        const uint4 p0 = ld_shared_v4(h_src + a0);
                         st_shared_v4(h_dst + a0, p0.x, p0.y, p0.z, p0.w);
-                        st_shared_v4(h_dst + a1, p1.x, p1.y, p1.z, p1.w);
                     }
                 }
                 if (s > 0) {
@@ -301,7 +292,7 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
     p.dbg = g_lstm_dbg;
     LstmSeq v; v.xproj = reinterpret_cast<const bf16*>(xproj_v); v.c = c_scratch; v.out = reinterpret_cast<bf16*>(vid_out);
     v.final_h = nullptr; v.q_off = nullptr; v.steps = T; v.B = B; v.h = h;
-    LstmSeq t; t.xproj = reinterpret_cast<const bf16*>(xproj_t); t.c = c_scratch + 2LL * B * h; t.out = reinterpret_cast<bf16*>(tokfeat);
+    LstmSeq t; t.xproj = reinterpret_cast<const bf16*>(xproj_t); t.c = c_scratch + 2LL * ((B + LF_ROWS - 1) / LF_ROWS) * LF_ROWS * h; t.out = reinterpret_cast<bf16*>(tokfeat);
     t.final_h = reinterpret_cast<bf16*>(qfeat); t.q_off = q_off; t.steps = L_max; t.B = B; t.h = h;
     const void* w[4];
     int nseq = 0;
