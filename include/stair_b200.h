@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define STAIR_ABI_VERSION 3
+#define STAIR_ABI_VERSION 4
 
 /* status codes */
 #define STAIR_OK 0
@@ -101,6 +101,7 @@ typedef struct StairModel {
     int32_t conv_k;      /* Temporal Conv1d kernel size round(T_max/4) when T_max > 32, else 0 */
     int32_t precision;   /* STAIR_BF16: bf16 storage, fp32 accumulate.  STAIR_F32: fp32 storage, bf16x3 split GEMMs */
     const void* w[STAIR_W_COUNT];
+    const void* wt[STAIR_W_COUNT];  /* training only (else NULL): transposed copies bf16 [nplanes][K, N_ld] of the *_W GEMM matrices */
 } StairModel;
 
 /* One (level, op, variant) group of module instances; groups are listed in schedule order (level-major). */
@@ -167,6 +168,25 @@ typedef struct StairItabLayout {
     int64_t total;
 } StairItabLayout;
 
+/* Training step state (train_module.py:33-194 losses, :341-412 window logic).  All pointers are device
+ * pointers owned by the caller.  Loss rows are collated by the host (stair_b200/train.py) with the reference's inclusion rules;
+ * every weight `w` already contains module_loss_weight (or decoder_loss_weight) / gradient_accumulation / #elements. */
+typedef struct StairTrain {
+    float* grad[STAIR_W_COUNT];   /* fp32 gradient accumulators, logical shapes of the parameters ([N,K] / vectors); NULL = frozen */
+    /* attention_score_criterion rows (Localize / Temporal / ExistsFrame), train_module.py:83-90,157-191 */
+    int32_t n_att; const int32_t* att_node; const int32_t* att_kind; const int32_t* att_slot; const float* att_gold; const float* att_w;
+    /* Exists / Xor (CE on the 2-way head) and Equals (MSE on the 1-way head), train_module.py:92-107 */
+    int32_t n_bin; const int32_t* bin_node; const int32_t* bin_which; const int32_t* bin_label; const float* bin_w;
+    /* contrastive CE of Filter / ToAction / Superlative against the window's class text reps, train_module.py:113-139,166-171,388-406 */
+    int32_t n_con; const int32_t* con_node; const int32_t* con_pos; const float* con_w; int32_t n_cls; const float* cls_rep;
+    /* decoder CE, train_module.py:193-194,376-380 */
+    const int32_t* answer; float dec_w;
+    float* loss;                  /* float[8] sums: 0 Localize 1 Temporal 2 ExistsFrame 3 Exists/Xor 4 Equals 5 contrastive 6 decoder */
+    float* dvid; float* dvec; float* datt; float* dtokfeat; float* dqfeat; float* dlogits;   /* gradient arenas (same shapes as the forward arenas) */
+    void* saved; int64_t saved_bytes;           /* LSTM gate / cell / state history written by stair_nmn_forward_train */
+    void* workspace; int64_t workspace_bytes;   /* backward scratch, >= stair_train_workspace_bytes */
+} StairTrain;
+
 int stair_version(void);
 
 /* ---- dense contraction (tcgen05 + TMA): C[M,N] = act(row_scale[m] * (A[M,K] . W[N,K]^T) + bias[n]) -------------
@@ -201,6 +221,16 @@ int64_t stair_nmn_workspace_bytes(const StairModel* model /*HOST*/, const StairB
 #define STAIR_FWD_ALL 31
 int stair_nmn_forward(const StairModel* model /*HOST*/, const StairBatch* batch /*HOST*/, const StairBuffers* buf /*HOST*/,
                       int phases, void* stream);
+/* Training: forward that keeps the encoder history, then losses + backward into StairTrain.grad (gradients ACCUMULATE; the
+ * caller zeroes them).  Module intermediates are recomputed per group in the backward pass instead of being stored. */
+int64_t stair_train_saved_bytes(const StairModel* model /*HOST*/, const StairBatch* batch /*HOST*/);
+int64_t stair_train_workspace_bytes(const StairModel* model /*HOST*/, const StairBatch* batch /*HOST*/, const StairBuffers* buf /*HOST*/,
+                                    const StairTrain* train /*HOST*/);
+int stair_nmn_forward_train(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, void* stream);
+int stair_nmn_backward(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, void* stream);
+/* torch.optim.Adam step (weight_decay 0) on one parameter tensor; `step` counts from 1 (train_module.py:326-332,408-412) */
+int stair_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
+                    float eps, int step, void* stream);
 /* number of kernels stair_nmn_forward launched in its last call on this thread (bench.py's gpu_launches). */
 int64_t stair_last_launch_count(void);
 

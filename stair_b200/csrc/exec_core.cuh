@@ -1,0 +1,367 @@
+// Core of the batched interpreter shared by the forward (executor.cu) and backward (executor_bwd.cu) entry points:
+// scratch plan, execution context, GEMM helpers and the per-group forward (video_nmn/module_net.py:94-133 per module).
+#pragma once
+#include "nmn_kernels.cuh"
+
+namespace stair {
+namespace ex {
+
+
+extern int g_lstm_impl;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
+constexpr long long ROW_CAP = 65536;     // frame rows per chunk of a VID-typed group
+constexpr long long VEC_CAP = 16384;     // instances per chunk of a VEC-typed group / decoder chunk
+
+inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+struct Plan {
+    // encoder phase
+    long long xv_in, xv, xq_in, xq, g, c, hs;
+    // module / decoder phase (aliases the encoder regions; everything is stream-ordered)
+    long long s0, s1, s2, pl, vp, v01, ats, a0;
+    long long total;
+    int nc_vid;          // instances per VID chunk
+    long long R;         // rows per VID chunk
+    long long PR;        // rows of the staging plane buffer
+};
+
+inline void make_plan(const StairModel& m, const StairBatch& b, Plan* p) {
+    const int np = m.precision == STAIR_F32 ? 3 : 1;
+    const long long esz = m.precision == STAIR_F32 ? 4 : 2;
+    const long long H = m.H, h = m.H / 2, T = b.T, B = b.B;
+    int max_count = 1;
+    for (int g = 0; g < b.n_groups; ++g) max_count = b.groups[g].count > max_count ? b.groups[g].count : max_count;
+    long long nc = ROW_CAP / (T > 0 ? T : 1);
+    if (nc < 1) nc = 1;
+    if (nc > max_count) nc = max_count;
+    p->nc_vid = static_cast<int>(nc);
+    p->R = nc * T;
+    p->PR = p->R + 2 * nc;
+    long long o = 0;
+    auto take = [&](long long bytes) { long long r = o; o = align_up(o + bytes, 1024); return r; };
+    // encoder regions
+    const bool stage_video = !(b.video_dtype == STAIR_BF16 && np == 1 && (m.V % 8) == 0);
+    p->xv_in = take(stage_video ? np * B * T * m.V_ld * 2 : 0);
+    p->xv = take(B * T * 4 * H * esz);
+    p->xq_in = take(static_cast<long long>(np) * b.n_tok * m.text_ld * 2);
+    p->xq = take(static_cast<long long>(b.n_tok) * 4 * H * esz);
+    p->g = take(2 * B * 4 * h * 4);
+    p->c = take(2 * 2 * ((B + 127) / 128 * 128) * h * 4);     // video + text cell states (the fused kernel runs both encoders at once)
+    p->hs = take(np * 2 * B * h * 2);
+    const long long enc_total = o;
+    // module regions
+    o = 0;
+    const long long Rv = VEC_CAP < max_count ? VEC_CAP : max_count;
+    const long long Rd = VEC_CAP < B ? VEC_CAP : B;
+    const long long Rvd = Rv > Rd ? Rv : Rd;
+    p->s0 = take(p->R * H * esz);
+    p->s1 = take(p->R * H * esz);
+    p->s2 = take(p->PR * H * esz);
+    p->pl = take(np * p->PR * H * 2);
+    p->vp = take(np * Rvd * 3 * H * 2);
+    p->v01 = take(Rvd * 2 * H * esz);
+    p->ats = take(p->R * (T > 2 ? T : 2) * 4);
+    p->a0 = take(p->R * 4);
+    p->total = o > enc_total ? o : enc_total;
+}
+
+struct Ctx {
+    const StairModel& m;
+    const StairBatch& b;
+    const StairBuffers& buf;
+    cudaStream_t st;
+    Plan plan;
+    char* ws;
+    int T, H, h, np, adt, esz;
+    StairItabLayout il;
+    const int *perm, *out_slot, *arg0, *arg1, *arg2, *pos_q, *span_s, *span_e;
+
+    template <typename P> P* at(long long off) const { return reinterpret_cast<P*>(ws + off); }
+    const void* W(int id) const { return m.w[id]; }
+    const float* Wf(int id) const { return reinterpret_cast<const float*>(m.w[id]); }
+    char* act_ptr(void* base, long long elem_off) const { return reinterpret_cast<char*>(base) + elem_off * esz; }
+};
+
+// C = act(row_scale * (A_planes . W^T) + bias)
+inline int gemm_planes(Ctx& c, const bf16* A, long long lda, long long a_plane_rows, int M, int N, int K, int wid, int bid, int act,
+                const float* row_scale, void* C, int cdt, long long ldc) {
+    GemmArgs a;
+    a.A = A; a.lda = lda; a.a_plane_rows = static_cast<int>(a_plane_rows); a.nplanes = c.np;
+    a.W = c.W(wid); a.ldw = align_up(K, 8); a.w_plane_rows = N;
+    a.bias = bid >= 0 ? c.Wf(bid) : nullptr; a.row_scale = row_scale;
+    a.C = C; a.ldc = ldc; a.out_dtype = cdt; a.M = M; a.N = N; a.K = K; a.act = act;
+    return launch_gemm(a, c.st);
+}
+
+// A = contiguous activation rows [M, K] (act dtype)
+inline int gemm_act(Ctx& c, const void* A, int M, int N, int K, int wid, int bid, int act, const float* row_scale, void* C, int cdt, long long ldc) {
+    if (c.np == 1) return gemm_planes(c, reinterpret_cast<const bf16*>(A), K, 0, M, N, K, wid, bid, act, row_scale, C, cdt, ldc);
+    if (M > c.plan.PR) return STAIR_ERR_CAPACITY;
+    bf16* pl = c.at<bf16>(c.plan.pl);
+    STAIR_TRY(launch_stage_rows(STAIR_F32, A, K, nullptr, 1, 1, pl, K, M, 3, M, K, c.st));
+    return gemm_planes(c, pl, K, M, M, N, K, wid, bid, act, row_scale, C, cdt, ldc);
+}
+
+// A = frame rows of n VID slots gathered from the arena (TMA gather when possible, staging copy otherwise)
+inline int gemm_vid(Ctx& c, const int* slots, int n, int N, int wid, int bid, int act, const float* row_scale, void* C, int cdt, long long ldc) {
+    const int M = n * c.T, K = c.H;
+    if (c.np == 1 && gemm_gather_ok(c.T)) {
+        GemmArgs a;
+        a.A = c.buf.vid; a.lda = K; a.arena_slots = c.buf.vid_slots; a.a_slots = slots; a.slot_rows = c.T;
+        a.W = c.W(wid); a.ldw = K; a.w_plane_rows = N; a.bias = bid >= 0 ? c.Wf(bid) : nullptr; a.row_scale = row_scale;
+        a.C = C; a.ldc = ldc; a.out_dtype = cdt; a.M = M; a.N = N; a.K = K; a.act = act;
+        return launch_gemm(a, c.st);
+    }
+    if (M > c.plan.PR) return STAIR_ERR_CAPACITY;
+    bf16* pl = c.at<bf16>(c.plan.pl);
+    STAIR_TRY(launch_stage_rows(c.adt, c.buf.vid, K, slots, c.T, c.T, pl, K, M, c.np, M, K, c.st));
+    return gemm_planes(c, pl, K, M, M, N, K, wid, bid, act, row_scale, C, cdt, ldc);
+}
+
+// A = gathered VEC rows (rps consecutive rows per index)
+inline int gemm_vec_rows(Ctx& c, const int* idx, int rps, int n, int N, int wid, int bid, int act, void* C, int cdt, long long ldc) {
+    const int M = n * rps, K = c.H;
+    if (M > c.plan.PR) return STAIR_ERR_CAPACITY;
+    bf16* pl = c.at<bf16>(c.plan.pl);
+    STAIR_TRY(launch_stage_rows(c.adt, c.buf.vec, K, idx, rps, 1, pl, K, M, c.np, M, K, c.st));
+    return gemm_planes(c, pl, K, M, M, N, K, wid, bid, act, nullptr, C, cdt, ldc);
+}
+
+// ---- encoders (module_net.py:147-163) --------------------------------------------------------------------------
+inline int run_encoders(Ctx& c, int phases) {
+    const StairModel& m = c.m; const StairBatch& b = c.b;
+    const int B = b.B, T = c.T, H = c.H, h = c.h;
+    const long long rows_v = static_cast<long long>(B) * T;
+    if (rows_v * 1 > 0x7fffffffLL || static_cast<long long>(b.n_tok) > 0x7fffffffLL) return STAIR_ERR_CAPACITY;
+    float* g = c.at<float>(c.plan.g);
+    float* cs = c.at<float>(c.plan.c);
+    bf16* hs = c.at<bf16>(c.plan.hs);
+    // video input projection: [B*T, V] x [V, 8h] for both directions at once
+    if (phases & STAIR_FWD_ENCODE_VIDEO) {
+        const bf16* A; long long lda, apr;
+        const bool direct = b.video_dtype == STAIR_BF16 && c.np == 1 && (m.V % 8) == 0;
+        if (direct) { A = reinterpret_cast<const bf16*>(b.video); lda = m.V; apr = 0; }
+        else {
+            bf16* in = c.at<bf16>(c.plan.xv_in);
+            STAIR_TRY(launch_stage_rows(b.video_dtype, b.video, m.V, nullptr, 1, 1, in, m.V_ld, rows_v, c.np, rows_v, m.V, c.st));
+            A = in; lda = m.V_ld; apr = rows_v;
+        }
+        GemmArgs a;
+        a.A = A; a.lda = lda; a.a_plane_rows = static_cast<int>(apr); a.nplanes = c.np; a.W = c.W(STAIR_W_VENC_WIH); a.ldw = m.V_ld;
+        a.w_plane_rows = 4 * H; a.bias = c.Wf(STAIR_W_VENC_B); a.C = c.at<void>(c.plan.xv); a.ldc = 4 * H; a.out_dtype = c.adt;
+        a.M = static_cast<int>(rows_v); a.N = 4 * H; a.K = m.V;
+        STAIR_TRY(launch_gemm(a, c.st));
+    }
+    const bool fused = lstm_fused_ok(m.precision, h) && g_lstm_impl == 0 && c.W(STAIR_W_VENC_WHHI_F) && c.W(STAIR_W_TENC_WHHI_F);
+    if ((phases & STAIR_FWD_ENCODE_VIDEO) && !fused) {
+    if (cudaMemsetAsync(cs, 0, sizeof(float) * 2 * B * h, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
+    for (int s = 0; s < T; ++s) {
+        if (s > 0)
+            for (int d = 0; d < 2; ++d)
+                STAIR_TRY(gemm_planes(c, hs + static_cast<long long>(d) * B * h, h, 2LL * B, B, 4 * h, h,
+                                      d == 0 ? STAIR_W_VENC_WHH_F : STAIR_W_VENC_WHH_R, -1, STAIR_ACT_NONE, nullptr,
+                                      g + static_cast<long long>(d) * B * 4 * h, STAIR_F32, 4 * h));
+        STAIR_TRY(launch_lstm_cell_video(c.adt, c.at<void>(c.plan.xv), g, cs, hs, c.np, c.adt, c.buf.vid, B, T, h, s, c.st));
+    }
+    }
+    if (!(phases & STAIR_FWD_ENCODE_TEXT)) {
+        if (fused && (phases & STAIR_FWD_ENCODE_VIDEO))
+            return launch_lstm_fused(c.at<void>(c.plan.xv), c.buf.vid, T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R), nullptr,
+                                     nullptr, nullptr, nullptr, 0, nullptr, nullptr, cs, B, h, 1, 0, err_flag_ptr(), c.st);
+        return STAIR_OK;
+    }
+    // text input projection over the packed tokens of all questions
+    {
+        bf16* in = c.at<bf16>(c.plan.xq_in);
+        STAIR_TRY(launch_stage_rows(b.question_dtype, b.question, m.text_size, nullptr, 1, 1, in, m.text_ld, b.n_tok, c.np, b.n_tok,
+                                    m.text_size, c.st));
+        GemmArgs a;
+        a.A = in; a.lda = m.text_ld; a.a_plane_rows = b.n_tok; a.nplanes = c.np; a.W = c.W(STAIR_W_TENC_WIH); a.ldw = m.text_ld;
+        a.w_plane_rows = 4 * H; a.bias = c.Wf(STAIR_W_TENC_B); a.C = c.at<void>(c.plan.xq); a.ldc = 4 * H; a.out_dtype = c.adt;
+        a.M = b.n_tok; a.N = 4 * H; a.K = m.text_size;
+        STAIR_TRY(launch_gemm(a, c.st));
+    }
+    if (fused)
+        return launch_lstm_fused(c.at<void>(c.plan.xv), c.buf.vid, T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R),
+                                 c.at<void>(c.plan.xq), c.buf.tokfeat, c.buf.qfeat, b.q_off, b.L_max, c.W(STAIR_W_TENC_WHHI_F),
+                                 c.W(STAIR_W_TENC_WHHI_R), cs, B, h, (phases & STAIR_FWD_ENCODE_VIDEO) ? 1 : 0, 1, err_flag_ptr(), c.st);
+    if (cudaMemsetAsync(cs, 0, sizeof(float) * 2 * B * h, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
+    for (int s = 0; s < b.L_max; ++s) {
+        if (s > 0)
+            for (int d = 0; d < 2; ++d)
+                STAIR_TRY(gemm_planes(c, hs + static_cast<long long>(d) * B * h, h, 2LL * B, B, 4 * h, h,
+                                      d == 0 ? STAIR_W_TENC_WHH_F : STAIR_W_TENC_WHH_R, -1, STAIR_ACT_NONE, nullptr,
+                                      g + static_cast<long long>(d) * B * 4 * h, STAIR_F32, 4 * h));
+        STAIR_TRY(launch_lstm_cell_text(c.adt, c.at<void>(c.plan.xq), g, cs, hs, c.np, c.adt, c.buf.tokfeat, c.buf.qfeat, b.q_off, B, h, s, c.st));
+    }
+    return STAIR_OK;
+}
+
+// ---- one chunk of one group --------------------------------------------------------------------------------------
+// p = sorted position of the chunk's first instance, n = instances, ob = first output index, ab = first aux index
+inline int run_chunk(Ctx& c, const StairGroup& g, int p, int n, int ob, int ab) {
+    const int T = c.T, H = c.H, dt = c.adt;
+    const int *a0 = c.arg0 + p, *a1 = c.arg1 + p, *a2 = c.arg2 + p;
+    void* S0 = c.at<void>(c.plan.s0); void* S1 = c.at<void>(c.plan.s1); void* S2 = c.at<void>(c.plan.s2);
+    bf16* VP = c.at<bf16>(c.plan.vp);
+    void* V0 = c.at<void>(c.plan.v01);
+    float* att = c.buf.att;
+    void* vid_out = c.act_ptr(c.buf.vid, static_cast<long long>(ob) * T * H);
+    void* vec_out = c.act_ptr(c.buf.vec, static_cast<long long>(ob) * H);
+    switch (g.op) {
+    case STAIR_OP_WORD:
+        return launch_word_embed(dt, c.buf.tokfeat, c.b.q_off, c.pos_q + p, c.span_s + p, c.span_e + p, c.buf.vec, ob, n, H, c.st);
+    case STAIR_OP_LOCALIZE: {                                   // modules.py:194-217; variant = K-1
+        const int K = g.variant + 1;
+        STAIR_TRY(gemm_vid(c, a0, n, H, STAIR_W_LOC_V0_W, STAIR_W_LOC_V0_B, STAIR_ACT_RELU, nullptr, S0, dt, H));
+        STAIR_TRY(gemm_act(c, S0, n * T, H, H, STAIR_W_LOC_V1_W, STAIR_W_LOC_V1_B, STAIR_ACT_NONE, nullptr, S1, dt, H));
+        STAIR_TRY(gemm_vec_rows(c, a1, K, n, H, STAIR_W_LOC_K_W, STAIR_W_LOC_K_B, STAIR_ACT_NONE, S2, dt, H));
+        return launch_cos_att(dt, S1, S2, K, T, H, att, ob, n, c.st);
+    }
+    case STAIR_OP_TEMPORAL: {                                   // modules.py:310-327; variant = mode*2 + (K-1)
+        const int mode = g.variant >> 1, K = (g.variant & 1) + 1;
+        const float* params[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (mode > 0) for (int j = 0; j < 6; ++j) params[j] = c.Wf(STAIR_W_TEMP_REL_BEFORE + 6 * (mode - 1) + j);
+        STAIR_TRY(launch_temporal_relate(att, a1, K, mode, c.m.conv_k, params, att, ab, n, T, c.st));
+        // dense(r[t] * feat[t]) = relu(r[t] * (W feat[t]) + b): the gate is the GEMM's row scale
+        STAIR_TRY(gemm_vid(c, a0, n, H, STAIR_W_TEMP_D_W, STAIR_W_TEMP_D_B, STAIR_ACT_RELU, att + static_cast<long long>(ab) * T, S0, dt, H));
+        return launch_layernorm(dt, S0, c.Wf(STAIR_W_TEMP_LN_G), c.Wf(STAIR_W_TEMP_LN_B), vid_out, static_cast<long long>(n) * T, H, c.st);
+    }
+    case STAIR_OP_FILTER: {                                     // modules.py:361-378; variant 0 repr,1 actions,2 objects,3 relations
+        const int w = STAIR_W_FILT_REPR + 4 * g.variant;
+        STAIR_TRY(gemm_vid(c, a0, n, H, w, w + 1, STAIR_ACT_RELU, nullptr, S0, dt, H));
+        STAIR_TRY(gemm_act(c, S0, n * T, H, H, w + 2, w + 3, STAIR_ACT_RELU, nullptr, S1, dt, H));
+        // tensor keyword: nn.Softmax() over a size-1 dim makes the attention exactly 1.0 -> plain sum over frames
+        STAIR_TRY(launch_sum_T(dt, S1, S2, n, T, H, c.st));
+        STAIR_TRY(gemm_act(c, S2, n, H, H, STAIR_W_FILT_D_W, STAIR_W_FILT_D_B, STAIR_ACT_RELU, nullptr, vec_out, dt, H));
+        if (g.head) return launch_l2norm(dt, c.buf.vec, ob, c.buf.head_vec, ab, n, H, c.st);
+        return STAIR_OK;
+    }
+    case STAIR_OP_FILTERFRAME: {                                // modules.py:398-414; variant 0 repr,1 relations,2 actions
+        const int w = STAIR_W_FF_REPR + 4 * g.variant;
+        STAIR_TRY(gemm_vid(c, a0, n, H, w, w + 1, STAIR_ACT_RELU, nullptr, S0, dt, H));
+        STAIR_TRY(gemm_act(c, S0, n * T, H, H, w + 2, w + 3, STAIR_ACT_RELU, nullptr, S1, dt, H));
+        const float* gate = nullptr;
+        if (g.variant == 0) {
+            float* A0 = c.at<float>(c.plan.a0);
+            STAIR_TRY(launch_ff_attn(dt, S1, c.buf.vec, a1, c.Wf(STAIR_W_FF_ATT_W), c.Wf(STAIR_W_FF_ATT_B), A0, n, T, H, c.st));
+            gate = A0;      // dense(a[t] * x[t]) = relu(a[t] * (W x[t]) + b)
+        }
+        STAIR_TRY(gemm_act(c, S1, n * T, H, H, STAIR_W_FF_D_W, STAIR_W_FF_D_B, STAIR_ACT_RELU, gate, vid_out, dt, H));
+        if (g.head)
+            return gemm_act(c, vid_out, n * T, c.m.O, H, STAIR_W_FF_HEAD_W, STAIR_W_FF_HEAD_B, STAIR_ACT_NONE, nullptr,
+                            c.buf.head_ff + static_cast<long long>(ab) * T * c.m.O, STAIR_F32, c.m.O);
+        return STAIR_OK;
+    }
+    case STAIR_OP_HASITEM:                                      // modules.py:131-138
+        STAIR_TRY(gemm_vid(c, a0, n, H, STAIR_W_HAS0_W, STAIR_W_HAS0_B, STAIR_ACT_RELU, nullptr, S0, dt, H));
+        return launch_rowdot_sigmoid(dt, S0, c.Wf(STAIR_W_HAS1_W), c.Wf(STAIR_W_HAS1_B), att, ob, n, T, H, c.st);
+    case STAIR_OP_EXISTSFRAME:                                  // (keyword, feat) modules.py:169-178
+        return launch_existsframe(dt, c.buf.vid, a1, c.buf.vec, a0, att, ob, n, T, H, c.st);
+    case STAIR_OP_RELATE:                                       // variant 0 forward, 1 backward; modules.py:423-435
+        return launch_relate(att, a0, c.Wf(STAIR_W_REL_BETA), g.variant == 0 ? 1 : -1, att, ob, n, T, c.st);
+    case STAIR_OP_ATTNVIDEO:
+        return launch_attnvideo(dt, c.buf.vid, a0, att, a1, ob, n, T, H, c.st);
+    case STAIR_OP_AND:
+    case STAIR_OP_XORFRAME: {                                   // variant 0: VEC rows, 1: [T] maps, 2: [2,T] maps
+        const int op = g.op == STAIR_OP_AND ? STAIR_BIN_MIN : STAIR_BIN_ABSDIFF;
+        if (g.variant == 0) return launch_binary(dt, c.buf.vec, a0, a1, ob, H, H, op, n, c.st);
+        return launch_binary(STAIR_F32, att, a0, a1, ob, T, g.variant * T, op, n, c.st);
+    }
+    case STAIR_OP_CHOOSE:
+        return launch_choose(dt, c.buf.vec, a0, a1, a2, ob, n, H, c.st);
+    case STAIR_OP_ARRAY2:
+        return launch_array2(dt, c.buf.vec, a0, a1, ob, n, H, c.st);
+    case STAIR_OP_COMPARE:
+    case STAIR_OP_EQUALS: {                                     // modules.py:15-37
+        const bool eq = g.op == STAIR_OP_EQUALS;
+        STAIR_TRY(launch_concat_vec(dt, c.buf.vec, a0, a1, STAIR_CAT_PAIR, VP, n, c.np, n, H, c.st));
+        STAIR_TRY(gemm_planes(c, VP, 2 * H, n, n, H, 2 * H, eq ? STAIR_W_EQUALS_W : STAIR_W_COMPARE_W, eq ? STAIR_W_EQUALS_B : STAIR_W_COMPARE_B,
+                              STAIR_ACT_RELU, nullptr, vec_out, dt, H));
+        if (eq && g.head)
+            return launch_small_head(dt, c.buf.vec, ob, c.Wf(STAIR_W_EQUALS_HEAD_W), c.Wf(STAIR_W_EQUALS_HEAD_B), 1, c.buf.head_small, ab, n, H, c.st);
+        return STAIR_OK;
+    }
+    case STAIR_OP_XOR:                                          // modules.py:59-72
+        STAIR_TRY(launch_concat_vec(dt, c.buf.vec, a0, a1, STAIR_CAT_XOR, VP, n, c.np, n, H, c.st));
+        STAIR_TRY(gemm_planes(c, VP, 3 * H, n, n, H, 3 * H, STAIR_W_XOR_W, STAIR_W_XOR_B, STAIR_ACT_RELU, nullptr, vec_out, dt, H));
+        if (g.head) return launch_small_head(dt, c.buf.vec, ob, c.Wf(STAIR_W_XOR_HEAD_W), c.Wf(STAIR_W_XOR_HEAD_B), 2, c.buf.head_small, ab, n, H, c.st);
+        return STAIR_OK;
+    case STAIR_OP_EXISTS:                                       // (keyword, feat) modules.py:141-159
+        STAIR_TRY(launch_concat_vec(dt, c.buf.vec, a0, a1, STAIR_CAT_EXISTS, VP, n, c.np, n, H, c.st));
+        STAIR_TRY(gemm_planes(c, VP, 3 * H, n, n, H, 3 * H, STAIR_W_EXISTS0_W, STAIR_W_EXISTS0_B, STAIR_ACT_RELU, nullptr, V0, dt, H));
+        STAIR_TRY(gemm_act(c, V0, n, H, H, STAIR_W_EXISTS1_W, STAIR_W_EXISTS1_B, STAIR_ACT_RELU, nullptr, vec_out, dt, H));
+        if (g.head) return launch_small_head(dt, c.buf.vec, ob, c.Wf(STAIR_W_EXISTS_HEAD_W), c.Wf(STAIR_W_EXISTS_HEAD_B), 2, c.buf.head_small, ab, n, H, c.st);
+        return STAIR_OK;
+    case STAIR_OP_TOACTION:                                     // (action, keyword) modules.py:102-120
+        STAIR_TRY(launch_concat_vec(dt, c.buf.vec, a0, a1, STAIR_CAT_PAIR, VP, n, c.np, n, H, c.st));
+        STAIR_TRY(gemm_planes(c, VP, 2 * H, n, n, H, 2 * H, STAIR_W_TOACT0_W, STAIR_W_TOACT0_B, STAIR_ACT_RELU, nullptr, V0, dt, H));
+        STAIR_TRY(gemm_act(c, V0, n, H, H, STAIR_W_TOACT1_W, STAIR_W_TOACT1_B, STAIR_ACT_RELU, nullptr, vec_out, dt, H));
+        if (g.head) return launch_l2norm(dt, c.buf.vec, ob, c.buf.head_vec, ab, n, H, c.st);
+        return STAIR_OK;
+    case STAIR_OP_SUPERLATIVE: {                                // (mode, actions, feat) modules.py:233-248
+        // variant = is_min + 2*kind ; kind 0: one VEC action, 1: Array2 (two rows), 2: [T,H] frame features as T actions
+        const int is_min = g.variant & 1, kind = g.variant >> 1;
+        const int K = kind == 0 ? 1 : (kind == 1 ? 2 : T);
+        STAIR_TRY(gemm_vid(c, a1, n, H, STAIR_W_LOC_V0_W, STAIR_W_LOC_V0_B, STAIR_ACT_RELU, nullptr, S0, dt, H));
+        STAIR_TRY(gemm_act(c, S0, n * T, H, H, STAIR_W_LOC_V1_W, STAIR_W_LOC_V1_B, STAIR_ACT_NONE, nullptr, S1, dt, H));
+        if (kind == 2) STAIR_TRY(gemm_vid(c, a0, n, H, STAIR_W_LOC_K_W, STAIR_W_LOC_K_B, STAIR_ACT_NONE, nullptr, S2, dt, H));
+        else STAIR_TRY(gemm_vec_rows(c, a0, K, n, H, STAIR_W_LOC_K_W, STAIR_W_LOC_K_B, STAIR_ACT_NONE, S2, dt, H));
+        float* ats = c.at<float>(c.plan.ats);
+        STAIR_TRY(launch_cos_att(dt, S1, S2, K, T, H, ats, 0, n, c.st));
+        STAIR_TRY(launch_super_mix(dt, ats, K, T, H, is_min, kind == 2 ? c.buf.vid : c.buf.vec, a0, kind == 2 ? T : 1, V0, n, c.st));
+        STAIR_TRY(gemm_act(c, V0, n, H, H, STAIR_W_SUP_D_W, STAIR_W_SUP_D_B, STAIR_ACT_RELU, nullptr, vec_out, dt, H));
+        if (g.head) return launch_l2norm(dt, c.buf.vec, ob, c.buf.head_vec, ab, n, H, c.st);
+        return STAIR_OK;
+    }
+    default:
+        return STAIR_ERR_LAYOUT;
+    }
+}
+
+inline bool op_is_vid_sized(int op) {
+    switch (op) {
+    case STAIR_OP_LOCALIZE: case STAIR_OP_TEMPORAL: case STAIR_OP_FILTER: case STAIR_OP_FILTERFRAME: case STAIR_OP_HASITEM:
+    case STAIR_OP_SUPERLATIVE: case STAIR_OP_ATTNVIDEO: case STAIR_OP_EXISTSFRAME:
+        return true;
+    default:
+        return false;
+    }
+}
+
+inline int run_modules(Ctx& c) {
+    for (int gi = 0; gi < c.b.n_groups; ++gi) {
+        const StairGroup& g = c.b.groups[gi];
+        const int cap = op_is_vid_sized(g.op) ? c.plan.nc_vid : static_cast<int>(VEC_CAP);
+        for (int done = 0; done < g.count; done += cap) {
+            const int n = g.count - done < cap ? g.count - done : cap;
+            STAIR_TRY(run_chunk(c, g, g.node_off + done, n, g.out_base + done * g.out_mult, g.aux_base >= 0 ? g.aux_base + done : -1));
+        }
+    }
+    return STAIR_OK;
+}
+
+// decoder (module_net.py:135-138) + argmax (train_module.py:252)
+inline int run_decoder(Ctx& c) {
+    const int B = c.b.B, H = c.H, A = c.m.A;
+    bf16* VP = c.at<bf16>(c.plan.vp);
+    void* D0 = c.at<void>(c.plan.v01);
+    for (int done = 0; done < B; done += static_cast<int>(VEC_CAP)) {
+        const int n = B - done < VEC_CAP ? B - done : static_cast<int>(VEC_CAP);
+        STAIR_TRY(launch_decoder_concat(c.adt, c.buf.vec, c.b.root_node + done, c.out_slot,
+                                        c.act_ptr(c.buf.qfeat, static_cast<long long>(done) * H), VP, n, c.np, n, H, c.st));
+        STAIR_TRY(gemm_planes(c, VP, 2 * H, n, n, 2 * H, 2 * H, STAIR_W_DEC0_W, STAIR_W_DEC0_B, STAIR_ACT_RELU, nullptr, D0, c.adt, 2 * H));
+        if (c.np == 1) {
+            STAIR_TRY(gemm_planes(c, reinterpret_cast<const bf16*>(D0), 2 * H, 0, n, A, 2 * H, STAIR_W_DEC1_W, STAIR_W_DEC1_B, STAIR_ACT_NONE, nullptr,
+                                  c.buf.logits + static_cast<long long>(done) * A, STAIR_F32, A));
+        } else {
+            STAIR_TRY(launch_stage_rows(STAIR_F32, D0, 2 * H, nullptr, 1, 1, VP, 2 * H, n, 3, n, 2 * H, c.st));
+            STAIR_TRY(gemm_planes(c, VP, 2 * H, n, n, A, 2 * H, STAIR_W_DEC1_W, STAIR_W_DEC1_B, STAIR_ACT_NONE, nullptr,
+                                  c.buf.logits + static_cast<long long>(done) * A, STAIR_F32, A));
+        }
+    }
+    return launch_argmax(c.buf.logits, c.buf.answers, B, A, c.st);
+}
+
+
+}  // namespace ex
+}  // namespace stair

@@ -1,0 +1,560 @@
+// Training step of the batched interpreter: forward with encoder history, intermediate-supervision losses
+// (train_module.py:33-194, window logic :341-406) and the backward pass of every operator, encoder and the decoder.
+//
+// Design: module intermediates are NOT stored by the forward; the backward walks the groups in reverse schedule order and,
+// per group chunk, re-runs the group's forward (ex::run_chunk, a few GEMMs) into the forward scratch and then back-propagates
+// through it.  Every nn.Linear backward is two tcgen05 GEMMs (dX = dZ.W via the transposed weight copy, dW += dZ^T.X with
+// fp32 accumulation in the epilogue) fed by a staging kernel (ReLU mask, row-scale, bias gradient) and two bf16 transposes.
+// The LSTMs use BPTT over the saved gate / cell / state history; their weight gradients are two big GEMMs after the loop.
+// Gradients are fp32; GEMM operands are bf16 (1 plane) or bf16x3 planes (strict fp32 mode), like the forward.
+#include "exec_core.cuh"
+#include "train_kernels.cuh"
+
+namespace stair {
+namespace {
+
+using namespace ex;
+
+struct Bump {
+    char* base = nullptr;
+    long long cap = 0, off = 0, peak = 0;
+    bool dry = false, overflow = false;
+    template <typename P> P* take(long long count) {
+        off = align_up(off, 256);
+        const long long o = off;
+        off += count * static_cast<long long>(sizeof(P));
+        if (off > peak) peak = off;
+        if (!dry && off > cap) overflow = true;
+        return reinterpret_cast<P*>(base + o);
+    }
+};
+
+struct BCtx {
+    Ctx& c;
+    const StairTrain& tr;
+    Bump ws;
+    bool dry;
+};
+
+#define RUN(expr) do { if (!b.dry) { if (b.ws.overflow) return STAIR_ERR_CAPACITY; int rc__ = (expr); if (rc__ != STAIR_OK) return rc__; } } while (0)
+
+inline float* G(BCtx& b, int id) { return id >= 0 ? b.tr.grad[id] : nullptr; }
+
+// ---- saved encoder history ------------------------------------------------------------------------------------------------
+struct EncSaved { long long gates, c, hs; int S; };          // byte offsets into StairTrain.saved
+struct SavedLayout { EncSaved enc[2]; long long total; };
+
+SavedLayout saved_layout(const StairModel& m, const StairBatch& b) {
+    const long long np = m.precision == STAIR_F32 ? 3 : 1, B = b.B, h = m.H / 2;
+    SavedLayout L;
+    long long o = 0;
+    for (int e = 0; e < 2; ++e) {
+        const long long S = e == 0 ? b.T : b.L_max;
+        L.enc[e].S = static_cast<int>(S);
+        L.enc[e].gates = o; o = align_up(o + S * 2 * B * 4 * h * 4, 1024);
+        L.enc[e].c = o; o = align_up(o + S * 2 * B * h * 4, 1024);
+        L.enc[e].hs = o; o = align_up(o + np * 2 * (S + 1) * B * h * 2, 1024);
+    }
+    L.total = o;
+    return L;
+}
+
+// ---- staging helpers ------------------------------------------------------------------------------------------------------------
+bf16* stage_act(BCtx& b, const void* A, int sdt, int M, int K, int* rc) {
+    Ctx& c = b.c;
+    const long long kld = align_up(K, 8);
+    bf16* p = b.ws.take<bf16>(static_cast<long long>(c.np) * M * kld);
+    if (!b.dry && !b.ws.overflow) *rc = launch_stage_rows(sdt, A, K, nullptr, 1, 1, p, kld, M, c.np, M, K, c.st);
+    return p;
+}
+bf16* stage_gather(BCtx& b, const void* base, int sdt, const int* idx, int rps, int unit, int n, int K, int* rc) {
+    Ctx& c = b.c;
+    const long long M = static_cast<long long>(n) * rps;
+    bf16* p = b.ws.take<bf16>(static_cast<long long>(c.np) * M * K);
+    if (!b.dry && !b.ws.overflow) *rc = launch_stage_rows(sdt, base, K, idx, rps, unit, p, K, M, c.np, M, K, c.st);
+    return p;
+}
+
+// Linear backward.  dY fp32 [M,N]; Y = post-activation output (ReLU mask) or null; rs = row scale or null;
+// Xp = layer input as bf16 planes [np][x_plane_rows, K_ld].  dX (fp32 [M,K]) receives dZ.W WITHOUT the row scale.
+int linear_bwd(BCtx& b, const float* dY, long long ld_dy, const void* Y, long long ld_y, const float* rs, const bf16* Xp,
+               long long x_plane_rows, int M, int N, int K, int wid, int bid, float* dX) {
+    Ctx& c = b.c;
+    if (M <= 0) return STAIR_OK;
+    const long long mark = b.ws.off;
+    const long long n_ld = align_up(N, 8), k_ld = align_up(K, 8), m_ld = align_up(M, 8);
+    bf16* dZ = b.ws.take<bf16>(c.np * static_cast<long long>(M) * n_ld);
+    bf16* dZs = rs ? b.ws.take<bf16>(c.np * static_cast<long long>(M) * n_ld) : dZ;
+    RUN(launch_dz_prep(c.adt, dY, ld_dy, Y, ld_y, rs, dZ, dZs, n_ld, M, c.np, G(b, bid), M, N, c.st));
+    float* gW = G(b, wid);
+    if (gW) {
+        bf16* dZt = b.ws.take<bf16>(c.np * static_cast<long long>(N) * m_ld);
+        bf16* Xt = b.ws.take<bf16>(c.np * static_cast<long long>(K) * m_ld);
+        RUN(launch_transpose_planes(dZs, n_ld, M, dZt, m_ld, N, c.np, M, N, c.st));
+        RUN(launch_transpose_planes(Xp, k_ld, x_plane_rows, Xt, m_ld, K, c.np, M, K, c.st));
+        GemmArgs a;
+        a.A = dZt; a.lda = m_ld; a.a_plane_rows = N; a.W = Xt; a.ldw = m_ld; a.w_plane_rows = K; a.nplanes = c.np;
+        a.C = gW; a.ldc = K; a.out_dtype = STAIR_F32; a.M = N; a.N = K; a.K = M; a.accumulate = 1;
+        RUN(launch_gemm(a, c.st));
+    }
+    if (dX) {
+        if (!c.m.wt[wid]) return STAIR_ERR_ARG;
+        GemmArgs a;
+        a.A = dZ; a.lda = n_ld; a.a_plane_rows = M; a.W = c.m.wt[wid]; a.ldw = n_ld; a.w_plane_rows = K; a.nplanes = c.np;
+        a.C = dX; a.ldc = K; a.out_dtype = STAIR_F32; a.M = M; a.N = K; a.K = N;
+        RUN(launch_gemm(a, c.st));
+    }
+    b.ws.off = mark;
+    return STAIR_OK;
+}
+
+#define STAGE_ACT(var, ptr, sdt, M, K) bf16* var; { int rc__ = STAIR_OK; var = stage_act(b, ptr, sdt, M, K, &rc__); if (rc__) return rc__; }
+#define STAGE_GATHER(var, base, sdt, idx, rps, unit, n, K) bf16* var; { int rc__ = STAIR_OK; var = stage_gather(b, base, sdt, idx, rps, unit, n, K, &rc__); if (rc__) return rc__; }
+
+// x = relu(W2 relu(W1 feat + b1) + b2) backward given dx (grad wrt S1); S0/S1 are the recomputed activations
+int mlp2_bwd(BCtx& b, float* dx, const void* S0, const void* S1, const int* feat_slots, int n, int w) {
+    Ctx& c = b.c;
+    const int T = c.T, H = c.H, M = n * T;
+    const long long mark = b.ws.off;
+    float* dS0 = b.ws.take<float>(static_cast<long long>(M) * H);
+    STAGE_ACT(s0p, S0, c.adt, M, H);
+    STAIR_TRY(linear_bwd(b, dx, H, S1, H, nullptr, s0p, M, M, H, H, w + 2, w + 3, dS0));
+    float* dF = b.ws.take<float>(static_cast<long long>(M) * H);
+    STAGE_GATHER(fp, c.buf.vid, c.adt, feat_slots, T, T, n, H);
+    STAIR_TRY(linear_bwd(b, dS0, H, S0, H, nullptr, fp, M, M, H, H, w, w + 1, dF));
+    RUN(launch_scatter_add_rows(dF, feat_slots, T, T, b.tr.dvid, M, H, c.st));
+    b.ws.off = mark;
+    return STAIR_OK;
+}
+
+// Localize body backward (shared with Superlative): df/dk from the cosine map -> video_linear, keyword_linear
+int localize_bwd(BCtx& b, const float* datt, long long att_base, const void* S0, const void* S1, const void* S2, const int* feat_slots,
+                 const void* kw_base, float* dkw_base, const int* kw_idx, int kw_rps, int kw_unit, int K, int n) {
+    Ctx& c = b.c;
+    const int T = c.T, H = c.H, M = n * T;
+    const long long mark = b.ws.off;
+    float* df = b.ws.take<float>(static_cast<long long>(M) * H);
+    float* dk = b.ws.take<float>(static_cast<long long>(n) * K * H);
+    RUN(launch_cos_att_bwd(c.adt, S1, S2, K, T, H, datt, att_base, df, dk, n, c.st));
+    float* dS0 = b.ws.take<float>(static_cast<long long>(M) * H);
+    STAGE_ACT(s0p, S0, c.adt, M, H);
+    STAIR_TRY(linear_bwd(b, df, H, nullptr, 0, nullptr, s0p, M, M, H, H, STAIR_W_LOC_V1_W, STAIR_W_LOC_V1_B, dS0));
+    float* dF = b.ws.take<float>(static_cast<long long>(M) * H);
+    STAGE_GATHER(fp, c.buf.vid, c.adt, feat_slots, T, T, n, H);
+    STAIR_TRY(linear_bwd(b, dS0, H, S0, H, nullptr, fp, M, M, H, H, STAIR_W_LOC_V0_W, STAIR_W_LOC_V0_B, dF));
+    RUN(launch_scatter_add_rows(dF, feat_slots, T, T, b.tr.dvid, M, H, c.st));
+    float* dKW = b.ws.take<float>(static_cast<long long>(n) * K * H);
+    STAGE_GATHER(kp, kw_base, c.adt, kw_idx, kw_rps, kw_unit, n, H);
+    STAIR_TRY(linear_bwd(b, dk, H, nullptr, 0, nullptr, kp, static_cast<long long>(n) * K, n * K, H, H, STAIR_W_LOC_K_W, STAIR_W_LOC_K_B, dKW));
+    RUN(launch_scatter_add_rows(dKW, kw_idx, kw_rps, kw_unit, dkw_base, static_cast<long long>(n) * K, H, c.st));
+    b.ws.off = mark;
+    return STAIR_OK;
+}
+
+// backward of one group chunk; the chunk's forward has just been recomputed into the forward scratch (c.plan)
+int chunk_bwd(BCtx& b, const StairGroup& g, int p, int n, int ob, int ab) {
+    Ctx& c = b.c;
+    const StairTrain& tr = b.tr;
+    const int T = c.T, H = c.H, dt = c.adt;
+    const int *a0 = c.arg0 + p, *a1 = c.arg1 + p, *a2 = c.arg2 + p;
+    void* S0 = c.at<void>(c.plan.s0); void* S1 = c.at<void>(c.plan.s1); void* S2 = c.at<void>(c.plan.s2);
+    bf16* VP = c.at<bf16>(c.plan.vp);
+    void* V0 = c.at<void>(c.plan.v01);
+    float* att = c.buf.att;
+    void* vid_out = c.act_ptr(c.buf.vid, static_cast<long long>(ob) * T * H);
+    void* vec_out = c.act_ptr(c.buf.vec, static_cast<long long>(ob) * H);
+    float* dvid_out = tr.dvid + static_cast<long long>(ob) * T * H;
+    float* dvec_out = tr.dvec + static_cast<long long>(ob) * H;
+    float* datt_out = tr.datt + static_cast<long long>(ob) * T;
+    const long long mark = b.ws.off;
+    const int M = n * T;
+    switch (g.op) {
+    case STAIR_OP_WORD:
+        RUN(launch_word_embed_bwd(tr.dvec, ob, c.b.q_off, c.pos_q + p, c.span_s + p, c.span_e + p, tr.dtokfeat, n, H, c.st));
+        break;
+    case STAIR_OP_LOCALIZE:
+        STAIR_TRY(localize_bwd(b, tr.datt, ob, S0, S1, S2, a0, c.buf.vec, tr.dvec, a1, g.variant + 1, 1, g.variant + 1, n));
+        break;
+    case STAIR_OP_TEMPORAL: {
+        const int mode = g.variant >> 1, K = (g.variant & 1) + 1;
+        const float* r = att + static_cast<long long>(ab) * T;
+        float* dr = tr.datt + static_cast<long long>(ab) * T;
+        float* dS0 = b.ws.take<float>(static_cast<long long>(M) * H);
+        RUN(launch_layernorm_bwd(dt, dvid_out, S0, c.Wf(STAIR_W_TEMP_LN_G), dS0, G(b, STAIR_W_TEMP_LN_G), G(b, STAIR_W_TEMP_LN_B), M, H, c.st));
+        float* Gx = b.ws.take<float>(static_cast<long long>(M) * H);
+        STAGE_GATHER(fp, c.buf.vid, dt, a0, T, T, n, H);
+        STAIR_TRY(linear_bwd(b, dS0, H, S0, H, r, fp, M, M, H, H, STAIR_W_TEMP_D_W, STAIR_W_TEMP_D_B, Gx));
+        RUN(launch_rowscale_bwd(dt, Gx, c.buf.vid, a0, T, T, r, dr, M, H, c.st));
+        RUN(launch_scatter_add_rows(Gx, a0, T, T, tr.dvid, M, H, c.st));
+        const float* params[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        float* dparams[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (mode > 0) for (int j = 0; j < 6; ++j) { params[j] = c.Wf(STAIR_W_TEMP_REL_BEFORE + 6 * (mode - 1) + j); dparams[j] = G(b, STAIR_W_TEMP_REL_BEFORE + 6 * (mode - 1) + j); }
+        RUN(launch_temporal_relate_bwd(att, a1, K, mode, c.m.conv_k, params, dparams, dr, tr.datt, n, T, c.st));
+        break;
+    }
+    case STAIR_OP_FILTER: {
+        const int w = STAIR_W_FILT_REPR + 4 * g.variant;
+        float* dAgg = b.ws.take<float>(static_cast<long long>(n) * H);
+        STAGE_ACT(aggp, S2, dt, n, H);
+        STAIR_TRY(linear_bwd(b, dvec_out, H, vec_out, H, nullptr, aggp, n, n, H, H, STAIR_W_FILT_D_W, STAIR_W_FILT_D_B, dAgg));
+        float* dx = b.ws.take<float>(static_cast<long long>(M) * H);
+        RUN(launch_bcast_T(dAgg, dx, n, T, H, c.st));
+        STAIR_TRY(mlp2_bwd(b, dx, S0, S1, a0, n, w));
+        break;
+    }
+    case STAIR_OP_FILTERFRAME: {
+        const int w = STAIR_W_FF_REPR + 4 * g.variant;
+        const float* gate = g.variant == 0 ? c.at<float>(c.plan.a0) : nullptr;
+        float* Gx = b.ws.take<float>(static_cast<long long>(M) * H);
+        STAGE_ACT(xp, S1, dt, M, H);
+        STAIR_TRY(linear_bwd(b, dvid_out, H, vid_out, H, gate, xp, M, M, H, H, STAIR_W_FF_D_W, STAIR_W_FF_D_B, Gx));
+        if (gate) {
+            float* da = b.ws.take<float>(M);
+            if (!b.dry && cudaMemsetAsync(da, 0, sizeof(float) * M, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
+            RUN(launch_rowscale_bwd(dt, Gx, S1, nullptr, 1, 1, gate, da, M, H, c.st));
+            RUN(launch_ff_attn_bwd(dt, S1, c.buf.vec, a1, c.Wf(STAIR_W_FF_ATT_W), gate, da, Gx, tr.dvec, G(b, STAIR_W_FF_ATT_W), G(b, STAIR_W_FF_ATT_B), n, T, H, c.st));
+        }
+        STAIR_TRY(mlp2_bwd(b, Gx, S0, S1, a0, n, w));
+        break;
+    }
+    case STAIR_OP_HASITEM: {
+        float* dS0 = b.ws.take<float>(static_cast<long long>(M) * H);
+        RUN(launch_rowdot_sigmoid_bwd(dt, S0, c.Wf(STAIR_W_HAS1_W), att + static_cast<long long>(ob) * T, datt_out, dS0, G(b, STAIR_W_HAS1_W), G(b, STAIR_W_HAS1_B), M, H, c.st));
+        float* dF = b.ws.take<float>(static_cast<long long>(M) * H);
+        STAGE_GATHER(fp, c.buf.vid, dt, a0, T, T, n, H);
+        STAIR_TRY(linear_bwd(b, dS0, H, S0, H, nullptr, fp, M, M, H, H, STAIR_W_HAS0_W, STAIR_W_HAS0_B, dF));
+        RUN(launch_scatter_add_rows(dF, a0, T, T, tr.dvid, M, H, c.st));
+        break;
+    }
+    case STAIR_OP_EXISTSFRAME:
+        RUN(launch_existsframe_bwd(dt, c.buf.vid, a1, c.buf.vec, a0, tr.datt, ob, tr.dvid, tr.dvec, n, T, H, c.st));
+        break;
+    case STAIR_OP_RELATE:
+        RUN(launch_relate_bwd(att, ob, tr.datt, a0, g.variant == 0 ? 1 : -1, tr.datt, G(b, STAIR_W_REL_BETA), n, T, c.st));
+        break;
+    case STAIR_OP_ATTNVIDEO:
+        RUN(launch_attnvideo_bwd(dt, dvid_out, c.buf.vid, a0, att, a1, tr.datt, tr.dvid, n, T, H, c.st));
+        break;
+    case STAIR_OP_AND:
+    case STAIR_OP_XORFRAME: {
+        const int op = g.op == STAIR_OP_AND ? STAIR_BIN_MIN : STAIR_BIN_ABSDIFF;
+        if (g.variant == 0) RUN(launch_binary_bwd(dt, c.buf.vec, a0, a1, dvec_out, tr.dvec, H, H, op, n, c.st));
+        else RUN(launch_binary_bwd(STAIR_F32, att, a0, a1, datt_out, tr.datt, T, g.variant * T, op, n, c.st));
+        break;
+    }
+    case STAIR_OP_CHOOSE:
+        RUN(launch_choose_bwd(dt, c.buf.vec, a0, a1, a2, dvec_out, tr.dvec, n, H, c.st));
+        break;
+    case STAIR_OP_ARRAY2:
+        RUN(launch_array2_bwd(dvec_out, a0, a1, tr.dvec, n, H, c.st));
+        break;
+    case STAIR_OP_COMPARE:
+    case STAIR_OP_EQUALS:
+    case STAIR_OP_XOR: {
+        const int mode = g.op == STAIR_OP_XOR ? STAIR_CAT_XOR : STAIR_CAT_PAIR;
+        const int Kc = (mode == STAIR_CAT_XOR ? 3 : 2) * H;
+        const int wid = g.op == STAIR_OP_XOR ? STAIR_W_XOR_W : (g.op == STAIR_OP_EQUALS ? STAIR_W_EQUALS_W : STAIR_W_COMPARE_W);
+        float* dcat = b.ws.take<float>(static_cast<long long>(n) * Kc);
+        STAIR_TRY(linear_bwd(b, dvec_out, H, vec_out, H, nullptr, VP, n, n, H, Kc, wid, wid + 1, dcat));
+        RUN(launch_concat_bwd(dt, c.buf.vec, a0, a1, mode, dcat, tr.dvec, n, H, c.st));
+        break;
+    }
+    case STAIR_OP_EXISTS:
+    case STAIR_OP_TOACTION: {
+        const bool ex = g.op == STAIR_OP_EXISTS;
+        const int mode = ex ? STAIR_CAT_EXISTS : STAIR_CAT_PAIR;
+        const int Kc = (ex ? 3 : 2) * H;
+        const int w0 = ex ? STAIR_W_EXISTS0_W : STAIR_W_TOACT0_W, w1 = ex ? STAIR_W_EXISTS1_W : STAIR_W_TOACT1_W;
+        float* dV0 = b.ws.take<float>(static_cast<long long>(n) * H);
+        STAGE_ACT(v0p, V0, dt, n, H);
+        STAIR_TRY(linear_bwd(b, dvec_out, H, vec_out, H, nullptr, v0p, n, n, H, H, w1, w1 + 1, dV0));
+        float* dcat = b.ws.take<float>(static_cast<long long>(n) * Kc);
+        STAIR_TRY(linear_bwd(b, dV0, H, V0, H, nullptr, VP, n, n, H, Kc, w0, w0 + 1, dcat));
+        RUN(launch_concat_bwd(dt, c.buf.vec, a0, a1, mode, dcat, tr.dvec, n, H, c.st));
+        break;
+    }
+    case STAIR_OP_SUPERLATIVE: {
+        const int is_min = g.variant & 1, kind = g.variant >> 1;
+        const int K = kind == 0 ? 1 : (kind == 1 ? 2 : T);
+        float* ats = c.at<float>(c.plan.ats);
+        float* dV0 = b.ws.take<float>(static_cast<long long>(n) * H);
+        STAGE_ACT(v0p, V0, dt, n, H);
+        STAIR_TRY(linear_bwd(b, dvec_out, H, vec_out, H, nullptr, v0p, n, n, H, H, STAIR_W_SUP_D_W, STAIR_W_SUP_D_B, dV0));
+        float* datt_s = b.ws.take<float>(static_cast<long long>(n) * K * T);
+        const void* act_base = kind == 2 ? c.buf.vid : c.buf.vec;
+        float* dact_base = kind == 2 ? tr.dvid : tr.dvec;
+        RUN(launch_super_mix_bwd(dt, ats, K, T, H, is_min, act_base, a0, kind == 2 ? T : 1, dV0, datt_s, dact_base, n, c.st));
+        STAIR_TRY(localize_bwd(b, datt_s, 0, S0, S1, S2, a1, act_base, dact_base, a0, K, kind == 2 ? T : 1, K, n));
+        break;
+    }
+    default:
+        return STAIR_ERR_LAYOUT;
+    }
+    b.ws.off = mark;
+    return STAIR_OK;
+}
+
+// ---- encoders with history (training forward) ---------------------------------------------------------------------------------------
+struct EncIO {
+    const void* xin; int xin_dt; long long rows; int Kin, Kin_ld, wih, bias, whh_f, whh_r;
+    void* xproj; void* out; void* qfeat; const int* q_off; int S;
+};
+
+EncIO enc_io(Ctx& c, int e) {
+    EncIO io;
+    const StairModel& m = c.m; const StairBatch& bt = c.b;
+    if (e == 0) {
+        io.xin = bt.video; io.xin_dt = bt.video_dtype; io.rows = static_cast<long long>(bt.B) * c.T; io.Kin = m.V; io.Kin_ld = m.V_ld;
+        io.wih = STAIR_W_VENC_WIH; io.bias = STAIR_W_VENC_B; io.whh_f = STAIR_W_VENC_WHH_F; io.whh_r = STAIR_W_VENC_WHH_R;
+        io.xproj = c.at<void>(c.plan.xv); io.out = c.buf.vid; io.qfeat = nullptr; io.q_off = nullptr; io.S = c.T;
+    } else {
+        io.xin = bt.question; io.xin_dt = bt.question_dtype; io.rows = bt.n_tok; io.Kin = m.text_size; io.Kin_ld = m.text_ld;
+        io.wih = STAIR_W_TENC_WIH; io.bias = STAIR_W_TENC_B; io.whh_f = STAIR_W_TENC_WHH_F; io.whh_r = STAIR_W_TENC_WHH_R;
+        io.xproj = c.at<void>(c.plan.xq); io.out = c.buf.tokfeat; io.qfeat = c.buf.qfeat; io.q_off = bt.q_off; io.S = bt.L_max;
+    }
+    return io;
+}
+
+int run_encoders_train(Ctx& c, const StairTrain& tr) {
+    const StairModel& m = c.m; const StairBatch& bt = c.b;
+    const int B = bt.B, H = c.H, h = c.h;
+    const SavedLayout SL = saved_layout(m, bt);
+    if (tr.saved_bytes < SL.total) return STAIR_ERR_CAPACITY;
+    char* sv = reinterpret_cast<char*>(tr.saved);
+    float* g = c.at<float>(c.plan.g);
+    for (int e = 0; e < 2; ++e) {
+        const EncIO io = enc_io(c, e);
+        bf16* in = c.at<bf16>(e == 0 ? c.plan.xv_in : c.plan.xq_in);
+        const bool direct = e == 0 && bt.video_dtype == STAIR_BF16 && c.np == 1 && (m.V % 8) == 0;
+        GemmArgs a;
+        if (direct) { a.A = io.xin; a.lda = io.Kin; a.a_plane_rows = 0; }
+        else {
+            STAIR_TRY(launch_stage_rows(io.xin_dt, io.xin, io.Kin, nullptr, 1, 1, in, io.Kin_ld, io.rows, c.np, io.rows, io.Kin, c.st));
+            a.A = in; a.lda = io.Kin_ld; a.a_plane_rows = static_cast<int>(io.rows);
+        }
+        a.nplanes = c.np; a.W = c.W(io.wih); a.ldw = io.Kin_ld; a.w_plane_rows = 4 * H; a.bias = c.Wf(io.bias); a.C = io.xproj; a.ldc = 4 * H;
+        a.out_dtype = c.adt; a.M = static_cast<int>(io.rows); a.N = 4 * H; a.K = io.Kin;
+        STAIR_TRY(launch_gemm(a, c.st));
+        const int S = io.S;
+        float* gates = reinterpret_cast<float*>(sv + SL.enc[e].gates);
+        float* cs = reinterpret_cast<float*>(sv + SL.enc[e].c);
+        bf16* hs = reinterpret_cast<bf16*>(sv + SL.enc[e].hs);
+        const long long hs_dir = static_cast<long long>(S + 1) * B * h;      // [np][2][S+1][B][h]
+        const long long hs_plane = 2 * hs_dir;
+        if (cudaMemsetAsync(hs, 0, sizeof(bf16) * c.np * hs_plane, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
+        for (int s = 0; s < S; ++s) {
+            if (s > 0)
+                for (int d = 0; d < 2; ++d) {
+                    GemmArgs r;
+                    r.A = hs + d * hs_dir + static_cast<long long>(s) * B * h; r.lda = h; r.a_plane_rows = static_cast<int>(hs_plane / h);
+                    r.nplanes = c.np; r.W = c.W(d == 0 ? io.whh_f : io.whh_r); r.ldw = h; r.w_plane_rows = 4 * h;
+                    r.C = g + static_cast<long long>(d) * B * 4 * h; r.ldc = 4 * h; r.out_dtype = STAIR_F32; r.M = B; r.N = 4 * h; r.K = h;
+                    STAIR_TRY(launch_gemm(r, c.st));
+                }
+            const float* c_prev = s > 0 ? cs + static_cast<long long>(s - 1) * 2 * B * h : cs;
+            STAIR_TRY(launch_lstm_cell_train(c.adt, io.xproj, g, c_prev, cs + static_cast<long long>(s) * 2 * B * h,
+                                             gates + static_cast<long long>(s) * 2 * B * 4 * h, hs + static_cast<long long>(s + 1) * B * h,
+                                             hs + static_cast<long long>(s) * B * h, hs_plane, hs_dir, c.np, c.adt, io.out, io.qfeat, io.q_off, B,
+                                             c.T, h, s, c.st));
+        }
+    }
+    return STAIR_OK;
+}
+
+int encoders_bwd(BCtx& b) {
+    Ctx& c = b.c;
+    const StairTrain& tr = b.tr;
+    const StairModel& m = c.m; const StairBatch& bt = c.b;
+    const int B = bt.B, H = c.H, h = c.h;
+    const SavedLayout SL = saved_layout(m, bt);
+    char* sv = reinterpret_cast<char*>(tr.saved);
+    for (int e = 1; e >= 0; --e) {
+        const EncIO io = enc_io(c, e);
+        const int S = io.S;
+        const long long mark = b.ws.off;
+        const float* gates = reinterpret_cast<const float*>(sv + SL.enc[e].gates);
+        const float* cs = reinterpret_cast<const float*>(sv + SL.enc[e].c);
+        const bf16* hs = reinterpret_cast<const bf16*>(sv + SL.enc[e].hs);
+        const long long hs_dir = static_cast<long long>(S + 1) * B * h, hs_plane = 2 * hs_dir;
+        float* dxproj = b.ws.take<float>(io.rows * 8 * h);
+        float* dg_hist = b.ws.take<float>(2LL * S * B * 4 * h);               // [2][S][B][4h]
+        const long long dg_dir = static_cast<long long>(S) * B * 4 * h;
+        bf16* dg_planes = b.ws.take<bf16>(static_cast<long long>(c.np) * 2 * B * 4 * h);
+        float* dh_rec = b.ws.take<float>(2LL * B * h);
+        float* dc = b.ws.take<float>(2LL * B * h);
+        const float* dout = e == 0 ? tr.dvid : tr.dtokfeat;
+        for (int s = S - 1; s >= 0; --s) {
+            const float* c_prev = s > 0 ? cs + static_cast<long long>(s - 1) * 2 * B * h : cs;
+            RUN(launch_lstm_cell_bwd(gates + static_cast<long long>(s) * 2 * B * 4 * h, c_prev, cs + static_cast<long long>(s) * 2 * B * h, dout, dh_rec,
+                                     e == 1 ? tr.dqfeat : nullptr, dc, dg_hist + static_cast<long long>(s) * B * 4 * h, dg_dir, dg_planes,
+                                     2LL * B * 4 * h, c.np, dxproj, io.q_off, B, c.T, h, s, S - 1, c.st));
+            if (s > 0)
+                for (int d = 0; d < 2; ++d) {
+                    const int wid = d == 0 ? io.whh_f : io.whh_r;
+                    if (!m.wt[wid]) return STAIR_ERR_ARG;
+                    GemmArgs r;
+                    r.A = dg_planes + static_cast<long long>(d) * B * 4 * h; r.lda = 4 * h; r.a_plane_rows = 2 * B; r.nplanes = c.np;
+                    r.W = m.wt[wid]; r.ldw = 4 * h; r.w_plane_rows = h; r.C = dh_rec + static_cast<long long>(d) * B * h; r.ldc = h;
+                    r.out_dtype = STAIR_F32; r.M = B; r.N = h; r.K = 4 * h;
+                    RUN(launch_gemm(r, c.st));
+                }
+        }
+        // dW_hh[d] += sum_s dG[d][s]^T h[d][s-1]   (one contraction over all (step, question) rows per direction)
+        for (int d = 0; d < 2; ++d)
+            STAIR_TRY(linear_bwd(b, dg_hist + d * dg_dir, 4 * h, nullptr, 0, nullptr, hs + d * hs_dir, hs_plane / h, S * B, 4 * h, h,
+                                 d == 0 ? io.whh_f : io.whh_r, -1, nullptr));
+        // dW_ih, d(b_ih + b_hh) from the gate gradients of every frame / token
+        {
+            const bool direct = e == 0 && bt.video_dtype == STAIR_BF16 && c.np == 1 && (m.V % 8) == 0;
+            const bf16* xin_p; long long xrows;
+            if (direct) { xin_p = reinterpret_cast<const bf16*>(io.xin); xrows = io.rows; }
+            else {
+                bf16* in = b.ws.take<bf16>(static_cast<long long>(c.np) * io.rows * io.Kin_ld);
+                RUN(launch_stage_rows(io.xin_dt, io.xin, io.Kin, nullptr, 1, 1, in, io.Kin_ld, io.rows, c.np, io.rows, io.Kin, c.st));
+                xin_p = in; xrows = io.rows;
+            }
+            STAIR_TRY(linear_bwd(b, dxproj, 4 * H, nullptr, 0, nullptr, xin_p, xrows, static_cast<int>(io.rows), 4 * H, io.Kin, io.wih, io.bias, nullptr));
+        }
+        b.ws.off = mark;
+    }
+    return STAIR_OK;
+}
+
+int losses(BCtx& b) {
+    Ctx& c = b.c;
+    const StairTrain& tr = b.tr;
+    const int H = c.H;
+    const int* aux_slot = c.buf.itab + c.il.aux_slot;
+    RUN(launch_loss_att(c.buf.att, tr.datt, c.out_slot, aux_slot, tr.att_node, tr.att_kind, tr.att_slot, tr.att_gold, tr.att_w, tr.loss, tr.n_att, c.T, c.st));
+    const float* hw[3] = {c.Wf(STAIR_W_EQUALS_HEAD_W), c.Wf(STAIR_W_XOR_HEAD_W), c.Wf(STAIR_W_EXISTS_HEAD_W)};
+    const float* hb[3] = {c.Wf(STAIR_W_EQUALS_HEAD_B), c.Wf(STAIR_W_XOR_HEAD_B), c.Wf(STAIR_W_EXISTS_HEAD_B)};
+    float* dhw[3] = {G(b, STAIR_W_EQUALS_HEAD_W), G(b, STAIR_W_XOR_HEAD_W), G(b, STAIR_W_EXISTS_HEAD_W)};
+    float* dhb[3] = {G(b, STAIR_W_EQUALS_HEAD_B), G(b, STAIR_W_XOR_HEAD_B), G(b, STAIR_W_EXISTS_HEAD_B)};
+    if (tr.n_bin > 0) {
+        for (int j = 0; j < 3; ++j) if (!hw[j] || !hb[j]) return STAIR_ERR_ARG;
+        RUN(launch_loss_bin(c.adt, c.buf.vec, tr.dvec, c.out_slot, tr.bin_node, nullptr, tr.bin_label, tr.bin_w, hw, hb, dhw, dhb, tr.bin_which,
+                            tr.loss, tr.n_bin, H, c.st));
+    }
+    RUN(launch_loss_con(c.adt, c.buf.vec, tr.dvec, c.out_slot, tr.con_node, tr.con_pos, tr.con_w, tr.cls_rep, tr.n_cls, tr.loss, tr.n_con, H, c.st));
+    RUN(launch_loss_dec(c.buf.logits, tr.answer, tr.dec_w, tr.dlogits, tr.loss, c.b.B, c.m.A, c.st));
+    return STAIR_OK;
+}
+
+int decoder_bwd(BCtx& b) {
+    Ctx& c = b.c;
+    const StairTrain& tr = b.tr;
+    const int B = c.b.B, H = c.H, A = c.m.A;
+    bf16* VP = c.at<bf16>(c.plan.vp);
+    void* D0 = c.at<void>(c.plan.v01);
+    for (int done = 0; done < B; done += static_cast<int>(VEC_CAP)) {
+        const int n = B - done < VEC_CAP ? B - done : static_cast<int>(VEC_CAP);
+        const long long mark = b.ws.off;
+        // recompute this chunk's decoder hidden layer (module_net.py:136-138)
+        RUN(launch_decoder_concat(c.adt, c.buf.vec, c.b.root_node + done, c.out_slot, c.act_ptr(c.buf.qfeat, static_cast<long long>(done) * H), VP, n, c.np, n, H, c.st));
+        RUN(gemm_planes(c, VP, 2 * H, n, n, 2 * H, 2 * H, STAIR_W_DEC0_W, STAIR_W_DEC0_B, STAIR_ACT_RELU, nullptr, D0, c.adt, 2 * H));
+        float* dD0 = b.ws.take<float>(static_cast<long long>(n) * 2 * H);
+        STAGE_ACT(d0p, D0, c.adt, n, 2 * H);
+        STAIR_TRY(linear_bwd(b, tr.dlogits + static_cast<long long>(done) * A, A, nullptr, 0, nullptr, d0p, n, n, A, 2 * H, STAIR_W_DEC1_W, STAIR_W_DEC1_B, dD0));
+        float* dcat = b.ws.take<float>(static_cast<long long>(n) * 2 * H);
+        STAIR_TRY(linear_bwd(b, dD0, 2 * H, D0, 2 * H, nullptr, VP, n, n, 2 * H, 2 * H, STAIR_W_DEC0_W, STAIR_W_DEC0_B, dcat));
+        RUN(launch_decoder_concat_bwd(dcat, c.b.root_node + done, c.out_slot, tr.dvec, tr.dqfeat + static_cast<long long>(done) * H, n, H, c.st));
+        b.ws.off = mark;
+    }
+    return STAIR_OK;
+}
+
+int run_backward(BCtx& b) {
+    Ctx& c = b.c;
+    const StairTrain& tr = b.tr;
+    const StairBuffers& buf = c.buf;
+    const long long T = c.T, H = c.H;
+    if (!b.dry) {
+        cudaError_t e = cudaMemsetAsync(tr.dvid, 0, sizeof(float) * buf.vid_slots * T * H, c.st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(tr.dvec, 0, sizeof(float) * buf.vec_rows * H, c.st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(tr.datt, 0, sizeof(float) * buf.att_rows * T, c.st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(tr.dtokfeat, 0, sizeof(float) * c.b.n_tok * H, c.st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(tr.dqfeat, 0, sizeof(float) * c.b.B * H, c.st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(tr.loss, 0, sizeof(float) * 8, c.st);
+        if (e != cudaSuccess) return STAIR_ERR_CUDA;
+    }
+    STAIR_TRY(losses(b));
+    STAIR_TRY(decoder_bwd(b));
+    for (int gi = c.b.n_groups - 1; gi >= 0; --gi) {
+        const StairGroup& g = c.b.groups[gi];
+        const int cap = op_is_vid_sized(g.op) ? c.plan.nc_vid : static_cast<int>(VEC_CAP);
+        for (int done = 0; done < g.count; done += cap) {
+            const int n = g.count - done < cap ? g.count - done : cap;
+            const int p = g.node_off + done, ob = g.out_base + done * g.out_mult, ab = g.aux_base >= 0 ? g.aux_base + done : -1;
+            if (g.op != STAIR_OP_WORD) RUN(run_chunk(c, g, p, n, ob, ab));      // recompute the chunk's intermediates
+            STAIR_TRY(chunk_bwd(b, g, p, n, ob, ab));
+        }
+    }
+    STAIR_TRY(encoders_bwd(b));
+    return STAIR_OK;
+}
+
+int make_ctx(Ctx& c, const StairModel& m, const StairBatch& b, const StairBuffers& buf) {
+    if (m.H % 16 || m.H > 1024 || b.T <= 0 || m.V_ld % 8 || m.text_ld % 8) return STAIR_ERR_UNSUPPORTED;
+    if (m.conv_k == 0 && b.T != m.T_max) return STAIR_ERR_UNSUPPORTED;
+    make_plan(m, b, &c.plan);
+    c.ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(buf.workspace) + 1023) & ~static_cast<uintptr_t>(1023));
+    c.T = b.T; c.H = m.H; c.h = m.H / 2; c.np = m.precision == STAIR_F32 ? 3 : 1; c.adt = m.precision; c.esz = m.precision == STAIR_F32 ? 4 : 2;
+    stair_itab_layout(b.n_nodes, b.n_groups, &c.il);
+    c.perm = buf.itab + c.il.perm; c.out_slot = buf.itab + c.il.out_slot;
+    c.arg0 = buf.itab + c.il.arg_slot; c.arg1 = c.arg0 + b.n_nodes; c.arg2 = c.arg1 + b.n_nodes;
+    c.pos_q = buf.itab + c.il.pos_q; c.span_s = buf.itab + c.il.pos_span; c.span_e = c.span_s + b.n_nodes;
+    return STAIR_OK;
+}
+
+}  // namespace
+}  // namespace stair
+
+using namespace stair;
+using namespace stair::ex;
+
+extern "C" int64_t stair_train_saved_bytes(const StairModel* model, const StairBatch* batch) {
+    if (!model || !batch) return -1;
+    return saved_layout(*model, *batch).total;
+}
+
+extern "C" int64_t stair_train_workspace_bytes(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train) {
+    if (!model || !batch || !buf || !train) return -1;
+    Ctx c{*model, *batch, *buf, nullptr};
+    if (make_ctx(c, *model, *batch, *buf) != STAIR_OK) return -1;
+    BCtx b{c, *train, Bump(), true};
+    b.ws.dry = true;
+    if (run_backward(b) != STAIR_OK) return -1;
+    return b.ws.peak + 4096;
+}
+
+extern "C" int stair_nmn_forward_train(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, void* stream) {
+    if (!model || !batch || !buf || !train) return STAIR_ERR_ARG;
+    if (batch->B <= 0) return STAIR_OK;
+    Ctx c{*model, *batch, *buf, reinterpret_cast<cudaStream_t>(stream)};
+    STAIR_TRY(make_ctx(c, *model, *batch, *buf));
+    if (buf->workspace_bytes < c.plan.total || buf->itab_ints < c.il.total) return STAIR_ERR_CAPACITY;
+    STAIR_TRY(launch_group_layouts(*batch, buf->itab, buf->status, c.st));
+    STAIR_TRY(run_encoders_train(c, *train));
+    STAIR_TRY(run_modules(c));
+    return run_decoder(c);
+}
+
+extern "C" int stair_nmn_backward(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, void* stream) {
+    if (!model || !batch || !buf || !train) return STAIR_ERR_ARG;
+    if (batch->B <= 0) return STAIR_OK;
+    Ctx c{*model, *batch, *buf, reinterpret_cast<cudaStream_t>(stream)};
+    STAIR_TRY(make_ctx(c, *model, *batch, *buf));
+    if (buf->workspace_bytes < c.plan.total) return STAIR_ERR_CAPACITY;
+    BCtx b{c, *train, Bump(), false};
+    b.ws.base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(train->workspace) + 255) & ~static_cast<uintptr_t>(255));
+    b.ws.cap = train->workspace_bytes - 256;
+    const int rc = run_backward(b);
+    if (rc == STAIR_OK && b.ws.overflow) return STAIR_ERR_CAPACITY;
+    return rc;
+}
+
+extern "C" int stair_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
+                               float eps, int step, void* stream) {
+    const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+    return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2, reinterpret_cast<cudaStream_t>(stream));
+}

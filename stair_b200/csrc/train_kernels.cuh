@@ -1,0 +1,72 @@
+// Backward / loss kernels of the NMN training step (train_kernels.cu), used by executor_bwd.cu.
+// Gradients are fp32 everywhere; activations (`dt`) are bf16 or fp32 like in the forward.  Every kernel ACCUMULATES (+=) into
+// its gradient outputs: the gradient arenas are zeroed once at the start of the backward pass.  "atomic" outputs may be hit by
+// several instances (shared video slots, shared token rows, weight gradients).
+#pragma once
+#include "nmn_kernels.cuh"
+
+namespace stair {
+
+// dz = dY * (Y > 0 if Y)  ->  bf16 planes dZ [np][M, N_ld]; dZs = rs[m] * dz planes (only if rs, else dZs may be null);
+// db[n] += sum_m dz (if db).  Columns N..N_ld are zero.
+int launch_dz_prep(int ydt, const float* dY, long long ld_dy, const void* Y, long long ld_y, const float* rs, bf16* dZ, bf16* dZs,
+                   long long n_ld, long long plane_rows, int nplanes, float* db, int M, int N, cudaStream_t st);
+// dst [np][C, ld_dst] = transpose(src [np][R, ld_src] (first C columns)); columns R..ld_dst zeroed
+int launch_transpose_planes(const bf16* src, long long ld_src, long long src_plane_rows, bf16* dst, long long ld_dst, long long dst_plane_rows,
+                            int nplanes, int R, int C, cudaStream_t st);
+// dr[m] += <G[m,:], X[m,:]> ; G[m,:] *= rs[m]      (X rows optionally gathered like launch_stage_rows)
+int launch_rowscale_bwd(int xdt, float* G, const void* X, const int* slots, int rps, int unit, const float* rs, float* dr, int M, int K, cudaStream_t st);
+// dst[(idx[r / rps] * unit + r % rps) * H + :] += src[r, :]   (atomic)
+int launch_scatter_add_rows(const float* src, const int* idx, int rps, int unit, float* dst, long long rows, int H, cudaStream_t st);
+int launch_layernorm_bwd(int xdt, const float* dOut, const void* X, const float* gamma, float* dX, float* dgamma, float* dbeta, long long rows, int H, cudaStream_t st);
+int launch_cos_att_bwd(int dt, const void* f, const void* kmat, int K, int T, int H, const float* datt, long long att_base, float* df, float* dk, int n, cudaStream_t st);
+int launch_existsframe_bwd(int dt, const void* vid, const int* feat_idx, const void* vec, const int* kw_idx, const float* datt, int att_base,
+                           float* dvid, float* dvec, int n, int T, int H, cudaStream_t st);
+int launch_temporal_relate_bwd(const float* att, const int* att_idx, int K, int mode, int conv_k, const float* const* params, float* const* dparams,
+                               const float* dr, float* datt, int n, int T, cudaStream_t st);
+int launch_bcast_T(const float* dagg, float* dx, int n, int T, int H, cudaStream_t st);
+int launch_ff_attn_bwd(int dt, const void* x, const void* vec, const int* kw_idx, const float* w, const float* a, const float* da, float* dx,
+                       float* dvec, float* dw, float* db, int n, int T, int H, cudaStream_t st);
+int launch_attnvideo_bwd(int dt, const float* dOut, const void* vid, const int* feat_idx, const float* att, const int* att_idx, float* datt,
+                         float* dvid, int n, int T, int H, cudaStream_t st);
+int launch_relate_bwd(const float* att_out, int out_base, const float* datt_out, const int* att_idx, int sign, float* datt, float* dbeta, int n, int T, cudaStream_t st);
+int launch_rowdot_sigmoid_bwd(int dt, const void* x, const float* w, const float* a, const float* da, float* dx, float* dw, float* db,
+                              long long rows, int H, cudaStream_t st);
+int launch_choose_bwd(int dt, const void* vec, const int* k1, const int* k2, const int* q, const float* dOut, float* dvec, int n, int H, cudaStream_t st);
+int launch_binary_bwd(int dt, const void* base, const int* a_idx, const int* b_idx, const float* dOut, float* dbase, int unit, int len, int op, int n, cudaStream_t st);
+int launch_array2_bwd(const float* dOut, const int* a_idx, const int* b_idx, float* dvec, int n, int H, cudaStream_t st);
+int launch_concat_bwd(int dt, const void* vec, const int* a_idx, const int* b_idx, int mode, const float* dcat, float* dvec, int n, int H, cudaStream_t st);
+int launch_super_mix_bwd(int dt, const float* att, int K, int T, int H, int is_min, const void* act_base, const int* act_idx, int act_unit,
+                         const float* dv, float* datt_s, float* dact_base, int n, cudaStream_t st);
+int launch_word_embed_bwd(const float* dvec, int out_base, const int* q_off, const int* pos_q, const int* span_s, const int* span_e,
+                          float* dtokfeat, int n, int H, cudaStream_t st);
+int launch_decoder_concat_bwd(const float* dcat, const int* root_node, const int* out_slot, float* dvec, float* dqfeat, int B, int H, cudaStream_t st);
+
+// ---- losses (train_module.py:83-194); every kernel adds weight * loss to loss[slot] and writes the prediction gradients ----------
+// attention_score_criterion rows: pred row = att[(kind < 2 ? out_slot[node] + kind : aux_slot[node])]; slot = 0 Localize, 1 Temporal, 2 ExistsFrame
+int launch_loss_att(const float* att, float* datt, const int* out_slot, const int* aux_slot, const int* node, const int* kind, const int* slot,
+                    const float* gold, const float* w, float* loss, int n, int T, cudaStream_t st);
+// Exists/Xor: CE over the 2-way head; Equals: MSE on the 1-way head.  Includes the head Linear backward.
+int launch_loss_bin(int dt, const void* vec, float* dvec, const int* out_slot, const int* node, const int* is_mse, const int* label, const float* w,
+                    const float* const* head_w /*[3]: equals, xor, exists*/, const float* const* head_b, float* const* dhead_w, float* const* dhead_b,
+                    const int* which /*0 equals,1 xor,2 exists*/, float* loss, int n, int H, cudaStream_t st);
+// contrastive CE of the L2-normalised module output against all class text reps of the window (train_module.py:113-132,388-406)
+int launch_loss_con(int dt, const void* vec, float* dvec, const int* out_slot, const int* node, const int* pos, const float* w,
+                    const float* cls_rep, int n_cls, float* loss, int n, int H, cudaStream_t st);
+int launch_loss_dec(const float* logits, const int* answer, float w, float* dlogits, float* loss, int B, int A, cudaStream_t st);
+
+// ---- LSTM with history (training forward) and its backward ---------------------------------------------------------------------------
+// gates_out [2][B][4h] (post-activation i,f,g,o), c_prev/c_out [2][B][h]; hstate planes [np][...] with plane stride hs_plane;
+// inactive (finished) questions copy their state forward.  q_off == null: video (row b*T+t); else ragged text.
+int launch_lstm_cell_train(int xdt, const void* xproj, const float* g, const float* c_prev, float* c_out, float* gates_out, bf16* hstate_out,
+                           const bf16* hstate_prev, long long hs_plane, long long hs_dir, int nplanes, int odt, void* out, void* qfeat, const int* q_off,
+                           int B, int T, int h, int step, cudaStream_t st);
+// one BPTT step: dh = dout(row) + dh_rec (+ dqfeat at a question's last step); writes the gate pre-activation gradients as
+// fp32 [2][B][4h], as bf16 planes (A operand of the recurrent GEMM) and into the dxproj row; updates dc in place.
+int launch_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_cur, const float* dout, const float* dh_rec, const float* dqfeat,
+                         float* dc, float* dgates, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, const int* q_off,
+                         int B, int T, int h, int step, int last_step, cudaStream_t st);
+
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1, float bc2, cudaStream_t st);
+
+}  // namespace stair
