@@ -188,6 +188,11 @@ typedef struct StairTrain {
 } StairTrain;
 
 int stair_version(void);
+/* sizeof() of the ABI structs as compiled (0 StairModel, 1 StairGroup, 2 StairBatch, 3 StairBuffers, 4 StairItabLayout, 5 StairTrain):
+ * lets a binding verify its mirror of the struct layouts. */
+int64_t stair_sizeof(int which);
+/* encoder recurrence implementation: 0 = fused persistent kernel when eligible (default), 1 = per-step GEMM + cell kernels */
+int stair_set_lstm_impl(int impl);
 
 /* ---- dense contraction (tcgen05 + TMA): C[M,N] = act(row_scale[m] * (A[M,K] . W[N,K]^T) + bias[n]) -------------
  * Replaces every nn.Linear / LSTM projection call site (video_nmn/modules.py passim, module_net.py:39-53). */

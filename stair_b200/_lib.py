@@ -50,7 +50,7 @@ W_COUNT = W['COUNT']
 
 class StairModel(ctypes.Structure):
     _fields_ = [('T_max', i32), ('V', i32), ('V_ld', i32), ('H', i32), ('text_size', i32), ('text_ld', i32), ('A', i32),
-                ('O', i32), ('conv_k', i32), ('precision', i32), ('w', vp * W_COUNT)]
+                ('O', i32), ('conv_k', i32), ('precision', i32), ('w', vp * W_COUNT), ('wt', vp * W_COUNT)]
 
 
 class StairGroup(ctypes.Structure):
@@ -77,6 +77,16 @@ class StairItabLayout(ctypes.Structure):
                 ('group_off', i64), ('total', i64)]
 
 
+class StairTrain(ctypes.Structure):
+    _fields_ = [('grad', vp * W_COUNT),
+                ('n_att', i32), ('att_node', vp), ('att_kind', vp), ('att_slot', vp), ('att_gold', vp), ('att_w', vp),
+                ('n_bin', i32), ('bin_node', vp), ('bin_which', vp), ('bin_label', vp), ('bin_w', vp),
+                ('n_con', i32), ('con_node', vp), ('con_pos', vp), ('con_w', vp), ('n_cls', i32), ('cls_rep', vp),
+                ('answer', vp), ('dec_w', ctypes.c_float), ('loss', vp),
+                ('dvid', vp), ('dvec', vp), ('datt', vp), ('dtokfeat', vp), ('dqfeat', vp), ('dlogits', vp),
+                ('saved', vp), ('saved_bytes', i64), ('workspace', vp), ('workspace_bytes', i64)]
+
+
 _lib = None
 
 
@@ -94,6 +104,8 @@ def lib():
         _lib.stair_itab_ints.restype = i64
         _lib.stair_nmn_workspace_bytes.restype = i64
         _lib.stair_last_launch_count.restype = i64
+        _lib.stair_train_saved_bytes.restype = i64
+        _lib.stair_train_workspace_bytes.restype = i64
     return _lib
 
 

@@ -25,6 +25,17 @@ using namespace stair::ex;
 
 extern "C" int stair_set_lstm_impl(int impl) { g_lstm_impl = impl; return STAIR_OK; }
 extern "C" int stair_version(void) { return STAIR_ABI_VERSION; }
+extern "C" int64_t stair_sizeof(int which) {
+    switch (which) {
+    case 0: return sizeof(StairModel);
+    case 1: return sizeof(StairGroup);
+    case 2: return sizeof(StairBatch);
+    case 3: return sizeof(StairBuffers);
+    case 4: return sizeof(StairItabLayout);
+    case 5: return sizeof(StairTrain);
+    default: return -1;
+    }
+}
 
 extern "C" int64_t stair_nmn_workspace_bytes(const StairModel* model, const StairBatch* batch) {
     if (!model || !batch) return -1;

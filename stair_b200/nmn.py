@@ -70,14 +70,15 @@ class VideoNMN(nn.Module):
         return frozenset(m for m in self.pretrain_modules if m in LY.HEAD_KIND)
 
     # ---- the batched forward ---------------------------------------------------------------------------------------
-    def forward_batch(self, batch: LY.NMNBatch, head_modules=frozenset(), phases=L.FWD_ALL, stream=None) -> ForwardState:
-        """Enqueue VideoNMN.forward for a collated batch on the current stream; returns the device buffers."""
+    def prepare(self, batch: LY.NMNBatch, head_modules=frozenset(), training=False):
+        """Allocate (grow-only cache) the arenas / tables of one call and fill the C-ABI structs.
+        Returns (state, StairModel, StairBatch, StairBuffers)."""
         if batch.device is None or batch.device.type != 'cuda':
             raise L.StairError('batch is not on a CUDA device: call batch.to("cuda") — stair_b200 has no CPU fallback')
         dev = batch.device
         cfg = self.config
         prec = PRECISIONS[self.precision]
-        model = self._packed.refresh(self.submodules, cfg, prec, dev)
+        model = self._packed.refresh(self.submodules, cfg, prec, dev, training=training)
         if batch.V != cfg['video_size'] or batch.text_size != cfg['text_size']:
             raise ValueError('feature sizes %s/%s do not match the config %s/%s' % (batch.V, batch.text_size, cfg['video_size'], cfg['text_size']))
         groups, tab, sizes = LY.build_groups(batch, head_modules)
@@ -121,13 +122,19 @@ class VideoNMN(nn.Module):
         bufs.itab, bufs.itab_ints = st.itab.data_ptr(), st.itab.numel()
         bufs.workspace, bufs.workspace_bytes = ws.data_ptr(), ws.numel()
         bufs.status = st.status.data_ptr()
-        rc = lib.stair_nmn_forward(ctypes.byref(model), ctypes.byref(sb), ctypes.byref(bufs), L.i32(phases), L.stream_ptr(stream))
-        L.check(rc, 'stair_nmn_forward')
-        self.last_launches = int(lib.stair_last_launch_count())
         st.keepalive = (gtab, model, sb, bufs)
         il = L.StairItabLayout()
         lib.stair_itab_layout(L.i32(n), L.i32(ng), ctypes.byref(il))
         st.itab_layout = il
+        return st, model, sb, bufs
+
+    def forward_batch(self, batch: LY.NMNBatch, head_modules=frozenset(), phases=L.FWD_ALL, stream=None) -> ForwardState:
+        """Enqueue VideoNMN.forward for a collated batch on the current stream; returns the device buffers."""
+        st, model, sb, bufs = self.prepare(batch, head_modules)
+        lib = L.lib()
+        rc = lib.stair_nmn_forward(ctypes.byref(model), ctypes.byref(sb), ctypes.byref(bufs), L.i32(phases), L.stream_ptr(stream))
+        L.check(rc, 'stair_nmn_forward')
+        self.last_launches = int(lib.stair_last_launch_count())
         return st
 
     def check_status(self, st: ForwardState):

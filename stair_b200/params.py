@@ -153,6 +153,15 @@ def _vector(v):
     return v.detach().float().contiguous().reshape(-1)
 
 
+def _matrix_t(w, nplanes):
+    """fp32 [N,K] -> transposed bf16 planes [nplanes][K, N_ld] (B operand of the dX = dZ.W GEMM of the backward pass)."""
+    return _matrix(w.detach().float().t().contiguous(), nplanes)
+
+
+# GEMM matrices whose layer input needs no gradient (encoder input projections): no transposed copy
+NO_DX = ('VENC_WIH', 'TENC_WIH')
+
+
 def weight_sources(sub, config):
     """{STAIR_W_* name: (kind, callable -> fp32 tensor)}; kind 'M' = GEMM matrix (bf16 planes), 'V' = fp32 vector."""
     s = {}
@@ -218,22 +227,92 @@ def weight_sources(sub, config):
     return {(L.W[k] if isinstance(k, str) else k): v for k, v in s.items()}
 
 
+def grad_targets(sub, config):
+    """{STAIR_W_* id: (numel, [(parameter, element offset inside the slot), ...])} — where the fp32 gradient accumulator of
+    each weight-table slot (StairTrain.grad, logical [N, K] / vector shapes) lands in the reference's parameter tree.
+    The two LSTM biases of a direction share one slot (the kernels see b_ih + b_hh), so both receive the same gradient."""
+    t = {}
+
+    def one(key, p):
+        t[L.W[key] if isinstance(key, str) else key] = (p.numel(), [(p, 0)])
+
+    def lin(prefix, layer):
+        one(prefix + '_W', layer.weight)
+        one(prefix + '_B', layer.bias)
+
+    def lstm(prefix, m):
+        n = m.weight_ih_l0.numel()
+        t[L.W[prefix + '_WIH']] = (2 * n, [(m.weight_ih_l0, 0), (m.weight_ih_l0_reverse, n)])
+        nb = m.bias_ih_l0.numel()
+        t[L.W[prefix + '_B']] = (2 * nb, [(m.bias_ih_l0, 0), (m.bias_hh_l0, 0), (m.bias_ih_l0_reverse, nb), (m.bias_hh_l0_reverse, nb)])
+        one(prefix + '_WHH_F', m.weight_hh_l0)
+        one(prefix + '_WHH_R', m.weight_hh_l0_reverse)
+
+    def mlp4(prefix, seq):
+        base = L.W[prefix]
+        for j, p in enumerate((seq[0].weight, seq[0].bias, seq[3].weight, seq[3].bias)):
+            one(base + j, p)
+
+    lstm('VENC', sub['video_encoder'])
+    lstm('TENC', sub['text_encoder'])
+    lin('DEC0', sub['decoder'][0]); lin('DEC1', sub['decoder'][3])
+    loc = sub['Localize']
+    lin('LOC_V0', loc.video_linear[0]); lin('LOC_V1', loc.video_linear[3]); lin('LOC_K', loc.keyword_linear[0])
+    tmp = sub['Temporal']
+    lin('TEMP_D', tmp.dense[0])
+    one('TEMP_LN_G', tmp.layer_norm.weight); one('TEMP_LN_B', tmp.layer_norm.bias)
+    for mode in ('BEFORE', 'AFTER', 'BETWEEN'):
+        seq = tmp.relate[mode.lower()]
+        base = L.W['TEMP_REL_' + mode]
+        for j, layer in enumerate((seq[0], seq[2], seq[4])):
+            one(base + 2 * j, layer.weight)
+            one(base + 2 * j + 1, layer.bias)
+    flt = sub['Filter']
+    for kind, slot in (('representation', 'FILT_REPR'), ('actions', 'FILT_ACTIONS'), ('objects', 'FILT_OBJECTS'), ('relations', 'FILT_RELATIONS')):
+        mlp4(slot, flt.param[kind])
+    lin('FILT_D', flt.dense[0])
+    ff = sub['FilterFrame']
+    for kind, slot in (('representation', 'FF_REPR'), ('relations', 'FF_RELATIONS'), ('actions', 'FF_ACTIONS')):
+        mlp4(slot, ff.param[kind])
+    lin('FF_ATT', ff.attention[0])
+    lin('FF_D', ff.dense[0])
+    if config['have_pretrain_head']:
+        lin('EQUALS_HEAD', sub['Equals'].pretrain_head)
+        lin('XOR_HEAD', sub['Xor'].pretrain_head)
+        lin('EXISTS_HEAD', sub['Exists'].pretrain_head)
+    has = sub['HasItem']
+    lin('HAS0', has.param[0]); lin('HAS1', has.param[3])
+    one('REL_BETA', sub['Relate'].beta)
+    lin('SUP_D', sub['Superlative'].dense[0])
+    lin('COMPARE', sub['Compare'].param[0])
+    lin('EQUALS', sub['Equals'].param[0])
+    lin('XOR', sub['Xor'].param[0])
+    lin('EXISTS0', sub['Exists'].param[0]); lin('EXISTS1', sub['Exists'].param[3])
+    lin('TOACT0', sub['ToAction'].param[0]); lin('TOACT1', sub['ToAction'].param[3])
+    return t
+
+
 class PackedWeights:
     """Device copies of the weights in the layout the kernels read, rebuilt when a parameter changes."""
 
     def __init__(self):
         self.signature = None
         self.tensors = {}
+        self.transposed = {}
+        self.want_transposed = False
         self.model_struct = None
 
-    def refresh(self, sub, config, precision, device):
+    def refresh(self, sub, config, precision, device, training=False):
         params = [p for p in sub.parameters()]
         sig = (precision, str(device)) + tuple((p.data_ptr(), p._version) for p in params)
-        if sig == self.signature:
+        training = training or self.want_transposed          # once a model trains, keep the transposed copies current
+        if sig == self.signature and (not training or self.transposed):
             return self.model_struct
+        self.want_transposed = training
         nplanes = 3 if precision == L.F32 else 1
         srcs = weight_sources(sub, config)
-        tensors = {}
+        tensors, transposed = {}, {}
+        no_dx = {L.W[k] for k in NO_DX}
         with torch.no_grad():
             for wid, (kind, get) in srcs.items():
                 w = get()
@@ -241,6 +320,8 @@ class PackedWeights:
                     raise L.StairError('model parameters live on %s but the batch is on %s; call model.to(device)' % (w.device, device))
                 if kind == 'M':
                     tensors[wid] = _matrix(w.reshape(w.shape[0], -1), nplanes)
+                    if training and wid not in no_dx:
+                        transposed[wid] = _matrix_t(w.reshape(w.shape[0], -1), nplanes)
                 elif kind == 'M1':
                     tensors[wid] = _matrix(w.reshape(w.shape[0], -1), 1)
                 else:
@@ -254,5 +335,6 @@ class PackedWeights:
         m.precision = precision
         for wid in range(L.W_COUNT):
             m.w[wid] = tensors[wid].data_ptr() if wid in tensors else None
-        self.tensors, self.model_struct, self.signature = tensors, m, sig
+            m.wt[wid] = transposed[wid].data_ptr() if wid in transposed else None
+        self.tensors, self.transposed, self.model_struct, self.signature = tensors, transposed, m, sig
         return m

@@ -1,0 +1,363 @@
+"""Training step of the batched NMN: intermediate-supervision losses + backward on the sm_100a library.
+
+Reference: ``train_module.py:33-194`` (``CriterionByModule``), ``:341-412`` (loop: per-question module losses, decoder CE,
+window-level contrastive losses, one ``backward()`` per gradient-accumulation window, Adam).  The reference runs one
+question per iteration and accumulates 32 of them; here one *batch* is one accumulation window: every loss is scaled by
+``module_loss_weight`` (or ``decoder_loss_weight``) ``/ gradient_accumulation`` exactly like ``train_module.py:372,379,403``
+with ``gradient_accumulation`` defaulting to the (global) number of questions in the window.
+
+Host side (this file) only *collates*: it applies the reference's inclusion rules (``module_net.py:107-113`` for
+``res_by_step``; ``train_module.py:350-366`` for which modules are supervised and how) and writes flat loss-row tables;
+the losses, their gradients and the whole backward pass run in ``libstair_b200.so`` (csrc/executor_bwd.cu,
+csrc/train_kernels.cu).  Gradients land in ``parameter.grad`` with the reference's shapes, parameters of modules that
+no question of the window used keep ``grad = None`` (so ``torch.optim.Adam`` skips them as in the reference — SURVEY.md
+hard part 4).  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import layout as LY
+from .params import grad_targets
+
+LOSS_SLOTS = ('Localize', 'Temporal', 'ExistsFrame', 'Exists/Xor', 'Equals', 'contrastive', 'decoder')
+CONTRASTIVE = ('Filter', 'Superlative', 'ToAction')
+SUPERVISED = ('Exists', 'Xor', 'Equals', 'Filter', 'ToAction', 'FilterFrame', 'ExistsFrame', 'Superlative', 'Localize',
+              'Temporal')                                   # CriterionByModule.criterions keys, train_module.py:36-48
+
+
+def span_to_attention(gold, T):
+    """train_module.py:67-81 — soft [T] mask from a float interval (host, numpy)."""
+    g = np.zeros(T, np.float32)
+    start, end = min(T - 0.002, max(0.001, gold[0])), min(T - 0.001, gold[1])
+    si, ei = math.ceil(start), math.floor(end)
+    if si < ei:
+        g[si:ei] += 1
+    if si <= ei:
+        g[si - 1] += si - start
+        g[ei] += end - ei
+    else:
+        g[ei] += end - start
+    return g
+
+
+class LossRows:
+    """Flat loss-row tables of one window (host numpy), see ``StairTrain`` in include/stair_b200.h."""
+
+    def __init__(self):
+        self.att_node, self.att_kind, self.att_slot, self.att_gold, self.att_w = [], [], [], [], []
+        self.bin_node, self.bin_which, self.bin_label, self.bin_w = [], [], [], []
+        self.con_node, self.con_cls, self.con_w = [], [], []
+        self.class_emb = {}                  # class name -> word-embedding phrase [n_w, text] (last writer wins, :364)
+        self.counts = {k: 0 for k in LOSS_SLOTS}
+
+
+def collate_losses(batch: LY.NMNBatch, pretrain_modules, T, module_loss_weight=1.0, gradient_accumulation=None,
+                   modules_no_intermediate_train=('FilterFrame',)) -> LossRows:
+    """train_module.py:350-373 over every question of the window -> loss rows."""
+    ga = float(gradient_accumulation or batch.B)
+    rows = LossRows()
+    if module_loss_weight == 0:
+        return rows
+    mlw = module_loss_weight / ga
+    for q, (lay, e) in enumerate(zip(batch.layouts, batch.examples)):
+        gold_by_step = e.get('sg_res_by_step') or {}
+        idx = e['nmn_program_idx']
+        base = int(batch.node_start[q])
+        res_by_step = {}                                                  # module_net.py:107-113: a dict keyed by the original
+        for i in range(len(lay.tokens) - 1, 0, -1):                       # program index (i != 0) — duplicated subtrees (Compare
+            tok = lay.tokens[i]                                           # rewrite) share an index and the last writer wins
+            if tok in LY.OP_OF and idx[i] is not None and tok in pretrain_modules:
+                res_by_step[idx[i]] = i
+        for step, i in res_by_step.items():                               # train_module.py:350-373
+            tok = lay.tokens[i]
+            if step not in gold_by_step or tok in modules_no_intermediate_train or tok not in SUPERVISED:
+                continue
+            gold = gold_by_step[step]
+            if gold is None:
+                continue
+            node = base + lay.node_of_token[i]
+            if tok in CONTRASTIVE:                                          # :360-366
+                for cname, emb in gold:
+                    rows.con_node.append(node); rows.con_cls.append(cname); rows.con_w.append(mlw)
+                    rows.class_emb[cname] = emb
+                    rows.counts['contrastive'] += 1
+            elif tok == 'Localize':                                         # criterion :173-182, mean over [K,T]
+                K = lay.out_K[lay.node_of_token[i]]
+                for k in range(K):
+                    rows.att_node.append(node); rows.att_kind.append(k); rows.att_slot.append(0)
+                    rows.att_gold.append(span_to_attention(gold[k], T)); rows.att_w.append(mlw / (K * T))
+                rows.counts['Localize'] += 1
+            elif tok in ('Temporal', 'ExistsFrame'):                        # :157-164,184-191
+                rows.att_node.append(node); rows.att_kind.append(2 if tok == 'Temporal' else 0)
+                rows.att_slot.append(1 if tok == 'Temporal' else 2)
+                rows.att_gold.append(span_to_attention(gold, T)); rows.att_w.append(mlw / T)
+                rows.counts[tok] += 1
+            elif tok in ('Exists', 'Xor', 'Equals'):                        # :92-107
+                rows.bin_node.append(node); rows.bin_which.append({'Equals': 0, 'Xor': 1, 'Exists': 2}[tok])
+                rows.bin_label.append(int(gold)); rows.bin_w.append(mlw)
+                rows.counts['Equals' if tok == 'Equals' else 'Exists/Xor'] += 1
+            else:
+                raise NotImplementedError('intermediate supervision of %s is excluded from training by default '
+                                          '(video_nmn/args.py:62, train_module.py:354) and has no CUDA backward here' % tok)
+    return rows
+
+
+def touched_slots(batch: LY.NMNBatch, rows: LossRows, have_heads: bool):
+    """Weight-table slots that receive a gradient in this window (host logic; the reference leaves ``grad = None`` on
+    parameters of modules no question used, and Adam skips them)."""
+    Wt = L.W
+    s = set()
+
+    def lin(prefix):
+        s.update((Wt[prefix + '_W'], Wt[prefix + '_B']))
+
+    for enc in ('VENC', 'TENC'):
+        s.update(Wt[enc + x] for x in ('_WIH', '_B', '_WHH_F', '_WHH_R'))
+    lin('DEC0'); lin('DEC1')
+    for key in batch.group_keys:
+        key = int(key)
+        variant, op = key % 8, (key // 8) % 32
+        name = LY.OP_NAME[op]
+        if name in ('Localize', 'Superlative'):
+            lin('LOC_V0'); lin('LOC_V1'); lin('LOC_K')
+            if name == 'Superlative':
+                lin('SUP_D')
+        elif name == 'Temporal':
+            lin('TEMP_D'); s.update((Wt['TEMP_LN_G'], Wt['TEMP_LN_B']))
+            mode = variant >> 1
+            if mode > 0:
+                s.update(range(Wt['TEMP_REL_BEFORE'] + 6 * (mode - 1), Wt['TEMP_REL_BEFORE'] + 6 * mode))
+        elif name == 'Filter':
+            s.update(range(Wt['FILT_REPR'] + 4 * variant, Wt['FILT_REPR'] + 4 * variant + 4)); lin('FILT_D')
+        elif name == 'FilterFrame':
+            s.update(range(Wt['FF_REPR'] + 4 * variant, Wt['FF_REPR'] + 4 * variant + 4)); lin('FF_D')
+            if variant == 0:
+                lin('FF_ATT')
+        elif name == 'HasItem':
+            lin('HAS0'); lin('HAS1')
+        elif name == 'Relate':
+            s.add(Wt['REL_BETA'])
+        elif name in ('Compare', 'Equals', 'Xor'):
+            lin(name.upper())
+        elif name == 'Exists':
+            lin('EXISTS0'); lin('EXISTS1')
+        elif name == 'ToAction':
+            lin('TOACT0'); lin('TOACT1')
+    if have_heads:
+        for which in set(rows.bin_which):
+            lin(('EQUALS_HEAD', 'XOR_HEAD', 'EXISTS_HEAD')[which])
+    return s
+
+
+class NMNTrainStep:
+    """``model(batch, return_res_by_step=True)`` + ``CriterionByModule`` + ``batch_loss.backward()`` of the reference
+    (train_module.py:345-408) for one window of questions, on the GPU.
+
+    >>> step = NMNTrainStep(model)                       # model: stair_b200.VideoNMN on a CUDA device
+    >>> opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    >>> out = step(list_of_data_dicts)                   # fills parameter.grad, returns losses / logits / answers
+    >>> opt.step(); opt.zero_grad()
+
+    Data-parallel (one process per GPU): pass ``process_group`` (or leave the default group initialised); every rank
+    passes its own shard, ``gradient_accumulation`` defaults to the global window size, gradients are summed with one
+    NCCL all-reduce over the flat fp32 gradient buffer and the per-parameter *touched* flags are OR-reduced.
+    """
+
+    def __init__(self, model, module_loss_weight=1.0, decoder_loss_weight=1.0, gradient_accumulation=None,
+                 modules_no_intermediate_train=('FilterFrame',), distributed=None, process_group=None, global_negatives=True):
+        self.model = model
+        self.module_loss_weight, self.decoder_loss_weight = module_loss_weight, decoder_loss_weight
+        self.gradient_accumulation = gradient_accumulation
+        self.modules_no_intermediate_train = tuple(modules_no_intermediate_train)
+        self.group = process_group
+        self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self.global_negatives = global_negatives
+        self._targets = None
+        self._cache = {}
+        self.last = None
+
+    # ---- flat gradient buffer ------------------------------------------------------------------------------------
+    def _layout(self):
+        if self._targets is None:
+            tg = grad_targets(self.model.submodules, self.model.config)
+            off, o = {}, 0
+            for wid in sorted(tg):
+                off[wid] = o
+                o += (tg[wid][0] + 63) // 64 * 64                 # 256-byte aligned slots
+            self._targets, self._offsets, self._flat_numel = tg, off, o
+        return self._targets, self._offsets, self._flat_numel
+
+    def _buf(self, name, numel, dtype, device):
+        t = self._cache.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype or t.device != device:
+            t = torch.empty(max(int(numel), 1), dtype=dtype, device=device)
+            self._cache[name] = t
+        return t
+
+    def _world(self):
+        return dist.get_world_size(self.group) if self.distributed else 1
+
+    # ---- the step ----------------------------------------------------------------------------------------------------
+    def __call__(self, data, assign_grads=True):
+        model = self.model
+        dev = next(model.parameters()).device
+        if dev.type != 'cuda':
+            raise L.StairError('VideoNMN parameters are on %s: stair_b200 trains only on CUDA (sm_100a) devices' % dev)
+        batch = data if isinstance(data, LY.NMNBatch) else LY.collate([data] if isinstance(data, dict) else list(data))
+        if batch.device is None:
+            batch.to(dev)
+        if batch.answer is None:
+            raise ValueError('training needs data["answer"] for every question (train_module.py:376)')
+        cfg = model.config
+        T, H, A = batch.T, cfg['hidden_size'], cfg['answer_vocab_length']
+        world = self._world()
+        n_window = batch.B
+        if world > 1:
+            cnt = torch.tensor([batch.B], device=dev, dtype=torch.int64)
+            dist.all_reduce(cnt, group=self.group)
+            n_window = int(cnt.item())
+        ga = self.gradient_accumulation or n_window
+        rows = collate_losses(batch, model.pretrain_modules, T, self.module_loss_weight, ga, self.modules_no_intermediate_train)
+        # window-level class text reps (train_module.py:360-366,388-406; gold text encoding module_net.py:78-89)
+        class_emb = rows.class_emb
+        if world > 1 and self.global_negatives:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, {k: v.cpu() for k, v in class_emb.items()}, group=self.group)
+            class_emb = {}
+            for part in gathered:
+                class_emb.update(part)
+        names = sorted(class_emb)
+        cls_rep = None
+        if names:
+            _, sent = model.encode_questions([class_emb[n] for n in names])
+            cls_rep = torch.empty((len(names), H), dtype=torch.float32, device=dev)
+            L.check(L.lib().stair_l2normalize(L.i32(L.dtype_code(sent.dtype)), L.ptr(sent), L.ptr(cls_rep), L.i32(len(names)), L.i32(H),
+                                              L.stream_ptr()), 'stair_l2normalize')
+        pos_of = {n: i for i, n in enumerate(names)}
+
+        st, ms, sb, bufs = model.prepare(batch, frozenset(), training=True)
+        lib = L.lib()
+        tg, offsets, flat_numel = self._layout()
+        flat = torch.zeros(flat_numel, dtype=torch.float32, device=dev)
+        tr = L.StairTrain()
+        for wid in range(L.W_COUNT):
+            tr.grad[wid] = flat.data_ptr() + 4 * offsets[wid] if wid in offsets else None
+
+        keep = []
+
+        def dev_i32(x):
+            t = torch.from_numpy(np.asarray(x, np.int32).reshape(-1)).to(dev, non_blocking=True)
+            keep.append(t)
+            return t.data_ptr() if t.numel() else None
+
+        def dev_f32(x):
+            t = torch.from_numpy(np.asarray(x, np.float32).reshape(-1)).to(dev, non_blocking=True)
+            keep.append(t)
+            return t.data_ptr() if t.numel() else None
+
+        tr.n_att = len(rows.att_node)
+        tr.att_node, tr.att_kind, tr.att_slot = dev_i32(rows.att_node), dev_i32(rows.att_kind), dev_i32(rows.att_slot)
+        tr.att_gold = dev_f32(np.stack(rows.att_gold) if rows.att_gold else np.zeros(0, np.float32))
+        tr.att_w = dev_f32(rows.att_w)
+        tr.n_bin = len(rows.bin_node)
+        tr.bin_node, tr.bin_which, tr.bin_label, tr.bin_w = dev_i32(rows.bin_node), dev_i32(rows.bin_which), dev_i32(rows.bin_label), dev_f32(rows.bin_w)
+        if tr.n_bin and not cfg['have_pretrain_head']:
+            raise L.StairError('Exists/Xor/Equals supervision needs have_pretrain_head (their criterion reads the head logits)')
+        tr.n_con = len(rows.con_node)
+        tr.con_node, tr.con_pos, tr.con_w = dev_i32(rows.con_node), dev_i32([pos_of[c] for c in rows.con_cls]), dev_f32(rows.con_w)
+        tr.n_cls = len(names)
+        tr.cls_rep = cls_rep.data_ptr() if cls_rep is not None else None
+        answer = batch.answer.to(torch.int32).to(dev, non_blocking=True)
+        keep.append(answer)
+        tr.answer = answer.data_ptr()
+        tr.dec_w = self.decoder_loss_weight / float(ga)
+        loss = torch.zeros(8, dtype=torch.float32, device=dev)
+        tr.loss = loss.data_ptr()
+        sizes = st.sizes
+        dvid = self._buf('dvid', sizes['vid'] * T * H, torch.float32, dev)
+        dvec = self._buf('dvec', sizes['vec'] * H, torch.float32, dev)
+        datt = self._buf('datt', sizes['att'] * T, torch.float32, dev)
+        dtok = self._buf('dtok', batch.n_tok * H, torch.float32, dev)
+        dq = self._buf('dq', batch.B * H, torch.float32, dev)
+        dlogits = self._buf('dlogits', batch.B * A, torch.float32, dev)
+        tr.dvid, tr.dvec, tr.datt, tr.dtokfeat, tr.dqfeat, tr.dlogits = (t.data_ptr() for t in (dvid, dvec, datt, dtok, dq, dlogits))
+        saved_bytes = int(lib.stair_train_saved_bytes(ctypes.byref(ms), ctypes.byref(sb)))
+        saved = self._buf('saved', saved_bytes, torch.uint8, dev)
+        tr.saved, tr.saved_bytes = saved.data_ptr(), saved.numel()
+        ws_bytes = int(lib.stair_train_workspace_bytes(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr)))
+        if ws_bytes < 0:
+            raise L.StairError('stair_train_workspace_bytes failed (unsupported configuration)')
+        ws = self._buf('train_ws', ws_bytes + 256, torch.uint8, dev)
+        tr.workspace, tr.workspace_bytes = ws.data_ptr(), ws.numel()
+        stream = L.stream_ptr()
+        L.check(lib.stair_nmn_forward_train(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), stream), 'stair_nmn_forward_train')
+        L.check(lib.stair_nmn_backward(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), stream), 'stair_nmn_backward')
+
+        touched = touched_slots(batch, rows, cfg['have_pretrain_head'])
+        if world > 1:
+            flag = torch.zeros(L.W_COUNT + 8, dtype=torch.float32, device=dev)
+            flag[list(touched)] = 1.0
+            dist.all_reduce(flat, group=self.group)                        # NCCL sum over NVLink: gradients
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)   # OR of the touched flags
+            dist.all_reduce(loss, group=self.group)
+            touched = set(int(i) for i in torch.nonzero(flag[:L.W_COUNT]).flatten().tolist())
+        if assign_grads:
+            for wid, (numel, targets) in tg.items():
+                if wid not in touched:
+                    continue
+                used = set()
+                for p, o in targets:
+                    if not p.requires_grad:
+                        continue
+                    g = flat[offsets[wid] + o: offsets[wid] + o + p.numel()].view_as(p)
+                    if o in used:
+                        g = g.clone()                                        # the two LSTM biases of a direction share a slot
+                    used.add(o)
+                    p.grad = g if p.grad is None else p.grad + g
+        self.last = dict(state=st, rows=rows, flat=flat, offsets=offsets, touched=touched, keep=keep, train=tr, class_names=names,
+                         cls_rep=cls_rep)
+        return {'logits': st.logits, 'answers': st.answers, 'loss_terms': loss, 'loss': loss[:7].sum(), 'loss_counts': dict(rows.counts),
+                'state': st}
+
+
+class Adam:
+    """``torch.optim.Adam(lr, betas, eps, weight_decay=0)`` (train_module.py:326-332) running ``stair_adam_step`` per parameter;
+    parameters whose ``grad`` is None are skipped (and their step counter does not advance), like torch."""
+
+    def __init__(self, params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.state = {}
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    @torch.no_grad()
+    def step(self, lr=None):
+        lib = L.lib()
+        lr = self.lr if lr is None else lr
+        for p in self.params:
+            if p.grad is None:
+                continue
+            L.require_cuda(p, 'parameter')
+            s = self.state.get(id(p))
+            if s is None:
+                s = self.state[id(p)] = {'step': 0, 'm': torch.zeros_like(p, dtype=torch.float32), 'v': torch.zeros_like(p, dtype=torch.float32)}
+            s['step'] += 1
+            g = p.grad.contiguous()
+            L.check(lib.stair_adam_step(L.ptr(p), L.ptr(g), L.ptr(s['m']), L.ptr(s['v']), L.i64(p.numel()), ctypes.c_float(lr),
+                                        ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]), ctypes.c_float(self.eps),
+                                        L.i32(s['step']), L.stream_ptr()), 'stair_adam_step')
+            # the update happened behind torch's back: bump the version counter so PackedWeights.refresh re-packs
+            torch.autograd.graph.increment_version(p)

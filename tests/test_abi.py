@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), 'missing export %s' % n
-    assert lib.stair_version() == 3
+    assert lib.stair_version() == 4
 
 
 def test_host_only_entry_points():
@@ -37,7 +37,9 @@ def test_host_only_entry_points():
 
 def test_struct_sizes_match_header_layout():
     # int32 fields first, then pointers: ctypes mirrors of the C structs must have the C sizes
+    lib = L.lib()
+    lib.stair_sizeof.restype = ctypes.c_longlong
+    for which, struct in enumerate((L.StairModel, L.StairGroup, L.StairBatch, L.StairBuffers, L.StairItabLayout, L.StairTrain)):
+        assert ctypes.sizeof(struct) == lib.stair_sizeof(L.i32(which)), struct.__name__
     assert ctypes.sizeof(L.StairGroup) == 9 * 4
-    assert ctypes.sizeof(L.StairModel) == 10 * 4 + 8 * L.W_COUNT
-    assert ctypes.sizeof(L.StairBatch) == 8 * 4 + 10 * 8
-    assert ctypes.sizeof(L.StairItabLayout) == 8 * 8
+    assert ctypes.sizeof(L.StairModel) == 10 * 4 + 2 * 8 * L.W_COUNT
