@@ -83,7 +83,7 @@ class ClockSampler:
 
 def build_inputs(rank, B):
     from stair_b200 import synthetic as syn, collate
-    qs = syn.make_questions(B, T, V, seed=1234 + rank)
+    qs = syn.make_questions(B, T, V, seed=1234 + rank, with_gold=True)      # gold is only read by the training leg
     batch = collate(qs, pin_memory=True, video_dtype=torch.bfloat16, question_dtype=torch.float32)
     return qs, batch
 
@@ -161,6 +161,7 @@ def main():
     ap.add_argument('--impl', default='stair_b200', choices=['stair_b200', 'reference'])
     ap.add_argument('--batch', type=int, default=PER_GPU_B, help='questions per GPU (default: the BASELINE config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step leg (BASELINE configs[3])')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -272,6 +273,47 @@ def main():
         for i, (n, _) in enumerate(phases):
             ph_ms[n] += evs[i].elapsed_time(evs[i + 1]) / nrep
         gemm_ms += evs[len(phases)].elapsed_time(evs[len(phases) + 1]) / nrep
+    # ---- training step (BASELINE configs[3]): forward with history + intermediate-supervision losses + backward +
+    # gradient all-reduce (N > 1) + Adam, one window = the rank's 4096 questions; device-timed, max over ranks -------------
+    train = None
+    if not args.no_train:
+        from stair_b200.train import NMNTrainStep, Adam
+        tmodel = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16')
+        tmodel.load_state_dict(weights)
+        tmodel = tmodel.to(dev).train()
+        tstep = NMNTrainStep(tmodel)
+        opt = Adam(tmodel.parameters(), lr=2e-4)
+        plan = tstep.plan(batch)
+
+        def train_step():
+            out = tstep.run(plan)
+            opt.step()
+            opt.zero_grad()
+            return out
+
+        for _ in range(2):
+            out = train_step()
+        tmodel.check_status(out['state'])
+        ksteps = max(2, min(args.steps, 5))
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(ksteps):
+            out = train_step()
+        t1e.record()
+        barrier()
+        tms = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        tms = float(tms.item())
+        train = {'value': world * B * ksteps / (tms * 1e-3), 'unit': UNIT, 'ms_per_step': tms / ksteps, 'steps': ksteps,
+                 'launches_per_step': tstep.last_launches, 'window_questions': world * B, 'loss': float(out['loss']),
+                 'loss_rows': out['loss_counts'],
+                 'what': 'forward with encoder history + losses (train_module.py:83-194) + backward + %sAdam; bf16 storage, fp32 gradients'
+                         % ('NCCL gradient all-reduce + ' if world > 1 else '')}
+        del tmodel, tstep, opt, plan
+        torch.cuda.empty_cache()
+
     pk = peaks()
     flops = 2.0 * M * N * K
     achieved_tf = flops / (gemm_ms * 1e-3) / 1e12
@@ -316,7 +358,7 @@ def main():
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': batch.h2d_bytes(), 'd2h_bytes_per_step': 4 * B * world,
                         'ms_per_step': 1e3 * e2e_s / args.steps, 'timer': 'wall clock between synchronize()s, pinned host batch'},
                 'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
-                'roofline': roofline, 'phases_ms': ph_ms, 'cpu_baseline': cpu, 'parity': parity}
+                'roofline': roofline, 'phases_ms': ph_ms, 'train': train, 'cpu_baseline': cpu, 'parity': parity}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -7,6 +7,7 @@ namespace stair {
 namespace ex {
 
 
+extern thread_local long long t_last_launches;   // kernels launched by the last entry-point call on this thread
 extern int g_lstm_impl;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
 constexpr long long ROW_CAP = 65536;     // frame rows per chunk of a VID-typed group
 constexpr long long VEC_CAP = 16384;     // instances per chunk of a VEC-typed group / decoder chunk

@@ -12,11 +12,8 @@
 namespace stair {
 namespace ex {
 int g_lstm_impl = 0;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
-}
-namespace {
 thread_local long long t_last_launches = 0;
-
-}  // namespace
+}
 
 }  // namespace stair
 

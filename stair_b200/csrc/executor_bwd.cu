@@ -533,10 +533,13 @@ extern "C" int stair_nmn_forward_train(const StairModel* model, const StairBatch
     Ctx c{*model, *batch, *buf, reinterpret_cast<cudaStream_t>(stream)};
     STAIR_TRY(make_ctx(c, *model, *batch, *buf));
     if (buf->workspace_bytes < c.plan.total || buf->itab_ints < c.il.total) return STAIR_ERR_CAPACITY;
+    const long long before = g_launch_count;
     STAIR_TRY(launch_group_layouts(*batch, buf->itab, buf->status, c.st));
     STAIR_TRY(run_encoders_train(c, *train));
     STAIR_TRY(run_modules(c));
-    return run_decoder(c);
+    STAIR_TRY(run_decoder(c));
+    t_last_launches = g_launch_count - before;
+    return STAIR_OK;
 }
 
 extern "C" int stair_nmn_backward(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, void* stream) {
@@ -548,7 +551,9 @@ extern "C" int stair_nmn_backward(const StairModel* model, const StairBatch* bat
     BCtx b{c, *train, Bump(), false};
     b.ws.base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(train->workspace) + 255) & ~static_cast<uintptr_t>(255));
     b.ws.cap = train->workspace_bytes - 256;
+    const long long before = g_launch_count;
     const int rc = run_backward(b);
+    t_last_launches = g_launch_count - before;
     if (rc == STAIR_OK && b.ws.overflow) return STAIR_ERR_CAPACITY;
     return rc;
 }

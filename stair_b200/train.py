@@ -182,6 +182,7 @@ class NMNTrainStep:
         self._targets = None
         self._cache = {}
         self.last = None
+        self.last_launches = 0
 
     # ---- flat gradient buffer ------------------------------------------------------------------------------------
     def _layout(self):
@@ -205,7 +206,9 @@ class NMNTrainStep:
         return dist.get_world_size(self.group) if self.distributed else 1
 
     # ---- the step ----------------------------------------------------------------------------------------------------
-    def __call__(self, data, assign_grads=True):
+    def plan(self, data):
+        """Host work of one window: collate, apply the reference's loss inclusion rules, upload the loss-row tables.
+        The returned plan can be ``run`` repeatedly (e.g. several epochs over a resident batch)."""
         model = self.model
         dev = next(model.parameters()).device
         if dev.type != 'cuda':
@@ -216,7 +219,6 @@ class NMNTrainStep:
         if batch.answer is None:
             raise ValueError('training needs data["answer"] for every question (train_module.py:376)')
         cfg = model.config
-        T, H, A = batch.T, cfg['hidden_size'], cfg['answer_vocab_length']
         world = self._world()
         n_window = batch.B
         if world > 1:
@@ -224,8 +226,11 @@ class NMNTrainStep:
             dist.all_reduce(cnt, group=self.group)
             n_window = int(cnt.item())
         ga = self.gradient_accumulation or n_window
-        rows = collate_losses(batch, model.pretrain_modules, T, self.module_loss_weight, ga, self.modules_no_intermediate_train)
-        # window-level class text reps (train_module.py:360-366,388-406; gold text encoding module_net.py:78-89)
+        rows = collate_losses(batch, model.pretrain_modules, batch.T, self.module_loss_weight, ga, self.modules_no_intermediate_train)
+        if rows.bin_node and not cfg['have_pretrain_head']:
+            raise L.StairError('Exists/Xor/Equals supervision needs have_pretrain_head (their criterion reads the head logits)')
+        # window-level class names (train_module.py:360-366,388-406): under data parallelism the negatives of the whole
+        # window are every rank's classes, so names + word embeddings are exchanged on the host (small)
         class_emb = rows.class_emb
         if world > 1 and self.global_negatives:
             gathered = [None] * world
@@ -233,51 +238,57 @@ class NMNTrainStep:
             class_emb = {}
             for part in gathered:
                 class_emb.update(part)
-        names = sorted(class_emb)
-        cls_rep = None
-        if names:
-            _, sent = model.encode_questions([class_emb[n] for n in names])
-            cls_rep = torch.empty((len(names), H), dtype=torch.float32, device=dev)
-            L.check(L.lib().stair_l2normalize(L.i32(L.dtype_code(sent.dtype)), L.ptr(sent), L.ptr(cls_rep), L.i32(len(names)), L.i32(H),
-                                              L.stream_ptr()), 'stair_l2normalize')
-        pos_of = {n: i for i, n in enumerate(names)}
+        pl = TrainPlan()
+        pl.batch, pl.rows, pl.ga, pl.world = batch, rows, float(ga), world
+        pl.class_names = sorted(class_emb)
+        pl.class_phrases = [class_emb[n] for n in pl.class_names]
+        pos_of = {n: i for i, n in enumerate(pl.class_names)}
 
-        st, ms, sb, bufs = model.prepare(batch, frozenset(), training=True)
+        def up(x, dtype):
+            return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype).reshape(-1))).to(dev, non_blocking=True)
+
+        pl.att = (up(rows.att_node, np.int32), up(rows.att_kind, np.int32), up(rows.att_slot, np.int32),
+                  up(np.stack(rows.att_gold) if rows.att_gold else np.zeros(0), np.float32), up(rows.att_w, np.float32))
+        pl.bin = (up(rows.bin_node, np.int32), up(rows.bin_which, np.int32), up(rows.bin_label, np.int32), up(rows.bin_w, np.float32))
+        pl.con = (up(rows.con_node, np.int32), up([pos_of[c] for c in rows.con_cls], np.int32), up(rows.con_w, np.float32))
+        pl.answer = batch.answer.to(torch.int32).to(dev, non_blocking=True)
+        pl.touched = touched_slots(batch, rows, cfg['have_pretrain_head'])
+        return pl
+
+    def run(self, pl, assign_grads=True):
+        """Device work of one window: forward with history, losses, backward, (all-reduce), gradients into ``.grad``."""
+        model, batch, rows = self.model, pl.batch, pl.rows
+        dev = batch.device
+        cfg = model.config
+        T, H, A = batch.T, cfg['hidden_size'], cfg['answer_vocab_length']
         lib = L.lib()
+        # gold text reps of the window's classes (module_net.py:78-89): text encoder without grad + L2Normalize
+        cls_rep = None
+        if pl.class_names:
+            _, sent = model.encode_questions(pl.class_phrases)
+            cls_rep = torch.empty((len(pl.class_names), H), dtype=torch.float32, device=dev)
+            L.check(lib.stair_l2normalize(L.i32(L.dtype_code(sent.dtype)), L.ptr(sent), L.ptr(cls_rep), L.i32(len(pl.class_names)), L.i32(H),
+                                          L.stream_ptr()), 'stair_l2normalize')
+        st, ms, sb, bufs = model.prepare(batch, frozenset(), training=True)
         tg, offsets, flat_numel = self._layout()
         flat = torch.zeros(flat_numel, dtype=torch.float32, device=dev)
         tr = L.StairTrain()
         for wid in range(L.W_COUNT):
             tr.grad[wid] = flat.data_ptr() + 4 * offsets[wid] if wid in offsets else None
 
-        keep = []
-
-        def dev_i32(x):
-            t = torch.from_numpy(np.asarray(x, np.int32).reshape(-1)).to(dev, non_blocking=True)
-            keep.append(t)
-            return t.data_ptr() if t.numel() else None
-
-        def dev_f32(x):
-            t = torch.from_numpy(np.asarray(x, np.float32).reshape(-1)).to(dev, non_blocking=True)
-            keep.append(t)
+        def p(t):
             return t.data_ptr() if t.numel() else None
 
         tr.n_att = len(rows.att_node)
-        tr.att_node, tr.att_kind, tr.att_slot = dev_i32(rows.att_node), dev_i32(rows.att_kind), dev_i32(rows.att_slot)
-        tr.att_gold = dev_f32(np.stack(rows.att_gold) if rows.att_gold else np.zeros(0, np.float32))
-        tr.att_w = dev_f32(rows.att_w)
+        tr.att_node, tr.att_kind, tr.att_slot, tr.att_gold, tr.att_w = (p(t) for t in pl.att)
         tr.n_bin = len(rows.bin_node)
-        tr.bin_node, tr.bin_which, tr.bin_label, tr.bin_w = dev_i32(rows.bin_node), dev_i32(rows.bin_which), dev_i32(rows.bin_label), dev_f32(rows.bin_w)
-        if tr.n_bin and not cfg['have_pretrain_head']:
-            raise L.StairError('Exists/Xor/Equals supervision needs have_pretrain_head (their criterion reads the head logits)')
+        tr.bin_node, tr.bin_which, tr.bin_label, tr.bin_w = (p(t) for t in pl.bin)
         tr.n_con = len(rows.con_node)
-        tr.con_node, tr.con_pos, tr.con_w = dev_i32(rows.con_node), dev_i32([pos_of[c] for c in rows.con_cls]), dev_f32(rows.con_w)
-        tr.n_cls = len(names)
+        tr.con_node, tr.con_pos, tr.con_w = (p(t) for t in pl.con)
+        tr.n_cls = len(pl.class_names)
         tr.cls_rep = cls_rep.data_ptr() if cls_rep is not None else None
-        answer = batch.answer.to(torch.int32).to(dev, non_blocking=True)
-        keep.append(answer)
-        tr.answer = answer.data_ptr()
-        tr.dec_w = self.decoder_loss_weight / float(ga)
+        tr.answer = pl.answer.data_ptr()
+        tr.dec_w = self.decoder_loss_weight / pl.ga
         loss = torch.zeros(8, dtype=torch.float32, device=dev)
         tr.loss = loss.data_ptr()
         sizes = st.sizes
@@ -298,10 +309,12 @@ class NMNTrainStep:
         tr.workspace, tr.workspace_bytes = ws.data_ptr(), ws.numel()
         stream = L.stream_ptr()
         L.check(lib.stair_nmn_forward_train(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), stream), 'stair_nmn_forward_train')
+        launches = int(lib.stair_last_launch_count())
         L.check(lib.stair_nmn_backward(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), stream), 'stair_nmn_backward')
+        self.last_launches = launches + int(lib.stair_last_launch_count())
 
-        touched = touched_slots(batch, rows, cfg['have_pretrain_head'])
-        if world > 1:
+        touched = pl.touched
+        if pl.world > 1:
             flag = torch.zeros(L.W_COUNT + 8, dtype=torch.float32, device=dev)
             flag[list(touched)] = 1.0
             dist.all_reduce(flat, group=self.group)                        # NCCL sum over NVLink: gradients
@@ -313,18 +326,25 @@ class NMNTrainStep:
                 if wid not in touched:
                     continue
                 used = set()
-                for p, o in targets:
-                    if not p.requires_grad:
+                for prm, o in targets:
+                    if not prm.requires_grad:
                         continue
-                    g = flat[offsets[wid] + o: offsets[wid] + o + p.numel()].view_as(p)
+                    g = flat[offsets[wid] + o: offsets[wid] + o + prm.numel()].view_as(prm)
                     if o in used:
                         g = g.clone()                                        # the two LSTM biases of a direction share a slot
                     used.add(o)
-                    p.grad = g if p.grad is None else p.grad + g
-        self.last = dict(state=st, rows=rows, flat=flat, offsets=offsets, touched=touched, keep=keep, train=tr, class_names=names,
-                         cls_rep=cls_rep)
+                    prm.grad = g if prm.grad is None else prm.grad + g
+        self.last = dict(state=st, plan=pl, flat=flat, offsets=offsets, touched=touched, train=tr, cls_rep=cls_rep)
         return {'logits': st.logits, 'answers': st.answers, 'loss_terms': loss, 'loss': loss[:7].sum(), 'loss_counts': dict(rows.counts),
                 'state': st}
+
+    def __call__(self, data, assign_grads=True):
+        return self.run(self.plan(data), assign_grads=assign_grads)
+
+
+class TrainPlan:
+    """Host-collated window: batch + loss-row tables on the device (see ``NMNTrainStep.plan``)."""
+    pass
 
 
 class Adam:

@@ -52,8 +52,8 @@ def _compare_grads(model, ref_grads, no_grad_keys, precision, tag):
         l2 = float((got - g).norm()) / max(float(g.norm()), 1e-30)
         num += float((got - g).double().pow(2).sum()); den += float(g.double().pow(2).sum())
         lines.append('%-60s max|g| %.3e  err %.3e  rel %.2e  l2rel %.2e' % (k, scale, err, err / max(scale, 1e-30), l2))
-        if precision == 'fp32':
-            ok = err <= tol * scale + 1e-7
+        if precision == 'fp32':     # elementwise bar, or (isolated ReLU-mask flips at H=512) a tight L2 bar with a looser elementwise one
+            ok = err <= tol * scale + 1e-7 or (l2 <= 1e-3 and err <= 5 * tol * scale)
         else:       # bf16 storage: single ReLU-mask flips move whole rows of a sparse gradient, so the bar is the tensor's L2 error
             ok = l2 <= tol or float((got - g).norm()) <= 1e-6
         if not ok:
