@@ -41,12 +41,14 @@ struct LstmFusedParams {
 };
 #define LF_DBG(slot, val) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { p.dbg[slot] = (val); __threadfence_system(); } } while (0)
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// sigmoid(x) = 0.5 + 0.5 tanh(x / 2): one MUFU op (the cell epilogue is MUFU-bound: 5 transcendentals per hidden unit)
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -73,7 +75,7 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
 __global__ void __launch_bounds__(LF_THREADS, 1)
 lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, const LstmFusedParams p) {
-    const LstmSeq& sq = p.seq[blockIdx.z];
+    const LstmSeq sq = blockIdx.z == 0 ? p.seq[0] : p.seq[1];      // by value: a runtime index into param space forces a local copy
     const int dir = blockIdx.y;
     const int wsel = blockIdx.z * 2 + dir;          // which W_hh map (never form a runtime-selected pointer to a param-space map)
     const int row0 = blockIdx.x * LF_ROWS;
@@ -169,6 +171,24 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                 }
             }
         }
+    } else if (warp == 3) {
+        // ===================== L2 prefetcher: the input-projection rows of step s+2 (they do not depend on the recurrence) ========
+        // xproj (134 + 268 MB at B=4096) does not fit in L2; without this every epilogue load is an HBM-latency miss.
+        for (int s = 0; s < S; ++s) {
+            // pace: rows of step s are requested once step s-3 is complete (two steps ahead of the cell epilogue).  A parity wait on
+            // a phase that is already two behind simply returns one phase later; a later phase of that parity always exists here.
+            if (s >= 3) mbar_wait(h_ready, static_cast<uint32_t>((s - 3) & 1), p.err_flag, 206);
+            for (int r = lane; r < LF_ROWS; r += 32) {
+                const int grow = row0 + r;
+                if (grow >= sq.B) continue;
+                int base, L = sq.steps;
+                if (ragged) { base = __ldg(sq.q_off + grow); L = __ldg(sq.q_off + grow + 1) - base; }
+                else base = grow * sq.steps;
+                if (s >= L) continue;
+                const bf16* xrow = sq.xproj + (static_cast<long long>(base) + (dir == 0 ? s : L - 1 - s)) * 8 * h + dir * 4 * h;
+                for (int b = 0; b < 4 * h * 2; b += 128) prefetch_l2(reinterpret_cast<const char*>(xrow) + b);
+            }
+        }
     } else if (warp >= 4) {
         // ===================== cell epilogue: 2 warps per TMEM lane quarter, each takes 32 of a chunk's 64 units =============
         const int quarter = warp & 3, halfsel = (warp - 4) >> 2;
@@ -194,44 +214,47 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
             const uint32_t h_src = sH0 + static_cast<uint32_t>((s & 1) * hbuf_bytes);
             const uint32_t h_dst = sH0 + static_cast<uint32_t>(((s + 1) & 1) * hbuf_bytes);
             for (int c = 0; c < NC; ++c) {
+                // all global operands of this chunk (input projection, previous cell state) are requested before waiting for the
+                // tensor core, so their latency overlaps the MMA of this chunk instead of serialising 4x per chunk
+                uint4 xq[4][4];
+                float4 cnext[2];                                      // cell state of the next 8 units (L2-resident, one sub-block ahead)
+                if (active) {
+#pragma unroll
+                    for (int sb = 0; sb < 4; ++sb) {
+                        const int u0 = c * 64 + halfsel * 32 + sb * 8;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) xq[sb][g] = __ldg(reinterpret_cast<const uint4*>(xrow + g * h + u0));
+                    }
+                    if (s > 0) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(cblk + ((c * 64 + halfsel * 32) / 4 + q) * (LF_ROWS * 4));
+                    }
+                }
                 if (s > 0) {
                     if (lane == 0) LF_DBG(2 + (warp - 4), 0x50000u + s * 256 + c);
                     mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 205);
                     tcgen05_fence_after();
                 }
-#pragma unroll 1
+#pragma unroll
                 for (int sb = 0; sb < 4; ++sb) {
                     const int u0 = c * 64 + halfsel * 32 + sb * 8;    // 8 hidden units u0 .. u0+7 (one 16-byte chunk of the h row)
                     uint32_t gi[8], gf[8], gg[8], go[8];
-                    if (s > 0) {
+                    if (s > 0) {                                      // tcgen05.ld / wait::ld are .sync.aligned: the whole warp, converged
                         const uint32_t t = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                            static_cast<uint32_t>(acc * 256 + halfsel * 32 + sb * 8);
                         tmem_ld8(t, gi); tmem_ld8(t + 64, gf); tmem_ld8(t + 128, gg); tmem_ld8(t + 192, go);
+                        tmem_ld_wait();
                     }
                     const uint32_t ch = static_cast<uint32_t>(halfsel * 4 + sb);
                     const uint32_t a0 = static_cast<uint32_t>(c) * LF_KB_BYTES + rowoff + ((ch ^ sw) << 4);
-                    uint4 xi, xf, xg, xo;
-                    float cprev[8];
-                    if (active) {
-                        xi = __ldg(reinterpret_cast<const uint4*>(xrow + u0));
-                        xf = __ldg(reinterpret_cast<const uint4*>(xrow + h + u0));
-                        xg = __ldg(reinterpret_cast<const uint4*>(xrow + 2 * h + u0));
-                        xo = __ldg(reinterpret_cast<const uint4*>(xrow + 3 * h + u0));
-                        if (s > 0) {
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                const float4 t4 = *reinterpret_cast<const float4*>(cblk + (u0 / 4 + q) * (LF_ROWS * 4));
-                                cprev[4 * q] = t4.x; cprev[4 * q + 1] = t4.y; cprev[4 * q + 2] = t4.z; cprev[4 * q + 3] = t4.w;
-                            }
-                        }
-                    }
-                    if (s > 0) {                                      // tcgen05.wait::ld is .sync.aligned: the whole warp, converged
-                        __syncwarp();
-                        tmem_ld_wait();
-                    }
                     if (active) {
                         float fi[8], ff[8], fg[8], fo[8], hn[8], cn[8];
-                        unpack8(xi, fi); unpack8(xf, ff); unpack8(xg, fg); unpack8(xo, fo);
+                        unpack8(xq[sb][0], fi); unpack8(xq[sb][1], ff); unpack8(xq[sb][2], fg); unpack8(xq[sb][3], fo);
+                        const float cprev[8] = {cnext[0].x, cnext[0].y, cnext[0].z, cnext[0].w, cnext[1].x, cnext[1].y, cnext[1].z, cnext[1].w};
+                        if (s > 0 && sb < 3) {
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(cblk + ((u0 + 8) / 4 + q) * (LF_ROWS * 4));
+                        }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float pi = fi[j], pf = ff[j], pg = fg[j], po = fo[j], cp = 0.0f;

@@ -202,6 +202,39 @@ class Layout:
         raise KeyError(tok)
 
 
+def schedule_waves(layouts, max_iter=64):
+    """Batch-level schedule: wave index per node of every distinct layout.
+
+    The reference semantics only need "children before parents" (module_net.py:94-133).  ASAP levels
+    (``Layout.level``, = utils/program_parser.py:307-321) give one (level, op, variant) group per distinct depth at which a
+    module type occurs in the batch; delaying nodes so that all instances of one (op, variant) share a wave whenever the
+    dependencies allow merges those groups (fewer, larger launches).  Fixpoint of
+        wave(node) = max(1 + max wave(children), max over the batch of wave(nodes with the same (op, variant)))
+    which converges when the (op, variant) dependency graph of the batch is acyclic; otherwise ASAP levels are kept."""
+    waves = [lay.level.astype(np.int64).copy() for lay in layouts]
+    kinds = [lay.op.astype(np.int64) * 8 + lay.variant for lay in layouts]
+    orders = [sorted(range(lay.n), key=lambda nd, lay=lay: -lay.token_of_node[nd]) for lay in layouts]     # children first
+    for _ in range(max_iter):
+        tgt = {}
+        for w, k in zip(waves, kinds):
+            for kk, ww in zip(k.tolist(), w.tolist()):
+                if ww > tgt.get(kk, -1):
+                    tgt[kk] = ww
+        changed = False
+        for lay, w, k, order in zip(layouts, waves, kinds, orders):
+            for nd in order:
+                lv = tgt[int(k[nd])]
+                for a in lay.args[:, nd]:
+                    if a >= 0 and w[a] + 1 > lv:
+                        lv = w[a] + 1
+                if lv != w[nd]:
+                    w[nd] = lv
+                    changed = True
+        if not changed:
+            return waves
+    return [lay.level.astype(np.int64).copy() for lay in layouts]
+
+
 _LAYOUT_CACHE = {}
 
 
@@ -280,7 +313,7 @@ class NMNBatch:
         return self.itab_host[o:o + size]
 
 
-def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None) -> NMNBatch:
+def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, merge_waves=True) -> NMNBatch:
     """Collate reference-schema ``data`` dicts (video_nmn/dataset.py:189-233) into one ``NMNBatch``.
 
     Replaces the reference's ``collate_fn = examples[0]`` (video_nmn/dataset.py:463-464).  All questions of a batch
@@ -332,11 +365,14 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None) -
     by_layout = {}
     for qi, lay in enumerate(layouts):
         by_layout.setdefault(id(lay), (lay, []))[1].append(qi)
-    for lay, qs in by_layout.values():
+    distinct = [lay for lay, _ in by_layout.values()]
+    waves = schedule_waves(distinct) if merge_waves else [lay.level.astype(np.int64) for lay in distinct]
+    b.wave_of_layout = {id(lay): w for lay, w in zip(distinct, waves)}
+    for (lay, qs), wave in zip(by_layout.values(), waves):
         qs = np.asarray(qs, np.int64)
         starts = node_start[qs]
         pos = (starts[:, None] + np.arange(lay.n)[None, :]).reshape(-1)
-        node_key[pos] = np.tile(lay.key, len(qs))
+        node_key[pos] = np.tile((wave * 32 + lay.op) * 8 + lay.variant, len(qs))          # ascending key = schedule order
         node_q[pos] = np.repeat(qs, lay.n).astype(np.int32)
         for k in range(3):
             a = lay.args[k]

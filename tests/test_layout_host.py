@@ -116,3 +116,38 @@ def test_product_path_fails_loudly_without_cuda():
     m = VideoNMN(cfg)
     with pytest.raises(_lib.StairError):
         m(questions[0][0])
+
+
+def test_wave_schedule_respects_dependencies_and_merges_groups():
+    """Batch-level wave schedule (layout.schedule_waves): children strictly before parents, never more groups than the
+    ASAP levels of utils/program_parser.py:307-321, and a cyclic (op, variant) dependency graph falls back to ASAP."""
+    import numpy as np
+    from stair_b200 import layout as LY, synthetic as syn
+    lays = [LY.compile_layout(t[1]) for t in syn.ALL_TEMPLATES.values()]
+    waves = LY.schedule_waves(lays)
+    asap, merged = set(), set()
+    for lay, w in zip(lays, waves):
+        for nd in range(lay.n):
+            for a in lay.args[:, nd]:
+                if a >= 0:
+                    assert w[a] < w[nd]
+            assert w[nd] >= lay.level[nd]
+            asap.add((int(lay.level[nd]), int(lay.op[nd]), int(lay.variant[nd])))
+            merged.add((int(w[nd]), int(lay.op[nd]), int(lay.variant[nd])))
+    assert len(merged) < len(asap)
+    # all instances of one (op, variant) share a wave when the kind graph is acyclic
+    per_kind = {}
+    for lay, w in zip(lays, waves):
+        for nd in range(lay.n):
+            per_kind.setdefault((int(lay.op[nd]), int(lay.variant[nd])), set()).add(int(w[nd]))
+    assert sum(len(v) > 1 for v in per_kind.values()) <= 2
+    # Exists feeding And feeding ... and And feeding Exists in another layout: cyclic kinds -> ASAP fallback, still valid
+    a = LY.compile_layout(['And', 'Exists', 'x', 'Filter', 'video', 'objects', 'Exists', 'y', 'Filter', 'video', 'objects'])
+    b = LY.compile_layout(['Exists', 'x', 'And', 'Filter', 'video', 'objects', 'Filter', 'video', 'actions'])
+    for lay, w in zip((a, b), LY.schedule_waves([a, b])):
+        assert np.array_equal(w, lay.level)
+    # collate uses the merged schedule by default and the ASAP one on request; both give the same node -> question tables
+    qs = syn.make_questions(40, 8, 32, seed=3, templates=list(syn.ALL_TEMPLATES))
+    m, p = LY.collate(qs), LY.collate(qs, merge_waves=False)
+    assert m.n_groups < p.n_groups and m.n_nodes == p.n_nodes
+    assert np.array_equal(m.host_tab('node_q').numpy(), p.host_tab('node_q').numpy())

@@ -51,3 +51,54 @@ def test_sharded_equals_unsharded():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _train_worker(rank, world, port, q):
+    """Data-parallel training step: each rank owns half of the window; after the NCCL all-reduce every rank must hold the
+    gradients of the whole window (== one process running the full window), incl. the window-wide contrastive negatives."""
+    import torch.distributed as dist
+    from stair_b200 import VideoNMN, synthetic as syn
+    from stair_b200.distributed import shard
+    from stair_b200.train import NMNTrainStep
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        cfg = syn.model_config(T=8, V=256, hidden=128, object_types=16)
+        torch.manual_seed(0)
+        model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32').cuda().train()
+        qs = syn.make_questions(56, 8, 256, seed=5, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+        dp = NMNTrainStep(model)
+        out = dp(shard(qs, rank, world))
+        torch.cuda.synchronize()
+        g_dp = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        loss_dp = float(out['loss'])
+        model.zero_grad(set_to_none=True)
+        single = NMNTrainStep(model, distributed=False)
+        out1 = single(qs)
+        torch.cuda.synchronize()
+        g_1 = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        ok = set(g_dp) == set(g_1) and abs(loss_dp - float(out1['loss'])) <= 1e-5 * abs(loss_dp)
+        worst = 0.0
+        for k in g_1:
+            scale = float(g_1[k].abs().max())
+            worst = max(worst, float((g_dp[k] - g_1[k]).abs().max()) / max(scale, 1e-12) if scale > 1e-9 else 0.0)
+        q.put((rank, bool(ok and worst <= 1e-4), worst))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradients_equal_single_process():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[:2] for r in res] == [(0, True), (1, True)], res
