@@ -17,7 +17,6 @@ namespace stair {
 
 namespace {
 
-constexpr int LF_THREADS = 384;
 constexpr int LF_ROWS = 128;
 constexpr int LF_KB_BYTES = LF_ROWS * 64 * 2;      // one 64-wide k-block of h: 16 KiB
 constexpr int LF_W_STAGE_BYTES = 256 * 64 * 2;     // one W tile (256 gate columns x 64 k): 32 KiB
@@ -72,7 +71,9 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
     for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(hh[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
 
-__global__ void __launch_bounds__(LF_THREADS, 1)
+// CG = epilogue warps per TMEM lane quarter (each takes 64 / CG of a chunk's hidden units); threads = 128 + 128 * CG
+template <int CG>
+__global__ void __launch_bounds__(128 + 128 * CG, 1)
 lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, const LstmFusedParams p) {
     const LstmSeq sq = blockIdx.z == 0 ? p.seq[0] : p.seq[1];      // by value: a runtime index into param space forces a local copy
@@ -83,6 +84,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
     const int h = sq.h, NC = h / 64;              // chunks of 64 hidden units == k-blocks of h
     const bool ragged = sq.q_off != nullptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int LF_THREADS = 128 + 128 * CG;
+    constexpr int SBN = 8 / CG;                   // 8-unit sub-blocks per thread per chunk
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -95,13 +98,13 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
     uint64_t* tmem_full = w_empty + LF_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint64_t* h_ready = tmem_empty + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(h_ready + 1);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(h_ready + 4);     // h_ready[kb]: k-block kb (= chunk kb) of h_s is in smem
     int* s_steps = reinterpret_cast<int*>(tmem_ptr_smem + 1);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < LF_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 256); }
-        mbar_init(h_ready, 256);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128 * CG); }
+        for (int a = 0; a < 4; ++a) mbar_init(&h_ready[a], 128 * CG);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *s_steps = ragged ? 0 : sq.steps;
     }
@@ -147,9 +150,6 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
             int acc = 0; uint32_t acc_phase = 0;
             for (int s = 1; s < S; ++s) {
                 LF_DBG(1, 0x20000u + s * 256);
-                mbar_wait(h_ready, static_cast<uint32_t>((s - 1) & 1), p.err_flag, 202);   // h_{s-1} fully written to sH[s & 1]
-                LF_DBG(1, 0x21000u + s * 256);
-                tcgen05_fence_after();
                 const uint32_t hb = smem_u32(sH + (s & 1) * hbuf_bytes);
                 for (int c = 0; c < NC; ++c) {
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.err_flag, 203);
@@ -157,6 +157,9 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
                     for (int kb = 0; kb < NC; ++kb) {
                         LF_DBG(1, 0x24000u + s * 256 + c * 16 + kb);
+                        // k-block kb of h_{s-1} is complete as soon as the cell epilogue of chunk kb of step s-1 is: the first
+                        // chunk of a step starts accumulating while the last chunks of the previous step are still in their epilogue
+                        if (c == 0) mbar_wait(&h_ready[kb], static_cast<uint32_t>((s - 1) & 1), p.err_flag, 202);
                         mbar_wait(&w_full[stage], phase, p.err_flag, 204);
                         tcgen05_fence_after();
                         const uint64_t adesc = make_umma_desc_kmajor_sw128(hb + kb * LF_KB_BYTES);
@@ -177,7 +180,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
         for (int s = 0; s < S; ++s) {
             // pace: rows of step s are requested once step s-3 is complete (two steps ahead of the cell epilogue).  A parity wait on
             // a phase that is already two behind simply returns one phase later; a later phase of that parity always exists here.
-            if (s >= 3) mbar_wait(h_ready, static_cast<uint32_t>((s - 3) & 1), p.err_flag, 206);
+            if (s >= 3) mbar_wait(&h_ready[NC - 1], static_cast<uint32_t>((s - 3) & 1), p.err_flag, 206);
             for (int r = lane; r < LF_ROWS; r += 32) {
                 const int grow = row0 + r;
                 if (grow >= sq.B) continue;
@@ -191,7 +194,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
         }
     } else if (warp >= 4) {
         // ===================== cell epilogue: 2 warps per TMEM lane quarter, each takes 32 of a chunk's 64 units =============
-        const int quarter = warp & 3, halfsel = (warp - 4) >> 2;
+        const int quarter = warp & 3, halfsel = (warp - 4) >> 2;   // halfsel = column group 0..CG-1
         const int row = quarter * 32 + lane;
         const int grow = row0 + row;
         const bool valid = grow < sq.B;
@@ -216,42 +219,41 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
             for (int c = 0; c < NC; ++c) {
                 // all global operands of this chunk (input projection, previous cell state) are requested before waiting for the
                 // tensor core, so their latency overlaps the MMA of this chunk instead of serialising 4x per chunk
-                uint4 xq[4][4];
+                uint4 xq[SBN][4];
                 float4 cnext[2];                                      // cell state of the next 8 units (L2-resident, one sub-block ahead)
                 if (active) {
 #pragma unroll
-                    for (int sb = 0; sb < 4; ++sb) {
-                        const int u0 = c * 64 + halfsel * 32 + sb * 8;
+                    for (int sb = 0; sb < SBN; ++sb) {
+                        const int u0 = c * 64 + halfsel * (SBN * 8) + sb * 8;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) xq[sb][g] = __ldg(reinterpret_cast<const uint4*>(xrow + g * h + u0));
                     }
                     if (s > 0) {
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(cblk + ((c * 64 + halfsel * 32) / 4 + q) * (LF_ROWS * 4));
+                        for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(cblk + ((c * 64 + halfsel * (SBN * 8)) / 4 + q) * (LF_ROWS * 4));
                     }
                 }
                 if (s > 0) {
-                    if (lane == 0) LF_DBG(2 + (warp - 4), 0x50000u + s * 256 + c);
                     mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 205);
                     tcgen05_fence_after();
                 }
 #pragma unroll
-                for (int sb = 0; sb < 4; ++sb) {
-                    const int u0 = c * 64 + halfsel * 32 + sb * 8;    // 8 hidden units u0 .. u0+7 (one 16-byte chunk of the h row)
+                for (int sb = 0; sb < SBN; ++sb) {
+                    const int u0 = c * 64 + halfsel * (SBN * 8) + sb * 8;    // 8 hidden units u0 .. u0+7 (one 16-byte chunk of the h row)
                     uint32_t gi[8], gf[8], gg[8], go[8];
                     if (s > 0) {                                      // tcgen05.ld / wait::ld are .sync.aligned: the whole warp, converged
                         const uint32_t t = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                           static_cast<uint32_t>(acc * 256 + halfsel * 32 + sb * 8);
+                                           static_cast<uint32_t>(acc * 256 + halfsel * (SBN * 8) + sb * 8);
                         tmem_ld8(t, gi); tmem_ld8(t + 64, gf); tmem_ld8(t + 128, gg); tmem_ld8(t + 192, go);
                         tmem_ld_wait();
                     }
-                    const uint32_t ch = static_cast<uint32_t>(halfsel * 4 + sb);
+                    const uint32_t ch = static_cast<uint32_t>(halfsel * SBN + sb);
                     const uint32_t a0 = static_cast<uint32_t>(c) * LF_KB_BYTES + rowoff + ((ch ^ sw) << 4);
                     if (active) {
                         float fi[8], ff[8], fg[8], fo[8], hn[8], cn[8];
                         unpack8(xq[sb][0], fi); unpack8(xq[sb][1], ff); unpack8(xq[sb][2], fg); unpack8(xq[sb][3], fo);
                         const float cprev[8] = {cnext[0].x, cnext[0].y, cnext[0].z, cnext[0].w, cnext[1].x, cnext[1].y, cnext[1].z, cnext[1].w};
-                        if (s > 0 && sb < 3) {
+                        if (s > 0 && sb < SBN - 1) {
 #pragma unroll
                             for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(cblk + ((u0 + 8) / 4 + q) * (LF_ROWS * 4));
                         }
@@ -286,10 +288,9 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                     mbar_arrive(&tmem_empty[acc]);
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
+                fence_async_smem();                                 // this chunk of h_s (generic-proxy stores) -> visible to tcgen05.mma
+                mbar_arrive(&h_ready[c]);
             }
-            fence_async_smem();                                     // h_s (generic-proxy stores) -> visible to tcgen05.mma
-            mbar_arrive(h_ready);
-            if (lane == 0) LF_DBG(2 + (warp - 4), 0x60000u + s * 256);
         }
     }
     tcgen05_fence_before();
@@ -303,6 +304,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
 }  // namespace
 
 static volatile unsigned int* g_lstm_dbg = nullptr;
+static int g_lstm_cg = 2;
 bool lstm_fused_ok(int precision, int h) { return precision == STAIR_BF16 && h >= 64 && h <= 256 && (h % 64) == 0; }
 
 // seq 0 = video (T steps), seq 1 = text (ragged, L_max steps); either may be disabled with steps = 0.
@@ -325,13 +327,17 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
     CUtensorMap tm[4];
     for (int i = 0; i < 4; ++i) STAIR_TRY(make_tmap_bf16_2d(&tm[i], w[i], h, 4ULL * h, h, 64, 256));
     const int smem = 2 * (h / 64) * LF_KB_BYTES + LF_STAGES * LF_W_STAGE_BYTES + 256 + 1024;
-    static int configured = 0;
-    if (configured < smem) {
-        if (cudaFuncSetAttribute(lstm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return STAIR_ERR_CUDA;
-        configured = smem;
+    static int configured[2] = {0, 0};
+    const int vi = g_lstm_cg == 4 ? 1 : 0;
+    if (configured[vi] < smem) {
+        const cudaError_t e = vi ? cudaFuncSetAttribute(lstm_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                : cudaFuncSetAttribute(lstm_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return STAIR_ERR_CUDA;
+        configured[vi] = smem;
     }
     dim3 grid((B + LF_ROWS - 1) / LF_ROWS, 2, nseq);
-    lstm_fused_kernel<<<grid, LF_THREADS, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
+    if (vi) lstm_fused_kernel<4><<<grid, 128 + 128 * 4, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
+    else lstm_fused_kernel<2><<<grid, 128 + 128 * 2, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -339,3 +345,4 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
 }  // namespace stair
 
 extern "C" int stair_lstm_debug(unsigned int* pinned_buf) { stair::g_lstm_dbg = pinned_buf; return STAIR_OK; }
+extern "C" int stair_lstm_colgroups(int cg) { if (cg != 2 && cg != 4) return STAIR_ERR_ARG; stair::g_lstm_cg = cg; return STAIR_OK; }
