@@ -4,7 +4,7 @@ Public surface (mirrors video_nmn/module_net.py + video_nmn/modules.py of the re
 
     from stair_b200 import VideoNMN, collate, NAME_TO_MODULE
 """
-from .layout import NARY as nary_mappings, MODULE_NAMES, WORDS_TO_KEEP, collate, compile_layout, NMNBatch  # noqa: F401
+from .layout import NARY as nary_mappings, MODULE_NAMES, WORDS_TO_KEEP, collate, collate_chunks, compile_layout, NMNBatch  # noqa: F401
 from .nmn import VideoNMN  # noqa: F401
 from .params import L2Normalize  # noqa: F401
 

@@ -413,6 +413,20 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
     return b
 
 
+def collate_chunks(examples, n_chunks, **kw):
+    """Collate ``examples`` as ``n_chunks`` contiguous sub-batches (sizes differ by at most one) for the pipelined forward
+    (``VideoNMN.forward_pipelined``): the host->device copy of chunk k+1 overlaps the execution of chunk k."""
+    n = len(examples)
+    n_chunks = max(1, min(int(n_chunks), n))
+    base, rem = divmod(n, n_chunks)
+    out, lo = [], 0
+    for c in range(n_chunks):
+        hi = lo + base + (1 if c < rem else 0)
+        out.append(collate(examples[lo:hi], **kw))
+        lo = hi
+    return out
+
+
 def build_groups(batch: NMNBatch, head_modules=frozenset()):
     """Group table (host ``StairGroup`` array + the device [4][n_groups] int table) and arena sizes for this batch."""
     ng = batch.n_groups

@@ -137,6 +137,34 @@ class VideoNMN(nn.Module):
         self.last_launches = int(lib.stair_last_launch_count())
         return st
 
+    def forward_pipelined(self, batches, head_modules=frozenset()):
+        """Inference over a list of HOST sub-batches (``layout.collate_chunks(..., pin_memory=True)``) with the host->device
+        copies on a separate stream: the upload of chunk k+1 overlaps the execution of chunk k, so a step costs about
+        max(PCIe time, compute time) instead of their sum.  Returns (answers [B] int32, logits [B, A], per-chunk states)."""
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda':
+            raise L.StairError('VideoNMN parameters are on %s: stair_b200 runs only on CUDA (sm_100a) devices' % dev)
+        comp = torch.cuda.current_stream(dev)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cs = self._copy_stream
+        events = []
+        for b in batches:
+            with torch.cuda.stream(cs):
+                b.to(dev)
+                for t in (b.video_dev, b.question_dev, b.itab_dev):
+                    t.record_stream(comp)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            events.append(ev)
+        states = []
+        for b, ev in zip(batches, events):
+            comp.wait_event(ev)
+            states.append(self.forward_batch(b, head_modules))
+        answers = torch.cat([st.answers for st in states]) if len(states) > 1 else states[0].answers
+        logits = torch.cat([st.logits for st in states]) if len(states) > 1 else states[0].logits
+        return answers, logits, states
+
     def check_status(self, st: ForwardState):
         """Synchronising check of the device-side status word (layout grouping mismatch)."""
         code = int(st.status[0].item())

@@ -190,3 +190,22 @@ def test_fused_lstm_matches_stepwise(hidden, T):
             got_s = outs[0][2].view(-1, hidden)[qi]
             assert float((got_v - v).abs().max()) <= 3e-2 * float(v.abs().max()) + 2e-3
             assert float((got_s - sent).abs().max()) <= 3e-2 * float(sent.abs().max()) + 2e-3
+
+
+def test_pipelined_forward_equals_plain_forward():
+    """forward_pipelined (chunked H2D on a copy stream overlapping compute) returns exactly the per-question results of forward."""
+    from stair_b200 import collate_chunks
+    T, V = 8, 256
+    cfg = syn.model_config(T=T, V=V, hidden=128)
+    torch.manual_seed(2)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().eval()
+    qs = syn.make_questions(203, T, V, seed=17, templates=list(syn.ALL_TEMPLATES))
+    full = model(qs, return_res_by_step=False, test_mode=True)
+    chunks = collate_chunks(qs, 4, pin_memory=True, video_dtype=torch.bfloat16, question_dtype=torch.bfloat16)
+    for _ in range(2):                                         # second pass re-uploads into recycled buffers
+        answers, logits, states = model.forward_pipelined(chunks)
+    torch.cuda.synchronize()
+    for st in states:
+        model.check_status(st)
+    assert torch.equal(answers, full['answers'])
+    assert torch.equal(logits, full['logits'])
