@@ -253,6 +253,18 @@ int stair_argmax(const float* x, int32_t* out, int rows, int cols, void* stream)
 int stair_l2normalize(int dtype, const void* x, float* out, int n, int H, void* stream);
 /* LayerNorm over H (eps 1e-5, biased variance) */
 int stair_layernorm(int dtype, const void* x, const float* gamma, const float* beta, void* out, long long rows, int H, void* stream);
+/* Filter's frame aggregation (modules.py:374): out[i] = sum_t x[i*T+t]  ([n*T,H] -> [n,H], act dtype) */
+int stair_sum_frames(int dtype, const void* x, void* out, int n, int T, int H, void* stream);
+/* AttnVideoModule (modules.py:330-340): vid[out_base+i][t] = att[att_idx[i]][t] * vid[feat_idx[i]][t]  (VID arena slots, ATT rows) */
+int stair_attn_video(int dtype, void* vid, const int32_t* feat_idx, const float* att, const int32_t* att_idx, int out_base, int n, int T, int H,
+                     void* stream);
+/* ExistsFrameModule (modules.py:162-178): att[out_base+i][t] = (cos(vid[feat_idx[i]][t], vec[kw_idx[i]]) + 1) * 0.49 */
+int stair_exists_frame(int dtype, const void* vid, const int32_t* feat_idx, const void* vec, const int32_t* kw_idx, float* att, int out_base,
+                       int n, int T, int H, void* stream);
+/* HasItem tail (modules.py:128-129): att[out_base+i][t] = sigmoid(w . x[i*T+t] + b) */
+int stair_hasitem_tail(int dtype, const void* x, const float* w, const float* b, float* att, int out_base, int n, int T, int H, void* stream);
+/* TMA-staged streaming variants of the row kernels: 0 off, 1 (default) HasItem tail, 2 also the cosine maps (slower; kept for measurement) */
+int stair_set_row_stream(int on);
 /* fp32 -> bf16 rows, and fp32 -> three bf16 planes (x = p0 + p1 + p2) used by the strict mode */
 int stair_cast_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, void* stream);
 int stair_split3(const float* src, long long ld_src, void* dst, long long ld_dst, long long plane_rows, long long rows, int cols, void* stream);

@@ -190,92 +190,124 @@ int launch_word_embed(int dt, const void* tokfeat, const int* q_off, const int* 
 // cosine attention maps                        Localize modules.py:205-216, ExistsFrame modules.py:170-177
 // nn.CosineSimilarity: each side divided by max(norm, 1e-8), then dotted.  One warp per frame row.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int MAXC = 8;     // vec8 chunks cached per lane: rows up to H = 32*8*8 = 2048
+// Row kernels below keep RPW rows of CH 16-byte chunks per lane in flight per warp, in storage format (Raw8; H = 512 -> 8 rows
+// x 2 chunks): all loads of an iteration are issued before the first warp reduction, so a warp has 8-16 independent 16-byte
+// requests outstanding instead of 2 (one row at a time was latency-bound at 11-28 % of the HBM roofline,
+// profiles/r1_module_kernel_roofline.txt).
+constexpr int MAXC = 8;     // vec8 chunks per lane: rows up to H = 32*8*8 = 2048
+#define DISPATCH_CH(H, ...)                                                                   \
+    do {                                                                                      \
+        const int hc__ = (H) / 8;                                                             \
+        if (hc__ <= 32) { constexpr int CH = 1, RPW = 8; __VA_ARGS__; }                       \
+        else if (hc__ <= 64) { constexpr int CH = 2, RPW = 4; __VA_ARGS__; }                  \
+        else if (hc__ <= 128) { constexpr int CH = 4, RPW = 2; __VA_ARGS__; }                 \
+        else { constexpr int CH = 8, RPW = 1; __VA_ARGS__; }                                  \
+    } while (0)
+// single-pass kernels (each value used once) can afford twice the rows in flight
+#define DISPATCH_CH16(H, ...)                                                                 \
+    do {                                                                                      \
+        const int hc__ = (H) / 8;                                                             \
+        if (hc__ <= 32) { constexpr int CH = 1, RPW = 8; __VA_ARGS__; }                       \
+        else if (hc__ <= 64) { constexpr int CH = 2, RPW = 8; __VA_ARGS__; }                  \
+        else if (hc__ <= 128) { constexpr int CH = 4, RPW = 4; __VA_ARGS__; }                 \
+        else { constexpr int CH = 8, RPW = 2; __VA_ARGS__; }                                  \
+    } while (0)
 
-template <typename AT>
-__device__ __forceinline__ float warp_row_load_sq(const AT* row, int hc, int lane, Vec8<AT> (&x)[MAXC]) {
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-        const int c = lane + 32 * i;
-        if (c < hc) {
-            x[i].load(row + c * 8);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ss += x[i].v[j] * x[i].v[j];
-        }
-    }
-    return warp_sum(ss);
+static inline int row_grid(long long rows, int rpw) {        // blocks of 8 warps, each warp RPW rows per iteration
+    long long b = (rows + 8LL * rpw - 1) / (8LL * rpw);
+    if (b < 1) b = 1;
+    return static_cast<int>(b > 148 * 8 ? 148 * 8 : b);
 }
 
-template <typename AT>
-__global__ void cos_att_kernel(const AT* __restrict__ f, const AT* __restrict__ kmat, int K, int T, int H, float* __restrict__ att,
-                               long long out_base, long long rows) {
-    const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    const int hc = H / 8;
-    for (long long row = blockIdx.x * static_cast<long long>(warps) + (threadIdx.x >> 5); row < rows; row += static_cast<long long>(gridDim.x) * warps) {
-        const long long i = row / T;
-        const int t = static_cast<int>(row % T);
-        Vec8<AT> x[MAXC];
-        const float nf = fmaxf(sqrtf(warp_row_load_sq(f + row * H, hc, lane, x)), 1e-8f);
+// att[(out_base + inst*K + k)*T + t] = (cos(f_row, kw_row) + 1) * 0.49 for RPW frame rows at a time.
+// f rows: contiguous [rows, H] (feat_idx == null) or gathered VID slots; keyword rows: contiguous [n*K, H] (kw_idx == null) or VEC rows.
+template <typename AT, int CH, int RPW>
+__global__ void __launch_bounds__(256, 2) cos_rows_kernel(const AT* __restrict__ f, const int* __restrict__ feat_idx, const AT* __restrict__ kmat,
+                                const int* __restrict__ kw_idx, int K, int T, int H, float* __restrict__ att, long long out_base, int rows) {
+    const int lane = threadIdx.x & 31, hc = H / 8;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int row0 = warp * RPW; row0 < rows; row0 += nwarps * RPW) {
+        Raw8<AT> x[RPW][CH];
+        int inst[RPW];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const int row = row0 + r < rows ? row0 + r : rows - 1;
+            inst[r] = row / T;
+            const int t = row - inst[r] * T;
+            const AT* fr = feat_idx ? f + (static_cast<long long>(__ldg(feat_idx + inst[r])) * T + t) * H : f + static_cast<long long>(row) * H;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int c = lane + 32 * i;
+                if (c < hc) x[r][i].load(fr + c * 8); else x[r][i].zero();
+            }
+        }
         for (int k = 0; k < K; ++k) {
-            const AT* kr = kmat + (i * K + k) * H;
-            float dot = 0.f, kk = 0.f;
+            Raw8<AT> y[RPW][CH];
 #pragma unroll
-            for (int c = 0; c < MAXC; ++c) {
-                const int cc = lane + 32 * c;
-                if (cc < hc) {
-                    Vec8<AT> y; y.load(kr + cc * 8);
+            for (int r = 0; r < RPW; ++r) {
+                const AT* kr = kw_idx ? kmat + static_cast<long long>(__ldg(kw_idx + inst[r])) * H : kmat + (static_cast<long long>(inst[r]) * K + k) * H;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { dot += x[c].v[j] * y.v[j]; kk += y.v[j] * y.v[j]; }
+                for (int i = 0; i < CH; ++i) {
+                    const int c = lane + 32 * i;
+                    if (c < hc) y[r][i].load(kr + c * 8); else y[r][i].zero();
                 }
             }
-            dot = warp_sum(dot); kk = warp_sum(kk);
-            if (lane == 0) {
-                const float nk = fmaxf(sqrtf(kk), 1e-8f);
-                att[(out_base + i * K + k) * T + t] = (dot / (nf * nk) + 1.0f) * 0.49f;
+            float dot[RPW], kk[RPW], ff[RPW];
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                float d = 0.f, q = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    float xv[8], yv[8];
+                    x[r][i].unpack(xv); y[r][i].unpack(yv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { d += xv[j] * yv[j]; q += yv[j] * yv[j]; s2 += xv[j] * xv[j]; }
+                }
+                dot[r] = d; kk[r] = q; ff[r] = s2;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], o);
+                    kk[r] += __shfl_xor_sync(0xffffffffu, kk[r], o);
+                    ff[r] += __shfl_xor_sync(0xffffffffu, ff[r], o);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                if (lane == r && row0 + r < rows) {                       // lane r writes row r: RPW scattered 4-byte stores in one instruction
+                    const float nf = fmaxf(sqrtf(ff[r]), 1e-8f), nk = fmaxf(sqrtf(kk[r]), 1e-8f);
+                    const int t = (row0 + r) - inst[r] * T;
+                    att[(out_base + static_cast<long long>(inst[r]) * K + k) * T + t] = (dot[r] / (nf * nk) + 1.0f) * 0.49f;
+                }
             }
         }
     }
 }
+
+int g_row_stream = 1;
 
 int launch_cos_att(int dt, const void* f, const void* kmat, int K, int T, int H, float* att, long long out_base, int n, cudaStream_t st) {
     if (n <= 0) return STAIR_OK;
     if (H % 8 || H > 256 * MAXC) return STAIR_ERR_UNSUPPORTED;
+    if (g_row_stream >= 2 && row_stream_ok(dt, K, T, H)) return launch_cos_stream(dt, f, nullptr, kmat, nullptr, K, T, H, att, out_base, n, st);
     const long long rows = static_cast<long long>(n) * T;
-    const int grid = min(blocks_for(rows, 8), 148 * 8);
-    DISPATCH_DT(dt, AT, (cos_att_kernel<AT><<<grid, 256, 0, st>>>(reinterpret_cast<const AT*>(f), reinterpret_cast<const AT*>(kmat), K, T, H, att, out_base, rows)));
+    DISPATCH_DT(dt, AT, DISPATCH_CH(H, (cos_rows_kernel<AT, CH, RPW><<<row_grid(rows, RPW), 256, 0, st>>>(
+                            reinterpret_cast<const AT*>(f), nullptr, reinterpret_cast<const AT*>(kmat), nullptr, K, T, H, att, out_base, static_cast<int>(rows)))));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
-}
-
-template <typename AT>
-__global__ void existsframe_kernel(const AT* __restrict__ vid, const int* __restrict__ feat_idx, const AT* __restrict__ vec,
-                                   const int* __restrict__ kw_idx, float* __restrict__ att, int out_base, long long rows, int T, int H) {
-    const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    const int hc = H / 8;
-    for (long long row = blockIdx.x * static_cast<long long>(warps) + (threadIdx.x >> 5); row < rows; row += static_cast<long long>(gridDim.x) * warps) {
-        const int i = static_cast<int>(row / T), t = static_cast<int>(row % T);
-        const AT* fr = vid + (static_cast<long long>(__ldg(feat_idx + i)) * T + t) * H;
-        const AT* kr = vec + static_cast<long long>(__ldg(kw_idx + i)) * H;
-        float dot = 0.f, ff = 0.f, kk = 0.f;
-        for (int c = lane; c < hc; c += 32) {
-            Vec8<AT> x, y; x.load(fr + c * 8); y.load(kr + c * 8);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { dot += x.v[j] * y.v[j]; ff += x.v[j] * x.v[j]; kk += y.v[j] * y.v[j]; }
-        }
-        dot = warp_sum(dot); ff = warp_sum(ff); kk = warp_sum(kk);
-        if (lane == 0)
-            att[static_cast<long long>(out_base + i) * T + t] = (dot / (fmaxf(sqrtf(ff), 1e-8f) * fmaxf(sqrtf(kk), 1e-8f)) + 1.0f) * 0.49f;
-    }
 }
 
 int launch_existsframe(int dt, const void* vid, const int* feat_idx, const void* vec, const int* kw_idx, float* att, int out_base,
                        int n, int T, int H, cudaStream_t st) {
     if (n <= 0) return STAIR_OK;
+    if (H % 8 || H > 256 * MAXC) return STAIR_ERR_UNSUPPORTED;
+    if (g_row_stream >= 2 && row_stream_ok(dt, 1, T, H)) return launch_cos_stream(dt, vid, feat_idx, vec, kw_idx, 1, T, H, att, out_base, n, st);
     const long long rows = static_cast<long long>(n) * T;
-    const int grid = min(blocks_for(rows, 8), 148 * 8);
-    DISPATCH_DT(dt, AT, (existsframe_kernel<AT><<<grid, 256, 0, st>>>(reinterpret_cast<const AT*>(vid), feat_idx, reinterpret_cast<const AT*>(vec),
-                                                                      kw_idx, att, out_base, rows, T, H)));
+    DISPATCH_DT(dt, AT, DISPATCH_CH(H, (cos_rows_kernel<AT, CH, RPW><<<row_grid(rows, RPW), 256, 0, st>>>(
+                            reinterpret_cast<const AT*>(vid), feat_idx, reinterpret_cast<const AT*>(vec), kw_idx, 1, T, H, att, out_base, static_cast<int>(rows)))));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -345,42 +377,74 @@ int launch_temporal_relate(const float* att, const int* att_idx, int K, int mode
 // ------------------------------------------------------------------------------------------------------------------
 // LayerNorm(H), eps 1e-5, biased variance (Temporal.layer_norm, modules.py:283,327).  One warp per row.
 // ------------------------------------------------------------------------------------------------------------------
-template <typename AT>
-__global__ void layernorm_kernel(const AT* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+template <typename AT, int CH, int RPW>
+__global__ void __launch_bounds__(256, 2) layernorm_kernel(const AT* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  AT* __restrict__ out, long long rows, int H) {
-    const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    const int hc = H / 8;
-    for (long long row = blockIdx.x * static_cast<long long>(warps) + (threadIdx.x >> 5); row < rows; row += static_cast<long long>(gridDim.x) * warps) {
-        Vec8<AT> v[MAXC];
-        float s = 0.f;
+    const int lane = threadIdx.x & 31, hc = H / 8;
+    const long long warp = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    const float fh = static_cast<float>(H);
+    for (long long row0 = warp * RPW; row0 < rows; row0 += nwarps * RPW) {
+        Raw8<AT> v[RPW][CH];
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
-            const int c = lane + 32 * i;
-            if (c < hc) {
-                v[i].load(x + row * H + c * 8);
+        for (int r = 0; r < RPW; ++r) {
+            const long long row = row0 + r < rows ? row0 + r : rows - 1;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) s += v[i].v[j];
+            for (int i = 0; i < CH; ++i) {
+                const int c = lane + 32 * i;
+                if (c < hc) v[r][i].load(x + row * H + c * 8); else v[r][i].zero();
             }
         }
-        const float mean = warp_sum(s) / H;
-        float q = 0.f;
+        float mean[RPW], rstd[RPW];
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
-            const int c = lane + 32 * i;
-            if (c < hc) {
+        for (int r = 0; r < RPW; ++r) {
+            float s = 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { const float d = v[i].v[j] - mean; q += d * d; }
+            for (int i = 0; i < CH; ++i) {
+                float f[8]; v[r][i].unpack(f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += f[j];
             }
+            mean[r] = s;
         }
-        const float rstd = rsqrtf(warp_sum(q) / H + 1e-5f);
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            mean[r] /= fh;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+                if (lane + 32 * i < hc) {
+                    float f[8]; v[r][i].unpack(f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const float d = f[j] - mean[r]; q += d * d; }
+                }
+            rstd[r] = q;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) rstd[r] = rsqrtf(rstd[r] / fh + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
             const int c = lane + 32 * i;
             if (c < hc) {
-                Vec8<AT> o;
+                Vec8<float> g, b; g.load(gamma + c * 8); b.load(beta + c * 8);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o.v[j] = (v[i].v[j] - mean) * rstd * __ldg(gamma + c * 8 + j) + __ldg(beta + c * 8 + j);
-                o.store(out + row * H + c * 8);
+                for (int r = 0; r < RPW; ++r) {
+                    if (row0 + r < rows) {
+                        float f[8]; v[r][i].unpack(f);
+                        Vec8<AT> o;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o.v[j] = (f[j] - mean[r]) * rstd[r] * g.v[j] + b.v[j];
+                        o.store(out + (row0 + r) * H + c * 8);
+                    }
+                }
             }
         }
     }
@@ -389,8 +453,8 @@ __global__ void layernorm_kernel(const AT* __restrict__ x, const float* __restri
 int launch_layernorm(int dt, const void* x, const float* gamma, const float* beta, void* out, long long rows, int H, cudaStream_t st) {
     if (rows <= 0) return STAIR_OK;
     if (H % 8 || H > 256 * MAXC) return STAIR_ERR_UNSUPPORTED;
-    const int grid = min(blocks_for(rows, 8), 148 * 8);
-    DISPATCH_DT(dt, AT, (layernorm_kernel<AT><<<grid, 256, 0, st>>>(reinterpret_cast<const AT*>(x), gamma, beta, reinterpret_cast<AT*>(out), rows, H)));
+    DISPATCH_DT(dt, AT, DISPATCH_CH(H, (layernorm_kernel<AT, CH, RPW><<<row_grid(rows, RPW), 256, 0, st>>>(
+                            reinterpret_cast<const AT*>(x), gamma, beta, reinterpret_cast<AT*>(out), rows, H))));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -404,7 +468,17 @@ __global__ void sum_T_kernel(const AT* __restrict__ x, AT* __restrict__ out, int
         const long long r = i / hc;
         const int c = static_cast<int>(i % hc) * 8;
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int t = 0; t < T; ++t) {
+        int t = 0;
+        for (; t + 8 <= T; t += 8) {                       // 8 independent 16-byte loads in flight, summed in frame order
+            Vec8<AT> v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u].load(x + (r * T + t + u) * H + c);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v[u].v[j];
+        }
+        for (; t < T; ++t) {
             Vec8<AT> v; v.load(x + (r * T + t) * H + c);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] += v.v[j];
@@ -507,28 +581,64 @@ int launch_relate(const float* att, const int* att_idx, const float* beta, int s
 }
 
 // HasItem tail: sigmoid(Linear(H,1)(x_t))                                                  modules.py:128-129
-template <typename AT>
+template <typename AT, int CH, int RPW>
 __global__ void rowdot_sigmoid_kernel(const AT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                       float* __restrict__ att, long long out_off, long long rows, int H) {
-    const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    const int hc = H / 8;
-    for (long long row = blockIdx.x * static_cast<long long>(warps) + (threadIdx.x >> 5); row < rows; row += static_cast<long long>(gridDim.x) * warps) {
-        float s = 0.f;
-        for (int c = lane; c < hc; c += 32) {
-            Vec8<AT> v; v.load(x + row * H + c * 8);
+    const int lane = threadIdx.x & 31, hc = H / 8;
+    const long long warp = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    Vec8<float> wv[CH];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s += v.v[j] * __ldg(w + c * 8 + j);
+    for (int i = 0; i < CH; ++i) {
+        const int c = lane + 32 * i;
+        if (c < hc) wv[i].load(w + c * 8);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wv[i].v[j] = 0.f;
         }
-        s = warp_sum(s);
-        if (lane == 0) att[out_off + row] = sigmoidf_(s + __ldg(b));
+    }
+    const float bias = __ldg(b);
+    for (long long row0 = warp * RPW; row0 < rows; row0 += nwarps * RPW) {
+        Raw8<AT> v[RPW][CH];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const long long row = row0 + r < rows ? row0 + r : rows - 1;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int c = lane + 32 * i;
+                if (c < hc) v[r][i].load(x + row * H + c * 8); else v[r][i].zero();
+            }
+        }
+        float s[RPW];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                float f[8]; v[r][i].unpack(f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a += f[j] * wv[i].v[j];
+            }
+            s[r] = a;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+        float mine = 0.f;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) if (lane == r) mine = s[r];
+        if (lane < RPW && row0 + lane < rows) att[out_off + row0 + lane] = sigmoidf_(mine + bias);       // one coalesced store per warp
     }
 }
 
 int launch_rowdot_sigmoid(int dt, const void* x, const float* w, const float* b, float* att, int out_base, int n, int T, int H, cudaStream_t st) {
     if (n <= 0) return STAIR_OK;
+    if (H % 8 || H > 256 * MAXC) return STAIR_ERR_UNSUPPORTED;
+    if (g_row_stream && row_stream_ok(dt, 1, T, H)) return launch_rowdot_stream(dt, x, w, b, att, out_base, n, T, H, st);
     const long long rows = static_cast<long long>(n) * T;
-    const int grid = min(blocks_for(rows, 8), 148 * 8);
-    DISPATCH_DT(dt, AT, (rowdot_sigmoid_kernel<AT><<<grid, 256, 0, st>>>(reinterpret_cast<const AT*>(x), w, b, att, static_cast<long long>(out_base) * T, rows, H)));
+    DISPATCH_DT(dt, AT, DISPATCH_CH16(H, (rowdot_sigmoid_kernel<AT, CH, RPW><<<row_grid(rows, RPW), 256, 0, st>>>(
+                            reinterpret_cast<const AT*>(x), w, b, att, static_cast<long long>(out_base) * T, rows, H))));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -857,3 +967,19 @@ extern "C" int stair_split3(const float* src, long long ld_src, void* dst, long 
     return launch_stage_rows(STAIR_F32, src, ld_src, nullptr, 1, 1, reinterpret_cast<bf16*>(dst), ld_dst, plane_rows, 3, rows, cols,
                              reinterpret_cast<cudaStream_t>(stream));
 }
+
+extern "C" int stair_sum_frames(int dtype, const void* x, void* out, int n, int T, int H, void* stream) {
+    return launch_sum_T(dtype, x, out, n, T, H, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int stair_attn_video(int dtype, void* vid, const int32_t* feat_idx, const float* att, const int32_t* att_idx, int out_base, int n, int T,
+                                int H, void* stream) {
+    return launch_attnvideo(dtype, vid, feat_idx, att, att_idx, out_base, n, T, H, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int stair_exists_frame(int dtype, const void* vid, const int32_t* feat_idx, const void* vec, const int32_t* kw_idx, float* att, int out_base,
+                                  int n, int T, int H, void* stream) {
+    return launch_existsframe(dtype, vid, feat_idx, vec, kw_idx, att, out_base, n, T, H, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int stair_hasitem_tail(int dtype, const void* x, const float* w, const float* b, float* att, int out_base, int n, int T, int H, void* stream) {
+    return launch_rowdot_sigmoid(dtype, x, w, b, att, out_base, n, T, H, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int stair_set_row_stream(int on) { g_row_stream = on < 0 ? 0 : (on > 2 ? 2 : on); return STAIR_OK; }

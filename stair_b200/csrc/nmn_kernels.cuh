@@ -60,6 +60,14 @@ int launch_l2norm(int dt, const void* vec, int row_base, float* out, int out_bas
 int launch_argmax(const float* logits, int* out, int rows, int cols, cudaStream_t st);
 int launch_relate_scan(const float* att, int mode, float* out, int n, int T, cudaStream_t st);
 
+// TMA-staged streaming versions (row_stream.cu) of the cosine maps and the HasItem tail; row_stream_ok says which shapes they cover
+bool row_stream_ok(int dt, int K, int T, int H);
+int launch_cos_stream(int dt, const void* f, const int* feat_idx, const void* kw, const int* kw_idx, int K, int T, int H, float* att,
+                      long long out_base, int n, cudaStream_t st);
+int launch_rowdot_stream(int dt, const void* x, const float* w, const float* b, float* att, long long out_base, int n, int T, int H, cudaStream_t st);
+extern int g_row_stream;      // 0: register-staged kernels only; 1 (default): HasItem tail streams; 2: the cosine maps stream too (measured slower: their
+                              // three reductions per 1 KB row are issue-bound, not bandwidth-bound)
+
 // ---- LSTM cells (gate order i,f,g,o; nn.LSTM, video_nmn/module_net.py:39-47) -------------------------------------
 // xproj [rows, 8h] = W_ih x + b for both directions (fwd gates | reverse gates); g [2][B, 4h] = W_hh h_prev (fp32);
 // c [2][B,h] fp32; hstate bf16 [nplanes][2*B, h] (A operand of the next step; direction d at rows d*B..);
