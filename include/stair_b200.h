@@ -206,6 +206,7 @@ int stair_gemm_bf16_gather(const void* arena, long long ld, long long arena_slot
                            int out_dtype, int M, int N, int K, int act, void* stream);
 int stair_set_gemm_impl(int impl);      /* 0 = tcgen05 (product); 1 = SIMT debug kernel used to cross-check in tests */
 int stair_get_gemm_impl(void);
+int stair_set_gemm_split_k(int on);      /* 1 (default) = split-K with atomic accumulation for accumulating GEMMs with few output tiles */
 int stair_set_gemm_epilogue(int impl);  /* 0 = smem-staged TMA-store epilogue (product); 1 = direct per-row stores (comparison) */
 int stair_gemm_debug_timeline(unsigned long long* dev_buf /* 8 x u64, or NULL to disable */);
 int stair_gemm_error_flag(void);

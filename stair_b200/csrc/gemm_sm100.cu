@@ -27,6 +27,8 @@ constexpr int GEMM_THREADS = 256;
 struct GemmParams {
     int M, N, K;
     int num_kb;            // ceil(K / 64)
+    int ksplit;            // split-K factor (>1 only with accumulate: partial tiles are added to C with vector atomics)
+    int kb_per_split;      // k-blocks per split
     int nseg;              // 1, or 6 in split mode
     int a_plane_rows, w_plane_rows;
     const float* bias;     // [N] or null
@@ -142,6 +144,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 float4 r = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.ksplit > 1) { atomicAdd(reinterpret_cast<float4*>(out + j), r); continue; }     // red.global.add.v4.f32
                 if (p.accumulate) {
                     float4 o = *reinterpret_cast<const float4*>(out + j);
                     r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
@@ -149,7 +152,11 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int
                 *reinterpret_cast<float4*>(out + j) = r;
             }
         } else {
-            for (int j = 0; j < 32; ++j) if (n + j < p.N) out[j] = p.accumulate ? out[j] + v[j] : v[j];
+            for (int j = 0; j < 32; ++j)
+                if (n + j < p.N) {
+                    if (p.ksplit > 1) atomicAdd(out + j, v[j]);
+                    else out[j] = p.accumulate ? out[j] + v[j] : v[j];
+                }
         }
     }
 }
@@ -179,8 +186,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 0) dbg_stamp(p, 0);
     const int tiles_n = (p.N + BN - 1) / BN;
     const int tiles_m = (p.M + BM - 1) / BM;
-    const int total_tiles = tiles_m * tiles_n;
-    const int kiters = p.nseg * p.num_kb;
+    const int mn_tiles = tiles_m * tiles_n;
+    const int total_tiles = mn_tiles * p.ksplit;           // work item = (output tile, K split); the K splits of a tile are adjacent in time
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -203,7 +210,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0) {
         // ===================== TMA producer (whole warp: in gather mode lane j loads slot j of the tile) ==========
         int stage = 0; uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+            const int tile = item % mn_tiles, ks = item / mn_tiles;
+            const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             int my_slot = -1, nvalid = 0;
             if (p.a_slots) {
@@ -215,7 +224,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int seg = 0; seg < p.nseg; ++seg) {
                 const int a_row = m0 + (p.nseg > 1 ? c_seg_a[seg] * p.a_plane_rows : 0);
                 const int b_row = n0 + (p.nseg > 1 ? c_seg_b[seg] * p.w_plane_rows : 0);
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     if (lane == 0) {
                         mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 101);
                         mbar_arrive_expect_tx(&full_bar[stage], a_bytes + B_STAGE_BYTES);
@@ -237,14 +246,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // ===================== MMA issuer =====================
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+                const int ks = item / mn_tiles;
+                const int kiters = p.nseg * (min(p.num_kb, (ks + 1) * p.kb_per_split) - ks * p.kb_per_split);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.err_flag, 102);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
                 for (int it = 0; it < kiters; ++it) {
                     mbar_wait(&full_bar[stage], phase, p.err_flag, 103);
                     tcgen05_fence_after();
-                    if (it == 0 && tile == blockIdx.x) dbg_stamp(p, 2);
+                    if (it == 0 && item == blockIdx.x) dbg_stamp(p, 2);
                     const uint64_t adesc = make_umma_desc_kmajor_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
                     const uint64_t bdesc = make_umma_desc_kmajor_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
 #pragma unroll
@@ -264,11 +275,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int quarter = warp - 4;                          // TMEM lanes [32*quarter, 32*quarter+32)
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+            const int tile = item % mn_tiles;
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 104);
             tcgen05_fence_after();
-            if (threadIdx.x == 128 && tile == blockIdx.x) dbg_stamp(p, 3);
+            if (threadIdx.x == 128 && item == blockIdx.x) dbg_stamp(p, 3);
             const int row = m0 + quarter * 32 + lane;
             const uint32_t t_base = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
             if (p.tma_store) {
@@ -406,6 +418,7 @@ static int g_gemm_impl = 0;      // 0 = tcgen05 (product), 1 = SIMT debug kernel
 static int g_epilogue_impl = 0;  // 0 = staged TMA-store epilogue, 1 = direct per-row stores (debug / comparison)
 static int* g_err_flag = nullptr;
 static int g_num_sms = 0;
+static int g_split_k = 1;        // 1 = split-K for accumulating GEMMs with few output tiles (weight gradients)
 static unsigned long long* g_dbg = nullptr;
 
 int* err_flag_ptr() {
@@ -426,8 +439,20 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
         configured = true;
     }
     const int tiles = ceil_div(p.M, BM) * ceil_div(p.N, BN);
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, tc, p);
+    GemmParams q = p;
+    // split-K for accumulating GEMMs with few output tiles and a long contraction (weight gradients: [N,K] outputs of a few
+    // tiles, contraction over thousands of rows): every SM gets a K range, partial tiles are added with vector atomics
+    if (p.accumulate && !p.bias && !p.row_scale && p.act == STAIR_ACT_NONE && g_split_k && tiles * 2 <= g_num_sms && p.num_kb >= 8) {
+        int ks = g_num_sms / tiles;
+        if (ks > p.num_kb / 4) ks = p.num_kb / 4;
+        if (ks > 1) {
+            q.kb_per_split = ceil_div(p.num_kb, ks);
+            q.ksplit = ceil_div(p.num_kb, q.kb_per_split);
+        }
+    }
+    const int items = tiles * q.ksplit;
+    const int grid = items < g_num_sms ? items : g_num_sms;
+    gemm_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, tc, q);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -443,6 +468,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     if (gather && (a.nplanes != 1 || !gemm_gather_ok(a.slot_rows) || a.M % a.slot_rows)) return STAIR_ERR_ARG;
     GemmParams p;
     p.M = a.M; p.N = a.N; p.K = a.K; p.num_kb = ceil_div(a.K, BK); p.nseg = a.nplanes == 3 ? 6 : 1;
+    p.ksplit = 1; p.kb_per_split = p.num_kb;
     p.a_plane_rows = a.a_plane_rows; p.w_plane_rows = a.w_plane_rows;
     p.bias = a.bias; p.row_scale = a.row_scale; p.C = a.C; p.ldc = a.ldc; p.out_dtype = a.out_dtype; p.act = a.act;
     p.accumulate = a.accumulate;
@@ -489,6 +515,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
 using namespace stair;
 
 extern "C" int stair_set_gemm_impl(int impl) { g_gemm_impl = impl; return STAIR_OK; }
+extern "C" int stair_set_gemm_split_k(int on) { g_split_k = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_gemm_debug_timeline(unsigned long long* dev_buf) { g_dbg = dev_buf; return STAIR_OK; }
 extern "C" int stair_set_gemm_epilogue(int impl) { g_epilogue_impl = impl; return STAIR_OK; }
 extern "C" int stair_get_gemm_impl() { return g_gemm_impl; }

@@ -24,6 +24,10 @@ __device__ __forceinline__ void split3f(float x, bf16& p0, bf16& p1, bf16& p2) {
     r -= __bfloat162float(p1);
     p2 = __float2bfloat16_rn(r);
 }
+__device__ __forceinline__ uint32_t pack_bf16_(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ void store_planes1(float v, bf16* dst, long long plane_stride, int nplanes) {
     if (nplanes == 1) { *dst = __float2bfloat16_rn(v); return; }
     bf16 a, b, c;
@@ -34,30 +38,81 @@ __device__ __forceinline__ void store_planes1(float v, bf16* dst, long long plan
 // ------------------------------------------------------------------------------------------------------------------
 // Linear backward staging
 // ------------------------------------------------------------------------------------------------------------------
+// One thread = 8 consecutive columns of one row (two float4 loads of dY, one 16-byte load of Y, 16-byte bf16 stores); the
+// column sums of the bias gradient are kept in registers over the block's rows, reduced through shared memory and added with
+// one atomic per column and block.
 template <typename YT>
 __global__ void dz_prep_kernel(const float* __restrict__ dY, long long ld_dy, const YT* __restrict__ Y, long long ld_y,
                                const float* __restrict__ rs, bf16* __restrict__ dZ, bf16* __restrict__ dZs, long long n_ld,
-                               long long plane_rows, int nplanes, float* __restrict__ db, int M, int N, int rows_per_block) {
-    const int nch = static_cast<int>(n_ld);                     // one thread per column (coalesced along N)
-    const int cols_b = nch < 256 ? nch : 256;
-    const int rl = threadIdx.x / cols_b, rstep = 256 / cols_b;
+                               long long plane_rows, int nplanes, float* __restrict__ db, int M, int N, int rows_per_block, int vec_ok) {
+    __shared__ float red[256 * 8];
+    const int n8 = static_cast<int>(n_ld / 8);
+    const int cols_b = n8 < 256 ? n8 : 256;                      // threads along the columns
+    const int rstep = 256 / cols_b;                              // rows processed in parallel by the block
+    const int rl = threadIdx.x / cols_b, cl = threadIdx.x % cols_b;
     const int m_begin = blockIdx.x * rows_per_block, m_end = min(M, m_begin + rows_per_block);
     const long long ps = plane_rows * n_ld;
-    for (int c0 = 0; c0 < nch; c0 += cols_b) {
-        const int col = c0 + threadIdx.x % cols_b;
-        float colsum = 0.f;
-        if (rl < rstep && col < nch) {
+    for (int c0 = 0; c0 < n8; c0 += cols_b) {
+        const int ch = c0 + cl, col = ch * 8;
+        float colsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (rl < rstep && ch < n8) {
             for (int m = m_begin + rl; m < m_end; m += rstep) {
-                float dz = 0.f;
-                if (col < N) {
-                    dz = dY[static_cast<long long>(m) * ld_dy + col];
-                    if (Y && !(ld1<YT>(Y + static_cast<long long>(m) * ld_y + col) > 0.f)) dz = 0.f;
+                float dz[8];
+                if (vec_ok && col + 8 <= N) {
+                    const float4 a = *reinterpret_cast<const float4*>(dY + static_cast<long long>(m) * ld_dy + col);
+                    const float4 b = *reinterpret_cast<const float4*>(dY + static_cast<long long>(m) * ld_dy + col + 4);
+                    dz[0] = a.x; dz[1] = a.y; dz[2] = a.z; dz[3] = a.w; dz[4] = b.x; dz[5] = b.y; dz[6] = b.z; dz[7] = b.w;
+                    if (Y) {
+                        Vec8<YT> y; y.load(Y + static_cast<long long>(m) * ld_y + col);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (!(y.v[j] > 0.f)) dz[j] = 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v = 0.f;
+                        if (col + j < N) {
+                            v = dY[static_cast<long long>(m) * ld_dy + col + j];
+                            if (Y && !(ld1<YT>(Y + static_cast<long long>(m) * ld_y + col + j) > 0.f)) v = 0.f;
+                        }
+                        dz[j] = v;
+                    }
                 }
-                colsum += dz;
-                store_planes1(dz, dZ + static_cast<long long>(m) * n_ld + col, ps, nplanes);
-                if (dZs) store_planes1(dz * __ldg(rs + m), dZs + static_cast<long long>(m) * n_ld + col, ps, nplanes);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) colsum[j] += dz[j];
+                bf16* d = dZ + static_cast<long long>(m) * n_ld + col;
+                if (nplanes == 1) {
+                    *reinterpret_cast<uint4*>(d) = make_uint4(pack_bf16_(dz[0], dz[1]), pack_bf16_(dz[2], dz[3]), pack_bf16_(dz[4], dz[5]), pack_bf16_(dz[6], dz[7]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) store_planes1(dz[j], d + j, ps, nplanes);
+                }
+                if (dZs) {
+                    const float r = __ldg(rs + m);
+                    bf16* e = dZs + static_cast<long long>(m) * n_ld + col;
+                    if (nplanes == 1) {
+                        *reinterpret_cast<uint4*>(e) = make_uint4(pack_bf16_(dz[0] * r, dz[1] * r), pack_bf16_(dz[2] * r, dz[3] * r),
+                                                                  pack_bf16_(dz[4] * r, dz[5] * r), pack_bf16_(dz[6] * r, dz[7] * r));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) store_planes1(dz[j] * r, e + j, ps, nplanes);
+                    }
+                }
             }
-            if (db && col < N && colsum != 0.f) atomicAdd(db + col, colsum);
+        }
+        if (db) {                                                // block-level column sums -> one atomic per column
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = colsum[j];
+            __syncthreads();
+            if (rl == 0 && ch < n8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float t = 0.f;
+                    for (int r = 0; r < rstep; ++r) t += red[(r * cols_b + cl) * 8 + j];
+                    if (col + j < N && t != 0.f) atomicAdd(db + col + j, t);
+                }
+            }
+            __syncthreads();
         }
     }
 }
@@ -65,37 +120,67 @@ __global__ void dz_prep_kernel(const float* __restrict__ dY, long long ld_dy, co
 int launch_dz_prep(int ydt, const float* dY, long long ld_dy, const void* Y, long long ld_y, const float* rs, bf16* dZ, bf16* dZs,
                    long long n_ld, long long plane_rows, int nplanes, float* db, int M, int N, cudaStream_t st) {
     if (M <= 0 || N <= 0) return STAIR_OK;
-    int rpb = (M + 591) / 592;
+    if (n_ld % 8) return STAIR_ERR_ARG;
+    int rpb = (M + 1183) / 1184;
     if (rpb < 8) rpb = 8;
     const int grid = (M + rpb - 1) / rpb;
+    const int yesz = ydt == STAIR_BF16 ? 2 : 4;
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(dY) & 15) == 0 && (ld_dy % 4) == 0 &&
+                        (!Y || ((reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (ld_y * yesz) % 16 == 0))) ? 1 : 0;
     DISPATCH_DT(ydt, YT, (dz_prep_kernel<YT><<<grid, 256, 0, st>>>(dY, ld_dy, reinterpret_cast<const YT*>(Y), ld_y, rs, dZ, rs ? dZs : nullptr,
-                                                                   n_ld, plane_rows, nplanes, db, M, N, rpb)));
+                                                                   n_ld, plane_rows, nplanes, db, M, N, rpb, vec_ok)));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
 
+// 64 x 64 bf16 tiles through shared memory: 16-byte loads along the source rows, 16-byte stores along the destination rows.
 __global__ void transpose_planes_kernel(const bf16* __restrict__ src, long long ld_src, long long src_plane, bf16* __restrict__ dst,
-                                        long long ld_dst, long long dst_plane, int R, int C) {
-    __shared__ unsigned short tile[32][33];
+                                        long long ld_dst, long long dst_plane, int R, int C, int vec_ok) {
+    __shared__ unsigned short tile[64][66];
     const unsigned short* s = reinterpret_cast<const unsigned short*>(src) + blockIdx.z * src_plane;
     unsigned short* d = reinterpret_cast<unsigned short*>(dst) + blockIdx.z * dst_plane;
-    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int r = r0 + i, c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (r < R && c < C) ? s[static_cast<long long>(r) * ld_src + c] : static_cast<unsigned short>(0);
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const int tr = threadIdx.x >> 3, tc = (threadIdx.x & 7) * 8;           // 32 rows x 8 column chunks per pass
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int r = r0 + tr + 32 * pass, c = c0 + tc;
+        unsigned short v[8];
+        if (vec_ok && r < R && c + 8 <= C) {
+            const uint4 q = *reinterpret_cast<const uint4*>(s + static_cast<long long>(r) * ld_src + c);
+            const unsigned short* h = reinterpret_cast<const unsigned short*>(&q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = h[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (r < R && c + j < C) ? s[static_cast<long long>(r) * ld_src + c + j] : static_cast<unsigned short>(0);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tile[tr + 32 * pass][tc + j] = v[j];
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int c = c0 + i, r = r0 + threadIdx.x;
-        if (c < C && r < ld_dst) d[static_cast<long long>(c) * ld_dst + r] = tile[threadIdx.x][i];
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int c = c0 + tr + 32 * pass;                       // destination row = source column
+        const int r = r0 + tc;                                   // 8 consecutive destination columns = source rows
+        if (c < C && r < ld_dst) {
+            uint4 q;
+            unsigned short* h = reinterpret_cast<unsigned short*>(&q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = tile[tc + j][tr + 32 * pass];
+            if (r + 8 <= ld_dst) *reinterpret_cast<uint4*>(d + static_cast<long long>(c) * ld_dst + r) = q;
+            else
+                for (int j = 0; j < 8 && r + j < ld_dst; ++j) d[static_cast<long long>(c) * ld_dst + r + j] = h[j];
+        }
     }
 }
 
 int launch_transpose_planes(const bf16* src, long long ld_src, long long src_plane_rows, bf16* dst, long long ld_dst, long long dst_plane_rows,
                             int nplanes, int R, int C, cudaStream_t st) {
     if (R <= 0 || C <= 0) return STAIR_OK;
-    dim3 grid((C + 31) / 32, static_cast<unsigned>((ld_dst + 31) / 32), nplanes), block(32, 8);
-    transpose_planes_kernel<<<grid, block, 0, st>>>(src, ld_src, src_plane_rows * ld_src, dst, ld_dst, dst_plane_rows * ld_dst, R, C);
+    if (ld_dst % 8) return STAIR_ERR_ARG;
+    dim3 grid((C + 63) / 64, static_cast<unsigned>((ld_dst + 63) / 64), nplanes);
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (ld_src % 8) == 0 && ((src_plane_rows * ld_src) % 8) == 0) ? 1 : 0;
+    transpose_planes_kernel<<<grid, 256, 0, st>>>(src, ld_src, src_plane_rows * ld_src, dst, ld_dst, dst_plane_rows * ld_dst, R, C, vec_ok);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
