@@ -206,31 +206,35 @@ class VideoNMN(nn.Module):
         return ret
 
     # ---- text encoder alone (module_net.py:147-158) -------------------------------------------------------------------
-    def encode_questions(self, questions):
-        """List of [L_i, text] embeddings -> (list of token features [L_i, H], sentence features [n, H])."""
+    def pack_questions(self, questions):
+        """Upload a list of [L_i, text] word-embedding phrases once: (packed [n_tok, text] fp32, q_off [n+1] int32 on the
+        device, host offsets, L_max).  ``encode_packed`` can then run any number of times without touching the host."""
         dev = next(self.parameters()).device
+        lens = np.array([int(q.shape[0]) for q in questions], np.int64)
+        q_off = np.zeros(len(questions) + 1, np.int64)
+        np.cumsum(lens, out=q_off[1:])
+        packed = torch.cat([q.detach().reshape(-1, self.config['text_size']).to(torch.float32) for q in questions]).to(dev)
+        qo = torch.from_numpy(q_off.astype(np.int32)).to(dev)
+        return packed, qo, q_off, int(lens.max())
+
+    def encode_packed(self, packed, qo, q_off, L_max):
+        """Text encoder (module_net.py:147-158) over packed phrases -> (token features [n_tok, H], sentence features [n, H])."""
+        dev = packed.device
         cfg = self.config
         H = cfg['hidden_size']
-        tb = LY.NMNBatch()
-        tb.B = len(questions)
-        lens = np.array([int(q.shape[0]) for q in questions], np.int64)
-        q_off = np.zeros(tb.B + 1, np.int64)
-        np.cumsum(lens, out=q_off[1:])
-        n_tok = int(q_off[-1])
-        packed = torch.cat([q.detach().reshape(-1, cfg['text_size']).to(torch.float32) for q in questions]).to(dev)
+        n, n_tok = len(q_off) - 1, int(q_off[-1])
         model = self._packed.refresh(self.submodules, cfg, PRECISIONS[self.precision], dev)
         sb = L.StairBatch()
-        sb.B, sb.T, sb.n_tok, sb.L_max, sb.n_nodes, sb.n_groups = tb.B, cfg['max_video_length'], n_tok, int(lens.max()), 0, 0
+        sb.B, sb.T, sb.n_tok, sb.L_max, sb.n_nodes, sb.n_groups = n, cfg['max_video_length'], n_tok, L_max, 0, 0
         sb.video_dtype, sb.question_dtype = L.F32, L.F32
-        qo = torch.from_numpy(q_off.astype(np.int32)).to(dev)
         sb.question, sb.q_off = packed.data_ptr(), qo.data_ptr()
         lib = L.lib()
         adt = self.act_dtype
         ws = torch.empty(int(lib.stair_nmn_workspace_bytes(ctypes.byref(model), ctypes.byref(sb))), dtype=torch.uint8, device=dev)
         tok = torch.empty((n_tok, H), dtype=adt, device=dev)
-        sent = torch.empty((tb.B, H), dtype=adt, device=dev)
+        sent = torch.empty((n, H), dtype=adt, device=dev)
         itab = torch.empty(int(lib.stair_itab_ints(L.i32(0), L.i32(0))) + 4, dtype=torch.int32, device=dev)
-        status = torch.zeros(4, dtype=torch.int32, device=dev)
+        status = torch.empty(4, dtype=torch.int32, device=dev)
         bufs = L.StairBuffers()
         bufs.tokfeat, bufs.qfeat = tok.data_ptr(), sent.data_ptr()
         bufs.itab, bufs.itab_ints = itab.data_ptr(), itab.numel()
@@ -238,7 +242,13 @@ class VideoNMN(nn.Module):
         bufs.status = status.data_ptr()
         L.check(lib.stair_nmn_forward(ctypes.byref(model), ctypes.byref(sb), ctypes.byref(bufs), L.i32(L.FWD_ENCODE_TEXT), L.stream_ptr()),
                 'stair_nmn_forward(text)')
-        return [tok[q_off[i]:q_off[i + 1]] for i in range(tb.B)], sent
+        return tok, sent
+
+    def encode_questions(self, questions):
+        """List of [L_i, text] embeddings -> (list of token features [L_i, H], sentence features [n, H])."""
+        packed, qo, q_off, L_max = self.pack_questions(questions)
+        tok, sent = self.encode_packed(packed, qo, q_off, L_max)
+        return [tok[q_off[i]:q_off[i + 1]] for i in range(len(questions))], sent
 
     def encode_question(self, question):
         toks, sent = self.encode_questions([question])

@@ -242,6 +242,7 @@ class NMNTrainStep:
         pl.batch, pl.rows, pl.ga, pl.world = batch, rows, float(ga), world
         pl.class_names = sorted(class_emb)
         pl.class_phrases = [class_emb[n] for n in pl.class_names]
+        pl.class_packed = model.pack_questions(pl.class_phrases) if pl.class_names else None     # uploaded once per window
         pos_of = {n: i for i, n in enumerate(pl.class_names)}
 
         def up(x, dtype):
@@ -265,7 +266,7 @@ class NMNTrainStep:
         # gold text reps of the window's classes (module_net.py:78-89): text encoder without grad + L2Normalize
         cls_rep = None
         if pl.class_names:
-            _, sent = model.encode_questions(pl.class_phrases)
+            _, sent = model.encode_packed(*pl.class_packed)
             cls_rep = torch.empty((len(pl.class_names), H), dtype=torch.float32, device=dev)
             L.check(lib.stair_l2normalize(L.i32(L.dtype_code(sent.dtype)), L.ptr(sent), L.ptr(cls_rep), L.i32(len(pl.class_names)), L.i32(H),
                                           L.stream_ptr()), 'stair_l2normalize')
