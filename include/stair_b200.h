@@ -240,6 +240,14 @@ int stair_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
 /* number of kernels stair_nmn_forward launched in its last call on this thread (bench.py's gpu_launches). */
 int64_t stair_last_launch_count(void);
 
+/* ---- raw-feature ingest, the step right before the path (video_nmn/dataset.py:134-172) ---------
+ * RX / TGIF-QA: out[b,t,0:Da] = mean over the F frames of appearance[b,t,:,:] (dataset.py:150-152), out[b,t,Da:] = motion[b,t,:]
+ * (dataset.py:161-172).  appearance [B,T,F,Da], motion [B,T,Dm] (NULL with Dm = 0), out [B,T,Da+Dm]; Da, Dm multiples of 8. */
+int stair_ingest_pool_concat(const void* appearance, const void* motion, int in_dtype, void* out, int out_dtype, int B, int T, int F,
+                             int Da, int Dm, void* stream);
+/* I3D npy features: out[b,t,:] = feats[b, t*step, :] for t < T (dataset.py:138-141: every 2nd row, then [:max_video_length]) */
+int stair_ingest_subsample(const void* feats, int in_dtype, void* out, int out_dtype, int B, int n_frames, int T, int D, int step, void* stream);
+
 /* ---- single operators (memory-bound kernels), exported for unit parity tests ----------------------------------- */
 /* TemporalModule.relate_ (video_nmn/modules.py:290-308): cumsum before/after/between masks.  mode: 0 while, 1 before,
  * 2 after, 3 between (att then holds two rows per instance).  att [n][K][T] fp32 -> out [n][T]. */

@@ -73,3 +73,13 @@ for n in (2048, 32768):
     lg = torch.randn(n, 172, device=dev); am = torch.empty(n, device=dev, dtype=torch.int32)
     row('argmax (answers)', n, n * 172 * 4 + n * 4,
         lambda: L.check(lib.stair_argmax(L.ptr(lg), L.ptr(am), L.i32(n), L.i32(172), st), 'am'))
+
+# ---- raw-feature ingest (csrc/ingest.cu): appearance [B,8,16,2048] mean-pooled + motion [B,8,2048] -> [B,8,4096] bf16 ------------------
+from stair_b200 import ingest
+for B, dt in ((256, torch.float32), (1024, torch.float32), (1024, torch.bfloat16)):
+    app = torch.rand(B, 8, 16, 2048, device=dev, dtype=torch.float32).to(dt)
+    mot = torch.rand(B, 8, 2048, device=dev, dtype=torch.float32).to(dt)
+    out = torch.empty(B, 8, 4096, device=dev, dtype=torch.bfloat16)
+    nb = app.numel() * app.element_size() + mot.numel() * mot.element_size() + out.numel() * 2
+    row('ingest pool+concat (%s in)' % ('fp32' if dt == torch.float32 else 'bf16'), B, nb, lambda: ingest.pool_concat(app, mot, out=out))
+    del app, mot, out

@@ -295,13 +295,20 @@ class NMNBatch:
         self.device = torch.device(device)
         if self.device.type == 'cuda' and self.device.index is None:
             self.device = torch.device('cuda', torch.cuda.current_device())
-        self.video_dev = self.video.to(self.device, non_blocking=non_blocking)
+        if self.video is None:                                   # raw features: pool + concat on the device (csrc/ingest.cu)
+            from . import ingest
+            app = self.appearance.to(self.device, non_blocking=non_blocking)
+            mot = self.motion.to(self.device, non_blocking=non_blocking) if self.motion is not None else None
+            self.video_dev = ingest.pool_concat(app, mot, out_dtype=self.video_dtype)
+        else:
+            self.video_dev = self.video.to(self.device, non_blocking=non_blocking)
         self.question_dev = self.question.to(self.device, non_blocking=non_blocking)
         self.itab_dev = self.itab_host.to(self.device, non_blocking=non_blocking)
         return self
 
     def h2d_bytes(self):
-        return (self.video.numel() * self.video.element_size() + self.question.numel() * self.question.element_size()
+        feats = [self.video] if self.video is not None else [self.appearance] + ([self.motion] if self.motion is not None else [])
+        return (sum(t.numel() * t.element_size() for t in feats) + self.question.numel() * self.question.element_size()
                 + self.itab_host.numel() * 4)
 
     def tab_ptr(self, name):
@@ -329,18 +336,39 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
     b.examples = examples
     layouts = [compile_layout(e['nmn_program_list']) for e in examples]
     b.layouts = layouts
-    v0 = examples[0]['video_features']
-    T, V = int(v0.shape[0]), int(v0.shape[1])
-    for e in examples:
-        if tuple(e['video_features'].shape) != (T, V):
-            raise ValueError('all questions of a batch must have the same [T, V] video features; bucket by length '
-                             '(got %s and %s)' % ((T, V), tuple(e['video_features'].shape)))
-    b.T, b.V = T, V
-    vdt = video_dtype or v0.dtype
-    video = torch.empty((B, T, V), dtype=vdt, pin_memory=pin_memory)
-    for i, e in enumerate(examples):
-        video[i].copy_(e['video_features'])
-    b.video = video
+    b.appearance = b.motion = None
+    if 'video_features' not in examples[0] and 'appearance_features' in examples[0]:
+        # raw TGIF-QA style features (video_nmn/dataset.py:145-172): appearance [T, F, Da] (+ motion [T, Dm]); the frame mean and the
+        # concat run on the device when the batch is uploaded (stair_b200/ingest.py)
+        a0 = examples[0]['appearance_features']
+        T, F, Da = (int(x) for x in a0.shape)
+        has_m = examples[0].get('motion_features') is not None
+        Dm = int(examples[0]['motion_features'].shape[1]) if has_m else 0
+        app = torch.empty((B, T, F, Da), dtype=a0.dtype, pin_memory=pin_memory)
+        mot = torch.empty((B, T, Dm), dtype=a0.dtype, pin_memory=pin_memory) if has_m else None
+        for i, e in enumerate(examples):
+            if tuple(e['appearance_features'].shape) != (T, F, Da):
+                raise ValueError('all questions of a batch must have the same [T, F, D] appearance features')
+            app[i].copy_(e['appearance_features'])
+            if has_m:
+                mot[i].copy_(e['motion_features'])
+        b.appearance, b.motion, b.video = app, mot, None
+        b.T, b.V = T, Da + Dm
+        b.video_dtype = video_dtype or torch.bfloat16
+    else:
+        v0 = examples[0]['video_features']
+        T, V = int(v0.shape[0]), int(v0.shape[1])
+        for e in examples:
+            if tuple(e['video_features'].shape) != (T, V):
+                raise ValueError('all questions of a batch must have the same [T, V] video features; bucket by length '
+                                 '(got %s and %s)' % ((T, V), tuple(e['video_features'].shape)))
+        b.T, b.V = T, V
+        vdt = video_dtype or v0.dtype
+        video = torch.empty((B, T, V), dtype=vdt, pin_memory=pin_memory)
+        for i, e in enumerate(examples):
+            video[i].copy_(e['video_features'])
+        b.video = video
+        b.video_dtype = vdt
     lens = np.array([int(e['question'].shape[0]) for e in examples], np.int64)
     q_off = np.zeros(B + 1, np.int64)
     np.cumsum(lens, out=q_off[1:])
