@@ -248,6 +248,13 @@ int stair_ingest_pool_concat(const void* appearance, const void* motion, int in_
 /* I3D npy features: out[b,t,:] = feats[b, t*step, :] for t < T (dataset.py:138-141: every 2nd row, then [:max_video_length]) */
 int stair_ingest_subsample(const void* feats, int in_dtype, void* out, int out_dtype, int B, int n_frames, int T, int D, int step, void* stream);
 
+/* ---- Filter-audit head, the step right after the path (evaluate.py:65-117) ----------------------
+ * out_idx[i, 0..k) = indices of the k phrase representations (reps fp32 [P, H]) most cosine-similar to query row i (row
+ * row_idx[i] of q, or row i when row_idx is NULL; pitch ldq elements of `dtype`), out_sim the similarities, descending
+ * (nn.CosineSimilarity eps 1e-8, torch.argsort(descending=True)[:k]; ties -> lowest index). */
+int stair_cosine_topk(int dtype, const void* q, long long ldq, const int32_t* row_idx, const float* reps, int P, int H, int k,
+                      int32_t* out_idx, float* out_sim, int n, void* stream);
+
 /* ---- single operators (memory-bound kernels), exported for unit parity tests ----------------------------------- */
 /* TemporalModule.relate_ (video_nmn/modules.py:290-308): cumsum before/after/between masks.  mode: 0 while, 1 before,
  * 2 after, 3 between (att then holds two rows per instance).  att [n][K][T] fp32 -> out [n][T]. */

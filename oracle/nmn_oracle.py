@@ -491,3 +491,34 @@ def window_loss(model: OracleNMN, crit: OracleCriterion, batch: List[dict], modu
             logs[name].append(float(l.detach()))
             total = total + l * module_loss_weight / ga
     return total, logs, outs
+
+
+# --------------------------------------------------------------------------------------------------
+# Filter audit — evaluate.py:65-117 (get_filter_text_results), one question at a time like the reference
+# --------------------------------------------------------------------------------------------------
+def filter_text_results(model: OracleNMN, batch: List[dict], filter_vocab: List[str], embed_sent, top_k: int = 10):
+    """-> ({qa_id: {prog_idx: (level, keyword, top-k phrases)}}, {qa_id: {prog_idx: sims [len(vocab)]}})."""
+    reps = []
+    for answer in filter_vocab:                                           # evaluate.py:66-75
+        _, rep = model.encode_question(embed_sent(answer))
+        reps.append(model.l2normalize(rep.squeeze()))
+    reps = torch.stack(reps)
+    out, sims_out = {}, {}
+    for data in batch:                                                    # evaluate.py:83-111
+        res = model.forward(data, return_res_by_step=False, return_result_of_each_step=True, test_mode=True)
+        prog = data['nmn_program_list']
+        idx = data.get('nmn_program_idx') or list(range(len(prog)))
+        levels = module_levels(prog)
+        children, _ = children_and_parents(prog)
+        entry, sims_entry = {}, {}
+        for i, (p, p_idx, lvl, ch) in enumerate(zip(prog, idx, levels, children)):
+            if p != 'Filter':
+                continue
+            _, result = res['result_of_each_step'][i]
+            sims = F.cosine_similarity(result.unsqueeze(0), reps)        # nn.CosineSimilarity() defaults: dim=1, eps=1e-8
+            ranks = torch.argsort(sims, descending=True)
+            entry[p_idx] = (lvl, prog[ch[1]].replace('_', ' '), [filter_vocab[int(j)] for j in ranks[:top_k]])
+            sims_entry[p_idx] = sims
+        out[data['qa_id']] = entry
+        sims_out[data['qa_id']] = sims_entry
+    return out, sims_out
