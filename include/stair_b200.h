@@ -191,6 +191,9 @@ int stair_version(void);
 /* sizeof() of the ABI structs as compiled (0 StairModel, 1 StairGroup, 2 StairBatch, 3 StairBuffers, 4 StairItabLayout, 5 StairTrain):
  * lets a binding verify its mirror of the struct layouts. */
 int64_t stair_sizeof(int which);
+/* concurrency of the module phase: independent groups of one schedule wave run on up to `lanes` (1..8, default 4) internal streams
+ * forked from and joined back into the caller's stream (the call stays stream-ordered for the caller) */
+int stair_set_lanes(int lanes);
 /* encoder recurrence implementation: 0 = fused persistent kernel when eligible (default), 1 = per-step GEMM + cell kernels */
 int stair_set_lstm_impl(int impl);
 

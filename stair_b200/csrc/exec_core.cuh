@@ -9,6 +9,7 @@ namespace ex {
 
 extern thread_local long long t_last_launches;   // kernels launched by the last entry-point call on this thread
 extern int g_lstm_impl;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
+constexpr int LANES = 8;                 // independent groups of one wave execute concurrently on up to LANES streams (main + side)
 constexpr long long ROW_CAP = 65536;     // frame rows per chunk of a VID-typed group
 constexpr long long VEC_CAP = 16384;     // instances per chunk of a VEC-typed group / decoder chunk
 
@@ -20,6 +21,7 @@ struct Plan {
     // module / decoder phase (aliases the encoder regions; everything is stream-ordered)
     long long s0, s1, s2, pl, vp, v01, ats, a0;
     long long total;
+    long long mod_bytes; // size of one lane's module scratch (lane l lives at l * mod_bytes)
     int nc_vid;          // instances per VID chunk
     long long R;         // rows per VID chunk
     long long PR;        // rows of the staging plane buffer
@@ -62,7 +64,8 @@ inline void make_plan(const StairModel& m, const StairBatch& b, Plan* p) {
     p->v01 = take(Rvd * 2 * H * esz);
     p->ats = take(p->R * (T > 2 ? T : 2) * 4);
     p->a0 = take(p->R * 4);
-    p->total = o > enc_total ? o : enc_total;
+    p->mod_bytes = o;
+    p->total = LANES * o > enc_total ? LANES * o : enc_total;
 }
 
 struct Ctx {
@@ -329,14 +332,93 @@ inline bool op_is_vid_sized(int op) {
     }
 }
 
-inline int run_modules(Ctx& c) {
-    for (int gi = 0; gi < c.b.n_groups; ++gi) {
-        const StairGroup& g = c.b.groups[gi];
-        const int cap = op_is_vid_sized(g.op) ? c.plan.nc_vid : static_cast<int>(VEC_CAP);
-        for (int done = 0; done < g.count; done += cap) {
-            const int n = g.count - done < cap ? g.count - done : cap;
-            STAIR_TRY(run_chunk(c, g, g.node_off + done, n, g.out_base + done * g.out_mult, g.aux_base >= 0 ? g.aux_base + done : -1));
+inline int run_group(Ctx& c, const StairGroup& g) {
+    const int cap = op_is_vid_sized(g.op) ? c.plan.nc_vid : static_cast<int>(VEC_CAP);
+    for (int done = 0; done < g.count; done += cap) {
+        const int n = g.count - done < cap ? g.count - done : cap;
+        STAIR_TRY(run_chunk(c, g, g.node_off + done, n, g.out_base + done * g.out_mult, g.aux_base >= 0 ? g.aux_base + done : -1));
+    }
+    return STAIR_OK;
+}
+
+// rough cost of a group for the lane assignment (launch-latency floor per kernel + work)
+inline long long group_cost(const StairGroup& g, int T) {
+    int launches;
+    switch (g.op) {
+    case STAIR_OP_LOCALIZE: launches = 5; break;
+    case STAIR_OP_SUPERLATIVE: launches = 7; break;
+    case STAIR_OP_FILTER: case STAIR_OP_FILTERFRAME: launches = 4; break;
+    case STAIR_OP_TEMPORAL: case STAIR_OP_EXISTS: case STAIR_OP_TOACTION: launches = 3; break;
+    case STAIR_OP_HASITEM: case STAIR_OP_COMPARE: case STAIR_OP_EQUALS: case STAIR_OP_XOR: launches = 2; break;
+    default: launches = 1;
+    }
+    return launches * 1000LL + static_cast<long long>(g.count) * (op_is_vid_sized(g.op) ? T : 1) / 16;
+}
+
+struct LaneStreams { cudaStream_t side[LANES - 1]; cudaEvent_t fork, join[LANES - 1]; bool ok = false; };
+inline LaneStreams* lane_streams() {
+    static thread_local LaneStreams ls;
+    if (!ls.ok) {
+        for (int l = 0; l < LANES - 1; ++l) {
+            if (cudaStreamCreateWithFlags(&ls.side[l], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&ls.join[l], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
+        if (cudaEventCreateWithFlags(&ls.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ls.ok = true;
+    }
+    return &ls;
+}
+
+extern int g_lanes;      // 1 = everything on the caller's stream; up to LANES
+
+// Groups are listed in schedule order (wave-major).  The groups of one wave are independent (they read earlier waves and write
+// disjoint arena ranges), so they are spread over up to LANES streams forked from / joined back into the caller's stream; every
+// lane has its own scratch.  At B = 4096 the module kernels are launch/latency-bound (10-20 us each on a mostly idle GPU):
+// running a wave's groups side by side hides that latency.
+inline int run_modules(Ctx& c) {
+    const int ng = c.b.n_groups;
+    LaneStreams* ls = g_lanes > 1 ? lane_streams() : nullptr;
+    int gi = 0;
+    while (gi < ng) {
+        int gj = gi + 1;
+        while (gj < ng && c.b.groups[gj].level == c.b.groups[gi].level) ++gj;
+        const int nw = gj - gi;
+        if (nw == 1 || !ls) {
+            for (int g = gi; g < gj; ++g) STAIR_TRY(run_group(c, c.b.groups[g]));
+            gi = gj;
+            continue;
+        }
+        const int lanes = nw < g_lanes ? nw : g_lanes;
+        // longest-processing-time-first assignment of the wave's groups to lanes
+        int order[64], lane_of[64];
+        long long load[LANES] = {0};
+        const int nwc = nw < 64 ? nw : 64;
+        for (int k = 0; k < nwc; ++k) order[k] = gi + k;
+        for (int a = 1; a < nwc; ++a)
+            for (int b2 = a; b2 > 0 && group_cost(c.b.groups[order[b2]], c.T) > group_cost(c.b.groups[order[b2 - 1]], c.T); --b2) {
+                const int t = order[b2]; order[b2] = order[b2 - 1]; order[b2 - 1] = t;
+            }
+        for (int k = 0; k < nwc; ++k) {
+            int best = 0;
+            for (int l = 1; l < lanes; ++l) if (load[l] < load[best]) best = l;
+            lane_of[k] = best;
+            load[best] += group_cost(c.b.groups[order[k]], c.T);
+        }
+        if (cudaEventRecord(ls->fork, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
+        for (int l = 1; l < lanes; ++l)
+            if (cudaStreamWaitEvent(ls->side[l - 1], ls->fork, 0) != cudaSuccess) return STAIR_ERR_CUDA;
+        for (int k = 0; k < nwc; ++k) {
+            Ctx lc = c;
+            const int l = lane_of[k];
+            if (l > 0) { lc.st = ls->side[l - 1]; lc.ws = c.ws + static_cast<long long>(l) * c.plan.mod_bytes; }
+            STAIR_TRY(run_group(lc, c.b.groups[order[k]]));
+        }
+        for (int g = gi + nwc; g < gj; ++g) STAIR_TRY(run_group(c, c.b.groups[g]));      // (more than 64 groups in a wave: the rest on the main lane)
+        for (int l = 1; l < lanes; ++l) {
+            if (cudaEventRecord(ls->join[l - 1], ls->side[l - 1]) != cudaSuccess) return STAIR_ERR_CUDA;
+            if (cudaStreamWaitEvent(c.st, ls->join[l - 1], 0) != cudaSuccess) return STAIR_ERR_CUDA;
+        }
+        gi = gj;
     }
     return STAIR_OK;
 }

@@ -13,6 +13,7 @@ namespace stair {
 namespace ex {
 int g_lstm_impl = 0;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
 thread_local long long t_last_launches = 0;
+int g_lanes = 4;
 }
 
 }  // namespace stair
@@ -21,6 +22,7 @@ using namespace stair;
 using namespace stair::ex;
 
 extern "C" int stair_set_lstm_impl(int impl) { g_lstm_impl = impl; return STAIR_OK; }
+extern "C" int stair_set_lanes(int lanes) { g_lanes = lanes < 1 ? 1 : (lanes > LANES ? LANES : lanes); return STAIR_OK; }
 extern "C" int stair_version(void) { return STAIR_ABI_VERSION; }
 extern "C" int64_t stair_sizeof(int which) {
     switch (which) {
