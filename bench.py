@@ -82,9 +82,12 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+TEMPLATES = None          # None = the ten AGQA templates
+
+
 def build_inputs(rank, B):
     from stair_b200 import synthetic as syn, collate
-    qs = syn.make_questions(B, T, V, seed=1234 + rank, with_gold=True)      # gold is only read by the training leg
+    qs = syn.make_questions(B, T, V, seed=1234 + rank, with_gold=True, templates=TEMPLATES)      # gold is only read by the training leg
     batch = collate(qs, pin_memory=True, video_dtype=torch.bfloat16, question_dtype=torch.float32)
     return qs, batch
 
@@ -127,7 +130,7 @@ def run_reference(args, rank, world):
     from stair_b200 import synthetic as syn
     cfg = syn.model_config(T=T, V=V)
     weights = make_weights(cfg)
-    qs = syn.make_questions(CPU_SAMPLE, T, V, seed=1234)
+    qs = syn.make_questions(CPU_SAMPLE, T, V, seed=1234, templates=TEMPLATES)
     from oracle import nmn_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     model = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES, aten_lstm=True)
@@ -163,9 +166,15 @@ def main():
     ap.add_argument('--batch', type=int, default=PER_GPU_B, help='questions per GPU (default: the BASELINE config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step leg (BASELINE configs[3])')
+    ap.add_argument('--workload', default='rx', choices=['rx', 'i3d'],
+                    help="rx (default, BASELINE configs[1]): T=8, V=4096, the 10 AGQA templates; i3d (configs[4] stress test): T=64, V=1024, "
+                         "conv-mode Temporal, only the >= 9-module layouts (compare, xor_between)")
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
+    global T, V, TEMPLATES
+    if args.workload == 'i3d':
+        T, V, TEMPLATES = 64, 1024, ['compare', 'xor_between']
     if args.impl == 'reference':
         run_reference(args, rank, world)
         return
@@ -323,10 +332,14 @@ def main():
     pk = peaks()
     flops = 2.0 * M * N * K
     achieved_tf = flops / (gemm_ms * 1e-3) / 1e12
-    roofline = {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel<256,4> (video input projection [B*T,4096]x[4096,2048])',
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the default shape, from the committed `ncu --set full` capture
+    # (profiles/r1_gemm_xproj_ncu_summary_v2.txt); algorithmic bytes: A 268 MB + W 17 MB + C 134 MB = 419 MB
+    traffic = 398.9e6 if (args.workload == 'rx' and B == PER_GPU_B) else None
+    roofline = {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel<256,4> (video input projection [%d,%d]x[%d,%d])' % (M, K, K, N),
                 'achieved': achieved_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': achieved_tf / pk['tf_sustained'],
                 'frac_of_burst_peak': achieved_tf / pk['tf_burst'], 'peak_source': pk['src'] + ' (sustained; kernel timed inside the step loop)',
-                'traffic': None, 'ms': gemm_ms, 'flops_per_launch': flops}
+                'traffic': traffic, 'traffic_source': 'profiles/r1_gemm_xproj_ncu_summary_v2.txt' if traffic else None, 'ms': gemm_ms,
+                'flops_per_launch': flops, 'algorithmic_bytes_per_launch': 2.0 * (M * K + N * K + M * N)}
 
     line = None
     if rank == 0:
@@ -355,9 +368,11 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
                 'data': 'synthetic',
-                'config': {'workload': 'ModuleNet batched inference, %d mixed-program questions per GPU (10 AGQA layout templates, 2-12 modules), '
-                                       'RX/TGIF-QA features [8,4096] bf16, questions 8-24 words x 300, random init, bf16 storage / fp32 accumulate'
-                                       % B, 'questions_per_gpu': B, 'global_questions': world * B, 'frames': T, 'video_size': V,
+                'config': {'workload': ('ModuleNet batched inference, %d mixed-program questions per GPU (10 AGQA layout templates, 2-12 modules), '
+                                        'RX/TGIF-QA features [8,4096] bf16, questions 8-24 words x 300, random init, bf16 storage / fp32 accumulate'
+                                        % B) if args.workload == 'rx' else
+                                       ('I3D stress test (BASELINE configs[4]): %d questions per GPU, compare / xor_between layouts (9-12 modules), '
+                                        'features [64,1024] bf16, conv-mode Temporal, random init, bf16 storage / fp32 accumulate' % B), 'questions_per_gpu': B, 'global_questions': world * B, 'frames': T, 'video_size': V,
                            'hidden_size': cfg['hidden_size'], 'parallelism': 'question-sharded x%d, answers all-gathered (NCCL)' % world,
                            'l2': 'inputs larger than L2 (video %.0f MB per step)' % (B * T * V * 2 / 1e6)},
                 'clocks': clock_info,
