@@ -63,8 +63,21 @@ extern "C" int stair_nmn_forward(const StairModel* model, const StairBatch* batc
     c.arg0 = buf->itab + c.il.arg_slot; c.arg1 = c.arg0 + b.n_nodes; c.arg2 = c.arg1 + b.n_nodes;
     c.pos_q = buf->itab + c.il.pos_q; c.span_s = buf->itab + c.il.pos_span; c.span_e = c.span_s + b.n_nodes;
     const long long before = g_launch_count;
-    if (phases & STAIR_FWD_GROUP) STAIR_TRY(launch_group_layouts(b, buf->itab, buf->status, c.st));
-    if (phases & (STAIR_FWD_ENCODE_VIDEO | STAIR_FWD_ENCODE_TEXT)) STAIR_TRY(run_encoders(c, phases));
+    // the layout grouping (4 small integer kernels, ~60 us of latency) does not depend on the encoders: it runs on a side lane
+    // while the input projections execute, and is joined before the first module group
+    const bool enc = (phases & (STAIR_FWD_ENCODE_VIDEO | STAIR_FWD_ENCODE_TEXT)) != 0;
+    LaneStreams* ls = ((phases & STAIR_FWD_GROUP) && enc && g_lanes > 1) ? lane_streams() : nullptr;
+    if (phases & STAIR_FWD_GROUP) {
+        if (ls) {
+            if (cudaEventRecord(ls->fork, c.st) != cudaSuccess || cudaStreamWaitEvent(ls->side[0], ls->fork, 0) != cudaSuccess) return STAIR_ERR_CUDA;
+            STAIR_TRY(launch_group_layouts(b, buf->itab, buf->status, ls->side[0]));
+            if (cudaEventRecord(ls->join[0], ls->side[0]) != cudaSuccess) return STAIR_ERR_CUDA;
+        } else {
+            STAIR_TRY(launch_group_layouts(b, buf->itab, buf->status, c.st));
+        }
+    }
+    if (enc) STAIR_TRY(run_encoders(c, phases));
+    if (ls && cudaStreamWaitEvent(c.st, ls->join[0], 0) != cudaSuccess) return STAIR_ERR_CUDA;
     if (phases & STAIR_FWD_MODULES) STAIR_TRY(run_modules(c));
     if (phases & STAIR_FWD_DECODE) STAIR_TRY(run_decoder(c));
     t_last_launches = g_launch_count - before;
