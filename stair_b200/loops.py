@@ -12,6 +12,7 @@ The arithmetic is the CUDA library's; these loops only move batches and bookkeep
 """
 from __future__ import annotations
 
+import collections
 import json
 import os
 
@@ -27,15 +28,10 @@ def evaluate(batches, model, unk_token_id=None, id2word=None, preds_file=None, p
     a question counts as correct iff pred == gold and gold != <UNK> (evaluate.py:46)."""
     correct, total = 0, 0
     out = {'preds': [], 'golds': [], 'qa_ids': []}
-    for data in batches:
-        batch = data if isinstance(data, LY.NMNBatch) else LY.collate(list(data), pin_memory=True)
-        if pipelined_chunks > 1 and not isinstance(data, LY.NMNBatch):
-            chunks = LY.collate_chunks(list(data), pipelined_chunks, pin_memory=True)
-            pred, _, _ = model.forward_pipelined(chunks)
-        else:
-            pred = model(batch, return_res_by_step=False, test_mode=True)['answers']
-        pred = pred.cpu().long()                                   # one D2H per batch (the reference syncs three times per question)
-        gold = batch.answer.long()
+
+    def account(pred, gold, examples):
+        nonlocal correct, total
+        pred, gold = pred.long(), gold.long()
         ok = pred == gold
         if unk_token_id is not None:
             ok &= gold != unk_token_id
@@ -44,7 +40,26 @@ def evaluate(batches, model, unk_token_id=None, id2word=None, preds_file=None, p
         conv = (lambda i: id2word[i]) if id2word is not None else (lambda i: i)
         out['preds'] += [conv(int(p)) for p in pred]
         out['golds'] += [conv(int(g)) for g in gold]
-        out['qa_ids'] += [e.get('qa_id') for e in batch.examples]
+        out['qa_ids'] += [e.get('qa_id') for e in examples]
+
+    if pipelined_chunks > 1:
+        # streaming: uploads of batch k+1 overlap the execution of batch k, answers return through pinned memory
+        pending = collections.deque()
+
+        def host_batches():
+            for data in batches:
+                chunks = [data] if isinstance(data, LY.NMNBatch) else LY.collate_chunks(list(data), pipelined_chunks, pin_memory=True)
+                pending.append(chunks)
+                yield chunks
+
+        for pred in model.forward_stream(host_batches(), depth=2):
+            chunks = pending.popleft()
+            account(pred, torch.cat([c.answer for c in chunks]), [e for c in chunks for e in c.examples])
+    else:
+        for data in batches:
+            batch = data if isinstance(data, LY.NMNBatch) else LY.collate(list(data), pin_memory=True)
+            pred = model(batch, return_res_by_step=False, test_mode=True)['answers']
+            account(pred.cpu(), batch.answer, batch.examples)   # one D2H per batch (the reference syncs three times per question)
     if preds_file is not None:
         json.dump(out, open(preds_file, 'w'))
     return (correct / total if total else 0.0), out

@@ -165,6 +165,57 @@ class VideoNMN(nn.Module):
         logits = torch.cat([st.logits for st in states]) if len(states) > 1 else states[0].logits
         return answers, logits, states
 
+    def forward_stream(self, host_batches, depth=2, head_modules=frozenset(), device_hook=None):
+        """Streaming inference over an iterable of HOST batches (each an ``NMNBatch`` or a list of chunk ``NMNBatch``es in
+        pinned memory, e.g. ``layout.collate_chunks(..., pin_memory=True)``).  Generator: yields the answers of every batch
+        (CPU int32 tensor, in order).  Up to ``depth`` batches are in flight: the host->device copies run on a copy stream and
+        never wait for the compute stream, the answers come back through an asynchronous device->host copy into pinned
+        memory, so in steady state a batch costs max(PCIe time, compute time) with no per-batch synchronisation bubble
+        (the per-call ``forward_pipelined`` + ``.cpu()`` pays the last chunk's compute and the first chunk's upload serially).
+        ``device_hook(answers) -> tensor`` runs on the compute stream before the read-back (e.g. the NCCL all-gather)."""
+        import collections
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda':
+            raise L.StairError('VideoNMN parameters are on %s: stair_b200 runs only on CUDA (sm_100a) devices' % dev)
+        comp = torch.cuda.current_stream(dev)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cs = self._copy_stream
+        inflight = collections.deque()
+
+        def finish():
+            host, done, _ = inflight.popleft()
+            done.synchronize()
+            return host
+
+        for hb in host_batches:
+            chunks = [hb] if isinstance(hb, LY.NMNBatch) else list(hb)
+            events = []
+            for b in chunks:
+                with torch.cuda.stream(cs):
+                    b.to(dev)
+                    for t in (b.video_dev, b.question_dev, b.itab_dev):
+                        t.record_stream(comp)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                events.append(ev)
+            states = []
+            for b, ev in zip(chunks, events):
+                comp.wait_event(ev)
+                states.append(self.forward_batch(b, head_modules))
+            answers = torch.cat([st.answers for st in states]) if len(states) > 1 else states[0].answers
+            if device_hook is not None:
+                answers = device_hook(answers)
+            host = torch.empty(answers.shape, dtype=answers.dtype, pin_memory=True)
+            host.copy_(answers, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(comp)
+            inflight.append((host, done, (states, answers)))
+            if len(inflight) >= max(1, depth):
+                yield finish()
+        while inflight:
+            yield finish()
+
     def check_status(self, st: ForwardState):
         """Synchronising check of the device-side status word (layout grouping mismatch)."""
         code = int(st.status[0].item())

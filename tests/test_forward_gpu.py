@@ -209,3 +209,26 @@ def test_pipelined_forward_equals_plain_forward():
         model.check_status(st)
     assert torch.equal(answers, full['answers'])
     assert torch.equal(logits, full['logits'])
+
+
+def test_streaming_forward_equals_plain_forward():
+    """forward_stream (uploads of batch k+1 overlap batch k, answers through pinned memory) yields, in order, exactly the
+    answers of the plain forward of every batch — including when the same host chunks are re-streamed (recycled buffers)."""
+    from stair_b200 import collate_chunks
+    T, V = 8, 256
+    cfg = syn.model_config(T=T, V=V, hidden=128)
+    torch.manual_seed(2)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().eval()
+    sets = [syn.make_questions(n, T, V, seed=s, templates=list(syn.ALL_TEMPLATES)) for n, s in ((90, 5), (131, 6), (64, 7))]
+    want = [model(qs, return_res_by_step=False, test_mode=True)['answers'].cpu() for qs in sets]
+    host = [collate_chunks(qs, 3, pin_memory=True, video_dtype=torch.bfloat16, question_dtype=torch.bfloat16) for qs in sets]
+    for depth in (1, 2, 3):
+        got = list(model.forward_stream(iter(host + host), depth=depth))
+        assert len(got) == 6
+        for g, w in zip(got, want + want):
+            assert g.device.type == 'cpu' and torch.equal(g, w)
+    # a plain NMNBatch (no chunking) and a device hook
+    from stair_b200 import collate
+    one = collate(sets[0], pin_memory=True, video_dtype=torch.bfloat16, question_dtype=torch.bfloat16)
+    got = list(model.forward_stream([one], device_hook=lambda a: a + 1))
+    assert torch.equal(got[0], want[0] + 1)
