@@ -34,6 +34,7 @@ METRIC, UNIT = 'nmn_questions_per_sec', 'questions/s'
 PER_GPU_B = 4096
 T, V = 8, 4096
 CPU_SAMPLE = 32
+TRAIN_DROPOUT = 0.25
 E2E_CHUNKS = 2
 
 
@@ -315,7 +316,8 @@ def main():
     train = None
     if not args.no_train:
         from stair_b200.train import NMNTrainStep, Adam
-        tmodel = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16')
+        # throughput run: the reference's default training dropout (video_nmn/args.py:31); parity runs (tests) use 0 or injected masks
+        tmodel = VideoNMN(dict(cfg, dropout=TRAIN_DROPOUT), pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16')
         tmodel.load_state_dict(weights)
         tmodel = tmodel.to(dev).train()
         tstep = NMNTrainStep(tmodel)
@@ -345,7 +347,7 @@ def main():
         tms = float(tms.item())
         train = {'value': world * B * ksteps / (tms * 1e-3), 'unit': UNIT, 'ms_per_step': tms / ksteps, 'steps': ksteps,
                  'launches_per_step': tstep.last_launches, 'window_questions': world * B, 'loss': float(out['loss']),
-                 'loss_rows': out['loss_counts'],
+                 'loss_rows': out['loss_counts'], 'dropout': TRAIN_DROPOUT,
                  'what': 'forward with encoder history + losses (train_module.py:83-194) + backward + %sAdam; bf16 storage, fp32 gradients'
                          % ('NCCL gradient all-reduce + ' if world > 1 else '')}
         del tmodel, tstep, opt, plan

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define STAIR_ABI_VERSION 4
+#define STAIR_ABI_VERSION 5
 
 /* status codes */
 #define STAIR_OK 0
@@ -185,8 +185,16 @@ typedef struct StairTrain {
     float* dvid; float* dvec; float* datt; float* dtokfeat; float* dqfeat; float* dlogits;   /* gradient arenas (same shapes as the forward arenas) */
     void* saved; int64_t saved_bytes;           /* LSTM gate / cell / state history written by stair_nmn_forward_train */
     void* workspace; int64_t workspace_bytes;   /* backward scratch, >= stair_train_workspace_bytes */
+    /* nn.Dropout(p) of the reference's training mode (video_nmn/args.py:31 default 0.25; sites: modules.py Linear->ReLU->Dropout
+     * of Exists/Filter/FilterFrame/HasItem/Localize/Temporal/ToAction, HasItem's Sigmoid->Dropout, decoder module_net.py:49-53).
+     * Counter-based masks keyed by (dropout_seed, site, global row, column); stair_nmn_backward must receive the same p and seed
+     * as the stair_nmn_forward_train it follows.  0 = no dropout (eval semantics). */
+    float dropout_p; uint64_t dropout_seed;
 } StairTrain;
 
+/* Host evaluation (no GPU work) of the dropout mask of site `site` (a STAIR_W_* id of the Linear the Dropout follows) for the
+ * elements (row0 + r, c), r < rows, c < cols: keep[r*cols + c] = 1 if kept.  Restated in oracle/nmn_oracle.py dropout_keep. */
+int stair_dropout_mask_host(float p, unsigned long long seed, int site, long long row0, int rows, int cols, unsigned char* keep);
 int stair_version(void);
 /* sizeof() of the ABI structs as compiled (0 StairModel, 1 StairGroup, 2 StairBatch, 3 StairBuffers, 4 StairItabLayout, 5 StairTrain):
  * lets a binding verify its mirror of the struct layouts. */

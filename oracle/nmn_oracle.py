@@ -148,11 +148,15 @@ class OracleNMN:
     (module_net.py:31-32) and is read from the ``Localize`` keys.
     """
 
-    def __init__(self, config: dict, weights: Dict[str, torch.Tensor], pretrain_modules=frozenset(), aten_lstm=False):
+    def __init__(self, config: dict, weights: Dict[str, torch.Tensor], pretrain_modules=frozenset(), aten_lstm=False, dropout=None):
         """``aten_lstm=True`` runs the two encoders through ``torch.nn.LSTM`` itself — the very ATen call the reference
         makes (module_net.py:39-47,151-163; mkldnn/cuDNN kernels) — instead of the explicit per-step restatement.  Used by
         the CPU-baseline timer so the baseline is not handicapped by a Python time loop; tested equal to the loop."""
         self.aten_lstm = aten_lstm
+        # training-mode nn.Dropout sites: ``dropout(site, x, (question_index, token_index)) -> tensor`` is called wherever the
+        # reference has an nn.Dropout (site = the Sequential entry it follows, e.g. 'Localize.video_linear.0'); None = eval
+        self.dropout = dropout
+        self._q, self._tok = 0, None
         self._lstm_cache = {}
         self.config = config
         self.W = weights
@@ -194,11 +198,17 @@ class OracleNMN:
         return x / x.norm().clamp_min(1e-12)
 
     # ---- operators (video_nmn/modules.py) ---------------------------------------------------------
-    def _mlp2(self, prefix, x, last_relu=True):
-        """Linear-ReLU-(Dropout)-Linear[-ReLU] with Sequential indices 0 and 3 (eval / dropout 0)."""
-        x = torch.relu(_linear(x, self.p(prefix + '.0.weight'), self.p(prefix + '.0.bias')))
+    def _drop(self, site, x):
+        return x if self.dropout is None else self.dropout(site, x, (self._q, self._tok))
+
+    def _mlp2(self, prefix, x, last_relu=True, drop_last=False):
+        """Linear-ReLU-Dropout-Linear[-ReLU[-Dropout]] with Sequential indices 0 and 3."""
+        x = self._drop(prefix + '.0', torch.relu(_linear(x, self.p(prefix + '.0.weight'), self.p(prefix + '.0.bias'))))
         x = _linear(x, self.p(prefix + '.3.weight'), self.p(prefix + '.3.bias'))
-        return torch.relu(x) if last_relu else x
+        if not last_relu:
+            return x
+        x = torch.relu(x)
+        return self._drop(prefix + '.3', x) if drop_last else x
 
     def And(self, a, b):                                 # modules.py:7-12
         return torch.min(a, b)
@@ -216,37 +226,37 @@ class OracleNMN:
         return torch.relu(_linear(torch.cat([f1, f2]), self.p('Equals.param.0.weight'), self.p('Equals.param.0.bias')))
 
     def Exists(self, keyword, feat):                     # modules.py:141-159
-        return self._mlp2('Exists.param', torch.cat([feat, keyword, feat * keyword]))
+        return self._mlp2('Exists.param', torch.cat([feat, keyword, feat * keyword]), drop_last=True)
 
     def ExistsFrame(self, keyword, feat):                # modules.py:162-178
         return (_cos(feat, keyword.unsqueeze(0)) + 1) * 0.49
 
     def Filter(self, feat, keyword):                     # modules.py:343-378
         if isinstance(keyword, torch.Tensor):
-            x = self._mlp2('Filter.param.representation', feat)
+            x = self._mlp2('Filter.param.representation', feat, drop_last=True)
             fk = torch.cat([x, keyword.unsqueeze(0).expand(x.size(0), -1)], dim=1)
             # nn.Softmax() on [T,1] -> implicit dim=1 -> attention == 1.0 exactly (SURVEY §8a Filter)
             a = _legacy_softmax(_linear(fk, self.p('Filter.attention.0.weight'), self.p('Filter.attention.0.bias')))
             agg = torch.sum(a * x, dim=0)
         else:
-            agg = torch.sum(self._mlp2('Filter.param.' + keyword, feat), dim=0)
+            agg = torch.sum(self._mlp2('Filter.param.' + keyword, feat, drop_last=True), dim=0)
         return torch.relu(_linear(agg, self.p('Filter.dense.0.weight'), self.p('Filter.dense.0.bias')))
 
     def FilterFrame(self, feat, keyword):                # modules.py:381-414 (no 'objects' key: KeyError as in ref)
         if isinstance(keyword, torch.Tensor):
-            x = self._mlp2('FilterFrame.param.representation', feat)
+            x = self._mlp2('FilterFrame.param.representation', feat, drop_last=True)
             fk = torch.cat([x, keyword.unsqueeze(0).expand(x.size(0), -1)], dim=1)
             a = torch.sigmoid(_linear(fk, self.p('FilterFrame.attention.0.weight'), self.p('FilterFrame.attention.0.bias')))
             agg = a * x
         else:
             if keyword not in ('relations', 'actions'):
                 raise KeyError(keyword)
-            agg = self._mlp2('FilterFrame.param.' + keyword, feat)
-        return torch.relu(_linear(agg, self.p('FilterFrame.dense.0.weight'), self.p('FilterFrame.dense.0.bias')))
+            agg = self._mlp2('FilterFrame.param.' + keyword, feat, drop_last=True)
+        return self._drop('FilterFrame.dense.0', torch.relu(_linear(agg, self.p('FilterFrame.dense.0.weight'), self.p('FilterFrame.dense.0.bias'))))
 
     def HasItem(self, feat):                             # modules.py:123-138
-        x = torch.relu(_linear(feat, self.p('HasItem.param.0.weight'), self.p('HasItem.param.0.bias')))
-        return torch.sigmoid(_linear(x, self.p('HasItem.param.3.weight'), self.p('HasItem.param.3.bias'))).squeeze()
+        x = self._drop('HasItem.param.0', torch.relu(_linear(feat, self.p('HasItem.param.0.weight'), self.p('HasItem.param.0.bias'))))
+        return self._drop('HasItem.param.3', torch.sigmoid(_linear(x, self.p('HasItem.param.3.weight'), self.p('HasItem.param.3.bias')))).squeeze()
 
     def Localize(self, feat, keyword):                   # modules.py:181-217
         f = self._mlp2('Localize.video_linear', feat, last_relu=False)             # [T,H]
@@ -284,7 +294,7 @@ class OracleNMN:
         a = attention.mean(dim=0)
         r = self.temporal_relate(mode, a)
         self._temporal_related = r
-        x = torch.relu(_linear(r.unsqueeze(-1) * feat, self.p('Temporal.dense.0.weight'), self.p('Temporal.dense.0.bias')))
+        x = self._drop('Temporal.dense.0', torch.relu(_linear(r.unsqueeze(-1) * feat, self.p('Temporal.dense.0.weight'), self.p('Temporal.dense.0.bias'))))
         return F.layer_norm(x, (x.size(-1),), self.p('Temporal.layer_norm.weight'), self.p('Temporal.layer_norm.bias'), 1e-5)
 
     @staticmethod
@@ -353,6 +363,7 @@ class OracleNMN:
                 for _ in range(NARY[tok]):
                     p = stack.pop()
                     params.append(video_feat if isinstance(p, str) and p == 'video' else p)
+                self._tok = i
                 out = getattr(self, tok)(*params)
                 if return_res_by_step and prog_idx[i] is not None and tok in self.pretrain_modules and i != 0:
                     res_by_step[prog_idx[i]] = (tok, self.pretrain_head(tok, out) if head else out)
@@ -370,7 +381,8 @@ class OracleNMN:
             stack.append(out)
         assert len(stack) == 1
         hid = torch.cat([stack[0], question_feature])
-        x = torch.relu(_linear(hid, self.p('decoder.0.weight'), self.p('decoder.0.bias')))
+        self._tok = None
+        x = self._drop('decoder.0', torch.relu(_linear(hid, self.p('decoder.0.weight'), self.p('decoder.0.bias'))))
         logits = _linear(x, self.p('decoder.3.weight'), self.p('decoder.3.bias'))
         ret = {'logits': logits, 'res_by_step': res_by_step}
         if return_result_of_each_step:
@@ -446,6 +458,33 @@ class OracleCriterion:
         raise KeyError(name)
 
 
+# --------------------------------------------------------------------------------------------------
+# dropout masks — restatement of the counter-based hash of csrc/stair_common.cuh (lowbias32 / make_drop / drop_keep).
+# torch's Philox stream is not reproducible in a batched executor, so parity under dropout is checked with the SAME masks
+# injected into this oracle (tests/test_train_gpu.py::test_dropout_*).
+# --------------------------------------------------------------------------------------------------
+def _lowbias32(x):
+    import numpy as np
+    x = np.asarray(x, dtype=np.uint64) & 0xffffffff
+    x ^= x >> 16; x = (x * 0x7feb352d) & 0xffffffff
+    x ^= x >> 15; x = (x * 0x846ca68b) & 0xffffffff
+    x ^= x >> 16
+    return x
+
+
+def dropout_keep(seed: int, site: int, row0: int, rows: int, cols: int, p: float):
+    """bool [rows, cols]: element (row0 + r, c) of dropout site ``site`` is kept."""
+    import numpy as np
+    thresh = min(int(float(np.float32(p)) * 4294967296.0), 0xffffffff)
+    key_lo = int(_lowbias32((seed & 0xffffffff) ^ ((site * 0x9E3779B1) & 0xffffffff)))
+    key_hi = int(_lowbias32((((seed >> 32) & 0xffffffff) + site * 0x85EBCA77 + 1) & 0xffffffff))
+    r = (np.arange(row0, row0 + rows, dtype=np.uint64) & 0xffffffff) ^ key_lo
+    rh = (_lowbias32(r) + key_hi) & 0xffffffff
+    c = (np.arange(cols, dtype=np.uint64) * 0x9E3779B1) & 0xffffffff
+    h = _lowbias32((rh[:, None] + c[None, :]) & 0xffffffff)
+    return h >= thresh
+
+
 def data_answer(a):
     return a if isinstance(a, torch.Tensor) else torch.tensor(int(a))
 
@@ -462,6 +501,7 @@ def window_loss(model: OracleNMN, crit: OracleCriterion, batch: List[dict], modu
     class_reps, neg_reps = {}, {}
     outs = []
     for it, data in enumerate(batch):
+        model._q = it
         out = model.forward(data, return_res_by_step=module_loss_weight != 0)
         outs.append(out)
         gold_by_step = out['sg_res_by_step']

@@ -84,7 +84,8 @@ class StairTrain(ctypes.Structure):
                 ('n_con', i32), ('con_node', vp), ('con_pos', vp), ('con_w', vp), ('n_cls', i32), ('cls_rep', vp),
                 ('answer', vp), ('dec_w', ctypes.c_float), ('loss', vp),
                 ('dvid', vp), ('dvec', vp), ('datt', vp), ('dtokfeat', vp), ('dqfeat', vp), ('dlogits', vp),
-                ('saved', vp), ('saved_bytes', i64), ('workspace', vp), ('workspace_bytes', i64)]
+                ('saved', vp), ('saved_bytes', i64), ('workspace', vp), ('workspace_bytes', i64),
+                ('dropout_p', ctypes.c_float), ('dropout_seed', ctypes.c_uint64)]
 
 
 _lib = None

@@ -34,7 +34,8 @@ def build(force=False, verbose=False):
         obj = os.path.join(HERE, 'build', os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
-                os.path.getmtime(src), *(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h')))):
+                os.path.getmtime(src), os.path.getmtime(os.path.join(os.path.dirname(HERE), 'include', 'stair_b200.h')),
+                *(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h')))):
             continue
         cmd = [nvcc] + NVCC_FLAGS + ['-I', os.path.join(os.path.dirname(HERE), 'include'), '-I', CSRC, '-c', src, '-o', obj]
         if verbose:

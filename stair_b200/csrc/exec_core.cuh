@@ -78,12 +78,22 @@ struct Ctx {
     int T, H, h, np, adt, esz;
     StairItabLayout il;
     const int *perm, *out_slot, *arg0, *arg1, *arg2, *pos_q, *span_s, *span_e;
+    // dropout (training entry points only; 0 = off): the next GEMM consumes `pending` (set by drop_next)
+    float drop_p = 0.0f;
+    unsigned long long drop_seed = 0;
+    DropSpec pending;
 
     template <typename P> P* at(long long off) const { return reinterpret_cast<P*>(ws + off); }
     const void* W(int id) const { return m.w[id]; }
     const float* Wf(int id) const { return reinterpret_cast<const float*>(m.w[id]); }
     char* act_ptr(void* base, long long elem_off) const { return reinterpret_cast<char*>(base) + elem_off * esz; }
 };
+
+// dropout site = id of the Linear whose (activated) output is dropped; row0 = global row id of the GEMM's first row
+inline void drop_next(Ctx& c, int site, long long row0) {
+    if (c.drop_p > 0.0f) c.pending = make_drop(c.drop_p, c.drop_seed, site, row0);
+}
+inline DropSpec take_drop(Ctx& c) { const DropSpec d = c.pending; c.pending = DropSpec(); return d; }
 
 // C = act(row_scale * (A_planes . W^T) + bias)
 inline int gemm_planes(Ctx& c, const bf16* A, long long lda, long long a_plane_rows, int M, int N, int K, int wid, int bid, int act,
@@ -93,6 +103,7 @@ inline int gemm_planes(Ctx& c, const bf16* A, long long lda, long long a_plane_r
     a.W = c.W(wid); a.ldw = align_up(K, 8); a.w_plane_rows = N;
     a.bias = bid >= 0 ? c.Wf(bid) : nullptr; a.row_scale = row_scale;
     a.C = C; a.ldc = ldc; a.out_dtype = cdt; a.M = M; a.N = N; a.K = K; a.act = act;
+    a.drop = take_drop(c);
     return launch_gemm(a, c.st);
 }
 
@@ -113,6 +124,7 @@ inline int gemm_vid(Ctx& c, const int* slots, int n, int N, int wid, int bid, in
         a.A = c.buf.vid; a.lda = K; a.arena_slots = c.buf.vid_slots; a.a_slots = slots; a.slot_rows = c.T;
         a.W = c.W(wid); a.ldw = K; a.w_plane_rows = N; a.bias = bid >= 0 ? c.Wf(bid) : nullptr; a.row_scale = row_scale;
         a.C = C; a.ldc = ldc; a.out_dtype = cdt; a.M = M; a.N = N; a.K = K; a.act = act;
+        a.drop = take_drop(c);
         return launch_gemm(a, c.st);
     }
     if (M > c.plan.PR) return STAIR_ERR_CAPACITY;
@@ -211,11 +223,13 @@ inline int run_chunk(Ctx& c, const StairGroup& g, int p, int n, int ob, int ab) 
     float* att = c.buf.att;
     void* vid_out = c.act_ptr(c.buf.vid, static_cast<long long>(ob) * T * H);
     void* vec_out = c.act_ptr(c.buf.vec, static_cast<long long>(ob) * H);
+    const long long pT = static_cast<long long>(p) * T;        // global row id of the chunk's first frame row (dropout masks)
     switch (g.op) {
     case STAIR_OP_WORD:
         return launch_word_embed(dt, c.buf.tokfeat, c.b.q_off, c.pos_q + p, c.span_s + p, c.span_e + p, c.buf.vec, ob, n, H, c.st);
     case STAIR_OP_LOCALIZE: {                                   // modules.py:194-217; variant = K-1
         const int K = g.variant + 1;
+        drop_next(c, STAIR_W_LOC_V0_W, pT);
         STAIR_TRY(gemm_vid(c, a0, n, H, STAIR_W_LOC_V0_W, STAIR_W_LOC_V0_B, STAIR_ACT_RELU, nullptr, S0, dt, H));
         STAIR_TRY(gemm_act(c, S0, n * T, H, H, STAIR_W_LOC_V1_W, STAIR_W_LOC_V1_B, STAIR_ACT_NONE, nullptr, S1, dt, H));
         STAIR_TRY(gemm_vec_rows(c, a1, K, n, H, STAIR_W_LOC_K_W, STAIR_W_LOC_K_B, STAIR_ACT_NONE, S2, dt, H));
@@ -227,12 +241,15 @@ inline int run_chunk(Ctx& c, const StairGroup& g, int p, int n, int ob, int ab) 
         if (mode > 0) for (int j = 0; j < 6; ++j) params[j] = c.Wf(STAIR_W_TEMP_REL_BEFORE + 6 * (mode - 1) + j);
         STAIR_TRY(launch_temporal_relate(att, a1, K, mode, c.m.conv_k, params, att, ab, n, T, c.st));
         // dense(r[t] * feat[t]) = relu(r[t] * (W feat[t]) + b): the gate is the GEMM's row scale
+        drop_next(c, STAIR_W_TEMP_D_W, pT);
         STAIR_TRY(gemm_vid(c, a0, n, H, STAIR_W_TEMP_D_W, STAIR_W_TEMP_D_B, STAIR_ACT_RELU, att + static_cast<long long>(ab) * T, S0, dt, H));
         return launch_layernorm(dt, S0, c.Wf(STAIR_W_TEMP_LN_G), c.Wf(STAIR_W_TEMP_LN_B), vid_out, static_cast<long long>(n) * T, H, c.st);
     }
     case STAIR_OP_FILTER: {                                     // modules.py:361-378; variant 0 repr,1 actions,2 objects,3 relations
         const int w = STAIR_W_FILT_REPR + 4 * g.variant;
+        drop_next(c, w, pT);
         STAIR_TRY(gemm_vid(c, a0, n, H, w, w + 1, STAIR_ACT_RELU, nullptr, S0, dt, H));
+        drop_next(c, w + 2, pT);
         STAIR_TRY(gemm_act(c, S0, n * T, H, H, w + 2, w + 3, STAIR_ACT_RELU, nullptr, S1, dt, H));
         // tensor keyword: nn.Softmax() over a size-1 dim makes the attention exactly 1.0 -> plain sum over frames
         STAIR_TRY(launch_sum_T(dt, S1, S2, n, T, H, c.st));
@@ -242,7 +259,9 @@ inline int run_chunk(Ctx& c, const StairGroup& g, int p, int n, int ob, int ab) 
     }
     case STAIR_OP_FILTERFRAME: {                                // modules.py:398-414; variant 0 repr,1 relations,2 actions
         const int w = STAIR_W_FF_REPR + 4 * g.variant;
+        drop_next(c, w, pT);
         STAIR_TRY(gemm_vid(c, a0, n, H, w, w + 1, STAIR_ACT_RELU, nullptr, S0, dt, H));
+        drop_next(c, w + 2, pT);
         STAIR_TRY(gemm_act(c, S0, n * T, H, H, w + 2, w + 3, STAIR_ACT_RELU, nullptr, S1, dt, H));
         const float* gate = nullptr;
         if (g.variant == 0) {
@@ -250,6 +269,7 @@ inline int run_chunk(Ctx& c, const StairGroup& g, int p, int n, int ob, int ab) 
             STAIR_TRY(launch_ff_attn(dt, S1, c.buf.vec, a1, c.Wf(STAIR_W_FF_ATT_W), c.Wf(STAIR_W_FF_ATT_B), A0, n, T, H, c.st));
             gate = A0;      // dense(a[t] * x[t]) = relu(a[t] * (W x[t]) + b)
         }
+        drop_next(c, STAIR_W_FF_D_W, pT);
         STAIR_TRY(gemm_act(c, S1, n * T, H, H, STAIR_W_FF_D_W, STAIR_W_FF_D_B, STAIR_ACT_RELU, gate, vid_out, dt, H));
         if (g.head)
             return gemm_act(c, vid_out, n * T, c.m.O, H, STAIR_W_FF_HEAD_W, STAIR_W_FF_HEAD_B, STAIR_ACT_NONE, nullptr,
@@ -257,8 +277,12 @@ inline int run_chunk(Ctx& c, const StairGroup& g, int p, int n, int ob, int ab) 
         return STAIR_OK;
     }
     case STAIR_OP_HASITEM:                                      // modules.py:131-138
+        drop_next(c, STAIR_W_HAS0_W, pT);
         STAIR_TRY(gemm_vid(c, a0, n, H, STAIR_W_HAS0_W, STAIR_W_HAS0_B, STAIR_ACT_RELU, nullptr, S0, dt, H));
-        return launch_rowdot_sigmoid(dt, S0, c.Wf(STAIR_W_HAS1_W), c.Wf(STAIR_W_HAS1_B), att, ob, n, T, H, c.st);
+        STAIR_TRY(launch_rowdot_sigmoid(dt, S0, c.Wf(STAIR_W_HAS1_W), c.Wf(STAIR_W_HAS1_B), att, ob, n, T, H, c.st));
+        if (c.drop_p > 0.0f)                                     // Sigmoid -> Dropout (modules.py:129): the output map itself is dropped
+            return launch_drop_rows(att + static_cast<long long>(ob) * T, static_cast<long long>(n) * T, make_drop(c.drop_p, c.drop_seed, STAIR_W_HAS1_W, pT), c.st);
+        return STAIR_OK;
     case STAIR_OP_EXISTSFRAME:                                  // (keyword, feat) modules.py:169-178
         return launch_existsframe(dt, c.buf.vid, a1, c.buf.vec, a0, att, ob, n, T, H, c.st);
     case STAIR_OP_RELATE:                                       // variant 0 forward, 1 backward; modules.py:423-435
@@ -292,12 +316,15 @@ inline int run_chunk(Ctx& c, const StairGroup& g, int p, int n, int ob, int ab) 
         return STAIR_OK;
     case STAIR_OP_EXISTS:                                       // (keyword, feat) modules.py:141-159
         STAIR_TRY(launch_concat_vec(dt, c.buf.vec, a0, a1, STAIR_CAT_EXISTS, VP, n, c.np, n, H, c.st));
+        drop_next(c, STAIR_W_EXISTS0_W, p);
         STAIR_TRY(gemm_planes(c, VP, 3 * H, n, n, H, 3 * H, STAIR_W_EXISTS0_W, STAIR_W_EXISTS0_B, STAIR_ACT_RELU, nullptr, V0, dt, H));
+        drop_next(c, STAIR_W_EXISTS1_W, p);
         STAIR_TRY(gemm_act(c, V0, n, H, H, STAIR_W_EXISTS1_W, STAIR_W_EXISTS1_B, STAIR_ACT_RELU, nullptr, vec_out, dt, H));
         if (g.head) return launch_small_head(dt, c.buf.vec, ob, c.Wf(STAIR_W_EXISTS_HEAD_W), c.Wf(STAIR_W_EXISTS_HEAD_B), 2, c.buf.head_small, ab, n, H, c.st);
         return STAIR_OK;
     case STAIR_OP_TOACTION:                                     // (action, keyword) modules.py:102-120
         STAIR_TRY(launch_concat_vec(dt, c.buf.vec, a0, a1, STAIR_CAT_PAIR, VP, n, c.np, n, H, c.st));
+        drop_next(c, STAIR_W_TOACT0_W, p);
         STAIR_TRY(gemm_planes(c, VP, 2 * H, n, n, H, 2 * H, STAIR_W_TOACT0_W, STAIR_W_TOACT0_B, STAIR_ACT_RELU, nullptr, V0, dt, H));
         STAIR_TRY(gemm_act(c, V0, n, H, H, STAIR_W_TOACT1_W, STAIR_W_TOACT1_B, STAIR_ACT_RELU, nullptr, vec_out, dt, H));
         if (g.head) return launch_l2norm(dt, c.buf.vec, ob, c.buf.head_vec, ab, n, H, c.st);
@@ -306,6 +333,7 @@ inline int run_chunk(Ctx& c, const StairGroup& g, int p, int n, int ob, int ab) 
         // variant = is_min + 2*kind ; kind 0: one VEC action, 1: Array2 (two rows), 2: [T,H] frame features as T actions
         const int is_min = g.variant & 1, kind = g.variant >> 1;
         const int K = kind == 0 ? 1 : (kind == 1 ? 2 : T);
+        drop_next(c, STAIR_W_LOC_V0_W, pT);
         STAIR_TRY(gemm_vid(c, a1, n, H, STAIR_W_LOC_V0_W, STAIR_W_LOC_V0_B, STAIR_ACT_RELU, nullptr, S0, dt, H));
         STAIR_TRY(gemm_act(c, S0, n * T, H, H, STAIR_W_LOC_V1_W, STAIR_W_LOC_V1_B, STAIR_ACT_NONE, nullptr, S1, dt, H));
         if (kind == 2) STAIR_TRY(gemm_vid(c, a0, n, H, STAIR_W_LOC_K_W, STAIR_W_LOC_K_B, STAIR_ACT_NONE, nullptr, S2, dt, H));
@@ -432,6 +460,7 @@ inline int run_decoder(Ctx& c) {
         const int n = B - done < VEC_CAP ? B - done : static_cast<int>(VEC_CAP);
         STAIR_TRY(launch_decoder_concat(c.adt, c.buf.vec, c.b.root_node + done, c.out_slot,
                                         c.act_ptr(c.buf.qfeat, static_cast<long long>(done) * H), VP, n, c.np, n, H, c.st));
+        drop_next(c, STAIR_W_DEC0_W, done);
         STAIR_TRY(gemm_planes(c, VP, 2 * H, n, n, 2 * H, 2 * H, STAIR_W_DEC0_W, STAIR_W_DEC0_B, STAIR_ACT_RELU, nullptr, D0, c.adt, 2 * H));
         if (c.np == 1) {
             STAIR_TRY(gemm_planes(c, reinterpret_cast<const bf16*>(D0), 2 * H, 0, n, A, 2 * H, STAIR_W_DEC1_W, STAIR_W_DEC1_B, STAIR_ACT_NONE, nullptr,

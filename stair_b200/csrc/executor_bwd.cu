@@ -39,6 +39,7 @@ struct BCtx {
 #define RUN(expr) do { if (!b.dry) { if (b.ws.overflow) return STAIR_ERR_CAPACITY; int rc__ = (expr); if (rc__ != STAIR_OK) return rc__; } } while (0)
 
 inline float* G(BCtx& b, int id) { return id >= 0 ? b.tr.grad[id] : nullptr; }
+inline float DS(BCtx& b) { return b.c.drop_p > 0.0f ? 1.0f / (1.0f - b.c.drop_p) : 1.0f; }     // scale of kept elements at a dropout site
 
 // ---- saved encoder history ------------------------------------------------------------------------------------------------
 struct EncSaved { long long gates, c, hs; int S; };          // byte offsets into StairTrain.saved
@@ -77,15 +78,16 @@ bf16* stage_gather(BCtx& b, const void* base, int sdt, const int* idx, int rps, 
 
 // Linear backward.  dY fp32 [M,N]; Y = post-activation output (ReLU mask) or null; rs = row scale or null;
 // Xp = layer input as bf16 planes [np][x_plane_rows, K_ld].  dX (fp32 [M,K]) receives dZ.W WITHOUT the row scale.
+// yscale = 1/(1-p) when Y went through Dropout after its ReLU (dropped elements are exactly 0 in Y, so Y > 0 is the joint mask).
 int linear_bwd(BCtx& b, const float* dY, long long ld_dy, const void* Y, long long ld_y, const float* rs, const bf16* Xp,
-               long long x_plane_rows, int M, int N, int K, int wid, int bid, float* dX) {
+               long long x_plane_rows, int M, int N, int K, int wid, int bid, float* dX, float yscale = 1.0f) {
     Ctx& c = b.c;
     if (M <= 0) return STAIR_OK;
     const long long mark = b.ws.off;
     const long long n_ld = align_up(N, 8), k_ld = align_up(K, 8), m_ld = align_up(M, 8);
     bf16* dZ = b.ws.take<bf16>(c.np * static_cast<long long>(M) * n_ld);
     bf16* dZs = rs ? b.ws.take<bf16>(c.np * static_cast<long long>(M) * n_ld) : dZ;
-    RUN(launch_dz_prep(c.adt, dY, ld_dy, Y, ld_y, rs, dZ, dZs, n_ld, M, c.np, G(b, bid), M, N, c.st));
+    RUN(launch_dz_prep(c.adt, dY, ld_dy, Y, ld_y, rs, dZ, dZs, n_ld, M, c.np, G(b, bid), M, N, Y ? yscale : 1.0f, c.st));
     float* gW = G(b, wid);
     if (gW) {
         bf16* dZt = b.ws.take<bf16>(c.np * static_cast<long long>(N) * m_ld);
@@ -118,10 +120,10 @@ int mlp2_bwd(BCtx& b, float* dx, const void* S0, const void* S1, const int* feat
     const long long mark = b.ws.off;
     float* dS0 = b.ws.take<float>(static_cast<long long>(M) * H);
     STAGE_ACT(s0p, S0, c.adt, M, H);
-    STAIR_TRY(linear_bwd(b, dx, H, S1, H, nullptr, s0p, M, M, H, H, w + 2, w + 3, dS0));
+    STAIR_TRY(linear_bwd(b, dx, H, S1, H, nullptr, s0p, M, M, H, H, w + 2, w + 3, dS0, DS(b)));
     float* dF = b.ws.take<float>(static_cast<long long>(M) * H);
     STAGE_GATHER(fp, c.buf.vid, c.adt, feat_slots, T, T, n, H);
-    STAIR_TRY(linear_bwd(b, dS0, H, S0, H, nullptr, fp, M, M, H, H, w, w + 1, dF));
+    STAIR_TRY(linear_bwd(b, dS0, H, S0, H, nullptr, fp, M, M, H, H, w, w + 1, dF, DS(b)));
     RUN(launch_scatter_add_rows(dF, feat_slots, T, T, b.tr.dvid, M, H, c.st));
     b.ws.off = mark;
     return STAIR_OK;
@@ -141,7 +143,7 @@ int localize_bwd(BCtx& b, const float* datt, long long att_base, const void* S0,
     STAIR_TRY(linear_bwd(b, df, H, nullptr, 0, nullptr, s0p, M, M, H, H, STAIR_W_LOC_V1_W, STAIR_W_LOC_V1_B, dS0));
     float* dF = b.ws.take<float>(static_cast<long long>(M) * H);
     STAGE_GATHER(fp, c.buf.vid, c.adt, feat_slots, T, T, n, H);
-    STAIR_TRY(linear_bwd(b, dS0, H, S0, H, nullptr, fp, M, M, H, H, STAIR_W_LOC_V0_W, STAIR_W_LOC_V0_B, dF));
+    STAIR_TRY(linear_bwd(b, dS0, H, S0, H, nullptr, fp, M, M, H, H, STAIR_W_LOC_V0_W, STAIR_W_LOC_V0_B, dF, DS(b)));
     RUN(launch_scatter_add_rows(dF, feat_slots, T, T, b.tr.dvid, M, H, c.st));
     float* dKW = b.ws.take<float>(static_cast<long long>(n) * K * H);
     STAGE_GATHER(kp, kw_base, c.adt, kw_idx, kw_rps, kw_unit, n, H);
@@ -183,7 +185,7 @@ int chunk_bwd(BCtx& b, const StairGroup& g, int p, int n, int ob, int ab) {
         RUN(launch_layernorm_bwd(dt, dvid_out, S0, c.Wf(STAIR_W_TEMP_LN_G), dS0, G(b, STAIR_W_TEMP_LN_G), G(b, STAIR_W_TEMP_LN_B), M, H, c.st));
         float* Gx = b.ws.take<float>(static_cast<long long>(M) * H);
         STAGE_GATHER(fp, c.buf.vid, dt, a0, T, T, n, H);
-        STAIR_TRY(linear_bwd(b, dS0, H, S0, H, r, fp, M, M, H, H, STAIR_W_TEMP_D_W, STAIR_W_TEMP_D_B, Gx));
+        STAIR_TRY(linear_bwd(b, dS0, H, S0, H, r, fp, M, M, H, H, STAIR_W_TEMP_D_W, STAIR_W_TEMP_D_B, Gx, DS(b)));
         RUN(launch_rowscale_bwd(dt, Gx, c.buf.vid, a0, T, T, r, dr, M, H, c.st));
         RUN(launch_scatter_add_rows(Gx, a0, T, T, tr.dvid, M, H, c.st));
         const float* params[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -207,7 +209,7 @@ int chunk_bwd(BCtx& b, const StairGroup& g, int p, int n, int ob, int ab) {
         const float* gate = g.variant == 0 ? c.at<float>(c.plan.a0) : nullptr;
         float* Gx = b.ws.take<float>(static_cast<long long>(M) * H);
         STAGE_ACT(xp, S1, dt, M, H);
-        STAIR_TRY(linear_bwd(b, dvid_out, H, vid_out, H, gate, xp, M, M, H, H, STAIR_W_FF_D_W, STAIR_W_FF_D_B, Gx));
+        STAIR_TRY(linear_bwd(b, dvid_out, H, vid_out, H, gate, xp, M, M, H, H, STAIR_W_FF_D_W, STAIR_W_FF_D_B, Gx, DS(b)));
         if (gate) {
             float* da = b.ws.take<float>(M);
             if (!b.dry && cudaMemsetAsync(da, 0, sizeof(float) * M, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
@@ -219,10 +221,10 @@ int chunk_bwd(BCtx& b, const StairGroup& g, int p, int n, int ob, int ab) {
     }
     case STAIR_OP_HASITEM: {
         float* dS0 = b.ws.take<float>(static_cast<long long>(M) * H);
-        RUN(launch_rowdot_sigmoid_bwd(dt, S0, c.Wf(STAIR_W_HAS1_W), att + static_cast<long long>(ob) * T, datt_out, dS0, G(b, STAIR_W_HAS1_W), G(b, STAIR_W_HAS1_B), M, H, c.st));
+        RUN(launch_rowdot_sigmoid_bwd(dt, S0, c.Wf(STAIR_W_HAS1_W), att + static_cast<long long>(ob) * T, datt_out, dS0, G(b, STAIR_W_HAS1_W), G(b, STAIR_W_HAS1_B), M, H, DS(b), c.st));
         float* dF = b.ws.take<float>(static_cast<long long>(M) * H);
         STAGE_GATHER(fp, c.buf.vid, dt, a0, T, T, n, H);
-        STAIR_TRY(linear_bwd(b, dS0, H, S0, H, nullptr, fp, M, M, H, H, STAIR_W_HAS0_W, STAIR_W_HAS0_B, dF));
+        STAIR_TRY(linear_bwd(b, dS0, H, S0, H, nullptr, fp, M, M, H, H, STAIR_W_HAS0_W, STAIR_W_HAS0_B, dF, DS(b)));
         RUN(launch_scatter_add_rows(dF, a0, T, T, tr.dvid, M, H, c.st));
         break;
     }
@@ -267,9 +269,9 @@ int chunk_bwd(BCtx& b, const StairGroup& g, int p, int n, int ob, int ab) {
         const int w0 = ex ? STAIR_W_EXISTS0_W : STAIR_W_TOACT0_W, w1 = ex ? STAIR_W_EXISTS1_W : STAIR_W_TOACT1_W;
         float* dV0 = b.ws.take<float>(static_cast<long long>(n) * H);
         STAGE_ACT(v0p, V0, dt, n, H);
-        STAIR_TRY(linear_bwd(b, dvec_out, H, vec_out, H, nullptr, v0p, n, n, H, H, w1, w1 + 1, dV0));
+        STAIR_TRY(linear_bwd(b, dvec_out, H, vec_out, H, nullptr, v0p, n, n, H, H, w1, w1 + 1, dV0, ex ? DS(b) : 1.0f));   // Exists drops after both ReLUs
         float* dcat = b.ws.take<float>(static_cast<long long>(n) * Kc);
-        STAIR_TRY(linear_bwd(b, dV0, H, V0, H, nullptr, VP, n, n, H, Kc, w0, w0 + 1, dcat));
+        STAIR_TRY(linear_bwd(b, dV0, H, V0, H, nullptr, VP, n, n, H, Kc, w0, w0 + 1, dcat, DS(b)));
         RUN(launch_concat_bwd(dt, c.buf.vec, a0, a1, mode, dcat, tr.dvec, n, H, c.st));
         break;
     }
@@ -451,12 +453,13 @@ int decoder_bwd(BCtx& b) {
         const long long mark = b.ws.off;
         // recompute this chunk's decoder hidden layer (module_net.py:136-138)
         RUN(launch_decoder_concat(c.adt, c.buf.vec, c.b.root_node + done, c.out_slot, c.act_ptr(c.buf.qfeat, static_cast<long long>(done) * H), VP, n, c.np, n, H, c.st));
+        if (!b.dry) drop_next(c, STAIR_W_DEC0_W, done);
         RUN(gemm_planes(c, VP, 2 * H, n, n, 2 * H, 2 * H, STAIR_W_DEC0_W, STAIR_W_DEC0_B, STAIR_ACT_RELU, nullptr, D0, c.adt, 2 * H));
         float* dD0 = b.ws.take<float>(static_cast<long long>(n) * 2 * H);
         STAGE_ACT(d0p, D0, c.adt, n, 2 * H);
         STAIR_TRY(linear_bwd(b, tr.dlogits + static_cast<long long>(done) * A, A, nullptr, 0, nullptr, d0p, n, n, A, 2 * H, STAIR_W_DEC1_W, STAIR_W_DEC1_B, dD0));
         float* dcat = b.ws.take<float>(static_cast<long long>(n) * 2 * H);
-        STAIR_TRY(linear_bwd(b, dD0, 2 * H, D0, 2 * H, nullptr, VP, n, n, 2 * H, 2 * H, STAIR_W_DEC0_W, STAIR_W_DEC0_B, dcat));
+        STAIR_TRY(linear_bwd(b, dD0, 2 * H, D0, 2 * H, nullptr, VP, n, n, 2 * H, 2 * H, STAIR_W_DEC0_W, STAIR_W_DEC0_B, dcat, DS(b)));
         RUN(launch_decoder_concat_bwd(dcat, c.b.root_node + done, c.out_slot, tr.dvec, tr.dqfeat + static_cast<long long>(done) * H, n, H, c.st));
         b.ws.off = mark;
     }
@@ -533,6 +536,8 @@ extern "C" int stair_nmn_forward_train(const StairModel* model, const StairBatch
     Ctx c{*model, *batch, *buf, reinterpret_cast<cudaStream_t>(stream)};
     STAIR_TRY(make_ctx(c, *model, *batch, *buf));
     if (buf->workspace_bytes < c.plan.total || buf->itab_ints < c.il.total) return STAIR_ERR_CAPACITY;
+    c.drop_p = train->dropout_p; c.drop_seed = train->dropout_seed;
+    if (!(c.drop_p >= 0.0f && c.drop_p < 1.0f)) return STAIR_ERR_ARG;
     const long long before = g_launch_count;
     STAIR_TRY(launch_group_layouts(*batch, buf->itab, buf->status, c.st));
     STAIR_TRY(run_encoders_train(c, *train));
@@ -548,6 +553,8 @@ extern "C" int stair_nmn_backward(const StairModel* model, const StairBatch* bat
     Ctx c{*model, *batch, *buf, reinterpret_cast<cudaStream_t>(stream)};
     STAIR_TRY(make_ctx(c, *model, *batch, *buf));
     if (buf->workspace_bytes < c.plan.total) return STAIR_ERR_CAPACITY;
+    c.drop_p = train->dropout_p; c.drop_seed = train->dropout_seed;     // the recomputed forward of every chunk regenerates the masks
+    if (!(c.drop_p >= 0.0f && c.drop_p < 1.0f)) return STAIR_ERR_ARG;
     BCtx b{c, *train, Bump(), false};
     b.ws.base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(train->workspace) + 255) & ~static_cast<uintptr_t>(255));
     b.ws.cap = train->workspace_bytes - 256;
@@ -562,4 +569,16 @@ extern "C" int stair_adam_step(float* param, const float* grad, float* exp_avg, 
                                float eps, int step, void* stream) {
     const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
     return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Host-side evaluation of the dropout mask (no GPU work): lets a binding / test restate and verify the counter-based mask that the
+// training kernels apply on the device (stair_common.cuh make_drop / drop_keep).
+extern "C" int stair_dropout_mask_host(float p, unsigned long long seed, int site, long long row0, int rows, int cols, unsigned char* keep) {
+    if (!keep || rows < 0 || cols < 0 || !(p >= 0.0f && p < 1.0f)) return STAIR_ERR_ARG;
+    const DropSpec d = make_drop(p, seed, site, row0);
+    for (int r = 0; r < rows; ++r) {
+        const uint32_t rh = drop_row_hash(d.key_lo, d.key_hi, d.row0 + r);
+        for (int c = 0; c < cols; ++c) keep[static_cast<long long>(r) * cols + c] = (!d.thresh || drop_keep(rh, static_cast<uint32_t>(c), d.thresh)) ? 1 : 0;
+    }
+    return STAIR_OK;
 }

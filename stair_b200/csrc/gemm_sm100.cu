@@ -42,6 +42,7 @@ struct GemmParams {
     int num_slots;         // ceil(M / slot_rows)
     int* err_flag;
     unsigned long long* dbg;   // debug timeline of block 0 (globaltimer ns), null in production
+    DropSpec drop;             // dropout after the activation (thresh 0 = off)
 };
 
 // plane pairs (a,b) of the 6-term bf16x3 product, smallest contributions first
@@ -57,7 +58,13 @@ __device__ __forceinline__ void dbg_stamp(const GemmParams& p, int slot) {
 }
 
 // act(rs * acc + bias) for one 32-column TMEM chunk of this thread's row
-__device__ __forceinline__ void epilogue_math(const GemmParams& p, int n, float rs, const uint32_t (&raw)[32], float (&v)[32]) {
+__device__ __forceinline__ void epilogue_drop(const GemmParams& p, int row, int n, float (&v)[32]) {
+    const uint32_t rh = drop_row_hash(p.drop.key_lo, p.drop.key_hi, p.drop.row0 + row);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = drop_keep(rh, static_cast<uint32_t>(n + j), p.drop.thresh) ? v[j] * p.drop.scale : 0.0f;
+}
+
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, int row, int n, float rs, const uint32_t (&raw)[32], float (&v)[32]) {
     if (p.bias && n + 32 <= p.N) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);     // n is a multiple of 32: 16-byte aligned
 #pragma unroll
@@ -80,6 +87,7 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n, float 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
     }
+    if (p.drop.thresh) epilogue_drop(p, row, n, v);
 }
 
 // write this thread's 32 values into the warp's staging buffer (row = lane, 128-byte rows, SWIZZLE_128B chunk order)
@@ -123,6 +131,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int
         if (p.act == STAIR_ACT_RELU) x = fmaxf(x, 0.0f);
         v[j] = x;
     }
+    if (p.drop.thresh) epilogue_drop(p, row, n, v);
     const bool full = p.vec_ok && (n + 32 <= p.N);
     if (p.out_dtype == STAIR_BF16) {
         bf16* out = reinterpret_cast<bf16*>(p.C) + static_cast<long long>(row) * p.ldc + n;
@@ -311,7 +320,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                         const uint32_t buf = stage0 + static_cast<uint32_t>(sbuf) * 4096u;
                         if (n < p.N) {
-                            epilogue_math(p, n, rs, hsel == 0 ? ra : rb, v);
+                            epilogue_math(p, row, n, rs, hsel == 0 ? ra : rb, v);
                             stage_chunk(buf, lane, half, p.out_dtype, v);
                         }
                         if (half == per_buf - 1) {
@@ -376,6 +385,8 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, long long lda, cons
         float x = acc * (p.row_scale ? p.row_scale[row] : 1.f);
         if (p.bias) x += p.bias[col];
         if (p.act == STAIR_ACT_RELU) x = fmaxf(x, 0.f);
+        if (p.drop.thresh)
+            x = drop_keep(drop_row_hash(p.drop.key_lo, p.drop.key_hi, p.drop.row0 + row), static_cast<uint32_t>(col), p.drop.thresh) ? x * p.drop.scale : 0.f;
         if (p.out_dtype == STAIR_BF16) reinterpret_cast<bf16*>(p.C)[static_cast<long long>(row) * p.ldc + col] = __float2bfloat16_rn(x);
         else {
             float* o = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + col;
@@ -472,6 +483,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     p.a_plane_rows = a.a_plane_rows; p.w_plane_rows = a.w_plane_rows;
     p.bias = a.bias; p.row_scale = a.row_scale; p.C = a.C; p.ldc = a.ldc; p.out_dtype = a.out_dtype; p.act = a.act;
     p.accumulate = a.accumulate;
+    p.drop = a.drop;
     const int esz = a.out_dtype == STAIR_BF16 ? 2 : 4;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.ldc * esz) % 16 == 0) ? 1 : 0;
     p.tma_store = (!a.accumulate && p.vec_ok && g_epilogue_impl == 0) ? 1 : 0;

@@ -643,6 +643,20 @@ int launch_rowdot_sigmoid(int dt, const void* x, const float* w, const float* b,
     return STAIR_OK;
 }
 
+__global__ void drop_rows_kernel(float* __restrict__ x, long long rows, DropSpec d) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < rows; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        x[i] = drop_keep(drop_row_hash(d.key_lo, d.key_hi, d.row0 + i), 0u, d.thresh) ? x[i] * d.scale : 0.0f;
+}
+
+int launch_drop_rows(float* x, long long rows, DropSpec d, cudaStream_t st) {
+    if (rows <= 0 || !d.thresh) return STAIR_OK;
+    long long blocks = (rows + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    drop_rows_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(x, rows, d);
+    STAIR_CHECK_LAUNCH();
+    return STAIR_OK;
+}
+
 // Choose: cos(k1,q) > cos(k2,q) ? k1 : k2 (strict '>', tie -> k2); device-side select, no host sync  modules.py:40-56
 template <typename AT>
 __global__ void choose_kernel(AT* __restrict__ vec, const int* __restrict__ k1, const int* __restrict__ k2, const int* __restrict__ q,

@@ -45,6 +45,8 @@ int launch_attnvideo(int dt, void* vid, const int* feat_idx, const float* att, c
 int launch_relate(const float* att, const int* att_idx, const float* beta, int sign, float* att_out, int out_base, int n, int T, cudaStream_t st);
 // att[(out_base+i)*T+t] = sigmoid(w.x[i*T+t] + b)                          (HasItem tail, modules.py:128-129)
 int launch_rowdot_sigmoid(int dt, const void* x, const float* w, const float* b, float* att, int out_base, int n, int T, int H, cudaStream_t st);
+// in-place dropout of an fp32 map: x[i] = keep(row0 + i, col 0) ? x[i] * scale : 0     (HasItem: Sigmoid -> Dropout, modules.py:129)
+int launch_drop_rows(float* x, long long rows, DropSpec d, cudaStream_t st);
 int launch_choose(int dt, void* vec, const int* k1, const int* k2, const int* q, int out_base, int n, int H, cudaStream_t st);
 #define STAIR_BIN_MIN 0
 #define STAIR_BIN_ABSDIFF 1

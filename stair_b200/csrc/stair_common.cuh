@@ -88,6 +88,41 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// ---- dropout (training only) -----------------------------------------------------------------------------
+// nn.Dropout(p) of the reference (video_nmn/modules.py: every Linear->ReLU->Dropout site, HasItem's Sigmoid->Dropout, decoder)
+// as a counter-based mask: element (row, col) of dropout site `site` is kept iff hash(seed, site, row, col) >= p * 2^32 and kept
+// values are scaled by 1/(1-p).  `row` is a global row id (sorted node position * rows-per-instance + r), so the mask does not
+// depend on chunking and the backward pass (which re-runs the forward of a chunk) regenerates exactly the same mask.  torch's
+// Philox stream cannot be reproduced batched (the reference draws per question, in interpreter order); parity is checked
+// against the oracle with the same masks injected (oracle/nmn_oracle.py dropout_keep).
+__host__ __device__ static inline uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+struct DropSpec {
+    uint32_t thresh = 0;      // p * 2^32 (0 = no dropout)
+    uint32_t key_lo = 0, key_hi = 0;
+    float scale = 1.0f;       // 1 / (1 - p)
+    long long row0 = 0;       // global row id of local row 0
+};
+__host__ __device__ static inline uint32_t drop_row_hash(uint32_t key_lo, uint32_t key_hi, long long row) {
+    return lowbias32(static_cast<uint32_t>(row) ^ key_lo) + key_hi;
+}
+__host__ __device__ static inline bool drop_keep(uint32_t row_hash, uint32_t col, uint32_t thresh) {
+    return lowbias32(row_hash + col * 0x9E3779B1u) >= thresh;
+}
+static inline DropSpec make_drop(float p, unsigned long long seed, int site, long long row0) {
+    DropSpec d;
+    if (!(p > 0.0f)) return d;
+    const double t = static_cast<double>(p) * 4294967296.0;
+    d.thresh = t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
+    d.key_lo = lowbias32(static_cast<uint32_t>(seed) ^ (static_cast<uint32_t>(site) * 0x9E3779B1u));
+    d.key_hi = lowbias32(static_cast<uint32_t>(seed >> 32) + static_cast<uint32_t>(site) * 0x85EBCA77u + 1u);
+    d.scale = 1.0f / (1.0f - p);
+    d.row0 = row0;
+    return d;
+}
+
 // ---- internal GEMM launch API (gemm_sm100.cu) ----------------------------------------------------
 struct GemmArgs {
     const void* A = nullptr;        // bf16 [nplanes][a_plane_rows, lda]  (or the slot arena in gather mode)
@@ -108,6 +143,7 @@ struct GemmArgs {
     int M = 0, N = 0, K = 0;
     int act = STAIR_ACT_NONE;
     int accumulate = 0;
+    DropSpec drop;                  // applied after the activation (training forward only)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
 int* err_flag_ptr();      // pinned host word that device-side protocol timeouts write their code to (stair_gemm_error_flag)

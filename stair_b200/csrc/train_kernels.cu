@@ -44,7 +44,7 @@ __device__ __forceinline__ void store_planes1(float v, bf16* dst, long long plan
 template <typename YT>
 __global__ void dz_prep_kernel(const float* __restrict__ dY, long long ld_dy, const YT* __restrict__ Y, long long ld_y,
                                const float* __restrict__ rs, bf16* __restrict__ dZ, bf16* __restrict__ dZs, long long n_ld,
-                               long long plane_rows, int nplanes, float* __restrict__ db, int M, int N, int rows_per_block, int vec_ok) {
+                               long long plane_rows, int nplanes, float* __restrict__ db, int M, int N, int rows_per_block, int vec_ok, float yscale) {
     __shared__ float red[256 * 8];
     const int n8 = static_cast<int>(n_ld / 8);
     const int cols_b = n8 < 256 ? n8 : 256;                      // threads along the columns
@@ -65,7 +65,7 @@ __global__ void dz_prep_kernel(const float* __restrict__ dY, long long ld_dy, co
                     if (Y) {
                         Vec8<YT> y; y.load(Y + static_cast<long long>(m) * ld_y + col);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) if (!(y.v[j] > 0.f)) dz[j] = 0.f;
+                        for (int j = 0; j < 8; ++j) dz[j] = y.v[j] > 0.f ? dz[j] * yscale : 0.f;
                     }
                 } else {
 #pragma unroll
@@ -73,7 +73,7 @@ __global__ void dz_prep_kernel(const float* __restrict__ dY, long long ld_dy, co
                         float v = 0.f;
                         if (col + j < N) {
                             v = dY[static_cast<long long>(m) * ld_dy + col + j];
-                            if (Y && !(ld1<YT>(Y + static_cast<long long>(m) * ld_y + col + j) > 0.f)) v = 0.f;
+                            if (Y) v = ld1<YT>(Y + static_cast<long long>(m) * ld_y + col + j) > 0.f ? v * yscale : 0.f;
                         }
                         dz[j] = v;
                     }
@@ -100,17 +100,19 @@ __global__ void dz_prep_kernel(const float* __restrict__ dY, long long ld_dy, co
                 }
             }
         }
-        if (db) {                                                // block-level column sums -> one atomic per column
+        if (db) {                                                // block-level column sums -> one atomic per column and block
 #pragma unroll
             for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = colsum[j];
             __syncthreads();
-            if (rl == 0 && ch < n8) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float t = 0.f;
-                    for (int r = 0; r < rstep; ++r) t += red[(r * cols_b + cl) * 8 + j];
-                    if (col + j < N && t != 0.f) atomicAdd(db + col + j, t);
-                }
+            // red[r][cl][j] is contiguous in (cl, j) = the column: consecutive threads take consecutive columns, so the shared-memory
+            // reads are conflict-free and a warp's 32 atomics hit 4 sectors of db instead of 32 (same-address atomics serialise
+            // in the L2 slice, so both their number — few, fat blocks — and their sector spread matter)
+            const int ncols = cols_b * 8;
+            for (int cc = threadIdx.x; cc < ncols; cc += 256) {
+                float t = 0.f;
+                for (int r = 0; r < rstep; ++r) t += red[r * ncols + cc];
+                const int col_g = c0 * 8 + cc;
+                if (col_g < N && t != 0.f) atomicAdd(db + col_g, t);
             }
             __syncthreads();
         }
@@ -118,17 +120,17 @@ __global__ void dz_prep_kernel(const float* __restrict__ dY, long long ld_dy, co
 }
 
 int launch_dz_prep(int ydt, const float* dY, long long ld_dy, const void* Y, long long ld_y, const float* rs, bf16* dZ, bf16* dZs,
-                   long long n_ld, long long plane_rows, int nplanes, float* db, int M, int N, cudaStream_t st) {
+                   long long n_ld, long long plane_rows, int nplanes, float* db, int M, int N, float yscale, cudaStream_t st) {
     if (M <= 0 || N <= 0) return STAIR_OK;
     if (n_ld % 8) return STAIR_ERR_ARG;
-    int rpb = (M + 1183) / 1184;
+    int rpb = (M + 591) / 592;                                   // <= 4 blocks per SM: every block adds N same-address atomics
     if (rpb < 8) rpb = 8;
     const int grid = (M + rpb - 1) / rpb;
     const int yesz = ydt == STAIR_BF16 ? 2 : 4;
     const int vec_ok = ((reinterpret_cast<uintptr_t>(dY) & 15) == 0 && (ld_dy % 4) == 0 &&
                         (!Y || ((reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (ld_y * yesz) % 16 == 0))) ? 1 : 0;
     DISPATCH_DT(ydt, YT, (dz_prep_kernel<YT><<<grid, 256, 0, st>>>(dY, ld_dy, reinterpret_cast<const YT*>(Y), ld_y, rs, dZ, rs ? dZs : nullptr,
-                                                                   n_ld, plane_rows, nplanes, db, M, N, rpb, vec_ok)));
+                                                                   n_ld, plane_rows, nplanes, db, M, N, rpb, vec_ok, yscale)));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -595,11 +597,14 @@ int launch_relate_bwd(const float* att_out, int out_base, const float* datt_out,
 // HasItem tail backward: a = sigmoid(w.x + b)
 template <typename AT>
 __global__ void rowdot_sigmoid_bwd_kernel(const AT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ a, const float* __restrict__ da,
-                                          float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long long rows, int H) {
+                                          float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long long rows, int H, float dscale) {
     const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
     for (long long row = blockIdx.x * static_cast<long long>(warps) + (threadIdx.x >> 5); row < rows; row += static_cast<long long>(gridDim.x) * warps) {
         const float av = a[row];
-        const float s = da[row] * av * (1.f - av);
+        float s;
+        if (dscale == 1.f) s = da[row] * av * (1.f - av);
+        else if (av == 0.f) s = 0.f;                              // dropped by the Sigmoid -> Dropout of HasItem (sigmoid itself is never 0)
+        else { const float sg = av / dscale; s = da[row] * dscale * sg * (1.f - sg); }
         for (int c = lane; c < H; c += 32) {
             dx[row * H + c] = s * __ldg(w + c);
             if (s != 0.f) atomicAdd(dw + c, s * ld1<AT>(x + row * H + c));
@@ -609,9 +614,9 @@ __global__ void rowdot_sigmoid_bwd_kernel(const AT* __restrict__ x, const float*
 }
 
 int launch_rowdot_sigmoid_bwd(int dt, const void* x, const float* w, const float* a, const float* da, float* dx, float* dw, float* db,
-                              long long rows, int H, cudaStream_t st) {
+                              long long rows, int H, float dscale, cudaStream_t st) {
     if (rows <= 0) return STAIR_OK;
-    DISPATCH_DT(dt, AT, (rowdot_sigmoid_bwd_kernel<AT><<<nblocks(rows, 8), 256, 0, st>>>(reinterpret_cast<const AT*>(x), w, a, da, dx, dw, db, rows, H)));
+    DISPATCH_DT(dt, AT, (rowdot_sigmoid_bwd_kernel<AT><<<nblocks(rows, 8), 256, 0, st>>>(reinterpret_cast<const AT*>(x), w, a, da, dx, dw, db, rows, H, dscale)));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }

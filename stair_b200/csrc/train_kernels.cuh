@@ -7,10 +7,10 @@
 
 namespace stair {
 
-// dz = dY * (Y > 0 if Y)  ->  bf16 planes dZ [np][M, N_ld]; dZs = rs[m] * dz planes (only if rs, else dZs may be null);
+// dz = dY * yscale * (Y > 0 if Y)  ->  bf16 planes dZ [np][M, N_ld]; dZs = rs[m] * dz planes (only if rs, else dZs may be null);
 // db[n] += sum_m dz (if db).  Columns N..N_ld are zero.
 int launch_dz_prep(int ydt, const float* dY, long long ld_dy, const void* Y, long long ld_y, const float* rs, bf16* dZ, bf16* dZs,
-                   long long n_ld, long long plane_rows, int nplanes, float* db, int M, int N, cudaStream_t st);
+                   long long n_ld, long long plane_rows, int nplanes, float* db, int M, int N, float yscale, cudaStream_t st);
 // dst [np][C, ld_dst] = transpose(src [np][R, ld_src] (first C columns)); columns R..ld_dst zeroed
 int launch_transpose_planes(const bf16* src, long long ld_src, long long src_plane_rows, bf16* dst, long long ld_dst, long long dst_plane_rows,
                             int nplanes, int R, int C, cudaStream_t st);
@@ -31,7 +31,7 @@ int launch_attnvideo_bwd(int dt, const float* dOut, const void* vid, const int* 
                          float* dvid, int n, int T, int H, cudaStream_t st);
 int launch_relate_bwd(const float* att_out, int out_base, const float* datt_out, const int* att_idx, int sign, float* datt, float* dbeta, int n, int T, cudaStream_t st);
 int launch_rowdot_sigmoid_bwd(int dt, const void* x, const float* w, const float* a, const float* da, float* dx, float* dw, float* db,
-                              long long rows, int H, cudaStream_t st);
+                              long long rows, int H, float dscale, cudaStream_t st);
 int launch_choose_bwd(int dt, const void* vec, const int* k1, const int* k2, const int* q, const float* dOut, float* dvec, int n, int H, cudaStream_t st);
 int launch_binary_bwd(int dt, const void* base, const int* a_idx, const int* b_idx, const float* dOut, float* dbase, int unit, int len, int op, int n, cudaStream_t st);
 int launch_array2_bwd(const float* dOut, const int* a_idx, const int* b_idx, float* dvec, int n, int H, cudaStream_t st);

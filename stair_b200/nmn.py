@@ -130,6 +130,9 @@ class VideoNMN(nn.Module):
 
     def forward_batch(self, batch: LY.NMNBatch, head_modules=frozenset(), phases=L.FWD_ALL, stream=None) -> ForwardState:
         """Enqueue VideoNMN.forward for a collated batch on the current stream; returns the device buffers."""
+        if self.training and float(self.config.get('dropout', 0.0) or 0.0) > 0.0:
+            raise L.StairError('forward() runs the inference path (no dropout); this model is in training mode with dropout=%g: '
+                               'train through stair_b200.train.NMNTrainStep (dropout applied there) or call model.eval()' % self.config['dropout'])
         st, model, sb, bufs = self.prepare(batch, head_modules)
         lib = L.lib()
         rc = lib.stair_nmn_forward(ctypes.byref(model), ctypes.byref(sb), ctypes.byref(bufs), L.i32(phases), L.stream_ptr(stream))

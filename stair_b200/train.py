@@ -171,7 +171,8 @@ class NMNTrainStep:
     """
 
     def __init__(self, model, module_loss_weight=1.0, decoder_loss_weight=1.0, gradient_accumulation=None,
-                 modules_no_intermediate_train=('FilterFrame',), distributed=None, process_group=None, global_negatives=True):
+                 modules_no_intermediate_train=('FilterFrame',), distributed=None, process_group=None, global_negatives=True,
+                 dropout_seed=None):
         self.model = model
         self.module_loss_weight, self.decoder_loss_weight = module_loss_weight, decoder_loss_weight
         self.gradient_accumulation = gradient_accumulation
@@ -179,6 +180,10 @@ class NMNTrainStep:
         self.group = process_group
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
         self.global_negatives = global_negatives
+        # nn.Dropout(config['dropout']) is active iff model.training (reference: model.train() in train_module.py:341).  Every run()
+        # draws a fresh counter-based mask: seed = base seed + number of windows run so far (+ rank under data parallelism).
+        self.dropout_seed = int(torch.initial_seed() if dropout_seed is None else dropout_seed) & 0xFFFFFFFFFFFFFFFF
+        self.windows_run = 0
         self._targets = None
         self._cache = {}
         self.last = None
@@ -256,8 +261,9 @@ class NMNTrainStep:
         pl.touched = touched_slots(batch, rows, cfg['have_pretrain_head'])
         return pl
 
-    def run(self, pl, assign_grads=True):
-        """Device work of one window: forward with history, losses, backward, (all-reduce), gradients into ``.grad``."""
+    def run(self, pl, assign_grads=True, dropout_seed=None):
+        """Device work of one window: forward with history, losses, backward, (all-reduce), gradients into ``.grad``.
+        ``dropout_seed`` pins the dropout masks of this window (tests); default: a fresh seed per call."""
         model, batch, rows = self.model, pl.batch, pl.rows
         dev = batch.device
         cfg = model.config
@@ -290,6 +296,12 @@ class NMNTrainStep:
         tr.cls_rep = cls_rep.data_ptr() if cls_rep is not None else None
         tr.answer = pl.answer.data_ptr()
         tr.dec_w = self.decoder_loss_weight / pl.ga
+        tr.dropout_p = float(cfg.get('dropout', 0.0) or 0.0) if model.training else 0.0
+        if dropout_seed is None:
+            rank = dist.get_rank(self.group) if self.distributed else 0
+            dropout_seed = (self.dropout_seed + 0x9E3779B97F4A7C15 * (self.windows_run * max(1, pl.world) + rank)) & 0xFFFFFFFFFFFFFFFF
+        tr.dropout_seed = int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
+        self.windows_run += 1
         loss = torch.zeros(8, dtype=torch.float32, device=dev)
         tr.loss = loss.data_ptr()
         sizes = st.sizes
@@ -339,8 +351,8 @@ class NMNTrainStep:
         return {'logits': st.logits, 'answers': st.answers, 'loss_terms': loss, 'loss': loss[:7].sum(), 'loss_counts': dict(rows.counts),
                 'state': st}
 
-    def __call__(self, data, assign_grads=True):
-        return self.run(self.plan(data), assign_grads=assign_grads)
+    def __call__(self, data, assign_grads=True, dropout_seed=None):
+        return self.run(self.plan(data), assign_grads=assign_grads, dropout_seed=dropout_seed)
 
 
 class TrainPlan:

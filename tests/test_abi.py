@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), 'missing export %s' % n
-    assert lib.stair_version() == 4
+    assert lib.stair_version() == 5
 
 
 def test_host_only_entry_points():
@@ -43,3 +43,25 @@ def test_struct_sizes_match_header_layout():
         assert ctypes.sizeof(struct) == lib.stair_sizeof(L.i32(which)), struct.__name__
     assert ctypes.sizeof(L.StairGroup) == 9 * 4
     assert ctypes.sizeof(L.StairModel) == 10 * 4 + 2 * 8 * L.W_COUNT
+
+
+def test_dropout_mask_host_matches_oracle_restatement():
+    """The counter-based dropout mask (csrc/stair_common.cuh) evaluated on the host by the library == the numpy restatement the
+    oracle injects (oracle/nmn_oracle.py dropout_keep); keep rate ~ 1 - p."""
+    import numpy as np
+    from oracle import nmn_oracle as orc
+    lib = L.lib()
+    for p, seed, site, row0, rows, cols in ((0.25, 12345678901234567, 17, 0, 64, 512), (0.5, 7, 3, 1000000, 33, 172),
+                                            (0.1, 2 ** 63 + 5, 99, 123456789, 8, 1), (0.0, 1, 2, 3, 4, 5)):
+        out = np.zeros((rows, cols), np.uint8)
+        rc = lib.stair_dropout_mask_host(ctypes.c_float(p), ctypes.c_uint64(seed), ctypes.c_int(site), ctypes.c_longlong(row0),
+                                         ctypes.c_int(rows), ctypes.c_int(cols), out.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+        want = orc.dropout_keep(seed, site, row0, rows, cols, p) if p > 0 else np.ones((rows, cols), bool)
+        assert np.array_equal(out.astype(bool), want)
+        if rows * cols > 4000:
+            assert abs(out.mean() - (1 - p)) < 0.02
+    # different sites / seeds give different masks
+    a = orc.dropout_keep(5, 1, 0, 32, 256, 0.25); b = orc.dropout_keep(5, 2, 0, 32, 256, 0.25); c = orc.dropout_keep(6, 1, 0, 32, 256, 0.25)
+    assert (a != b).mean() > 0.2 and (a != c).mean() > 0.2
+    assert lib.stair_dropout_mask_host(ctypes.c_float(1.0), ctypes.c_uint64(0), 0, ctypes.c_longlong(0), 1, 1, None) != 0

@@ -174,3 +174,95 @@ def test_adam_matches_torch():
         torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-7, msg=lambda m: '%s: %s' % (k, m))
     # and training moved the parameters
     assert float((a.submodules['decoder'][0].weight - before).abs().max()) > 1e-4
+
+
+# ---- dropout (reference default 0.25, video_nmn/args.py:31) --------------------------------------------------------------------
+_SITE_W = {'Localize.video_linear.0': 'LOC_V0_W', 'Temporal.dense.0': 'TEMP_D_W', 'FilterFrame.dense.0': 'FF_D_W', 'HasItem.param.0': 'HAS0_W',
+           'HasItem.param.3': 'HAS1_W', 'Exists.param.0': 'EXISTS0_W', 'Exists.param.3': 'EXISTS1_W', 'ToAction.param.0': 'TOACT0_W',
+           'decoder.0': 'DEC0_W'}
+
+
+def _mask_hook(batch, T, seed, p):
+    """Dropout hook for the oracle that reproduces the CUDA masks: site = the Linear the Dropout follows, row = sorted node position
+    (x T + frame for [T, H] activations), see csrc/exec_core.cuh drop_next."""
+    import numpy as np
+    from stair_b200 import _lib as L, layout as LY
+    perm = LY.host_grouping(batch)
+    pos = np.empty(len(perm), np.int64)
+    pos[perm] = np.arange(len(perm))
+
+    def site_id(site):
+        parts = site.split('.')
+        if parts[0] in ('Filter', 'FilterFrame') and parts[1] == 'param':
+            base = L.W[('FILT_' if parts[0] == 'Filter' else 'FF_') + {'representation': 'REPR'}.get(parts[2], parts[2].upper())]
+            return base + (0 if parts[3] == '0' else 2)
+        return L.W[_SITE_W[site]]
+
+    def hook(site, x, ctx):
+        q, i = ctx
+        if site == 'decoder.0':
+            row0, rows = q, 1
+        else:
+            pp = int(pos[int(batch.node_start[q]) + batch.layouts[q].node_of_token[i]])
+            row0, rows = (pp * T, x.shape[0]) if x.dim() == 2 else (pp, 1)
+        keep = orc.dropout_keep(seed, site_id(site), row0, rows, x.shape[-1], p)
+        return x * torch.from_numpy(keep.reshape(tuple(x.shape))).to(x.dtype) * (1.0 / (1.0 - p))
+    return hook
+
+
+@pytest.mark.parametrize('shape', ['rx', 'i3d'])
+def test_dropout_window_matches_oracle_with_the_same_masks(shape):
+    """Training mode with the reference's default dropout 0.25: loss and every gradient equal the oracle's autograd when the oracle
+    applies the same masks at every nn.Dropout site (all 14 layouts; Linear->ReLU->Dropout, HasItem's Sigmoid->Dropout, decoder)."""
+    from stair_b200 import collate
+    T, V, hid = (8, 256, 128) if shape == 'rx' else (64, 128, 64)
+    p, seed = 0.25, 0x1234567890ABCDEF
+    cfg = syn.model_config(T=T, V=V, hidden=hid, dropout=p, object_types=16)
+    torch.manual_seed(1)
+    ref_model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
+    weights = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
+    qs = syn.make_questions(28, T, V, seed=77, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    batch = collate(qs)
+    w = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
+    for k in list(w):
+        if k.startswith('submodules.Superlative.localize_module.'):
+            w[k] = w[k.replace('Superlative.localize_module', 'Localize')]
+    oracle = orc.OracleNMN(cfg, w, syn.PRETRAIN_MODULES, dropout=_mask_hook(batch, T, seed, p))
+    crit = orc.OracleCriterion({'obj_%d' % i: i for i in range(cfg['object_types'])})
+    total, _, _ = orc.window_loss(oracle, crit, qs)
+    total.backward()
+    ref_grads = {k: v.grad.detach() for k, v in w.items() if v.grad is not None and not k.startswith('submodules.Superlative.localize_module.')}
+    no_grad = [k for k, v in w.items() if v.grad is None]
+    # and the no-dropout loss differs (the masks really were applied)
+    plain = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES)
+    with torch.no_grad():
+        total_plain, _, _ = orc.window_loss(plain, crit, qs)
+    assert abs(float(total_plain) - float(total)) > 1e-3 * abs(float(total))
+    model = _model(cfg, weights, syn.PRETRAIN_MODULES, 'fp32')
+    step = NMNTrainStep(model)
+    out = step(batch, dropout_seed=seed)
+    torch.cuda.synchronize()
+    model.check_status(out['state'])
+    assert abs(float(out['loss']) - float(total)) <= LOSS_TOL['fp32'] * abs(float(total)), (float(out['loss']), float(total))
+    bad = _compare_grads(model, ref_grads, no_grad, 'fp32', 'dropout ' + shape)
+    assert not bad, '\n'.join(bad)
+    g_seeded = model.submodules['decoder'][0].weight.grad.clone()
+    # same seed -> bit-identical step; fresh seed -> different masks; eval mode -> no dropout at all
+    for prm in model.parameters():
+        prm.grad = None
+    out2 = step(batch, dropout_seed=seed)
+    assert float(out2['loss']) == float(out['loss']) and torch.equal(model.submodules['decoder'][0].weight.grad, g_seeded)
+    out3 = step(batch)
+    assert float(out3['loss']) != float(out['loss'])
+    model.eval()
+    for prm in model.parameters():
+        prm.grad = None
+    out4 = step(batch, dropout_seed=seed)
+    assert abs(float(out4['loss']) - float(total_plain)) <= LOSS_TOL['fp32'] * abs(float(total_plain))
+    # the inference entry point refuses a training-mode model with dropout (it would silently skip the masks)
+    from stair_b200._lib import StairError
+    model.train()
+    with pytest.raises(StairError):
+        model(qs[:2], return_res_by_step=False, test_mode=True)
+    model.eval()
+    model(qs[:2], return_res_by_step=False, test_mode=True)
