@@ -247,13 +247,14 @@ def test_dropout_window_matches_oracle_with_the_same_masks(shape):
     bad = _compare_grads(model, ref_grads, no_grad, 'fp32', 'dropout ' + shape)
     assert not bad, '\n'.join(bad)
     g_seeded = model.submodules['decoder'][0].weight.grad.clone()
-    # same seed -> bit-identical step; fresh seed -> different masks; eval mode -> no dropout at all
+    # same seed -> the same masks (sums differ only by atomic ordering); fresh seed -> different masks; eval mode -> no dropout
     for prm in model.parameters():
         prm.grad = None
     out2 = step(batch, dropout_seed=seed)
-    assert float(out2['loss']) == float(out['loss']) and torch.equal(model.submodules['decoder'][0].weight.grad, g_seeded)
+    assert abs(float(out2['loss']) - float(out['loss'])) <= 1e-6 * abs(float(out['loss']))
+    torch.testing.assert_close(model.submodules['decoder'][0].weight.grad, g_seeded, rtol=1e-4, atol=1e-7)
     out3 = step(batch)
-    assert float(out3['loss']) != float(out['loss'])
+    assert abs(float(out3['loss']) - float(out['loss'])) > 1e-5 * abs(float(out['loss']))
     model.eval()
     for prm in model.parameters():
         prm.grad = None
