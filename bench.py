@@ -315,13 +315,13 @@ def main():
     # gradient all-reduce (N > 1) + Adam, one window = the rank's 4096 questions; device-timed, max over ranks -------------
     train = None
     if not args.no_train:
-        from stair_b200.train import NMNTrainStep, Adam
+        from stair_b200.train import NMNTrainStep, FusedAdam
         # throughput run: the reference's default training dropout (video_nmn/args.py:31); parity runs (tests) use 0 or injected masks
         tmodel = VideoNMN(dict(cfg, dropout=TRAIN_DROPOUT), pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16')
         tmodel.load_state_dict(weights)
         tmodel = tmodel.to(dev).train()
         tstep = NMNTrainStep(tmodel)
-        opt = Adam(tmodel.parameters(), lr=2e-4)
+        opt = FusedAdam(tmodel, lr=2e-4)
         plan = tstep.plan(batch)
 
         def train_step():
@@ -348,7 +348,7 @@ def main():
         train = {'value': world * B * ksteps / (tms * 1e-3), 'unit': UNIT, 'ms_per_step': tms / ksteps, 'steps': ksteps,
                  'launches_per_step': tstep.last_launches, 'window_questions': world * B, 'loss': float(out['loss']),
                  'loss_rows': out['loss_counts'], 'dropout': TRAIN_DROPOUT,
-                 'what': 'forward with encoder history + losses (train_module.py:83-194) + backward + %sAdam; bf16 storage, fp32 gradients'
+                 'what': 'forward with encoder history + losses (train_module.py:83-194) + backward + %sAdam (one fused multi-tensor kernel that also refreshes the bf16 weight copies); bf16 storage, fp32 gradients'
                          % ('NCCL gradient all-reduce + ' if world > 1 else '')}
         del tmodel, tstep, opt, plan
         torch.cuda.empty_cache()

@@ -197,7 +197,7 @@ typedef struct StairTrain {
 int stair_dropout_mask_host(float p, unsigned long long seed, int site, long long row0, int rows, int cols, unsigned char* keep);
 int stair_version(void);
 /* sizeof() of the ABI structs as compiled (0 StairModel, 1 StairGroup, 2 StairBatch, 3 StairBuffers, 4 StairItabLayout, 5 StairTrain):
- * lets a binding verify its mirror of the struct layouts. */
+ * 6 StairAdamSeg; lets a binding verify its mirror of the struct layouts. */
 int64_t stair_sizeof(int which);
 /* concurrency of the module phase: independent groups of one schedule wave run on up to `lanes` (1..8, default 4) internal streams
  * forked from and joined back into the caller's stream (the call stays stream-ordered for the caller) */
@@ -248,6 +248,21 @@ int stair_nmn_backward(const StairModel* model, const StairBatch* batch, const S
 /* torch.optim.Adam step (weight_decay 0) on one parameter tensor; `step` counts from 1 (train_module.py:326-332,408-412) */
 int stair_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
                     float eps, int step, void* stream);
+/* Multi-tensor Adam fused with the refresh of the kernels' weight copies: ONE launch updates every listed parameter (fp32 master,
+ * exp_avg, exp_avg_sq; same arithmetic as stair_adam_step) and rewrites what the forward / backward kernels read — the bf16 plane
+ * copy [nplanes][rows, ld], its transposed copy [cols, ld_t] (B operand of dX = dZ.W), the gate-interleaved W_hh copy of the fused
+ * recurrence, or the fp32 vector copy.  Replaces one optimizer kernel per tensor plus a re-pack of all 119 tensors per step.
+ * `segs` is a DEVICE array; tiles are 64 x 64 elements (matrices) or 1024 elements (vectors); tile0 = prefix sum of tile counts. */
+typedef struct StairAdamSeg {
+    float* p; const float* g; float* m; float* v;            /* [rows, cols] fp32, contiguous */
+    float* p2; const float* g2; float* m2; float* v2;        /* optional second parameter whose SUM with p the kernels read (LSTM b_ih + b_hh); NULL = none */
+    void* packed; int64_t packed_ld; int64_t packed_plane;   /* kind 1: bf16 row r at packed + r*ld (+ plane*packed_plane); kind 0: fp32 vector */
+    void* packed_t; int64_t packed_t_ld; int64_t packed_t_plane;   /* transposed bf16 copy: element (r, c) at packed_t + c*ld_t + r; NULL = none */
+    void* packed_perm;                                       /* bf16 copy with rows gate-interleaved (r = g*hh + c64*64 + j -> c64*256 + g*64 + j); NULL = none */
+    int32_t rows, cols, kind, nplanes, perm_hh, tile0;
+    float bc1, bc2;                                          /* 1 - beta1^step, 1 - beta2^step of this parameter */
+} StairAdamSeg;
+int stair_adam_multi(const StairAdamSeg* segs /*DEVICE*/, int n_segs, int total_tiles, float lr, float beta1, float beta2, float eps, void* stream);
 /* number of kernels stair_nmn_forward launched in its last call on this thread (bench.py's gpu_launches). */
 int64_t stair_last_launch_count(void);
 

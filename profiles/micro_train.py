@@ -3,16 +3,16 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from stair_b200 import VideoNMN, synthetic as syn, collate
-from stair_b200.train import NMNTrainStep, Adam
+from stair_b200.train import NMNTrainStep, FusedAdam
 
 B, T, V = int(os.environ.get('B', 4096)), 8, 4096
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-cfg = syn.model_config(T=T, V=V)
+cfg = syn.model_config(T=T, V=V, dropout=float(os.environ.get('DROPOUT', 0.25)))
 torch.manual_seed(0)
 model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().train()
 qs = syn.make_questions(B, T, V, seed=1234, with_gold=True)
 batch = collate(qs, video_dtype=torch.bfloat16).to('cuda')
-step, opt = NMNTrainStep(model), Adam(model.parameters())
+step, opt = NMNTrainStep(model), FusedAdam(model)
 plan = step.plan(batch)
 for i in range(steps):
     torch.cuda.synchronize()

@@ -88,6 +88,14 @@ class StairTrain(ctypes.Structure):
                 ('dropout_p', ctypes.c_float), ('dropout_seed', ctypes.c_uint64)]
 
 
+class StairAdamSeg(ctypes.Structure):
+    _fields_ = [('p', vp), ('g', vp), ('m', vp), ('v', vp), ('p2', vp), ('g2', vp), ('m2', vp), ('v2', vp),
+                ('packed', vp), ('packed_ld', i64), ('packed_plane', i64),
+                ('packed_t', vp), ('packed_t_ld', i64), ('packed_t_plane', i64), ('packed_perm', vp),
+                ('rows', i32), ('cols', i32), ('kind', i32), ('nplanes', i32), ('perm_hh', i32), ('tile0', i32),
+                ('bc1', ctypes.c_float), ('bc2', ctypes.c_float)]
+
+
 _lib = None
 
 

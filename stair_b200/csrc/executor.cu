@@ -32,6 +32,7 @@ extern "C" int64_t stair_sizeof(int which) {
     case 3: return sizeof(StairBuffers);
     case 4: return sizeof(StairItabLayout);
     case 5: return sizeof(StairTrain);
+    case 6: return sizeof(StairAdamSeg);
     default: return -1;
     }
 }

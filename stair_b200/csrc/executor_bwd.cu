@@ -571,6 +571,11 @@ extern "C" int stair_adam_step(float* param, const float* grad, float* exp_avg, 
     return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int stair_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, float beta1, float beta2, float eps, void* stream) {
+    if (!segs && n_segs > 0) return STAIR_ERR_ARG;
+    return launch_adam_multi(segs, n_segs, total_tiles, lr, beta1, beta2, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // Host-side evaluation of the dropout mask (no GPU work): lets a binding / test restate and verify the counter-based mask that the
 // training kernels apply on the device (stair_common.cuh make_drop / drop_keep).
 extern "C" int stair_dropout_mask_host(float p, unsigned long long seed, int site, long long row0, int rows, int cols, unsigned char* keep) {

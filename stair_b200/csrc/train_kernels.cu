@@ -1123,6 +1123,142 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-tensor Adam + weight-copy refresh (see StairAdamSeg in include/stair_b200.h)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float adam_update(float& p, float g, float& m, float& v, float lr, float b1, float b2, float eps, float bc1, float bc2) {
+    const float mi = b1 * m + (1.f - b1) * g;
+    const float vi = b2 * v + (1.f - b2) * g * g;
+    m = mi; v = vi;
+    p -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+    return p;
+}
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const StairAdamSeg* __restrict__ segs, int n_segs, float lr, float b1, float b2, float eps) {
+    __shared__ unsigned short tile[3][64][66];
+    __shared__ StairAdamSeg sg;
+    // segment of this block's tile: last seg with tile0 <= blockIdx.x
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n_segs - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (segs[mid].tile0 <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+        }
+        sg = segs[lo];
+    }
+    __syncthreads();
+    const int t = static_cast<int>(blockIdx.x) - sg.tile0;
+    if (sg.kind == 0) {                                          // fp32 vector: 1024 elements per tile
+        const long long n = static_cast<long long>(sg.rows) * sg.cols;
+        float* dst = reinterpret_cast<float*>(sg.packed);
+        for (int k = 0; k < 4; ++k) {
+            const long long i = static_cast<long long>(t) * 1024 + k * 256 + threadIdx.x;
+            if (i >= n) break;
+            float pv = sg.p[i], mv = sg.m[i], vv = sg.v[i];
+            float val = adam_update(pv, sg.g[i], mv, vv, lr, b1, b2, eps, sg.bc1, sg.bc2);
+            sg.p[i] = pv; sg.m[i] = mv; sg.v[i] = vv;
+            if (sg.p2) {
+                float p2 = sg.p2[i], m2 = sg.m2[i], v2 = sg.v2[i];
+                val += adam_update(p2, sg.g2[i], m2, v2, lr, b1, b2, eps, sg.bc1, sg.bc2);
+                sg.p2[i] = p2; sg.m2[i] = m2; sg.v2[i] = v2;
+            }
+            if (dst) dst[i] = val;
+        }
+        return;
+    }
+    const int tiles_c = (sg.cols + 63) >> 6;
+    const int r0 = (t / tiles_c) * 64, c0 = (t % tiles_c) * 64;
+    const int tr = threadIdx.x >> 3, tc = (threadIdx.x & 7) * 8;
+    const bool vec = (sg.cols & 3) == 0;
+    bf16* pk = reinterpret_cast<bf16*>(sg.packed);
+    bf16* pp = reinterpret_cast<bf16*>(sg.packed_perm);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int r = r0 + tr + 32 * pass, c = c0 + tc;
+        float w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = 0.f;
+        if (r < sg.rows && c < sg.cols) {
+            const long long o = static_cast<long long>(r) * sg.cols + c;
+            if (vec && c + 8 <= sg.cols) {
+                float4 pa = *reinterpret_cast<const float4*>(sg.p + o), pb = *reinterpret_cast<const float4*>(sg.p + o + 4);
+                const float4 ga = *reinterpret_cast<const float4*>(sg.g + o), gb = *reinterpret_cast<const float4*>(sg.g + o + 4);
+                float4 ma = *reinterpret_cast<const float4*>(sg.m + o), mb = *reinterpret_cast<const float4*>(sg.m + o + 4);
+                float4 va = *reinterpret_cast<const float4*>(sg.v + o), vb = *reinterpret_cast<const float4*>(sg.v + o + 4);
+                w[0] = adam_update(pa.x, ga.x, ma.x, va.x, lr, b1, b2, eps, sg.bc1, sg.bc2);
+                w[1] = adam_update(pa.y, ga.y, ma.y, va.y, lr, b1, b2, eps, sg.bc1, sg.bc2);
+                w[2] = adam_update(pa.z, ga.z, ma.z, va.z, lr, b1, b2, eps, sg.bc1, sg.bc2);
+                w[3] = adam_update(pa.w, ga.w, ma.w, va.w, lr, b1, b2, eps, sg.bc1, sg.bc2);
+                w[4] = adam_update(pb.x, gb.x, mb.x, vb.x, lr, b1, b2, eps, sg.bc1, sg.bc2);
+                w[5] = adam_update(pb.y, gb.y, mb.y, vb.y, lr, b1, b2, eps, sg.bc1, sg.bc2);
+                w[6] = adam_update(pb.z, gb.z, mb.z, vb.z, lr, b1, b2, eps, sg.bc1, sg.bc2);
+                w[7] = adam_update(pb.w, gb.w, mb.w, vb.w, lr, b1, b2, eps, sg.bc1, sg.bc2);
+                *reinterpret_cast<float4*>(sg.p + o) = pa; *reinterpret_cast<float4*>(sg.p + o + 4) = pb;
+                *reinterpret_cast<float4*>(sg.m + o) = ma; *reinterpret_cast<float4*>(sg.m + o + 4) = mb;
+                *reinterpret_cast<float4*>(sg.v + o) = va; *reinterpret_cast<float4*>(sg.v + o + 4) = vb;
+            } else {
+                for (int j = 0; j < 8 && c + j < sg.cols; ++j) {
+                    float pv = sg.p[o + j], mv = sg.m[o + j], vv = sg.v[o + j];
+                    w[j] = adam_update(pv, sg.g[o + j], mv, vv, lr, b1, b2, eps, sg.bc1, sg.bc2);
+                    sg.p[o + j] = pv; sg.m[o + j] = mv; sg.v[o + j] = vv;
+                }
+            }
+            // bf16 planes of the updated weights: row-major copy (+ gate-interleaved copy), staged in smem for the transposed copy
+            int rp = r;
+            if (pp) { const int hh = sg.perm_hh, gi = r / hh, rem = r % hh; rp = (rem >> 6) * 256 + gi * 64 + (rem & 63); }
+            for (int pl = 0; pl < sg.nplanes; ++pl) {
+                unsigned short hv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bf16 hb = __float2bfloat16_rn(w[j]);
+                    hv[j] = *reinterpret_cast<const unsigned short*>(&hb);
+                    w[j] -= __bfloat162float(hb);                 // residual for the next plane (exact bf16x3 split)
+                    tile[pl][tr + 32 * pass][tc + j] = hv[j];
+                }
+                const uint4 q = make_uint4(hv[0] | (static_cast<uint32_t>(hv[1]) << 16), hv[2] | (static_cast<uint32_t>(hv[3]) << 16),
+                                           hv[4] | (static_cast<uint32_t>(hv[5]) << 16), hv[6] | (static_cast<uint32_t>(hv[7]) << 16));
+                bf16* d = pk + pl * sg.packed_plane + static_cast<long long>(r) * sg.packed_ld + c;
+                if (c + 8 <= sg.cols && (sg.packed_ld & 7) == 0) *reinterpret_cast<uint4*>(d) = q;
+                else for (int j = 0; j < 8 && c + j < sg.cols; ++j) reinterpret_cast<unsigned short*>(d)[j] = hv[j];
+                if (pp && pl == 0) {
+                    bf16* e = pp + static_cast<long long>(rp) * sg.packed_ld + c;
+                    if (c + 8 <= sg.cols && (sg.packed_ld & 7) == 0) *reinterpret_cast<uint4*>(e) = q;
+                    else for (int j = 0; j < 8 && c + j < sg.cols; ++j) reinterpret_cast<unsigned short*>(e)[j] = hv[j];
+                }
+            }
+        } else {
+            for (int pl = 0; pl < sg.nplanes; ++pl)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tile[pl][tr + 32 * pass][tc + j] = 0;
+        }
+    }
+    if (!sg.packed_t) return;                                    // block-uniform
+    __syncthreads();
+    unsigned short* pt = reinterpret_cast<unsigned short*>(sg.packed_t);
+    for (int pl = 0; pl < sg.nplanes; ++pl)
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int c = c0 + tr + 32 * pass;                   // row of the transposed copy = source column
+            const int r = r0 + tc;                               // 8 consecutive destination columns = source rows
+            if (c >= sg.cols || r >= sg.rows) continue;
+            unsigned short hv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hv[j] = tile[pl][tc + j][tr + 32 * pass];
+            unsigned short* d = pt + pl * sg.packed_t_plane + static_cast<long long>(c) * sg.packed_t_ld + r;
+            if (r + 8 <= sg.rows && (sg.packed_t_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0)
+                *reinterpret_cast<uint4*>(d) = make_uint4(hv[0] | (static_cast<uint32_t>(hv[1]) << 16), hv[2] | (static_cast<uint32_t>(hv[3]) << 16),
+                                                          hv[4] | (static_cast<uint32_t>(hv[5]) << 16), hv[6] | (static_cast<uint32_t>(hv[7]) << 16));
+            else for (int j = 0; j < 8 && r + j < sg.rows; ++j) d[j] = hv[j];
+        }
+}
+
+int launch_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, float b1, float b2, float eps, cudaStream_t st) {
+    if (n_segs <= 0 || total_tiles <= 0) return STAIR_OK;
+    adam_multi_kernel<<<total_tiles, 256, 0, st>>>(segs, n_segs, lr, b1, b2, eps);
+    STAIR_CHECK_LAUNCH();
+    return STAIR_OK;
+}
+
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1, float bc2, cudaStream_t st) {
     if (n <= 0) return STAIR_OK;
     adam_kernel<<<nblocks(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2);

@@ -19,7 +19,7 @@ import os
 import torch
 
 from . import layout as LY
-from .train import NMNTrainStep, LOSS_SLOTS
+from .train import NMNTrainStep, FusedAdam, LOSS_SLOTS
 
 
 @torch.no_grad()
@@ -80,7 +80,8 @@ def train(windows, model, lr=2e-4, weight_decay=0.0, module_loss_weight=1.0, dec
     step = forward + losses + backward on the GPU, torch Adam (skips parameters the window did not touch, like the reference),
     scheduler step.  Returns the trainer state (optimizer, scheduler, global_steps, loss history) for ``save_checkpoint``."""
     if state is None:
-        opt = torch.optim.Adam(model.parameters(), lr, weight_decay=weight_decay)
+        # reference optimizer (weight_decay 0): one fused kernel per step that also refreshes the kernels' weight copies
+        opt = FusedAdam(model, lr=lr) if weight_decay == 0 else torch.optim.Adam(model.parameters(), lr, weight_decay=weight_decay)
         state = {'optimizer': opt, 'scheduler': make_scheduler(opt, **(scheduler_kwargs or {})), 'global_steps': 0, 'losses': [],
                  'scheduler_kwargs': dict(scheduler_kwargs or {})}
     step = NMNTrainStep(model, module_loss_weight=module_loss_weight, decoder_loss_weight=decoder_loss_weight,
@@ -128,7 +129,7 @@ def load_checkpoint(ckpt_dir, model_cls, device='cuda', precision='bf16', pretra
     model = model.to(device)
     if not with_trainer_state:
         return model
-    opt = torch.optim.Adam(model.parameters(), lr)
+    opt = FusedAdam(model, lr=lr)
     p = os.path.join(ckpt_dir, 'trainer_state.pt')
     ts = torch.load(p, map_location='cpu', weights_only=False) if os.path.exists(p) else None
     kw = dict(ts.get('scheduler_kwargs', {})) if ts else {}          # the LambdaLR schedule itself is not in its state_dict

@@ -302,6 +302,10 @@ class PackedWeights:
         self.want_transposed = False
         self.model_struct = None
 
+    def mark_current(self, sub, precision, device):
+        """The packed copies were just rewritten from the parameters by ``stair_adam_multi`` (train.FusedAdam)."""
+        self.signature = (precision, str(device)) + tuple((p.data_ptr(), p._version) for p in sub.parameters())
+
     def refresh(self, sub, config, precision, device, training=False):
         params = [p for p in sub.parameters()]
         sig = (precision, str(device)) + tuple((p.data_ptr(), p._version) for p in params)

@@ -394,3 +394,133 @@ class Adam:
                                         L.i32(s['step']), L.stream_ptr()), 'stair_adam_step')
             # the update happened behind torch's back: bump the version counter so PackedWeights.refresh re-packs
             torch.autograd.graph.increment_version(p)
+
+
+class FusedAdam(torch.optim.Adam):
+    """``torch.optim.Adam(model.parameters(), lr, betas, eps, weight_decay=0)`` (train_module.py:326-332) as ONE kernel per step
+    (``stair_adam_multi``): every parameter with a gradient is updated (parameters whose ``grad`` is None are skipped and their
+    step counter does not advance, like torch) and the copies the CUDA kernels read — bf16 planes, transposed planes, the
+    gate-interleaved W_hh, fp32 vectors (``PackedWeights``) — are rewritten in the same pass, so the next forward neither re-packs
+    119 tensors with ~400 small torch kernels nor launches one optimizer kernel per tensor.
+
+    State layout (``state[p] = {'step', 'exp_avg', 'exp_avg_sq'}``), ``param_groups`` (so ``LambdaLR`` works) and ``state_dict()``
+    are torch.optim.Adam's: checkpoints are interchangeable with the reference's optimizer."""
+
+    def __init__(self, model, lr=2e-4, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(model.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=0.0)
+        self.model = model
+        self._slots = None
+
+    def _slot_table(self):
+        if self._slots is None:
+            from .params import weight_sources
+            sub, cfg = self.model.submodules, self.model.config
+            kinds = {wid: kind for wid, (kind, _) in weight_sources(sub, cfg).items()}
+            perm_of = {}
+            for enc in ('VENC', 'TENC'):
+                for d in ('F', 'R'):
+                    if L.W.get('%s_WHHI_%s' % (enc, d)) in kinds:
+                        perm_of[L.W['%s_WHH_%s' % (enc, d)]] = L.W['%s_WHHI_%s' % (enc, d)]
+            slots = []
+            for wid, (_, targets) in sorted(grad_targets(sub, cfg).items()):
+                if wid not in kinds:
+                    continue
+                if kinds[wid] == 'V':                       # pair parameters that share an offset (b_ih + b_hh of one direction)
+                    by_off = {}
+                    for prm, o in targets:
+                        by_off.setdefault(o, []).append(prm)
+                    for o, prms in sorted(by_off.items()):
+                        if len(prms) > 2:
+                            raise L.StairError('more than two parameters share weight-table slot %d' % wid)
+                        slots.append((wid, 'V', prms[0], prms[1] if len(prms) > 1 else None, o, None))
+                else:
+                    for prm, o in targets:
+                        slots.append((wid, 'M', prm, None, o, perm_of.get(wid)))
+            self._slots = slots
+        return self._slots
+
+    def _state_of(self, p):
+        s = self.state[p]
+        if not s:
+            s['step'] = torch.tensor(0.0, dtype=torch.float32)
+            s['exp_avg'] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
+            s['exp_avg_sq'] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
+        return s
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from .nmn import PRECISIONS
+        if closure is not None:
+            raise L.StairError('FusedAdam does not take a closure')
+        if len(self.param_groups) != 1 or self.param_groups[0].get('weight_decay', 0):
+            raise L.StairError('FusedAdam implements the reference optimizer: one parameter group, weight_decay = 0')
+        model = self.model
+        group = self.param_groups[0]
+        lr, (b1, b2), eps = float(group['lr']), group['betas'], float(group['eps'])
+        dev = next(model.parameters()).device
+        pw = model._packed
+        pw.refresh(model.submodules, model.config, PRECISIONS[model.precision], dev, training=True)   # no-op when current
+        lib = L.lib()
+        segs, covered, tile0 = [], set(), 0
+        for wid, kind, prm, prm2, off, perm_wid in self._slot_table():
+            covered.add(id(prm))
+            if prm2 is not None:
+                covered.add(id(prm2))
+            if prm.grad is None or (prm2 is not None and prm2.grad is None):
+                continue
+            L.require_cuda(prm, 'parameter')
+            sg = L.StairAdamSeg()
+            st = self._state_of(prm)
+            st['step'] += 1
+            k = float(st['step'])
+            sg.bc1, sg.bc2 = 1.0 - b1 ** k, 1.0 - b2 ** k
+            g = prm.grad if prm.grad.is_contiguous() else prm.grad.contiguous()
+            sg.p, sg.g, sg.m, sg.v = prm.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr()
+            keep = [g]
+            if prm2 is not None:
+                s2 = self._state_of(prm2)
+                s2['step'] += 1
+                g2 = prm2.grad if prm2.grad.is_contiguous() else prm2.grad.contiguous()
+                sg.p2, sg.g2, sg.m2, sg.v2 = prm2.data_ptr(), g2.data_ptr(), s2['exp_avg'].data_ptr(), s2['exp_avg_sq'].data_ptr()
+                keep.append(g2)
+            packed = pw.tensors[wid]
+            if kind == 'V':
+                sg.kind, sg.nplanes, sg.rows, sg.cols = 0, 1, 1, prm.numel()
+                sg.packed = packed.data_ptr() + 4 * off
+                ntiles = (prm.numel() + 1023) // 1024
+            else:
+                rows = prm.shape[0]
+                cols = prm.numel() // rows
+                nplanes = packed.shape[0] if packed.dim() == 3 else 1
+                n_total, ld = packed.shape[-2], packed.shape[-1]
+                row_off = off // cols
+                sg.kind, sg.nplanes, sg.rows, sg.cols = 1, nplanes, rows, cols
+                sg.packed, sg.packed_ld, sg.packed_plane = packed.data_ptr() + 2 * row_off * ld, ld, n_total * ld
+                tt = pw.transposed.get(wid)
+                if tt is not None:
+                    ld_t = tt.shape[-1]
+                    sg.packed_t, sg.packed_t_ld, sg.packed_t_plane = tt.data_ptr() + 2 * row_off, ld_t, tt.shape[-2] * ld_t
+                if perm_wid is not None and perm_wid in pw.tensors:
+                    sg.packed_perm, sg.perm_hh = pw.tensors[perm_wid].data_ptr(), cols
+                ntiles = ((rows + 63) // 64) * ((cols + 63) // 64)
+            sg.tile0 = tile0
+            tile0 += ntiles
+            segs.append((sg, keep))
+        if segs:
+            arr = (L.StairAdamSeg * len(segs))(*[s for s, _ in segs])
+            table = torch.frombuffer(bytearray(arr), dtype=torch.uint8).to(dev, non_blocking=True)
+            L.check(lib.stair_adam_multi(L.ptr(table), L.i32(len(segs)), L.i32(tile0), ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2),
+                                         ctypes.c_float(eps), L.stream_ptr()), 'stair_adam_multi')
+            # the update (and the refresh of the packed copies) happened behind torch's back: keep PackedWeights' signature valid
+            pw.mark_current(model.submodules, PRECISIONS[model.precision], dev)
+        # parameters outside the weight table (none in the reference model) fall back to the per-tensor kernel + a full re-pack
+        for prm in group['params']:
+            if id(prm) in covered or prm.grad is None:
+                continue
+            st = self._state_of(prm)
+            st['step'] += 1
+            L.check(lib.stair_adam_step(L.ptr(prm), L.ptr(prm.grad.contiguous()), L.ptr(st['exp_avg']), L.ptr(st['exp_avg_sq']), L.i64(prm.numel()),
+                                        ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps), L.i32(int(st['step'])),
+                                        L.stream_ptr()), 'stair_adam_step')
+            torch.autograd.graph.increment_version(prm)
+        return None

@@ -39,7 +39,8 @@ def test_struct_sizes_match_header_layout():
     # int32 fields first, then pointers: ctypes mirrors of the C structs must have the C sizes
     lib = L.lib()
     lib.stair_sizeof.restype = ctypes.c_longlong
-    for which, struct in enumerate((L.StairModel, L.StairGroup, L.StairBatch, L.StairBuffers, L.StairItabLayout, L.StairTrain)):
+    for which, struct in enumerate((L.StairModel, L.StairGroup, L.StairBatch, L.StairBuffers, L.StairItabLayout, L.StairTrain,
+                                    L.StairAdamSeg)):
         assert ctypes.sizeof(struct) == lib.stair_sizeof(L.i32(which)), struct.__name__
     assert ctypes.sizeof(L.StairGroup) == 9 * 4
     assert ctypes.sizeof(L.StairModel) == 10 * 4 + 2 * 8 * L.W_COUNT

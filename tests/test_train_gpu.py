@@ -18,7 +18,7 @@ import torch
 
 from oracle import nmn_oracle as orc
 from stair_b200 import VideoNMN, synthetic as syn
-from stair_b200.train import NMNTrainStep, Adam, span_to_attention
+from stair_b200.train import NMNTrainStep, Adam, FusedAdam, span_to_attention
 from tests import golden_util as gu
 
 pytestmark = pytest.mark.gpu
@@ -267,3 +267,49 @@ def test_dropout_window_matches_oracle_with_the_same_masks(shape):
         model(qs[:2], return_res_by_step=False, test_mode=True)
     model.eval()
     model(qs[:2], return_res_by_step=False, test_mode=True)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_fused_adam_matches_torch_and_refreshes_the_packed_weights(precision):
+    """stair_adam_multi (one launch: Adam + rewrite of the bf16 / transposed / gate-interleaved / fp32 copies the kernels read) ==
+    torch.optim.Adam followed by a full re-pack: same parameters, same optimizer state, and the NEXT forward / training step of the
+    fused model (which reuses the rewritten copies) equals the one of the re-packed model."""
+    cfg = syn.model_config(T=8, V=128, hidden=64, object_types=16)
+    torch.manual_seed(5)
+    a = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision=precision).cuda().train()
+    b = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision=precision).cuda().train()
+    b.load_state_dict(a.state_dict())
+    qs = syn.make_questions(14, 8, 128, seed=9, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    qs2 = syn.make_questions(4, 8, 128, seed=10, templates=['equals', 'toaction'], with_gold=True, object_types=16)
+    oa, ob = FusedAdam(a, lr=2e-3), torch.optim.Adam(b.parameters(), lr=2e-3)
+    sched = torch.optim.lr_scheduler.LambdaLR(oa, lambda it: 1.0 - 0.1 * it)         # param_groups['lr'] is honoured
+    sched_b = torch.optim.lr_scheduler.LambdaLR(ob, lambda it: 1.0 - 0.1 * it)
+    sa, sb = NMNTrainStep(a), NMNTrainStep(b)
+    tol = dict(rtol=1e-5, atol=1e-7) if precision == 'fp32' else dict(rtol=2e-2, atol=2e-4)
+    for window in (qs, qs2, qs):                          # the middle window leaves most modules untouched (skipped by Adam)
+        la = sa(window)['loss']; oa.step(); oa.zero_grad(); sched.step()
+        lb = sb(window)['loss']; ob.step(); ob.zero_grad(); sched_b.step()
+        assert abs(float(la) - float(lb)) <= (1e-5 if precision == 'fp32' else 2e-2) * abs(float(lb))
+    torch.cuda.synchronize()
+    if precision == 'fp32':
+        for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            torch.testing.assert_close(pa, pb, msg=lambda m: '%s: %s' % (k, m), **tol)
+    # the packed copies the fused kernel rewrote == a fresh re-pack of the same parameters
+    import copy
+    fresh = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision=precision).cuda().train()
+    fresh.load_state_dict(a.state_dict())
+    NMNTrainStep(fresh)(qs2, assign_grads=False)          # builds fresh packed + transposed copies
+    for wid, t in fresh._packed.tensors.items():
+        assert torch.equal(a._packed.tensors[wid], t), 'packed copy of weight slot %d is stale' % wid
+    for wid, t in fresh._packed.transposed.items():
+        assert torch.equal(a._packed.transposed[wid], t), 'transposed copy of weight slot %d is stale' % wid
+    # optimizer state is torch.optim.Adam's: load it into a torch Adam over the same parameters
+    oc = torch.optim.Adam(a.parameters(), lr=2e-3)
+    oc.load_state_dict(oa.state_dict())
+    n_state = sum(1 for p in a.parameters() if oc.state.get(p))
+    assert n_state == sum(1 for p in b.parameters() if ob.state.get(p)) and n_state > 40
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        if ob.state.get(pb):
+            assert float(oc.state[pa]['step']) == float(ob.state[pb]['step'])
+            if precision == 'fp32':
+                torch.testing.assert_close(oc.state[pa]['exp_avg'], ob.state[pb]['exp_avg'], rtol=1e-4, atol=1e-9)
