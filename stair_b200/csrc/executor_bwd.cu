@@ -324,6 +324,9 @@ int run_encoders_train(Ctx& c, const StairTrain& tr) {
     if (tr.saved_bytes < SL.total) return STAIR_ERR_CAPACITY;
     char* sv = reinterpret_cast<char*>(tr.saved);
     float* g = c.at<float>(c.plan.g);
+    // bf16 path: both recurrences run in the persistent fused kernel (csrc/lstm_fused.cu), which writes the BPTT history itself
+    const bool fused = lstm_fused_ok(m.precision, h) && g_lstm_impl == 0 && c.W(STAIR_W_VENC_WHHI_F) && c.W(STAIR_W_TENC_WHHI_F);
+    LstmHist hist;
     for (int e = 0; e < 2; ++e) {
         const EncIO io = enc_io(c, e);
         bf16* in = c.at<bf16>(e == 0 ? c.plan.xv_in : c.plan.xq_in);
@@ -344,6 +347,12 @@ int run_encoders_train(Ctx& c, const StairTrain& tr) {
         const long long hs_dir = static_cast<long long>(S + 1) * B * h;      // [np][2][S+1][B][h]
         const long long hs_plane = 2 * hs_dir;
         if (cudaMemsetAsync(hs, 0, sizeof(bf16) * c.np * hs_plane, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
+        if (fused) {
+            hist.gates[e] = gates; hist.c[e] = cs; hist.hs[e] = hs; hist.hs_dir[e] = hs_dir;
+            // finished questions of the ragged text batch are not written by the fused kernel: their gate history must read as 0
+            // nowhere (the BPTT cell skips inactive rows) but their cell history is read as c_prev only while active — nothing to clear
+            continue;
+        }
         for (int s = 0; s < S; ++s) {
             if (s > 0)
                 for (int d = 0; d < 2; ++d) {
@@ -360,6 +369,10 @@ int run_encoders_train(Ctx& c, const StairTrain& tr) {
                                              c.T, h, s, c.st));
         }
     }
+    if (fused)
+        return launch_lstm_fused(c.at<void>(c.plan.xv), c.buf.vid, c.T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R),
+                                 c.at<void>(c.plan.xq), c.buf.tokfeat, c.buf.qfeat, bt.q_off, bt.L_max, c.W(STAIR_W_TENC_WHHI_F),
+                                 c.W(STAIR_W_TENC_WHHI_R), c.at<float>(c.plan.c), B, h, 1, 1, err_flag_ptr(), c.st, &hist);
     return STAIR_OK;
 }
 

@@ -31,6 +31,9 @@ struct LstmSeq {
     const int* q_off;       // text: [B+1] token offsets (ragged) ; video: null
     int steps;              // video: T ; text: L_max
     int B, h;
+    // training (HIST): per-step history for BPTT in the layout of executor_bwd.cu's saved_layout — gates [S][2][B][4h] (post-activation
+    // i,f,g,o), cell state [S][2][B][h] (also the running c: no private scratch), h as bf16 [2][S+1][B][h] (row block s+1 = h after step s)
+    float* gates_h; float* c_h; bf16* hs_h; long long hs_dir;
 };
 
 struct LstmFusedParams {
@@ -72,7 +75,7 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
 }
 
 // CG = epilogue warps per TMEM lane quarter (each takes 64 / CG of a chunk's hidden units); threads = 128 + 128 * CG
-template <int CG>
+template <int CG, bool HIST>
 __global__ void __launch_bounds__(128 + 128 * CG, 1)
 lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, const LstmFusedParams p) {
@@ -204,6 +207,13 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
         // cell state scratch, private to this CTA, laid out [unit/4][row][4] so that a warp's float4 accesses are contiguous
         const int nblk = (sq.B + LF_ROWS - 1) / LF_ROWS;
         float* cblk = sq.c + (static_cast<long long>(dir) * nblk + blockIdx.x) * (static_cast<long long>(h) * LF_ROWS) + row * 4;
+        // HIST: the cell state of step s lives in the history (row-major [B][h]); q-th float4 of the 8 units starting at `unit`
+        const long long hist_row = (static_cast<long long>(dir) * sq.B + grow) * h;        // + step * 2 * B * h
+        const long long hist_step = 2LL * sq.B * h;
+        auto c_ptr = [&](int step, int unit, int q) -> float* {
+            if (HIST) return sq.c_h + step * hist_step + hist_row + unit + 4 * q;
+            return cblk + (unit / 4 + q) * (LF_ROWS * 4);
+        };
         const uint32_t sH0 = smem_u32(sH);
         const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
         const uint32_t sw = static_cast<uint32_t>(row & 7);
@@ -230,7 +240,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                     }
                     if (s > 0) {
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(cblk + ((c * 64 + halfsel * (SBN * 8)) / 4 + q) * (LF_ROWS * 4));
+                        for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(c_ptr(s - 1, c * 64 + halfsel * (SBN * 8), q));
                     }
                 }
                 if (s > 0) {
@@ -255,7 +265,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                         const float cprev[8] = {cnext[0].x, cnext[0].y, cnext[0].z, cnext[0].w, cnext[1].x, cnext[1].y, cnext[1].z, cnext[1].w};
                         if (s > 0 && sb < SBN - 1) {
 #pragma unroll
-                            for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(cblk + ((u0 + 8) / 4 + q) * (LF_ROWS * 4));
+                            for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(c_ptr(s - 1, u0 + 8, q));
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -265,16 +275,29 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                                 pg += __uint_as_float(gg[j]); po += __uint_as_float(go[j]);
                                 cp = cprev[j];
                             }
-                            const float cc = fast_sigmoid(pf) * cp + fast_sigmoid(pi) * fast_tanh(pg);
+                            const float ig = fast_sigmoid(pi), fgt = fast_sigmoid(pf), gg2 = fast_tanh(pg), og = fast_sigmoid(po);
+                            const float cc = fgt * cp + ig * gg2;
                             cn[j] = cc;
-                            hn[j] = fast_sigmoid(po) * fast_tanh(cc);
+                            hn[j] = og * fast_tanh(cc);
+                            if (HIST) { fi[j] = ig; ff[j] = fgt; fg[j] = gg2; fo[j] = og; }
                         }
 #pragma unroll
                         for (int q = 0; q < 2; ++q)
-                            *reinterpret_cast<float4*>(cblk + (u0 / 4 + q) * (LF_ROWS * 4)) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
+                            *reinterpret_cast<float4*>(c_ptr(s, u0, q)) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
+                        if (HIST) {
+                            float* gh = sq.gates_h + (static_cast<long long>(s) * 2 * sq.B + static_cast<long long>(dir) * sq.B + grow) * 4 * h + u0;
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                *reinterpret_cast<float4*>(gh + 4 * q) = make_float4(fi[4 * q], fi[4 * q + 1], fi[4 * q + 2], fi[4 * q + 3]);
+                                *reinterpret_cast<float4*>(gh + h + 4 * q) = make_float4(ff[4 * q], ff[4 * q + 1], ff[4 * q + 2], ff[4 * q + 3]);
+                                *reinterpret_cast<float4*>(gh + 2 * h + 4 * q) = make_float4(fg[4 * q], fg[4 * q + 1], fg[4 * q + 2], fg[4 * q + 3]);
+                                *reinterpret_cast<float4*>(gh + 3 * h + 4 * q) = make_float4(fo[4 * q], fo[4 * q + 1], fo[4 * q + 2], fo[4 * q + 3]);
+                            }
+                        }
                         uint4 o0;
                         o0.x = pack_bf16(hn[0], hn[1]); o0.y = pack_bf16(hn[2], hn[3]); o0.z = pack_bf16(hn[4], hn[5]); o0.w = pack_bf16(hn[6], hn[7]);
                         *reinterpret_cast<uint4*>(orow + u0) = o0;
+                        if (HIST) *reinterpret_cast<uint4*>(sq.hs_h + static_cast<long long>(dir) * sq.hs_dir + (static_cast<long long>(s + 1) * sq.B + grow) * h + u0) = o0;
                         if (last) *reinterpret_cast<uint4*>(sq.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0) = o0;
                         st_shared_v4(h_dst + a0, o0.x, o0.y, o0.z, o0.w);
                     } else {
@@ -310,7 +333,8 @@ bool lstm_fused_ok(int precision, int h) { return precision == STAIR_BF16 && h >
 // seq 0 = video (T steps), seq 1 = text (ragged, L_max steps); either may be disabled with steps = 0.
 int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh_v_f, const void* whh_v_r,
                       const void* xproj_t, void* tokfeat, void* qfeat, const int* q_off, int L_max, const void* whh_t_f,
-                      const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st) {
+                      const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st,
+                      const LstmHist* hist) {
     if (B <= 0 || (!run_video && !run_text)) return STAIR_OK;
     LstmFusedParams p;
     p.err_flag = err_flag;
@@ -319,6 +343,8 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
     v.final_h = nullptr; v.q_off = nullptr; v.steps = T; v.B = B; v.h = h;
     LstmSeq t; t.xproj = reinterpret_cast<const bf16*>(xproj_t); t.c = c_scratch + 2LL * ((B + LF_ROWS - 1) / LF_ROWS) * LF_ROWS * h; t.out = reinterpret_cast<bf16*>(tokfeat);
     t.final_h = reinterpret_cast<bf16*>(qfeat); t.q_off = q_off; t.steps = L_max; t.B = B; t.h = h;
+    v.gates_h = hist ? hist->gates[0] : nullptr; v.c_h = hist ? hist->c[0] : nullptr; v.hs_h = hist ? hist->hs[0] : nullptr; v.hs_dir = hist ? hist->hs_dir[0] : 0;
+    t.gates_h = hist ? hist->gates[1] : nullptr; t.c_h = hist ? hist->c[1] : nullptr; t.hs_h = hist ? hist->hs[1] : nullptr; t.hs_dir = hist ? hist->hs_dir[1] : 0;
     const void* w[4];
     int nseq = 0;
     if (run_video) { p.seq[nseq] = v; w[2 * nseq] = whh_v_f; w[2 * nseq + 1] = whh_v_r; ++nseq; }
@@ -327,17 +353,19 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
     CUtensorMap tm[4];
     for (int i = 0; i < 4; ++i) STAIR_TRY(make_tmap_bf16_2d(&tm[i], w[i], h, 4ULL * h, h, 64, 256));
     const int smem = 2 * (h / 64) * LF_KB_BYTES + LF_STAGES * LF_W_STAGE_BYTES + 256 + 1024;
-    static int configured[2] = {0, 0};
-    const int vi = g_lstm_cg == 4 ? 1 : 0;
+    static int configured[3] = {0, 0, 0};
+    const int vi = hist ? 2 : (g_lstm_cg == 4 ? 1 : 0);
     if (configured[vi] < smem) {
-        const cudaError_t e = vi ? cudaFuncSetAttribute(lstm_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                                : cudaFuncSetAttribute(lstm_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const cudaError_t e = vi == 2 ? cudaFuncSetAttribute(lstm_fused_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                            : vi == 1 ? cudaFuncSetAttribute(lstm_fused_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                      : cudaFuncSetAttribute(lstm_fused_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return STAIR_ERR_CUDA;
         configured[vi] = smem;
     }
     dim3 grid((B + LF_ROWS - 1) / LF_ROWS, 2, nseq);
-    if (vi) lstm_fused_kernel<4><<<grid, 128 + 128 * 4, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
-    else lstm_fused_kernel<2><<<grid, 128 + 128 * 2, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
+    if (vi == 2) lstm_fused_kernel<2, true><<<grid, 128 + 128 * 2, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
+    else if (vi == 1) lstm_fused_kernel<4, false><<<grid, 128 + 128 * 4, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
+    else lstm_fused_kernel<2, false><<<grid, 128 + 128 * 2, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }

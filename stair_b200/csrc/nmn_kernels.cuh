@@ -82,9 +82,13 @@ int launch_lstm_cell_text(int xdt, const void* xproj, const float* g, float* c, 
 
 // fused persistent recurrence for both encoders and both directions (lstm_fused.cu; bf16 path, h in {64,128,192,256})
 bool lstm_fused_ok(int precision, int h);
+// training: BPTT history written by the fused kernel, index 0 = video encoder, 1 = text encoder (layouts: executor_bwd.cu saved_layout).
+// hs must be zero-filled by the caller (rows of finished questions are not written); c_scratch is unused with a history.
+struct LstmHist { float* gates[2]; float* c[2]; bf16* hs[2]; long long hs_dir[2]; };
 int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh_v_f, const void* whh_v_r,
                       const void* xproj_t, void* tokfeat, void* qfeat, const int* q_off, int L_max, const void* whh_t_f,
-                      const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st);
+                      const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st,
+                      const LstmHist* hist = nullptr);
 
 // ---- layout grouping (layout_group.cu) ----------------------------------------------------------------------------
 int launch_group_layouts(const StairBatch& b, int32_t* itab, int32_t* status, cudaStream_t st);

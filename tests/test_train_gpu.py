@@ -285,7 +285,8 @@ def test_fused_adam_matches_torch_and_refreshes_the_packed_weights(precision):
     sched = torch.optim.lr_scheduler.LambdaLR(oa, lambda it: 1.0 - 0.1 * it)         # param_groups['lr'] is honoured
     sched_b = torch.optim.lr_scheduler.LambdaLR(ob, lambda it: 1.0 - 0.1 * it)
     sa, sb = NMNTrainStep(a), NMNTrainStep(b)
-    tol = dict(rtol=1e-5, atol=1e-7) if precision == 'fp32' else dict(rtol=2e-2, atol=2e-4)
+    # lr is 10x the reference's: Adam's m / sqrt(v) amplifies the atomic-ordering noise of near-zero gradients to ~1e-3 * lr
+    tol = dict(rtol=1e-5, atol=1e-5) if precision == 'fp32' else dict(rtol=2e-2, atol=2e-4)
     for window in (qs, qs2, qs):                          # the middle window leaves most modules untouched (skipped by Adam)
         la = sa(window)['loss']; oa.step(); oa.zero_grad(); sched.step()
         lb = sb(window)['loss']; ob.step(); ob.zero_grad(); sched_b.step()
