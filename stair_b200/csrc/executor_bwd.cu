@@ -47,13 +47,14 @@ struct SavedLayout { EncSaved enc[2]; long long total; };
 
 SavedLayout saved_layout(const StairModel& m, const StairBatch& b) {
     const long long np = m.precision == STAIR_F32 ? 3 : 1, B = b.B, h = m.H / 2;
+    const long long Bp = align_up(B, 128);       // the blocked history of the fused recurrence pads the batch to whole 128-row CTAs
     SavedLayout L;
     long long o = 0;
     for (int e = 0; e < 2; ++e) {
         const long long S = e == 0 ? b.T : b.L_max;
         L.enc[e].S = static_cast<int>(S);
-        L.enc[e].gates = o; o = align_up(o + S * 2 * B * 4 * h * 4, 1024);
-        L.enc[e].c = o; o = align_up(o + S * 2 * B * h * 4, 1024);
+        L.enc[e].gates = o; o = align_up(o + S * 2 * Bp * 4 * h * 4, 1024);
+        L.enc[e].c = o; o = align_up(o + S * 2 * Bp * h * 4, 1024);
         L.enc[e].hs = o; o = align_up(o + np * 2 * (S + 1) * B * h * 2, 1024);
     }
     L.total = o;
@@ -317,6 +318,11 @@ EncIO enc_io(Ctx& c, int e) {
     return io;
 }
 
+// true when the training forward runs the fused recurrence (history of gates / cell state in the blocked layout)
+bool fused_history(const Ctx& c) {
+    return lstm_fused_ok(c.m.precision, c.h) && g_lstm_impl == 0 && c.W(STAIR_W_VENC_WHHI_F) && c.W(STAIR_W_TENC_WHHI_F);
+}
+
 int run_encoders_train(Ctx& c, const StairTrain& tr) {
     const StairModel& m = c.m; const StairBatch& bt = c.b;
     const int B = bt.B, H = c.H, h = c.h;
@@ -325,7 +331,7 @@ int run_encoders_train(Ctx& c, const StairTrain& tr) {
     char* sv = reinterpret_cast<char*>(tr.saved);
     float* g = c.at<float>(c.plan.g);
     // bf16 path: both recurrences run in the persistent fused kernel (csrc/lstm_fused.cu), which writes the BPTT history itself
-    const bool fused = lstm_fused_ok(m.precision, h) && g_lstm_impl == 0 && c.W(STAIR_W_VENC_WHHI_F) && c.W(STAIR_W_TENC_WHHI_F);
+    const bool fused = fused_history(c);
     LstmHist hist;
     for (int e = 0; e < 2; ++e) {
         const EncIO io = enc_io(c, e);
@@ -383,6 +389,7 @@ int encoders_bwd(BCtx& b) {
     const int B = bt.B, H = c.H, h = c.h;
     const SavedLayout SL = saved_layout(m, bt);
     char* sv = reinterpret_cast<char*>(tr.saved);
+    const bool blocked = fused_history(c);
     for (int e = 1; e >= 0; --e) {
         const EncIO io = enc_io(c, e);
         const int S = io.S;
@@ -400,9 +407,13 @@ int encoders_bwd(BCtx& b) {
         const float* dout = e == 0 ? tr.dvid : tr.dtokfeat;
         for (int s = S - 1; s >= 0; --s) {
             const float* c_prev = s > 0 ? cs + static_cast<long long>(s - 1) * 2 * B * h : cs;
+            if (blocked)
+                RUN(launch_lstm_cell_bwd(gates, nullptr, cs, dout, dh_rec, e == 1 ? tr.dqfeat : nullptr, dc, dg_hist + static_cast<long long>(s) * B * 4 * h,
+                                         dg_dir, dg_planes, 2LL * B * 4 * h, c.np, dxproj, io.q_off, B, c.T, h, s, S - 1, 1, c.st));
+            else
             RUN(launch_lstm_cell_bwd(gates + static_cast<long long>(s) * 2 * B * 4 * h, c_prev, cs + static_cast<long long>(s) * 2 * B * h, dout, dh_rec,
                                      e == 1 ? tr.dqfeat : nullptr, dc, dg_hist + static_cast<long long>(s) * B * 4 * h, dg_dir, dg_planes,
-                                     2LL * B * 4 * h, c.np, dxproj, io.q_off, B, c.T, h, s, S - 1, c.st));
+                                     2LL * B * 4 * h, c.np, dxproj, io.q_off, B, c.T, h, s, S - 1, 0, c.st));
             if (s > 0)
                 for (int d = 0; d < 2; ++d) {
                     const int wid = d == 0 ? io.whh_f : io.whh_r;

@@ -31,8 +31,11 @@ struct LstmSeq {
     const int* q_off;       // text: [B+1] token offsets (ragged) ; video: null
     int steps;              // video: T ; text: L_max
     int B, h;
-    // training (HIST): per-step history for BPTT in the layout of executor_bwd.cu's saved_layout — gates [S][2][B][4h] (post-activation
-    // i,f,g,o), cell state [S][2][B][h] (also the running c: no private scratch), h as bf16 [2][S+1][B][h] (row block s+1 = h after step s)
+    // training (HIST): per-step history for BPTT.  Gates (post-activation i,f,g,o) and cell state are written in the BLOCKED layout of
+    // train_kernels.cuh (lstm_hist_gate_off / lstm_hist_c_off: [step][dir][32-row block][8-unit block][gate][row][8 units]) so that a
+    // warp's stores are contiguous (row-major history = 32 scattered 16-byte pieces per store instruction, measured 3x slower);
+    // the cell history is also the running c (no private scratch).  h goes to bf16 [2][S+1][B][h] row-major (row block s+1 = h after
+    // step s): it is the A operand of the dW_hh GEMM.
     float* gates_h; float* c_h; bf16* hs_h; long long hs_dir;
 };
 
@@ -207,11 +210,12 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
         // cell state scratch, private to this CTA, laid out [unit/4][row][4] so that a warp's float4 accesses are contiguous
         const int nblk = (sq.B + LF_ROWS - 1) / LF_ROWS;
         float* cblk = sq.c + (static_cast<long long>(dir) * nblk + blockIdx.x) * (static_cast<long long>(h) * LF_ROWS) + row * 4;
-        // HIST: the cell state of step s lives in the history (row-major [B][h]); q-th float4 of the 8 units starting at `unit`
-        const long long hist_row = (static_cast<long long>(dir) * sq.B + grow) * h;        // + step * 2 * B * h
-        const long long hist_step = 2LL * sq.B * h;
+        // HIST: the cell state of step s lives in the blocked history; q-th float4 of the 8 units starting at `unit`
+        const long long RB = (sq.B + 127) / 128 * 4;                                      // 32-row blocks per (step, direction)
+        const long long hist_rb = (static_cast<long long>(dir) * RB + (grow >> 5)) * (h >> 3);      // + step * 2 * RB * (h/8); then + unit/8
+        const long long hist_step = 2 * RB * (h >> 3);
         auto c_ptr = [&](int step, int unit, int q) -> float* {
-            if (HIST) return sq.c_h + step * hist_step + hist_row + unit + 4 * q;
+            if (HIST) return sq.c_h + (step * hist_step + hist_rb + (unit >> 3)) * 256 + lane * 8 + 4 * q;
             return cblk + (unit / 4 + q) * (LF_ROWS * 4);
         };
         const uint32_t sH0 = smem_u32(sH);
@@ -285,13 +289,13 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                         for (int q = 0; q < 2; ++q)
                             *reinterpret_cast<float4*>(c_ptr(s, u0, q)) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
                         if (HIST) {
-                            float* gh = sq.gates_h + (static_cast<long long>(s) * 2 * sq.B + static_cast<long long>(dir) * sq.B + grow) * 4 * h + u0;
+                            float* gh = sq.gates_h + (s * hist_step + hist_rb + (u0 >> 3)) * 1024 + lane * 8;      // [gate][row][8 units]
 #pragma unroll
                             for (int q = 0; q < 2; ++q) {
                                 *reinterpret_cast<float4*>(gh + 4 * q) = make_float4(fi[4 * q], fi[4 * q + 1], fi[4 * q + 2], fi[4 * q + 3]);
-                                *reinterpret_cast<float4*>(gh + h + 4 * q) = make_float4(ff[4 * q], ff[4 * q + 1], ff[4 * q + 2], ff[4 * q + 3]);
-                                *reinterpret_cast<float4*>(gh + 2 * h + 4 * q) = make_float4(fg[4 * q], fg[4 * q + 1], fg[4 * q + 2], fg[4 * q + 3]);
-                                *reinterpret_cast<float4*>(gh + 3 * h + 4 * q) = make_float4(fo[4 * q], fo[4 * q + 1], fo[4 * q + 2], fo[4 * q + 3]);
+                                *reinterpret_cast<float4*>(gh + 256 + 4 * q) = make_float4(ff[4 * q], ff[4 * q + 1], ff[4 * q + 2], ff[4 * q + 3]);
+                                *reinterpret_cast<float4*>(gh + 512 + 4 * q) = make_float4(fg[4 * q], fg[4 * q + 1], fg[4 * q + 2], fg[4 * q + 3]);
+                                *reinterpret_cast<float4*>(gh + 768 + 4 * q) = make_float4(fo[4 * q], fo[4 * q + 1], fo[4 * q + 2], fo[4 * q + 3]);
                             }
                         }
                         uint4 o0;

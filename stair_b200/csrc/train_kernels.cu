@@ -1058,7 +1058,7 @@ int launch_lstm_cell_train(int xdt, const void* xproj, const float* g, const flo
 __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
                                      const float* __restrict__ dout, const float* __restrict__ dh_rec, const float* __restrict__ dqfeat,
                                      float* __restrict__ dc, float* __restrict__ dgates, long long dg_dir, bf16* __restrict__ dg_planes, long long dg_plane, int nplanes,
-                                     float* __restrict__ dxproj, const int* __restrict__ q_off, int B, int T, int h, int step, int last_step) {
+                                     float* __restrict__ dxproj, const int* __restrict__ q_off, int B, int T, int h, int step, int last_step, int blocked) {
     const long long total = 2LL * B * h;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int d = static_cast<int>(i / (static_cast<long long>(B) * h));
@@ -1078,10 +1078,19 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const floa
             float dh = dout[row * 2 * h + d * h + j];
             if (step < last_step) dh += dh_rec[si];
             if (dqfeat && final_step) dh += dqfeat[static_cast<long long>(b) * 2 * h + d * h + j];
-            const float ig = gates[gi], fg = gates[gi + h], gg = gates[gi + 2 * h], og = gates[gi + 3 * h];
-            const float tc = tanhf(c_cur[si]);
+            float ig, fg, gg, og, ccur, cp = 0.f;
+            if (blocked) {
+                const long long go = lstm_hist_gate_off(step, d, b, 0, j, B, h);
+                ig = gates[go]; fg = gates[go + 256]; gg = gates[go + 512]; og = gates[go + 768];
+                ccur = c_cur[lstm_hist_c_off(step, d, b, j, B, h)];
+                if (step > 0) cp = c_cur[lstm_hist_c_off(step - 1, d, b, j, B, h)];
+            } else {
+                ig = gates[gi]; fg = gates[gi + h]; gg = gates[gi + 2 * h]; og = gates[gi + 3 * h];
+                ccur = c_cur[si];
+                if (step > 0) cp = c_prev[si];
+            }
+            const float tc = tanhf(ccur);
             const float dct = (step < last_step ? dc[si] : 0.f) + dh * og * (1.f - tc * tc);
-            const float cp = step > 0 ? c_prev[si] : 0.f;
             dpi = dct * gg * ig * (1.f - ig);
             dpf = dct * cp * fg * (1.f - fg);
             dpg = dct * ig * (1.f - gg * gg);
@@ -1103,10 +1112,11 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const floa
 
 int launch_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_cur, const float* dout, const float* dh_rec, const float* dqfeat,
                          float* dc, float* dgates, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, const int* q_off,
-                         int B, int T, int h, int step, int last_step, cudaStream_t st) {
+                         int B, int T, int h, int step, int last_step, int blocked, cudaStream_t st) {
     if (B <= 0) return STAIR_OK;
+    if (blocked && (h % 8)) return STAIR_ERR_ARG;
     lstm_cell_bwd_kernel<<<nblocks(2LL * B * h, 256), 256, 0, st>>>(gates, c_prev, c_cur, dout, dh_rec, dqfeat, dc, dgates, dg_dir, dg_planes, dg_plane, nplanes,
-                                                                   dxproj, q_off, B, T, h, step, last_step);
+                                                                   dxproj, q_off, B, T, h, step, last_step, blocked);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }

@@ -55,6 +55,17 @@ int launch_loss_con(int dt, const void* vec, float* dvec, const int* out_slot, c
                     const float* cls_rep, int n_cls, float* loss, int n, int H, cudaStream_t st);
 int launch_loss_dec(const float* logits, const int* answer, float w, float* dlogits, float* loss, int B, int A, cudaStream_t st);
 
+// Blocked BPTT history written by the fused recurrence kernel (lstm_fused.cu, HIST): 32-row x 8-unit blocks, 32 contiguous bytes per
+// (row, gate) — the writer's warp stores 1 KiB-contiguous pieces, the row-major reader below reads whole 32-byte sectors.
+// RB = 32-row blocks per (step, direction) = ceil(B / 128) * 4.
+__host__ __device__ static inline long long lstm_hist_rb(int B) { return (static_cast<long long>(B) + 127) / 128 * 4; }
+__host__ __device__ static inline long long lstm_hist_gate_off(int step, int d, int b, int gate, int u, int B, int h) {
+    return ((((static_cast<long long>(step) * 2 + d) * lstm_hist_rb(B) + (b >> 5)) * (h >> 3) + (u >> 3)) * 4 + gate) * 256 + (b & 31) * 8 + (u & 7);
+}
+__host__ __device__ static inline long long lstm_hist_c_off(int step, int d, int b, int u, int B, int h) {
+    return (((static_cast<long long>(step) * 2 + d) * lstm_hist_rb(B) + (b >> 5)) * (h >> 3) + (u >> 3)) * 256 + (b & 31) * 8 + (u & 7);
+}
+
 // ---- LSTM with history (training forward) and its backward ---------------------------------------------------------------------------
 // gates_out [2][B][4h] (post-activation i,f,g,o), c_prev/c_out [2][B][h]; hstate planes [np][...] with plane stride hs_plane;
 // inactive (finished) questions copy their state forward.  q_off == null: video (row b*T+t); else ragged text.
@@ -63,9 +74,11 @@ int launch_lstm_cell_train(int xdt, const void* xproj, const float* g, const flo
                            int B, int T, int h, int step, cudaStream_t st);
 // one BPTT step: dh = dout(row) + dh_rec (+ dqfeat at a question's last step); writes the gate pre-activation gradients as
 // fp32 [2][B][4h], as bf16 planes (A operand of the recurrent GEMM) and into the dxproj row; updates dc in place.
+// blocked = 0: gates / c_prev / c_cur point at step `step`'s row-major slices ([2][B][4h], [2][B][h]; c_prev at step-1's);
+// blocked = 1: gates / c_cur are the BASE of the blocked history (lstm_hist_*_off), c_prev is ignored.
 int launch_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_cur, const float* dout, const float* dh_rec, const float* dqfeat,
                          float* dc, float* dgates, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, const int* q_off,
-                         int B, int T, int h, int step, int last_step, cudaStream_t st);
+                         int B, int T, int h, int step, int last_step, int blocked, cudaStream_t st);
 
 int launch_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, float b1, float b2, float eps, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1, float bc2, cudaStream_t st);

@@ -171,7 +171,7 @@ def test_adam_matches_torch():
         sb(window); ob.step(); ob.zero_grad()
     torch.cuda.synchronize()
     for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
-        torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-7, msg=lambda m: '%s: %s' % (k, m))
+        torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-6, msg=lambda m: "%s: %s" % (k, m))   # atomics: summation order varies
     # and training moved the parameters
     assert float((a.submodules['decoder'][0].weight - before).abs().max()) > 1e-4
 
