@@ -215,6 +215,12 @@ int stair_gemm_bf16(const void* A, long long lda, int a_plane_rows, const void* 
 int stair_gemm_bf16_gather(const void* arena, long long ld, long long arena_slots, const int32_t* a_slots, int slot_rows,
                            const void* W, long long ldw, const float* bias, const float* row_scale, void* C, long long ldc,
                            int out_dtype, int M, int N, int K, int act, void* stream);
+/* Weight-gradient contraction C[M,N] (+)= A^T . W over K rows: A bf16 [nplanes][a_plane_rows, lda] with element (k, m) at k*lda + m,
+ * W bf16 [nplanes][w_plane_rows, ldw] with element (k, n); operands are consumed in place as MN-major tensor-core tiles
+ * (dW = dZ^T . X of every nn.Linear backward, train_module.py:408).  C fp32; accumulate = 1 adds into C (split-K with atomics). */
+int stair_gemm_bf16_tn(const void* A, long long lda, int a_plane_rows, const void* W, long long ldw, int w_plane_rows, int nplanes,
+                       float* C, long long ldc, int M, int N, int K, int accumulate, void* stream);
+int stair_set_dw_impl(int impl);        /* weight gradients: 0 = MN-major operands in place (product); 1 = transposed copies + K-major GEMM */
 int stair_set_gemm_impl(int impl);      /* 0 = tcgen05 (product); 1 = SIMT debug kernel used to cross-check in tests */
 int stair_get_gemm_impl(void);
 int stair_set_gemm_split_k(int on);      /* 1 (default) = split-K with atomic accumulation for accumulating GEMMs with few output tiles */

@@ -15,6 +15,8 @@ namespace {
 
 using namespace ex;
 
+int g_dw_impl = 0;      // 0 = MN-major weight-gradient GEMM (product); 1 = transposed copies + K-major GEMM (comparison)
+
 struct Bump {
     char* base = nullptr;
     long long cap = 0, off = 0, peak = 0;
@@ -90,7 +92,13 @@ int linear_bwd(BCtx& b, const float* dY, long long ld_dy, const void* Y, long lo
     bf16* dZs = rs ? b.ws.take<bf16>(c.np * static_cast<long long>(M) * n_ld) : dZ;
     RUN(launch_dz_prep(c.adt, dY, ld_dy, Y, ld_y, rs, dZ, dZs, n_ld, M, c.np, G(b, bid), M, N, Y ? yscale : 1.0f, c.st));
     float* gW = G(b, wid);
-    if (gW) {
+    if (gW && g_dw_impl == 0) {
+        // dW[N,K] += dZs^T . X over the M rows: both operands in place as MN-major tiles (no transposed copies)
+        GemmArgs a;
+        a.A = dZs; a.lda = n_ld; a.a_plane_rows = M; a.W = Xp; a.ldw = k_ld; a.w_plane_rows = static_cast<int>(x_plane_rows); a.nplanes = c.np;
+        a.C = gW; a.ldc = K; a.out_dtype = STAIR_F32; a.M = N; a.N = K; a.K = M; a.accumulate = 1; a.mn_major = 1;
+        RUN(launch_gemm(a, c.st));
+    } else if (gW) {
         bf16* dZt = b.ws.take<bf16>(c.np * static_cast<long long>(N) * m_ld);
         bf16* Xt = b.ws.take<bf16>(c.np * static_cast<long long>(K) * m_ld);
         RUN(launch_transpose_planes(dZs, n_ld, M, dZt, m_ld, N, c.np, M, N, c.st));
@@ -594,6 +602,8 @@ extern "C" int stair_adam_step(float* param, const float* grad, float* exp_avg, 
     const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
     return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2, reinterpret_cast<cudaStream_t>(stream));
 }
+
+extern "C" int stair_set_dw_impl(int impl) { g_dw_impl = impl ? 1 : 0; return STAIR_OK; }
 
 extern "C" int stair_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, float beta1, float beta2, float eps, void* stream) {
     if (!segs && n_segs > 0) return STAIR_ERR_ARG;

@@ -43,6 +43,7 @@ struct GemmParams {
     int* err_flag;
     unsigned long long* dbg;   // debug timeline of block 0 (globaltimer ns), null in production
     DropSpec drop;             // dropout after the activation (thresh 0 = off)
+    int mn_major;              // operands stored [k][m] / [k][n] (C = A^T . W): MN-major UMMA tiles, 3-D tensor maps {mn, k, plane}
 };
 
 // plane pairs (a,b) of the 6-term bf16x3 product, smallest contributions first
@@ -237,8 +238,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (lane == 0) {
                         mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 101);
                         mbar_arrive_expect_tx(&full_bar[stage], a_bytes + B_STAGE_BYTES);
+                        if (p.mn_major) {
+                            // [64 k-rows][64 mn] boxes (128-byte rows): one box per 64 output rows / columns of the tile; rows
+                            // past K and columns past M / N are zero-filled by TMA (per plane: the plane is the third coordinate)
+                            const int pa = p.nseg > 1 ? c_seg_a[seg] : 0, pb = p.nseg > 1 ? c_seg_b[seg] : 0;
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_3d(sB + stage * B_STAGE_BYTES + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * BK, pb);
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j)
+                                tma_load_3d(sA + stage * A_STAGE_BYTES + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, kb * BK, pa);
+                        } else {
                         tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, b_row);
                         if (!p.a_slots) tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, a_row);
+                        }
                     }
                     if (p.a_slots) {
                         __syncwarp();
@@ -265,12 +278,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(&full_bar[stage], phase, p.err_flag, 103);
                     tcgen05_fence_after();
                     if (it == 0 && item == blockIdx.x) dbg_stamp(p, 2);
+                    if (p.mn_major) {
+                        const uint64_t adesc = make_umma_desc_mnmajor_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
+                        const uint64_t bdesc = make_umma_desc_mnmajor_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)      // UMMA_K = 16 = two 8-row groups of 1024 B -> +128 in the (addr>>4) field
+                            umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, IDESC | UMMA_IDESC_A_MN_MAJOR | UMMA_IDESC_B_MN_MAJOR,
+                                      (it | k) != 0 ? 1u : 0u);
+                    } else {
                     const uint64_t adesc = make_umma_desc_kmajor_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
                     const uint64_t bdesc = make_umma_desc_kmajor_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // +32 B per UMMA_K=16 bf16 inside the swizzle atom -> +2 in the (addr>>4) field
                         umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+                    }
                     }
                     umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -373,8 +395,13 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, long long lda, cons
         const long long b_off = p.nseg > 1 ? static_cast<long long>(c_seg_b[seg]) * p.w_plane_rows : 0;
         for (int k0 = 0; k0 < p.K; k0 += 16) {
             const int ar = blockIdx.y * 16 + ty, br = blockIdx.x * 16 + ty;
+            if (p.mn_major) {
+                sa[ty][tx] = (ar < p.M && k0 + tx < p.K) ? __bfloat162float(A[(a_off + k0 + tx) * lda + ar]) : 0.f;
+                sb[ty][tx] = (br < p.N && k0 + tx < p.K) ? __bfloat162float(W[(b_off + k0 + tx) * ldw + br]) : 0.f;
+            } else {
             sa[ty][tx] = (ar < p.M && k0 + tx < p.K) ? __bfloat162float(A[(a_off + ar) * lda + k0 + tx]) : 0.f;
             sb[ty][tx] = (br < p.N && k0 + tx < p.K) ? __bfloat162float(W[(b_off + br) * ldw + k0 + tx]) : 0.f;
+            }
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sb[tx][k];
@@ -403,6 +430,20 @@ static int make_tmap_bf16_slots(CUtensorMap* tm, const void* base, uint64_t cols
     cuuint64_t gdim[3] = {cols, slot_rows, slots};
     cuuint64_t gstride[2] = {row_pitch_elems * 2, row_pitch_elems * 2 * slot_rows};
     cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(slot_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? STAIR_OK : STAIR_ERR_ARG;
+}
+
+// MN-major operand [planes][plane_rows (k), ld] with `mn` valid columns and `k` valid rows per plane; box = 64 k-rows x 64 columns
+static int make_tmap_bf16_mn(CUtensorMap* tm, const void* base, uint64_t mn, uint64_t k, uint64_t planes, uint64_t plane_rows, uint64_t ld) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return STAIR_ERR_CUDA;
+    cuuint64_t gdim[3] = {mn, k, planes};
+    cuuint64_t gstride[2] = {ld * 2, ld * 2 * plane_rows};
+    cuuint32_t box[3] = {64, 64, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -477,6 +518,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     if (a.accumulate && a.out_dtype != STAIR_F32) return STAIR_ERR_ARG;
     const bool gather = a.a_slots != nullptr;
     if (gather && (a.nplanes != 1 || !gemm_gather_ok(a.slot_rows) || a.M % a.slot_rows)) return STAIR_ERR_ARG;
+    if (a.mn_major && (gather || (a.nplanes > 1 && (a.a_plane_rows < a.K || a.w_plane_rows < a.K)))) return STAIR_ERR_ARG;
     GemmParams p;
     p.M = a.M; p.N = a.N; p.K = a.K; p.num_kb = ceil_div(a.K, BK); p.nseg = a.nplanes == 3 ? 6 : 1;
     p.ksplit = 1; p.kb_per_split = p.num_kb;
@@ -484,6 +526,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     p.bias = a.bias; p.row_scale = a.row_scale; p.C = a.C; p.ldc = a.ldc; p.out_dtype = a.out_dtype; p.act = a.act;
     p.accumulate = a.accumulate;
     p.drop = a.drop;
+    p.mn_major = a.mn_major;
     const int esz = a.out_dtype == STAIR_BF16 ? 2 : 4;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.ldc * esz) % 16 == 0) ? 1 : 0;
     p.tma_store = (!a.accumulate && p.vec_ok && g_epilogue_impl == 0) ? 1 : 0;
@@ -507,10 +550,17 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     const int tiles128 = ceil_div(a.M, BM) * ceil_div(a.N, 128);
     const int bn = a.N <= 64 ? 64 : ((a.N % 256 == 0 && tiles128 >= 2 * g_num_sms) ? 256 : 128);
     CUtensorMap ta, tb;
-    int rc = gather ? make_tmap_bf16_slots(&ta, a.A, a.K, a.slot_rows, a.arena_slots, a.lda)
+    int rc;
+    if (a.mn_major) {
+        rc = make_tmap_bf16_mn(&ta, a.A, a.M, a.K, a.nplanes, a.nplanes > 1 ? a.a_plane_rows : a.K, a.lda);
+        if (rc) return rc;
+        rc = make_tmap_bf16_mn(&tb, a.W, a.N, a.K, a.nplanes, a.nplanes > 1 ? a.w_plane_rows : a.K, a.ldw);
+    } else {
+        rc = gather ? make_tmap_bf16_slots(&ta, a.A, a.K, a.slot_rows, a.arena_slots, a.lda)
                     : make_tmap_bf16_2d(&ta, a.A, a.K, a_rows, a.lda, BK, BM);
-    if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tb, a.W, a.K, w_rows, a.ldw, BK, bn);
+        if (rc) return rc;
+        rc = make_tmap_bf16_2d(&tb, a.W, a.K, w_rows, a.ldw, BK, bn);
+    }
     if (rc) return rc;
     CUtensorMap tc = tb;
     if (p.tma_store) {
@@ -541,6 +591,16 @@ extern "C" int stair_gemm_bf16(const void* A, long long lda, int a_plane_rows, c
     a.A = A; a.lda = lda; a.a_plane_rows = a_plane_rows; a.W = W; a.ldw = ldw; a.w_plane_rows = w_plane_rows; a.nplanes = nplanes;
     a.bias = bias; a.row_scale = row_scale; a.C = C; a.ldc = ldc; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K;
     a.act = act; a.accumulate = accumulate;
+    return launch_gemm(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Weight-gradient contraction C[M,N] (+)= A^T . W with A = [nplanes][a_plane_rows, lda] (element (k, m)), W = [nplanes][w_plane_rows, ldw]
+// (element (k, n)): both operands are read in place as MN-major UMMA tiles (no transposed copies).  fp32 output.
+extern "C" int stair_gemm_bf16_tn(const void* A, long long lda, int a_plane_rows, const void* W, long long ldw, int w_plane_rows, int nplanes,
+                                  float* C, long long ldc, int M, int N, int K, int accumulate, void* stream) {
+    GemmArgs a;
+    a.A = A; a.lda = lda; a.a_plane_rows = a_plane_rows; a.W = W; a.ldw = ldw; a.w_plane_rows = w_plane_rows; a.nplanes = nplanes;
+    a.C = C; a.ldc = ldc; a.out_dtype = STAIR_F32; a.M = M; a.N = N; a.K = K; a.accumulate = accumulate; a.mn_major = 1;
     return launch_gemm(a, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -143,6 +143,10 @@ struct GemmArgs {
     int M = 0, N = 0, K = 0;
     int act = STAIR_ACT_NONE;
     int accumulate = 0;
+    // mn_major = 1: both operands are stored "transposed": A = [nplanes][a_plane_rows (>= K), lda] with element (k, m) at k*lda + m,
+    // W = [nplanes][w_plane_rows (>= K), ldw] with element (k, n) at k*ldw + n, i.e. C[M,N] = A^T . W — the weight-gradient
+    // contraction dW = dZ^T . X over the rows of a layer, read in place (MN-major UMMA operands, no transposed copies).
+    int mn_major = 0;
     DropSpec drop;                  // applied after the activation (training forward only)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);

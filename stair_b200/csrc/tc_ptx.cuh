@@ -96,6 +96,20 @@ __device__ __forceinline__ uint64_t make_umma_desc_kmajor_sw128(uint32_t smem_ad
     return d;
 }
 // Instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major, N>>3 @17, M>>4 @24.
+// MN-major operand tile (element (k, mn) with mn contiguous), SWIZZLE_128B: 64 (MN) x 8 (K) atoms = 8 rows of 128 bytes;
+// SBO = stride between 8-row groups along K (1024 B for a [64 k-rows][128 B] TMA box), LBO = stride between 64-element atoms
+// along MN (one whole box: 64 rows x 128 B = 8192 B).  One UMMA_K = 16 step = two 8-row groups = +2048 B.
+__device__ __forceinline__ uint64_t make_umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(8192 >> 4) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+constexpr uint32_t UMMA_IDESC_A_MN_MAJOR = 1u << 15, UMMA_IDESC_B_MN_MAJOR = 1u << 16;
+
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }

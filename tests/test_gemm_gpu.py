@@ -119,3 +119,60 @@ def test_gemm_slot_gather(T, H):
     torch.cuda.synchronize()
     ref = torch.relu((arena[idx.long()].reshape(n * T, H).float() @ W.float().t()) * rs[:, None] + bias)
     assert (out - ref).abs().max().item() < 2e-3
+
+
+TN_CASES = [
+    # M (out features), N (in features), K (rows), planes, accumulate
+    (128, 128, 64, 1, False),
+    (512, 512, 19648, 1, True),        # a module Linear's dW over 2456 x 8 frame rows (split-K)
+    (512, 1536, 4096, 1, True),
+    (172, 1024, 4096, 1, False),       # decoder head: M not a multiple of 64
+    (1024, 304, 777, 1, True),         # text W_ih: N = padded 300, K not a multiple of 64
+    (64, 192, 333, 3, True),           # strict fp32: three bf16 planes, plane stride > K
+    (2048, 4096, 8192, 1, False),
+]
+
+
+@pytest.mark.parametrize('impl', [0, 1], ids=['tc', 'simt'])
+@pytest.mark.parametrize('case', TN_CASES)
+def test_gemm_tn_matches_fp32_reference(case, impl):
+    """C = A^T . W with both operands read in place as MN-major tiles (the weight-gradient contraction, no transposed copies)."""
+    import ctypes
+    M, N, K, planes, acc = case
+    if impl == 1 and M * N * K > 3e9:
+        pytest.skip('SIMT debug kernel: small cases only')
+    g = torch.Generator(device='cuda').manual_seed(M + 3 * N + 7 * K)
+    lda, ldw = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    prow = K + 5                                        # plane stride in rows (> K: rows past K belong to nobody)
+    a32 = torch.randn(K, M, device='cuda', generator=g) * K ** -0.5
+    w32 = torch.randn(K, N, device='cuda', generator=g)
+
+    def pack(x, ld):
+        buf = torch.full((planes, prow, ld), 7.0, device='cuda', dtype=torch.bfloat16)      # poison outside the valid region
+        r = x.clone()
+        for p in range(planes):
+            h = r.bfloat16()
+            buf[p, :K, :x.shape[1]] = h
+            buf[p, :K, x.shape[1]:] = 0
+            r = r - h.float()
+        return buf
+
+    A, W = pack(a32, lda), pack(w32, ldw)
+    if planes == 1:
+        ref = A[0, :K, :M].float().t() @ W[0, :K, :N].float()
+    else:
+        ref = a32.double().t() @ w32.double()
+    C0 = torch.randn(M, N, device='cuda', generator=g)
+    C = C0.clone()
+    lib = L.lib()
+    lib.stair_set_gemm_impl(impl)
+    try:
+        rc = lib.stair_gemm_bf16_tn(L.ptr(A), ctypes.c_longlong(lda), L.i32(prow), L.ptr(W), ctypes.c_longlong(ldw), L.i32(prow), L.i32(planes),
+                                    L.ptr(C), ctypes.c_longlong(N), L.i32(M), L.i32(N), L.i32(K), L.i32(1 if acc else 0), L.stream_ptr())
+        torch.cuda.synchronize()
+    finally:
+        lib.stair_set_gemm_impl(0)
+    assert rc == 0 and lib.stair_gemm_error_flag() == 0
+    want = (ref.float() + C0) if acc else ref.float()
+    err = (C - want).abs().max().item()
+    assert err <= 2e-4 * max(want.abs().max().item(), 1.0), 'max err %g' % err
