@@ -211,6 +211,19 @@ int launch_rowscale_bwd(int xdt, float* G, const void* X, const int* slots, int 
     return STAIR_OK;
 }
 
+// 4 columns per thread: one 16-byte load and one vector reduction (red.global.add.v4.f32) instead of four scalar atomics
+__global__ void scatter_add_rows_v4_kernel(const float* __restrict__ src, const int* __restrict__ idx, int rps, int unit, float* __restrict__ dst,
+                                           long long rows, int H4) {
+    const long long total = rows * H4;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / H4;
+        const int c = static_cast<int>(i % H4);
+        const long long dr = static_cast<long long>(__ldg(idx + r / rps)) * unit + r % rps;
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(reinterpret_cast<float4*>(dst + dr * H4 * 4) + c, v);
+    }
+}
+
 __global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, int rps, int unit, float* __restrict__ dst,
                                         long long rows, int H) {
     const long long total = rows * H;
@@ -225,6 +238,11 @@ __global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int
 
 int launch_scatter_add_rows(const float* src, const int* idx, int rps, int unit, float* dst, long long rows, int H, cudaStream_t st) {
     if (rows <= 0) return STAIR_OK;
+    if ((H & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        scatter_add_rows_v4_kernel<<<nblocks(rows * (H / 4), 256), 256, 0, st>>>(src, idx, rps < 1 ? 1 : rps, unit, dst, rows, H / 4);
+        STAIR_CHECK_LAUNCH();
+        return STAIR_OK;
+    }
     scatter_add_rows_kernel<<<nblocks(rows * H, 256), 256, 0, st>>>(src, idx, rps < 1 ? 1 : rps, unit, dst, rows, H);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
@@ -292,19 +310,33 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dOut, const XT* _
             }
         }
     }
+    // block-level reduction (8 warps -> 1) through shared memory, then one coalesced atomic per column and block: same-address
+    // atomics serialise in L2, so their number per column (= blocks) and their sector spread both matter
+    __shared__ float red[8][LN_MAXC * 256];
+    const int wi = threadIdx.x >> 5;
+    for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-    for (int i = 0; i < LN_MAXC; ++i) {
-        const int c = lane + 32 * i;
-        if (c < hc)
+        for (int i = 0; i < LN_MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < hc)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { atomicAdd(dgamma + c * 8 + j, pg[i][j]); atomicAdd(dbeta + c * 8 + j, pb[i][j]); }
+                for (int j = 0; j < 8; ++j) red[wi][c * 8 + j] = pass == 0 ? pg[i][j] : pb[i][j];
+        }
+        __syncthreads();
+        float* dst = pass == 0 ? dgamma : dbeta;
+        for (int c = threadIdx.x; c < H; c += blockDim.x) {
+            float t = 0.f;
+            for (int w2 = 0; w2 < warps; ++w2) t += red[w2][c];
+            if (t != 0.f) atomicAdd(dst + c, t);
+        }
+        __syncthreads();
     }
 }
 
 int launch_layernorm_bwd(int xdt, const float* dOut, const void* X, const float* gamma, float* dX, float* dgamma, float* dbeta, long long rows, int H, cudaStream_t st) {
     if (rows <= 0) return STAIR_OK;
     if (H % 8 || H > 256 * LN_MAXC) return STAIR_ERR_UNSUPPORTED;
-    DISPATCH_DT(xdt, XT, (layernorm_bwd_kernel<XT><<<nblocks(rows, 64, 148), 256, 0, st>>>(dOut, reinterpret_cast<const XT*>(X), gamma, dX, dgamma, dbeta, rows, H)));
+    DISPATCH_DT(xdt, XT, (layernorm_bwd_kernel<XT><<<nblocks(rows, 32, 296), 256, 0, st>>>(dOut, reinterpret_cast<const XT*>(X), gamma, dX, dgamma, dbeta, rows, H)));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -917,13 +949,23 @@ __global__ void loss_con_kernel(const AT* __restrict__ vec, float* __restrict__ 
         for (int q = 0; q < CON_MAXC; ++q) { const int c = lane + 32 * q; x[q] = c < H ? ld1<AT>(vec + ro + c) : 0.f; ss += x[q] * x[q]; }
         const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
         float m = -INFINITY;
-        for (int j = 0; j < n_cls; ++j) {
-            float d = 0.f;
+        for (int j0 = 0; j0 < n_cls; j0 += 4) {                               // 4 classes per pass: interleaved shuffle reductions
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int q = 0; q < CON_MAXC; ++q) { const int c = lane + 32 * q; if (c < H) d += x[q] * __ldg(G + static_cast<long long>(j) * H + c); }
-            d = warp_sum(d) / nrm;
-            if (lane == 0) s[j] = d;
-            m = fmaxf(m, d);
+            for (int q = 0; q < CON_MAXC; ++q) {
+                const int c = lane + 32 * q;
+                if (c < H) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (j0 + u < n_cls) d[u] = fmaf(x[q], __ldg(G + static_cast<long long>(j0 + u) * H + c), d[u]);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j0 + u < n_cls) { const float v = d[u] / nrm; if (lane == 0) s[j0 + u] = v; m = fmaxf(m, v); }
         }
         __syncwarp();
         float se = 0.f;
@@ -933,19 +975,21 @@ __global__ void loss_con_kernel(const AT* __restrict__ vec, float* __restrict__ 
         const int ps = __ldg(pos + i);
         const float wi = __ldg(w + i);
         if (lane == 0) atomicAdd(loss + 5, wi * (lse - s[ps]));
+        __syncwarp();
+        for (int j = lane; j < n_cls; j += 32) s[j] = expf(s[j] - lse);      // softmax probabilities, once per row
+        __syncwarp();
         float dp[CON_MAXC];
         float pdp = 0.f;
 #pragma unroll
-        for (int q = 0; q < CON_MAXC; ++q) {
-            const int c = lane + 32 * q;
-            dp[q] = 0.f;
-            if (c < H) {
-                float acc = -__ldg(G + static_cast<long long>(ps) * H + c);
-                for (int j = 0; j < n_cls; ++j) acc += expf(s[j] - lse) * __ldg(G + static_cast<long long>(j) * H + c);
-                dp[q] = acc;
-                pdp += acc * x[q] / nrm;
-            }
+        for (int q = 0; q < CON_MAXC; ++q) { const int c = lane + 32 * q; dp[q] = c < H ? -__ldg(G + static_cast<long long>(ps) * H + c) : 0.f; }
+        for (int j = 0; j < n_cls; ++j) {                                       // class-major: coalesced rows of G, one smem broadcast per class
+            const float pj = s[j];
+            const float* Gj = G + static_cast<long long>(j) * H;
+#pragma unroll
+            for (int q = 0; q < CON_MAXC; ++q) { const int c = lane + 32 * q; if (c < H) dp[q] = fmaf(pj, __ldg(Gj + c), dp[q]); }
         }
+#pragma unroll
+        for (int q = 0; q < CON_MAXC; ++q) pdp += dp[q] * x[q] / nrm;
         pdp = warp_sum(pdp);
 #pragma unroll
         for (int q = 0; q < CON_MAXC; ++q) {
