@@ -934,79 +934,122 @@ int launch_loss_bin(int dt, const void* vec, float* dvec, const int* out_slot, c
 
 // contrastive CE (train_module.py:113-132): p = normalize(x); s_j = p . G_j over all classes of the window; loss = lse(s) - s_pos
 constexpr int CON_MAXC = 32;       // columns per lane: H <= 1024
-template <typename AT>
+constexpr int CON_R = 4;           // rows per warp: every element of G fetched from L2/L1 serves CON_R rows (the class matrix, n_cls x H fp32,
+                                   // is re-read for every row: at one row per warp the kernel is bound by that traffic)
+template <typename AT, int MAXC>
 __global__ void loss_con_kernel(const AT* __restrict__ vec, float* __restrict__ dvec, const int* __restrict__ out_slot, const int* __restrict__ node,
                                 const int* __restrict__ pos, const float* __restrict__ w, const float* __restrict__ G, int n_cls,
                                 float* __restrict__ loss, int n, int H) {
-    extern __shared__ float sc[];                                  // [warps][n_cls] class scores of the warp's current row
+    extern __shared__ float sc[];                                  // [warps][CON_R][n_cls] class scores of the warp's current rows
     const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    float* s = sc + static_cast<size_t>(threadIdx.x >> 5) * n_cls;
-    for (int i = blockIdx.x * warps + (threadIdx.x >> 5); i < n; i += gridDim.x * warps) {
-        const long long ro = static_cast<long long>(out_slot[__ldg(node + i)]) * H;
-        float x[CON_MAXC];
-        float ss = 0.f;
+    float* s = sc + static_cast<size_t>(threadIdx.x >> 5) * CON_R * n_cls;
+    float lsum = 0.f;
+    for (int i0 = (blockIdx.x * warps + (threadIdx.x >> 5)) * CON_R; i0 < n; i0 += gridDim.x * warps * CON_R) {
+        long long ro[CON_R];
+        float x[CON_R][MAXC], nrm[CON_R];
 #pragma unroll
-        for (int q = 0; q < CON_MAXC; ++q) { const int c = lane + 32 * q; x[q] = c < H ? ld1<AT>(vec + ro + c) : 0.f; ss += x[q] * x[q]; }
-        const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
-        float m = -INFINITY;
-        for (int j0 = 0; j0 < n_cls; j0 += 4) {                               // 4 classes per pass: interleaved shuffle reductions
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < CON_R; ++r) {
+            const int i = min(i0 + r, n - 1);                        // tail rows recompute the last row (their results are discarded)
+            ro[r] = static_cast<long long>(out_slot[__ldg(node + i)]) * H;
+            float ss = 0.f;
 #pragma unroll
-            for (int q = 0; q < CON_MAXC; ++q) {
+            for (int q = 0; q < MAXC; ++q) { const int c = lane + 32 * q; x[r][q] = c < H ? ld1<AT>(vec + ro[r] + c) : 0.f; ss += x[r][q] * x[r][q]; }
+            nrm[r] = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+        }
+        float m[CON_R];
+#pragma unroll
+        for (int r = 0; r < CON_R; ++r) m[r] = -INFINITY;
+        for (int j = 0; j < n_cls; ++j) {
+            const float* Gj = G + static_cast<long long>(j) * H;
+            float d[CON_R];
+#pragma unroll
+            for (int r = 0; r < CON_R; ++r) d[r] = 0.f;
+#pragma unroll
+            for (int q = 0; q < MAXC; ++q) {
                 const int c = lane + 32 * q;
                 if (c < H) {
+                    const float g = __ldg(Gj + c);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) if (j0 + u < n_cls) d[u] = fmaf(x[q], __ldg(G + static_cast<long long>(j0 + u) * H + c), d[u]);
+                    for (int r = 0; r < CON_R; ++r) d[r] = fmaf(x[r][q], g, d[r]);
                 }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+                for (int r = 0; r < CON_R; ++r) d[r] += __shfl_xor_sync(0xffffffffu, d[r], o);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (j0 + u < n_cls) { const float v = d[u] / nrm; if (lane == 0) s[j0 + u] = v; m = fmaxf(m, v); }
+            for (int r = 0; r < CON_R; ++r) { const float v = d[r] / nrm[r]; if (lane == 0) s[r * n_cls + j] = v; m[r] = fmaxf(m[r], v); }
         }
         __syncwarp();
-        float se = 0.f;
-        for (int j = lane; j < n_cls; j += 32) se += expf(s[j] - m);
-        se = warp_sum(se);
-        const float lse = m + logf(se);
-        const int ps = __ldg(pos + i);
-        const float wi = __ldg(w + i);
-        if (lane == 0) atomicAdd(loss + 5, wi * (lse - s[ps]));
-        __syncwarp();
-        for (int j = lane; j < n_cls; j += 32) s[j] = expf(s[j] - lse);      // softmax probabilities, once per row
-        __syncwarp();
-        float dp[CON_MAXC];
-        float pdp = 0.f;
+        float wi[CON_R];
+        int ps[CON_R];
 #pragma unroll
-        for (int q = 0; q < CON_MAXC; ++q) { const int c = lane + 32 * q; dp[q] = c < H ? -__ldg(G + static_cast<long long>(ps) * H + c) : 0.f; }
-        for (int j = 0; j < n_cls; ++j) {                                       // class-major: coalesced rows of G, one smem broadcast per class
-            const float pj = s[j];
+        for (int r = 0; r < CON_R; ++r) {
+            float se = 0.f;
+            for (int j = lane; j < n_cls; j += 32) se += expf(s[r * n_cls + j] - m[r]);
+            se = warp_sum(se);
+            const float lse = m[r] + logf(se);
+            const int i = min(i0 + r, n - 1);
+            ps[r] = __ldg(pos + i);
+            wi[r] = i0 + r < n ? __ldg(w + i) : 0.f;
+            lsum += wi[r] * (lse - s[r * n_cls + ps[r]]);
+            __syncwarp();
+            for (int j = lane; j < n_cls; j += 32) s[r * n_cls + j] = expf(s[r * n_cls + j] - lse);      // softmax probabilities
+        }
+        __syncwarp();
+        float dp[CON_R][MAXC];
+#pragma unroll
+        for (int r = 0; r < CON_R; ++r)
+#pragma unroll
+            for (int q = 0; q < MAXC; ++q) { const int c = lane + 32 * q; dp[r][q] = c < H ? -__ldg(G + static_cast<long long>(ps[r]) * H + c) : 0.f; }
+        for (int j = 0; j < n_cls; ++j) {
             const float* Gj = G + static_cast<long long>(j) * H;
+            float pj[CON_R];
 #pragma unroll
-            for (int q = 0; q < CON_MAXC; ++q) { const int c = lane + 32 * q; if (c < H) dp[q] = fmaf(pj, __ldg(Gj + c), dp[q]); }
+            for (int r = 0; r < CON_R; ++r) pj[r] = s[r * n_cls + j];
+#pragma unroll
+            for (int q = 0; q < MAXC; ++q) {
+                const int c = lane + 32 * q;
+                if (c < H) {
+                    const float g = __ldg(Gj + c);
+#pragma unroll
+                    for (int r = 0; r < CON_R; ++r) dp[r][q] = fmaf(pj[r], g, dp[r][q]);
+                }
+            }
         }
 #pragma unroll
-        for (int q = 0; q < CON_MAXC; ++q) pdp += dp[q] * x[q] / nrm;
-        pdp = warp_sum(pdp);
+        for (int r = 0; r < CON_R; ++r) {
+            float pdp = 0.f;
 #pragma unroll
-        for (int q = 0; q < CON_MAXC; ++q) {
-            const int c = lane + 32 * q;
-            if (c < H) atomicAdd(dvec + ro + c, wi * (dp[q] - x[q] / nrm * pdp) / nrm);
+            for (int q = 0; q < MAXC; ++q) pdp += dp[r][q] * x[r][q] / nrm[r];
+            pdp = warp_sum(pdp);
+            if (i0 + r < n) {
+#pragma unroll
+                for (int q = 0; q < MAXC; ++q) {
+                    const int c = lane + 32 * q;
+                    if (c < H) atomicAdd(dvec + ro[r] + c, wi[r] * (dp[r][q] - x[r][q] / nrm[r] * pdp) / nrm[r]);
+                }
+            }
         }
         __syncwarp();
     }
+    if (lane == 0 && lsum != 0.f) atomicAdd(loss + 5, lsum);
 }
 
 int launch_loss_con(int dt, const void* vec, float* dvec, const int* out_slot, const int* node, const int* pos, const float* w,
                     const float* cls_rep, int n_cls, float* loss, int n, int H, cudaStream_t st) {
     if (n <= 0 || n_cls <= 0) return STAIR_OK;
-    if (H > 32 * CON_MAXC || n_cls > 2048) return STAIR_ERR_UNSUPPORTED;
+    if (H > 32 * CON_MAXC || n_cls > 1024) return STAIR_ERR_UNSUPPORTED;
     const int warps = 4;
-    DISPATCH_DT(dt, AT, (loss_con_kernel<AT><<<nblocks(n, warps), warps * 32, warps * n_cls * sizeof(float), st>>>(
-                            reinterpret_cast<const AT*>(vec), dvec, out_slot, node, pos, w, cls_rep, n_cls, loss, n, H)));
+    const size_t smem = static_cast<size_t>(warps) * CON_R * n_cls * sizeof(float);
+    const int grid = nblocks((n + CON_R - 1) / CON_R, warps);
+    if (H <= 512) {
+        DISPATCH_DT(dt, AT, (loss_con_kernel<AT, 16><<<grid, warps * 32, smem, st>>>(reinterpret_cast<const AT*>(vec), dvec, out_slot, node, pos, w, cls_rep,
+                                                                                    n_cls, loss, n, H)));
+    } else {
+        DISPATCH_DT(dt, AT, (loss_con_kernel<AT, CON_MAXC><<<grid, warps * 32, smem, st>>>(reinterpret_cast<const AT*>(vec), dvec, out_slot, node, pos, w, cls_rep,
+                                                                                          n_cls, loss, n, H)));
+    }
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
