@@ -159,6 +159,10 @@ def run_reference(args, rank, world):
 
 
 def main():
+    # the driver reads ONE JSON line from stdout: libraries that print there (NCCL's version banner) go to stderr instead
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, 'w')
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

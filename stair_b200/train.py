@@ -237,12 +237,19 @@ class NMNTrainStep:
         # window-level class names (train_module.py:360-366,388-406): under data parallelism the negatives of the whole
         # window are every rank's classes, so names + word embeddings are exchanged on the host (small)
         class_emb = rows.class_emb
-        if world > 1 and self.global_negatives:
+        touched = touched_slots(batch, rows, cfg['have_pretrain_head'])
+        if world > 1:
+            # one host-side exchange per window: class phrases (contrastive negatives) and the touched-parameter sets (Adam skips
+            # parameters no rank's questions used, like the reference) — known from the layouts, so run() needs no device sync
             gathered = [None] * world
-            dist.all_gather_object(gathered, {k: v.cpu() for k, v in class_emb.items()}, group=self.group)
-            class_emb = {}
+            mine = {'classes': {k: v.cpu() for k, v in class_emb.items()} if self.global_negatives else {}, 'touched': sorted(touched)}
+            dist.all_gather_object(gathered, mine, group=self.group)
+            if self.global_negatives:
+                class_emb = {}
+                for part in gathered:
+                    class_emb.update(part['classes'])
             for part in gathered:
-                class_emb.update(part)
+                touched |= set(part['touched'])
         pl = TrainPlan()
         pl.batch, pl.rows, pl.ga, pl.world = batch, rows, float(ga), world
         pl.class_names = sorted(class_emb)
@@ -258,7 +265,7 @@ class NMNTrainStep:
         pl.bin = (up(rows.bin_node, np.int32), up(rows.bin_which, np.int32), up(rows.bin_label, np.int32), up(rows.bin_w, np.float32))
         pl.con = (up(rows.con_node, np.int32), up([pos_of[c] for c in rows.con_cls], np.int32), up(rows.con_w, np.float32))
         pl.answer = batch.answer.to(torch.int32).to(dev, non_blocking=True)
-        pl.touched = touched_slots(batch, rows, cfg['have_pretrain_head'])
+        pl.touched = touched
         return pl
 
     def run(self, pl, assign_grads=True, dropout_seed=None):
@@ -326,14 +333,10 @@ class NMNTrainStep:
         L.check(lib.stair_nmn_backward(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), stream), 'stair_nmn_backward')
         self.last_launches = launches + int(lib.stair_last_launch_count())
 
-        touched = pl.touched
+        touched = pl.touched                                               # already the union over ranks (plan)
         if pl.world > 1:
-            flag = torch.zeros(L.W_COUNT + 8, dtype=torch.float32, device=dev)
-            flag[list(touched)] = 1.0
             dist.all_reduce(flat, group=self.group)                        # NCCL sum over NVLink: gradients
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)   # OR of the touched flags
             dist.all_reduce(loss, group=self.group)
-            touched = set(int(i) for i in torch.nonzero(flag[:L.W_COUNT]).flatten().tolist())
         if assign_grads:
             for wid, (numel, targets) in tg.items():
                 if wid not in touched:
