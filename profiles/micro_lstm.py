@@ -22,7 +22,8 @@ def run(ph, n=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 ref = None
-for cg in [2, 4]:
+for rows, cg in [(128, 2), (128, 4), (64, 4)]:
+    lib.stair_lstm_rows(rows)
     lib.stair_lstm_colgroups(cg)
     both = run(L.FWD_ENCODE_VIDEO | L.FWD_ENCODE_TEXT)
     text = run(L.FWD_ENCODE_TEXT)
@@ -33,5 +34,6 @@ for cg in [2, 4]:
     if ref is None:
         ref = out
     err = max(float((a - b).abs().max()) for a, b in zip(out, ref))
-    print('colgroups %d: video+text %.3f ms   text only %.3f   video only %.3f   (GEMMs included; max diff vs cg=2 %.3g)' % (cg, both, text, video, err), flush=True)
+    print('rows/CTA %d colgroups %d: video+text %.3f ms   text only %.3f   video only %.3f   (GEMMs included; max diff vs cg=2 %.3g)' % (rows, cg, both, text, video, err), flush=True)
 lib.stair_lstm_colgroups(2)
+lib.stair_lstm_rows(64)

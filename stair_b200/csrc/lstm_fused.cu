@@ -77,21 +77,33 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
     for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(hh[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
 
-// CG = epilogue warps per TMEM lane quarter (each takes 64 / CG of a chunk's hidden units); threads = 128 + 128 * CG
-template <int CG, bool HIST>
-__global__ void __launch_bounds__(128 + 128 * CG, 1)
+// CG = epilogue warps per TMEM lane quarter (each takes 64 / CG of a chunk's hidden units).
+// VROWS = questions per CTA.  128: all four TMEM lane quarters carry rows, warps 0-3 are the role warps, 4.. the epilogue
+// (threads = 128 + 128 * CG).  64 (with CG = 4): the MMA is still M = 128 but only lanes 0-63 carry rows, so the 8 epilogue warps
+// are the ones whose TMEM quarter (warp % 4) is 0 or 1 — warps 0,1,4,5,8,9,12,13 — and each owns 16 of a chunk's units: half the
+// per-step epilogue latency per question block (the recurrence is a chain of L sequential steps, so that latency is the kernel's
+// critical path) and twice as many CTAs to fill the SMs the video blocks free after T steps.  Role warps: 2 TMA, 3 MMA, 6 TMEM
+// allocator, 7 L2 prefetch; 16 warps -> 128 registers per thread.
+template <int CG, bool HIST, int VROWS>
+__global__ void __launch_bounds__(VROWS == 64 ? 512 : 128 + 128 * CG, 1)
 lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, const LstmFusedParams p) {
     const LstmSeq sq = blockIdx.z == 0 ? p.seq[0] : p.seq[1];      // by value: a runtime index into param space forces a local copy
     const int dir = blockIdx.y;
     const int wsel = blockIdx.z * 2 + dir;          // which W_hh map (never form a runtime-selected pointer to a param-space map)
-    const int row0 = blockIdx.x * LF_ROWS;
+    static_assert(VROWS == 128 || (VROWS == 64 && CG == 4), "64-row blocks use 4 column groups on TMEM quarters 0 and 1");
+    const int row0 = blockIdx.x * VROWS;
     if (row0 >= sq.B) return;
     const int h = sq.h, NC = h / 64;              // chunks of 64 hidden units == k-blocks of h
     const bool ragged = sq.q_off != nullptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int LF_THREADS = 128 + 128 * CG;
+    constexpr int LF_THREADS = VROWS == 64 ? 512 : 128 + 128 * CG;
     constexpr int SBN = 8 / CG;                   // 8-unit sub-blocks per thread per chunk
+    constexpr int EPI_THREADS = VROWS * CG;       // epilogue threads (arrival count of the tmem_empty / h_ready barriers)
+    // role warps and the (TMEM quarter, column group) of an epilogue warp
+    constexpr int W_TMA = VROWS == 64 ? 2 : 0, W_MMA = VROWS == 64 ? 3 : 1, W_ALLOC = VROWS == 64 ? 6 : 2, W_PREF = VROWS == 64 ? 7 : 3;
+    const bool is_epi = VROWS == 64 ? ((warp & 3) < 2) : (warp >= 4);
+    const int quarter = warp & 3, halfsel = VROWS == 64 ? (warp >> 2) : ((warp - 4) >> 2);      // halfsel = column group 0..CG-1
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -109,18 +121,18 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < LF_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128 * CG); }
-        for (int a = 0; a < 4; ++a) mbar_init(&h_ready[a], 128 * CG);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_THREADS); }
+        for (int a = 0; a < 4; ++a) mbar_init(&h_ready[a], EPI_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *s_steps = ragged ? 0 : sq.steps;
     }
-    if (warp == 2) {
+    if (warp == W_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr_smem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 2 * hbuf_bytes / 16; i += LF_THREADS) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    if (ragged && threadIdx.x < LF_ROWS) {                          // this CTA only runs as many steps as its longest question
+    if (ragged && threadIdx.x < VROWS) {                            // this CTA only runs as many steps as its longest question
         const int r = row0 + threadIdx.x;
         if (r < sq.B) atomicMax(s_steps, __ldg(sq.q_off + r + 1) - __ldg(sq.q_off + r));
     }
@@ -131,7 +143,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
     const uint32_t tmem_base = *tmem_ptr_smem;
     const int S = *s_steps;
 
-    if (warp == 0) {
+    if (warp == W_TMA) {
         if (lane == 0) {
             // ===================== TMA producer: W_hh tiles, (chunk, k-block) order, every step after the first ==========
             int stage = 0; uint32_t phase = 0;
@@ -149,7 +161,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                         if (++stage == LF_STAGES) { stage = 0; phase ^= 1; }
                     }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         if (lane == 0) {
             // ===================== MMA issuer: gates[128, 256c..] = h_{s-1}[128, h] . W_hh[chunk]^T ============================
             int stage = 0; uint32_t phase = 0;
@@ -180,14 +192,14 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                 }
             }
         }
-    } else if (warp == 3) {
+    } else if (warp == W_PREF) {
         // ===================== L2 prefetcher: the input-projection rows of step s+2 (they do not depend on the recurrence) ========
         // xproj (134 + 268 MB at B=4096) does not fit in L2; without this every epilogue load is an HBM-latency miss.
         for (int s = 0; s < S; ++s) {
             // pace: rows of step s are requested once step s-3 is complete (two steps ahead of the cell epilogue).  A parity wait on
             // a phase that is already two behind simply returns one phase later; a later phase of that parity always exists here.
             if (s >= 3) mbar_wait(&h_ready[NC - 1], static_cast<uint32_t>((s - 3) & 1), p.err_flag, 206);
-            for (int r = lane; r < LF_ROWS; r += 32) {
+            for (int r = lane; r < VROWS; r += 32) {
                 const int grow = row0 + r;
                 if (grow >= sq.B) continue;
                 int base, L = sq.steps;
@@ -198,9 +210,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                 for (int b = 0; b < 4 * h * 2; b += 128) prefetch_l2(reinterpret_cast<const char*>(xrow) + b);
             }
         }
-    } else if (warp >= 4) {
-        // ===================== cell epilogue: 2 warps per TMEM lane quarter, each takes 32 of a chunk's 64 units =============
-        const int quarter = warp & 3, halfsel = (warp - 4) >> 2;   // halfsel = column group 0..CG-1
+    } else if (is_epi) {
+        // ===================== cell epilogue: CG warps per TMEM lane quarter, each takes 64 / CG of a chunk's 64 units =============
         const int row = quarter * 32 + lane;
         const int grow = row0 + row;
         const bool valid = grow < sq.B;
@@ -208,15 +219,15 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
         if (ragged) { base = valid ? __ldg(sq.q_off + grow) : 0; L = valid ? __ldg(sq.q_off + grow + 1) - base : 0; }
         else base = grow * sq.steps;
         // cell state scratch, private to this CTA, laid out [unit/4][row][4] so that a warp's float4 accesses are contiguous
-        const int nblk = (sq.B + LF_ROWS - 1) / LF_ROWS;
-        float* cblk = sq.c + (static_cast<long long>(dir) * nblk + blockIdx.x) * (static_cast<long long>(h) * LF_ROWS) + row * 4;
+        const int nblk = (sq.B + VROWS - 1) / VROWS;
+        float* cblk = sq.c + (static_cast<long long>(dir) * nblk + blockIdx.x) * (static_cast<long long>(h) * VROWS) + row * 4;
         // HIST: the cell state of step s lives in the blocked history; q-th float4 of the 8 units starting at `unit`
         const long long RB = (sq.B + 127) / 128 * 4;                                      // 32-row blocks per (step, direction)
         const long long hist_rb = (static_cast<long long>(dir) * RB + (grow >> 5)) * (h >> 3);      // + step * 2 * RB * (h/8); then + unit/8
         const long long hist_step = 2 * RB * (h >> 3);
         auto c_ptr = [&](int step, int unit, int q) -> float* {
             if (HIST) return sq.c_h + (step * hist_step + hist_rb + (unit >> 3)) * 256 + lane * 8 + 4 * q;
-            return cblk + (unit / 4 + q) * (LF_ROWS * 4);
+            return cblk + (unit / 4 + q) * (VROWS * 4);
         };
         const uint32_t sH0 = smem_u32(sH);
         const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
@@ -322,7 +333,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == W_ALLOC) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
@@ -332,6 +343,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
 
 static volatile unsigned int* g_lstm_dbg = nullptr;
 static int g_lstm_cg = 2;
+static int g_lstm_rows = 64;      // questions per CTA of the fused recurrence (128 = round-1 layout)
 bool lstm_fused_ok(int precision, int h) { return precision == STAIR_BF16 && h >= 64 && h <= 256 && (h % 64) == 0; }
 
 // seq 0 = video (T steps), seq 1 = text (ragged, L_max steps); either may be disabled with steps = 0.
@@ -357,19 +369,32 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
     CUtensorMap tm[4];
     for (int i = 0; i < 4; ++i) STAIR_TRY(make_tmap_bf16_2d(&tm[i], w[i], h, 4ULL * h, h, 64, 256));
     const int smem = 2 * (h / 64) * LF_KB_BYTES + LF_STAGES * LF_W_STAGE_BYTES + 256 + 1024;
-    static int configured[3] = {0, 0, 0};
-    const int vi = hist ? 2 : (g_lstm_cg == 4 ? 1 : 0);
+    // variants: 0 = 128 rows, 2 column groups (round-1 default); 1 = 128 rows, 4 column groups (comparison); 2 = training history,
+    // 128 rows; 3 = 64 rows per CTA, 4 column groups; 4 = training history, 64 rows
+    static int configured[5] = {0, 0, 0, 0, 0};
+    const bool r64 = g_lstm_rows == 64;
+    const int vi = hist ? (r64 ? 4 : 2) : (r64 ? 3 : (g_lstm_cg == 4 ? 1 : 0));
     if (configured[vi] < smem) {
-        const cudaError_t e = vi == 2 ? cudaFuncSetAttribute(lstm_fused_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                            : vi == 1 ? cudaFuncSetAttribute(lstm_fused_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                                      : cudaFuncSetAttribute(lstm_fused_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e;
+        switch (vi) {
+        case 4: e = cudaFuncSetAttribute(lstm_fused_kernel<4, true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+        case 3: e = cudaFuncSetAttribute(lstm_fused_kernel<4, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+        case 2: e = cudaFuncSetAttribute(lstm_fused_kernel<2, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+        case 1: e = cudaFuncSetAttribute(lstm_fused_kernel<4, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+        default: e = cudaFuncSetAttribute(lstm_fused_kernel<2, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+        }
         if (e != cudaSuccess) return STAIR_ERR_CUDA;
         configured[vi] = smem;
     }
-    dim3 grid((B + LF_ROWS - 1) / LF_ROWS, 2, nseq);
-    if (vi == 2) lstm_fused_kernel<2, true><<<grid, 128 + 128 * 2, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
-    else if (vi == 1) lstm_fused_kernel<4, false><<<grid, 128 + 128 * 4, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
-    else lstm_fused_kernel<2, false><<<grid, 128 + 128 * 2, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
+    const int vrows = r64 ? 64 : 128;
+    dim3 grid((B + vrows - 1) / vrows, 2, nseq);
+    switch (vi) {
+    case 4: lstm_fused_kernel<4, true, 64><<<grid, 512, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
+    case 3: lstm_fused_kernel<4, false, 64><<<grid, 512, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
+    case 2: lstm_fused_kernel<2, true, 128><<<grid, 128 + 128 * 2, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
+    case 1: lstm_fused_kernel<4, false, 128><<<grid, 128 + 128 * 4, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
+    default: lstm_fused_kernel<2, false, 128><<<grid, 128 + 128 * 2, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
+    }
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -377,4 +402,5 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
 }  // namespace stair
 
 extern "C" int stair_lstm_debug(unsigned int* pinned_buf) { stair::g_lstm_dbg = pinned_buf; return STAIR_OK; }
+extern "C" int stair_lstm_rows(int rows) { if (rows != 64 && rows != 128) return STAIR_ERR_ARG; stair::g_lstm_rows = rows; return STAIR_OK; }
 extern "C" int stair_lstm_colgroups(int cg) { if (cg != 2 && cg != 4) return STAIR_ERR_ARG; stair::g_lstm_cg = cg; return STAIR_OK; }
