@@ -137,8 +137,6 @@ typedef struct StairBatch {
     const int32_t* root_node;  /* [B] node index of token 0 */
     const StairGroup* groups;  /* HOST [n_groups] */
     const int32_t* group_tab;  /* device [4][n_groups]: node_off, out_base, out_mult, aux_base (same as `groups`) */
-    const int32_t* q_order;    /* device [B] or NULL: question ids in descending question length — a scheduling hint for the text recurrence
-                                * (a CTA's questions then have similar lengths and it stops at its own longest); results do not depend on it */
 } StairBatch;
 
 /* Caller-owned output / scratch buffers. */

@@ -199,8 +199,7 @@ inline int run_encoders(Ctx& c, int phases) {
     if (fused)
         return launch_lstm_fused(c.at<void>(c.plan.xv), c.buf.vid, T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R),
                                  c.at<void>(c.plan.xq), c.buf.tokfeat, c.buf.qfeat, b.q_off, b.L_max, c.W(STAIR_W_TENC_WHHI_F),
-                                 c.W(STAIR_W_TENC_WHHI_R), cs, B, h, (phases & STAIR_FWD_ENCODE_VIDEO) ? 1 : 0, 1, err_flag_ptr(), c.st, nullptr,
-                                 b.q_order);
+                                 c.W(STAIR_W_TENC_WHHI_R), cs, B, h, (phases & STAIR_FWD_ENCODE_VIDEO) ? 1 : 0, 1, err_flag_ptr(), c.st);
     if (cudaMemsetAsync(cs, 0, sizeof(float) * 2 * B * h, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
     for (int s = 0; s < b.L_max; ++s) {
         if (s > 0)

@@ -29,8 +29,6 @@ struct LstmSeq {
     bf16* out;              // video: [B*T, 2h] (VID arena slots 0..B-1) ; text: token_feature [n_tok, 2h]
     bf16* final_h;          // text: question_feature [B, 2h] (h_n of both directions) ; video: null
     const int* q_off;       // text: [B+1] token offsets (ragged) ; video: null
-    const int* order;       // text, inference: [B] question ids in descending length (row r of the grid = question order[r]) so that a
-                            // CTA's questions have similar lengths and it only runs its own longest; null = batch order
     int steps;              // video: T ; text: L_max
     int B, h;
     // training (HIST): per-step history for BPTT.  Gates (post-activation i,f,g,o) and cell state are written in the BLOCKED layout of
@@ -135,11 +133,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
     for (int i = threadIdx.x; i < 2 * hbuf_bytes / 16; i += LF_THREADS) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     if (ragged && threadIdx.x < VROWS) {                            // this CTA only runs as many steps as its longest question
-        const int pos = row0 + threadIdx.x;
-        if (pos < sq.B) {
-            const int r = sq.order ? __ldg(sq.order + pos) : pos;
-            atomicMax(s_steps, __ldg(sq.q_off + r + 1) - __ldg(sq.q_off + r));
-        }
+        const int r = row0 + threadIdx.x;
+        if (r < sq.B) atomicMax(s_steps, __ldg(sq.q_off + r + 1) - __ldg(sq.q_off + r));
     }
     fence_async_smem();                                            // zero-filled h buffers visible to the tensor core (async proxy)
     tcgen05_fence_before();
@@ -205,8 +200,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
             // a phase that is already two behind simply returns one phase later; a later phase of that parity always exists here.
             if (s >= 3) mbar_wait(&h_ready[NC - 1], static_cast<uint32_t>((s - 3) & 1), p.err_flag, 206);
             for (int r = lane; r < VROWS; r += 32) {
-                if (row0 + r >= sq.B) continue;
-                const int grow = sq.order ? __ldg(sq.order + row0 + r) : row0 + r;
+                const int grow = row0 + r;
+                if (grow >= sq.B) continue;
                 int base, L = sq.steps;
                 if (ragged) { base = __ldg(sq.q_off + grow); L = __ldg(sq.q_off + grow + 1) - base; }
                 else base = grow * sq.steps;
@@ -218,8 +213,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
     } else if (is_epi) {
         // ===================== cell epilogue: CG warps per TMEM lane quarter, each takes 64 / CG of a chunk's 64 units =============
         const int row = quarter * 32 + lane;
-        const bool valid = row0 + row < sq.B;
-        const int grow = valid ? (sq.order ? __ldg(sq.order + row0 + row) : row0 + row) : row0 + row;
+        const int grow = row0 + row;
+        const bool valid = grow < sq.B;
         int base = 0, L = sq.steps;
         if (ragged) { base = valid ? __ldg(sq.q_off + grow) : 0; L = valid ? __ldg(sq.q_off + grow + 1) - base : 0; }
         else base = grow * sq.steps;
@@ -355,15 +350,15 @@ bool lstm_fused_ok(int precision, int h) { return precision == STAIR_BF16 && h >
 int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh_v_f, const void* whh_v_r,
                       const void* xproj_t, void* tokfeat, void* qfeat, const int* q_off, int L_max, const void* whh_t_f,
                       const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st,
-                      const LstmHist* hist, const int* text_order) {
+                      const LstmHist* hist) {
     if (B <= 0 || (!run_video && !run_text)) return STAIR_OK;
     LstmFusedParams p;
     p.err_flag = err_flag;
     p.dbg = g_lstm_dbg;
     LstmSeq v; v.xproj = reinterpret_cast<const bf16*>(xproj_v); v.c = c_scratch; v.out = reinterpret_cast<bf16*>(vid_out);
-    v.final_h = nullptr; v.q_off = nullptr; v.order = nullptr; v.steps = T; v.B = B; v.h = h;
+    v.final_h = nullptr; v.q_off = nullptr; v.steps = T; v.B = B; v.h = h;
     LstmSeq t; t.xproj = reinterpret_cast<const bf16*>(xproj_t); t.c = c_scratch + 2LL * ((B + LF_ROWS - 1) / LF_ROWS) * LF_ROWS * h; t.out = reinterpret_cast<bf16*>(tokfeat);
-    t.final_h = reinterpret_cast<bf16*>(qfeat); t.q_off = q_off; t.order = hist ? nullptr : text_order; t.steps = L_max; t.B = B; t.h = h;
+    t.final_h = reinterpret_cast<bf16*>(qfeat); t.q_off = q_off; t.steps = L_max; t.B = B; t.h = h;
     v.gates_h = hist ? hist->gates[0] : nullptr; v.c_h = hist ? hist->c[0] : nullptr; v.hs_h = hist ? hist->hs[0] : nullptr; v.hs_dir = hist ? hist->hs_dir[0] : 0;
     t.gates_h = hist ? hist->gates[1] : nullptr; t.c_h = hist ? hist->c[1] : nullptr; t.hs_h = hist ? hist->hs[1] : nullptr; t.hs_dir = hist ? hist->hs_dir[1] : 0;
     const void* w[4];

@@ -88,7 +88,7 @@ struct LstmHist { float* gates[2]; float* c[2]; bf16* hs[2]; long long hs_dir[2]
 int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh_v_f, const void* whh_v_r,
                       const void* xproj_t, void* tokfeat, void* qfeat, const int* q_off, int L_max, const void* whh_t_f,
                       const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st,
-                      const LstmHist* hist = nullptr, const int* text_order = nullptr);
+                      const LstmHist* hist = nullptr);
 
 // ---- layout grouping (layout_group.cu) ----------------------------------------------------------------------------
 int launch_group_layouts(const StairBatch& b, int32_t* itab, int32_t* status, cudaStream_t st);

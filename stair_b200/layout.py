@@ -284,7 +284,7 @@ class NMNBatch:
         B, n = self.B, self.n_nodes
         o, out = 0, {}
         for name, size in (('q_off', B + 1), ('node_gid', n), ('node_q', n), ('node_arg', 3 * n), ('node_span', 2 * n),
-                           ('root_node', B), ('q_order', B)):
+                           ('root_node', B)):
             out[name] = (o, size)
             o += (size + 3) // 4 * 4
         out['_total'] = (0, o)
@@ -430,10 +430,8 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
     sl = b._slices()
     itab = torch.empty(sl['_total'][1], dtype=torch.int32, pin_memory=pin_memory)
     it = itab.numpy()
-    # scheduling hint for the text recurrence: questions in descending length (stable)
-    q_order = np.argsort(-np.diff(np.asarray(q_off, np.int64)), kind='stable').astype(np.int32)
     for name, arr in (('q_off', q_off), ('node_gid', gid), ('node_q', node_q), ('node_arg', node_arg.reshape(-1)),
-                      ('node_span', node_span.reshape(-1)), ('root_node', root), ('q_order', q_order)):
+                      ('node_span', node_span.reshape(-1)), ('root_node', root)):
         o, size = sl[name]
         it[o:o + size] = arr
     b.itab_host = itab

@@ -92,7 +92,7 @@ class VideoNMN(nn.Module):
         sb.B, sb.T, sb.n_tok, sb.L_max, sb.n_nodes, sb.n_groups = B, T, batch.n_tok, batch.L_max, n, ng
         sb.video_dtype, sb.question_dtype = L.dtype_code(batch.video_dev.dtype), L.dtype_code(batch.question_dev.dtype)
         sb.video, sb.question = batch.video_dev.data_ptr(), batch.question_dev.data_ptr()
-        for name in ('q_off', 'node_gid', 'node_q', 'node_arg', 'node_span', 'root_node', 'q_order'):
+        for name in ('q_off', 'node_gid', 'node_q', 'node_arg', 'node_span', 'root_node'):
             setattr(sb, name, batch.tab_ptr(name))
         sb.groups = ctypes.cast(groups, ctypes.POINTER(L.StairGroup))
         sb.group_tab = gtab.data_ptr()
