@@ -313,6 +313,7 @@ int stair_exists_frame(int dtype, const void* vid, const int32_t* feat_idx, cons
 int stair_hasitem_tail(int dtype, const void* x, const float* w, const float* b, float* att, int out_base, int n, int T, int H, void* stream);
 /* TMA-staged streaming variants of the row kernels: 0 off, 1 (default) HasItem tail, 2 also the cosine maps (slower; kept for measurement) */
 int stair_set_row_stream(int on);
+int stair_set_cos_impl(int impl);      /* cosine maps (Localize / ExistsFrame): 0 = instance-major kernel when T % 8 == 0 (product); 1 = row-major kernel */
 /* fp32 -> bf16 rows, and fp32 -> three bf16 planes (x = p0 + p1 + p2) used by the strict mode */
 int stair_cast_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, void* stream);
 int stair_split3(const float* src, long long ld_src, void* dst, long long ld_dst, long long plane_rows, long long rows, int cols, void* stream);

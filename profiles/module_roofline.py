@@ -14,6 +14,7 @@ T, H, K = 8, 512, 1
 pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
 PEAK = json.load(open(pk))['hbm_gbs'] if os.path.exists(pk) else 6650.0
 lib = L.lib()
+lib.stair_set_cos_impl(int(os.environ.get('COS_IMPL', 0)))       # 0 = instance-major cosine maps (product), 1 = row-major
 dev = 'cuda'
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 

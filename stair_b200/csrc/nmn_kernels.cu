@@ -287,13 +287,103 @@ __global__ void __launch_bounds__(256, 2) cos_rows_kernel(const AT* __restrict__
     }
 }
 
+// Instance-major variant for T % 8 == 0: one warp owns a whole instance, R (8 / 4 / 2 by row width) frame rows in flight per pass.  The keyword row and its
+// norm are loaded / reduced once per (instance, keyword) instead of once per frame row, |f_t|^2 once per frame instead of once per
+// (frame, keyword), and the 8 results of a pass leave as one 32-byte store: ~1.75x fewer instructions per row than cos_rows_kernel,
+// which was issue-bound at 44 % of the HBM roofline (profiles/r1_module_kernel_roofline.txt).
+template <typename AT, int CH, int R>
+__global__ void __launch_bounds__(256, 2) cos_inst_kernel(const AT* __restrict__ f, const int* __restrict__ feat_idx, const AT* __restrict__ kmat,
+                                                          const int* __restrict__ kw_idx, int K, int T, int H, float* __restrict__ att,
+                                                          long long out_base, int n) {
+    const int lane = threadIdx.x & 31, hc = H / 8;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int inst = warp; inst < n; inst += nwarps) {
+        const AT* fbase = feat_idx ? f + static_cast<long long>(__ldg(feat_idx + inst)) * T * H : f + static_cast<long long>(inst) * T * H;
+        for (int t0 = 0; t0 < T; t0 += R) {
+            Raw8<AT> x[R][CH];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const int c = lane + 32 * i;
+                    if (c < hc) x[r][i].load(fbase + static_cast<long long>(t0 + r) * H + c * 8); else x[r][i].zero();
+                }
+            float ff[R];
+            for (int k = 0; k < K; ++k) {
+                const AT* kr = kw_idx ? kmat + static_cast<long long>(__ldg(kw_idx + inst)) * H : kmat + (static_cast<long long>(inst) * K + k) * H;
+                float yv[CH][8];
+                float kk = 0.f;
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const int c = lane + 32 * i;
+                    Raw8<AT> y;
+                    if (c < hc) y.load(kr + c * 8); else y.zero();
+                    y.unpack(yv[i]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) kk = fmaf(yv[i][j], yv[i][j], kk);
+                }
+                float dot[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float d = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        float xv[8];
+                        x[r][i].unpack(xv);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { d = fmaf(xv[j], yv[i][j], d); if (k == 0) s2 = fmaf(xv[j], xv[j], s2); }
+                    }
+                    dot[r] = d;
+                    if (k == 0) ff[r] = s2;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], o);
+                        if (k == 0) ff[r] += __shfl_xor_sync(0xffffffffu, ff[r], o);
+                    }
+                    kk += __shfl_xor_sync(0xffffffffu, kk, o);
+                }
+                const float nk = fmaxf(sqrtf(kk), 1e-8f);
+                float mine = 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (lane == r) mine = (dot[r] / (fmaxf(sqrtf(ff[r]), 1e-8f) * nk) + 1.0f) * 0.49f;
+                if (lane < R) att[(out_base + static_cast<long long>(inst) * K + k) * T + t0 + lane] = mine;      // one contiguous store of R results
+            }
+        }
+    }
+}
+
+static inline int inst_grid(int n) {                         // blocks of 8 warps, one instance per warp and iteration
+    int b = (n + 7) / 8;
+    if (b < 1) b = 1;
+    return b > 148 * 8 ? 148 * 8 : b;
+}
+#define DISPATCH_CH_ONLY(H, ...)                                                              \
+    do {                                                                                      \
+        const int hc__ = (H) / 8;                                                             \
+        if (hc__ <= 32) { constexpr int CH = 1, R = 8; __VA_ARGS__; }                         \
+        else if (hc__ <= 64) { constexpr int CH = 2, R = 4; __VA_ARGS__; }                    \
+        else { constexpr int CH = 4, R = 2; __VA_ARGS__; }                                    \
+    } while (0)
+
 int g_row_stream = 1;
+int g_cos_impl = 0;      // 0 = instance-major cosine maps when T % 8 == 0 (product); 1 = row-major cos_rows_kernel (comparison)
 
 int launch_cos_att(int dt, const void* f, const void* kmat, int K, int T, int H, float* att, long long out_base, int n, cudaStream_t st) {
     if (n <= 0) return STAIR_OK;
     if (H % 8 || H > 256 * MAXC) return STAIR_ERR_UNSUPPORTED;
     if (g_row_stream >= 2 && row_stream_ok(dt, K, T, H)) return launch_cos_stream(dt, f, nullptr, kmat, nullptr, K, T, H, att, out_base, n, st);
     const long long rows = static_cast<long long>(n) * T;
+    if (T % 8 == 0 && H <= 1024 && g_cos_impl == 0) {
+        DISPATCH_DT(dt, AT, DISPATCH_CH_ONLY(H, (cos_inst_kernel<AT, CH, R><<<inst_grid(n), 256, 0, st>>>(
+                                reinterpret_cast<const AT*>(f), nullptr, reinterpret_cast<const AT*>(kmat), nullptr, K, T, H, att, out_base, n))));
+        STAIR_CHECK_LAUNCH();
+        return STAIR_OK;
+    }
     DISPATCH_DT(dt, AT, DISPATCH_CH(H, (cos_rows_kernel<AT, CH, RPW><<<row_grid(rows, RPW), 256, 0, st>>>(
                             reinterpret_cast<const AT*>(f), nullptr, reinterpret_cast<const AT*>(kmat), nullptr, K, T, H, att, out_base, static_cast<int>(rows)))));
     STAIR_CHECK_LAUNCH();
@@ -306,6 +396,12 @@ int launch_existsframe(int dt, const void* vid, const int* feat_idx, const void*
     if (H % 8 || H > 256 * MAXC) return STAIR_ERR_UNSUPPORTED;
     if (g_row_stream >= 2 && row_stream_ok(dt, 1, T, H)) return launch_cos_stream(dt, vid, feat_idx, vec, kw_idx, 1, T, H, att, out_base, n, st);
     const long long rows = static_cast<long long>(n) * T;
+    if (T % 8 == 0 && H <= 1024 && g_cos_impl == 0) {
+        DISPATCH_DT(dt, AT, DISPATCH_CH_ONLY(H, (cos_inst_kernel<AT, CH, R><<<inst_grid(n), 256, 0, st>>>(
+                                reinterpret_cast<const AT*>(vid), feat_idx, reinterpret_cast<const AT*>(vec), kw_idx, 1, T, H, att, out_base, n))));
+        STAIR_CHECK_LAUNCH();
+        return STAIR_OK;
+    }
     DISPATCH_DT(dt, AT, DISPATCH_CH(H, (cos_rows_kernel<AT, CH, RPW><<<row_grid(rows, RPW), 256, 0, st>>>(
                             reinterpret_cast<const AT*>(vid), feat_idx, reinterpret_cast<const AT*>(vec), kw_idx, 1, T, H, att, out_base, static_cast<int>(rows)))));
     STAIR_CHECK_LAUNCH();
@@ -996,4 +1092,5 @@ extern "C" int stair_exists_frame(int dtype, const void* vid, const int32_t* fea
 extern "C" int stair_hasitem_tail(int dtype, const void* x, const float* w, const float* b, float* att, int out_base, int n, int T, int H, void* stream) {
     return launch_rowdot_sigmoid(dtype, x, w, b, att, out_base, n, T, H, reinterpret_cast<cudaStream_t>(stream));
 }
+extern "C" int stair_set_cos_impl(int impl) { g_cos_impl = impl ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_row_stream(int on) { g_row_stream = on < 0 ? 0 : (on > 2 ? 2 : on); return STAIR_OK; }
