@@ -291,15 +291,39 @@ __global__ void __launch_bounds__(256, 2) cos_rows_kernel(const AT* __restrict__
 // norm are loaded / reduced once per (instance, keyword) instead of once per frame row, |f_t|^2 once per frame instead of once per
 // (frame, keyword), and the 8 results of a pass leave as one 32-byte store: ~1.75x fewer instructions per row than cos_rows_kernel,
 // which was issue-bound at 44 % of the HBM roofline (profiles/r1_module_kernel_roofline.txt).
+// Reduce V per-lane partial sums over the warp with V/2 + V/4 + ... + 1 + (5 - log2 V) shuffles instead of 5 V: each exchange step
+// halves the number of live values per lane.  Returns, in every lane, the warp-wide sum of v[lane >> (5 - log2 V)].
+template <int V>
+__device__ __forceinline__ float warp_sum_multi(float (&v)[V], int lane) {
+    static_assert(V == 2 || V == 4 || V == 8 || V == 16, "power of two");
+    int bit = 16;
+#pragma unroll
+    for (int half = V / 2; half >= 1; half >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half], keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    for (; bit >= 1; bit >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
+    return v[0];
+}
+
 template <typename AT, int CH, int R>
 __global__ void __launch_bounds__(256, 2) cos_inst_kernel(const AT* __restrict__ f, const int* __restrict__ feat_idx, const AT* __restrict__ kmat,
                                                           const int* __restrict__ kw_idx, int K, int T, int H, float* __restrict__ att,
                                                           long long out_base, int n) {
+    constexpr int V = 2 * R, SH = R == 8 ? 1 : (R == 4 ? 2 : 3);       // values per reduction; lane >> SH = index of the value a lane ends up with
     const int lane = threadIdx.x & 31, hc = H / 8;
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const int my_r = (lane >> SH) & (R - 1);                            // frame row (within a pass) whose results this lane receives
+    const bool writer = (lane & 16) == 0 && (lane & ((1 << SH) - 1)) == 0;
     for (int inst = warp; inst < n; inst += nwarps) {
         const AT* fbase = feat_idx ? f + static_cast<long long>(__ldg(feat_idx + inst)) * T * H : f + static_cast<long long>(inst) * T * H;
+        float yv[CH][8];
+        float nk = 1.f;
         for (int t0 = 0; t0 < T; t0 += R) {
             Raw8<AT> x[R][CH];
 #pragma unroll
@@ -309,21 +333,23 @@ __global__ void __launch_bounds__(256, 2) cos_inst_kernel(const AT* __restrict__
                     const int c = lane + 32 * i;
                     if (c < hc) x[r][i].load(fbase + static_cast<long long>(t0 + r) * H + c * 8); else x[r][i].zero();
                 }
-            float ff[R];
+            float ff_mine = 0.f;
             for (int k = 0; k < K; ++k) {
-                const AT* kr = kw_idx ? kmat + static_cast<long long>(__ldg(kw_idx + inst)) * H : kmat + (static_cast<long long>(inst) * K + k) * H;
-                float yv[CH][8];
-                float kk = 0.f;
+                if (K > 1 || t0 == 0) {                                // one keyword: its row and norm are computed once per instance
+                    const AT* kr = kw_idx ? kmat + static_cast<long long>(__ldg(kw_idx + inst)) * H : kmat + (static_cast<long long>(inst) * K + k) * H;
+                    float kk = 0.f;
 #pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                    const int c = lane + 32 * i;
-                    Raw8<AT> y;
-                    if (c < hc) y.load(kr + c * 8); else y.zero();
-                    y.unpack(yv[i]);
+                    for (int i = 0; i < CH; ++i) {
+                        const int c = lane + 32 * i;
+                        Raw8<AT> y;
+                        if (c < hc) y.load(kr + c * 8); else y.zero();
+                        y.unpack(yv[i]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) kk = fmaf(yv[i][j], yv[i][j], kk);
+                        for (int j = 0; j < 8; ++j) kk = fmaf(yv[i][j], yv[i][j], kk);
+                    }
+                    nk = fmaxf(sqrtf(warp_sum(kk)), 1e-8f);
                 }
-                float dot[R];
+                float v[V];                                             // v[r] = dot(f_r, k), v[R + r] = |f_r|^2 (first keyword only)
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     float d = 0.f, s2 = 0.f;
@@ -334,24 +360,12 @@ __global__ void __launch_bounds__(256, 2) cos_inst_kernel(const AT* __restrict__
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { d = fmaf(xv[j], yv[i][j], d); if (k == 0) s2 = fmaf(xv[j], xv[j], s2); }
                     }
-                    dot[r] = d;
-                    if (k == 0) ff[r] = s2;
+                    v[r] = d; v[R + r] = s2;
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], o);
-                        if (k == 0) ff[r] += __shfl_xor_sync(0xffffffffu, ff[r], o);
-                    }
-                    kk += __shfl_xor_sync(0xffffffffu, kk, o);
-                }
-                const float nk = fmaxf(sqrtf(kk), 1e-8f);
-                float mine = 0.f;
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (lane == r) mine = (dot[r] / (fmaxf(sqrtf(ff[r]), 1e-8f) * nk) + 1.0f) * 0.49f;
-                if (lane < R) att[(out_base + static_cast<long long>(inst) * K + k) * T + t0 + lane] = mine;      // one contiguous store of R results
+                const float mine = warp_sum_multi<V>(v, lane);           // lanes < 16: dot of row my_r ; lanes >= 16: |f|^2 of row my_r
+                const float other = __shfl_xor_sync(0xffffffffu, mine, 16);
+                if (k == 0) ff_mine = other;
+                if (writer) att[(out_base + static_cast<long long>(inst) * K + k) * T + t0 + my_r] = (mine / (fmaxf(sqrtf(ff_mine), 1e-8f) * nk) + 1.0f) * 0.49f;
             }
         }
     }
