@@ -731,14 +731,11 @@ __global__ void rowdot_sigmoid_kernel(const AT* __restrict__ x, const float* __r
             }
             s[r] = a;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int r = 0; r < RPW; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
-        float mine = 0.f;
-#pragma unroll
-        for (int r = 0; r < RPW; ++r) if (lane == r) mine = s[r];
-        if (lane < RPW && row0 + lane < rows) att[out_off + row0 + lane] = sigmoidf_(mine + bias);       // one coalesced store per warp
+        // RPW sums with RPW/2 + ... + 1 + (5 - log2 RPW) shuffles; lane l ends up with the sum of row l >> SH
+        constexpr int SH = RPW == 8 ? 2 : (RPW == 4 ? 3 : 4);
+        const float mine = warp_sum_multi<RPW>(s, lane);
+        const int r = lane >> SH;
+        if ((lane & ((1 << SH) - 1)) == 0 && row0 + r < rows) att[out_off + row0 + r] = sigmoidf_(mine + bias);       // RPW consecutive floats per warp
     }
 }
 
