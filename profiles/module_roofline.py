@@ -14,7 +14,7 @@ T, H, K = 8, 512, 1
 pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
 PEAK = json.load(open(pk))['hbm_gbs'] if os.path.exists(pk) else 6650.0
 lib = L.lib()
-lib.stair_set_row_stream(int(os.environ.get('ROW_STREAM', 1)))     # HasItem tail: 1 = TMA-staged streaming kernel, 0 = register-staged
+lib.stair_set_row_stream(int(os.environ.get('ROW_STREAM', 0)))     # HasItem tail: 0 = register-staged kernel (product), 1 = TMA-staged streaming kernel
 lib.stair_set_cos_impl(int(os.environ.get('COS_IMPL', 0)))       # 0 = instance-major cosine maps (product), 1 = row-major
 dev = 'cuda'
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -67,7 +67,7 @@ bool row_stream_ok(int dt, int K, int T, int H);
 int launch_cos_stream(int dt, const void* f, const int* feat_idx, const void* kw, const int* kw_idx, int K, int T, int H, float* att,
                       long long out_base, int n, cudaStream_t st);
 int launch_rowdot_stream(int dt, const void* x, const float* w, const float* b, float* att, long long out_base, int n, int T, int H, cudaStream_t st);
-extern int g_row_stream;      // 0: register-staged kernels only; 1 (default): HasItem tail streams; 2: the cosine maps stream too (measured slower: their
+extern int g_row_stream;      // 0 (default): register-staged kernels only; 1: HasItem tail streams; 2: the cosine maps stream too (measured slower: their
                               // three reductions per 1 KB row are issue-bound, not bandwidth-bound)
 
 // ---- LSTM cells (gate order i,f,g,o; nn.LSTM, video_nmn/module_net.py:39-47) -------------------------------------
