@@ -1,0 +1,101 @@
+"""GPU edge cases and size-independent properties of the batched forward (through the C ABI).
+
+  * ragged / odd batches against the CPU oracle (fp32 strict): 1 question, batches that do not fill a 64-row recurrence block or a
+    128-row GEMM tile, one-word and 40-word questions, a batch of a single layout;
+  * at BASELINE.json's full size (4096 questions, H = 512, bf16): the results of a question do not depend on where it sits in the
+    batch (permutation invariance, bit-exact) nor on what it is batched with (split invariance, bit-exact);
+  * a batch larger than the executor's chunk caps (> 65 536 frame rows per group) equals its halves.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nmn_oracle as orc
+from stair_b200 import VideoNMN, collate, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _with_length(d, L, rng):
+    d = dict(d)
+    d['question'] = torch.from_numpy((rng.standard_normal((L, d['question'].shape[1])) * 0.4).astype(np.float32))
+    spans = {}
+    for i in d['prog_str_to_question_tokens']:
+        w = int(rng.integers(1, min(3, L) + 1))
+        s = int(rng.integers(0, L - w + 1))
+        spans[i] = (s, s + w)
+    d['prog_str_to_question_tokens'] = spans
+    return d
+
+
+@pytest.mark.parametrize('B', [1, 3, 65, 129])
+def test_odd_batches_and_extreme_question_lengths_against_oracle(B):
+    T, V, hid = 8, 192, 128
+    cfg = syn.model_config(T=T, V=V, hidden=hid, object_types=16)
+    torch.manual_seed(B)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
+    weights = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    rng = np.random.default_rng(100 + B)
+    qs = syn.make_questions(B, T, V, seed=B, templates=list(syn.ALL_TEMPLATES), object_types=16)
+    qs = [_with_length(d, (1, 40, 2, 25)[i % 4], rng) if i % 2 == 0 else d for i, d in enumerate(qs)]     # 1-word and 40-word questions
+    oracle = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES)
+    with torch.no_grad():
+        want = torch.stack([oracle(d, return_res_by_step=False, test_mode=True)['logits'] for d in qs])
+    model = model.cuda().eval()
+    out = model(qs, return_res_by_step=False, test_mode=True)
+    torch.cuda.synchronize()
+    model.check_status(out['state'])
+    got = out['logits'].cpu()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-4 * max(1.0, float(want.abs().max()))
+    assert torch.equal(out['answers'].cpu().long(), want.argmax(1))
+
+
+def test_single_layout_batch_and_single_dict():
+    T, V, hid = 8, 128, 64
+    cfg = syn.model_config(T=T, V=V, hidden=hid, object_types=16)
+    torch.manual_seed(0)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32').cuda().eval()
+    qs = syn.make_questions(70, T, V, seed=3, templates=['xor_between'], object_types=16)
+    batched = model(qs, return_res_by_step=False, test_mode=True)['logits']
+    single = torch.stack([model(d, return_res_by_step=False, test_mode=True)['logits'] for d in qs[:5]])
+    torch.testing.assert_close(batched[:5], single, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        collate([])
+
+
+def test_full_size_permutation_and_split_invariance():
+    """BASELINE configs[1] size.  A question's logits are bit-identical wherever it sits in the batch and whatever it is batched with."""
+    B, T, V = 4096, 8, 4096
+    cfg = syn.model_config(T=T, V=V)
+    torch.manual_seed(0)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().eval()
+    qs = syn.make_questions(B, T, V, seed=1234)
+    base = model(qs, return_res_by_step=False, test_mode=True)
+    torch.cuda.synchronize()
+    model.check_status(base['state'])
+    logits, answers = base['logits'].clone(), base['answers'].clone()
+    assert bool(torch.isfinite(logits).all())
+    assert torch.equal(answers.long(), logits.argmax(1))
+    perm = torch.from_numpy(np.random.default_rng(5).permutation(B))
+    out_p = model([qs[i] for i in perm.tolist()], return_res_by_step=False, test_mode=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out_p['logits'], logits[perm.cuda()])
+    assert torch.equal(out_p['answers'], answers[perm.cuda()])
+    parts = [model(qs[a:b], return_res_by_step=False, test_mode=True)['logits'].clone() for a, b in ((0, 1000), (1000, 1001), (1001, B))]
+    assert torch.equal(torch.cat(parts), logits)
+
+
+def test_batch_beyond_the_chunk_caps_equals_its_halves():
+    """9000 questions of one 12-module layout: every group exceeds the 65 536-frame-row chunk cap of the executor."""
+    B, T, V, hid = 9000, 8, 128, 128
+    cfg = syn.model_config(T=T, V=V, hidden=hid, object_types=16)
+    torch.manual_seed(1)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().eval()
+    qs = syn.make_questions(B, T, V, seed=8, templates=['xor_between', 'compare'], object_types=16)
+    whole = model(qs, return_res_by_step=False, test_mode=True)
+    torch.cuda.synchronize()
+    model.check_status(whole['state'])
+    logits = whole['logits'].clone()
+    halves = [model(qs[a:b], return_res_by_step=False, test_mode=True)['logits'].clone() for a, b in ((0, 4500), (4500, B))]
+    assert torch.equal(torch.cat(halves), logits)
