@@ -470,6 +470,7 @@ static int g_gemm_impl = 0;      // 0 = tcgen05 (product), 1 = SIMT debug kernel
 static int g_epilogue_impl = 0;  // 0 = staged TMA-store epilogue, 1 = direct per-row stores (debug / comparison)
 static int* g_err_flag = nullptr;
 static int g_num_sms = 0;
+static int g_dw_wide = 0;        // 1 = 128 x 256 tiles for MN-major (weight-gradient) GEMMs (measured slower: 33.4 vs 30.7 us, profiles/micro_dw.py)
 static int g_split_k = 1;        // 1 = split-K for accumulating GEMMs with few output tiles (weight gradients)
 static unsigned long long* g_dbg = nullptr;
 
@@ -548,7 +549,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     const uint64_t a_rows = static_cast<uint64_t>(a.nplanes - 1) * a.a_plane_rows + a.M;
     const uint64_t w_rows = static_cast<uint64_t>(a.nplanes - 1) * a.w_plane_rows + a.N;
     const int tiles128 = ceil_div(a.M, BM) * ceil_div(a.N, 128);
-    const int bn = a.N <= 64 ? 64 : ((a.N % 256 == 0 && tiles128 >= 2 * g_num_sms) ? 256 : 128);
+    // wide tiles when there are plenty of them.  The weight-gradient contraction (16 output tiles, K ~ 20 000 split over all SMs) is bound
+    // by L2 -> SM operand traffic (every 128-column operand slice is re-read by 4 tiles: 160 MB for 40 MB of operands, ~6 TB/s); 128 x 256
+    // tiles move 25 % fewer bytes but double the same-address atomics of the split-K epilogue and measured slower (g_dw_wide).
+    const int bn = a.N <= 64 ? 64 : ((a.N % 256 == 0 && (tiles128 >= 2 * g_num_sms || (a.mn_major && g_dw_wide))) ? 256 : 128);
     CUtensorMap ta, tb;
     int rc;
     if (a.mn_major) {
@@ -577,6 +581,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
 using namespace stair;
 
 extern "C" int stair_set_gemm_impl(int impl) { g_gemm_impl = impl; return STAIR_OK; }
+extern "C" int stair_set_gemm_dw_wide(int on) { g_dw_wide = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_split_k(int on) { g_split_k = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_gemm_debug_timeline(unsigned long long* dev_buf) { g_dbg = dev_buf; return STAIR_OK; }
 extern "C" int stair_set_gemm_epilogue(int impl) { g_epilogue_impl = impl; return STAIR_OK; }
