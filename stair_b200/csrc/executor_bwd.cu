@@ -407,36 +407,41 @@ int encoders_bwd(BCtx& b) {
         const bf16* hs = reinterpret_cast<const bf16*>(sv + SL.enc[e].hs);
         const long long hs_dir = static_cast<long long>(S + 1) * B * h, hs_plane = 2 * hs_dir;
         float* dxproj = b.ws.take<float>(io.rows * 8 * h);
-        float* dg_hist = b.ws.take<float>(2LL * S * B * 4 * h);               // [2][S][B][4h]
-        const long long dg_dir = static_cast<long long>(S) * B * 4 * h;
-        bf16* dg_planes = b.ws.take<bf16>(static_cast<long long>(c.np) * 2 * B * 4 * h);
+        const long long dg_dir = static_cast<long long>(S) * B * 4 * h, dg_plane = 2 * dg_dir;
+        bf16* dg_hist = b.ws.take<bf16>(static_cast<long long>(c.np) * dg_plane);     // gate gradients, bf16 planes [np][2][S][B][4h]
         float* dh_rec = b.ws.take<float>(2LL * B * h);
         float* dc = b.ws.take<float>(2LL * B * h);
         const float* dout = e == 0 ? tr.dvid : tr.dtokfeat;
         for (int s = S - 1; s >= 0; --s) {
+            bf16* dg_step = dg_hist + static_cast<long long>(s) * B * 4 * h;
             const float* c_prev = s > 0 ? cs + static_cast<long long>(s - 1) * 2 * B * h : cs;
             if (blocked)
-                RUN(launch_lstm_cell_bwd(gates, nullptr, cs, dout, dh_rec, e == 1 ? tr.dqfeat : nullptr, dc, dg_hist + static_cast<long long>(s) * B * 4 * h,
-                                         dg_dir, dg_planes, 2LL * B * 4 * h, c.np, dxproj, io.q_off, B, c.T, h, s, S - 1, 1, c.st));
+                RUN(launch_lstm_cell_bwd(gates, nullptr, cs, dout, dh_rec, e == 1 ? tr.dqfeat : nullptr, dc, dg_dir, dg_step, dg_plane, c.np, dxproj,
+                                         io.q_off, B, c.T, h, s, S - 1, 1, c.st));
             else
-            RUN(launch_lstm_cell_bwd(gates + static_cast<long long>(s) * 2 * B * 4 * h, c_prev, cs + static_cast<long long>(s) * 2 * B * h, dout, dh_rec,
-                                     e == 1 ? tr.dqfeat : nullptr, dc, dg_hist + static_cast<long long>(s) * B * 4 * h, dg_dir, dg_planes,
-                                     2LL * B * 4 * h, c.np, dxproj, io.q_off, B, c.T, h, s, S - 1, 0, c.st));
+                RUN(launch_lstm_cell_bwd(gates + static_cast<long long>(s) * 2 * B * 4 * h, c_prev, cs + static_cast<long long>(s) * 2 * B * h, dout, dh_rec,
+                                         e == 1 ? tr.dqfeat : nullptr, dc, dg_dir, dg_step, dg_plane, c.np, dxproj, io.q_off, B, c.T, h, s, S - 1, 0, c.st));
             if (s > 0)
                 for (int d = 0; d < 2; ++d) {
                     const int wid = d == 0 ? io.whh_f : io.whh_r;
                     if (!m.wt[wid]) return STAIR_ERR_ARG;
                     GemmArgs r;
-                    r.A = dg_planes + static_cast<long long>(d) * B * 4 * h; r.lda = 4 * h; r.a_plane_rows = 2 * B; r.nplanes = c.np;
+                    r.A = dg_step + d * dg_dir; r.lda = 4 * h; r.a_plane_rows = static_cast<int>(dg_plane / (4 * h)); r.nplanes = c.np;
                     r.W = m.wt[wid]; r.ldw = 4 * h; r.w_plane_rows = h; r.C = dh_rec + static_cast<long long>(d) * B * h; r.ldc = h;
                     r.out_dtype = STAIR_F32; r.M = B; r.N = h; r.K = 4 * h;
                     RUN(launch_gemm(r, c.st));
                 }
         }
-        // dW_hh[d] += sum_s dG[d][s]^T h[d][s-1]   (one contraction over all (step, question) rows per direction)
-        for (int d = 0; d < 2; ++d)
-            STAIR_TRY(linear_bwd(b, dg_hist + d * dg_dir, 4 * h, nullptr, 0, nullptr, hs + d * hs_dir, hs_plane / h, S * B, 4 * h, h,
-                                 d == 0 ? io.whh_f : io.whh_r, -1, nullptr));
+        // dW_hh[d] += sum_s dG[d][s]^T h[d][s-1]: one contraction over all (step, question) rows per direction, both operands in place
+        for (int d = 0; d < 2; ++d) {
+            float* gW = G(b, d == 0 ? io.whh_f : io.whh_r);
+            if (!gW) continue;
+            GemmArgs a;
+            a.A = dg_hist + d * dg_dir; a.lda = 4 * h; a.a_plane_rows = static_cast<int>(dg_plane / (4 * h)); a.nplanes = c.np;
+            a.W = hs + d * hs_dir; a.ldw = h; a.w_plane_rows = static_cast<int>(hs_plane / h);
+            a.C = gW; a.ldc = h; a.out_dtype = STAIR_F32; a.M = 4 * h; a.N = h; a.K = S * B; a.accumulate = 1; a.mn_major = 1;
+            RUN(launch_gemm(a, c.st));
+        }
         // dW_ih, d(b_ih + b_hh) from the gate gradients of every frame / token
         {
             const bool direct = e == 0 && bt.video_dtype == STAIR_BF16 && c.np == 1 && (m.V % 8) == 0;

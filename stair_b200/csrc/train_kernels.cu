@@ -449,67 +449,88 @@ int launch_existsframe_bwd(int dt, const void* vid, const int* feat_idx, const v
 struct RelateBwdParams { const float* p[6]; float* d[6]; };
 
 __global__ void temporal_relate_bwd_kernel(const float* __restrict__ att, const int* __restrict__ att_idx, int K, int mode, int conv_k,
-                                           RelateBwdParams rp, const float* __restrict__ dr, float* __restrict__ datt, int n, int T) {
+                                           RelateBwdParams rp, const float* __restrict__ dr, float* __restrict__ datt, int n, int T, int wsz) {
     extern __shared__ float sm[];
     float* act[4] = {sm, sm + T, sm + 2 * T, sm + 3 * T};       // a0 (mean), a1, a2, r
     float* dz = sm + 4 * T;                                     // gradient wrt the current layer's pre-activation
     float* da = sm + 5 * T;
-    const int i = blockIdx.x, t = threadIdx.x;
-    const long long r0 = __ldg(att_idx + i);
-    if (t < T) {
-        float s = 0.f;
-        for (int k = 0; k < K; ++k) s += att[(r0 + k) * T + t];
-        act[0][t] = s / static_cast<float>(K);
-    }
+    // parameter gradients of the block's instances accumulate in shared memory (thread t owns row t of every dW / element t of db,
+    // so no conflicts) and are added to the global gradient once per block: per-instance atomics put n x (T*T + T) x 3 same-address
+    // atomics on 216 addresses, which serialise in L2
+    float* accw = sm + 6 * T;                                   // [3][wsz]
+    float* accb = accw + 3 * wsz;                               // [3][T]
+    const int t = threadIdx.x;
+    for (int j = t; j < 3 * wsz + 3 * T; j += blockDim.x) accw[j] = 0.f;
     __syncthreads();
-    if (mode == 0) {
-        if (t < T) { const float g = dr[static_cast<long long>(i) * T + t] / K; for (int k = 0; k < K; ++k) atomicAdd(datt + (r0 + k) * T + t, g); }
-        return;
-    }
-    for (int layer = 0; layer < 3; ++layer) {
-        const float* w = rp.p[2 * layer]; const float* b = rp.p[2 * layer + 1];
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const long long r0 = __ldg(att_idx + i);
         if (t < T) {
-            float y;
-            if (conv_k == 0) {
-                y = __ldg(b + t);
-                for (int u = 0; u < T; ++u) y += __ldg(w + t * T + u) * act[layer][u];
-            } else {
-                const int k = layer < 2 ? conv_k : 2 * conv_k + 1, left = (k - 1) / 2;
-                y = __ldg(b);
-                for (int j = 0; j < k; ++j) { const int u = t + j - left; if (u >= 0 && u < T) y += __ldg(w + j) * act[layer][u]; }
-            }
-            act[layer + 1][t] = layer < 2 ? fmaxf(y, 0.f) : sigmoidf_(y);
+            float s = 0.f;
+            for (int k = 0; k < K; ++k) s += att[(r0 + k) * T + t];
+            act[0][t] = s / static_cast<float>(K);
         }
         __syncthreads();
-    }
-    if (t < T) { const float r = act[3][t]; dz[t] = dr[static_cast<long long>(i) * T + t] * r * (1.f - r); }
-    __syncthreads();
-    for (int layer = 2; layer >= 0; --layer) {
-        const float* w = rp.p[2 * layer];
-        float* dw = rp.d[2 * layer]; float* db = rp.d[2 * layer + 1];
-        if (t < T) {
-            float g = 0.f;                                       // d/d act[layer][t]
+        if (mode == 0) {
+            if (t < T) { const float g = dr[static_cast<long long>(i) * T + t] / K; for (int k = 0; k < K; ++k) atomicAdd(datt + (r0 + k) * T + t, g); }
+            __syncthreads();
+            continue;
+        }
+        for (int layer = 0; layer < 3; ++layer) {
+            const float* w = rp.p[2 * layer]; const float* b = rp.p[2 * layer + 1];
+            if (t < T) {
+                float y;
+                if (conv_k == 0) {
+                    y = __ldg(b + t);
+                    for (int u = 0; u < T; ++u) y += __ldg(w + t * T + u) * act[layer][u];
+                } else {
+                    const int k = layer < 2 ? conv_k : 2 * conv_k + 1, left = (k - 1) / 2;
+                    y = __ldg(b);
+                    for (int j = 0; j < k; ++j) { const int u = t + j - left; if (u >= 0 && u < T) y += __ldg(w + j) * act[layer][u]; }
+                }
+                act[layer + 1][t] = layer < 2 ? fmaxf(y, 0.f) : sigmoidf_(y);
+            }
+            __syncthreads();
+        }
+        if (t < T) { const float r = act[3][t]; dz[t] = dr[static_cast<long long>(i) * T + t] * r * (1.f - r); }
+        __syncthreads();
+        for (int layer = 2; layer >= 0; --layer) {
+            const float* w = rp.p[2 * layer];
+            float* aw = accw + layer * wsz; float* ab = accb + layer * T;
             if (conv_k == 0) {
-                for (int o = 0; o < T; ++o) g += __ldg(w + o * T + t) * dz[o];
-                const float d = dz[t];
-                if (d != 0.f) { for (int u = 0; u < T; ++u) atomicAdd(dw + t * T + u, d * act[layer][u]); atomicAdd(db + t, d); }
+                if (t < T) {
+                    float g = 0.f;                               // d/d act[layer][t]
+                    for (int o = 0; o < T; ++o) g += __ldg(w + o * T + t) * dz[o];
+                    const float d = dz[t];
+                    if (d != 0.f) { for (int u = 0; u < T; ++u) aw[t * T + u] += d * act[layer][u]; ab[t] += d; }
+                    da[t] = g;
+                }
             } else {
                 const int k = layer < 2 ? conv_k : 2 * conv_k + 1, left = (k - 1) / 2;
-                for (int j = 0; j < k; ++j) { const int o = t - j + left; if (o >= 0 && o < T) g += __ldg(w + j) * dz[o]; }
+                if (t < T) {
+                    float g = 0.f;
+                    for (int j = 0; j < k; ++j) { const int o = t - j + left; if (o >= 0 && o < T) g += __ldg(w + j) * dz[o]; }
+                    da[t] = g;
+                }
                 if (t < k) {                                     // thread j = t accumulates dw[j] over positions
                     float s = 0.f;
                     for (int o = 0; o < T; ++o) { const int u = o + t - left; if (u >= 0 && u < T) s += dz[o] * act[layer][u]; }
-                    atomicAdd(dw + t, s);
+                    aw[t] += s;
                 }
-                if (t == 0) { float s = 0.f; for (int o = 0; o < T; ++o) s += dz[o]; atomicAdd(db, s); }
+                if (t == 0) { float s = 0.f; for (int o = 0; o < T; ++o) s += dz[o]; ab[0] += s; }
             }
-            da[t] = g;
+            __syncthreads();
+            if (t < T) dz[t] = layer > 0 ? (act[layer][t] > 0.f ? da[t] : 0.f) : da[t];     // ReLU of the previous layer
+            __syncthreads();
         }
-        __syncthreads();
-        if (t < T) dz[t] = layer > 0 ? (act[layer][t] > 0.f ? da[t] : 0.f) : da[t];     // ReLU of the previous layer
+        if (t < T) { const float g = dz[t] / K; for (int k = 0; k < K; ++k) atomicAdd(datt + (r0 + k) * T + t, g); }
         __syncthreads();
     }
-    if (t < T) { const float g = dz[t] / K; for (int k = 0; k < K; ++k) atomicAdd(datt + (r0 + k) * T + t, g); }
+    if (mode == 0) return;
+    for (int layer = 0; layer < 3; ++layer) {
+        const int nw = conv_k == 0 ? T * T : (layer < 2 ? conv_k : 2 * conv_k + 1), nb = conv_k == 0 ? T : 1;
+        for (int j = t; j < nw; j += blockDim.x) { const float v = accw[layer * wsz + j]; if (v != 0.f) atomicAdd(rp.d[2 * layer] + j, v); }
+        for (int j = t; j < nb; j += blockDim.x) { const float v = accb[layer * T + j]; if (v != 0.f) atomicAdd(rp.d[2 * layer + 1] + j, v); }
+    }
 }
 
 int launch_temporal_relate_bwd(const float* att, const int* att_idx, int K, int mode, int conv_k, const float* const* params, float* const* dparams,
@@ -520,7 +541,11 @@ int launch_temporal_relate_bwd(const float* att, const int* att_idx, int K, int 
     for (int j = 0; j < 6; ++j) { rp.p[j] = params ? params[j] : nullptr; rp.d[j] = dparams ? dparams[j] : nullptr; }
     int threads = ((T + 31) / 32) * 32;
     if (conv_k && threads < 2 * conv_k + 1) threads = ((2 * conv_k + 1 + 31) / 32) * 32;
-    temporal_relate_bwd_kernel<<<n, threads, 6 * T * sizeof(float), st>>>(att, att_idx, K, mode, conv_k, rp, dr, datt, n, T);
+    const int wsz = conv_k == 0 ? T * T : 2 * conv_k + 1;
+    if (conv_k == 0 && T > 64) return STAIR_ERR_UNSUPPORTED;      // Linear(T,T) mode exists only for T_max <= 32 (modules.py:267)
+    const size_t smem = (6 * T + 3 * wsz + 3 * T) * sizeof(float);
+    const int grid = n < 148 * 4 ? n : 148 * 4;
+    temporal_relate_bwd_kernel<<<grid, threads, smem, st>>>(att, att_idx, K, mode, conv_k, rp, dr, datt, n, T, wsz);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -540,32 +565,57 @@ int launch_bcast_T(const float* dagg, float* dx, int n, int T, int H, cudaStream
 }
 
 // FilterFrame.attention backward: a = sigmoid(w_x.x + w_k.kw + b)
+constexpr int FFA_MAXC = 32;       // columns per lane: H <= 1024
 template <typename AT>
 __global__ void ff_attn_bwd_kernel(const AT* __restrict__ x, const AT* __restrict__ vec, const int* __restrict__ kw_idx, const float* __restrict__ w,
                                    const float* __restrict__ a, const float* __restrict__ da, float* __restrict__ dx, float* __restrict__ dvec,
                                    float* __restrict__ dw, float* __restrict__ db, long long rows, int T, int H) {
-    const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    for (long long row = blockIdx.x * static_cast<long long>(warps) + (threadIdx.x >> 5); row < rows; row += static_cast<long long>(gridDim.x) * warps) {
+    // the gradient of the 2H attention weights is a sum over ALL rows: it is accumulated in registers across a warp's rows, reduced over
+    // the block's warps in shared memory and added once per block (per-row atomics = rows x 2H same-address atomics on 2H addresses)
+    __shared__ float red[8][FFA_MAXC * 32];
+    const int warps = blockDim.x >> 5, lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    float gx[FFA_MAXC], gk[FFA_MAXC];
+#pragma unroll
+    for (int q = 0; q < FFA_MAXC; ++q) { gx[q] = 0.f; gk[q] = 0.f; }
+    float gb = 0.f;
+    for (long long row = blockIdx.x * static_cast<long long>(warps) + wi; row < rows; row += static_cast<long long>(gridDim.x) * warps) {
         const float av = a[row];
         const float s = da[row] * av * (1.f - av);
         if (s == 0.f) continue;
         const long long ko = static_cast<long long>(__ldg(kw_idx + row / T)) * H;
-        for (int c = lane; c < H; c += 32) {
-            dx[row * H + c] += s * __ldg(w + c);
-            atomicAdd(dvec + ko + c, s * __ldg(w + H + c));
-            atomicAdd(dw + c, s * ld1<AT>(x + row * H + c));
-            atomicAdd(dw + H + c, s * ld1<AT>(vec + ko + c));
+#pragma unroll
+        for (int q = 0; q < FFA_MAXC; ++q) {
+            const int c = lane + 32 * q;
+            if (c < H) {
+                dx[row * H + c] += s * __ldg(w + c);
+                atomicAdd(dvec + ko + c, s * __ldg(w + H + c));
+                gx[q] = fmaf(s, ld1<AT>(x + row * H + c), gx[q]);
+                gk[q] = fmaf(s, ld1<AT>(vec + ko + c), gk[q]);
+            }
         }
-        if (lane == 0) atomicAdd(db, s);
+        gb += s;
     }
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int q = 0; q < FFA_MAXC; ++q) { const int c = lane + 32 * q; if (c < H) red[wi][c] = pass == 0 ? gx[q] : gk[q]; }
+        __syncthreads();
+        for (int c = threadIdx.x; c < H; c += blockDim.x) {
+            float t = 0.f;
+            for (int w2 = 0; w2 < warps; ++w2) t += red[w2][c];
+            if (t != 0.f) atomicAdd(dw + pass * H + c, t);
+        }
+        __syncthreads();
+    }
+    if (lane == 0 && gb != 0.f) atomicAdd(db, gb);
 }
 
 int launch_ff_attn_bwd(int dt, const void* x, const void* vec, const int* kw_idx, const float* w, const float* a, const float* da, float* dx,
                        float* dvec, float* dw, float* db, int n, int T, int H, cudaStream_t st) {
     if (n <= 0) return STAIR_OK;
+    if (H > 32 * FFA_MAXC) return STAIR_ERR_UNSUPPORTED;
     const long long rows = static_cast<long long>(n) * T;
-    DISPATCH_DT(dt, AT, (ff_attn_bwd_kernel<AT><<<nblocks(rows, 8), 256, 0, st>>>(reinterpret_cast<const AT*>(x), reinterpret_cast<const AT*>(vec), kw_idx, w, a, da,
-                                                                                  dx, dvec, dw, db, rows, T, H)));
+    DISPATCH_DT(dt, AT, (ff_attn_bwd_kernel<AT><<<nblocks(rows, 8, 148 * 2), 256, 0, st>>>(reinterpret_cast<const AT*>(x), reinterpret_cast<const AT*>(vec), kw_idx, w, a, da,
+                                                                                           dx, dvec, dw, db, rows, T, H)));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -1144,7 +1194,7 @@ int launch_lstm_cell_train(int xdt, const void* xproj, const float* g, const flo
 // One BPTT step of both directions.  dout rows = gradient of the encoder output (video: dvid slot rows; text: dtokfeat rows).
 __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
                                      const float* __restrict__ dout, const float* __restrict__ dh_rec, const float* __restrict__ dqfeat,
-                                     float* __restrict__ dc, float* __restrict__ dgates, long long dg_dir, bf16* __restrict__ dg_planes, long long dg_plane, int nplanes,
+                                     float* __restrict__ dc, long long dg_dir, bf16* __restrict__ dg_planes, long long dg_plane, int nplanes,
                                      float* __restrict__ dxproj, const int* __restrict__ q_off, int B, int T, int h, int step, int last_step, int blocked) {
     const long long total = 2LL * B * h;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1188,21 +1238,22 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const floa
         } else {
             dc[si] = 0.f;
         }
-        float* dgh = dgates + static_cast<long long>(d) * dg_dir + static_cast<long long>(b) * 4 * h + j;        // direction-major history
-        dgh[0] = dpi; dgh[h] = dpf; dgh[2 * h] = dpg; dgh[3 * h] = dpo;
-        store_planes1(dpi, dg_planes + gi, dg_plane, nplanes);
-        store_planes1(dpf, dg_planes + gi + h, dg_plane, nplanes);
-        store_planes1(dpg, dg_planes + gi + 2 * h, dg_plane, nplanes);
-        store_planes1(dpo, dg_planes + gi + 3 * h, dg_plane, nplanes);
+        // gate gradients of this step as bf16 planes, written straight into the direction-major history [np][2][S][B][4h]: the step's
+        // slice is the A operand of the recurrent GEMM (dh = dG . W_hh) and the whole history the MN-major operand of dW_hh += dG^T . h
+        bf16* dgp = dg_planes + static_cast<long long>(d) * dg_dir + static_cast<long long>(b) * 4 * h + j;
+        store_planes1(dpi, dgp, dg_plane, nplanes);
+        store_planes1(dpf, dgp + h, dg_plane, nplanes);
+        store_planes1(dpg, dgp + 2 * h, dg_plane, nplanes);
+        store_planes1(dpo, dgp + 3 * h, dg_plane, nplanes);
     }
 }
 
 int launch_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_cur, const float* dout, const float* dh_rec, const float* dqfeat,
-                         float* dc, float* dgates, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, const int* q_off,
+                         float* dc, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, const int* q_off,
                          int B, int T, int h, int step, int last_step, int blocked, cudaStream_t st) {
     if (B <= 0) return STAIR_OK;
     if (blocked && (h % 8)) return STAIR_ERR_ARG;
-    lstm_cell_bwd_kernel<<<nblocks(2LL * B * h, 256), 256, 0, st>>>(gates, c_prev, c_cur, dout, dh_rec, dqfeat, dc, dgates, dg_dir, dg_planes, dg_plane, nplanes,
+    lstm_cell_bwd_kernel<<<nblocks(2LL * B * h, 256), 256, 0, st>>>(gates, c_prev, c_cur, dout, dh_rec, dqfeat, dc, dg_dir, dg_planes, dg_plane, nplanes,
                                                                    dxproj, q_off, B, T, h, step, last_step, blocked);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;

@@ -72,12 +72,13 @@ __host__ __device__ static inline long long lstm_hist_c_off(int step, int d, int
 int launch_lstm_cell_train(int xdt, const void* xproj, const float* g, const float* c_prev, float* c_out, float* gates_out, bf16* hstate_out,
                            const bf16* hstate_prev, long long hs_plane, long long hs_dir, int nplanes, int odt, void* out, void* qfeat, const int* q_off,
                            int B, int T, int h, int step, cudaStream_t st);
-// one BPTT step: dh = dout(row) + dh_rec (+ dqfeat at a question's last step); writes the gate pre-activation gradients as
-// fp32 [2][B][4h], as bf16 planes (A operand of the recurrent GEMM) and into the dxproj row; updates dc in place.
+// one BPTT step: dh = dout(row) + dh_rec (+ dqfeat at a question's last step); writes the gate pre-activation gradients as bf16 planes
+// into the step's slice of the direction-major history (dg_planes + d*dg_dir + b*4h, plane stride dg_plane) and as fp32 into the dxproj
+// row; updates dc in place.
 // blocked = 0: gates / c_prev / c_cur point at step `step`'s row-major slices ([2][B][4h], [2][B][h]; c_prev at step-1's);
 // blocked = 1: gates / c_cur are the BASE of the blocked history (lstm_hist_*_off), c_prev is ignored.
 int launch_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_cur, const float* dout, const float* dh_rec, const float* dqfeat,
-                         float* dc, float* dgates, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, const int* q_off,
+                         float* dc, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, const int* q_off,
                          int B, int T, int h, int step, int last_step, int blocked, cudaStream_t st);
 
 int launch_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, float b1, float b2, float eps, cudaStream_t st);
