@@ -190,6 +190,10 @@ typedef struct StairTrain {
      * Counter-based masks keyed by (dropout_seed, site, global row, column); stair_nmn_backward must receive the same p and seed
      * as the stair_nmn_forward_train it follows.  0 = no dropout (eval semantics). */
     float dropout_p; uint64_t dropout_seed;
+    /* optional: >= stair_train_act_bytes bytes in which stair_nmn_forward_train keeps every group chunk's module intermediates, so that
+     * stair_nmn_backward reads them back instead of re-running the chunk's forward (NULL = recompute; HBM is 180 GB, a 4096-question
+     * window needs ~3 GB) */
+    void* act_saved; int64_t act_saved_bytes;
 } StairTrain;
 
 /* Host evaluation (no GPU work) of the dropout mask of site `site` (a STAIR_W_* id of the Linear the Dropout follows) for the
@@ -247,6 +251,7 @@ int stair_nmn_forward(const StairModel* model /*HOST*/, const StairBatch* batch 
 /* Training: forward that keeps the encoder history, then losses + backward into StairTrain.grad (gradients ACCUMULATE; the
  * caller zeroes them).  Module intermediates are recomputed per group in the backward pass instead of being stored. */
 int64_t stair_train_saved_bytes(const StairModel* model /*HOST*/, const StairBatch* batch /*HOST*/);
+int64_t stair_train_act_bytes(const StairModel* model /*HOST*/, const StairBatch* batch /*HOST*/, const StairBuffers* buf /*HOST*/);
 int64_t stair_train_workspace_bytes(const StairModel* model /*HOST*/, const StairBatch* batch /*HOST*/, const StairBuffers* buf /*HOST*/,
                                     const StairTrain* train /*HOST*/);
 int stair_nmn_forward_train(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, void* stream);

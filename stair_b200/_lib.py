@@ -85,7 +85,7 @@ class StairTrain(ctypes.Structure):
                 ('answer', vp), ('dec_w', ctypes.c_float), ('loss', vp),
                 ('dvid', vp), ('dvec', vp), ('datt', vp), ('dtokfeat', vp), ('dqfeat', vp), ('dlogits', vp),
                 ('saved', vp), ('saved_bytes', i64), ('workspace', vp), ('workspace_bytes', i64),
-                ('dropout_p', ctypes.c_float), ('dropout_seed', ctypes.c_uint64)]
+                ('dropout_p', ctypes.c_float), ('dropout_seed', ctypes.c_uint64), ('act_saved', vp), ('act_saved_bytes', i64)]
 
 
 class StairAdamSeg(ctypes.Structure):
@@ -115,6 +115,7 @@ def lib():
         _lib.stair_last_launch_count.restype = i64
         _lib.stair_train_saved_bytes.restype = i64
         _lib.stair_train_workspace_bytes.restype = i64
+        _lib.stair_train_act_bytes.restype = i64
     return _lib
 
 

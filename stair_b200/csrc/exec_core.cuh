@@ -82,6 +82,10 @@ struct Ctx {
     float drop_p = 0.0f;
     unsigned long long drop_seed = 0;
     DropSpec pending;
+    // training with saved module activations: chunk k of the schedule (groups in order, chunks of a group in order) keeps its scratch
+    // (S0/S1/S2/VP/V0/...) at act_base + k * plan.mod_bytes instead of the shared per-lane scratch, so the backward reads it back
+    // instead of re-running the chunk's forward
+    char* act_base = nullptr;
 
     template <typename P> P* at(long long off) const { return reinterpret_cast<P*>(ws + off); }
     const void* W(int id) const { return m.w[id]; }
@@ -360,11 +364,26 @@ inline bool op_is_vid_sized(int op) {
     }
 }
 
-inline int run_group(Ctx& c, const StairGroup& g) {
-    const int cap = op_is_vid_sized(g.op) ? c.plan.nc_vid : static_cast<int>(VEC_CAP);
-    for (int done = 0; done < g.count; done += cap) {
+inline int group_cap(const Ctx& c, const StairGroup& g) { return op_is_vid_sized(g.op) ? c.plan.nc_vid : static_cast<int>(VEC_CAP); }
+inline long long group_chunks(const Ctx& c, const StairGroup& g) { const int cap = group_cap(c, g); return (g.count + cap - 1) / cap; }
+// index of the first chunk of group gi in schedule order (saved-activation slots)
+inline long long chunk_base(const Ctx& c, int gi) {
+    long long k = 0;
+    for (int g = 0; g < gi; ++g) k += group_chunks(c, c.b.groups[g]);
+    return k;
+}
+inline long long total_chunks(const Ctx& c) { return chunk_base(c, c.b.n_groups); }
+
+inline int run_group(Ctx& c, const StairGroup& g, int gi) {
+    const int cap = group_cap(c, g);
+    long long k = c.act_base ? chunk_base(c, gi) : 0;
+    char* const ws0 = c.ws;
+    for (int done = 0; done < g.count; done += cap, ++k) {
         const int n = g.count - done < cap ? g.count - done : cap;
-        STAIR_TRY(run_chunk(c, g, g.node_off + done, n, g.out_base + done * g.out_mult, g.aux_base >= 0 ? g.aux_base + done : -1));
+        if (c.act_base) c.ws = c.act_base + k * c.plan.mod_bytes;
+        const int rc = run_chunk(c, g, g.node_off + done, n, g.out_base + done * g.out_mult, g.aux_base >= 0 ? g.aux_base + done : -1);
+        c.ws = ws0;
+        if (rc != STAIR_OK) return rc;
     }
     return STAIR_OK;
 }
@@ -412,7 +431,7 @@ inline int run_modules(Ctx& c) {
         while (gj < ng && c.b.groups[gj].level == c.b.groups[gi].level) ++gj;
         const int nw = gj - gi;
         if (nw == 1 || !ls) {
-            for (int g = gi; g < gj; ++g) STAIR_TRY(run_group(c, c.b.groups[g]));
+            for (int g = gi; g < gj; ++g) STAIR_TRY(run_group(c, c.b.groups[g], g));
             gi = gj;
             continue;
         }
@@ -439,9 +458,9 @@ inline int run_modules(Ctx& c) {
             Ctx lc = c;
             const int l = lane_of[k];
             if (l > 0) { lc.st = ls->side[l - 1]; lc.ws = c.ws + static_cast<long long>(l) * c.plan.mod_bytes; }
-            STAIR_TRY(run_group(lc, c.b.groups[order[k]]));
+            STAIR_TRY(run_group(lc, c.b.groups[order[k]], order[k]));
         }
-        for (int g = gi + nwc; g < gj; ++g) STAIR_TRY(run_group(c, c.b.groups[g]));      // (more than 64 groups in a wave: the rest on the main lane)
+        for (int g = gi + nwc; g < gj; ++g) STAIR_TRY(run_group(c, c.b.groups[g], g));      // (more than 64 groups in a wave: the rest on the main lane)
         for (int l = 1; l < lanes; ++l) {
             if (cudaEventRecord(ls->join[l - 1], ls->side[l - 1]) != cudaSuccess) return STAIR_ERR_CUDA;
             if (cudaStreamWaitEvent(c.st, ls->join[l - 1], 0) != cudaSuccess) return STAIR_ERR_CUDA;

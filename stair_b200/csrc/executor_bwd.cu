@@ -519,17 +519,32 @@ int run_backward(BCtx& b) {
     }
     STAIR_TRY(losses(b));
     STAIR_TRY(decoder_bwd(b));
+    char* const ws0 = c.ws;
     for (int gi = c.b.n_groups - 1; gi >= 0; --gi) {
         const StairGroup& g = c.b.groups[gi];
-        const int cap = op_is_vid_sized(g.op) ? c.plan.nc_vid : static_cast<int>(VEC_CAP);
-        for (int done = 0; done < g.count; done += cap) {
+        const int cap = group_cap(c, g);
+        long long k = c.act_base ? chunk_base(c, gi) : 0;
+        for (int done = 0; done < g.count; done += cap, ++k) {
             const int n = g.count - done < cap ? g.count - done : cap;
             const int p = g.node_off + done, ob = g.out_base + done * g.out_mult, ab = g.aux_base >= 0 ? g.aux_base + done : -1;
-            if (g.op != STAIR_OP_WORD) RUN(run_chunk(c, g, p, n, ob, ab));      // recompute the chunk's intermediates
-            STAIR_TRY(chunk_bwd(b, g, p, n, ob, ab));
+            if (c.act_base) c.ws = c.act_base + k * c.plan.mod_bytes;           // the chunk's intermediates were kept by the training forward
+            else if (g.op != STAIR_OP_WORD) RUN(run_chunk(c, g, p, n, ob, ab));  // recompute the chunk's intermediates
+            const int rc = chunk_bwd(b, g, p, n, ob, ab);
+            c.ws = ws0;
+            if (rc != STAIR_OK) return rc;
         }
     }
     STAIR_TRY(encoders_bwd(b));
+    return STAIR_OK;
+}
+
+// StairTrain.act_saved (optional): one scratch region per (group, chunk) so that the backward does not re-run the module forward
+int bind_saved_activations(Ctx& c, const StairTrain& tr) {
+    c.act_base = nullptr;
+    if (!tr.act_saved) return STAIR_OK;
+    const long long need = total_chunks(c) * c.plan.mod_bytes + 1024;
+    if (tr.act_saved_bytes < need) return STAIR_ERR_CAPACITY;
+    c.act_base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tr.act_saved) + 1023) & ~static_cast<uintptr_t>(1023));
     return STAIR_OK;
 }
 
@@ -557,6 +572,13 @@ extern "C" int64_t stair_train_saved_bytes(const StairModel* model, const StairB
     return saved_layout(*model, *batch).total;
 }
 
+extern "C" int64_t stair_train_act_bytes(const StairModel* model, const StairBatch* batch, const StairBuffers* buf) {
+    if (!model || !batch || !buf) return -1;
+    Ctx c{*model, *batch, *buf, nullptr};
+    if (make_ctx(c, *model, *batch, *buf) != STAIR_OK) return -1;
+    return total_chunks(c) * c.plan.mod_bytes + 1024;
+}
+
 extern "C" int64_t stair_train_workspace_bytes(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train) {
     if (!model || !batch || !buf || !train) return -1;
     Ctx c{*model, *batch, *buf, nullptr};
@@ -575,6 +597,7 @@ extern "C" int stair_nmn_forward_train(const StairModel* model, const StairBatch
     if (buf->workspace_bytes < c.plan.total || buf->itab_ints < c.il.total) return STAIR_ERR_CAPACITY;
     c.drop_p = train->dropout_p; c.drop_seed = train->dropout_seed;
     if (!(c.drop_p >= 0.0f && c.drop_p < 1.0f)) return STAIR_ERR_ARG;
+    STAIR_TRY(bind_saved_activations(c, *train));
     const long long before = g_launch_count;
     STAIR_TRY(launch_group_layouts(*batch, buf->itab, buf->status, c.st));
     STAIR_TRY(run_encoders_train(c, *train));
@@ -592,6 +615,7 @@ extern "C" int stair_nmn_backward(const StairModel* model, const StairBatch* bat
     if (buf->workspace_bytes < c.plan.total) return STAIR_ERR_CAPACITY;
     c.drop_p = train->dropout_p; c.drop_seed = train->dropout_seed;     // the recomputed forward of every chunk regenerates the masks
     if (!(c.drop_p >= 0.0f && c.drop_p < 1.0f)) return STAIR_ERR_ARG;
+    STAIR_TRY(bind_saved_activations(c, *train));
     BCtx b{c, *train, Bump(), false};
     b.ws.base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(train->workspace) + 255) & ~static_cast<uintptr_t>(255));
     b.ws.cap = train->workspace_bytes - 256;

@@ -172,7 +172,7 @@ class NMNTrainStep:
 
     def __init__(self, model, module_loss_weight=1.0, decoder_loss_weight=1.0, gradient_accumulation=None,
                  modules_no_intermediate_train=('FilterFrame',), distributed=None, process_group=None, global_negatives=True,
-                 dropout_seed=None):
+                 dropout_seed=None, save_activations_budget=24 << 30):
         self.model = model
         self.module_loss_weight, self.decoder_loss_weight = module_loss_weight, decoder_loss_weight
         self.gradient_accumulation = gradient_accumulation
@@ -184,6 +184,8 @@ class NMNTrainStep:
         # draws a fresh counter-based mask: seed = base seed + number of windows run so far (+ rank under data parallelism).
         self.dropout_seed = int(torch.initial_seed() if dropout_seed is None else dropout_seed) & 0xFFFFFFFFFFFFFFFF
         self.windows_run = 0
+        # keep the module intermediates of the forward for the backward when they fit in this many bytes (else recompute them)
+        self.save_activations_budget = int(save_activations_budget)
         self._targets = None
         self._cache = {}
         self.last = None
@@ -322,6 +324,10 @@ class NMNTrainStep:
         saved_bytes = int(lib.stair_train_saved_bytes(ctypes.byref(ms), ctypes.byref(sb)))
         saved = self._buf('saved', saved_bytes, torch.uint8, dev)
         tr.saved, tr.saved_bytes = saved.data_ptr(), saved.numel()
+        act_bytes = int(lib.stair_train_act_bytes(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs)))
+        if 0 < act_bytes <= self.save_activations_budget:
+            act = self._buf('act_saved', act_bytes, torch.uint8, dev)
+            tr.act_saved, tr.act_saved_bytes = act.data_ptr(), act.numel()
         ws_bytes = int(lib.stair_train_workspace_bytes(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr)))
         if ws_bytes < 0:
             raise L.StairError('stair_train_workspace_bytes failed (unsupported configuration)')

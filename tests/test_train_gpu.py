@@ -320,3 +320,27 @@ def test_fused_adam_matches_torch_and_refreshes_the_packed_weights(precision):
             if precision == 'fp32':
                 ma, mb = oc.state[pa]['exp_avg'], ob.state[pb]['exp_avg']
                 assert float((ma - mb).norm()) <= 1e-3 * float(mb.norm()) + 1e-9
+
+
+@pytest.mark.parametrize('dropout', [0.0, 0.25])
+def test_saved_activations_equal_recompute(dropout):
+    """The backward reading the module intermediates kept by the training forward (StairTrain.act_saved) == the backward that re-runs
+    every chunk's forward (including, under dropout, the regenerated masks)."""
+    cfg = syn.model_config(T=8, V=128, hidden=64, object_types=16, dropout=dropout)
+    torch.manual_seed(11)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32').cuda().train()
+    qs = syn.make_questions(56, 8, 128, seed=21, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    grads = []
+    for budget in (0, 1 << 34):
+        for prm in model.parameters():
+            prm.grad = None
+        step = NMNTrainStep(model, save_activations_budget=budget)
+        out = step(qs, dropout_seed=99)
+        torch.cuda.synchronize()
+        assert (step.last['train'].act_saved is not None) == (budget > 0)
+        grads.append((float(out['loss']), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = grads
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)
+    assert g0.keys() == g1.keys() and len(g0) > 60
+    for k in g0:
+        assert float((g0[k] - g1[k]).norm()) <= 1e-5 * float(g0[k].norm()) + 1e-12, k
