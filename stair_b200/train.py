@@ -234,6 +234,7 @@ class NMNTrainStep:
             n_window = int(cnt.item())
         ga = self.gradient_accumulation or n_window
         rows = collate_losses(batch, model.pretrain_modules, batch.T, self.module_loss_weight, ga, self.modules_no_intermediate_train)
+        rows.counts['decoder'] = batch.B if self.decoder_loss_weight != 0 else 0          # decoder CE applies to every question (:376-380)
         if rows.bin_node and not cfg['have_pretrain_head']:
             raise L.StairError('Exists/Xor/Equals supervision needs have_pretrain_head (their criterion reads the head logits)')
         # window-level class names (train_module.py:360-366,388-406): under data parallelism the negatives of the whole
