@@ -390,7 +390,9 @@ int run_encoders_train(Ctx& c, const StairTrain& tr) {
     return STAIR_OK;
 }
 
-int encoders_bwd(BCtx& b) {
+// BPTT of one encoder (e = 0 video, 1 text) on the stream of b.c; `dir_lane` = index of the side stream that runs the reverse direction's
+// recurrent GEMMs next to the forward direction's
+int encoder_bwd(BCtx& b, int e, int dir_lane) {
     Ctx& c = b.c;
     const StairTrain& tr = b.tr;
     const StairModel& m = c.m; const StairBatch& bt = c.b;
@@ -398,7 +400,7 @@ int encoders_bwd(BCtx& b) {
     const SavedLayout SL = saved_layout(m, bt);
     char* sv = reinterpret_cast<char*>(tr.saved);
     const bool blocked = fused_history(c);
-    for (int e = 1; e >= 0; --e) {
+    {
         const EncIO io = enc_io(c, e);
         const int S = io.S;
         const long long mark = b.ws.off;
@@ -421,7 +423,13 @@ int encoders_bwd(BCtx& b) {
             else
                 RUN(launch_lstm_cell_bwd(gates + static_cast<long long>(s) * 2 * B * 4 * h, c_prev, cs + static_cast<long long>(s) * 2 * B * h, dout, dh_rec,
                                          e == 1 ? tr.dqfeat : nullptr, dc, dg_dir, dg_step, dg_plane, c.np, dxproj, io.q_off, B, c.T, h, s, S - 1, 0, c.st));
-            if (s > 0)
+            if (s > 0) {
+                // dh_{s-1} = dG_s . W_hh of the two directions are independent and small (B/128 x h/128 tiles each): the reverse direction
+                // runs on a side stream next to the forward one instead of after it
+                LaneStreams* ls = (!b.dry && g_lanes > 1) ? lane_streams() : nullptr;
+                if (ls) {
+                    if (cudaEventRecord(ls->join[dir_lane + 1], c.st) != cudaSuccess || cudaStreamWaitEvent(ls->side[dir_lane], ls->join[dir_lane + 1], 0) != cudaSuccess) return STAIR_ERR_CUDA;
+                }
                 for (int d = 0; d < 2; ++d) {
                     const int wid = d == 0 ? io.whh_f : io.whh_r;
                     if (!m.wt[wid]) return STAIR_ERR_ARG;
@@ -429,8 +437,12 @@ int encoders_bwd(BCtx& b) {
                     r.A = dg_step + d * dg_dir; r.lda = 4 * h; r.a_plane_rows = static_cast<int>(dg_plane / (4 * h)); r.nplanes = c.np;
                     r.W = m.wt[wid]; r.ldw = 4 * h; r.w_plane_rows = h; r.C = dh_rec + static_cast<long long>(d) * B * h; r.ldc = h;
                     r.out_dtype = STAIR_F32; r.M = B; r.N = h; r.K = 4 * h;
-                    RUN(launch_gemm(r, c.st));
+                    RUN(launch_gemm(r, (ls && d == 1) ? ls->side[dir_lane] : c.st));
                 }
+                if (ls) {
+                    if (cudaEventRecord(ls->join[dir_lane], ls->side[dir_lane]) != cudaSuccess || cudaStreamWaitEvent(c.st, ls->join[dir_lane], 0) != cudaSuccess) return STAIR_ERR_CUDA;
+                }
+            }
         }
         // dW_hh[d] += sum_s dG[d][s]^T h[d][s-1]: one contraction over all (step, question) rows per direction, both operands in place
         for (int d = 0; d < 2; ++d) {
@@ -455,6 +467,34 @@ int encoders_bwd(BCtx& b) {
             STAIR_TRY(linear_bwd(b, dxproj, 4 * H, nullptr, 0, nullptr, xin_p, xrows, static_cast<int>(io.rows), 4 * H, io.Kin, io.wih, io.bias, nullptr));
         }
         b.ws.off = mark;
+    }
+    return STAIR_OK;
+}
+
+// The two encoders' BPTT chains are independent (24 + 8 sequential steps of small kernels): the video encoder runs on a side stream
+// next to the text encoder, each with its own slice of the backward workspace.
+int encoders_bwd(BCtx& b) {
+    Ctx& c = b.c;
+    LaneStreams* ls = (!b.dry && g_lanes > 1) ? lane_streams() : nullptr;
+    const long long mark = b.ws.off;
+    // video (e = 0): side stream 2 (+ side stream 3 for its reverse-direction GEMMs); workspace [mark, video peak)
+    Ctx cv = c;
+    if (ls) {
+        cv.st = ls->side[2];
+        if (cudaEventRecord(ls->fork, c.st) != cudaSuccess || cudaStreamWaitEvent(cv.st, ls->fork, 0) != cudaSuccess) return STAIR_ERR_CUDA;
+    }
+    BCtx bv{cv, b.tr, b.ws, b.dry};
+    bv.ws.peak = mark;
+    const int rc_v = encoder_bwd(bv, 0, 3);
+    if (rc_v != STAIR_OK) return rc_v;
+    if (bv.ws.overflow) b.ws.overflow = true;
+    // text (e = 1): caller's stream (+ side stream 0), workspace after the video encoder's
+    b.ws.off = bv.ws.peak;
+    if (b.ws.off > b.ws.peak) b.ws.peak = b.ws.off;
+    STAIR_TRY(encoder_bwd(b, 1, 0));
+    b.ws.off = mark;
+    if (ls) {
+        if (cudaEventRecord(ls->join[2], ls->side[2]) != cudaSuccess || cudaStreamWaitEvent(c.st, ls->join[2], 0) != cudaSuccess) return STAIR_ERR_CUDA;
     }
     return STAIR_OK;
 }
