@@ -257,8 +257,8 @@ int64_t stair_train_workspace_bytes(const StairModel* model /*HOST*/, const Stai
 int stair_nmn_forward_train(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, void* stream);
 int stair_nmn_backward(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, void* stream);
 /* torch.optim.Adam step (weight_decay 0) on one parameter tensor; `step` counts from 1 (train_module.py:326-332,408-412) */
-int stair_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
-                    float eps, int step, void* stream);
+int stair_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, double beta1, double beta2,
+                    float eps, int step, void* stream);      /* betas are doubles: 1 - beta is formed in double like torch does */
 /* Multi-tensor Adam fused with the refresh of the kernels' weight copies: ONE launch updates every listed parameter (fp32 master,
  * exp_avg, exp_avg_sq; same arithmetic as stair_adam_step) and rewrites what the forward / backward kernels read — the bf16 plane
  * copy [nplanes][rows, ld], its transposed copy [cols, ld_t] (B operand of dX = dZ.W), the gate-interleaved W_hh copy of the fused
@@ -273,7 +273,7 @@ typedef struct StairAdamSeg {
     int32_t rows, cols, kind, nplanes, perm_hh, tile0;
     float bc1, bc2;                                          /* 1 - beta1^step, 1 - beta2^step of this parameter */
 } StairAdamSeg;
-int stair_adam_multi(const StairAdamSeg* segs /*DEVICE*/, int n_segs, int total_tiles, float lr, float beta1, float beta2, float eps, void* stream);
+int stair_adam_multi(const StairAdamSeg* segs /*DEVICE*/, int n_segs, int total_tiles, float lr, double beta1, double beta2, float eps, void* stream);
 /* number of kernels stair_nmn_forward launched in its last call on this thread (bench.py's gpu_launches). */
 int64_t stair_last_launch_count(void);
 

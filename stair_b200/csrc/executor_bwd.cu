@@ -666,15 +666,15 @@ extern "C" int stair_nmn_backward(const StairModel* model, const StairBatch* bat
     return rc;
 }
 
-extern "C" int stair_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
+extern "C" int stair_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, double beta1, double beta2,
                                float eps, int step, void* stream) {
-    const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+    const float bc1 = static_cast<float>(1.0 - pow(beta1, step)), bc2 = static_cast<float>(1.0 - pow(beta2, step));
     return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int stair_set_dw_impl(int impl) { g_dw_impl = impl ? 1 : 0; return STAIR_OK; }
 
-extern "C" int stair_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, float beta1, float beta2, float eps, void* stream) {
+extern "C" int stair_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, double beta1, double beta2, float eps, void* stream) {
     if (!segs && n_segs > 0) return STAIR_ERR_ARG;
     return launch_adam_multi(segs, n_segs, total_tiles, lr, beta1, beta2, eps, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -1261,11 +1261,11 @@ int launch_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c
 
 // Adam (torch.optim.Adam semantics, weight_decay 0, train_module.py:326-332)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-                            float lr, float b1, float b2, float eps, float bc1, float bc2) {
+                            float lr, float2 b1, float2 b2, float eps, float bc1, float bc2) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float gi = g[i];
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        const float mi = b1.x * m[i] + b1.y * gi;
+        const float vi = b2.x * v[i] + b2.y * gi * gi;
         m[i] = mi; v[i] = vi;
         p[i] -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
     }
@@ -1274,15 +1274,17 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // ------------------------------------------------------------------------------------------------------------------
 // Multi-tensor Adam + weight-copy refresh (see StairAdamSeg in include/stair_b200.h)
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float adam_update(float& p, float g, float& m, float& v, float lr, float b1, float b2, float eps, float bc1, float bc2) {
-    const float mi = b1 * m + (1.f - b1) * g;
-    const float vi = b2 * v + (1.f - b2) * g * g;
+// b1 / b2 arrive as {beta, 1 - beta} pairs with 1 - beta rounded from double (torch computes 1 - beta in double: in fp32, 1 - 0.999f is
+// off by 1.3e-5 relative, which the second moment inherits)
+__device__ __forceinline__ float adam_update(float& p, float g, float& m, float& v, float lr, float2 b1, float2 b2, float eps, float bc1, float bc2) {
+    const float mi = b1.x * m + b1.y * g;
+    const float vi = b2.x * v + b2.y * g * g;
     m = mi; v = vi;
     p -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
     return p;
 }
 
-__global__ void __launch_bounds__(256) adam_multi_kernel(const StairAdamSeg* __restrict__ segs, int n_segs, float lr, float b1, float b2, float eps) {
+__global__ void __launch_bounds__(256) adam_multi_kernel(const StairAdamSeg* __restrict__ segs, int n_segs, float lr, float2 b1, float2 b2, float eps) {
     __shared__ unsigned short tile[3][64][66];
     __shared__ StairAdamSeg sg;
     // segment of this block's tile: last seg with tile0 <= blockIdx.x
@@ -1400,16 +1402,18 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const StairAdamSeg* __r
         }
 }
 
-int launch_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, float b1, float b2, float eps, cudaStream_t st) {
+int launch_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, double b1, double b2, float eps, cudaStream_t st) {
     if (n_segs <= 0 || total_tiles <= 0) return STAIR_OK;
-    adam_multi_kernel<<<total_tiles, 256, 0, st>>>(segs, n_segs, lr, b1, b2, eps);
+    adam_multi_kernel<<<total_tiles, 256, 0, st>>>(segs, n_segs, lr, make_float2(static_cast<float>(b1), static_cast<float>(1.0 - b1)),
+                                                   make_float2(static_cast<float>(b2), static_cast<float>(1.0 - b2)), eps);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
 
-int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1, float bc2, cudaStream_t st) {
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, double b1, double b2, float eps, float bc1, float bc2, cudaStream_t st) {
     if (n <= 0) return STAIR_OK;
-    adam_kernel<<<nblocks(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2);
+    adam_kernel<<<nblocks(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, make_float2(static_cast<float>(b1), static_cast<float>(1.0 - b1)),
+                                                 make_float2(static_cast<float>(b2), static_cast<float>(1.0 - b2)), eps, bc1, bc2);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }

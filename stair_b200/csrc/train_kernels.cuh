@@ -81,7 +81,7 @@ int launch_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c
                          float* dc, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, const int* q_off,
                          int B, int T, int h, int step, int last_step, int blocked, cudaStream_t st);
 
-int launch_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, float b1, float b2, float eps, cudaStream_t st);
-int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1, float bc2, cudaStream_t st);
+int launch_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, double b1, double b2, float eps, cudaStream_t st);
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, double b1, double b2, float eps, float bc1, float bc2, cudaStream_t st);
 
 }  // namespace stair

@@ -400,7 +400,7 @@ class Adam:
             s['step'] += 1
             g = p.grad.contiguous()
             L.check(lib.stair_adam_step(L.ptr(p), L.ptr(g), L.ptr(s['m']), L.ptr(s['v']), L.i64(p.numel()), ctypes.c_float(lr),
-                                        ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]), ctypes.c_float(self.eps),
+                                        ctypes.c_double(self.betas[0]), ctypes.c_double(self.betas[1]), ctypes.c_float(self.eps),
                                         L.i32(s['step']), L.stream_ptr()), 'stair_adam_step')
             # the update happened behind torch's back: bump the version counter so PackedWeights.refresh re-packs
             torch.autograd.graph.increment_version(p)
@@ -519,7 +519,7 @@ class FusedAdam(torch.optim.Adam):
         if segs:
             arr = (L.StairAdamSeg * len(segs))(*[s for s, _ in segs])
             table = torch.frombuffer(bytearray(arr), dtype=torch.uint8).to(dev, non_blocking=True)
-            L.check(lib.stair_adam_multi(L.ptr(table), L.i32(len(segs)), L.i32(tile0), ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2),
+            L.check(lib.stair_adam_multi(L.ptr(table), L.i32(len(segs)), L.i32(tile0), ctypes.c_float(lr), ctypes.c_double(b1), ctypes.c_double(b2),
                                          ctypes.c_float(eps), L.stream_ptr()), 'stair_adam_multi')
             # the update (and the refresh of the packed copies) happened behind torch's back: keep PackedWeights' signature valid
             pw.mark_current(model.submodules, PRECISIONS[model.precision], dev)
@@ -530,7 +530,7 @@ class FusedAdam(torch.optim.Adam):
             st = self._state_of(prm)
             st['step'] += 1
             L.check(lib.stair_adam_step(L.ptr(prm), L.ptr(prm.grad.contiguous()), L.ptr(st['exp_avg']), L.ptr(st['exp_avg_sq']), L.i64(prm.numel()),
-                                        ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps), L.i32(int(st['step'])),
+                                        ctypes.c_float(lr), ctypes.c_double(b1), ctypes.c_double(b2), ctypes.c_float(eps), L.i32(int(st['step'])),
                                         L.stream_ptr()), 'stair_adam_step')
             torch.autograd.graph.increment_version(prm)
         return None
