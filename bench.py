@@ -361,12 +361,12 @@ def main():
     flops = 2.0 * M * N * K
     achieved_tf = flops / (gemm_ms * 1e-3) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the default shape, from the committed `ncu --set full` capture
-    # (profiles/r1_gemm_xproj_ncu_summary_v2.txt); algorithmic bytes: A 268 MB + W 17 MB + C 134 MB = 419 MB
+    # (profiles/r1_gemm_xproj_ncu_summary_v3.txt); algorithmic bytes: A 268 MB + W 17 MB + C 134 MB = 419 MB
     traffic = 398.9e6 if (args.workload == 'rx' and B == PER_GPU_B) else None
     roofline = {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel<256,4> (video input projection [%d,%d]x[%d,%d])' % (M, K, K, N),
                 'achieved': achieved_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': achieved_tf / pk['tf_sustained'],
                 'frac_of_burst_peak': achieved_tf / pk['tf_burst'], 'peak_source': pk['src'] + ' (sustained; kernel timed inside the step loop)',
-                'traffic': traffic, 'traffic_source': 'profiles/r1_gemm_xproj_ncu_summary_v2.txt' if traffic else None, 'ms': gemm_ms,
+                'traffic': traffic, 'traffic_source': 'profiles/r1_gemm_xproj_ncu_summary_v3.txt' if traffic else None, 'ms': gemm_ms,
                 'flops_per_launch': flops, 'algorithmic_bytes_per_launch': 2.0 * (M * K + N * K + M * N)}
 
     line = None
