@@ -224,6 +224,7 @@ int stair_gemm_bf16_gather(const void* arena, long long ld, long long arena_slot
  * (dW = dZ^T . X of every nn.Linear backward, train_module.py:408).  C fp32; accumulate = 1 adds into C (split-K with atomics). */
 int stair_gemm_bf16_tn(const void* A, long long lda, int a_plane_rows, const void* W, long long ldw, int w_plane_rows, int nplanes,
                        float* C, long long ldc, int M, int N, int K, int accumulate, void* stream);
+int stair_set_bwd_lanes(int lanes);     /* module backward: groups of one schedule wave on up to `lanes` concurrent streams (1 = sequential) */
 int stair_set_dw_impl(int impl);        /* weight gradients: 0 = MN-major operands in place (product); 1 = transposed copies + K-major GEMM */
 int stair_set_gemm_impl(int impl);      /* 0 = tcgen05 (product); 1 = SIMT debug kernel used to cross-check in tests */
 int stair_get_gemm_impl(void);

@@ -12,6 +12,8 @@ torch.manual_seed(0)
 model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().train()
 qs = syn.make_questions(B, T, V, seed=1234, with_gold=True)
 batch = collate(qs, video_dtype=torch.bfloat16).to('cuda')
+from stair_b200 import _lib as L
+L.lib().stair_set_bwd_lanes(int(os.environ.get('BWD_LANES', 1)))
 step, opt = NMNTrainStep(model), FusedAdam(model)
 plan = step.plan(batch)
 for i in range(steps):

@@ -15,6 +15,7 @@ namespace {
 
 using namespace ex;
 
+extern int g_bwd_lanes;
 int g_dw_impl = 0;      // 0 = MN-major weight-gradient GEMM (product); 1 = transposed copies + K-major GEMM (comparison)
 
 struct Bump {
@@ -66,6 +67,9 @@ SavedLayout saved_layout(const StairModel& m, const StairBatch& b) {
 // ---- staging helpers ------------------------------------------------------------------------------------------------------------
 bf16* stage_act(BCtx& b, const void* A, int sdt, int M, int K, int* rc) {
     Ctx& c = b.c;
+    // bf16 storage, one plane, 16-byte row pitch: the activation rows already ARE the GEMM operand
+    if (c.np == 1 && sdt == STAIR_BF16 && (K % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0)
+        return reinterpret_cast<bf16*>(const_cast<void*>(A));
     const long long kld = align_up(K, 8);
     bf16* p = b.ws.take<bf16>(static_cast<long long>(c.np) * M * kld);
     if (!b.dry && !b.ws.overflow) *rc = launch_stage_rows(sdt, A, K, nullptr, 1, 1, p, kld, M, c.np, M, K, c.st);
@@ -97,6 +101,7 @@ int linear_bwd(BCtx& b, const float* dY, long long ld_dy, const void* Y, long lo
         GemmArgs a;
         a.A = dZs; a.lda = n_ld; a.a_plane_rows = M; a.W = Xp; a.ldw = k_ld; a.w_plane_rows = static_cast<int>(x_plane_rows); a.nplanes = c.np;
         a.C = gW; a.ldc = K; a.out_dtype = STAIR_F32; a.M = N; a.N = K; a.K = M; a.accumulate = 1; a.mn_major = 1;
+        a.atomic_acc = g_bwd_lanes > 1;                          // groups sharing a weight may run concurrently
         RUN(launch_gemm(a, c.st));
     } else if (gW) {
         bf16* dZt = b.ws.take<bf16>(c.np * static_cast<long long>(N) * m_ld);
@@ -106,6 +111,7 @@ int linear_bwd(BCtx& b, const float* dY, long long ld_dy, const void* Y, long lo
         GemmArgs a;
         a.A = dZt; a.lda = m_ld; a.a_plane_rows = N; a.W = Xt; a.ldw = m_ld; a.w_plane_rows = K; a.nplanes = c.np;
         a.C = gW; a.ldc = K; a.out_dtype = STAIR_F32; a.M = N; a.N = K; a.K = M; a.accumulate = 1;
+        a.atomic_acc = g_bwd_lanes > 1;
         RUN(launch_gemm(a, c.st));
     }
     if (dX) {
@@ -543,6 +549,106 @@ int decoder_bwd(BCtx& b) {
     return STAIR_OK;
 }
 
+// backward of every chunk of group gi on the stream / workspace of b (forward scratch of the recompute path: b.c.ws)
+int group_bwd(BCtx& b, int gi) {
+    Ctx& c = b.c;
+    const StairGroup& g = c.b.groups[gi];
+    const int cap = group_cap(c, g);
+    char* const ws0 = c.ws;
+    long long k = c.act_base ? chunk_base(c, gi) : 0;
+    for (int done = 0; done < g.count; done += cap, ++k) {
+        const int n = g.count - done < cap ? g.count - done : cap;
+        const int p = g.node_off + done, ob = g.out_base + done * g.out_mult, ab = g.aux_base >= 0 ? g.aux_base + done : -1;
+        if (c.act_base) c.ws = c.act_base + k * c.plan.mod_bytes;           // the chunk's intermediates were kept by the training forward
+        else if (g.op != STAIR_OP_WORD) RUN(run_chunk(c, g, p, n, ob, ab));  // recompute the chunk's intermediates
+        const int rc = chunk_bwd(b, g, p, n, ob, ab);
+        c.ws = ws0;
+        if (rc != STAIR_OK) return rc;
+    }
+    return STAIR_OK;
+}
+
+int g_bwd_lanes = 1;      // 1 = groups one after the other on the caller's stream; > 1 = the groups of a schedule wave on concurrent streams
+
+// Module backward: groups in reverse schedule order.  The groups of one wave are independent of each other in the backward pass too
+// (they read their own output gradients and ADD into shared gradient arenas / parameter gradients with atomics), so with
+// g_bwd_lanes > 1 they run on concurrent streams, every lane with its own slice of the backward workspace: the small staging /
+// scatter / reduction kernels of one group then overlap the GEMMs of another.
+int modules_bwd(BCtx& b) {
+    Ctx& c = b.c;
+    const int ng = c.b.n_groups;
+    const int max_lanes = g_bwd_lanes < LANES ? g_bwd_lanes : LANES;
+    if (max_lanes <= 1) {
+        for (int gi = ng - 1; gi >= 0; --gi) STAIR_TRY(group_bwd(b, gi));
+        return STAIR_OK;
+    }
+    // workspace of the largest chunk (host-only pass: allocations without launches)
+    long long chunk_peak = 0;
+    {
+        BCtx d{c, b.tr, Bump(), true};
+        d.ws.dry = true;
+        for (int gi = 0; gi < ng; ++gi) {
+            d.ws.off = 0; d.ws.peak = 0;
+            STAIR_TRY(group_bwd(d, gi));
+            if (d.ws.peak > chunk_peak) chunk_peak = d.ws.peak;
+        }
+        chunk_peak = align_up(chunk_peak + 256, 1024);
+    }
+    const long long mark = b.ws.off;
+    char* lane_base = b.ws.take<char>(max_lanes * chunk_peak);
+    if (b.dry) { b.ws.off = mark; return STAIR_OK; }
+    if (b.ws.overflow) return STAIR_ERR_CAPACITY;
+    LaneStreams* ls = lane_streams();
+    if (!ls) return STAIR_ERR_CUDA;
+    int gj = ng;
+    while (gj > 0) {
+        int gi = gj - 1;
+        while (gi > 0 && c.b.groups[gi - 1].level == c.b.groups[gj - 1].level) --gi;      // wave = groups [gi, gj)
+        const int nw = gj - gi;
+        const int lanes = nw < max_lanes ? nw : max_lanes;
+        int order[64], lane_of[64];
+        long long load[LANES] = {0};
+        const int nwc = nw < 64 ? nw : 64;
+        for (int k = 0; k < nwc; ++k) order[k] = gi + k;
+        for (int a = 1; a < nwc; ++a)
+            for (int b2 = a; b2 > 0 && group_cost(c.b.groups[order[b2]], c.T) > group_cost(c.b.groups[order[b2 - 1]], c.T); --b2) {
+                const int t = order[b2]; order[b2] = order[b2 - 1]; order[b2 - 1] = t;
+            }
+        for (int k = 0; k < nwc; ++k) {
+            int best = 0;
+            for (int l = 1; l < lanes; ++l) if (load[l] < load[best]) best = l;
+            lane_of[k] = best;
+            load[best] += group_cost(c.b.groups[order[k]], c.T);
+        }
+        if (lanes > 1) {
+            if (cudaEventRecord(ls->fork, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
+            for (int l = 1; l < lanes; ++l)
+                if (cudaStreamWaitEvent(ls->side[l - 1], ls->fork, 0) != cudaSuccess) return STAIR_ERR_CUDA;
+        }
+        for (int k = 0; k < nwc; ++k) {
+            const int l = lane_of[k];
+            Ctx lc = c;
+            if (l > 0) { lc.st = ls->side[l - 1]; lc.ws = c.ws + static_cast<long long>(l) * c.plan.mod_bytes; }
+            BCtx bl{lc, b.tr, Bump(), false};
+            bl.ws.base = lane_base + l * chunk_peak; bl.ws.cap = chunk_peak;
+            STAIR_TRY(group_bwd(bl, order[k]));
+            if (bl.ws.overflow) return STAIR_ERR_CAPACITY;
+        }
+        for (int g = gi + nwc; g < gj; ++g) {                       // (more than 64 groups in a wave: the rest on the main lane)
+            BCtx bl{c, b.tr, Bump(), false};
+            bl.ws.base = lane_base; bl.ws.cap = chunk_peak;
+            STAIR_TRY(group_bwd(bl, g));
+        }
+        for (int l = 1; l < lanes; ++l) {
+            if (cudaEventRecord(ls->join[l - 1], ls->side[l - 1]) != cudaSuccess) return STAIR_ERR_CUDA;
+            if (cudaStreamWaitEvent(c.st, ls->join[l - 1], 0) != cudaSuccess) return STAIR_ERR_CUDA;
+        }
+        gj = gi;
+    }
+    b.ws.off = mark;
+    return STAIR_OK;
+}
+
 int run_backward(BCtx& b) {
     Ctx& c = b.c;
     const StairTrain& tr = b.tr;
@@ -559,21 +665,7 @@ int run_backward(BCtx& b) {
     }
     STAIR_TRY(losses(b));
     STAIR_TRY(decoder_bwd(b));
-    char* const ws0 = c.ws;
-    for (int gi = c.b.n_groups - 1; gi >= 0; --gi) {
-        const StairGroup& g = c.b.groups[gi];
-        const int cap = group_cap(c, g);
-        long long k = c.act_base ? chunk_base(c, gi) : 0;
-        for (int done = 0; done < g.count; done += cap, ++k) {
-            const int n = g.count - done < cap ? g.count - done : cap;
-            const int p = g.node_off + done, ob = g.out_base + done * g.out_mult, ab = g.aux_base >= 0 ? g.aux_base + done : -1;
-            if (c.act_base) c.ws = c.act_base + k * c.plan.mod_bytes;           // the chunk's intermediates were kept by the training forward
-            else if (g.op != STAIR_OP_WORD) RUN(run_chunk(c, g, p, n, ob, ab));  // recompute the chunk's intermediates
-            const int rc = chunk_bwd(b, g, p, n, ob, ab);
-            c.ws = ws0;
-            if (rc != STAIR_OK) return rc;
-        }
-    }
+    STAIR_TRY(modules_bwd(b));
     STAIR_TRY(encoders_bwd(b));
     return STAIR_OK;
 }
@@ -672,6 +764,7 @@ extern "C" int stair_adam_step(float* param, const float* grad, float* exp_avg, 
     return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int stair_set_bwd_lanes(int lanes) { g_bwd_lanes = lanes < 1 ? 1 : (lanes > LANES ? LANES : lanes); return STAIR_OK; }
 extern "C" int stair_set_dw_impl(int impl) { g_dw_impl = impl ? 1 : 0; return STAIR_OK; }
 
 extern "C" int stair_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, double beta1, double beta2, float eps, void* stream) {

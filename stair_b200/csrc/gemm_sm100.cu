@@ -43,6 +43,7 @@ struct GemmParams {
     int* err_flag;
     unsigned long long* dbg;   // debug timeline of block 0 (globaltimer ns), null in production
     DropSpec drop;             // dropout after the activation (thresh 0 = off)
+    int atomic_acc;            // fp32 accumulate with atomics even when ksplit == 1
     int mn_major;              // operands stored [k][m] / [k][n] (C = A^T . W): MN-major UMMA tiles, 3-D tensor maps {mn, k, plane}
 };
 
@@ -154,7 +155,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 float4 r = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (p.ksplit > 1) { atomicAdd(reinterpret_cast<float4*>(out + j), r); continue; }     // red.global.add.v4.f32
+                if (p.ksplit > 1 || p.atomic_acc) { atomicAdd(reinterpret_cast<float4*>(out + j), r); continue; }     // red.global.add.v4.f32
                 if (p.accumulate) {
                     float4 o = *reinterpret_cast<const float4*>(out + j);
                     r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
@@ -164,7 +165,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int
         } else {
             for (int j = 0; j < 32; ++j)
                 if (n + j < p.N) {
-                    if (p.ksplit > 1) atomicAdd(out + j, v[j]);
+                    if (p.ksplit > 1 || p.atomic_acc) atomicAdd(out + j, v[j]);
                     else out[j] = p.accumulate ? out[j] + v[j] : v[j];
                 }
         }
@@ -528,6 +529,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     p.accumulate = a.accumulate;
     p.drop = a.drop;
     p.mn_major = a.mn_major;
+    p.atomic_acc = (a.atomic_acc && a.accumulate) ? 1 : 0;
     const int esz = a.out_dtype == STAIR_BF16 ? 2 : 4;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.ldc * esz) % 16 == 0) ? 1 : 0;
     p.tma_store = (!a.accumulate && p.vec_ok && g_epilogue_impl == 0) ? 1 : 0;

@@ -147,6 +147,7 @@ struct GemmArgs {
     // W = [nplanes][w_plane_rows (>= K), ldw] with element (k, n) at k*ldw + n, i.e. C[M,N] = A^T . W — the weight-gradient
     // contraction dW = dZ^T . X over the rows of a layer, read in place (MN-major UMMA operands, no transposed copies).
     int mn_major = 0;
+    int atomic_acc = 0;             // accumulate with atomics even without split-K (concurrent launches adding into the same C)
     DropSpec drop;                  // applied after the activation (training forward only)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);

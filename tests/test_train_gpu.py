@@ -344,3 +344,32 @@ def test_saved_activations_equal_recompute(dropout):
     assert g0.keys() == g1.keys() and len(g0) > 60
     for k in g0:
         assert float((g0[k] - g1[k]).norm()) <= 1e-5 * float(g0[k].norm()) + 1e-12, k
+
+
+def test_concurrent_backward_lanes_equal_sequential():
+    """stair_set_bwd_lanes(4): the groups of a schedule wave back-propagate on concurrent streams (own workspace slice per lane, atomic
+    accumulation into shared parameter gradients) == the sequential backward, with saved activations and with recompute."""
+    from stair_b200 import _lib as L
+    cfg = syn.model_config(T=8, V=128, hidden=64, object_types=16, dropout=0.25)
+    torch.manual_seed(12)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32').cuda().train()
+    qs = syn.make_questions(84, 8, 128, seed=22, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    res = {}
+    try:
+        for lanes in (1, 4):
+            for budget in (1 << 34, 0):
+                L.lib().stair_set_bwd_lanes(lanes)
+                for prm in model.parameters():
+                    prm.grad = None
+                out = NMNTrainStep(model, save_activations_budget=budget)(qs, dropout_seed=5)
+                torch.cuda.synchronize()
+                model.check_status(out['state'])
+                res[(lanes, budget)] = (float(out['loss']), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    finally:
+        L.lib().stair_set_bwd_lanes(1)
+    l0, g0 = res[(1, 1 << 34)]
+    for key, (l1, g1) in res.items():
+        assert abs(l0 - l1) <= 1e-6 * abs(l0), key
+        assert g0.keys() == g1.keys()
+        for k in g0:
+            assert float((g0[k] - g1[k]).norm()) <= 1e-5 * float(g0[k].norm()) + 1e-12, (key, k)
