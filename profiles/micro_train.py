@@ -13,7 +13,7 @@ model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').c
 qs = syn.make_questions(B, T, V, seed=1234, with_gold=True)
 batch = collate(qs, video_dtype=torch.bfloat16).to('cuda')
 from stair_b200 import _lib as L
-L.lib().stair_set_bwd_lanes(int(os.environ.get('BWD_LANES', 1)))
+L.lib().stair_set_bwd_lanes(int(os.environ.get('BWD_LANES', 4)))
 step, opt = NMNTrainStep(model), FusedAdam(model)
 plan = step.plan(batch)
 for i in range(steps):

@@ -568,7 +568,7 @@ int group_bwd(BCtx& b, int gi) {
     return STAIR_OK;
 }
 
-int g_bwd_lanes = 1;      // 1 = groups one after the other on the caller's stream; > 1 = the groups of a schedule wave on concurrent streams
+int g_bwd_lanes = 4;      // 1 = groups one after the other on the caller's stream; > 1 = the groups of a schedule wave on concurrent streams
 
 // Module backward: groups in reverse schedule order.  The groups of one wave are independent of each other in the backward pass too
 // (they read their own output gradients and ADD into shared gradient arenas / parameter gradients with atomics), so with

@@ -343,7 +343,7 @@ def test_saved_activations_equal_recompute(dropout):
     assert abs(l0 - l1) <= 1e-6 * abs(l0)
     assert g0.keys() == g1.keys() and len(g0) > 60
     for k in g0:
-        assert float((g0[k] - g1[k]).norm()) <= 1e-5 * float(g0[k].norm()) + 1e-12, k
+        assert float((g0[k] - g1[k]).norm()) <= 1e-5 * float(g0[k].norm()) + 1e-9, k          # + atomic summation noise of cancelling sums
 
 
 def test_concurrent_backward_lanes_equal_sequential():
@@ -372,4 +372,4 @@ def test_concurrent_backward_lanes_equal_sequential():
         assert abs(l0 - l1) <= 1e-6 * abs(l0), key
         assert g0.keys() == g1.keys()
         for k in g0:
-            assert float((g0[k] - g1[k]).norm()) <= 1e-5 * float(g0[k].norm()) + 1e-12, (key, k)
+            assert float((g0[k] - g1[k]).norm()) <= 1e-5 * float(g0[k].norm()) + 1e-9, (key, k)
