@@ -181,7 +181,7 @@ typedef struct StairTrain {
     int32_t n_con; const int32_t* con_node; const int32_t* con_pos; const float* con_w; int32_t n_cls; const float* cls_rep;
     /* decoder CE, train_module.py:193-194,376-380 */
     const int32_t* answer; float dec_w;
-    float* loss;                  /* float[8] sums: 0 Localize 1 Temporal 2 ExistsFrame 3 Exists/Xor 4 Equals 5 contrastive 6 decoder */
+    float* loss;                  /* float[8] sums: 0 Localize 1 Temporal 2 ExistsFrame 3 Exists/Xor 4 Equals 5 contrastive 6 decoder 7 FilterFrame */
     float* dvid; float* dvec; float* datt; float* dtokfeat; float* dqfeat; float* dlogits;   /* gradient arenas (same shapes as the forward arenas) */
     void* saved; int64_t saved_bytes;           /* LSTM gate / cell / state history written by stair_nmn_forward_train */
     void* workspace; int64_t workspace_bytes;   /* backward scratch, >= stair_train_workspace_bytes */
@@ -194,6 +194,10 @@ typedef struct StairTrain {
      * stair_nmn_backward reads them back instead of re-running the chunk's forward (NULL = recompute; HBM is 180 GB, a 4096-question
      * window needs ~3 GB) */
     void* act_saved; int64_t act_saved_bytes;
+    /* criterion_filterframe (train_module.py:141-155; excluded from training by default, video_nmn/args.py:62): BCELoss(softmax_O(head),
+     * gold / rowsum) on the [T, O] head of supervised FilterFrame nodes.  ff_gold [n_ff][T][O] is the normalised gold, ff_w the weight
+     * per element (module_loss_weight / (ga T O)); dhead_ff has the shape of StairBuffers.head_ff.  loss[7] receives the sum. */
+    int32_t n_ff; const int32_t* ff_node; const float* ff_gold; const float* ff_w; float* dhead_ff; int64_t dhead_ff_elems;
 } StairTrain;
 
 /* Host evaluation (no GPU work) of the dropout mask of site `site` (a STAIR_W_* id of the Linear the Dropout follows) for the

@@ -85,7 +85,8 @@ class StairTrain(ctypes.Structure):
                 ('answer', vp), ('dec_w', ctypes.c_float), ('loss', vp),
                 ('dvid', vp), ('dvec', vp), ('datt', vp), ('dtokfeat', vp), ('dqfeat', vp), ('dlogits', vp),
                 ('saved', vp), ('saved_bytes', i64), ('workspace', vp), ('workspace_bytes', i64),
-                ('dropout_p', ctypes.c_float), ('dropout_seed', ctypes.c_uint64), ('act_saved', vp), ('act_saved_bytes', i64)]
+                ('dropout_p', ctypes.c_float), ('dropout_seed', ctypes.c_uint64), ('act_saved', vp), ('act_saved_bytes', i64),
+                ('n_ff', i32), ('ff_node', vp), ('ff_gold', vp), ('ff_w', vp), ('dhead_ff', vp), ('dhead_ff_elems', i64)]
 
 
 class StairAdamSeg(ctypes.Structure):

@@ -222,6 +222,14 @@ int chunk_bwd(BCtx& b, const StairGroup& g, int p, int n, int ob, int ab) {
     case STAIR_OP_FILTERFRAME: {
         const int w = STAIR_W_FF_REPR + 4 * g.variant;
         const float* gate = g.variant == 0 ? c.at<float>(c.plan.a0) : nullptr;
+        if (g.head && tr.n_ff > 0 && ab >= 0) {                   // criterion_filterframe: through pretrain_head = Linear(H, O) into d(vid_out)
+            const int O = c.m.O;
+            float* dHd = tr.dhead_ff + static_cast<long long>(ab) * T * O;
+            float* dOut2 = b.ws.take<float>(static_cast<long long>(M) * H);
+            STAGE_ACT(vop, vid_out, dt, M, H);
+            STAIR_TRY(linear_bwd(b, dHd, O, nullptr, 0, nullptr, vop, M, M, O, H, STAIR_W_FF_HEAD_W, STAIR_W_FF_HEAD_B, dOut2));
+            RUN(launch_add_inplace(dvid_out, dOut2, static_cast<long long>(M) * H, c.st));
+        }
         float* Gx = b.ws.take<float>(static_cast<long long>(M) * H);
         STAGE_ACT(xp, S1, dt, M, H);
         STAIR_TRY(linear_bwd(b, dvid_out, H, vid_out, H, gate, xp, M, M, H, H, STAIR_W_FF_D_W, STAIR_W_FF_D_B, Gx, DS(b)));
@@ -522,6 +530,10 @@ int losses(BCtx& b) {
     }
     RUN(launch_loss_con(c.adt, c.buf.vec, tr.dvec, c.out_slot, tr.con_node, tr.con_pos, tr.con_w, tr.cls_rep, tr.n_cls, tr.loss, tr.n_con, H, c.st));
     RUN(launch_loss_dec(c.buf.logits, tr.answer, tr.dec_w, tr.dlogits, tr.loss, c.b.B, c.m.A, c.st));
+    if (tr.n_ff > 0) {
+        if (!tr.dhead_ff || !c.buf.head_ff || c.m.O <= 0) return STAIR_ERR_ARG;
+        RUN(launch_loss_ff(c.buf.head_ff, tr.dhead_ff, aux_slot, tr.ff_node, tr.ff_gold, tr.ff_w, tr.loss, tr.n_ff, c.T, c.m.O, c.st));
+    }
     return STAIR_OK;
 }
 
@@ -661,6 +673,7 @@ int run_backward(BCtx& b) {
         if (e == cudaSuccess) e = cudaMemsetAsync(tr.dtokfeat, 0, sizeof(float) * c.b.n_tok * H, c.st);
         if (e == cudaSuccess) e = cudaMemsetAsync(tr.dqfeat, 0, sizeof(float) * c.b.B * H, c.st);
         if (e == cudaSuccess) e = cudaMemsetAsync(tr.loss, 0, sizeof(float) * 8, c.st);
+        if (e == cudaSuccess && tr.n_ff > 0 && tr.dhead_ff) e = cudaMemsetAsync(tr.dhead_ff, 0, sizeof(float) * tr.dhead_ff_elems, c.st);
         if (e != cudaSuccess) return STAIR_ERR_CUDA;
     }
     STAIR_TRY(losses(b));

@@ -1104,6 +1104,64 @@ int launch_loss_con(int dt, const void* vec, float* dvec, const int* out_slot, c
     return STAIR_OK;
 }
 
+// criterion_filterframe (train_module.py:141-155): BCELoss(softmax_O(z), gold), mean over the [T, O] elements (folded into w).
+// One warp per (supervised node, frame).  BCELoss clamps log() at -100 and its backward divides by max(p (1 - p), 1e-12) (ATen).
+__global__ void loss_ff_kernel(const float* __restrict__ head, float* __restrict__ dhead, const int* __restrict__ aux_slot, const int* __restrict__ node,
+                               const float* __restrict__ gold, const float* __restrict__ w, float* __restrict__ loss, int n, int T, int O) {
+    const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    float lsum = 0.f;
+    for (long long r = blockIdx.x * static_cast<long long>(warps) + (threadIdx.x >> 5); r < static_cast<long long>(n) * T; r += static_cast<long long>(gridDim.x) * warps) {
+        const int i = static_cast<int>(r / T), t = static_cast<int>(r % T);
+        const long long hr = (static_cast<long long>(aux_slot[__ldg(node + i)]) * T + t) * O;
+        const float* z = head + hr;
+        const float* g = gold + r * O;
+        const float wi = __ldg(w + i);
+        float m = -INFINITY;
+        for (int j = lane; j < O; j += 32) m = fmaxf(m, z[j]);
+        m = warp_max(m);
+        float se = 0.f;
+        for (int j = lane; j < O; j += 32) se += expf(z[j] - m);
+        se = warp_sum(se);
+        float l = 0.f, dot = 0.f;                                  // dot = sum_k dL/dp_k p_k
+        for (int j = lane; j < O; j += 32) {
+            const float p = expf(z[j] - m) / se, gj = g[j];
+            l -= gj * fmaxf(logf(p), -100.f) + (1.f - gj) * fmaxf(logf(1.f - p), -100.f);
+            dot += (p - gj) / fmaxf(p * (1.f - p), 1e-12f) * p;
+        }
+        l = warp_sum(l); dot = warp_sum(dot);
+        for (int j = lane; j < O; j += 32) {
+            const float p = expf(z[j] - m) / se, gj = g[j];
+            dhead[hr + j] = wi * p * ((p - gj) / fmaxf(p * (1.f - p), 1e-12f) - dot);
+        }
+        lsum += wi * l;
+    }
+    if (lane == 0 && lsum != 0.f) atomicAdd(loss + 7, lsum);
+}
+
+int launch_loss_ff(const float* head, float* dhead, const int* aux_slot, const int* node, const float* gold, const float* w, float* loss,
+                   int n, int T, int O, cudaStream_t st) {
+    if (n <= 0) return STAIR_OK;
+    loss_ff_kernel<<<nblocks(static_cast<long long>(n) * T, 8), 256, 0, st>>>(head, dhead, aux_slot, node, gold, w, loss, n, T, O);
+    STAIR_CHECK_LAUNCH();
+    return STAIR_OK;
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float4 a = reinterpret_cast<float4*>(dst)[i];
+        const float4 b = reinterpret_cast<const float4*>(src)[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        reinterpret_cast<float4*>(dst)[i] = a;
+    }
+}
+int launch_add_inplace(float* dst, const float* src, long long n, cudaStream_t st) {
+    if (n <= 0) return STAIR_OK;
+    if (n % 4) return STAIR_ERR_ARG;
+    add_inplace_kernel<<<nblocks(n / 4, 256), 256, 0, st>>>(dst, src, n / 4);
+    STAIR_CHECK_LAUNCH();
+    return STAIR_OK;
+}
+
 __global__ void loss_dec_kernel(const float* __restrict__ logits, const int* __restrict__ answer, float w, float* __restrict__ dlogits,
                                 float* __restrict__ loss, int B, int A) {
     const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;

@@ -53,6 +53,10 @@ int launch_loss_bin(int dt, const void* vec, float* dvec, const int* out_slot, c
 // contrastive CE of the L2-normalised module output against all class text reps of the window (train_module.py:113-132,388-406)
 int launch_loss_con(int dt, const void* vec, float* dvec, const int* out_slot, const int* node, const int* pos, const float* w,
                     const float* cls_rep, int n_cls, float* loss, int n, int H, cudaStream_t st);
+// criterion_filterframe: BCELoss(softmax_O(head row), gold row) per (node, frame); writes d head (not accumulated) and adds to loss[7]
+int launch_loss_ff(const float* head, float* dhead, const int* aux_slot, const int* node, const float* gold, const float* w, float* loss,
+                   int n, int T, int O, cudaStream_t st);
+int launch_add_inplace(float* dst, const float* src, long long n, cudaStream_t st);     // dst += src (n a multiple of 4, 16-byte aligned)
 int launch_loss_dec(const float* logits, const int* answer, float w, float* dlogits, float* loss, int B, int A, cudaStream_t st);
 
 // Blocked BPTT history written by the fused recurrence kernel (lstm_fused.cu, HIST): 32-row x 8-unit blocks, 32 contiguous bytes per

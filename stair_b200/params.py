@@ -277,6 +277,7 @@ def grad_targets(sub, config):
     lin('FF_ATT', ff.attention[0])
     lin('FF_D', ff.dense[0])
     if config['have_pretrain_head']:
+        lin('FF_HEAD', ff.pretrain_head)                    # only receives a gradient when FilterFrame is supervised (off by default)
         lin('EQUALS_HEAD', sub['Equals'].pretrain_head)
         lin('XOR_HEAD', sub['Xor'].pretrain_head)
         lin('EXISTS_HEAD', sub['Exists'].pretrain_head)

@@ -26,7 +26,7 @@ from . import _lib as L
 from . import layout as LY
 from .params import grad_targets
 
-LOSS_SLOTS = ('Localize', 'Temporal', 'ExistsFrame', 'Exists/Xor', 'Equals', 'contrastive', 'decoder')
+LOSS_SLOTS = ('Localize', 'Temporal', 'ExistsFrame', 'Exists/Xor', 'Equals', 'contrastive', 'decoder', 'FilterFrame')
 CONTRASTIVE = ('Filter', 'Superlative', 'ToAction')
 SUPERVISED = ('Exists', 'Xor', 'Equals', 'Filter', 'ToAction', 'FilterFrame', 'ExistsFrame', 'Superlative', 'Localize',
               'Temporal')                                   # CriterionByModule.criterions keys, train_module.py:36-48
@@ -54,12 +54,22 @@ class LossRows:
         self.att_node, self.att_kind, self.att_slot, self.att_gold, self.att_w = [], [], [], [], []
         self.bin_node, self.bin_which, self.bin_label, self.bin_w = [], [], [], []
         self.con_node, self.con_cls, self.con_w = [], [], []
+        self.ff_node, self.ff_gold, self.ff_w = [], [], []       # criterion_filterframe rows (only when FilterFrame is not excluded)
         self.class_emb = {}                  # class name -> word-embedding phrase [n_w, text] (last writer wins, :364)
         self.counts = {k: 0 for k in LOSS_SLOTS}
 
 
+def filterframe_gold(gold, T, O, word2index):
+    """train_module.py:146-154 — {entity: interval} -> [T, O] soft masks, every frame normalised by its sum (0/0 -> 0)."""
+    g = np.zeros((T, O), np.float32)
+    for key, val in gold.items():
+        g[:, word2index[key]] = span_to_attention(val, T)
+    ssum = g.sum(axis=1, keepdims=True)
+    return np.where(ssum > 0, g / np.where(ssum > 0, ssum, 1), 0).astype(np.float32)
+
+
 def collate_losses(batch: LY.NMNBatch, pretrain_modules, T, module_loss_weight=1.0, gradient_accumulation=None,
-                   modules_no_intermediate_train=('FilterFrame',)) -> LossRows:
+                   modules_no_intermediate_train=('FilterFrame',), word2index=None, object_types=0) -> LossRows:
     """train_module.py:350-373 over every question of the window -> loss rows."""
     ga = float(gradient_accumulation or batch.B)
     rows = LossRows()
@@ -103,9 +113,15 @@ def collate_losses(batch: LY.NMNBatch, pretrain_modules, T, module_loss_weight=1
                 rows.bin_node.append(node); rows.bin_which.append({'Equals': 0, 'Xor': 1, 'Exists': 2}[tok])
                 rows.bin_label.append(int(gold)); rows.bin_w.append(mlw)
                 rows.counts['Equals' if tok == 'Equals' else 'Exists/Xor'] += 1
+            elif tok == 'FilterFrame':                                      # criterion :141-155 (excluded by default, args.py:62)
+                if word2index is None or object_types <= 0:
+                    raise ValueError('FilterFrame supervision needs word2id (CriterionByModule(word2id), train_module.py:33-55) and '
+                                     'config["object_types"]')
+                rows.ff_node.append(node); rows.ff_gold.append(filterframe_gold(gold, T, object_types, word2index))
+                rows.ff_w.append(mlw / (T * object_types))
+                rows.counts['FilterFrame'] += 1
             else:
-                raise NotImplementedError('intermediate supervision of %s is excluded from training by default '
-                                          '(video_nmn/args.py:62, train_module.py:354) and has no CUDA backward here' % tok)
+                raise NotImplementedError('no criterion for module %s (train_module.py:36-48)' % tok)
     return rows
 
 
@@ -153,6 +169,8 @@ def touched_slots(batch: LY.NMNBatch, rows: LossRows, have_heads: bool):
     if have_heads:
         for which in set(rows.bin_which):
             lin(('EQUALS_HEAD', 'XOR_HEAD', 'EXISTS_HEAD')[which])
+        if rows.ff_node:
+            lin('FF_HEAD')
     return s
 
 
@@ -172,7 +190,7 @@ class NMNTrainStep:
 
     def __init__(self, model, module_loss_weight=1.0, decoder_loss_weight=1.0, gradient_accumulation=None,
                  modules_no_intermediate_train=('FilterFrame',), distributed=None, process_group=None, global_negatives=True,
-                 dropout_seed=None, save_activations_budget=24 << 30):
+                 dropout_seed=None, save_activations_budget=24 << 30, word2id=None):
         self.model = model
         self.module_loss_weight, self.decoder_loss_weight = module_loss_weight, decoder_loss_weight
         self.gradient_accumulation = gradient_accumulation
@@ -186,6 +204,12 @@ class NMNTrainStep:
         self.windows_run = 0
         # keep the module intermediates of the forward for the backward when they fit in this many bytes (else recompute them)
         self.save_activations_budget = int(save_activations_budget)
+        # CriterionByModule(word2id) (train_module.py:33-55): entity name -> class id; ids are re-indexed to 0..O-1 in sorted order
+        self.word2index = None
+        if word2id is not None:
+            ids = sorted(set(word2id.values()))
+            id2index = {v: i for i, v in enumerate(ids)}
+            self.word2index = {w: id2index[v] for w, v in word2id.items()}
         self._targets = None
         self._cache = {}
         self.last = None
@@ -233,7 +257,10 @@ class NMNTrainStep:
             dist.all_reduce(cnt, group=self.group)
             n_window = int(cnt.item())
         ga = self.gradient_accumulation or n_window
-        rows = collate_losses(batch, model.pretrain_modules, batch.T, self.module_loss_weight, ga, self.modules_no_intermediate_train)
+        rows = collate_losses(batch, model.pretrain_modules, batch.T, self.module_loss_weight, ga, self.modules_no_intermediate_train,
+                              self.word2index, int(cfg.get('object_types', 0) or 0))
+        if rows.ff_node and not cfg['have_pretrain_head']:
+            raise L.StairError('FilterFrame supervision needs have_pretrain_head (its criterion reads the [T, O] head)')
         rows.counts['decoder'] = batch.B if self.decoder_loss_weight != 0 else 0          # decoder CE applies to every question (:376-380)
         if rows.bin_node and not cfg['have_pretrain_head']:
             raise L.StairError('Exists/Xor/Equals supervision needs have_pretrain_head (their criterion reads the head logits)')
@@ -267,6 +294,7 @@ class NMNTrainStep:
                   up(np.stack(rows.att_gold) if rows.att_gold else np.zeros(0), np.float32), up(rows.att_w, np.float32))
         pl.bin = (up(rows.bin_node, np.int32), up(rows.bin_which, np.int32), up(rows.bin_label, np.int32), up(rows.bin_w, np.float32))
         pl.con = (up(rows.con_node, np.int32), up([pos_of[c] for c in rows.con_cls], np.int32), up(rows.con_w, np.float32))
+        pl.ff = (up(rows.ff_node, np.int32), up(np.stack(rows.ff_gold) if rows.ff_gold else np.zeros(0), np.float32), up(rows.ff_w, np.float32))
         pl.answer = batch.answer.to(torch.int32).to(dev, non_blocking=True)
         pl.touched = touched
         return pl
@@ -286,7 +314,7 @@ class NMNTrainStep:
             cls_rep = torch.empty((len(pl.class_names), H), dtype=torch.float32, device=dev)
             L.check(lib.stair_l2normalize(L.i32(L.dtype_code(sent.dtype)), L.ptr(sent), L.ptr(cls_rep), L.i32(len(pl.class_names)), L.i32(H),
                                           L.stream_ptr()), 'stair_l2normalize')
-        st, ms, sb, bufs = model.prepare(batch, frozenset(), training=True)
+        st, ms, sb, bufs = model.prepare(batch, frozenset(['FilterFrame']) if rows.ff_node else frozenset(), training=True)
         tg, offsets, flat_numel = self._layout()
         flat = torch.zeros(flat_numel, dtype=torch.float32, device=dev)
         tr = L.StairTrain()
@@ -302,6 +330,11 @@ class NMNTrainStep:
         tr.bin_node, tr.bin_which, tr.bin_label, tr.bin_w = (p(t) for t in pl.bin)
         tr.n_con = len(rows.con_node)
         tr.con_node, tr.con_pos, tr.con_w = (p(t) for t in pl.con)
+        tr.n_ff = len(rows.ff_node)
+        if tr.n_ff:
+            tr.ff_node, tr.ff_gold, tr.ff_w = (p(t) for t in pl.ff)
+            dhead = self._buf('dhead_ff', st.head_ff.numel(), torch.float32, dev)
+            tr.dhead_ff, tr.dhead_ff_elems = dhead.data_ptr(), st.head_ff.numel()
         tr.n_cls = len(pl.class_names)
         tr.cls_rep = cls_rep.data_ptr() if cls_rep is not None else None
         tr.answer = pl.answer.data_ptr()
@@ -358,7 +391,7 @@ class NMNTrainStep:
                     used.add(o)
                     prm.grad = g if prm.grad is None else prm.grad + g
         self.last = dict(state=st, plan=pl, flat=flat, offsets=offsets, touched=touched, train=tr, cls_rep=cls_rep)
-        return {'logits': st.logits, 'answers': st.answers, 'loss_terms': loss, 'loss': loss[:7].sum(), 'loss_counts': dict(rows.counts),
+        return {'logits': st.logits, 'answers': st.answers, 'loss_terms': loss, 'loss': loss[:8].sum(), 'loss_counts': dict(rows.counts),
                 'state': st}
 
     def __call__(self, data, assign_grads=True, dropout_seed=None):

@@ -373,3 +373,47 @@ def test_concurrent_backward_lanes_equal_sequential():
         assert g0.keys() == g1.keys()
         for k in g0:
             assert float((g0[k] - g1[k]).norm()) <= 1e-5 * float(g0[k].norm()) + 1e-9, (key, k)
+
+
+@pytest.mark.parametrize('shape', ['rx', 'i3d'])
+def test_filterframe_criterion_when_not_excluded(shape):
+    """criterion_filterframe (train_module.py:141-155) is excluded from training by default (video_nmn/args.py:62); with
+    modules_no_intermediate_train=() its BCELoss(softmax_O(head), gold / rowsum) and the backward through FilterFrame.pretrain_head
+    match the oracle's autograd, and the default (excluded) window is unchanged."""
+    T, V, hid = (8, 256, 128) if shape == 'rx' else (64, 128, 64)
+    cfg = syn.model_config(T=T, V=V, hidden=hid, object_types=16)
+    torch.manual_seed(4)
+    ref_model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
+    weights = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
+    qs = syn.make_questions(28, T, V, seed=55, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    assert any('FilterFrame' in d['nmn_program_list'] for d in qs)
+    word2id = {'obj_%d' % i: i for i in range(cfg['object_types'])}
+    w = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
+    for k in list(w):
+        if k.startswith('submodules.Superlative.localize_module.'):
+            w[k] = w[k.replace('Superlative.localize_module', 'Localize')]
+    oracle = orc.OracleNMN(cfg, w, syn.PRETRAIN_MODULES)
+    crit = orc.OracleCriterion(word2id)
+    total, logs, _ = orc.window_loss(oracle, crit, qs, modules_no_intermediate_train=())
+    assert len(logs['FilterFrame']) > 0
+    total.backward()
+    ref_grads = {k: v.grad.detach() for k, v in w.items() if v.grad is not None and not k.startswith('submodules.Superlative.localize_module.')}
+    assert 'submodules.FilterFrame.pretrain_head.weight' in ref_grads
+    no_grad = [k for k, v in w.items() if v.grad is None]
+    model = _model(cfg, weights, syn.PRETRAIN_MODULES, 'fp32')
+    out = NMNTrainStep(model, modules_no_intermediate_train=(), word2id=word2id)(qs)
+    torch.cuda.synchronize()
+    model.check_status(out['state'])
+    assert abs(float(out['loss']) - float(total)) <= LOSS_TOL['fp32'] * abs(float(total)), (float(out['loss']), float(total))
+    ref_ff = sum(logs['FilterFrame']) / len(qs)
+    assert abs(float(out['loss_terms'][7]) - ref_ff) <= 2 * LOSS_TOL['fp32'] * max(abs(ref_ff), 1e-3)
+    bad = _compare_grads(model, ref_grads, no_grad, 'fp32', 'filterframe ' + shape)
+    assert not bad, '\\n'.join(bad)
+    # without word2id the supervision cannot be built
+    with pytest.raises(ValueError):
+        NMNTrainStep(model, modules_no_intermediate_train=())(qs)
+    # default: excluded, the head gets no gradient
+    for prm in model.parameters():
+        prm.grad = None
+    out2 = NMNTrainStep(model)(qs)
+    assert float(out2['loss_terms'][7]) == 0.0 and model.submodules['FilterFrame'].pretrain_head.weight.grad is None
