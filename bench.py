@@ -93,12 +93,12 @@ def build_inputs(rank, B):
     return qs, batch
 
 
-def cpu_reference_timer(qs, weights, cfg, min_seconds=10.0, max_passes=50):
+def cpu_reference_timer(qs, weights, cfg, min_seconds=10.0, max_passes=50, threads=None):
     """The reference's CPU path restated (oracle port, encoders through torch.nn.LSTM exactly like the reference):
     per-question Python loop, eval, no_grad (train_module.py:229-232 / evaluate.py:33-38)."""
     from oracle import nmn_oracle as orc
     from stair_b200 import synthetic as syn
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     model = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES, aten_lstm=True)
     sample = qs[:CPU_SAMPLE]
     logits = None
@@ -315,6 +315,25 @@ def main():
         for i, (n, _) in enumerate(phases):
             ph_ms[n] += evs[i].elapsed_time(evs[i + 1]) / nrep
         gemm_ms += evs[len(phases)].elapsed_time(evs[len(phases) + 1]) / nrep
+    # ---- audit mode: the same forward with every pretrain head computed (res_by_step / result_of_each_step:
+    # FilterFrame [T, O] head GEMM, L2-normalised Filter / ToAction / Superlative outputs, Exists / Xor / Equals heads) -------------
+    heads = model._head_modules(True, True)
+    for _ in range(3):
+        model.forward_batch(batch, heads)
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(nrep):
+        model.forward_batch(batch, heads)
+    a1.record()
+    barrier()
+    ta = torch.tensor([a0.elapsed_time(a1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+    audit_ms = float(ta.item()) / nrep
+    audit = {'value': world * B / (audit_ms * 1e-3), 'unit': UNIT, 'ms_per_step': audit_ms, 'launches_per_step': model.last_launches,
+             'what': 'forward with all pretrain heads (return_res_by_step / return_result_of_each_step device work)'}
+
     # ---- training step (BASELINE configs[3]): forward with history + intermediate-supervision losses + backward +
     # gradient all-reduce (N > 1) + Adam, one window = the rank's 4096 questions; device-timed, max over ranks -------------
     train = None
@@ -354,7 +373,28 @@ def main():
                  'loss_rows': out['loss_counts'], 'dropout': TRAIN_DROPOUT,
                  'what': 'forward with encoder history + losses (train_module.py:83-194) + backward + %sAdam (one fused multi-tensor kernel that also refreshes the bf16 weight copies); bf16 storage, fp32 gradients'
                          % ('NCCL gradient all-reduce + ' if world > 1 else '')}
-        del tmodel, tstep, opt, plan
+        # the reference-faithful window: 32 questions per optimizer step (train_module.py gradient_accumulation = 32), latency-bound
+        plan32 = tstep.plan(qs[:32])
+
+        def train_step32():
+            o = tstep.run(plan32)
+            opt.step()
+            opt.zero_grad()
+            return o
+
+        for _ in range(3):
+            train_step32()
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(10):
+            train_step32()
+        w1.record()
+        barrier()
+        w32 = w0.elapsed_time(w1) / 10
+        train['window32'] = {'ms_per_step': w32, 'value': 32 / (w32 * 1e-3), 'unit': UNIT,
+                             'what': 'one 32-question window per optimizer step on this rank (reference accumulation window; launch-latency bound)'}
+        del tmodel, tstep, opt, plan, plan32
         torch.cuda.empty_cache()
 
     pk = peaks()
@@ -374,8 +414,10 @@ def main():
         cpu = None
         parity = None
         if not args.no_cpu_baseline and world == 1:
+            qps1, med1, _, _ = cpu_reference_timer(qs, weights, cfg, min_seconds=5.0, max_passes=20, threads=1)
             qps, med, npass, ref_logits = cpu_reference_timer(qs, weights, cfg)
             cpu = {'value': qps, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                   'single_thread': {'value': qps1, 'cores': 1, 'median_s_per_pass': med1},
                    'sample': 'first %d questions of the GPU batch, %d passes, median %.3f s/pass, torch threads=%d; oracle port with the '
                              'encoders through torch.nn.LSTM' % (CPU_SAMPLE, npass, med, torch.get_num_threads())}
             ref_ans = ref_logits.argmax(1)
@@ -411,7 +453,7 @@ def main():
                         'timer': 'wall clock between synchronize()s over all steps; VideoNMN.forward_stream: every step uploads its pinned host batch '
                                  '(%d chunks, copy stream) and reads its answers back (async D2H into pinned memory), 2 steps in flight' % E2E_CHUNKS},
                 'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
-                'roofline': roofline, 'phases_ms': ph_ms, 'train': train, 'cpu_baseline': cpu, 'parity': parity}
+                'roofline': roofline, 'phases_ms': ph_ms, 'audit': audit, 'train': train, 'cpu_baseline': cpu, 'parity': parity}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
