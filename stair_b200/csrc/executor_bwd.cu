@@ -422,21 +422,26 @@ int encoder_bwd(BCtx& b, int e, int dir_lane) {
         const float* cs = reinterpret_cast<const float*>(sv + SL.enc[e].c);
         const bf16* hs = reinterpret_cast<const bf16*>(sv + SL.enc[e].hs);
         const long long hs_dir = static_cast<long long>(S + 1) * B * h, hs_plane = 2 * hs_dir;
-        float* dxproj = b.ws.take<float>(io.rows * 8 * h);
-        const long long dg_dir = static_cast<long long>(S) * B * 4 * h, dg_plane = 2 * dg_dir;
-        bf16* dg_hist = b.ws.take<bf16>(static_cast<long long>(c.np) * dg_plane);     // gate gradients, bf16 planes [np][2][S][B][4h]
+        // blocked (= fused bf16 forward): the gate gradients are kept ONCE, as bf16 rows in token order [rows][8h] — operand of both weight
+        // gradients (dW_ih = dG^T . x, dW_hh = dG^T . h_prev with h_prev in token order, written by the fused forward) and source of the
+        // bias gradient; only the current step's slice [2][B][4h] is also written for the recurrent GEMM.  Otherwise (step-wise forward,
+        // fp32-strict planes): fp32 dxproj + the direction-major plane history.
+        float* dxproj = blocked ? nullptr : b.ws.take<float>(io.rows * 8 * h);
+        bf16* dxb = blocked ? b.ws.take<bf16>(io.rows * 8 * h) : nullptr;
+        const long long dg_dir = blocked ? static_cast<long long>(B) * 4 * h : static_cast<long long>(S) * B * 4 * h, dg_plane = 2 * dg_dir;
+        bf16* dg_hist = b.ws.take<bf16>(static_cast<long long>(c.np) * dg_plane);     // gate gradients, bf16 planes [np][2][S | 1][B][4h]
         float* dh_rec = b.ws.take<float>(2LL * B * h);
         float* dc = b.ws.take<float>(2LL * B * h);
         const float* dout = e == 0 ? tr.dvid : tr.dtokfeat;
         for (int s = S - 1; s >= 0; --s) {
-            bf16* dg_step = dg_hist + static_cast<long long>(s) * B * 4 * h;
+            bf16* dg_step = blocked ? dg_hist : dg_hist + static_cast<long long>(s) * B * 4 * h;
             const float* c_prev = s > 0 ? cs + static_cast<long long>(s - 1) * 2 * B * h : cs;
             if (blocked)
-                RUN(launch_lstm_cell_bwd(gates, nullptr, cs, dout, dh_rec, e == 1 ? tr.dqfeat : nullptr, dc, dg_dir, dg_step, dg_plane, c.np, dxproj,
+                RUN(launch_lstm_cell_bwd(gates, nullptr, cs, dout, dh_rec, e == 1 ? tr.dqfeat : nullptr, dc, dg_dir, dg_step, dg_plane, c.np, nullptr, dxb,
                                          io.q_off, B, c.T, h, s, S - 1, 1, c.st));
             else
                 RUN(launch_lstm_cell_bwd(gates + static_cast<long long>(s) * 2 * B * 4 * h, c_prev, cs + static_cast<long long>(s) * 2 * B * h, dout, dh_rec,
-                                         e == 1 ? tr.dqfeat : nullptr, dc, dg_dir, dg_step, dg_plane, c.np, dxproj, io.q_off, B, c.T, h, s, S - 1, 0, c.st));
+                                         e == 1 ? tr.dqfeat : nullptr, dc, dg_dir, dg_step, dg_plane, c.np, dxproj, nullptr, io.q_off, B, c.T, h, s, S - 1, 0, c.st));
             if (s > 0) {
                 // dh_{s-1} = dG_s . W_hh of the two directions are independent and small (B/128 x h/128 tiles each): the reverse direction
                 // runs on a side stream next to the forward one instead of after it
@@ -457,6 +462,38 @@ int encoder_bwd(BCtx& b, int e, int dir_lane) {
                     if (cudaEventRecord(ls->join[dir_lane], ls->side[dir_lane]) != cudaSuccess || cudaStreamWaitEvent(c.st, ls->join[dir_lane], 0) != cudaSuccess) return STAIR_ERR_CUDA;
                 }
             }
+        }
+        if (blocked) {
+            const long long rows = io.rows;
+            const bf16* hs_tok = hs;                              // [rows][2h] h_prev in token order (lstm_fused.cu HIST)
+            for (int d = 0; d < 2; ++d) {                         // dW_hh[d] += dG[:, d]^T . h_prev[:, d] over all token rows
+                float* gW = G(b, d == 0 ? io.whh_f : io.whh_r);
+                if (!gW) continue;
+                GemmArgs a;
+                a.A = dxb + d * 4 * h; a.lda = 8 * h; a.a_plane_rows = static_cast<int>(rows); a.nplanes = 1;
+                a.W = hs_tok + d * h; a.ldw = 2 * h; a.w_plane_rows = static_cast<int>(rows);
+                a.C = gW; a.ldc = h; a.out_dtype = STAIR_F32; a.M = 4 * h; a.N = h; a.K = static_cast<int>(rows); a.accumulate = 1; a.mn_major = 1;
+                RUN(launch_gemm(a, c.st));
+            }
+            // d(b_ih + b_hh) = column sums of the gate gradients; dW_ih = dG^T . x over the token rows (x in place when it is bf16)
+            RUN(launch_colsum_bf16(dxb, rows, 8 * h, 8 * h, G(b, io.bias), c.st));
+            float* gWih = G(b, io.wih);
+            if (gWih) {
+                const bool direct = e == 0 && bt.video_dtype == STAIR_BF16 && (m.V % 8) == 0;
+                const bf16* xin_p = reinterpret_cast<const bf16*>(io.xin);
+                if (!direct) {
+                    bf16* in = b.ws.take<bf16>(io.rows * io.Kin_ld);
+                    RUN(launch_stage_rows(io.xin_dt, io.xin, io.Kin, nullptr, 1, 1, in, io.Kin_ld, io.rows, 1, io.rows, io.Kin, c.st));
+                    xin_p = in;
+                }
+                GemmArgs a;
+                a.A = dxb; a.lda = 8 * h; a.a_plane_rows = static_cast<int>(rows); a.nplanes = 1;
+                a.W = xin_p; a.ldw = io.Kin_ld; a.w_plane_rows = static_cast<int>(rows);
+                a.C = gWih; a.ldc = io.Kin; a.out_dtype = STAIR_F32; a.M = 8 * h; a.N = io.Kin; a.K = static_cast<int>(rows); a.accumulate = 1; a.mn_major = 1;
+                RUN(launch_gemm(a, c.st));
+            }
+            b.ws.off = mark;
+            return STAIR_OK;
         }
         // dW_hh[d] += sum_s dG[d][s]^T h[d][s-1]: one contraction over all (step, question) rows per direction, both operands in place
         for (int d = 0; d < 2; ++d) {

@@ -34,8 +34,8 @@ struct LstmSeq {
     // training (HIST): per-step history for BPTT.  Gates (post-activation i,f,g,o) and cell state are written in the BLOCKED layout of
     // train_kernels.cuh (lstm_hist_gate_off / lstm_hist_c_off: [step][dir][32-row block][8-unit block][gate][row][8 units]) so that a
     // warp's stores are contiguous (row-major history = 32 scattered 16-byte pieces per store instruction, measured 3x slower);
-    // the cell history is also the running c (no private scratch).  h goes to bf16 [2][S+1][B][h] row-major (row block s+1 = h after
-    // step s): it is the A operand of the dW_hh GEMM.
+    // the cell history is also the running c (no private scratch).  h goes to hs_h [rows][2h] bf16 in token order, shifted by one step
+    // (row of token r holds the state BEFORE r was consumed): the second operand of the dW_hh contraction.
     float* gates_h; float* c_h; bf16* hs_h; long long hs_dir;
 };
 
@@ -312,7 +312,9 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                         uint4 o0;
                         o0.x = pack_bf16(hn[0], hn[1]); o0.y = pack_bf16(hn[2], hn[3]); o0.z = pack_bf16(hn[4], hn[5]); o0.w = pack_bf16(hn[6], hn[7]);
                         *reinterpret_cast<uint4*>(orow + u0) = o0;
-                        if (HIST) *reinterpret_cast<uint4*>(sq.hs_h + static_cast<long long>(dir) * sq.hs_dir + (static_cast<long long>(s + 1) * sq.B + grow) * h + u0) = o0;
+                        // h_s is the *previous* state of the next step's token: stored at that token's row ([rows][2h], zero where a direction
+                        // starts), so dW_hh = dGates^T . h_prev is one contraction over token rows with both operands in token order
+                        if (HIST && s + 1 < L) *reinterpret_cast<uint4*>(sq.hs_h + (tokrow + (dir == 0 ? 1 : -1)) * 2 * h + dir * h + u0) = o0;
                         if (last) *reinterpret_cast<uint4*>(sq.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0) = o0;
                         st_shared_v4(h_dst + a0, o0.x, o0.y, o0.z, o0.w);
                     } else {

@@ -1146,6 +1146,34 @@ int launch_loss_ff(const float* head, float* dhead, const int* aux_slot, const i
     return STAIR_OK;
 }
 
+// db[c] += sum_rows x[row][c] for a bf16 matrix (bias gradient of the encoder input projections from the bf16 gate gradients);
+// a block owns 64 columns x a slab of rows, 4 row-groups of 64 threads, one atomic per column and block
+__global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long rows, int cols, long long ld, float* __restrict__ db, long long rows_per_block) {
+    __shared__ float red[4][64];
+    const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int c = blockIdx.x * 64 + cl;
+    const long long r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    float s = 0.f;
+    if (c < cols)
+        for (long long r = r0 + rg; r < r1; r += 4) s += __bfloat162float(x[r * ld + c]);
+    red[rg][cl] = s;
+    __syncthreads();
+    if (rg == 0 && c < cols) {
+        const float t = red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl];
+        if (t != 0.f) atomicAdd(db + c, t);
+    }
+}
+int launch_colsum_bf16(const bf16* x, long long rows, int cols, long long ld, float* db, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0 || !db) return STAIR_OK;
+    const int gx = (cols + 63) / 64;
+    int gy = static_cast<int>((148 * 8 + gx - 1) / gx);
+    if (gy > rows / 64 + 1) gy = static_cast<int>(rows / 64 + 1);
+    const long long rpb = (rows + gy - 1) / gy;
+    colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, rows, cols, ld, db, rpb);
+    STAIR_CHECK_LAUNCH();
+    return STAIR_OK;
+}
+
 __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
         float4 a = reinterpret_cast<float4*>(dst)[i];
@@ -1253,7 +1281,8 @@ int launch_lstm_cell_train(int xdt, const void* xproj, const float* g, const flo
 __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
                                      const float* __restrict__ dout, const float* __restrict__ dh_rec, const float* __restrict__ dqfeat,
                                      float* __restrict__ dc, long long dg_dir, bf16* __restrict__ dg_planes, long long dg_plane, int nplanes,
-                                     float* __restrict__ dxproj, const int* __restrict__ q_off, int B, int T, int h, int step, int last_step, int blocked) {
+                                     float* __restrict__ dxproj, bf16* __restrict__ dxproj_bf16, const int* __restrict__ q_off, int B, int T, int h, int step,
+                                     int last_step, int blocked) {
     const long long total = 2LL * B * h;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int d = static_cast<int>(i / (static_cast<long long>(B) * h));
@@ -1291,8 +1320,13 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const floa
             dpg = dct * ig * (1.f - gg * gg);
             dpo = dh * tc * og * (1.f - og);
             dc[si] = dct * fg;
-            float* xr = dxproj + row * 8 * h + d * 4 * h + j;
-            xr[0] = dpi; xr[h] = dpf; xr[2 * h] = dpg; xr[3 * h] = dpo;
+            if (dxproj_bf16) {                                   // bf16 path: the row-major bf16 copy IS the weight-gradient GEMM operand
+                bf16* xb = dxproj_bf16 + row * 8 * h + d * 4 * h + j;
+                xb[0] = __float2bfloat16_rn(dpi); xb[h] = __float2bfloat16_rn(dpf); xb[2 * h] = __float2bfloat16_rn(dpg); xb[3 * h] = __float2bfloat16_rn(dpo);
+            } else {
+                float* xr = dxproj + row * 8 * h + d * 4 * h + j;
+                xr[0] = dpi; xr[h] = dpf; xr[2 * h] = dpg; xr[3 * h] = dpo;
+            }
         } else {
             dc[si] = 0.f;
         }
@@ -1307,12 +1341,12 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const floa
 }
 
 int launch_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_cur, const float* dout, const float* dh_rec, const float* dqfeat,
-                         float* dc, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, const int* q_off,
+                         float* dc, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, bf16* dxproj_bf16, const int* q_off,
                          int B, int T, int h, int step, int last_step, int blocked, cudaStream_t st) {
     if (B <= 0) return STAIR_OK;
     if (blocked && (h % 8)) return STAIR_ERR_ARG;
     lstm_cell_bwd_kernel<<<nblocks(2LL * B * h, 256), 256, 0, st>>>(gates, c_prev, c_cur, dout, dh_rec, dqfeat, dc, dg_dir, dg_planes, dg_plane, nplanes,
-                                                                   dxproj, q_off, B, T, h, step, last_step, blocked);
+                                                                   dxproj, dxproj_bf16, q_off, B, T, h, step, last_step, blocked);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }

@@ -82,8 +82,9 @@ int launch_lstm_cell_train(int xdt, const void* xproj, const float* g, const flo
 // blocked = 0: gates / c_prev / c_cur point at step `step`'s row-major slices ([2][B][4h], [2][B][h]; c_prev at step-1's);
 // blocked = 1: gates / c_cur are the BASE of the blocked history (lstm_hist_*_off), c_prev is ignored.
 int launch_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_cur, const float* dout, const float* dh_rec, const float* dqfeat,
-                         float* dc, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, const int* q_off,
-                         int B, int T, int h, int step, int last_step, int blocked, cudaStream_t st);
+                         float* dc, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, bf16* dxproj_bf16, const int* q_off,
+                         int B, int T, int h, int step, int last_step, int blocked, cudaStream_t st);     // dxproj_bf16 != null: bf16 rows instead of fp32
+int launch_colsum_bf16(const bf16* x, long long rows, int cols, long long ld, float* db, cudaStream_t st);      // db[c] += sum_r x[r][c]
 
 int launch_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, double b1, double b2, float eps, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, double b1, double b2, float eps, float bc1, float bc2, cudaStream_t st);

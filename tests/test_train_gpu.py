@@ -417,3 +417,32 @@ def test_filterframe_criterion_when_not_excluded(shape):
         prm.grad = None
     out2 = NMNTrainStep(model)(qs)
     assert float(out2['loss_terms'][7]) == 0.0 and model.submodules['FilterFrame'].pretrain_head.weight.grad is None
+
+
+def test_fused_recurrence_training_path_matches_stepwise_bf16():
+    """bf16 training: fused forward recurrence + blocked history + token-order bf16 gate gradients (dW_ih / dW_hh / bias straight from
+    them) == the step-wise path (per-step GEMM + cell kernels, fp32 dxproj + staging) up to the fused kernel's tanh.approx activations."""
+    from stair_b200 import _lib as L
+    cfg = syn.model_config(T=8, V=256, hidden=128, object_types=16)
+    torch.manual_seed(13)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().train()
+    qs = syn.make_questions(150, 8, 256, seed=23, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    res = {}
+    try:
+        for impl in (1, 0):
+            L.lib().stair_set_lstm_impl(impl)
+            for prm in model.parameters():
+                prm.grad = None
+            out = NMNTrainStep(model)(qs)
+            torch.cuda.synchronize()
+            model.check_status(out['state'])
+            res[impl] = (float(out['loss']), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    finally:
+        L.lib().stair_set_lstm_impl(0)
+    (l1, g1), (l0, g0) = res[1], res[0]
+    assert abs(l0 - l1) <= 5e-3 * abs(l1)
+    assert g0.keys() == g1.keys()
+    for k in g1:
+        if 'encoder' in k:                                # the tensors the two paths compute differently
+            l2 = float((g0[k] - g1[k]).norm()) / max(float(g1[k].norm()), 1e-30)
+            assert l2 <= 5e-2, '%s: relative L2 %g' % (k, l2)
