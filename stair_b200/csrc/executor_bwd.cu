@@ -17,6 +17,7 @@ using namespace ex;
 
 extern int g_bwd_lanes;
 int g_dw_impl = 0;      // 0 = MN-major weight-gradient GEMM (product); 1 = transposed copies + K-major GEMM (comparison)
+int g_bptt_impl = 0;    // 0 = persistent fused BPTT kernel when eligible (lstm_bptt.cu; product); 1 = per-step cell kernel + recurrent GEMMs
 
 struct Bump {
     char* base = nullptr;
@@ -406,7 +407,7 @@ int run_encoders_train(Ctx& c, const StairTrain& tr) {
 
 // BPTT of one encoder (e = 0 video, 1 text) on the stream of b.c; `dir_lane` = index of the side stream that runs the reverse direction's
 // recurrent GEMMs next to the forward direction's
-int encoder_bwd(BCtx& b, int e, int dir_lane) {
+int encoder_bwd(BCtx& b, int e, int dir_lane, bf16* dxb_done = nullptr) {
     Ctx& c = b.c;
     const StairTrain& tr = b.tr;
     const StairModel& m = c.m; const StairBatch& bt = c.b;
@@ -426,14 +427,16 @@ int encoder_bwd(BCtx& b, int e, int dir_lane) {
         // gradients (dW_ih = dG^T . x, dW_hh = dG^T . h_prev with h_prev in token order, written by the fused forward) and source of the
         // bias gradient; only the current step's slice [2][B][4h] is also written for the recurrent GEMM.  Otherwise (step-wise forward,
         // fp32-strict planes): fp32 dxproj + the direction-major plane history.
+        // dxb_done: the persistent fused BPTT kernel (encoders_bwd) already produced the token-order gate gradients of this encoder
         float* dxproj = blocked ? nullptr : b.ws.take<float>(io.rows * 8 * h);
-        bf16* dxb = blocked ? b.ws.take<bf16>(io.rows * 8 * h) : nullptr;
+        bf16* dxb = dxb_done ? dxb_done : blocked ? b.ws.take<bf16>(io.rows * 8 * h) : nullptr;
+        const int S_loop = dxb_done ? 0 : S;
         const long long dg_dir = blocked ? static_cast<long long>(B) * 4 * h : static_cast<long long>(S) * B * 4 * h, dg_plane = 2 * dg_dir;
-        bf16* dg_hist = b.ws.take<bf16>(static_cast<long long>(c.np) * dg_plane);     // gate gradients, bf16 planes [np][2][S | 1][B][4h]
-        float* dh_rec = b.ws.take<float>(2LL * B * h);
-        float* dc = b.ws.take<float>(2LL * B * h);
+        bf16* dg_hist = dxb_done ? nullptr : b.ws.take<bf16>(static_cast<long long>(c.np) * dg_plane);     // gate gradients, bf16 planes [np][2][S | 1][B][4h]
+        float* dh_rec = dxb_done ? nullptr : b.ws.take<float>(2LL * B * h);
+        float* dc = dxb_done ? nullptr : b.ws.take<float>(2LL * B * h);
         const float* dout = e == 0 ? tr.dvid : tr.dtokfeat;
-        for (int s = S - 1; s >= 0; --s) {
+        for (int s = S_loop - 1; s >= 0; --s) {
             bf16* dg_step = blocked ? dg_hist : dg_hist + static_cast<long long>(s) * B * 4 * h;
             const float* c_prev = s > 0 ? cs + static_cast<long long>(s - 1) * 2 * B * h : cs;
             if (blocked)
@@ -527,6 +530,31 @@ int encoder_bwd(BCtx& b, int e, int dir_lane) {
 int encoders_bwd(BCtx& b) {
     Ctx& c = b.c;
     LaneStreams* ls = (!b.dry && g_lanes > 1) ? lane_streams() : nullptr;
+    const long long mark0 = b.ws.off;
+    // bf16 path: the whole time loop of both encoders and both directions is ONE persistent launch (lstm_bptt.cu); what remains per
+    // encoder is the weight / bias gradients from the token-order gate gradients it leaves behind
+    bf16* dxb_done[2] = {nullptr, nullptr};
+    const StairModel& m = c.m;
+    const bool fused_bptt = fused_history(c) && g_bptt_impl == 0 && lstm_bptt_fused_ok(m.precision, c.h) && m.wt[STAIR_W_VENC_WHH_F] &&
+                            m.wt[STAIR_W_VENC_WHH_R] && m.wt[STAIR_W_TENC_WHH_F] && m.wt[STAIR_W_TENC_WHH_R];
+    if (fused_bptt) {
+        const int B = c.b.B, h = c.h;
+        const SavedLayout SL = saved_layout(m, c.b);
+        char* sv = reinterpret_cast<char*>(b.tr.saved);
+        LstmBptt a;
+        for (int e = 0; e < 2; ++e) {
+            const EncIO io = enc_io(c, e);
+            dxb_done[e] = b.ws.take<bf16>(io.rows * 8 * h);
+            a.gates[e] = reinterpret_cast<const float*>(sv + SL.enc[e].gates);
+            a.c[e] = reinterpret_cast<const float*>(sv + SL.enc[e].c);
+            a.dout[e] = e == 0 ? b.tr.dvid : b.tr.dtokfeat;
+            a.dxb[e] = dxb_done[e];
+            a.dc[e] = b.ws.take<float>(2LL * align_up(B, 64) * h);
+            a.whhT[2 * e] = m.wt[io.whh_f]; a.whhT[2 * e + 1] = m.wt[io.whh_r];
+        }
+        a.dqfeat = b.tr.dqfeat;
+        RUN(launch_lstm_bptt_fused(a, B, h, c.T, c.b.L_max, c.b.q_off, err_flag_ptr(), c.st));
+    }
     const long long mark = b.ws.off;
     // video (e = 0): side stream 2 (+ side stream 3 for its reverse-direction GEMMs); workspace [mark, video peak)
     Ctx cv = c;
@@ -536,14 +564,14 @@ int encoders_bwd(BCtx& b) {
     }
     BCtx bv{cv, b.tr, b.ws, b.dry};
     bv.ws.peak = mark;
-    const int rc_v = encoder_bwd(bv, 0, 3);
+    const int rc_v = encoder_bwd(bv, 0, 3, dxb_done[0]);
     if (rc_v != STAIR_OK) return rc_v;
     if (bv.ws.overflow) b.ws.overflow = true;
     // text (e = 1): caller's stream (+ side stream 0), workspace after the video encoder's
     b.ws.off = bv.ws.peak;
     if (b.ws.off > b.ws.peak) b.ws.peak = b.ws.off;
-    STAIR_TRY(encoder_bwd(b, 1, 0));
-    b.ws.off = mark;
+    STAIR_TRY(encoder_bwd(b, 1, 0, dxb_done[1]));
+    b.ws.off = mark0;
     if (ls) {
         if (cudaEventRecord(ls->join[2], ls->side[2]) != cudaSuccess || cudaStreamWaitEvent(c.st, ls->join[2], 0) != cudaSuccess) return STAIR_ERR_CUDA;
     }
@@ -816,6 +844,7 @@ extern "C" int stair_adam_step(float* param, const float* grad, float* exp_avg, 
 
 extern "C" int stair_set_bwd_lanes(int lanes) { g_bwd_lanes = lanes < 1 ? 1 : (lanes > LANES ? LANES : lanes); return STAIR_OK; }
 extern "C" int stair_set_dw_impl(int impl) { g_dw_impl = impl ? 1 : 0; return STAIR_OK; }
+extern "C" int stair_set_bptt_impl(int impl) { g_bptt_impl = impl ? 1 : 0; return STAIR_OK; }
 
 extern "C" int stair_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, double beta1, double beta2, float eps, void* stream) {
     if (!segs && n_segs > 0) return STAIR_ERR_ARG;

@@ -90,6 +90,16 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
                       const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st,
                       const LstmHist* hist = nullptr);
 
+// fused persistent BPTT of both encoders and directions (lstm_bptt.cu; bf16 path, after a fused forward with history).
+// index 0 = video, 1 = text.  gates / c: the forward's blocked history; dout: fp32 [rows][2h] gradient of the encoder output; dxb: bf16
+// [rows][8h] gate pre-activation gradients in token order (output); dc: scratch of 2 * ceil(B/64)*64 * h floats per encoder;
+// whhT[2*e + dir]: transposed W_hh copies [h][4h] (StairModel.wt).
+struct LstmBptt {
+    const float* gates[2]; const float* c[2]; const float* dout[2]; const float* dqfeat; bf16* dxb[2]; float* dc[2]; const void* whhT[4];
+};
+bool lstm_bptt_fused_ok(int precision, int h);
+int launch_lstm_bptt_fused(const LstmBptt& a, int B, int h, int T, int L_max, const int* q_off, int* err_flag, cudaStream_t st);
+
 // ---- layout grouping (layout_group.cu) ----------------------------------------------------------------------------
 int launch_group_layouts(const StairBatch& b, int32_t* itab, int32_t* status, cudaStream_t st);
 

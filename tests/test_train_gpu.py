@@ -446,3 +446,35 @@ def test_fused_recurrence_training_path_matches_stepwise_bf16():
         if 'encoder' in k:                                # the tensors the two paths compute differently
             l2 = float((g0[k] - g1[k]).norm()) / max(float(g1[k].norm()), 1e-30)
             assert l2 <= 5e-2, '%s: relative L2 %g' % (k, l2)
+
+
+@pytest.mark.parametrize('hidden,n_q', [(128, 150), (512, 200), (256, 64)])
+def test_persistent_bptt_matches_stepwise_bptt(hidden, n_q):
+    """stair_set_bptt_impl(0) (product): the backward time loop of both BiLSTM encoders and both directions in ONE persistent launch
+    (csrc/lstm_bptt.cu: gate gradients -> shared memory -> tcgen05 dh_rec, double-buffered in TMEM) == the per-step cell kernel +
+    recurrent GEMMs (impl 1) from the same fused-forward history.  Both round the gate gradients to bf16 once, so the encoder gradients
+    agree to fp32 summation order; ragged question lengths and a batch that is not a multiple of the 64-question CTA are covered."""
+    from stair_b200 import _lib as L
+    cfg = syn.model_config(T=8, V=256, hidden=hidden, object_types=16)
+    torch.manual_seed(17)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().train()
+    qs = syn.make_questions(n_q, 8, 256, seed=29, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    res = {}
+    try:
+        for impl in (1, 0):
+            L.lib().stair_set_bptt_impl(impl)
+            for prm in model.parameters():
+                prm.grad = None
+            out = NMNTrainStep(model)(qs)
+            torch.cuda.synchronize()
+            model.check_status(out['state'])
+            res[impl] = (float(out['loss']), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    finally:
+        L.lib().stair_set_bptt_impl(0)
+    (l1, g1), (l0, g0) = res[1], res[0]
+    assert abs(l0 - l1) <= 1e-6 * abs(l1)
+    assert g0.keys() == g1.keys()
+    for k in g1:
+        if 'encoder' in k:
+            l2 = float((g0[k] - g1[k]).norm()) / max(float(g1[k].norm()), 1e-30)
+            assert l2 <= 5e-3, '%s: relative L2 %g' % (k, l2)
