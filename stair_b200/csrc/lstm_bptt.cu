@@ -14,8 +14,10 @@
 //   transposed W_hh copy (StairModel.wt, [h][4h]: box {64 k, 256 n} at k = gate*h + 64c) streamed through a TMA ring; D is
 //   double-buffered in TMEM by step parity so the MMA of step s-1 never waits for the last reads of D_s.
 //
-// Warps (512 threads, 128 registers): 2 TMA producer, 3 MMA issuer, 6 TMEM allocator, 7 L2 prefetch of the next steps' history,
+// Warps (512 threads, 128 registers): 2 TMA producer, 3 MMA issuer, 6 TMEM allocator,
 // epilogue = the 8 warps whose TMEM lane quarter (warp % 4) is 0 or 1 (rows 0-63), 4 column groups of 16 units per chunk.
+// (An L2-prefetch warp running 1-3 steps ahead was measured and removed: 795 -> 875-895 us and 1.53 -> 2.8-3.1 GB of DRAM reads at
+// B = 4096 — the steps in flight of 148 CTAs do not stay in L2.)
 #include "nmn_kernels.cuh"
 #include "tc_ptx.cuh"
 #include "train_kernels.cuh"
@@ -79,7 +81,6 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
     uint64_t* d_empty = d_full + 2;                 // [2] epilogue done reading D of a step
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(d_empty + 2);
     int* s_steps = reinterpret_cast<int*>(tmem_ptr_smem + 1);
-    volatile int* s_progress = s_steps + 1;         // steps the epilogue has finished (paces the prefetcher; a hint, no ordering needed)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < LB_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -89,7 +90,6 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *s_steps = ragged ? 0 : sq.steps;
-        *s_progress = 0;
     }
     if (warp == 6) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr_smem)) : "memory");
@@ -157,30 +157,6 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
                     umma_commit(&a_empty[ab]);
                 }
                 umma_commit(&d_full[db]);
-            }
-        }
-    } else if (warp == 7) {
-        // ===================== L2 prefetcher: history + output-gradient rows of step s-2 (independent of the recurrence) ==========
-        const long long RB = (sq.B + 127) / 128 * 4;
-        for (int s = S - 1; s >= 0; --s) {
-            // paced at most three steps ahead of the epilogue (bounded spin: pacing only)
-            for (int spin = 0; spin < (1 << 20) && *s_progress < (S - 1 - s) - 2; ++spin) __nanosleep(64);
-            for (int rb = 0; rb < 2; ++rb) {
-                const long long blk = ((static_cast<long long>(s) * 2 + dir) * RB + ((row0 >> 5) + rb)) * (h >> 3);
-                const char* gp = reinterpret_cast<const char*>(sq.gates_h + blk * 1024);
-                const char* cp = reinterpret_cast<const char*>(sq.c_h + blk * 256);
-                for (int o = lane * 128; o < (h >> 3) * 4096; o += 32 * 128) prefetch_l2(gp + o);
-                for (int o = lane * 128; o < (h >> 3) * 1024; o += 32 * 128) prefetch_l2(cp + o);
-            }
-            for (int r = lane; r < LB_ROWS; r += 32) {
-                const int grow = row0 + r;
-                if (grow >= sq.B) continue;
-                int base, L = sq.steps;
-                if (ragged) { base = __ldg(sq.q_off + grow); L = __ldg(sq.q_off + grow + 1) - base; }
-                else base = grow * sq.steps;
-                if (s >= L) continue;
-                const float* drow = sq.dout + (static_cast<long long>(base) + (dir == 0 ? s : L - 1 - s)) * 2 * h + dir * h;
-                for (int b = 0; b < h * 4; b += 128) prefetch_l2(reinterpret_cast<const char*>(drow) + b);
             }
         }
     } else if (is_epi) {
@@ -304,7 +280,6 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
                 tcgen05_fence_before();
                 mbar_arrive(&d_empty[dbuf]);
             }
-            if (threadIdx.x == 0) *s_progress = it + 1;
         }
     }
     tcgen05_fence_before();
