@@ -4,9 +4,11 @@
 // critical path of the training step).
 //
 // One CTA owns 64 questions of one (encoder, direction) for all steps, walking s = S-1 .. 0:
-//   dh_s      = d(encoder output)[token row] (+ dh_rec from step s+1: TMEM) (+ d question_feature at a question's last step)
-//   gate math = the derivative of the cell (lstm.cu / train_kernels.cu lstm_cell_bwd_kernel) from the forward's blocked history
-//               (gates i,f,g,o post-activation and cell states, lstm_hist_*_off) and the running dc (fp32, private, coalesced)
+//   dh_s      = d(encoder output)[token row] (+ dh_rec from step s+1: TMEM); d question_feature is added to the rows of each
+//               question's last step by a small kernel before the loop
+//   gate math = the derivative of the cell (lstm.cu / train_kernels.cu lstm_cell_bwd_kernel) from the forward's blocked bf16
+//               coefficient history (train_kernels.cuh lstm_hist_coef_off: six multiplies per unit, no transcendentals) and the
+//               running dc (fp32, private, coalesced)
 //   dG_s      -> bf16 rows [rows][8h] in token order (the operand of dW_ih / dW_hh / bias, executor_bwd.cu) and, as the A operand of
 //               dh_rec_{s-1} = dG_s . W_hh, into shared memory: chunk c = the four gates of hidden units 64c .. 64c+63 = four k-blocks
 //               (one per gate) of a [128 x 256] K-major SWIZZLE_128B tile, double-buffered by chunk parity
@@ -14,10 +16,10 @@
 //   transposed W_hh copy (StairModel.wt, [h][4h]: box {64 k, 256 n} at k = gate*h + 64c) streamed through a TMA ring; D is
 //   double-buffered in TMEM by step parity so the MMA of step s-1 never waits for the last reads of D_s.
 //
-// Warps (512 threads, 128 registers): 2 TMA producer, 3 MMA issuer, 6 TMEM allocator,
+// Warps (448 threads, 144 registers): 2 TMA producer, 3 MMA issuer, 6 TMEM allocator,
 // epilogue = the 8 warps whose TMEM lane quarter (warp % 4) is 0 or 1 (rows 0-63), 4 column groups of 16 units per chunk.
-// (An L2-prefetch warp running 1-3 steps ahead was measured and removed: 795 -> 875-895 us and 1.53 -> 2.8-3.1 GB of DRAM reads at
-// B = 4096 — the steps in flight of 148 CTAs do not stay in L2.)
+// L2 prefetching was measured and removed twice: a warp running 1-3 steps ahead doubled the DRAM reads (the steps in flight of 148
+// CTAs do not stay in L2) and prefetching 2-8 sub-block iterations ahead from the epilogue changed nothing (850 us either way).
 #include "nmn_kernels.cuh"
 #include "tc_ptx.cuh"
 #include "train_kernels.cuh"
@@ -31,15 +33,13 @@ constexpr int LB_KB_BYTES = 128 * 64 * 2;          // one 64-wide k-block of the
 constexpr int LB_A_BYTES = 4 * LB_KB_BYTES;        // one chunk: 4 gates x 64 units
 constexpr int LB_W_STAGE_BYTES = 256 * 64 * 2;     // one B tile (256 n x 64 k): 32 KiB
 constexpr int LB_STAGES = 3;
-constexpr int LB_THREADS = 512;
+constexpr int LB_THREADS = 448;                     // 14 warps: the last epilogue warp is 13 (144 registers per thread)
 constexpr int LB_EPI = 256;                        // epilogue threads
 constexpr uint32_t LB_IDESC = make_idesc_bf16(128, 256);
 
 struct BpttSeq {
-    const float* gates_h;   // blocked history (lstm_hist_gate_off)
-    const float* c_h;       // blocked history (lstm_hist_c_off)
+    const bf16* coef_h;     // blocked bf16 coefficient history of the fused forward (train_kernels.cuh lstm_hist_coef_off)
     const float* dout;      // [rows][2h] gradient of the encoder output
-    const float* dqfeat;    // text: [B][2h] gradient of question_feature (added at a question's last step); video: null
     bf16* dxb;              // [rows][8h] gate pre-activation gradients, token order
     float* dc;              // running dc scratch [2][nblk][h][64]
     const int* q_off;       // text: [B+1]; video: null
@@ -52,7 +52,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// operands of one sub-block iteration of the cell backward (8 hidden units of one question row)
+struct BpttStage { uint4 co[LSTM_NCOEF]; float4 dh[2]; };
+// j-th of the 8 bf16 values packed in a uint4
+__device__ __forceinline__ float coef_at(const uint4& v, int j) {
+    const uint32_t w = j < 2 ? v.x : j < 4 ? v.y : j < 6 ? v.z : v.w;
+    return __uint_as_float((j & 1) ? (w & 0xFFFF0000u) : (w << 16));
+}
 
 __global__ void __launch_bounds__(LB_THREADS, 1)
 lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
@@ -160,7 +166,10 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
             }
         }
     } else if (is_epi) {
-        // ===================== cell backward: thread = question row, 16 units per chunk =============================================
+        // ===================== cell backward: thread = question row, 16 units per chunk (two sub-blocks of 8) =========================
+        // The step is a chain of 2 NC sub-block iterations, each needing ~100 bytes per thread from HBM (coefficients, output gradient)
+        // and L2 (dc): the operands of iteration k+1 are requested before iteration k is processed (two register stages), so the
+        // recurrence waits on the tensor core, not on memory.
         const int row = quarter * 32 + lane;
         const int grow = row0 + row;
         const bool valid = grow < sq.B;
@@ -176,15 +185,78 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
         const uint32_t sA0 = smem_u32(sA);
         const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
         const uint32_t sw = static_cast<uint32_t>(row & 7);
-        int aw[2] = {0, 0};                                        // writes into each chunk buffer so far
+
+        auto load_stage = [&](BpttStage& st, int s, int c, int sb) {
+            if (s < 0 || s >= L) return;
+            const int u0 = c * 64 + cgrp * 16 + sb * 8;
+            const bf16* cp = sq.coef_h + (s * hist_step + hist_rb + (u0 >> 3)) * (LSTM_NCOEF * 256) + lane * 8;
+#pragma unroll
+            for (int k = 0; k < LSTM_NCOEF; ++k) st.co[k] = ld_stream_v4(cp + k * 256);
+            const float* drow = sq.dout + (static_cast<long long>(base) + (dir == 0 ? s : L - 1 - s)) * 2 * h + dir * h + u0;
+            st.dh[0] = __ldg(reinterpret_cast<const float4*>(drow));
+            st.dh[1] = __ldg(reinterpret_cast<const float4*>(drow + 4));
+        };
+        // running dc of one sub-block (written by this thread one step ago: L2).  One register set: the next iteration's values are
+        // requested as soon as the current ones are consumed, half an iteration ahead of their use
+        float4 dcr[2];
+        auto load_dc = [&](int s, int c, int sb) {
+            if (s < 0 || s + 1 >= L) return;
+            const int u0 = c * 64 + cgrp * 16 + sb * 8;
+            dcr[0] = *reinterpret_cast<const float4*>(dcblk + (u0 / 4) * (LB_ROWS * 4));
+            dcr[1] = *reinterpret_cast<const float4*>(dcblk + (u0 / 4 + 1) * (LB_ROWS * 4));
+        };
+        int aw0 = 0, aw1 = 0;                                      // writes into each chunk buffer so far
+        auto process = [&](const BpttStage& st, int s, int c, int sb, int dbuf, int ns, int nc, int nsb) {
+            const int ab = c & 1;
+            const int u0 = c * 64 + cgrp * 16 + sb * 8;
+            const bool active = s < L, has_next = s + 1 < L;       // has_next: this row was active at step s+1, dh_rec / dc carry over
+            uint32_t dr[8];
+            if (s < S - 1) {                                        // .sync.aligned: the whole warp, converged
+                tmem_ld8(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(dbuf * 256 + u0), dr);
+                tmem_ld_wait();
+            }
+            const uint32_t ch = static_cast<uint32_t>((u0 & 63) >> 3);      // A operand of dh_rec_{s-1}: k-block = gate, 16-byte chunk = (u0 % 64) / 8
+            const uint32_t a0 = sA0 + static_cast<uint32_t>(ab * LB_A_BYTES) + rowoff + ((ch ^ sw) << 4);
+            if (active) {
+                float dh8[8] = {st.dh[0].x, st.dh[0].y, st.dh[0].z, st.dh[0].w, st.dh[1].x, st.dh[1].y, st.dh[1].z, st.dh[1].w};
+                float dct8[8] = {dcr[0].x, dcr[0].y, dcr[0].z, dcr[0].w, dcr[1].x, dcr[1].y, dcr[1].z, dcr[1].w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (has_next) dh8[j] += __uint_as_float(dr[j]);
+                    dct8[j] = fmaf(dh8[j], coef_at(st.co[LSTM_CO_A], j), has_next ? dct8[j] : 0.f);
+                }
+                load_dc(ns, nc, nsb);
+                if (s > 0) {
+                    float dcn[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dcn[j] = dct8[j] * coef_at(st.co[LSTM_CO_F], j);
+                    *reinterpret_cast<float4*>(dcblk + (u0 / 4) * (LB_ROWS * 4)) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+                    *reinterpret_cast<float4*>(dcblk + (u0 / 4 + 1) * (LB_ROWS * 4)) = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
+                }
+                bf16* xrow = sq.dxb + (static_cast<long long>(base) + (dir == 0 ? s : L - 1 - s)) * 8 * h + dir * 4 * h + u0;
+                // gate by gate: multiply, pack, store (token-order row + shared-memory operand) — short live ranges
+                auto emit = [&](int g, const float (&x)[8], const uint4& co) {
+                    uint4 v;
+                    v.x = pack_bf16(x[0] * coef_at(co, 0), x[1] * coef_at(co, 1)); v.y = pack_bf16(x[2] * coef_at(co, 2), x[3] * coef_at(co, 3));
+                    v.z = pack_bf16(x[4] * coef_at(co, 4), x[5] * coef_at(co, 5)); v.w = pack_bf16(x[6] * coef_at(co, 6), x[7] * coef_at(co, 7));
+                    *reinterpret_cast<uint4*>(xrow + g * h) = v;
+                    if (s >= 1) st_shared_v4(a0 + g * LB_KB_BYTES, v.x, v.y, v.z, v.w);
+                };
+                emit(0, dct8, st.co[LSTM_CO_BI]);
+                emit(1, dct8, st.co[LSTM_CO_BF]);
+                emit(2, dct8, st.co[LSTM_CO_BG]);
+                emit(3, dh8, st.co[LSTM_CO_BO]);
+            } else if (s >= 1) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) st_shared_v4(a0 + g * LB_KB_BYTES, 0u, 0u, 0u, 0u);
+            }
+        };
+
+        BpttStage st0, st1;
+        load_stage(st0, S - 1, 0, 0);
+        dcr[0] = dcr[1] = make_float4(0.f, 0.f, 0.f, 0.f);
         int it = 0;
         for (int s = S - 1; s >= 0; --s, ++it) {
-            const bool active = s < L;
-            const bool has_next = s + 1 < L;                       // this row was active at step s+1: dh_rec / dc carry over
-            const bool final_step = s == L - 1;
-            const long long tokrow = static_cast<long long>(base) + (dir == 0 ? s : L - 1 - s);
-            const float* drow = sq.dout + tokrow * 2 * h + dir * h;
-            bf16* xrow = sq.dxb + tokrow * 8 * h + dir * 4 * h;
             const int dbuf = (s + 1) & 1;                           // D of step s+1
             if (s < S - 1) {
                 mbar_wait(&d_full[dbuf], static_cast<uint32_t>(((it - 1) >> 1) & 1), p.err_flag, 405);
@@ -192,85 +264,17 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
             }
             for (int c = 0; c < NC; ++c) {
                 const int ab = c & 1;
+                load_stage(st1, s, c, 1);
                 if (s >= 1) {
                     // the MMAs that read the previous contents of this chunk buffer must have retired (one commit per use, in order)
-                    if (aw[ab] > 0) mbar_wait(&a_empty[ab], static_cast<uint32_t>((aw[ab] - 1) & 1), p.err_flag, 407);
-                    ++aw[ab];
+                    const int aw = ab ? aw1 : aw0;
+                    if (aw > 0) mbar_wait(&a_empty[ab], static_cast<uint32_t>((aw - 1) & 1), p.err_flag, 407);
+                    if (ab) ++aw1; else ++aw0;
                 }
-#pragma unroll
-                for (int sb = 0; sb < 2; ++sb) {
-                    const int u0 = c * 64 + cgrp * 16 + sb * 8;
-                    uint32_t dr[8];
-                    if (s < S - 1) {                                // .sync.aligned: the whole warp, converged
-                        tmem_ld8(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(dbuf * 256 + u0), dr);
-                        tmem_ld_wait();
-                    }
-                    float dpi[8], dpf[8], dpg[8], dpo[8];
-                    if (active) {
-                        const float* gp = sq.gates_h + (s * hist_step + hist_rb + (u0 >> 3)) * 1024 + lane * 8;
-                        const float* cc = sq.c_h + (s * hist_step + hist_rb + (u0 >> 3)) * 256 + lane * 8;
-                        float ig[8], fg[8], gg[8], og[8], ccur[8], cprev[8], dh[8], dcv[8];
-                        *reinterpret_cast<float4*>(ig) = *reinterpret_cast<const float4*>(gp);
-                        *reinterpret_cast<float4*>(ig + 4) = *reinterpret_cast<const float4*>(gp + 4);
-                        *reinterpret_cast<float4*>(fg) = *reinterpret_cast<const float4*>(gp + 256);
-                        *reinterpret_cast<float4*>(fg + 4) = *reinterpret_cast<const float4*>(gp + 260);
-                        *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(gp + 512);
-                        *reinterpret_cast<float4*>(gg + 4) = *reinterpret_cast<const float4*>(gp + 516);
-                        *reinterpret_cast<float4*>(og) = *reinterpret_cast<const float4*>(gp + 768);
-                        *reinterpret_cast<float4*>(og + 4) = *reinterpret_cast<const float4*>(gp + 772);
-                        *reinterpret_cast<float4*>(ccur) = *reinterpret_cast<const float4*>(cc);
-                        *reinterpret_cast<float4*>(ccur + 4) = *reinterpret_cast<const float4*>(cc + 4);
-                        if (s > 0) {
-                            const float* cpp = cc - hist_step * 256;
-                            *reinterpret_cast<float4*>(cprev) = *reinterpret_cast<const float4*>(cpp);
-                            *reinterpret_cast<float4*>(cprev + 4) = *reinterpret_cast<const float4*>(cpp + 4);
-                        }
-                        *reinterpret_cast<float4*>(dh) = *reinterpret_cast<const float4*>(drow + u0);
-                        *reinterpret_cast<float4*>(dh + 4) = *reinterpret_cast<const float4*>(drow + u0 + 4);
-                        if (has_next) {
-                            *reinterpret_cast<float4*>(dcv) = *reinterpret_cast<const float4*>(dcblk + (u0 / 4) * (LB_ROWS * 4));
-                            *reinterpret_cast<float4*>(dcv + 4) = *reinterpret_cast<const float4*>(dcblk + (u0 / 4 + 1) * (LB_ROWS * 4));
-                        }
-                        if (final_step && sq.dqfeat) {
-                            const float* qr = sq.dqfeat + static_cast<long long>(grow) * 2 * h + dir * h + u0;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) dh[j] += qr[j];
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float dhj = dh[j];
-                            if (has_next) dhj += __uint_as_float(dr[j]);
-                            const float tc = tanhf(ccur[j]);
-                            const float dct = (has_next ? dcv[j] : 0.f) + dhj * og[j] * (1.f - tc * tc);
-                            const float cp = s > 0 ? cprev[j] : 0.f;
-                            dpi[j] = dct * gg[j] * ig[j] * (1.f - ig[j]);
-                            dpf[j] = dct * cp * fg[j] * (1.f - fg[j]);
-                            dpg[j] = dct * ig[j] * (1.f - gg[j] * gg[j]);
-                            dpo[j] = dhj * tc * og[j] * (1.f - og[j]);
-                            dcv[j] = dct * fg[j];
-                        }
-                        *reinterpret_cast<float4*>(dcblk + (u0 / 4) * (LB_ROWS * 4)) = make_float4(dcv[0], dcv[1], dcv[2], dcv[3]);
-                        *reinterpret_cast<float4*>(dcblk + (u0 / 4 + 1) * (LB_ROWS * 4)) = make_float4(dcv[4], dcv[5], dcv[6], dcv[7]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { dpi[j] = 0.f; dpf[j] = 0.f; dpg[j] = 0.f; dpo[j] = 0.f; }
-                    }
-                    uint4 q[4];
-                    q[0] = make_uint4(pack_bf16(dpi[0], dpi[1]), pack_bf16(dpi[2], dpi[3]), pack_bf16(dpi[4], dpi[5]), pack_bf16(dpi[6], dpi[7]));
-                    q[1] = make_uint4(pack_bf16(dpf[0], dpf[1]), pack_bf16(dpf[2], dpf[3]), pack_bf16(dpf[4], dpf[5]), pack_bf16(dpf[6], dpf[7]));
-                    q[2] = make_uint4(pack_bf16(dpg[0], dpg[1]), pack_bf16(dpg[2], dpg[3]), pack_bf16(dpg[4], dpg[5]), pack_bf16(dpg[6], dpg[7]));
-                    q[3] = make_uint4(pack_bf16(dpo[0], dpo[1]), pack_bf16(dpo[2], dpo[3]), pack_bf16(dpo[4], dpo[5]), pack_bf16(dpo[6], dpo[7]));
-                    if (active) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(xrow + g * h + u0) = q[g];
-                    }
-                    if (s >= 1) {                                   // A operand of dh_rec_{s-1}: k-block = gate, 16-byte chunk = (u0 % 64) / 8
-                        const uint32_t ch = static_cast<uint32_t>((u0 & 63) >> 3);
-                        const uint32_t a0 = sA0 + static_cast<uint32_t>(ab * LB_A_BYTES) + rowoff + ((ch ^ sw) << 4);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) st_shared_v4(a0 + g * LB_KB_BYTES, q[g].x, q[g].y, q[g].z, q[g].w);
-                    }
-                }
+                process(st0, s, c, 0, dbuf, s, c, 1);
+                const int ns = c + 1 < NC ? s : s - 1, nc = c + 1 < NC ? c + 1 : 0;
+                load_stage(st0, ns, nc, 0);
+                process(st1, s, c, 1, dbuf, ns, nc, 0);
                 if (s >= 1) {
                     fence_async_smem();
                     mbar_arrive(&a_ready[ab]);
@@ -290,6 +294,18 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
     }
 }
 
+// d question_feature = gradient of the final hidden state of both directions (module_net.py:160-163): direction 0 ends on a question's
+// last token, direction 1 on its first
+__global__ void add_qfeat_grad_kernel(float* __restrict__ dtok, const float* __restrict__ dqfeat, const int* __restrict__ q_off, int B, int h) {
+    const long long total = static_cast<long long>(B) * 2 * h;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int b = static_cast<int>(i / (2 * h)), j = static_cast<int>(i % (2 * h));
+        const int base = __ldg(q_off + b), L = __ldg(q_off + b + 1) - base;
+        if (L <= 0) continue;
+        dtok[(static_cast<long long>(base) + (j < h ? L - 1 : 0)) * 2 * h + j] += dqfeat[i];
+    }
+}
+
 }  // namespace
 
 bool lstm_bptt_fused_ok(int precision, int h) { return precision == STAIR_BF16 && h >= 64 && h <= 256 && (h % 64) == 0; }
@@ -301,8 +317,12 @@ int launch_lstm_bptt_fused(const LstmBptt& a, int B, int h, int T, int L_max, co
     p.err_flag = err_flag;
     for (int e = 0; e < 2; ++e) {
         BpttSeq& s = p.seq[e];
-        s.gates_h = a.gates[e]; s.c_h = a.c[e]; s.dout = a.dout[e]; s.dqfeat = e == 1 ? a.dqfeat : nullptr; s.dxb = a.dxb[e];
+        s.coef_h = reinterpret_cast<const bf16*>(a.gates[e]); s.dout = a.dout[e]; s.dxb = a.dxb[e];
         s.dc = a.dc[e]; s.q_off = e == 1 ? q_off : nullptr; s.steps = e == 0 ? T : L_max; s.B = B; s.h = h;
+    }
+    if (a.dqfeat) {
+        add_qfeat_grad_kernel<<<static_cast<int>((static_cast<long long>(B) * 2 * h + 255) / 256), 256, 0, st>>>(a.dout[1], a.dqfeat, q_off, B, h);
+        STAIR_CHECK_LAUNCH();
     }
     CUtensorMap tm[4];
     for (int i = 0; i < 4; ++i) STAIR_TRY(make_tmap_bf16_2d(&tm[i], a.whhT[i], 4ULL * h, h, 4ULL * h, 64, 256));

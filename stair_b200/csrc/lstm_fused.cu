@@ -12,6 +12,7 @@
 // warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4..11: cell epilogue (2 warps per TMEM lane quarter)
 #include "nmn_kernels.cuh"
 #include "tc_ptx.cuh"
+#include "train_kernels.cuh"
 
 namespace stair {
 
@@ -31,12 +32,12 @@ struct LstmSeq {
     const int* q_off;       // text: [B+1] token offsets (ragged) ; video: null
     int steps;              // video: T ; text: L_max
     int B, h;
-    // training (HIST): per-step history for BPTT.  Gates (post-activation i,f,g,o) and cell state are written in the BLOCKED layout of
-    // train_kernels.cuh (lstm_hist_gate_off / lstm_hist_c_off: [step][dir][32-row block][8-unit block][gate][row][8 units]) so that a
-    // warp's stores are contiguous (row-major history = 32 scattered 16-byte pieces per store instruction, measured 3x slower);
-    // the cell history is also the running c (no private scratch).  h goes to hs_h [rows][2h] bf16 in token order, shifted by one step
-    // (row of token r holds the state BEFORE r was consumed): the second operand of the dW_hh contraction.
-    float* gates_h; float* c_h; bf16* hs_h; long long hs_dir;
+    // training (HIST): per-step history for BPTT = the six bf16 cell-derivative coefficients of train_kernels.cuh (lstm_hist_coef_off:
+    // [step][dir][32-row block][8-unit block][coefficient][row][8 units]) so that a warp's stores are contiguous (a row-major history =
+    // 32 scattered 16-byte pieces per store instruction, measured 3x slower).  The running cell state stays in the private fp32 scratch
+    // `c` (the backward never reads c).  h goes to hs_h [rows][2h] bf16 in token order, shifted by one step (row of token r holds the
+    // state BEFORE r was consumed): the second operand of the dW_hh contraction.
+    bf16* coef_h; bf16* hs_h; long long hs_dir;
 };
 
 struct LstmFusedParams {
@@ -221,14 +222,10 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
         // cell state scratch, private to this CTA, laid out [unit/4][row][4] so that a warp's float4 accesses are contiguous
         const int nblk = (sq.B + VROWS - 1) / VROWS;
         float* cblk = sq.c + (static_cast<long long>(dir) * nblk + blockIdx.x) * (static_cast<long long>(h) * VROWS) + row * 4;
-        // HIST: the cell state of step s lives in the blocked history; q-th float4 of the 8 units starting at `unit`
         const long long RB = (sq.B + 127) / 128 * 4;                                      // 32-row blocks per (step, direction)
         const long long hist_rb = (static_cast<long long>(dir) * RB + (grow >> 5)) * (h >> 3);      // + step * 2 * RB * (h/8); then + unit/8
         const long long hist_step = 2 * RB * (h >> 3);
-        auto c_ptr = [&](int step, int unit, int q) -> float* {
-            if (HIST) return sq.c_h + (step * hist_step + hist_rb + (unit >> 3)) * 256 + lane * 8 + 4 * q;
-            return cblk + (unit / 4 + q) * (VROWS * 4);
-        };
+        auto c_ptr = [&](int, int unit, int q) -> float* { return cblk + (unit / 4 + q) * (VROWS * 4); };     // q-th float4 of 8 units
         const uint32_t sH0 = smem_u32(sH);
         const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
         const uint32_t sw = static_cast<uint32_t>(row & 7);
@@ -251,7 +248,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                     for (int sb = 0; sb < SBN; ++sb) {
                         const int u0 = c * 64 + halfsel * (SBN * 8) + sb * 8;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) xq[sb][g] = __ldg(reinterpret_cast<const uint4*>(xrow + g * h + u0));
+                        for (int g = 0; g < 4; ++g) xq[sb][g] = __ldg(reinterpret_cast<const uint4*>(xrow + g * h + u0));      // L1-allocating: the next sub-block reads the other half of the sector (no-allocate measured 1.6x slower)
                     }
                     if (s > 0) {
 #pragma unroll
@@ -275,7 +272,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                     const uint32_t ch = static_cast<uint32_t>(halfsel * SBN + sb);
                     const uint32_t a0 = static_cast<uint32_t>(c) * LF_KB_BYTES + rowoff + ((ch ^ sw) << 4);
                     if (active) {
-                        float fi[8], ff[8], fg[8], fo[8], hn[8], cn[8];
+                        float fi[8], ff[8], fg[8], fo[8], hn[8], cn[8], ca[8], cf[8];
                         unpack8(xq[sb][0], fi); unpack8(xq[sb][1], ff); unpack8(xq[sb][2], fg); unpack8(xq[sb][3], fo);
                         const float cprev[8] = {cnext[0].x, cnext[0].y, cnext[0].z, cnext[0].w, cnext[1].x, cnext[1].y, cnext[1].z, cnext[1].w};
                         if (s > 0 && sb < SBN - 1) {
@@ -293,21 +290,27 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                             const float ig = fast_sigmoid(pi), fgt = fast_sigmoid(pf), gg2 = fast_tanh(pg), og = fast_sigmoid(po);
                             const float cc = fgt * cp + ig * gg2;
                             cn[j] = cc;
-                            hn[j] = og * fast_tanh(cc);
-                            if (HIST) { fi[j] = ig; ff[j] = fgt; fg[j] = gg2; fo[j] = og; }
+                            const float tc = fast_tanh(cc);
+                            hn[j] = og * tc;
+                            if (HIST) {                               // the backward's coefficients (train_kernels.cuh), reusing fi / ff / fg / fo / cprev
+                                fi[j] = gg2 * ig * (1.0f - ig);           // Bi
+                                ff[j] = cp * fgt * (1.0f - fgt);          // Bf
+                                fg[j] = ig * (1.0f - gg2 * gg2);          // Bg
+                                fo[j] = tc * og * (1.0f - og);            // Bo
+                                ca[j] = og * (1.0f - tc * tc);            // A
+                                cf[j] = fgt;                              // F
+                            }
                         }
 #pragma unroll
                         for (int q = 0; q < 2; ++q)
                             *reinterpret_cast<float4*>(c_ptr(s, u0, q)) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
                         if (HIST) {
-                            float* gh = sq.gates_h + (s * hist_step + hist_rb + (u0 >> 3)) * 1024 + lane * 8;      // [gate][row][8 units]
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                *reinterpret_cast<float4*>(gh + 4 * q) = make_float4(fi[4 * q], fi[4 * q + 1], fi[4 * q + 2], fi[4 * q + 3]);
-                                *reinterpret_cast<float4*>(gh + 256 + 4 * q) = make_float4(ff[4 * q], ff[4 * q + 1], ff[4 * q + 2], ff[4 * q + 3]);
-                                *reinterpret_cast<float4*>(gh + 512 + 4 * q) = make_float4(fg[4 * q], fg[4 * q + 1], fg[4 * q + 2], fg[4 * q + 3]);
-                                *reinterpret_cast<float4*>(gh + 768 + 4 * q) = make_float4(fo[4 * q], fo[4 * q + 1], fo[4 * q + 2], fo[4 * q + 3]);
-                            }
+                            bf16* gh = sq.coef_h + (s * hist_step + hist_rb + (u0 >> 3)) * (LSTM_NCOEF * 256) + lane * 8;      // [coefficient][row][8 units]
+                            auto put = [&](int co, const float (&v)[8]) {
+                                *reinterpret_cast<uint4*>(gh + co * 256) =
+                                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            };
+                            put(LSTM_CO_A, ca); put(LSTM_CO_BI, fi); put(LSTM_CO_BF, ff); put(LSTM_CO_BG, fg); put(LSTM_CO_BO, fo); put(LSTM_CO_F, cf);
                         }
                         uint4 o0;
                         o0.x = pack_bf16(hn[0], hn[1]); o0.y = pack_bf16(hn[2], hn[3]); o0.z = pack_bf16(hn[4], hn[5]); o0.w = pack_bf16(hn[6], hn[7]);
@@ -361,8 +364,8 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
     v.final_h = nullptr; v.q_off = nullptr; v.steps = T; v.B = B; v.h = h;
     LstmSeq t; t.xproj = reinterpret_cast<const bf16*>(xproj_t); t.c = c_scratch + 2LL * ((B + LF_ROWS - 1) / LF_ROWS) * LF_ROWS * h; t.out = reinterpret_cast<bf16*>(tokfeat);
     t.final_h = reinterpret_cast<bf16*>(qfeat); t.q_off = q_off; t.steps = L_max; t.B = B; t.h = h;
-    v.gates_h = hist ? hist->gates[0] : nullptr; v.c_h = hist ? hist->c[0] : nullptr; v.hs_h = hist ? hist->hs[0] : nullptr; v.hs_dir = hist ? hist->hs_dir[0] : 0;
-    t.gates_h = hist ? hist->gates[1] : nullptr; t.c_h = hist ? hist->c[1] : nullptr; t.hs_h = hist ? hist->hs[1] : nullptr; t.hs_dir = hist ? hist->hs_dir[1] : 0;
+    v.coef_h = hist ? reinterpret_cast<bf16*>(hist->gates[0]) : nullptr; v.hs_h = hist ? hist->hs[0] : nullptr; v.hs_dir = hist ? hist->hs_dir[0] : 0;
+    t.coef_h = hist ? reinterpret_cast<bf16*>(hist->gates[1]) : nullptr; t.hs_h = hist ? hist->hs[1] : nullptr; t.hs_dir = hist ? hist->hs_dir[1] : 0;
     const void* w[4];
     int nseq = 0;
     if (run_video) { p.seq[nseq] = v; w[2 * nseq] = whh_v_f; w[2 * nseq + 1] = whh_v_r; ++nseq; }

@@ -83,7 +83,8 @@ int launch_lstm_cell_text(int xdt, const void* xproj, const float* g, float* c, 
 // fused persistent recurrence for both encoders and both directions (lstm_fused.cu; bf16 path, h in {64,128,192,256})
 bool lstm_fused_ok(int precision, int h);
 // training: BPTT history written by the fused kernel, index 0 = video encoder, 1 = text encoder (layouts: executor_bwd.cu saved_layout).
-// hs must be zero-filled by the caller (rows of finished questions are not written); c_scratch is unused with a history.
+// hs must be zero-filled by the caller (rows of finished questions are not written).  gates[e] holds the bf16 coefficient history
+// (train_kernels.cuh lstm_hist_coef_off); c[e] is unused (the running cell state stays in c_scratch).
 struct LstmHist { float* gates[2]; float* c[2]; bf16* hs[2]; long long hs_dir[2]; };
 int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh_v_f, const void* whh_v_r,
                       const void* xproj_t, void* tokfeat, void* qfeat, const int* q_off, int L_max, const void* whh_t_f,
@@ -91,11 +92,11 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
                       const LstmHist* hist = nullptr);
 
 // fused persistent BPTT of both encoders and directions (lstm_bptt.cu; bf16 path, after a fused forward with history).
-// index 0 = video, 1 = text.  gates / c: the forward's blocked history; dout: fp32 [rows][2h] gradient of the encoder output; dxb: bf16
+// index 0 = video, 1 = text.  gates: the forward's blocked bf16 coefficient history (c unused); dout: fp32 [rows][2h] gradient of the encoder output (dout[1] is modified: dqfeat is added to each question's last-step rows); dxb: bf16
 // [rows][8h] gate pre-activation gradients in token order (output); dc: scratch of 2 * ceil(B/64)*64 * h floats per encoder;
 // whhT[2*e + dir]: transposed W_hh copies [h][4h] (StairModel.wt).
 struct LstmBptt {
-    const float* gates[2]; const float* c[2]; const float* dout[2]; const float* dqfeat; bf16* dxb[2]; float* dc[2]; const void* whhT[4];
+    const float* gates[2]; const float* c[2]; float* dout[2]; const float* dqfeat; bf16* dxb[2]; float* dc[2]; const void* whhT[4];
 };
 bool lstm_bptt_fused_ok(int precision, int h);
 int launch_lstm_bptt_fused(const LstmBptt& a, int B, int h, int T, int L_max, const int* q_off, int* err_flag, cudaStream_t st);

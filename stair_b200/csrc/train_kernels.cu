@@ -1302,24 +1302,25 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const floa
             float dh = dout[row * 2 * h + d * h + j];
             if (step < last_step) dh += dh_rec[si];
             if (dqfeat && final_step) dh += dqfeat[static_cast<long long>(b) * 2 * h + d * h + j];
-            float ig, fg, gg, og, ccur, cp = 0.f;
-            if (blocked) {
-                const long long go = lstm_hist_gate_off(step, d, b, 0, j, B, h);
-                ig = gates[go]; fg = gates[go + 256]; gg = gates[go + 512]; og = gates[go + 768];
-                ccur = c_cur[lstm_hist_c_off(step, d, b, j, B, h)];
-                if (step > 0) cp = c_cur[lstm_hist_c_off(step - 1, d, b, j, B, h)];
+            if (blocked) {                                           // bf16 coefficient history of the fused forward (train_kernels.cuh)
+                const bf16* co = reinterpret_cast<const bf16*>(gates) + lstm_hist_coef_off(step, d, b, 0, j, B, h);
+                const float dct = (step < last_step ? dc[si] : 0.f) + dh * __bfloat162float(co[LSTM_CO_A * 256]);
+                dpi = dct * __bfloat162float(co[LSTM_CO_BI * 256]);
+                dpf = dct * __bfloat162float(co[LSTM_CO_BF * 256]);
+                dpg = dct * __bfloat162float(co[LSTM_CO_BG * 256]);
+                dpo = dh * __bfloat162float(co[LSTM_CO_BO * 256]);
+                dc[si] = dct * __bfloat162float(co[LSTM_CO_F * 256]);
             } else {
-                ig = gates[gi]; fg = gates[gi + h]; gg = gates[gi + 2 * h]; og = gates[gi + 3 * h];
-                ccur = c_cur[si];
-                if (step > 0) cp = c_prev[si];
+                const float ig = gates[gi], fg = gates[gi + h], gg = gates[gi + 2 * h], og = gates[gi + 3 * h];
+                const float ccur = c_cur[si], cp = step > 0 ? c_prev[si] : 0.f;
+                const float tc = tanhf(ccur);
+                const float dct = (step < last_step ? dc[si] : 0.f) + dh * og * (1.f - tc * tc);
+                dpi = dct * gg * ig * (1.f - ig);
+                dpf = dct * cp * fg * (1.f - fg);
+                dpg = dct * ig * (1.f - gg * gg);
+                dpo = dh * tc * og * (1.f - og);
+                dc[si] = dct * fg;
             }
-            const float tc = tanhf(ccur);
-            const float dct = (step < last_step ? dc[si] : 0.f) + dh * og * (1.f - tc * tc);
-            dpi = dct * gg * ig * (1.f - ig);
-            dpf = dct * cp * fg * (1.f - fg);
-            dpg = dct * ig * (1.f - gg * gg);
-            dpo = dh * tc * og * (1.f - og);
-            dc[si] = dct * fg;
             if (dxproj_bf16) {                                   // bf16 path: the row-major bf16 copy IS the weight-gradient GEMM operand
                 bf16* xb = dxproj_bf16 + row * 8 * h + d * 4 * h + j;
                 xb[0] = __float2bfloat16_rn(dpi); xb[h] = __float2bfloat16_rn(dpf); xb[2 * h] = __float2bfloat16_rn(dpg); xb[3 * h] = __float2bfloat16_rn(dpo);

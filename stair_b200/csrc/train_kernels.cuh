@@ -59,15 +59,19 @@ int launch_loss_ff(const float* head, float* dhead, const int* aux_slot, const i
 int launch_add_inplace(float* dst, const float* src, long long n, cudaStream_t st);     // dst += src (n a multiple of 4, 16-byte aligned)
 int launch_loss_dec(const float* logits, const int* answer, float w, float* dlogits, float* loss, int B, int A, cudaStream_t st);
 
-// Blocked BPTT history written by the fused recurrence kernel (lstm_fused.cu, HIST): 32-row x 8-unit blocks, 32 contiguous bytes per
-// (row, gate) — the writer's warp stores 1 KiB-contiguous pieces, the row-major reader below reads whole 32-byte sectors.
-// RB = 32-row blocks per (step, direction) = ceil(B / 128) * 4.
+// Blocked BPTT history written by the fused recurrence kernel (lstm_fused.cu, HIST).  Not the gates themselves but the six per-unit
+// COEFFICIENTS the backward multiplies by, as bf16 (12 bytes per hidden unit and step instead of 24 bytes of fp32 gates + c + c_prev;
+// the transcendental part of the cell derivative is computed once, in the forward, where tanh(c) is already in a register):
+//   A  = o (1 - tanh(c)^2)      dc_t  = dc_carry + dh A          Bi = g i (1 - i)       d pre_i = dc_t Bi
+//   Bf = c_prev f (1 - f)       d pre_f = dc_t Bf                Bg = i (1 - g^2)       d pre_g = dc_t Bg
+//   Bo = tanh(c) o (1 - o)      d pre_o = dh Bo                  F  = f                 dc_carry' = dc_t F
+// Layout: [step][dir][32-row block][8-unit block][coefficient][row][8 units] — the writer's warp stores 512-byte contiguous pieces, a
+// reader fetches 16 bytes per (row, coefficient).  RB = 32-row blocks per (step, direction) = ceil(B / 128) * 4.
+constexpr int LSTM_NCOEF = 6;
+enum { LSTM_CO_A = 0, LSTM_CO_BI, LSTM_CO_BF, LSTM_CO_BG, LSTM_CO_BO, LSTM_CO_F };
 __host__ __device__ static inline long long lstm_hist_rb(int B) { return (static_cast<long long>(B) + 127) / 128 * 4; }
-__host__ __device__ static inline long long lstm_hist_gate_off(int step, int d, int b, int gate, int u, int B, int h) {
-    return ((((static_cast<long long>(step) * 2 + d) * lstm_hist_rb(B) + (b >> 5)) * (h >> 3) + (u >> 3)) * 4 + gate) * 256 + (b & 31) * 8 + (u & 7);
-}
-__host__ __device__ static inline long long lstm_hist_c_off(int step, int d, int b, int u, int B, int h) {
-    return (((static_cast<long long>(step) * 2 + d) * lstm_hist_rb(B) + (b >> 5)) * (h >> 3) + (u >> 3)) * 256 + (b & 31) * 8 + (u & 7);
+__host__ __device__ static inline long long lstm_hist_coef_off(int step, int d, int b, int coef, int u, int B, int h) {      // in bf16 elements
+    return ((((static_cast<long long>(step) * 2 + d) * lstm_hist_rb(B) + (b >> 5)) * (h >> 3) + (u >> 3)) * LSTM_NCOEF + coef) * 256 + (b & 31) * 8 + (u & 7);
 }
 
 // ---- LSTM with history (training forward) and its backward ---------------------------------------------------------------------------
@@ -80,7 +84,7 @@ int launch_lstm_cell_train(int xdt, const void* xproj, const float* g, const flo
 // into the step's slice of the direction-major history (dg_planes + d*dg_dir + b*4h, plane stride dg_plane) and as fp32 into the dxproj
 // row; updates dc in place.
 // blocked = 0: gates / c_prev / c_cur point at step `step`'s row-major slices ([2][B][4h], [2][B][h]; c_prev at step-1's);
-// blocked = 1: gates / c_cur are the BASE of the blocked history (lstm_hist_*_off), c_prev is ignored.
+// blocked = 1: gates is the BASE of the blocked bf16 coefficient history (lstm_hist_coef_off); c_prev / c_cur are ignored.
 int launch_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_cur, const float* dout, const float* dh_rec, const float* dqfeat,
                          float* dc, long long dg_dir, bf16* dg_planes, long long dg_plane, int nplanes, float* dxproj, bf16* dxproj_bf16, const int* q_off,
                          int B, int T, int h, int step, int last_step, int blocked, cudaStream_t st);     // dxproj_bf16 != null: bf16 rows instead of fp32
