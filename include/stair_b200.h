@@ -230,6 +230,7 @@ int stair_gemm_bf16_tn(const void* A, long long lda, int a_plane_rows, const voi
                        float* C, long long ldc, int M, int N, int K, int accumulate, void* stream);
 int stair_set_bwd_lanes(int lanes);     /* module backward: groups of one schedule wave on up to `lanes` concurrent streams (1 = sequential) */
 int stair_set_dw_impl(int impl);        /* weight gradients: 0 = MN-major operands in place (product); 1 = transposed copies + K-major GEMM */
+int stair_set_loss_con_impl(int impl);  /* contrastive loss: 0 = shared-memory kernel for windows of <= 64 classes (product); 1 = register kernel always */
 int stair_set_bptt_impl(int impl);      /* encoder BPTT (bf16 path): 0 = one persistent fused kernel for both encoders / directions (product); 1 = per-step cell kernel + recurrent GEMMs */
 int stair_set_gemm_impl(int impl);      /* 0 = tcgen05 (product); 1 = SIMT debug kernel used to cross-check in tests */
 int stair_get_gemm_impl(void);

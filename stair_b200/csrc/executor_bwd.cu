@@ -845,6 +845,7 @@ extern "C" int stair_adam_step(float* param, const float* grad, float* exp_avg, 
 extern "C" int stair_set_bwd_lanes(int lanes) { g_bwd_lanes = lanes < 1 ? 1 : (lanes > LANES ? LANES : lanes); return STAIR_OK; }
 extern "C" int stair_set_dw_impl(int impl) { g_dw_impl = impl ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_bptt_impl(int impl) { g_bptt_impl = impl ? 1 : 0; return STAIR_OK; }
+extern "C" int stair_set_loss_con_impl(int impl) { g_loss_con_impl = impl ? 1 : 0; return STAIR_OK; }
 
 extern "C" int stair_adam_multi(const StairAdamSeg* segs, int n_segs, int total_tiles, float lr, double beta1, double beta2, float eps, void* stream) {
     if (!segs && n_segs > 0) return STAIR_ERR_ARG;

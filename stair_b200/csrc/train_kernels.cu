@@ -983,6 +983,7 @@ int launch_loss_bin(int dt, const void* vec, float* dvec, const int* out_slot, c
 }
 
 // contrastive CE (train_module.py:113-132): p = normalize(x); s_j = p . G_j over all classes of the window; loss = lse(s) - s_pos
+int g_loss_con_impl = 0;           // 0 = shared-memory kernel when the window has <= 64 classes (product); 1 = register kernel always
 constexpr int CON_MAXC = 32;       // columns per lane: H <= 1024
 constexpr int CON_R = 4;           // rows per warp: every element of G fetched from L2/L1 serves CON_R rows (the class matrix, n_cls x H fp32,
                                    // is re-read for every row: at one row per warp the kernel is bound by that traffic)
@@ -1086,10 +1087,142 @@ __global__ void loss_con_kernel(const AT* __restrict__ vec, float* __restrict__ 
     if (lane == 0 && lsum != 0.f) atomicAdd(loss + 5, lsum);
 }
 
+
+// Shared-memory form of the contrastive CE for the common window (n_cls <= 64 classes, H <= 512, H % 32 == 0): the class matrix is staged
+// once per CTA ([64][H + 1] fp32, conflict-free both by class and by column), a warp takes four rows at a time.  Scores: lane = class
+// (lane, lane + 32), the normalised row is broadcast from shared memory — no shuffle reductions; gradient: lane = column.  With
+// a_j = softmax_j - [j == pos]: d x_hat = sum_j a_j G_j and x_hat . d x_hat = sum_j a_j s_j (s_j = x_hat . G_j), so the projection term of
+// normalize's backward needs no second sweep.  (The register form below executes 38 K warp instructions per four rows, this one ~12 K.)
+constexpr int CON_S_CLS = 64, CON_S_WARPS = 8;
+template <typename AT>
+__global__ void __launch_bounds__(CON_S_WARPS * 32) loss_con_smem_kernel(const AT* __restrict__ vec, float* __restrict__ dvec, const int* __restrict__ out_slot,
+                                                                           const int* __restrict__ node, const int* __restrict__ pos, const float* __restrict__ w,
+                                                                           const float* __restrict__ G, int n_cls, float* __restrict__ loss, int n, int H) {
+    extern __shared__ float sm[];
+    const int GS = H + 1;
+    float* sG = sm;                                                    // [64][H + 1]
+    float* sx = sG + CON_S_CLS * GS + ((CON_S_CLS * GS) & 3 ? 4 - ((CON_S_CLS * GS) & 3) : 0);      // [warps][4][H] normalised rows (16-byte aligned)
+    float* sa = sx + CON_S_WARPS * CON_R * H;                          // [warps][64][4] a_j of the warp's four rows
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < CON_S_CLS * H; i += blockDim.x) {
+        const int j = i / H, c = i - j * H;
+        sG[j * GS + c] = j < n_cls ? __ldg(G + static_cast<long long>(j) * H + c) : 0.f;
+    }
+    __syncthreads();
+    float* x = sx + warp * CON_R * H;
+    float* a = sa + warp * CON_S_CLS * CON_R;
+    const int nq = H >> 5;
+    float lsum = 0.f;
+    for (int i0 = (blockIdx.x * CON_S_WARPS + warp) * CON_R; i0 < n; i0 += gridDim.x * CON_S_WARPS * CON_R) {
+        long long ro[CON_R]; float rn[CON_R];
+#pragma unroll
+        for (int r = 0; r < CON_R; ++r) {
+            const int i = min(i0 + r, n - 1);                          // tail rows recompute the last row (their results are discarded)
+            ro[r] = static_cast<long long>(out_slot[__ldg(node + i)]) * H;
+            float ss = 0.f;
+            for (int q = 0; q < nq; ++q) { const float v = ld1<AT>(vec + ro[r] + lane + 32 * q); x[r * H + lane + 32 * q] = v; ss = fmaf(v, v, ss); }
+            rn[r] = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+        }
+        __syncwarp();
+        // scores of classes (lane, lane + 32) for the four rows
+        float s0[CON_R], s1[CON_R];
+#pragma unroll
+        for (int r = 0; r < CON_R; ++r) { s0[r] = 0.f; s1[r] = 0.f; }
+        const float* g0 = sG + lane * GS;
+        const float* g1 = sG + (lane + 32) * GS;
+#pragma unroll 2
+        for (int c = 0; c < H; c += 4) {
+            float4 xv[CON_R];
+#pragma unroll
+            for (int r = 0; r < CON_R; ++r) xv[r] = *reinterpret_cast<const float4*>(x + r * H + c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float ga = g0[c + k], gb = g1[c + k];
+#pragma unroll
+                for (int r = 0; r < CON_R; ++r) {
+                    const float xk = k == 0 ? xv[r].x : k == 1 ? xv[r].y : k == 2 ? xv[r].z : xv[r].w;
+                    s0[r] = fmaf(xk, ga, s0[r]); s1[r] = fmaf(xk, gb, s1[r]);
+                }
+            }
+        }
+        float wi[CON_R], pdp[CON_R];
+#pragma unroll
+        for (int r = 0; r < CON_R; ++r) {
+            const float v0 = lane < n_cls ? s0[r] * rn[r] : -INFINITY, v1 = lane + 32 < n_cls ? s1[r] * rn[r] : -INFINITY;
+            const float m = warp_max(fmaxf(v0, v1));
+            const float se = warp_sum(expf(v0 - m) + expf(v1 - m));
+            const float lse = m + logf(se);
+            const int i = min(i0 + r, n - 1);
+            const int ps = __ldg(pos + i);
+            wi[r] = i0 + r < n ? __ldg(w + i) : 0.f;
+            const float sp = __shfl_sync(0xffffffffu, ps < 32 ? v0 : v1, ps & 31);
+            lsum += wi[r] * (lse - sp);
+            const float a0 = (lane < n_cls ? expf(v0 - lse) : 0.f) - (ps == lane ? 1.f : 0.f);
+            const float a1 = (lane + 32 < n_cls ? expf(v1 - lse) : 0.f) - (ps == lane + 32 ? 1.f : 0.f);
+            a[lane * CON_R + r] = a0; a[(lane + 32) * CON_R + r] = a1;
+            pdp[r] = warp_sum((lane < n_cls ? a0 * v0 : 0.f) + (lane + 32 < n_cls ? a1 * v1 : 0.f));
+        }
+        __syncwarp();
+        // d x_hat[c] = sum_j a_j G[j][c], lane = column (8 columns per sweep), then normalize's backward and the scatter
+        for (int q0 = 0; q0 < nq; q0 += 8) {
+            float dp[CON_R][8];
+#pragma unroll
+            for (int r = 0; r < CON_R; ++r)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dp[r][q] = 0.f;
+#pragma unroll 2
+            for (int j = 0; j < n_cls; ++j) {
+                const float4 aj = *reinterpret_cast<const float4*>(a + j * CON_R);
+                const float* gj = sG + j * GS + lane + 32 * q0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (q0 + q < nq) {
+                        const float g = gj[32 * q];
+                        dp[0][q] = fmaf(aj.x, g, dp[0][q]); dp[1][q] = fmaf(aj.y, g, dp[1][q]);
+                        dp[2][q] = fmaf(aj.z, g, dp[2][q]); dp[3][q] = fmaf(aj.w, g, dp[3][q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < CON_R; ++r) {
+                if (i0 + r < n) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (q0 + q < nq) {
+                            const int c = lane + 32 * (q0 + q);
+                            atomicAdd(dvec + ro[r] + c, wi[r] * (dp[r][q] - x[r * H + c] * rn[r] * pdp[r]) * rn[r]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && lsum != 0.f) atomicAdd(loss + 5, lsum);          // every lane holds the same sum
+}
+
 int launch_loss_con(int dt, const void* vec, float* dvec, const int* out_slot, const int* node, const int* pos, const float* w,
                     const float* cls_rep, int n_cls, float* loss, int n, int H, cudaStream_t st) {
     if (n <= 0 || n_cls <= 0) return STAIR_OK;
     if (H > 32 * CON_MAXC || n_cls > 1024) return STAIR_ERR_UNSUPPORTED;
+    static_assert(CON_R == 4, "loss_con_smem_kernel keeps the a_j of a warp's rows as one float4");
+    if (g_loss_con_impl == 0 && n_cls <= CON_S_CLS && H <= 512 && (H % 32) == 0) {
+        const size_t smem_s = (static_cast<size_t>(CON_S_CLS) * (H + 1) + 4 + CON_S_WARPS * CON_R * H + CON_S_WARPS * CON_S_CLS * CON_R) * sizeof(float);
+        const int groups = (n + CON_S_WARPS * CON_R - 1) / (CON_S_WARPS * CON_R);
+        const int grid_s = groups < 148 ? groups : 148;
+        static size_t configured[2] = {0, 0};
+        const int di = dt == STAIR_BF16 ? 0 : 1;
+        if (configured[di] < smem_s) {
+            cudaError_t e = dt == STAIR_BF16 ? cudaFuncSetAttribute(loss_con_smem_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_s))
+                                             : cudaFuncSetAttribute(loss_con_smem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_s));
+            if (e != cudaSuccess) return STAIR_ERR_CUDA;
+            configured[di] = smem_s;
+        }
+        DISPATCH_DT(dt, AT, (loss_con_smem_kernel<AT><<<grid_s, CON_S_WARPS * 32, smem_s, st>>>(reinterpret_cast<const AT*>(vec), dvec, out_slot, node, pos, w, cls_rep,
+                                                                                               n_cls, loss, n, H)));
+        STAIR_CHECK_LAUNCH();
+        return STAIR_OK;
+    }
     const int warps = 4;
     const size_t smem = static_cast<size_t>(warps) * CON_R * n_cls * sizeof(float);
     const int grid = nblocks((n + CON_R - 1) / CON_R, warps);

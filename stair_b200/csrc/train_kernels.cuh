@@ -53,6 +53,7 @@ int launch_loss_bin(int dt, const void* vec, float* dvec, const int* out_slot, c
 // contrastive CE of the L2-normalised module output against all class text reps of the window (train_module.py:113-132,388-406)
 int launch_loss_con(int dt, const void* vec, float* dvec, const int* out_slot, const int* node, const int* pos, const float* w,
                     const float* cls_rep, int n_cls, float* loss, int n, int H, cudaStream_t st);
+extern int g_loss_con_impl;      // 0 = shared-memory kernel when n_cls <= 64, H <= 512 (product); 1 = register kernel always
 // criterion_filterframe: BCELoss(softmax_O(head row), gold row) per (node, frame); writes d head (not accumulated) and adds to loss[7]
 int launch_loss_ff(const float* head, float* dhead, const int* aux_slot, const int* node, const float* gold, const float* w, float* loss,
                    int n, int T, int O, cudaStream_t st);

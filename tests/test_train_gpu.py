@@ -478,3 +478,38 @@ def test_persistent_bptt_matches_stepwise_bptt(hidden, n_q):
         if 'encoder' in k:
             l2 = float((g0[k] - g1[k]).norm()) / max(float(g1[k].norm()), 1e-30)
             assert l2 <= 5e-3, '%s: relative L2 %g' % (k, l2)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_shared_memory_contrastive_loss_matches_register_kernel(precision):
+    """stair_set_loss_con_impl(0) (product for windows of <= 64 classes): class matrix staged in shared memory, lane = class for the
+    scores and lane = column for the gradient == the register kernel (impl 1), which the golden / oracle tests above also cover through
+    whichever implementation is active.  Contrastive CE: train_module.py:113-132."""
+    from stair_b200 import _lib as L
+    cfg = syn.model_config(T=8, V=128, hidden=128, object_types=16)
+    torch.manual_seed(19)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision=precision).cuda().train()
+    qs = syn.make_questions(203, 8, 128, seed=31, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    res = {}
+    try:
+        for impl in (1, 0):
+            L.lib().stair_set_loss_con_impl(impl)
+            for prm in model.parameters():
+                prm.grad = None
+            out = NMNTrainStep(model)(qs)
+            torch.cuda.synchronize()
+            model.check_status(out['state'])
+            res[impl] = (float(out['loss']), out['loss_terms'].detach().cpu().clone(),
+                         {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    finally:
+        L.lib().stair_set_loss_con_impl(0)
+    (l1, t1, g1), (l0, t0, g0) = res[1], res[0]
+    assert float(t1[5]) != 0.0                                     # the window has contrastive rows
+    assert abs(float(t0[5]) - float(t1[5])) <= 2e-6 * abs(float(t1[5]))
+    assert abs(l0 - l1) <= 2e-6 * abs(l1)
+    assert g0.keys() == g1.keys()
+    # bf16: the backward GEMMs round d vec to bf16, so fp32 summation-order differences of 1e-7 can move single operands by one bf16 ulp
+    tol = 2e-5 if precision == 'fp32' else 5e-3
+    for k in g1:
+        err = float((g0[k] - g1[k]).norm())
+        assert err <= tol * float(g1[k].norm()) + 1e-9, '%s: %g vs norm %g' % (k, err, float(g1[k].norm()))
