@@ -194,6 +194,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
     from stair_b200 import VideoNMN, synthetic as syn, _lib as L
+    from stair_b200.distributed import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local) if world > 1 else {'numa_node': None}     # before any pinned allocation
+    if world > 1:
+        sys.stderr.write('rank %d: %s\n' % (rank, numa))
 
     cfg = syn.model_config(T=T, V=V)
     weights = make_weights(cfg)
@@ -450,6 +454,7 @@ def main():
                         'ms_per_step': 1e3 * e2e_s / args.steps,
                         'per_call': {'value': world * B * args.steps / percall_s, 'ms_per_step': 1e3 * percall_s / args.steps,
                                      'what': 'forward_pipelined(host chunks) + answers.cpu() per step, synchronising every step'},
+                        'host_numa_binding': numa,
                         'timer': 'wall clock between synchronize()s over all steps; VideoNMN.forward_stream: every step uploads its pinned host batch '
                                  '(%d chunks, copy stream) and reads its answers back (async D2H into pinned memory), 2 steps in flight' % E2E_CHUNKS},
                 'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,

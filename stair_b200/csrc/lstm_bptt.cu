@@ -16,8 +16,8 @@
 //   transposed W_hh copy (StairModel.wt, [h][4h]: box {64 k, 256 n} at k = gate*h + 64c) streamed through a TMA ring; D is
 //   double-buffered in TMEM by step parity so the MMA of step s-1 never waits for the last reads of D_s.
 //
-// Warps (448 threads, 144 registers): 2 TMA producer, 3 MMA issuer, 6 TMEM allocator,
-// epilogue = the 8 warps whose TMEM lane quarter (warp % 4) is 0 or 1 (rows 0-63), 4 column groups of 16 units per chunk.
+// Warps (352 threads, 168 registers): 0-7 epilogue (all four TMEM lane quarters: rows 64-127 of the dG operand are a copy of rows 0-63,
+// 4 column groups of 16 units per chunk), 8 TMA producer, 9 MMA issuer, 10 TMEM allocator.
 // L2 prefetching was measured and removed twice: a warp running 1-3 steps ahead doubled the DRAM reads (the steps in flight of 148
 // CTAs do not stay in L2) and prefetching 2-8 sub-block iterations ahead from the epilogue changed nothing (850 us either way).
 #include "nmn_kernels.cuh"
@@ -28,12 +28,12 @@ namespace stair {
 
 namespace {
 
-constexpr int LB_ROWS = 64;                        // questions per CTA (MMA M = 128, lanes 64-127 unused)
+constexpr int LB_ROWS = 64;                        // questions per CTA (MMA M = 128, lanes 64-127 = a copy of lanes 0-63)
 constexpr int LB_KB_BYTES = 128 * 64 * 2;          // one 64-wide k-block of the A tile (128 rows): 16 KiB
 constexpr int LB_A_BYTES = 4 * LB_KB_BYTES;        // one chunk: 4 gates x 64 units
 constexpr int LB_W_STAGE_BYTES = 256 * 64 * 2;     // one B tile (256 n x 64 k): 32 KiB
 constexpr int LB_STAGES = 3;
-constexpr int LB_THREADS = 448;                     // 14 warps: the last epilogue warp is 13 (144 registers per thread)
+constexpr int LB_THREADS = 352;                     // 11 warps: 8 epilogue + TMA + MMA + TMEM allocator (<= 3 warps per SM sub-partition: 168 registers)
 constexpr int LB_EPI = 256;                        // epilogue threads
 constexpr uint32_t LB_IDESC = make_idesc_bf16(128, 256);
 
@@ -71,8 +71,11 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
     const int h = sq.h, NC = h / 64;
     const bool ragged = sq.q_off != nullptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool is_epi = (warp & 3) < 2;
-    const int quarter = warp & 3, cgrp = warp >> 2;          // column group 0..3: units 16*cgrp .. +15 of a chunk
+    // Rows 64-127 of the dG operand hold a COPY of rows 0-63 (the MMA is M = 128 either way), so TMEM lanes 64-127 carry the same dh_rec
+    // as lanes 0-63 and the 8 epilogue warps can sit on all four TMEM lane quarters = all four SM sub-partitions: quarters q and q + 2
+    // share the rows (q & 1) * 32 .. + 31 and split the column groups.
+    const bool is_epi = warp < 8;
+    const int quarter = warp & 3, cgrp = (warp >> 2) * 2 + (quarter >> 1);          // column group 0..3: units 16*cgrp .. +15 of a chunk
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -97,7 +100,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *s_steps = ragged ? 0 : sq.steps;
     }
-    if (warp == 6) {
+    if (warp == 10) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr_smem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -114,7 +117,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
     const uint32_t tmem_base = *tmem_ptr_smem;
     const int S = *s_steps;
 
-    if (warp == 2) {
+    if (warp == 8) {
         if (lane == 0) {
             // ===================== TMA producer: B tiles of W_hh^T, (chunk, gate) order, every step that feeds an earlier one ==========
             int stage = 0; uint32_t phase = 0;
@@ -132,7 +135,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
                         if (++stage == LB_STAGES) { stage = 0; phase ^= 1; }
                     }
         }
-    } else if (warp == 3) {
+    } else if (warp == 9) {
         if (lane == 0) {
             // ===================== MMA issuer: D_s[128, h] = dG_s[128, 4h] . W_hh  (chunk by chunk as the epilogue produces dG_s) ==========
             int stage = 0; uint32_t phase = 0;
@@ -170,13 +173,14 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
         // The step is a chain of 2 NC sub-block iterations, each needing ~100 bytes per thread from HBM (coefficients, output gradient)
         // and L2 (dc): the operands of iteration k+1 are requested before iteration k is processed (two register stages), so the
         // recurrence waits on the tensor core, not on memory.
-        const int row = quarter * 32 + lane;
+        const int row = (quarter & 1) * 32 + lane;
         const int grow = row0 + row;
         const bool valid = grow < sq.B;
         int base = 0, L = sq.steps;
         if (ragged) { base = valid ? __ldg(sq.q_off + grow) : 0; L = valid ? __ldg(sq.q_off + grow + 1) - base : 0; }
         else base = grow * sq.steps;
         if (!valid) L = 0;
+        constexpr uint32_t DUP = 64u * 128u;                       // byte offset of the copy of a row in the dG operand (row + 64)
         const int nblk = (sq.B + LB_ROWS - 1) / LB_ROWS;
         float* dcblk = sq.dc + (static_cast<long long>(dir) * nblk + blockIdx.x) * (static_cast<long long>(h) * LB_ROWS) + row * 4;   // [unit/4][row][4]
         const long long RB = (sq.B + 127) / 128 * 4;
@@ -240,7 +244,10 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
                     v.x = pack_bf16(x[0] * coef_at(co, 0), x[1] * coef_at(co, 1)); v.y = pack_bf16(x[2] * coef_at(co, 2), x[3] * coef_at(co, 3));
                     v.z = pack_bf16(x[4] * coef_at(co, 4), x[5] * coef_at(co, 5)); v.w = pack_bf16(x[6] * coef_at(co, 6), x[7] * coef_at(co, 7));
                     *reinterpret_cast<uint4*>(xrow + g * h) = v;
-                    if (s >= 1) st_shared_v4(a0 + g * LB_KB_BYTES, v.x, v.y, v.z, v.w);
+                    if (s >= 1) {
+                        st_shared_v4(a0 + g * LB_KB_BYTES, v.x, v.y, v.z, v.w);
+                        st_shared_v4(a0 + g * LB_KB_BYTES + DUP, v.x, v.y, v.z, v.w);
+                    }
                 };
                 emit(0, dct8, st.co[LSTM_CO_BI]);
                 emit(1, dct8, st.co[LSTM_CO_BF]);
@@ -248,7 +255,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
                 emit(3, dh8, st.co[LSTM_CO_BO]);
             } else if (s >= 1) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) st_shared_v4(a0 + g * LB_KB_BYTES, 0u, 0u, 0u, 0u);
+                for (int g = 0; g < 4; ++g) { st_shared_v4(a0 + g * LB_KB_BYTES, 0u, 0u, 0u, 0u); st_shared_v4(a0 + g * LB_KB_BYTES + DUP, 0u, 0u, 0u, 0u); }
             }
         };
 
@@ -288,7 +295,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 6) {
+    if (warp == 10) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }

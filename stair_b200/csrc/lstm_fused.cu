@@ -86,25 +86,30 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
 // critical path) and twice as many CTAs to fill the SMs the video blocks free after T steps.  Role warps: 2 TMA, 3 MMA, 6 TMEM
 // allocator, 7 L2 prefetch; 16 warps -> 128 registers per thread.
 template <int CG, bool HIST, int VROWS>
-__global__ void __launch_bounds__(VROWS == 64 ? 512 : 128 + 128 * CG, 1)
+__global__ void __launch_bounds__(VROWS == 64 ? 384 : 128 + 128 * CG, 1)
 lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, const LstmFusedParams p) {
     const LstmSeq sq = blockIdx.z == 0 ? p.seq[0] : p.seq[1];      // by value: a runtime index into param space forces a local copy
     const int dir = blockIdx.y;
     const int wsel = blockIdx.z * 2 + dir;          // which W_hh map (never form a runtime-selected pointer to a param-space map)
-    static_assert(VROWS == 128 || (VROWS == 64 && CG == 4), "64-row blocks use 4 column groups on TMEM quarters 0 and 1");
+    static_assert(VROWS == 128 || (VROWS == 64 && CG == 4), "64-row blocks use 4 column groups: 2 per pair of TMEM quarters");
     const int row0 = blockIdx.x * VROWS;
     if (row0 >= sq.B) return;
     const int h = sq.h, NC = h / 64;              // chunks of 64 hidden units == k-blocks of h
     const bool ragged = sq.q_off != nullptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int LF_THREADS = VROWS == 64 ? 512 : 128 + 128 * CG;
+    constexpr int LF_THREADS = VROWS == 64 ? 384 : 128 + 128 * CG;
     constexpr int SBN = 8 / CG;                   // 8-unit sub-blocks per thread per chunk
     constexpr int EPI_THREADS = VROWS * CG;       // epilogue threads (arrival count of the tmem_empty / h_ready barriers)
     // role warps and the (TMEM quarter, column group) of an epilogue warp
-    constexpr int W_TMA = VROWS == 64 ? 2 : 0, W_MMA = VROWS == 64 ? 3 : 1, W_ALLOC = VROWS == 64 ? 6 : 2, W_PREF = VROWS == 64 ? 7 : 3;
-    const bool is_epi = VROWS == 64 ? ((warp & 3) < 2) : (warp >= 4);
-    const int quarter = warp & 3, halfsel = VROWS == 64 ? (warp >> 2) : ((warp - 4) >> 2);      // halfsel = column group 0..CG-1
+    // 64-row blocks: the MMA is still M = 128, and rows 64-127 of the h operand hold a COPY of rows 0-63, so TMEM lanes 64-127 carry the
+    // same gate pre-activations as lanes 0-63.  That lets the 8 epilogue warps sit on all four TMEM lane quarters = all four SM
+    // sub-partitions (warp % 4): quarters q and q + 2 share the rows (q & 1) * 32 .. + 31 and split the column groups.  With the epilogue
+    // on quarters 0 and 1 only (zero rows 64-127), two schedulers and half of the MUFU units did all the cell math.
+    constexpr int W_TMA = VROWS == 64 ? 8 : 0, W_MMA = VROWS == 64 ? 9 : 1, W_ALLOC = VROWS == 64 ? 10 : 2, W_PREF = VROWS == 64 ? 11 : 3;
+    const bool is_epi = VROWS == 64 ? (warp < 8) : (warp >= 4);
+    const int quarter = warp & 3;
+    const int halfsel = VROWS == 64 ? ((warp >> 2) * 2 + (quarter >> 1)) : ((warp - 4) >> 2);      // halfsel = column group 0..CG-1
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -213,12 +218,13 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
         }
     } else if (is_epi) {
         // ===================== cell epilogue: CG warps per TMEM lane quarter, each takes 64 / CG of a chunk's 64 units =============
-        const int row = quarter * 32 + lane;
+        const int row = (VROWS == 64 ? (quarter & 1) : quarter) * 32 + lane;
         const int grow = row0 + row;
         const bool valid = grow < sq.B;
         int base = 0, L = sq.steps;
         if (ragged) { base = valid ? __ldg(sq.q_off + grow) : 0; L = valid ? __ldg(sq.q_off + grow + 1) - base : 0; }
         else base = grow * sq.steps;
+        constexpr uint32_t DUP = VROWS == 64 ? 64u * 128u : 0u;      // byte offset of the copy of a row in the h operand (row + 64)
         // cell state scratch, private to this CTA, laid out [unit/4][row][4] so that a warp's float4 accesses are contiguous
         const int nblk = (sq.B + VROWS - 1) / VROWS;
         float* cblk = sq.c + (static_cast<long long>(dir) * nblk + blockIdx.x) * (static_cast<long long>(h) * VROWS) + row * 4;
@@ -354,10 +360,12 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                         if (HIST && s + 1 < L) *reinterpret_cast<uint4*>(sq.hs_h + (tokrow + (dir == 0 ? 1 : -1)) * 2 * h + dir * h + u0) = o0;
                         if (last) *reinterpret_cast<uint4*>(sq.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0) = o0;
                         st_shared_v4(h_dst + a0, o0.x, o0.y, o0.z, o0.w);
+                        if (DUP) st_shared_v4(h_dst + a0 + DUP, o0.x, o0.y, o0.z, o0.w);
                     } else {
                         // finished (or padding) row: carry h forward unchanged so the next step's MMA reads a defined operand
                         const uint4 p0 = ld_shared_v4(h_src + a0);
                         st_shared_v4(h_dst + a0, p0.x, p0.y, p0.z, p0.w);
+                        if (DUP) st_shared_v4(h_dst + a0 + DUP, p0.x, p0.y, p0.z, p0.w);
                     }
                 }
                 if (s > 0) {
@@ -428,8 +436,8 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
     const int vrows = r64 ? 64 : 128;
     dim3 grid((B + vrows - 1) / vrows, 2, nseq);
     switch (vi) {
-    case 4: lstm_fused_kernel<4, true, 64><<<grid, 512, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
-    case 3: lstm_fused_kernel<4, false, 64><<<grid, 512, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
+    case 4: lstm_fused_kernel<4, true, 64><<<grid, 384, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
+    case 3: lstm_fused_kernel<4, false, 64><<<grid, 384, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
     case 2: lstm_fused_kernel<2, true, 128><<<grid, 128 + 128 * 2, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
     case 1: lstm_fused_kernel<4, false, 128><<<grid, 128 + 128 * 4, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
     default: lstm_fused_kernel<2, false, 128><<<grid, 128 + 128 * 2, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;

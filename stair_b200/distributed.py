@@ -11,6 +11,45 @@ import torch
 import torch.distributed as dist
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int, sysfs: str = '/sys') -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated.
+
+    Every rank streams its own batches over its own PCIe link (no data-path collective); with 8 ranks the host side
+    only keeps up if each rank's pinned buffers are first-touched on the memory controller next to its GPU (measured without
+    binding: end-to-end 2.4 M q/s at 8 GPUs vs 8 x 0.72 M).  Returns what was found / done; never raises (containers may hide
+    sysfs or restrict the CPU set — then the process is left as it is)."""
+    import os
+    info = {'device': device_index, 'numa_node': None, 'bound_cpus': 0}
+    try:
+        bus = torch.cuda.get_device_properties(device_index)
+        bus_id = '%04x:%02x:%02x.0' % (bus.pci_domain_id, bus.pci_bus_id, bus.pci_device_id)
+        info['pci'] = bus_id
+        with open(os.path.join(sysfs, 'bus/pci/devices', bus_id, 'numa_node')) as f:
+            node = int(f.read().strip())
+        info['numa_node'] = node
+        if node < 0:
+            return info
+        with open(os.path.join(sysfs, 'devices/system/node/node%d/cpulist' % node)) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info['bound_cpus'] = len(allowed)
+    except Exception as e:                                            # noqa: BLE001 — diagnostics only
+        info['error'] = '%s: %s' % (type(e).__name__, e)
+    return info
+
+
 def shard_bounds(n: int, rank: int, world: int):
     """Contiguous slice [lo, hi) of ``n`` questions owned by ``rank``; sizes differ by at most one."""
     base, rem = divmod(n, world)

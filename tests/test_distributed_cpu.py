@@ -59,3 +59,12 @@ def test_gather_world2_gloo(n):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+def test_numa_binding_helper_is_tolerant(tmp_path):
+    """bind_to_gpu_numa_node: cpulist parsing, and no exception when there is no GPU / no sysfs entry (containers)."""
+    from stair_b200.distributed import _parse_cpulist, bind_to_gpu_numa_node
+    assert _parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist('') == set()
+    info = bind_to_gpu_numa_node(0, sysfs=str(tmp_path))
+    assert info['bound_cpus'] == 0 and info['numa_node'] is None
