@@ -13,6 +13,7 @@
 #include "nmn_kernels.cuh"
 #include "tc_ptx.cuh"
 #include "train_kernels.cuh"
+#include <cstdlib>
 
 namespace stair {
 
@@ -44,6 +45,8 @@ struct LstmFusedParams {
     LstmSeq seq[2];
     int* err_flag;
     volatile unsigned int* dbg;   // debug progress words (pinned host memory), null in production
+    int prefetch;                 // 1 = the L2 prefetch warp runs two steps ahead of the cell epilogue (STAIR_LSTM_PF=1; off by default: since
+                                  // the chunk's operands are requested before the MMA wait it only adds DRAM reads, 405 -> 495 MB, 400 -> 403 us)
 };
 #define LF_DBG(slot, val) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { p.dbg[slot] = (val); __threadfence_system(); } } while (0)
 
@@ -86,19 +89,19 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
 // critical path) and twice as many CTAs to fill the SMs the video blocks free after T steps.  Role warps: 2 TMA, 3 MMA, 6 TMEM
 // allocator, 7 L2 prefetch; 16 warps -> 128 registers per thread.
 template <int CG, bool HIST, int VROWS>
-__global__ void __launch_bounds__(VROWS == 64 ? 384 : 128 + 128 * CG, 1)
+__global__ void __launch_bounds__(VROWS == 64 ? 64 * CG + 128 : 128 + 128 * CG, 1)
 lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, const LstmFusedParams p) {
     const LstmSeq sq = blockIdx.z == 0 ? p.seq[0] : p.seq[1];      // by value: a runtime index into param space forces a local copy
     const int dir = blockIdx.y;
     const int wsel = blockIdx.z * 2 + dir;          // which W_hh map (never form a runtime-selected pointer to a param-space map)
-    static_assert(VROWS == 128 || (VROWS == 64 && CG == 4), "64-row blocks use 4 column groups: 2 per pair of TMEM quarters");
+    static_assert(VROWS == 128 || (VROWS == 64 && (CG == 4 || CG == 8)), "64-row blocks use 4 or 8 column groups: half of them per pair of TMEM quarters");
     const int row0 = blockIdx.x * VROWS;
     if (row0 >= sq.B) return;
     const int h = sq.h, NC = h / 64;              // chunks of 64 hidden units == k-blocks of h
     const bool ragged = sq.q_off != nullptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int LF_THREADS = VROWS == 64 ? 384 : 128 + 128 * CG;
+    constexpr int LF_THREADS = VROWS == 64 ? 64 * CG + 128 : 128 + 128 * CG;
     constexpr int SBN = 8 / CG;                   // 8-unit sub-blocks per thread per chunk
     constexpr int EPI_THREADS = VROWS * CG;       // epilogue threads (arrival count of the tmem_empty / h_ready barriers)
     // role warps and the (TMEM quarter, column group) of an epilogue warp
@@ -106,8 +109,10 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
     // same gate pre-activations as lanes 0-63.  That lets the 8 epilogue warps sit on all four TMEM lane quarters = all four SM
     // sub-partitions (warp % 4): quarters q and q + 2 share the rows (q & 1) * 32 .. + 31 and split the column groups.  With the epilogue
     // on quarters 0 and 1 only (zero rows 64-127), two schedulers and half of the MUFU units did all the cell math.
-    constexpr int W_TMA = VROWS == 64 ? 8 : 0, W_MMA = VROWS == 64 ? 9 : 1, W_ALLOC = VROWS == 64 ? 10 : 2, W_PREF = VROWS == 64 ? 11 : 3;
-    const bool is_epi = VROWS == 64 ? (warp < 8) : (warp >= 4);
+    constexpr int W_EPI64 = 2 * CG;               // 64-row blocks: epilogue warps 0 .. 2 CG - 1, then the four role warps
+    constexpr int W_TMA = VROWS == 64 ? W_EPI64 : 0, W_MMA = VROWS == 64 ? W_EPI64 + 1 : 1, W_ALLOC = VROWS == 64 ? W_EPI64 + 2 : 2,
+                  W_PREF = VROWS == 64 ? W_EPI64 + 3 : 3;
+    const bool is_epi = VROWS == 64 ? (warp < W_EPI64) : (warp >= 4);
     const int quarter = warp & 3;
     const int halfsel = VROWS == 64 ? ((warp >> 2) * 2 + (quarter >> 1)) : ((warp - 4) >> 2);      // halfsel = column group 0..CG-1
 
@@ -201,7 +206,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
     } else if (warp == W_PREF) {
         // ===================== L2 prefetcher: the input-projection rows of step s+2 (they do not depend on the recurrence) ========
         // xproj (134 + 268 MB at B=4096) does not fit in L2; without this every epilogue load is an HBM-latency miss.
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < S && p.prefetch; ++s) {
             // pace: rows of step s are requested once step s-3 is complete (two steps ahead of the cell epilogue).  A parity wait on
             // a phase that is already two behind simply returns one phase later; a later phase of that parity always exists here.
             if (s >= 3) mbar_wait(&h_ready[NC - 1], static_cast<uint32_t>((s - 3) & 1), p.err_flag, 206);
@@ -402,6 +407,9 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
     LstmFusedParams p;
     p.err_flag = err_flag;
     p.dbg = g_lstm_dbg;
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("STAIR_LSTM_PF"); pf = e ? atoi(e) : 0; }
+    p.prefetch = pf;
     LstmSeq v; v.xproj = reinterpret_cast<const bf16*>(xproj_v); v.c = c_scratch; v.out = reinterpret_cast<bf16*>(vid_out);
     v.final_h = nullptr; v.q_off = nullptr; v.steps = T; v.B = B; v.h = h;
     LstmSeq t; t.xproj = reinterpret_cast<const bf16*>(xproj_t); t.c = c_scratch + 2LL * ((B + LF_ROWS - 1) / LF_ROWS) * LF_ROWS * h; t.out = reinterpret_cast<bf16*>(tokfeat);
@@ -418,12 +426,15 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
     const int smem = 2 * (h / 64) * LF_KB_BYTES + LF_STAGES * LF_W_STAGE_BYTES + 256 + 1024;
     // variants: 0 = 128 rows, 2 column groups (round-1 default); 1 = 128 rows, 4 column groups (comparison); 2 = training history,
     // 128 rows; 3 = 64 rows per CTA, 4 column groups; 4 = training history, 64 rows
-    static int configured[5] = {0, 0, 0, 0, 0};
+    // 5 / 6 = 64 rows, 8 column groups (16 epilogue warps, 96 registers; comparison), inference / training history
+    static int configured[7] = {0, 0, 0, 0, 0, 0, 0};
     const bool r64 = g_lstm_rows == 64;
-    const int vi = hist ? (r64 ? 4 : 2) : (r64 ? 3 : (g_lstm_cg == 4 ? 1 : 0));
+    const int vi = hist ? (r64 ? (g_lstm_cg == 8 ? 6 : 4) : 2) : (r64 ? (g_lstm_cg == 8 ? 5 : 3) : (g_lstm_cg == 4 ? 1 : 0));
     if (configured[vi] < smem) {
         cudaError_t e;
         switch (vi) {
+        case 6: e = cudaFuncSetAttribute(lstm_fused_kernel<8, true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+        case 5: e = cudaFuncSetAttribute(lstm_fused_kernel<8, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
         case 4: e = cudaFuncSetAttribute(lstm_fused_kernel<4, true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
         case 3: e = cudaFuncSetAttribute(lstm_fused_kernel<4, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
         case 2: e = cudaFuncSetAttribute(lstm_fused_kernel<2, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
@@ -436,6 +447,8 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
     const int vrows = r64 ? 64 : 128;
     dim3 grid((B + vrows - 1) / vrows, 2, nseq);
     switch (vi) {
+    case 6: lstm_fused_kernel<8, true, 64><<<grid, 640, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
+    case 5: lstm_fused_kernel<8, false, 64><<<grid, 640, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
     case 4: lstm_fused_kernel<4, true, 64><<<grid, 384, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
     case 3: lstm_fused_kernel<4, false, 64><<<grid, 384, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
     case 2: lstm_fused_kernel<2, true, 128><<<grid, 128 + 128 * 2, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p); break;
@@ -450,4 +463,4 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
 
 extern "C" int stair_lstm_debug(unsigned int* pinned_buf) { stair::g_lstm_dbg = pinned_buf; return STAIR_OK; }
 extern "C" int stair_lstm_rows(int rows) { if (rows != 64 && rows != 128) return STAIR_ERR_ARG; stair::g_lstm_rows = rows; return STAIR_OK; }
-extern "C" int stair_lstm_colgroups(int cg) { if (cg != 2 && cg != 4) return STAIR_ERR_ARG; stair::g_lstm_cg = cg; return STAIR_OK; }
+extern "C" int stair_lstm_colgroups(int cg) { if (cg != 2 && cg != 4 && cg != 8) return STAIR_ERR_ARG; stair::g_lstm_cg = cg; return STAIR_OK; }
