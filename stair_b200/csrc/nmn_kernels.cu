@@ -2,6 +2,7 @@
 // Each kernel states the reference lines it implements (video_nmn/modules.py, video_nmn/module_net.py) and reads its
 // [.., H] rows with 16-byte vector loads (8 x bf16 / 2 x float4), one warp (or a few lanes) per row.
 #include "nmn_kernels.cuh"
+#include <mutex>
 
 namespace stair {
 
@@ -203,23 +204,41 @@ constexpr int MAXC = 8;     // vec8 chunks per lane: rows up to H = 32*8*8 = 204
         else if (hc__ <= 128) { constexpr int CH = 4, RPW = 2; __VA_ARGS__; }                 \
         else { constexpr int CH = 8, RPW = 1; __VA_ARGS__; }                                  \
     } while (0)
-// single-pass kernels (each value used once) can afford twice the rows in flight
+// the single-pass HasItem tail: measured at H = 512 with the grid sized to the resident blocks, 8 / 4 / 2 rows per warp and pass reach
+// 59.6 / 70.9 / 78.7 % of the HBM roofline (fewer registers -> more resident warps, finer interleaving of loads and reductions);
+// the two-pass kernels (cosine maps, layernorm) measured the other way round (R = 4 -> 2: 68 -> 57 %, 82 -> 72 %)
 #define DISPATCH_CH16(H, ...)                                                                 \
     do {                                                                                      \
         const int hc__ = (H) / 8;                                                             \
-        if (hc__ <= 32) { constexpr int CH = 1, RPW = 8; __VA_ARGS__; }                       \
-        else if (hc__ <= 64) { constexpr int CH = 2, RPW = 8; __VA_ARGS__; }                  \
+        if (hc__ <= 32) { constexpr int CH = 1, RPW = 4; __VA_ARGS__; }                       \
+        else if (hc__ <= 64) { constexpr int CH = 2, RPW = 2; __VA_ARGS__; }                  \
         else if (hc__ <= 128) { constexpr int CH = 4, RPW = 4; __VA_ARGS__; }                 \
         else { constexpr int CH = 8, RPW = 2; __VA_ARGS__; }                                  \
     } while (0)
 
-// blocks of 8 warps, each warp RPW rows per iteration; at most 8 blocks per SM, and every warp gets the same number of iterations
-// (a plain cap leaves a partial last sweep: 3.46 sweeps at 32768 instances = 13 % of the time with half the machine idle)
-static inline int row_grid(long long rows, int rpw) {
+// Row kernels are persistent: blocks of 8 warps, each warp RPW rows per grid-stride iteration, and never more blocks than are RESIDENT
+// at once (148 SMs x the kernel's true occupancy, queried once per instantiation).  Sizing the grid for 8 blocks per SM when the
+// registers allow 2-3 ran 1024 blocks as 2.3-3.5 waves of 296-444 — the last wave with half the machine idle (rowdot 58 %, cosine
+// maps 67-69 % of the HBM roofline at streaming sizes).  With one resident sweep the warps differ by at most one iteration.
+static int kernel_occ(const void* fn) {
+    struct Entry { const void* fn; int occ; };
+    static Entry cache[64];
+    static int n = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n; ++i) if (cache[i].fn == fn) return cache[i].occ;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    if (occ > 8) occ = 8;
+    if (n < 64) { cache[n].fn = fn; cache[n].occ = occ; ++n; }
+    return occ;
+}
+template <typename KF>
+static inline int row_grid(KF fn, long long rows, int rpw) {
     long long b = (rows + 8LL * rpw - 1) / (8LL * rpw);
     if (b < 1) b = 1;
-    if (b > 148 * 8) { const long long iters = (b + 148 * 8 - 1) / (148 * 8); b = (b + iters - 1) / iters; }
-    return static_cast<int>(b);
+    const long long cap = 148LL * kernel_occ(reinterpret_cast<const void*>(fn));
+    return static_cast<int>(b > cap ? cap : b);
 }
 
 // att[(out_base + inst*K + k)*T + t] = (cos(f_row, kw_row) + 1) * 0.49 for RPW frame rows at a time.
@@ -374,7 +393,6 @@ __global__ void __launch_bounds__(256, 2) cos_inst_kernel(const AT* __restrict__
     }
 }
 
-static inline int inst_grid(int n) { return row_grid(n, 1); }      // blocks of 8 warps, one instance per warp and iteration
 #define DISPATCH_CH_ONLY(H, ...)                                                              \
     do {                                                                                      \
         const int hc__ = (H) / 8;                                                             \
@@ -383,7 +401,7 @@ static inline int inst_grid(int n) { return row_grid(n, 1); }      // blocks of 
         else { constexpr int CH = 4, R = 2; __VA_ARGS__; }                                    \
     } while (0)
 
-int g_row_stream = 0;      // HasItem tail: 0 = register-staged kernel (58 % of the HBM roofline at streaming sizes), 1 = TMA-staged (54 %)
+int g_row_stream = 0;      // HasItem tail: 0 = register-staged kernel (76-79 % of the HBM roofline at streaming sizes), 1 = TMA-staged (54 %)
 int g_cos_impl = 0;      // 0 = instance-major cosine maps when T % 8 == 0 (product); 1 = row-major cos_rows_kernel (comparison)
 
 int launch_cos_att(int dt, const void* f, const void* kmat, int K, int T, int H, float* att, long long out_base, int n, cudaStream_t st) {
@@ -392,12 +410,12 @@ int launch_cos_att(int dt, const void* f, const void* kmat, int K, int T, int H,
     if (g_row_stream >= 2 && row_stream_ok(dt, K, T, H)) return launch_cos_stream(dt, f, nullptr, kmat, nullptr, K, T, H, att, out_base, n, st);
     const long long rows = static_cast<long long>(n) * T;
     if (T % 8 == 0 && H <= 1024 && g_cos_impl == 0) {
-        DISPATCH_DT(dt, AT, DISPATCH_CH_ONLY(H, (cos_inst_kernel<AT, CH, R><<<inst_grid(n), 256, 0, st>>>(
+        DISPATCH_DT(dt, AT, DISPATCH_CH_ONLY(H, (cos_inst_kernel<AT, CH, R><<<row_grid(cos_inst_kernel<AT, CH, R>, n, 1), 256, 0, st>>>(
                                 reinterpret_cast<const AT*>(f), nullptr, reinterpret_cast<const AT*>(kmat), nullptr, K, T, H, att, out_base, n))));
         STAIR_CHECK_LAUNCH();
         return STAIR_OK;
     }
-    DISPATCH_DT(dt, AT, DISPATCH_CH(H, (cos_rows_kernel<AT, CH, RPW><<<row_grid(rows, RPW), 256, 0, st>>>(
+    DISPATCH_DT(dt, AT, DISPATCH_CH(H, (cos_rows_kernel<AT, CH, RPW><<<row_grid(cos_rows_kernel<AT, CH, RPW>, rows, RPW), 256, 0, st>>>(
                             reinterpret_cast<const AT*>(f), nullptr, reinterpret_cast<const AT*>(kmat), nullptr, K, T, H, att, out_base, static_cast<int>(rows)))));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
@@ -410,12 +428,12 @@ int launch_existsframe(int dt, const void* vid, const int* feat_idx, const void*
     if (g_row_stream >= 2 && row_stream_ok(dt, 1, T, H)) return launch_cos_stream(dt, vid, feat_idx, vec, kw_idx, 1, T, H, att, out_base, n, st);
     const long long rows = static_cast<long long>(n) * T;
     if (T % 8 == 0 && H <= 1024 && g_cos_impl == 0) {
-        DISPATCH_DT(dt, AT, DISPATCH_CH_ONLY(H, (cos_inst_kernel<AT, CH, R><<<inst_grid(n), 256, 0, st>>>(
+        DISPATCH_DT(dt, AT, DISPATCH_CH_ONLY(H, (cos_inst_kernel<AT, CH, R><<<row_grid(cos_inst_kernel<AT, CH, R>, n, 1), 256, 0, st>>>(
                                 reinterpret_cast<const AT*>(vid), feat_idx, reinterpret_cast<const AT*>(vec), kw_idx, 1, T, H, att, out_base, n))));
         STAIR_CHECK_LAUNCH();
         return STAIR_OK;
     }
-    DISPATCH_DT(dt, AT, DISPATCH_CH(H, (cos_rows_kernel<AT, CH, RPW><<<row_grid(rows, RPW), 256, 0, st>>>(
+    DISPATCH_DT(dt, AT, DISPATCH_CH(H, (cos_rows_kernel<AT, CH, RPW><<<row_grid(cos_rows_kernel<AT, CH, RPW>, rows, RPW), 256, 0, st>>>(
                             reinterpret_cast<const AT*>(vid), feat_idx, reinterpret_cast<const AT*>(vec), kw_idx, 1, T, H, att, out_base, static_cast<int>(rows)))));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
@@ -562,7 +580,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_kernel(const AT* __restrict_
 int launch_layernorm(int dt, const void* x, const float* gamma, const float* beta, void* out, long long rows, int H, cudaStream_t st) {
     if (rows <= 0) return STAIR_OK;
     if (H % 8 || H > 256 * MAXC) return STAIR_ERR_UNSUPPORTED;
-    DISPATCH_DT(dt, AT, DISPATCH_CH(H, (layernorm_kernel<AT, CH, RPW><<<row_grid(rows, RPW), 256, 0, st>>>(
+    DISPATCH_DT(dt, AT, DISPATCH_CH(H, (layernorm_kernel<AT, CH, RPW><<<row_grid(layernorm_kernel<AT, CH, RPW>, rows, RPW), 256, 0, st>>>(
                             reinterpret_cast<const AT*>(x), gamma, beta, reinterpret_cast<AT*>(out), rows, H))));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
@@ -743,7 +761,7 @@ int launch_rowdot_sigmoid(int dt, const void* x, const float* w, const float* b,
     if (H % 8 || H > 256 * MAXC) return STAIR_ERR_UNSUPPORTED;
     if (g_row_stream && row_stream_ok(dt, 1, T, H)) return launch_rowdot_stream(dt, x, w, b, att, out_base, n, T, H, st);
     const long long rows = static_cast<long long>(n) * T;
-    DISPATCH_DT(dt, AT, DISPATCH_CH16(H, (rowdot_sigmoid_kernel<AT, CH, RPW><<<row_grid(rows, RPW), 256, 0, st>>>(
+    DISPATCH_DT(dt, AT, DISPATCH_CH16(H, (rowdot_sigmoid_kernel<AT, CH, RPW><<<row_grid(rowdot_sigmoid_kernel<AT, CH, RPW>, rows, RPW), 256, 0, st>>>(
                             reinterpret_cast<const AT*>(x), w, b, att, static_cast<long long>(out_base) * T, rows, H))));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
