@@ -47,6 +47,22 @@ def span_to_attention(gold, T):
     return g
 
 
+def create_attention_from_frame_interval(frame_interval, K, T):
+    """module_net.py:190-208 — soft gold attention [K, T] from K float intervals (host, numpy).  Unused by the reference's own training
+    loop (which calls ``span_to_attention``); kept because it is part of the module_net.py surface.  Same arithmetic, including the
+    wrap-around of ``gold[start_int - 1]`` when ``start_int == 0`` cannot happen (start is clamped to >= 0.001) and the IndexError the
+    reference raises when ``floor(end) == T`` cannot either (end is clamped to <= T - 0.001)."""
+    g = np.zeros((K, T), np.float32)
+    for i in range(K):
+        start, end = max(0.001, frame_interval[i][0]), min(T - 0.001, frame_interval[i][1])
+        si, ei = math.ceil(start), math.floor(end)
+        if si < ei:
+            g[i, si:ei] += 1
+        g[i, si - 1] += si - start
+        g[i, ei] += end - ei
+    return g
+
+
 class LossRows:
     """Flat loss-row tables of one window (host numpy), see ``StairTrain`` in include/stair_b200.h."""
 

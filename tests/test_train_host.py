@@ -1,5 +1,6 @@
 """CPU: host side of the training step — loss-row collation (train_module.py:350-373 inclusion rules), span_to_attention,
 touched-parameter bookkeeping — against the golden fixtures written by the unmodified reference."""
+import numpy as np
 import pytest
 import torch
 
@@ -72,3 +73,12 @@ def test_grad_slots_cover_every_trainable_tensor_once():
     assert all(k.startswith(('submodules.Filter.attention.', 'submodules.FilterFrame.pretrain_head.')) for k in missing), missing
     assert all(v == 1 for v in covered.values())
     assert L.W['COUNT'] > max(tg)
+
+
+def test_create_attention_from_frame_interval_known_answers():
+    """module_net.py:190-208 (the worked example in its comments: (0.2, 5.8) -> gold[0] = 0.8, gold[1:5] = 1, gold[5] = 0.8)."""
+    from stair_b200.train import create_attention_from_frame_interval
+    g = create_attention_from_frame_interval([(0.2, 5.8), (2.0, 3.5), (-1.0, 99.0)], 3, 8)
+    np.testing.assert_allclose(g[0], [0.8, 1, 1, 1, 1, 0.8, 0, 0], atol=1e-6)
+    np.testing.assert_allclose(g[1], [0, 0, 1, 0.5, 0, 0, 0, 0], atol=1e-6)          # ceil(2.0) = 2 = floor: gold[1] += 0, gold[2:3] = 1, gold[3] += 0.5
+    np.testing.assert_allclose(g[2], [0.999, 1, 1, 1, 1, 1, 1, 0.999], atol=1e-5)    # clamped to (0.001, T - 0.001)
