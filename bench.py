@@ -171,6 +171,8 @@ def main():
     ap.add_argument('--batch', type=int, default=PER_GPU_B, help='questions per GPU (default: the BASELINE config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step leg (BASELINE configs[3])')
+    ap.add_argument('--no-overlap-allreduce', action='store_true',
+                    help='training leg at N > 1: one gradient all-reduce after the whole backward instead of overlapping it with BPTT (comparison)')
     ap.add_argument('--workload', default='rx', choices=['rx', 'i3d'],
                     help="rx (default, BASELINE configs[1]): T=8, V=4096, the 10 AGQA templates; i3d (configs[4] stress test): T=64, V=1024, "
                          "conv-mode Temporal, only the >= 9-module layouts (compare, xor_between)")
@@ -347,7 +349,7 @@ def main():
         tmodel = VideoNMN(dict(cfg, dropout=TRAIN_DROPOUT), pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16')
         tmodel.load_state_dict(weights)
         tmodel = tmodel.to(dev).train()
-        tstep = NMNTrainStep(tmodel)
+        tstep = NMNTrainStep(tmodel, overlap_allreduce=not args.no_overlap_allreduce)
         opt = FusedAdam(tmodel, lr=2e-4)
         plan = tstep.plan(batch)
 

@@ -263,6 +263,14 @@ int64_t stair_train_workspace_bytes(const StairModel* model /*HOST*/, const Stai
                                     const StairTrain* train /*HOST*/);
 int stair_nmn_forward_train(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, void* stream);
 int stair_nmn_backward(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, void* stream);
+/* The same backward in two enqueue steps (train_module.py:408 is one loss.backward()): STAIR_BWD_MODULES = losses + decoder + module
+ * groups — afterwards every StairTrain.grad slot except the encoders' (STAIR_W_VENC_* / STAIR_W_TENC_*) is final —, STAIR_BWD_ENCODERS =
+ * BPTT + encoder weight gradients.  A data-parallel caller all-reduces the module gradients while the encoders back-propagate. */
+#define STAIR_BWD_MODULES 1
+#define STAIR_BWD_ENCODERS 2
+#define STAIR_BWD_ALL 3
+int stair_nmn_backward_phases(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, int phases,
+                              void* stream);
 /* torch.optim.Adam step (weight_decay 0) on one parameter tensor; `step` counts from 1 (train_module.py:326-332,408-412) */
 int stair_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, double beta1, double beta2,
                     float eps, int step, void* stream);      /* betas are doubles: 1 - beta is formed in double like torch does */

@@ -726,11 +726,15 @@ int modules_bwd(BCtx& b) {
     return STAIR_OK;
 }
 
-int run_backward(BCtx& b) {
+// phases: STAIR_BWD_MODULES = losses + decoder + module groups (every gradient slot except the encoders' is final afterwards),
+// STAIR_BWD_ENCODERS = BPTT + encoder weight gradients.  Split so that a data-parallel caller can all-reduce the module gradients
+// while the encoders are still back-propagating.
+int run_backward(BCtx& b, int phases = STAIR_BWD_ALL) {
     Ctx& c = b.c;
     const StairTrain& tr = b.tr;
     const StairBuffers& buf = c.buf;
     const long long T = c.T, H = c.H;
+    if (!(phases & STAIR_BWD_MODULES)) return (phases & STAIR_BWD_ENCODERS) ? encoders_bwd(b) : STAIR_OK;
     if (!b.dry) {
         cudaError_t e = cudaMemsetAsync(tr.dvid, 0, sizeof(float) * buf.vid_slots * T * H, c.st);
         if (e == cudaSuccess) e = cudaMemsetAsync(tr.dvec, 0, sizeof(float) * buf.vec_rows * H, c.st);
@@ -744,7 +748,7 @@ int run_backward(BCtx& b) {
     STAIR_TRY(losses(b));
     STAIR_TRY(decoder_bwd(b));
     STAIR_TRY(modules_bwd(b));
-    STAIR_TRY(encoders_bwd(b));
+    if (phases & STAIR_BWD_ENCODERS) STAIR_TRY(encoders_bwd(b));
     return STAIR_OK;
 }
 
@@ -818,7 +822,12 @@ extern "C" int stair_nmn_forward_train(const StairModel* model, const StairBatch
 }
 
 extern "C" int stair_nmn_backward(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, void* stream) {
-    if (!model || !batch || !buf || !train) return STAIR_ERR_ARG;
+    return stair_nmn_backward_phases(model, batch, buf, train, STAIR_BWD_ALL, stream);
+}
+
+extern "C" int stair_nmn_backward_phases(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, int phases,
+                                         void* stream) {
+    if (!model || !batch || !buf || !train || !(phases & STAIR_BWD_ALL)) return STAIR_ERR_ARG;
     if (batch->B <= 0) return STAIR_OK;
     Ctx c{*model, *batch, *buf, reinterpret_cast<cudaStream_t>(stream)};
     STAIR_TRY(make_ctx(c, *model, *batch, *buf));
@@ -830,7 +839,7 @@ extern "C" int stair_nmn_backward(const StairModel* model, const StairBatch* bat
     b.ws.base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(train->workspace) + 255) & ~static_cast<uintptr_t>(255));
     b.ws.cap = train->workspace_bytes - 256;
     const long long before = g_launch_count;
-    const int rc = run_backward(b);
+    const int rc = run_backward(b, phases);
     t_last_launches = g_launch_count - before;
     if (rc == STAIR_OK && b.ws.overflow) return STAIR_ERR_CAPACITY;
     return rc;

@@ -200,13 +200,14 @@ class NMNTrainStep:
     >>> opt.step(); opt.zero_grad()
 
     Data-parallel (one process per GPU): pass ``process_group`` (or leave the default group initialised); every rank
-    passes its own shard, ``gradient_accumulation`` defaults to the global window size, gradients are summed with one
-    NCCL all-reduce over the flat fp32 gradient buffer and the per-parameter *touched* flags are OR-reduced.
+    passes its own shard, ``gradient_accumulation`` defaults to the global window size, gradients are summed with NCCL
+    all-reduces over the flat fp32 gradient buffer (decoder / module slots while the encoders still back-propagate, encoder slots
+    after; ``overlap_allreduce=False`` = one all-reduce after the whole backward) and the *touched* flags are OR-reduced.
     """
 
     def __init__(self, model, module_loss_weight=1.0, decoder_loss_weight=1.0, gradient_accumulation=None,
                  modules_no_intermediate_train=('FilterFrame',), distributed=None, process_group=None, global_negatives=True,
-                 dropout_seed=None, save_activations_budget=24 << 30, word2id=None):
+                 dropout_seed=None, save_activations_budget=24 << 30, word2id=None, overlap_allreduce=True):
         self.model = model
         self.module_loss_weight, self.decoder_loss_weight = module_loss_weight, decoder_loss_weight
         self.gradient_accumulation = gradient_accumulation
@@ -230,6 +231,10 @@ class NMNTrainStep:
         self._cache = {}
         self.last = None
         self.last_launches = 0
+        # data parallel: all-reduce the decoder / module gradients while the encoders are still back-propagating (two-phase backward);
+        # split_backward forces the two-phase enqueue without a process group (single-GPU equivalence test)
+        self.overlap_allreduce = bool(overlap_allreduce)
+        self.split_backward = False
 
     # ---- flat gradient buffer ------------------------------------------------------------------------------------
     def _layout(self):
@@ -386,13 +391,32 @@ class NMNTrainStep:
         stream = L.stream_ptr()
         L.check(lib.stair_nmn_forward_train(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), stream), 'stair_nmn_forward_train')
         launches = int(lib.stair_last_launch_count())
-        L.check(lib.stair_nmn_backward(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), stream), 'stair_nmn_backward')
-        self.last_launches = launches + int(lib.stair_last_launch_count())
-
         touched = pl.touched                                               # already the union over ranks (plan)
-        if pl.world > 1:
-            dist.all_reduce(flat, group=self.group)                        # NCCL sum over NVLink: gradients
-            dist.all_reduce(loss, group=self.group)
+        if (pl.world > 1 or self.split_backward) and self.overlap_allreduce:
+            # Two enqueue steps: once losses + decoder + module groups are back-propagated every gradient slot except the encoders' is
+            # final, so its NCCL all-reduce (the tail of the flat buffer: slots are laid out in STAIR_W_* order, encoders first) runs on
+            # NCCL's stream while BPTT and the encoder weight gradients are still computed; the encoder slots follow.
+            enc_end = min(offsets[w] for w in offsets if w >= L.W['DEC0_W'])
+            L.check(lib.stair_nmn_backward_phases(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), L.i32(1), stream),
+                    'stair_nmn_backward_phases(modules)')
+            launches += int(lib.stair_last_launch_count())
+            works = []
+            if pl.world > 1:
+                works.append(dist.all_reduce(flat[enc_end:], group=self.group, async_op=True))
+            L.check(lib.stair_nmn_backward_phases(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), L.i32(2), stream),
+                    'stair_nmn_backward_phases(encoders)')
+            self.last_launches = launches + int(lib.stair_last_launch_count())
+            if pl.world > 1:
+                works.append(dist.all_reduce(flat[:enc_end], group=self.group, async_op=True))
+                works.append(dist.all_reduce(loss, group=self.group, async_op=True))
+                for w in works:
+                    w.wait()                                               # the current stream waits for NCCL's
+        else:
+            L.check(lib.stair_nmn_backward(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), stream), 'stair_nmn_backward')
+            self.last_launches = launches + int(lib.stair_last_launch_count())
+            if pl.world > 1:
+                dist.all_reduce(flat, group=self.group)                    # NCCL sum over NVLink: gradients
+                dist.all_reduce(loss, group=self.group)
         if assign_grads:
             for wid, (numel, targets) in tg.items():
                 if wid not in touched:

@@ -513,3 +513,27 @@ def test_shared_memory_contrastive_loss_matches_register_kernel(precision):
     for k in g1:
         err = float((g0[k] - g1[k]).norm())
         assert err <= tol * float(g1[k].norm()) + 1e-9, '%s: %g vs norm %g' % (k, err, float(g1[k].norm()))
+
+
+def test_two_phase_backward_equals_single_call():
+    """stair_nmn_backward_phases(MODULES) then (ENCODERS) — the enqueue order the data-parallel step uses to overlap the NCCL all-reduce
+    of the module gradients with BPTT — leaves the same gradients as the single stair_nmn_backward call."""
+    cfg = syn.model_config(T=8, V=256, hidden=128, object_types=16)
+    torch.manual_seed(23)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().train()
+    qs = syn.make_questions(97, 8, 256, seed=37, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    res = []
+    for split in (False, True):
+        for prm in model.parameters():
+            prm.grad = None
+        step = NMNTrainStep(model, dropout_seed=3)
+        step.split_backward = split
+        out = step(qs, dropout_seed=11)
+        torch.cuda.synchronize()
+        model.check_status(out['state'])
+        res.append((float(out['loss']), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = res
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)                                  # the loss terms are atomic float sums
+    assert g0.keys() == g1.keys() and any('encoder' in k for k in g0)
+    for k in g0:
+        assert float((g0[k] - g1[k]).norm()) <= 1e-5 * float(g0[k].norm()) + 1e-9, k           # atomic summation order only
