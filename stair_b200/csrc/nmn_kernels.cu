@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256, 2) cos_inst_kernel(const AT* __restrict__
 #pragma unroll
                 for (int i = 0; i < CH; ++i) {
                     const int c = lane + 32 * i;
-                    if (c < hc) x[r][i].load(fbase + static_cast<long long>(t0 + r) * H + c * 8); else x[r][i].zero();
+                    if (c < hc) x[r][i].load_stream(fbase + static_cast<long long>(t0 + r) * H + c * 8); else x[r][i].zero();
                 }
             float ff_mine = 0.f;
             for (int k = 0; k < K; ++k) {
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_kernel(const AT* __restrict_
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
                 const int c = lane + 32 * i;
-                if (c < hc) v[r][i].load(x + row * H + c * 8); else v[r][i].zero();
+                if (c < hc) v[r][i].load_stream(x + row * H + c * 8); else v[r][i].zero();
             }
         }
         float mean[RPW], rstd[RPW];
@@ -599,7 +599,7 @@ __global__ void sum_T_kernel(const AT* __restrict__ x, AT* __restrict__ out, int
         for (; t + 8 <= T; t += 8) {                       // 8 independent 16-byte loads in flight, summed in frame order
             Vec8<AT> v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u].load(x + (r * T + t + u) * H + c);
+            for (int u = 0; u < 8; ++u) v[u].load_stream(x + (r * T + t + u) * H + c);
 #pragma unroll
             for (int u = 0; u < 8; ++u)
 #pragma unroll
@@ -733,7 +733,7 @@ __global__ void rowdot_sigmoid_kernel(const AT* __restrict__ x, const float* __r
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
                 const int c = lane + 32 * i;
-                if (c < hc) v[r][i].load(x + row * H + c * 8); else v[r][i].zero();
+                if (c < hc) v[r][i].load_stream(x + row * H + c * 8); else v[r][i].zero();
             }
         }
         float s[RPW];
