@@ -959,8 +959,66 @@ __global__ void l2norm_kernel(const AT* __restrict__ vec, int row_base, float* _
     }
 }
 
+// same, R rows per warp and pass held in registers (each row read once, past L1); H <= 256 * CH
+template <typename AT, int CH, int R>
+__global__ void __launch_bounds__(256) l2norm_rows_kernel(const AT* __restrict__ vec, int row_base, float* __restrict__ out, int out_base, int n, int H) {
+    const int lane = threadIdx.x & 31, hc = H / 8;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int i0 = warp * R; i0 < n; i0 += nwarps * R) {
+        Raw8<AT> x[R][CH];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = i0 + r < n ? i0 + r : n - 1;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int c = lane + 32 * k;
+                if (c < hc) x[r][k].load_stream(vec + static_cast<long long>(row_base + i) * H + c * 8); else x[r][k].zero();
+            }
+        }
+        float ss[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                float f[8]; x[r][k].unpack(f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a = fmaf(f[j], f[j], a);
+            }
+            ss[r] = a;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < R; ++r) ss[r] += __shfl_xor_sync(0xffffffffu, ss[r], o);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (i0 + r >= n) break;
+            const float inv = 1.0f / fmaxf(sqrtf(ss[r]), 1e-12f);
+            float* o = out + static_cast<long long>(out_base + i0 + r) * H;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int c = lane + 32 * k;
+                if (c < hc) {
+                    float f[8]; x[r][k].unpack(f);
+                    Vec8<float> y;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y.v[j] = f[j] * inv;
+                    y.store(o + c * 8);
+                }
+            }
+        }
+    }
+}
+
 int launch_l2norm(int dt, const void* vec, int row_base, float* out, int out_base, int n, int H, cudaStream_t st) {
     if (n <= 0) return STAIR_OK;
+    if (H % 8 == 0 && H <= 1024) {
+        DISPATCH_DT(dt, AT, DISPATCH_CH_ONLY(H, (l2norm_rows_kernel<AT, CH, 4><<<row_grid(l2norm_rows_kernel<AT, CH, 4>, n, 4), 256, 0, st>>>(
+                                reinterpret_cast<const AT*>(vec), row_base, out, out_base, n, H))));
+        STAIR_CHECK_LAUNCH();
+        return STAIR_OK;
+    }
     DISPATCH_DT(dt, AT, (l2norm_kernel<AT><<<min(blocks_for(n, 8), 148 * 8), 256, 0, st>>>(reinterpret_cast<const AT*>(vec), row_base, out, out_base, n, H)));
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
