@@ -111,11 +111,15 @@ __device__ __forceinline__ void stage_chunk(uint32_t buf, int lane, int half, in
     }
 }
 
-template <int BN, int STAGES>
+// EPI = epilogue warp sets (4 warps each, one per TMEM lane quarter).  With EPI = 2 the second set (warps 8-11) takes the upper half of
+// the tile's columns: short-K GEMMs (module Linears K = 512, text projection K = 300) are bound by the epilogue — TMEM -> registers ->
+// bias / ReLU / dropout -> bf16 -> swizzled smem -> TMA store takes longer than the tile's MMAs — so two sets halve the tile time; the
+// extra staging costs one pipeline stage of shared memory, which a K loop of <= 8 k-blocks does not miss.
+template <int BN, int STAGES, int EPI = 1>
 struct GemmSmem {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int TILE_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-    static constexpr int STAGING_BYTES = 4 * 2 * 4096;            // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+    static constexpr int STAGING_BYTES = EPI * 4 * 2 * 4096;      // 4 EPI epilogue warps x 2 buffers x (32 rows x 128 B)
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr int TOTAL = TILE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
 };
@@ -172,11 +176,12 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int
     }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS + 128 * (EPI - 1), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-    using S = GemmSmem<BN, STAGES>;
+    using S = GemmSmem<BN, STAGES, EPI>;
+    static_assert(EPI == 1 || (EPI == 2 && BN >= 128), "two epilogue sets split the tile's 64-column boxes");
     constexpr int B_STAGE_BYTES = S::B_STAGE_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // power of two by construction (BN in {64,128,256})
     constexpr uint32_t IDESC = make_idesc_bf16(BM, BN);
@@ -205,7 +210,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128 * EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -304,7 +309,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int quarter = warp - 4;                          // TMEM lanes [32*quarter, 32*quarter+32)
+        const int quarter = (warp - 4) & 3;                    // TMEM lanes [32*quarter, 32*quarter+32)
+        const int eset = (warp - 4) >> 2;                      // epilogue set: 32-column chunks [c_begin, c_end) of the tile
+        constexpr int CHUNKS = BN / 32 / EPI;
+        const int c_begin = eset * CHUNKS, c_end = c_begin + CHUNKS;
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;
         for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
@@ -318,13 +326,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (p.tma_store) {
                 // TMEM -> registers (next chunk's tcgen05.ld in flight while this one is processed) -> swizzled smem -> TMA store
                 const float rs = (p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.0f;
-                const uint32_t stage0 = smem_u32(sStage) + static_cast<uint32_t>(quarter) * 8192u;
+                const uint32_t stage0 = smem_u32(sStage) + static_cast<uint32_t>(eset * 4 + quarter) * 8192u;
                 const int per_buf = p.out_dtype == STAIR_BF16 ? 2 : 1;          // TMEM chunks per 128-byte staging row
                 uint32_t ra[32], rb[32];
                 float v[32];
-                tmem_ld32(t_base, ra);
+                tmem_ld32(t_base + static_cast<uint32_t>(c_begin * 32), ra);
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; c += 2) {
+                for (int c = c_begin; c < c_end; c += 2) {
                     if (n0 + c * 32 >= p.N) break;                               // warp-uniform
                     tmem_ld_wait();
                     tmem_ld32(t_base + static_cast<uint32_t>((c + 1) * 32), rb);
@@ -333,7 +341,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const int cc = c + hsel;
                         if (hsel == 1) {
                             tmem_ld_wait();
-                            if (cc + 1 < BN / 32) tmem_ld32(t_base + static_cast<uint32_t>((cc + 1) * 32), ra);
+                            if (cc + 1 < c_end) tmem_ld32(t_base + static_cast<uint32_t>((cc + 1) * 32), ra);
                         }
                         const int n = n0 + cc * 32;
                         const int half = per_buf == 2 ? hsel : 0;
@@ -358,7 +366,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tmem_ld_wait();
             } else {
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = c_begin * 32; c0 < c_end * 32; c0 += 32) {
                 if (n0 + c0 >= p.N) break;                     // warp-uniform
                 uint32_t v[32];
                 tmem_ld32(t_base + static_cast<uint32_t>(c0), v);
@@ -472,6 +480,7 @@ static int g_epilogue_impl = 0;  // 0 = staged TMA-store epilogue, 1 = direct pe
 static int* g_err_flag = nullptr;
 static int g_num_sms = 0;
 static int g_dw_wide = 0;        // 1 = 128 x 256 tiles for MN-major (weight-gradient) GEMMs (measured slower: 33.4 vs 30.7 us, profiles/micro_dw.py)
+static int g_gemm_epi2 = 1;      // 1 = two epilogue warp sets for short-K GEMMs (num_kb <= 8); 0 = always one set (comparison)
 static int g_split_k = 1;        // 1 = split-K for accumulating GEMMs with few output tiles (weight gradients)
 static unsigned long long* g_dbg = nullptr;
 
@@ -483,12 +492,12 @@ int* err_flag_ptr() {
     return g_err_flag;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI = 1>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, cudaStream_t st) {
-    using S = GemmSmem<BN, STAGES>;
+    using S = GemmSmem<BN, STAGES, EPI>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
             return STAIR_ERR_CUDA;
         configured = true;
     }
@@ -506,7 +515,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     }
     const int items = tiles * q.ksplit;
     const int grid = items < g_num_sms ? items : g_num_sms;
-    gemm_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, tc, q);
+    gemm_tcgen05_kernel<BN, STAGES, EPI><<<grid, GEMM_THREADS + 128 * (EPI - 1), S::TOTAL, st>>>(ta, tb, tc, q);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -573,9 +582,11 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
         rc = make_tmap_out(&tc, a.C, a.out_dtype, a.N, a.M, a.ldc);
         if (rc) return rc;
     }
+    // short K loops are epilogue-bound: two epilogue warp sets, one pipeline stage fewer (see GemmSmem)
+    const bool epi2 = g_gemm_epi2 && p.num_kb * p.nseg <= 8 && !a.mn_major;
     if (bn == 64) return launch_tc<64, 8>(ta, tb, tc, p, st);
-    if (bn == 256) return launch_tc<256, 4>(ta, tb, tc, p, st);
-    return launch_tc<128, 6>(ta, tb, tc, p, st);
+    if (bn == 256) return epi2 ? launch_tc<256, 3, 2>(ta, tb, tc, p, st) : launch_tc<256, 4>(ta, tb, tc, p, st);
+    return epi2 ? launch_tc<128, 5, 2>(ta, tb, tc, p, st) : launch_tc<128, 6>(ta, tb, tc, p, st);
 }
 
 }  // namespace stair
@@ -583,6 +594,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
 using namespace stair;
 
 extern "C" int stair_set_gemm_impl(int impl) { g_gemm_impl = impl; return STAIR_OK; }
+extern "C" int stair_set_gemm_epi2(int on) { g_gemm_epi2 = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_dw_wide(int on) { g_dw_wide = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_split_k(int on) { g_split_k = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_gemm_debug_timeline(unsigned long long* dev_buf) { g_dbg = dev_buf; return STAIR_OK; }

@@ -176,3 +176,31 @@ def test_gemm_tn_matches_fp32_reference(case, impl):
     want = (ref.float() + C0) if acc else ref.float()
     err = (C - want).abs().max().item()
     assert err <= 2e-4 * max(want.abs().max().item(), 1.0), 'max err %g' % err
+
+
+@pytest.mark.parametrize('shape', [(1000, 512, 512), (333, 256, 300), (4096, 2048, 320), (130, 384, 64), (2048, 512, 1024)])
+@pytest.mark.parametrize('odt', [torch.bfloat16, torch.float32])
+def test_two_epilogue_warp_sets_are_bit_identical(shape, odt):
+    """stair_set_gemm_epi2(1) (product for K <= 512): a second set of four epilogue warps takes the upper half of every tile's columns.
+    Same accumulators, same epilogue arithmetic -> bit-identical to the single-set kernel, including ragged M / N and TMA-clipped boxes;
+    K = 1024 stays on the single-set kernel either way."""
+    M, N, K = shape
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp, device='cuda', dtype=torch.bfloat16)
+    W = torch.zeros(N, Kp, device='cuda', dtype=torch.bfloat16)
+    A[:, :K] = torch.randn(M, K, device='cuda', generator=g).bfloat16()
+    W[:, :K] = (torch.randn(N, K, device='cuda', generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device='cuda', generator=g)
+    rs = torch.rand(M, device='cuda', generator=g)
+    outs = []
+    try:
+        for on in (0, 1):
+            L.lib().stair_set_gemm_epi2(on)
+            outs.append(L.gemm(A, W, bias=bias, out_dtype=odt, act=L.ACT_RELU, row_scale=rs, K=K).clone())
+            torch.cuda.synchronize()
+    finally:
+        L.lib().stair_set_gemm_epi2(1)
+    assert torch.equal(outs[0], outs[1])
+    ref = _ref(A[:, :K], W[:, :K], bias, rs, True)
+    assert (outs[1].float() - ref).abs().max().item() <= (2e-2 if odt == torch.bfloat16 else 2e-4) * max(ref.abs().max().item(), 1.0)
