@@ -234,6 +234,7 @@ int stair_set_loss_con_impl(int impl);  /* contrastive loss: 0 = shared-memory k
 int stair_set_bptt_impl(int impl);      /* encoder BPTT (bf16 path): 0 = one persistent fused kernel for both encoders / directions (product); 1 = per-step cell kernel + recurrent GEMMs */
 int stair_set_gemm_impl(int impl);      /* 0 = tcgen05 (product); 1 = SIMT debug kernel used to cross-check in tests */
 int stair_get_gemm_impl(void);
+int stair_set_gemm_wide_min(int half_waves); /* 128 x 256 tiles when a GEMM has more than half_waves * SMs / 2 tiles of 128 x 128 (default 1; 4 = the round-1 rule of two full waves) */
 int stair_set_gemm_epi2(int on);         /* 1 (default) = two epilogue warp sets (384 threads) for GEMMs with <= 8 k-blocks; 0 = one set always */
 int stair_set_gemm_split_k(int on);      /* 1 (default) = split-K with atomic accumulation for accumulating GEMMs with few output tiles */
 int stair_set_gemm_epilogue(int impl);  /* 0 = smem-staged TMA-store epilogue (product); 1 = direct per-row stores (comparison) */

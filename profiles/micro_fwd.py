@@ -12,6 +12,7 @@ qs = syn.make_questions(B, T, V, seed=1234)
 batch = collate(qs, video_dtype=torch.bfloat16).to('cuda')
 L.lib().stair_set_lanes(int(os.environ.get('LANES', 6)))
 L.lib().stair_set_gemm_epi2(int(os.environ.get('GEMM_EPI2', 1)))
+L.lib().stair_set_gemm_wide_min(int(os.environ.get('GEMM_WIDE_MIN', 1)))
 ref = None
 for cg in [2] + ([int(os.environ['LSTM_CG'])] if 'LSTM_CG' in os.environ else []):
     L.lib().stair_lstm_colgroups(cg)

@@ -481,6 +481,9 @@ static int* g_err_flag = nullptr;
 static int g_num_sms = 0;
 static int g_dw_wide = 0;        // 1 = 128 x 256 tiles for MN-major (weight-gradient) GEMMs (measured slower: 33.4 vs 30.7 us, profiles/micro_dw.py)
 static int g_gemm_epi2 = 1;      // 1 = two epilogue warp sets for short-K GEMMs (num_kb <= 8); 0 = always one set (comparison)
+static int g_wide_tiles_min = 1;  // 128 x 256 tiles when there are more than this many half-waves (SMs / 2) of 128 x 128 tiles.  Wide tiles move 25 %
+                                  // fewer operand bytes per flop and these GEMMs are L2 -> SM bandwidth bound: measured at B = 4096, forward
+                                  // 1.550 / 1.519 / 1.507 ms and training step 6.59 / 6.53 / 6.73 ms for 4 (two waves, the old rule) / 1 / 0
 static int g_split_k = 1;        // 1 = split-K for accumulating GEMMs with few output tiles (weight gradients)
 static unsigned long long* g_dbg = nullptr;
 
@@ -563,7 +566,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     // wide tiles when there are plenty of them.  The weight-gradient contraction (16 output tiles, K ~ 20 000 split over all SMs) is bound
     // by L2 -> SM operand traffic (every 128-column operand slice is re-read by 4 tiles: 160 MB for 40 MB of operands, ~6 TB/s); 128 x 256
     // tiles move 25 % fewer bytes but double the same-address atomics of the split-K epilogue and measured slower (g_dw_wide).
-    const int bn = a.N <= 64 ? 64 : ((a.N % 256 == 0 && (tiles128 >= 2 * g_num_sms || (a.mn_major && g_dw_wide))) ? 256 : 128);
+    const int bn = a.N <= 64 ? 64 : ((a.N % 256 == 0 && (tiles128 > g_wide_tiles_min * g_num_sms / 2 || (a.mn_major && g_dw_wide))) ? 256 : 128);
     CUtensorMap ta, tb;
     int rc;
     if (a.mn_major) {
@@ -595,6 +598,7 @@ using namespace stair;
 
 extern "C" int stair_set_gemm_impl(int impl) { g_gemm_impl = impl; return STAIR_OK; }
 extern "C" int stair_set_gemm_epi2(int on) { g_gemm_epi2 = on ? 1 : 0; return STAIR_OK; }
+extern "C" int stair_set_gemm_wide_min(int half_waves) { g_wide_tiles_min = half_waves < 0 ? 0 : half_waves; return STAIR_OK; }
 extern "C" int stair_set_gemm_dw_wide(int on) { g_dw_wide = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_split_k(int on) { g_split_k = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_gemm_debug_timeline(unsigned long long* dev_buf) { g_dbg = dev_buf; return STAIR_OK; }
