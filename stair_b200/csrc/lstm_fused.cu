@@ -1,7 +1,7 @@
 // Persistent fused BiLSTM recurrence (bf16 path): the whole time loop of nn.LSTM (video_nmn/module_net.py:39-47,
 // 147-163) in ONE launch for both encoders and both directions.
 //
-// One CTA owns 128 questions of one (encoder, direction) for all T (or L) steps:
+// One CTA owns 64 (product) or 128 questions of one (encoder, direction) for all T (or L) steps:
 //   h_{t-1} lives in shared memory as the bf16 A operand (128 x h, K-major, SWIZZLE_128B, double-buffered),
 //   W_hh (gate-interleaved so that a 256-column chunk = 64 hidden units x {i,f,g,o}) streams from L2 through a TMA ring,
 //   tcgen05.mma accumulates the 128 x 256 gate pre-activations of a chunk in TMEM (two chunks in flight),
@@ -9,7 +9,8 @@
 //   L2-resident), write h_t to the encoder output and straight back into the other shared-memory h buffer.
 // No per-step launches, no [B,4h] round trips: per step only xproj rows and h rows touch HBM.
 //
-// warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4..11: cell epilogue (2 warps per TMEM lane quarter)
+// 128-row form: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4.. cell epilogue; 64-row form (product): see the
+// kernel's template comment.
 #include "nmn_kernels.cuh"
 #include "tc_ptx.cuh"
 #include "train_kernels.cuh"
@@ -81,13 +82,14 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
     for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(hh[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
 
-// CG = epilogue warps per TMEM lane quarter (each takes 64 / CG of a chunk's hidden units).
-// VROWS = questions per CTA.  128: all four TMEM lane quarters carry rows, warps 0-3 are the role warps, 4.. the epilogue
-// (threads = 128 + 128 * CG).  64 (with CG = 4): the MMA is still M = 128 but only lanes 0-63 carry rows, so the 8 epilogue warps
-// are the ones whose TMEM quarter (warp % 4) is 0 or 1 — warps 0,1,4,5,8,9,12,13 — and each owns 16 of a chunk's units: half the
-// per-step epilogue latency per question block (the recurrence is a chain of L sequential steps, so that latency is the kernel's
-// critical path) and twice as many CTAs to fill the SMs the video blocks free after T steps.  Role warps: 2 TMA, 3 MMA, 6 TMEM
-// allocator, 7 L2 prefetch; 16 warps -> 128 registers per thread.
+// CG = column groups of a chunk's 64 hidden units (each epilogue thread takes 64 / CG of them).
+// VROWS = questions per CTA.  128: all four TMEM lane quarters carry distinct rows, warps 0-3 are the role warps, 4.. the epilogue
+// (CG warps per quarter, threads = 128 + 128 * CG).  64 (product, CG = 4; CG = 8 kept for comparison): the MMA is still M = 128 and
+// rows 64-127 of the h operand hold a COPY of rows 0-63, so TMEM lanes 64-127 repeat lanes 0-63 and the 2 CG epilogue warps (warps
+// 0 .. 2 CG - 1) sit on all four lane quarters = all four SM sub-partitions; quarters q and q + 2 share rows and split the column
+// groups.  Half the per-step epilogue latency per question block of the 128-row form (the recurrence is a chain of L sequential
+// steps, so that latency is the kernel's critical path) and twice as many CTAs to fill the SMs the video blocks free after T steps.
+// Role warps follow the epilogue warps: TMA, MMA, TMEM allocator, (optional) L2 prefetch; 12 warps -> up to 168 registers per thread.
 template <int CG, bool HIST, int VROWS>
 __global__ void __launch_bounds__(VROWS == 64 ? 64 * CG + 128 : 128 + 128 * CG, 1)
 lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
