@@ -124,6 +124,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t sme
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // streaming 16-byte load that does not allocate in L1: the recurrence kernels leave ~28 KiB of L1 next to 224 KiB of shared memory,
 // and that is where their register spills and L2-resident running state live
