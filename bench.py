@@ -148,8 +148,16 @@ def run_reference(args, rank, world):
     line = {'impl': 'reference', 'metric': METRIC, 'value': qps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': {'workload': 'ModuleNet inference, RX/TGIF-QA features [8,4096], mixed 10-template programs, random init; '
-                                   'CPU reference path: per-question loop, eval, no_grad; step = %d questions' % CPU_SAMPLE},
+            # the measured arm's config (same workload, same keys), plus what one reference step is
+            'config': {'workload': ('ModuleNet batched inference, %d mixed-program questions per GPU (10 AGQA layout templates, 2-12 modules), '
+                                    'RX/TGIF-QA features [8,4096] bf16, questions 8-24 words x 300, random init, bf16 storage / fp32 accumulate'
+                                    % args.batch) if args.workload == 'rx' else
+                                   ('I3D stress test (BASELINE configs[4]): %d questions per GPU, compare / xor_between layouts (9-12 modules), '
+                                    'features [64,1024] bf16, conv-mode Temporal, random init, bf16 storage / fp32 accumulate' % args.batch),
+                       'questions_per_gpu': args.batch, 'global_questions': args.gpus * args.batch, 'frames': T, 'video_size': V,
+                       'hidden_size': cfg['hidden_size'], 'parallelism': 'reference arm: host cores of rank 0 only',
+                       'reference_step': 'CPU reference path (fp32): per-question loop, eval, no_grad; one step = the first %d questions of '
+                                         'that workload (bounded sample)' % CPU_SAMPLE},
             'cpu_baseline': {'value': qps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': '%d questions per step x %d steps, torch threads=%d; oracle port of module_net.py/modules.py with '
                                        'the encoders through torch.nn.LSTM (the reference cannot travel to the GPU box: its import needs '
