@@ -183,7 +183,9 @@ typedef struct StairTrain {
     const int32_t* answer; float dec_w;
     float* loss;                  /* float[8] sums: 0 Localize 1 Temporal 2 ExistsFrame 3 Exists/Xor 4 Equals 5 contrastive 6 decoder 7 FilterFrame */
     float* dvid; float* dvec; float* datt; float* dtokfeat; float* dqfeat; float* dlogits;   /* gradient arenas (same shapes as the forward arenas) */
-    void* saved; int64_t saved_bytes;           /* LSTM gate / cell / state history written by stair_nmn_forward_train */
+    void* saved; int64_t saved_bytes;           /* BPTT history written by stair_nmn_forward_train (opaque: fp32 gates / cell / hidden state for the
+                                                 * step-wise fp32-strict path, bf16 cell-derivative coefficients + token-order hidden states for the
+                                                 * fused bf16 path); size from stair_train_saved_bytes */
     void* workspace; int64_t workspace_bytes;   /* backward scratch, >= stair_train_workspace_bytes */
     /* nn.Dropout(p) of the reference's training mode (video_nmn/args.py:31 default 0.25; sites: modules.py Linear->ReLU->Dropout
      * of Exists/Filter/FilterFrame/HasItem/Localize/Temporal/ToAction, HasItem's Sigmoid->Dropout, decoder module_net.py:49-53).
