@@ -275,6 +275,16 @@ int stair_nmn_backward(const StairModel* model, const StairBatch* batch, const S
 #define STAIR_BWD_ALL 3
 int stair_nmn_backward_phases(const StairModel* model, const StairBatch* batch, const StairBuffers* buf, const StairTrain* train, int phases,
                               void* stream);
+/* ---- one operator outside the interpreter: the per-class forward(*params) of video_nmn/modules.py:7-465 for group->count instances ----
+ * The caller places the operands in the arenas of `buf` (VID slots / VEC rows / ATT rows; tokfeat / qfeat / logits / answers / itab unused) and
+ * passes their indices: args[k * count + i] = arena index of argument k (< 3) of instance i, in the argument order the layout compiler resolves
+ * (stair_b200/layout.py Layout._resolve: keyword strings are folded into group->variant, so e.g. Temporal = {feat VID slot, attention ATT row},
+ * ExistsFrame = {keyword VEC row, feat VID slot}).  Output i lands at group->out_base + i * group->out_mult of the op's arena, aux / head rows as
+ * in StairGroup.  group->node_off is ignored.  Runs the same group code as stair_nmn_forward (no separate kernels).  buf->workspace needs
+ * stair_op_workspace_bytes bytes. */
+int64_t stair_op_workspace_bytes(const StairModel* model /*HOST*/, int T, const StairGroup* group /*HOST*/);
+int stair_op_forward(const StairModel* model /*HOST*/, int T, const StairGroup* group /*HOST*/, const int32_t* args /*DEVICE [3][count]*/,
+                     const StairBuffers* buf /*HOST*/, void* stream);
 /* torch.optim.Adam step (weight_decay 0) on one parameter tensor; `step` counts from 1 (train_module.py:326-332,408-412) */
 int stair_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, double beta1, double beta2,
                     float eps, int step, void* stream);      /* betas are doubles: 1 - beta is formed in double like torch does */

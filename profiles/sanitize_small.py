@@ -9,7 +9,7 @@ for T, V, H, prec in ((8, 128, 128, 'bf16'), (8, 64, 64, 'fp32'), (64, 64, 64, '
     cfg = syn.model_config(T=T, V=V, hidden=H, object_types=16)
     torch.manual_seed(0)
     model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision=prec).cuda().eval()
-    qs = syn.make_questions(28, T, V, seed=3, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    qs = syn.make_questions(32, T, V, seed=3, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
     out = model(qs, return_res_by_step=True, return_result_of_each_step=True)
     torch.cuda.synchronize()
     model.train()

@@ -8,5 +8,7 @@ from .layout import NARY as nary_mappings, MODULE_NAMES, WORDS_TO_KEEP, collate,
 from .nmn import VideoNMN  # noqa: F401
 from .params import L2Normalize  # noqa: F401
 
-NAME_TO_MODULE = tuple(MODULE_NAMES)      # module names in the reference's registration order (modules.py:446-465)
+from .modules import NAME_TO_MODULE  # noqa: F401,E402   name -> operator class, the reference's registration order (modules.py:446-465)
+
+assert list(NAME_TO_MODULE) == list(MODULE_NAMES)
 __version__ = '0.1.0'

@@ -290,7 +290,8 @@ inline int run_chunk(Ctx& c, const StairGroup& g, int p, int n, int ob, int ab) 
     case STAIR_OP_EXISTSFRAME:                                  // (keyword, feat) modules.py:169-178
         return launch_existsframe(dt, c.buf.vid, a1, c.buf.vec, a0, att, ob, n, T, H, c.st);
     case STAIR_OP_RELATE:                                       // variant 0 forward, 1 backward; modules.py:423-435
-        return launch_relate(att, a0, c.Wf(STAIR_W_REL_BETA), g.variant == 0 ? 1 : -1, att, ob, n, T, c.st);
+        // variants 2 / 3: the operand is a 2-D [1, T] map -> the reference adds the constant beta[0]: softmax_T(attn), sign 0
+        return launch_relate(att, a0, c.Wf(STAIR_W_REL_BETA), g.variant >= 2 ? 0 : (g.variant == 0 ? 1 : -1), att, ob, n, T, c.st);
     case STAIR_OP_ATTNVIDEO:
         return launch_attnvideo(dt, c.buf.vid, a0, att, a1, ob, n, T, H, c.st);
     case STAIR_OP_AND:

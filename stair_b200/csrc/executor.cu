@@ -84,3 +84,44 @@ extern "C" int stair_nmn_forward(const StairModel* model, const StairBatch* batc
     t_last_launches = g_launch_count - before;
     return STAIR_OK;
 }
+
+// ---- one operator group outside the interpreter ----------------------------------------------------------------------------
+// The reference exposes every operator as an nn.Module with its own forward(*params) (video_nmn/modules.py:7-465); the drop-in's
+// per-class forward (stair_b200/modules.py) packs the operands of n instances into small arenas and runs them through the very
+// same group code the interpreter uses (run_chunk), so a per-operator parity test exercises the product kernels.
+static int op_setup(const StairModel& m, int T, const StairGroup& g, StairBatch* b, Plan* plan) {
+    if (m.H % 16 || m.H > 2048 || T <= 0 || g.count <= 0) return STAIR_ERR_ARG;
+    if (g.op <= STAIR_OP_WORD || g.op >= STAIR_OP_COUNT) return STAIR_ERR_ARG;
+    if (m.conv_k == 0 && g.op == STAIR_OP_TEMPORAL && (g.variant >> 1) > 0 && T != m.T_max) return STAIR_ERR_UNSUPPORTED;
+    *b = StairBatch();
+    b->T = T; b->n_groups = 1; b->groups = &g; b->n_nodes = g.count;
+    make_plan(m, *b, plan);
+    return STAIR_OK;
+}
+
+extern "C" int64_t stair_op_workspace_bytes(const StairModel* model, int T, const StairGroup* group) {
+    if (!model || !group) return -1;
+    StairBatch b; Plan plan;
+    if (op_setup(*model, T, *group, &b, &plan) != STAIR_OK) return -1;
+    return plan.mod_bytes + 4096;
+}
+
+extern "C" int stair_op_forward(const StairModel* model, int T, const StairGroup* group, const int32_t* args, const StairBuffers* buf, void* stream) {
+    if (!model || !group || !args || !buf) return STAIR_ERR_ARG;
+    const StairModel& m = *model; const StairGroup& g = *group;
+    StairBatch b; Plan plan;
+    STAIR_TRY(op_setup(m, T, g, &b, &plan));
+    Ctx c{m, b, *buf, reinterpret_cast<cudaStream_t>(stream)};
+    c.plan = plan;
+    if (buf->workspace_bytes < plan.mod_bytes + 1024) return STAIR_ERR_CAPACITY;
+    c.ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(buf->workspace) + 1023) & ~static_cast<uintptr_t>(1023));
+    c.T = T; c.H = m.H; c.h = m.H / 2; c.np = m.precision == STAIR_F32 ? 3 : 1; c.adt = m.precision; c.esz = m.precision == STAIR_F32 ? 4 : 2;
+    c.perm = c.out_slot = c.pos_q = c.span_s = c.span_e = nullptr;
+    c.arg0 = args; c.arg1 = args + g.count; c.arg2 = args + 2 * g.count;
+    const long long before = g_launch_count;
+    StairGroup g0 = g;
+    g0.node_off = 0;
+    const int rc = run_group(c, g0, 0);
+    t_last_launches = g_launch_count - before;
+    return rc;
+}

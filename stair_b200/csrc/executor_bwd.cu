@@ -256,7 +256,7 @@ int chunk_bwd(BCtx& b, const StairGroup& g, int p, int n, int ob, int ab) {
         RUN(launch_existsframe_bwd(dt, c.buf.vid, a1, c.buf.vec, a0, tr.datt, ob, tr.dvid, tr.dvec, n, T, H, c.st));
         break;
     case STAIR_OP_RELATE:
-        RUN(launch_relate_bwd(att, ob, tr.datt, a0, g.variant == 0 ? 1 : -1, tr.datt, G(b, STAIR_W_REL_BETA), n, T, c.st));
+        RUN(launch_relate_bwd(att, ob, tr.datt, a0, g.variant >= 2 ? 0 : (g.variant == 0 ? 1 : -1), tr.datt, G(b, STAIR_W_REL_BETA), n, T, c.st));
         break;
     case STAIR_OP_ATTNVIDEO:
         RUN(launch_attnvideo_bwd(dt, dvid_out, c.buf.vid, a0, att, a1, tr.datt, tr.dvid, n, T, H, c.st));

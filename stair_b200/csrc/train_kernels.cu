@@ -671,7 +671,7 @@ __global__ void relate_bwd_kernel(const float* __restrict__ att_out, int out_bas
 
 int launch_relate_bwd(const float* att_out, int out_base, const float* datt_out, const int* att_idx, int sign, float* datt, float* dbeta, int n, int T, cudaStream_t st) {
     if (n <= 0) return STAIR_OK;
-    relate_bwd_kernel<<<nblocks(n, 8), 256, 0, st>>>(att_out, out_base, datt_out, att_idx, sign >= 0 ? 1.f : -1.f, datt, dbeta, n, T);
+    relate_bwd_kernel<<<nblocks(n, 8), 256, 0, st>>>(att_out, out_base, datt_out, att_idx, sign > 0 ? 1.f : (sign < 0 ? -1.f : 0.f), datt, dbeta, n, T);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }

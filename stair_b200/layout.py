@@ -85,10 +85,13 @@ def program_is_valid(tokens):
 
 
 class _Val:
-    __slots__ = ('type', 'node', 'K', 'text', 'level')
+    """A value on the simulated interpreter stack.  ``rank2`` distinguishes the two attention-map shapes of the reference:
+    Localize returns a 2-D ``[K, T]`` map (modules.py:205-216), ExistsFrame / HasItem a 1-D ``[T]`` one (modules.py:138,170-177) —
+    AttnVideo, Relate and Temporal behave differently (or fail) depending on which one they are given."""
+    __slots__ = ('type', 'node', 'K', 'text', 'level', 'rank2')
 
-    def __init__(self, type_, node=-1, K=1, text=None, level=0):
-        self.type, self.node, self.K, self.text, self.level = type_, node, K, text, level
+    def __init__(self, type_, node=-1, K=1, text=None, level=0, rank2=False):
+        self.type, self.node, self.K, self.text, self.level, self.rank2 = type_, node, K, text, level, bool(rank2) or K > 1
 
 
 def _type_error(tok, what):
@@ -111,7 +114,7 @@ class Layout:
         self.token_of_node = [i for i, x in enumerate(node_of_token) if x >= 0]
         op = np.zeros(n, np.int32); variant = np.zeros(n, np.int32); level = np.zeros(n, np.int32)
         args = np.full((3, n), -1, np.int32)
-        out_type = [None] * n; out_K = [1] * n
+        out_type = [None] * n; out_K = [1] * n; out_rank2 = [False] * n
         self.param_tokens = [[] for _ in range(n_tok)]          # token positions of each call's params (pop order)
         stack = []
         for i in range(n_tok - 1, -1, -1):
@@ -128,7 +131,8 @@ class Layout:
                 lvl = 1 + max(p.level for p in ps)
                 level[nd] = lvl
                 out_type[nd], out_K[nd] = t, K
-                stack.append(_Val(t, nd, K, level=lvl))
+                out_rank2[nd] = self._att_rank2(tok, vals, t, K)
+                stack.append(_Val(t, nd, K, level=lvl, rank2=out_rank2[nd]))
             elif tok in words_to_keep:                           # module_net.py:121-124
                 stack.append(_Val(STR, text=(tok, i)))
             else:                                                # module_net.py:126-131: phrase embedding
@@ -142,10 +146,18 @@ class Layout:
             raise _type_error(tokens[0], 'the program result must be a [hidden] vector for the decoder, got %s' % root.type)
         self.root = root.node
         self.op, self.variant, self.level, self.args = op, variant, level, args
-        self.out_type, self.out_K = out_type, out_K
+        self.out_type, self.out_K, self.out_rank2 = out_type, out_K, out_rank2
         self.key = (level.astype(np.int64) * 32 + op) * 8 + variant          # ascending key = schedule order
         self.word_nodes = [nd for nd in range(n) if op[nd] == OP_WORD]
         self.is_module = op != OP_WORD
+
+    @staticmethod
+    def _att_rank2(tok, p, out_type, K):
+        """Is an attention-map result 2-D ([K, T]) in the reference?  Localize always; elementwise / Relate results keep the
+        rank of their (broadcast) operands."""
+        if out_type != ATT:
+            return False
+        return K > 1 or tok == 'Localize' or (tok in ('And', 'XorFrame', 'Relate') and any(x.type == ATT and x.rank2 for x in p))
 
     @staticmethod
     def _resolve(tok, p):
@@ -160,6 +172,8 @@ class Layout:
             return (0 if ty[0] == VEC else p[0].K), [p[0].node, p[1].node], ty[0], p[0].K
         if tok == 'AttnVideo':                                                   # (feat, attn) modules.py:330-340
             need(ty[0] == VID and ty[1] == ATT and p[1].K == 1, 'expects (frame features, [T] attention)')
+            # attn.unsqueeze(1) * feat (modules.py:340) does not broadcast for a 2-D [1, T] map (Localize output)
+            need(not p[1].rank2, 'the attention must be a 1-D [T] map (ExistsFrame / HasItem / Relate), not a [K, T] Localize map')
             return 0, [p[0].node, p[1].node], VID, 1
         if tok == 'Choose':
             need(ty == [VEC, VEC, VEC], 'expects three vectors')
@@ -191,13 +205,19 @@ class Layout:
             return K - 1, [p[0].node, p[1].node], ATT, K
         if tok == 'Relate':                                                      # (mode, attn) modules.py:423
             need(ty[0] == STR and ty[1] == ATT and p[1].K == 1, 'expects (direction word, [T] attention)')
-            return (0 if p[0].text[0] == 'forward' else 1), [p[1].node], ATT, 1
+            # on a 2-D [1, T] map the reference adds beta[:attn.size(0)] = beta[:1], a constant, and the implicit-dim softmax runs over
+            # T (modules.py:427-435): the result is softmax_T(attn) whatever the direction -> variants 2 / 3 (no beta)
+            return (0 if p[0].text[0] == 'forward' else 1) + (2 if p[1].rank2 else 0), [p[1].node], ATT, 1
         if tok == 'Superlative':                                                 # (mode, actions, feat) modules.py:233
             need(ty[0] == STR and ty[1] in (VEC, VEC2, VID) and ty[2] == VID, 'expects (max|min, actions, frame features)')
             kind = {VEC: 0, VEC2: 1, VID: 2}[ty[1]]
             return (1 if p[0].text[0] == 'min' else 0) + 2 * kind, [p[1].node, p[2].node], VEC, 1
         if tok == 'Temporal':                                                    # (mode, feat, attention) modules.py:310
             need(ty[0] == STR and ty[1] == VID and ty[2] == ATT, 'expects (mode word, frame features, attention map)')
+            # torch.mean(attention_scores, dim=0) (modules.py:318) turns a 1-D [T] map into a scalar: Linear(T, T) then fails; the
+            # 'while' / conv modes would gate every frame with that one scalar — not a temporal map any more, not supported here
+            need(p[2].rank2, 'the attention must be a 2-D [K, T] map (a Localize output); a 1-D [T] map is reduced to a scalar by '
+                             'the reference (mean over dim 0)')
             return TEMPORAL_MODES[p[0].text[0]] * 2 + (p[2].K - 1), [p[1].node, p[2].node], VID, 1
         if tok == 'Array2':
             need(ty == [VEC, VEC], 'expects two vectors')

@@ -28,7 +28,13 @@ PRECISIONS = {'bf16': L.BF16, 'fp32': L.F32}
 
 
 class ForwardState:
-    """Device buffers of one forward call (arenas, tables) — kept so audit outputs can be sliced lazily."""
+    """Device buffers of one forward call (arenas, tables).
+
+    ``logits``, ``answers`` and ``status`` are allocated per call and stay valid.  The arenas (``vid``, ``vec``, ``att``, ``tokfeat``,
+    ``qfeat``, ``head_*``, ``itab``) are views into the model's grow-only buffer cache: they are valid only until the NEXT
+    ``forward`` / ``forward_batch`` / training step on the same model (``generation`` records which call filled them; ``OutputViews``
+    refuses a stale state).  Everything ``VideoNMN.forward`` returns to the caller (``res_by_step``, ``result_of_each_step``) is copied out
+    of the arenas first, like the independent tensors the reference returns."""
     pass
 
 
@@ -48,6 +54,21 @@ class VideoNMN(nn.Module):
         self._ws = None                  # grow-only workspace / arena cache (torch caching allocator owns the memory)
         self._cache = {}
         self.last_launches = 0
+        self._bind_operators()
+
+    def _bind_operators(self):
+        """Give every operator object a weak back-reference to this model (packed weights / precision for ``submodules[name](*params)``)."""
+        from .modules import Operator
+        for m in self.submodules.values():
+            if isinstance(m, Operator):
+                m._bind(self)
+
+    def __setstate__(self, state):                      # pickled-Module loading (train_module.py:296-298)
+        super().__setstate__(state)
+        self._bind_operators()
+
+    def _precision_code(self):
+        return PRECISIONS[self.precision]
 
     # ---- helpers ---------------------------------------------------------------------------------------------------
     def _buf(self, name, numel, dtype, device):
@@ -85,6 +106,8 @@ class VideoNMN(nn.Module):
         B, T, H, A, O = batch.B, batch.T, cfg['hidden_size'], cfg['answer_vocab_length'], cfg.get('object_types', 0) or 0
         adt = self.act_dtype
         st = ForwardState()
+        self._generation = getattr(self, '_generation', 0) + 1         # the cached arenas now belong to this call
+        st.generation = self._generation
         st.batch, st.groups, st.sizes, st.T, st.H = batch, groups, sizes, T, H
         n, ng = batch.n_nodes, batch.n_groups
         gtab = torch.from_numpy(tab.reshape(-1)).to(dev, non_blocking=True)
@@ -143,7 +166,9 @@ class VideoNMN(nn.Module):
     def forward_pipelined(self, batches, head_modules=frozenset()):
         """Inference over a list of HOST sub-batches (``layout.collate_chunks(..., pin_memory=True)``) with the host->device
         copies on a separate stream: the upload of chunk k+1 overlaps the execution of chunk k, so a step costs about
-        max(PCIe time, compute time) instead of their sum.  Returns (answers [B] int32, logits [B, A], per-chunk states)."""
+        max(PCIe time, compute time) instead of their sum.  Returns (answers [B] int32, logits [B, A], per-chunk states).
+        The chunks share the model's arena cache: of the returned states only ``logits`` / ``answers`` / ``status`` are valid for every
+        chunk, the arenas (intermediates) only for the LAST one (see ``ForwardState``); use ``forward`` per chunk for audit outputs."""
         dev = next(self.parameters()).device
         if dev.type != 'cuda':
             raise L.StairError('VideoNMN parameters are on %s: stair_b200 runs only on CUDA (sm_100a) devices' % dev)
@@ -338,24 +363,30 @@ class VideoNMN(nn.Module):
 
 
 class OutputViews:
-    """Rebuilds the reference's per-question ``res_by_step`` / ``result_of_each_step`` from the arenas (tensor views)."""
+    """Rebuilds the reference's per-question ``res_by_step`` / ``result_of_each_step`` from the arenas.
+
+    The used part of every arena is copied ONCE into storage private to this object (a handful of device copies per forward), and the
+    per-question tensors are views of those copies: what leaves ``forward`` never aliases the model's grow-only buffer cache, so a
+    later forward on the same model cannot overwrite results a caller kept (evaluate.py:65-117 accumulates Filter outputs)."""
 
     def __init__(self, model: VideoNMN, st: ForwardState, heads):
+        if getattr(st, 'generation', None) != getattr(model, '_generation', None):
+            raise L.StairError('stale ForwardState: its arenas were overwritten by a later forward on the same model')
         self.model, self.st, self.heads = model, st, heads
         b = st.batch
         il = st.itab_layout
         itab = st.itab.cpu().numpy()
         n = b.n_nodes
-        self.out_slot = itab[il.out_slot:il.out_slot + n]
-        self.aux_slot = itab[il.aux_slot:il.aux_slot + n]
+        self.out_slot = itab[il.out_slot:il.out_slot + n].copy()
+        self.aux_slot = itab[il.aux_slot:il.aux_slot + n].copy()
         T, H = st.T, st.H
-        self.vid = st.vid[:st.sizes['vid'] * T * H].view(-1, T, H)
-        self.vec = st.vec[:st.sizes['vec'] * H].view(-1, H)
-        self.att = st.att[:st.sizes['att'] * T].view(-1, T)
+        self.vid = st.vid[:st.sizes['vid'] * T * H].clone().view(-1, T, H)
+        self.vec = st.vec[:st.sizes['vec'] * H].clone().view(-1, H)
+        self.att = st.att[:st.sizes['att'] * T].clone().view(-1, T)
         O = model.config.get('object_types', 0) or 0
-        self.head_small = st.head_small[:st.sizes['small'] * 2].view(-1, 2)
-        self.head_vec = st.head_vec[:st.sizes['hvec'] * H].view(-1, H)
-        self.head_ff = st.head_ff[:st.sizes['ff'] * T * O].view(-1, T, max(O, 1)) if O else None
+        self.head_small = st.head_small[:st.sizes['small'] * 2].clone().view(-1, 2)
+        self.head_vec = st.head_vec[:st.sizes['hvec'] * H].clone().view(-1, H)
+        self.head_ff = st.head_ff[:st.sizes['ff'] * T * O].clone().view(-1, T, max(O, 1)) if O else None
         self._last_temporal = None
 
     def node_output(self, q, nd):
@@ -371,9 +402,9 @@ class OutputViews:
             return self.vec[s:s + 2]
         K = lay.out_K[nd]
         name = LY.OP_NAME[int(lay.op[nd])]
-        if name == 'Localize':
-            return self.att[s:s + K]                      # [K, T]
-        return self.att[s] if K == 1 else self.att[s:s + K]
+        if K > 1 or lay.out_rank2[nd]:
+            return self.att[s:s + K]                      # [K, T] (Localize, and whatever keeps a Localize map's rank)
+        return self.att[s]                                # [T]
 
     def head_output(self, q, nd):
         """``submodules[prog].pretrain_head(execution_result)`` for node nd."""

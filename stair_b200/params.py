@@ -3,9 +3,9 @@
 The tree reproduces the reference ``state_dict`` exactly (119 keys such as
 ``submodules.Localize.video_linear.{0,3}.weight``, ``submodules.Temporal.relate.before.{0,2,4}.*``,
 ``submodules.video_encoder.weight_ih_l0_reverse``), so ``load_state_dict`` (evaluate.py:139) and pickled-module
-loading (train_module.py:296-298) work unchanged.  It is built from a compact spec instead of one class per module:
-the torch layers here are *parameter holders with the reference's default initialisation* — their ``forward`` is
-never used; all arithmetic runs in the CUDA library (csrc/).
+loading (train_module.py:296-298) work unchanged.  The operator classes live in ``stair_b200/modules.py`` (one class per
+module + ``NAME_TO_MODULE``, like video_nmn/modules.py); the torch layers are *parameter holders with the reference's default
+initialisation* — their ``forward`` is never used; all arithmetic runs in the CUDA library (csrc/).
 
 Reference for the layer shapes: video_nmn/modules.py:15-443 and video_nmn/module_net.py:39-53.
 """
@@ -29,98 +29,19 @@ class L2Normalize(nn.Module):
         return out
 
 
-def _seq(spec, p):
-    """spec: list of ('lin', in, out) | 'relu' | 'drop' | 'sigmoid' | 'softmax' -> nn.Sequential with reference indices."""
-    layers = []
-    for s in spec:
-        if isinstance(s, tuple):
-            layers.append(nn.Linear(s[1], s[2]))
-        elif s == 'relu':
-            layers.append(nn.ReLU())
-        elif s == 'drop':
-            layers.append(nn.Dropout(p))
-        elif s == 'sigmoid':
-            layers.append(nn.Sigmoid())
-        elif s == 'softmax':
-            layers.append(nn.Softmax(dim=None))
-    return nn.Sequential(*layers)
-
-
-class Operator(nn.Module):
-    """Parameter holder for one NMN module type.  Calling it directly is not supported: modules execute batched,
-    grouped by type, inside ``VideoNMN.forward`` (csrc/executor.cu)."""
-
-    def __init__(self, name):
-        super().__init__()
-        self.op_name = name
-
-    def forward(self, *params):
-        raise L.StairError('%s executes inside the batched CUDA interpreter; call VideoNMN.forward' % self.op_name)
-
-
-class TemporalOperator(Operator):
-    """Adds the reference's stateful head: ``pretrain_head()`` returns the related attention stashed by the last
-    forward that executed a Temporal module (video_nmn/modules.py:287-288, 321-325)."""
-
-    def __init__(self):
-        super().__init__('Temporal')
-        self.related_attn = None
-
-    def pretrain_head(self, *args):
-        return self.related_attn
-
-
 def build_submodules(config, contrastive_head):
-    """nn.ModuleDict in NAME_TO_MODULE order + encoders + decoder (module_net.py:27-53)."""
-    H, p, T = config['hidden_size'], config['dropout'], config['max_video_length']
-    head = config['have_pretrain_head']
-    mlp2 = lambda i: [('lin', i, H), 'relu', 'drop', ('lin', H, H), 'relu', 'drop']       # noqa: E731
+    """nn.ModuleDict in NAME_TO_MODULE order + encoders + decoder, constructed like module_net.py:27-53: ``Superlative`` receives the
+    same ``Localize`` object, ``Filter`` / ``Superlative`` / ``ToAction`` the shared ``contrastive_head``."""
+    from .modules import NAME_TO_MODULE, _seq
+    H, p = config['hidden_size'], config['dropout']
     sub = nn.ModuleDict()
-
-    def op(name, **children):
-        m = TemporalOperator() if name == 'Temporal' else Operator(name)
-        for k, v in children.items():
-            if v is not None:
-                setattr(m, k, v)
-        sub[name] = m
-        return m
-
-    op('And')
-    op('AttnVideo')
-    op('Choose')
-    op('Compare', param=_seq([('lin', 2 * H, H), 'relu'], p))
-    op('Equals', param=_seq([('lin', 2 * H, H), 'relu'], p), pretrain_head=nn.Linear(H, 1) if head else None)
-    op('Exists', param=_seq(mlp2(3 * H), p), pretrain_head=nn.Linear(H, 2) if head else None)
-    op('ExistsFrame', pretrain_head=nn.Identity() if head else None)
-    op('Filter', param=nn.ModuleDict({kw: _seq(mlp2(H), p) for kw in ['representation', 'actions', 'objects', 'relations']}),
-       attention=_seq([('lin', 2 * H, 1), 'softmax'], p), dense=_seq([('lin', H, H), 'relu'], p),
-       pretrain_head=contrastive_head if head else None)
-    op('FilterFrame', param=nn.ModuleDict({kw: _seq(mlp2(H), p) for kw in ['representation', 'relations', 'actions']}),
-       attention=_seq([('lin', 2 * H, 1), 'sigmoid'], p), dense=_seq([('lin', H, H), 'relu', 'drop'], p),
-       pretrain_head=nn.Linear(H, config['object_types']) if head else None)
-    op('HasItem', param=_seq([('lin', H, H), 'relu', 'drop', ('lin', H, 1), 'sigmoid', 'drop'], p),
-       pretrain_head=nn.Identity() if head else None)
-    loc = op('Localize', video_linear=_seq([('lin', H, H), 'relu', 'drop', ('lin', H, H)], p),
-             keyword_linear=_seq([('lin', H, H)], p), pretrain_head=nn.Identity() if head else None)
-    rel = op('Relate')
-    rel.beta = nn.Parameter(torch.rand(T))
-    op('Superlative', localize_module=loc, dense=_seq([('lin', H, H), 'relu'], p),
-       pretrain_head=contrastive_head if head else None)
-    if T > 32:                                                   # modules.py:255-266
-        k = round(T / 4)
-        relate = {m: nn.Sequential(nn.Conv1d(1, 1, k, padding='same'), nn.ReLU(), nn.Conv1d(1, 1, k, padding='same'), nn.ReLU(),
-                                   nn.Conv1d(1, 1, 2 * k + 1, padding='same'), nn.Sigmoid()) for m in ['before', 'after', 'between']}
-    else:                                                        # modules.py:267-277
-        relate = {m: _seq([('lin', T, T), 'relu', ('lin', T, T), 'relu', ('lin', T, T), 'sigmoid'], p)
-                  for m in ['before', 'after', 'between']}
-    relate = nn.ModuleDict(relate)
-    relate['while'] = nn.Identity()
-    op('Temporal', relate=relate, dense=_seq([('lin', H, H), 'relu', 'drop'], p), layer_norm=nn.LayerNorm(H))
-    op('ToAction', param=_seq([('lin', 2 * H, H), 'relu', 'drop', ('lin', H, H), 'relu'], p),
-       pretrain_head=contrastive_head if head else None)
-    op('Xor', param=_seq([('lin', 3 * H, H), 'relu'], p), pretrain_head=nn.Linear(H, 2) if head else None)
-    op('XorFrame')
-    sub['Array2'] = Operator('Array2')
+    for name, cls in NAME_TO_MODULE.items():
+        init_params = [config]
+        if name in ['Superlative']:
+            init_params.append(sub['Localize'])
+        if name in ['Filter', 'Superlative', 'ToAction']:
+            init_params.append(contrastive_head)
+        sub[name] = cls(*init_params)
     sub['video_encoder'] = nn.LSTM(input_size=config['video_size'], hidden_size=H // 2, batch_first=True, bidirectional=True)
     sub['text_encoder'] = nn.LSTM(input_size=config['text_size'], hidden_size=H // 2, batch_first=True, bidirectional=True)
     sub['decoder'] = _seq([('lin', 2 * H, 2 * H), 'relu', 'drop', ('lin', 2 * H, config['answer_vocab_length'])], p)

@@ -64,7 +64,8 @@ TEMPLATES = {
 
 # Extra hand-written layouts (valid for the reference interpreter, module_net.py:94-133) that reach the
 # operators / dynamic-typing cases the ten AGQA templates above do not: XorFrame, And on attention maps,
-# Superlative over an Array2 of keywords (min mode), FilterFrame with string keywords, Filter 'relations'.
+# Superlative over an Array2 of keywords (min mode), FilterFrame with string keywords, Filter 'relations', supervised (non-root)
+# Equals / Xor.
 EXTRA_TEMPLATES = {
     'xorframe': (
         None,
@@ -85,6 +86,25 @@ EXTRA_TEMPLATES = {
         ['Equals', 'ToAction', 'holding', 'Filter', 'video', 'cup', 'Superlative', 'max', 'Array2', 'running', 'sitting_down',
          'Temporal', 'after', 'video', 'Localize', 'video', 'opening_a_door'],
         [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, None, None, 12, None, 13]),
+    # non-root Equals / Xor: the only way criterion_equals (MSE on the Linear(H,1) head) and criterion_exists on the Xor head
+    # (train_module.py:92-107) ever run — the root is trained by the decoder only (module_net.py:107-113), and in the ten AGQA
+    # templates Equals / Xor are always the root
+    'and_equals_xor': (
+        None,
+        ['And', 'Equals', 'Filter', 'video', 'holding', 'Filter', 'video', 'touching',
+         'Xor', 'Exists', 'dish', 'Filter', 'video', 'objects', 'Exists', 'food', 'Filter', 'video', 'objects'],
+        list(range(19))),
+    # Relate on a 2-D [1, T] Localize map: the reference adds beta[:1] (a constant) and softmaxes over T (modules.py:427-435); the
+    # result keeps the [1, T] shape, which Temporal accepts
+    'relate_localize': (
+        None,
+        ['Filter', 'Temporal', 'while', 'video', 'Relate', 'forward', 'Localize', 'video', 'opening_a_door', 'objects'],
+        [0, 1, None, None, 2, None, 3, None, 4, 5]),
+    'compare_xor_equals': (
+        None,
+        ['Compare', 'Xor', 'Filter', 'video', 'actions', 'Filter', 'video', 'cup',
+         'Equals', 'ToAction', 'holding', 'Filter', 'video', 'relations', 'Filter', 'video', 'dish'],
+        list(range(17))),
 }
 
 ALL_TEMPLATES = {**TEMPLATES, **EXTRA_TEMPLATES}

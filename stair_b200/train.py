@@ -141,21 +141,71 @@ def collate_losses(batch: LY.NMNBatch, pretrain_modules, T, module_loss_weight=1
     return rows
 
 
-def touched_slots(batch: LY.NMNBatch, rows: LossRows, have_heads: bool):
-    """Weight-table slots that receive a gradient in this window (host logic; the reference leaves ``grad = None`` on
-    parameters of modules no question used, and Adam skips them)."""
+def _subtree_info(lay):
+    """Per node of a compiled layout: ({(op, variant)} of the module calls in its subtree, reads the text encoder?, reads the video encoder?).
+    Cached on the layout.  Children follow their parent in token order, so a reverse sweep sees them first."""
+    info = getattr(lay, '_subtree_info', None)
+    if info is None:
+        kinds, text, video = [None] * lay.n, [False] * lay.n, [False] * lay.n
+        for nd in range(lay.n - 1, -1, -1):
+            if lay.op[nd] == LY.OP_WORD:
+                kinds[nd], text[nd] = frozenset(), True
+                continue
+            k = {(int(lay.op[nd]), int(lay.variant[nd]))}
+            for a in lay.args[:, nd]:
+                if a == -2:
+                    video[nd] = True
+                elif a >= 0:
+                    k |= kinds[a]
+                    text[nd] |= text[a]
+                    video[nd] |= video[a]
+            kinds[nd] = frozenset(k)
+        info = lay._subtree_info = (kinds, text, video)
+    return info
+
+
+def touched_slots(batch: LY.NMNBatch, rows: LossRows, have_heads: bool, decoder_active: bool = True):
+    """Weight-table slots that receive a gradient in this window (host logic).  The reference leaves ``grad = None`` on every parameter
+    no loss of the window reaches, and Adam skips those (no step count, no momentum drift — SURVEY hard part 4): a parameter is touched
+    iff it belongs to a module call inside the subtree of a supervised node, or — when the decoder loss is active
+    (``decoder_loss_weight != 0``, train_module.py:376) — to any module of any question, the decoder, and the encoders feeding them."""
     Wt = L.W
     s = set()
 
     def lin(prefix):
         s.update((Wt[prefix + '_W'], Wt[prefix + '_B']))
 
-    for enc in ('VENC', 'TENC'):
-        s.update(Wt[enc + x] for x in ('_WIH', '_B', '_WHH_F', '_WHH_R'))
-    lin('DEC0'); lin('DEC1')
-    for key in batch.group_keys:
-        key = int(key)
-        variant, op = key % 8, (key // 8) % 32
+    live, text, video = set(), False, False
+    if decoder_active:
+        lin('DEC0'); lin('DEC1')
+        text = True                                                    # question_feature feeds the decoder (module_net.py:136)
+        seen = set()
+        for lay in batch.layouts:
+            if id(lay) in seen:
+                continue
+            seen.add(id(lay))
+            kinds, tx, vd = _subtree_info(lay)
+            live |= kinds[lay.root]
+            video |= vd[lay.root]
+    else:
+        nodes = np.unique(np.asarray(list(rows.att_node) + list(rows.bin_node) + list(rows.con_node) + list(rows.ff_node), np.int64))
+        qs = np.searchsorted(batch.node_start, nodes, side='right') - 1
+        seen = set()
+        for node, q in zip(nodes.tolist(), qs.tolist()):
+            lay = batch.layouts[q]
+            nd = node - int(batch.node_start[q])
+            if (id(lay), nd) in seen:
+                continue
+            seen.add((id(lay), nd))
+            kinds, tx, vd = _subtree_info(lay)
+            live |= kinds[nd]
+            text |= tx[nd]
+            video |= vd[nd]
+    if video:
+        s.update(Wt['VENC' + x] for x in ('_WIH', '_B', '_WHH_F', '_WHH_R'))
+    if text:
+        s.update(Wt['TENC' + x] for x in ('_WIH', '_B', '_WHH_F', '_WHH_R'))
+    for op, variant in sorted(live):
         name = LY.OP_NAME[op]
         if name in ('Localize', 'Superlative'):
             lin('LOC_V0'); lin('LOC_V1'); lin('LOC_K')
@@ -285,10 +335,23 @@ class NMNTrainStep:
         rows.counts['decoder'] = batch.B if self.decoder_loss_weight != 0 else 0          # decoder CE applies to every question (:376-380)
         if rows.bin_node and not cfg['have_pretrain_head']:
             raise L.StairError('Exists/Xor/Equals supervision needs have_pretrain_head (their criterion reads the head logits)')
+        if rows.con_node and not cfg['have_pretrain_head']:
+            # without the head the reference scores the raw execution_result (module_net.py:110-113); the contrastive kernel always
+            # L2-normalises (the contrastive_head), so that configuration is refused rather than silently computed differently
+            raise L.StairError('Filter/ToAction/Superlative supervision needs have_pretrain_head (the contrastive loss is defined on the '
+                               'L2-normalised head output)')
+        # labels index device tables without a range check: validate them here like nn.CrossEntropyLoss does in the reference
+        A = int(cfg['answer_vocab_length'])
+        ans = batch.answer.reshape(-1)
+        if self.decoder_loss_weight != 0 and (int(ans.min()) < 0 or int(ans.max()) >= A):
+            bad = int(((ans < 0) | (ans >= A)).nonzero()[0])
+            raise IndexError('Target %d is out of bounds (question %d; answer_vocab_length = %d)' % (int(ans[bad]), bad, A))
+        if any(l not in (0, 1) for l in rows.bin_label):
+            raise ValueError('Exists / Xor / Equals gold must be a bool (train_module.py:92-107), got labels %s' % sorted(set(rows.bin_label)))
         # window-level class names (train_module.py:360-366,388-406): under data parallelism the negatives of the whole
         # window are every rank's classes, so names + word embeddings are exchanged on the host (small)
         class_emb = rows.class_emb
-        touched = touched_slots(batch, rows, cfg['have_pretrain_head'])
+        touched = touched_slots(batch, rows, cfg['have_pretrain_head'], decoder_active=self.decoder_loss_weight != 0)
         if world > 1:
             # one host-side exchange per window: class phrases (contrastive negatives) and the touched-parameter sets (Adam skips
             # parameters no rank's questions used, like the reference) — known from the layouts, so run() needs no device sync

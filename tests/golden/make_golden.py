@@ -216,7 +216,31 @@ def layout_fixture():
     print('layouts', len(out['templates']))
 
 
+def relate_scan_fixture():
+    """TemporalModule.relate_ (video_nmn/modules.py:290-308) of the unmodified reference on seeded random maps: the cumsum
+    before / after / between masks the north star names (dead code in the reference forward, callable on the module object).
+    Inputs contain negative values so the ReLU in front of the scans is exercised; 'while' returns its input untouched."""
+    store = {}
+    rng = np.random.default_rng(2468)
+    for T in (8, 64):
+        cfg = syn.model_config(T=T, V=32, hidden=16)
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            temporal = VideoNMN(cfg).submodules['Temporal']
+        for mode in ('while', 'before', 'after', 'between'):
+            K = 2 if mode == 'between' else 1
+            att = torch.from_numpy(rng.uniform(-0.4, 0.98, size=(24, K, T)).astype(np.float32))
+            with torch.no_grad():
+                out = torch.stack([temporal.relate_(a, mode) for a in att])
+            assert out.shape == (24, T), (mode, out.shape)
+            store['T%d/%s/att' % (T, mode)] = att.numpy()
+            store['T%d/%s/out' % (T, mode)] = out.numpy()
+    np.savez_compressed(os.path.join(HERE, 'relate_scan.npz'), **store)
+    print('relate_scan', len(store) // 2, 'cases')
+
+
 if __name__ == '__main__':
     layout_fixture()
+    relate_scan_fixture()
     for n, c in CONFIGS.items():
         run_config(n, c)

@@ -30,7 +30,7 @@ def test_filter_audit_matches_reference_procedure(heads):
     weights = {k: v.detach().clone() for k, v in model.state_dict().items()}
     model = model.cuda().eval()
     oracle = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES)
-    qs = syn.make_questions(28, T, V, seed=4, templates=list(syn.ALL_TEMPLATES))
+    qs = syn.make_questions(32, T, V, seed=4, templates=list(syn.ALL_TEMPLATES))
     vocab = ['phrase %d word%d' % (i, i % 7) if i % 3 else 'single%d' % i for i in range(214)]      # 214 phrases like filter_answers.json
     embed = _embed(cfg['text_size'])
     with torch.no_grad():

@@ -99,3 +99,30 @@ def test_batch_beyond_the_chunk_caps_equals_its_halves():
     logits = whole['logits'].clone()
     halves = [model(qs[a:b], return_res_by_step=False, test_mode=True)['logits'].clone() for a, b in ((0, 4500), (4500, B))]
     assert torch.equal(torch.cat(halves), logits)
+
+
+def test_returned_intermediates_survive_later_forwards():
+    """res_by_step / result_of_each_step tensors must be independent of the model's arena cache (the reference returns fresh
+    tensors; evaluate.py:65-117 keeps Filter outputs across calls).  A second, different forward must not change what the first returned,
+    and a stale ForwardState is refused instead of silently read."""
+    from stair_b200 import _lib as L
+    from stair_b200.nmn import OutputViews
+    T, V, hid = 8, 128, 64
+    cfg = syn.model_config(T=T, V=V, hidden=hid, object_types=16)
+    torch.manual_seed(4)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32').cuda().eval()
+    qa = syn.make_questions(34, T, V, seed=1, templates=list(syn.ALL_TEMPLATES), object_types=16)
+    qb = syn.make_questions(34, T, V, seed=2, templates=list(syn.ALL_TEMPLATES), object_types=16)
+    first = model(qa, return_res_by_step=True, return_result_of_each_step=True, test_mode=True)
+    keep = [[(r.clone() if isinstance(r, torch.Tensor) else r) for _, r in steps] for steps in first['result_of_each_step']]
+    keep_res = [{k: v[1].clone() for k, v in d.items()} for d in first['res_by_step']]
+    model(qb, return_res_by_step=True, return_result_of_each_step=True, test_mode=True)           # overwrites the arenas
+    torch.cuda.synchronize()
+    for steps, kept in zip(first['result_of_each_step'], keep):
+        for (_, r), k in zip(steps, kept):
+            assert (r == k) if isinstance(r, str) else torch.equal(r, k)
+    for d, kept in zip(first['res_by_step'], keep_res):
+        for k, v in d.items():
+            assert torch.equal(v[1], kept[k])
+    with pytest.raises(L.StairError):
+        OutputViews(model, first['state'], frozenset())

@@ -61,6 +61,24 @@ def test_interpreter_errors_mirror_reference():
         LY.Layout(['Filter', 'FilterFrame', 'video', 'objects', 'objects'])
 
 
+def test_attention_rank_follows_the_reference():
+    """Localize returns a 2-D [K, T] map, ExistsFrame / HasItem / Relate(1-D) a 1-D [T] one; the reference's AttnVideo / Relate / Temporal
+    behave differently on the two (modules.py:318,340,427-435) — the layout compiler tracks the rank."""
+    # Relate on a Localize map -> variant 2 (softmax without beta), result keeps the [1, T] shape and feeds Temporal
+    lay = LY.Layout(['Filter', 'Temporal', 'while', 'video', 'Relate', 'forward', 'Localize', 'video', 'x', 'objects'])
+    rel = lay.node_of_token[4]
+    assert lay.variant[rel] == 2 and lay.out_rank2[rel] and lay.out_rank2[lay.node_of_token[6]]
+    lay = LY.Layout(['Filter', 'AttnVideo', 'video', 'Relate', 'backward', 'ExistsFrame', 'x', 'video', 'objects'])
+    rel = lay.node_of_token[3]
+    assert lay.variant[rel] == 1 and not lay.out_rank2[rel]
+    with pytest.raises(TypeError):      # attn.unsqueeze(1) * feat does not broadcast for a [1, T] map
+        LY.Layout(['Filter', 'AttnVideo', 'video', 'Localize', 'video', 'x', 'objects'])
+    with pytest.raises(TypeError):      # mean over dim 0 of a 1-D map is a scalar
+        LY.Layout(['Filter', 'Temporal', 'before', 'video', 'ExistsFrame', 'x', 'video', 'objects'])
+    with pytest.raises(TypeError):      # [2, T] + beta[:2] does not broadcast
+        LY.Layout(['Filter', 'Temporal', 'while', 'video', 'Relate', 'forward', 'Localize', 'video', 'Array2', 'a', 'b', 'objects'])
+
+
 def test_collate_tables_and_grouping():
     qs = syn.make_questions(64, 8, 32, seed=3, templates=list(syn.ALL_TEMPLATES))
     b = LY.collate(qs)

@@ -45,7 +45,7 @@ def test_evaluate_matches_reference_accuracy_rule():
 def test_train_reduces_loss_and_checkpoint_round_trip(tmp_path):
     cfg, model = _model(1)
     model = model.cuda()
-    qs = syn.make_questions(28, 8, 128, seed=5, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    qs = syn.make_questions(32, 8, 128, seed=5, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
     windows = [qs] * 12
     state = loops.train(windows, model, lr=2e-3, scheduler_kwargs=dict(total_iters=100), report_interval=4)
     totals = [sum(l.values()) for l in state['losses']]

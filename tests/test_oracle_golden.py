@@ -93,6 +93,32 @@ def test_window_loss_and_gradients(fx):
             assert w[k].grad is None or float(w[k].grad.abs().max()) == 0.0, k
 
 
+def test_relate_scan_pinned_to_the_reference():
+    """oracle.relate_scan == the reference's own TemporalModule.relate_ (modules.py:290-308) on the committed fixture
+    (tests/golden/relate_scan.npz, written by make_golden.py from the unmodified reference object): all four modes, T = 8 and 64."""
+    import numpy as np
+    fx = np.load(os.path.join(gu.GOLDEN_DIR, 'relate_scan.npz'))
+    n = 0
+    for T in (8, 64):
+        for mode in ('while', 'before', 'after', 'between'):
+            att = torch.from_numpy(fx['T%d/%s/att' % (T, mode)])
+            want = torch.from_numpy(fx['T%d/%s/out' % (T, mode)])
+            got = torch.stack([orc.OracleNMN.relate_scan(a, mode) for a in att])
+            assert torch.equal(got, want), (T, mode)          # same ATen ops in the same order: bit-identical
+            n += len(att)
+    assert n == 8 * 24
+
+
+def test_golden_window_supervises_equals_and_xor(fx):
+    """criterion_equals / criterion_exists-on-Xor (train_module.py:92-107) only run for NON-root Equals / Xor nodes; the fixtures
+    must contain such rows so that the loss and gradient tests above (and the GPU ones) cover them."""
+    logs = fx[3]['window']['logs']
+    assert len(logs['Equals']) >= 2 and len(logs['Xor']) >= 2 and len(logs['Exists']) >= 5
+    assert 'submodules.Equals.pretrain_head.weight' in fx[4] and 'submodules.Xor.pretrain_head.weight' in fx[4]
+    assert float(fx[4]['submodules.Equals.pretrain_head.weight'].abs().max()) > 0
+    assert float(fx[4]['submodules.Xor.pretrain_head.weight'].abs().max()) > 0
+
+
 def test_relate_scan_matches_reference_formula():
     # modules.py:290-308 is dead code in the reference forward; restated and checked on a hand example.
     a = torch.tensor([0.1, -0.2, 0.5, 0.0, 0.3])

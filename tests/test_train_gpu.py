@@ -110,13 +110,13 @@ def test_span_to_attention_known_answers(fx):
 
 @pytest.mark.parametrize('shape', ['rx', 'i3d'])
 def test_full_size_window_against_oracle_autograd(shape):
-    """One 28-question window (all 14 layouts twice) at the real dimensions (H=512): CUDA backward vs the oracle's autograd."""
+    """One 32-question window (all 16 layouts twice) at the real dimensions (H=512): CUDA backward vs the oracle's autograd."""
     T, V = (8, 4096) if shape == 'rx' else (64, 1024)
     cfg = syn.model_config(T=T, V=V)
     torch.manual_seed(0)
     ref_model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
     weights = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
-    qs = syn.make_questions(28, T, V, seed=321, templates=list(syn.ALL_TEMPLATES), with_gold=True)
+    qs = syn.make_questions(32, T, V, seed=321, templates=list(syn.ALL_TEMPLATES), with_gold=True)
     w = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
     for k in list(w):
         if k.startswith('submodules.Superlative.localize_module.'):
@@ -161,7 +161,7 @@ def test_adam_matches_torch():
     a = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32').cuda().train()
     b = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32').cuda().train()
     b.load_state_dict(a.state_dict())
-    qs = syn.make_questions(14, 8, 128, seed=9, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    qs = syn.make_questions(16, 8, 128, seed=9, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
     qs2 = syn.make_questions(4, 8, 128, seed=10, templates=['equals', 'toaction'], with_gold=True, object_types=16)
     before = a.submodules['decoder'][0].weight.detach().clone()
     oa, ob = Adam(a.parameters(), lr=2e-4), torch.optim.Adam(b.parameters(), lr=2e-4)
@@ -217,7 +217,7 @@ def _mask_hook(batch, T, seed, p):
 @pytest.mark.parametrize('shape', ['rx', 'i3d'])
 def test_dropout_window_matches_oracle_with_the_same_masks(shape):
     """Training mode with the reference's default dropout 0.25: loss and every gradient equal the oracle's autograd when the oracle
-    applies the same masks at every nn.Dropout site (all 14 layouts; Linear->ReLU->Dropout, HasItem's Sigmoid->Dropout, decoder)."""
+    applies the same masks at every nn.Dropout site (all 16 layouts; Linear->ReLU->Dropout, HasItem's Sigmoid->Dropout, decoder)."""
     from stair_b200 import collate
     T, V, hid = (8, 256, 128) if shape == 'rx' else (64, 128, 64)
     p, seed = 0.25, 0x1234567890ABCDEF
@@ -225,7 +225,7 @@ def test_dropout_window_matches_oracle_with_the_same_masks(shape):
     torch.manual_seed(1)
     ref_model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
     weights = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
-    qs = syn.make_questions(28, T, V, seed=77, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    qs = syn.make_questions(32, T, V, seed=77, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
     batch = collate(qs)
     w = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
     for k in list(w):
@@ -283,7 +283,7 @@ def test_fused_adam_matches_torch_and_refreshes_the_packed_weights(precision):
     a = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision=precision).cuda().train()
     b = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision=precision).cuda().train()
     b.load_state_dict(a.state_dict())
-    qs = syn.make_questions(14, 8, 128, seed=9, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    qs = syn.make_questions(16, 8, 128, seed=9, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
     qs2 = syn.make_questions(4, 8, 128, seed=10, templates=['equals', 'toaction'], with_gold=True, object_types=16)
     oa, ob = FusedAdam(a, lr=2e-3), torch.optim.Adam(b.parameters(), lr=2e-3)
     sched = torch.optim.lr_scheduler.LambdaLR(oa, lambda it: 1.0 - 0.1 * it)         # param_groups['lr'] is honoured
@@ -385,7 +385,7 @@ def test_filterframe_criterion_when_not_excluded(shape):
     torch.manual_seed(4)
     ref_model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
     weights = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
-    qs = syn.make_questions(28, T, V, seed=55, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    qs = syn.make_questions(32, T, V, seed=55, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
     assert any('FilterFrame' in d['nmn_program_list'] for d in qs)
     word2id = {'obj_%d' % i: i for i in range(cfg['object_types'])}
     w = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
@@ -537,3 +537,61 @@ def test_two_phase_backward_equals_single_call():
     assert g0.keys() == g1.keys() and any('encoder' in k for k in g0)
     for k in g0:
         assert float((g0[k] - g1[k]).norm()) <= 1e-5 * float(g0[k].norm()) + 1e-9, k           # atomic summation order only
+
+
+@pytest.mark.parametrize('phase', ['modules_only', 'decoder_only'])
+def test_staged_phases_leave_unreached_parameters_without_gradient(phase):
+    """ADVICE r1: with decoder_loss_weight == 0 (or module_loss_weight == 0) the reference's autograd reaches only part of the model;
+    every other parameter keeps grad None and Adam skips it (train_module.py:349,376 staged schedules).  The set of parameters with a
+    gradient and the gradients themselves must equal the oracle's."""
+    T, V, hid = 8, 128, 64
+    cfg = syn.model_config(T=T, V=V, hidden=hid, object_types=16)
+    torch.manual_seed(11)
+    ref_model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
+    weights = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
+    # 'equals' / 'iterate_until': their roots (and HasItem / AttnVideo / Relate below the root) are only reached through the decoder
+    qs = syn.make_questions(12, T, V, seed=41, templates=['equals', 'iterate_until', 'toaction'], with_gold=True, object_types=16)
+    mlw, dlw = (1.0, 0.0) if phase == 'modules_only' else (0.0, 1.0)
+    w = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
+    for k in list(w):
+        if k.startswith('submodules.Superlative.localize_module.'):
+            w[k] = w[k.replace('Superlative.localize_module', 'Localize')]
+    oracle = orc.OracleNMN(cfg, w, syn.PRETRAIN_MODULES)
+    crit = orc.OracleCriterion({'obj_%d' % i: i for i in range(cfg['object_types'])})
+    total, _, _ = orc.window_loss(oracle, crit, qs, module_loss_weight=mlw, decoder_loss_weight=dlw)
+    total.backward()
+    ref_grads = {k: v.grad.detach() for k, v in w.items() if v.grad is not None and not k.startswith('submodules.Superlative.localize_module.')}
+    no_grad = [k for k, v in w.items() if v.grad is None]
+    model = _model(cfg, weights, syn.PRETRAIN_MODULES, 'fp32')
+    out = NMNTrainStep(model, module_loss_weight=mlw, decoder_loss_weight=dlw)(qs)
+    torch.cuda.synchronize()
+    assert abs(float(out['loss']) - float(total)) <= LOSS_TOL['fp32'] * abs(float(total))
+    bad = _compare_grads(model, ref_grads, no_grad, 'fp32', 'staged ' + phase)
+    assert not bad, '\n'.join(bad)
+    named = dict(model.named_parameters())
+    # parameters the oracle's autograd did not reach (exactly-zero gradients count as unreached: dead Filter.attention) stay None here
+    for k in no_grad:
+        if k in named and not k.startswith('submodules.Superlative.localize_module.'):
+            assert named[k].grad is None, k
+    if phase == 'modules_only':
+        assert named['submodules.decoder.0.weight'].grad is None and named['submodules.Equals.param.0.weight'].grad is None
+        assert named['submodules.HasItem.param.0.weight'].grad is None
+        assert named['submodules.Filter.dense.0.weight'].grad is not None
+    else:
+        assert named['submodules.decoder.0.weight'].grad is not None and named['submodules.Equals.param.0.weight'].grad is not None
+
+
+def test_out_of_range_labels_raise_like_the_reference():
+    """an answer id outside [0, A) must raise on the host (nn.CrossEntropyLoss raises IndexError in the reference) instead of
+    becoming an out-of-bounds device read."""
+    cfg = syn.model_config(T=8, V=128, hidden=64, object_types=16)
+    torch.manual_seed(3)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32').cuda().train()
+    qs = syn.make_questions(6, 8, 128, seed=7, templates=['equals', 'toaction'], with_gold=True, object_types=16)
+    step = NMNTrainStep(model)
+    qs[2]['answer'] = torch.tensor(cfg['answer_vocab_length'])
+    with pytest.raises(IndexError):
+        step(qs)
+    qs[2]['answer'] = torch.tensor(-1)
+    with pytest.raises(IndexError):
+        step(qs)
