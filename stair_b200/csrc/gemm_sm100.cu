@@ -16,6 +16,7 @@
 // the six significant plane products are accumulated into the same TMEM tile by looping the K range six
 // times with different plane row-offsets.  It is the strict-parity mode.
 #include "tc_ptx.cuh"
+#include <cstdlib>
 
 namespace stair {
 
@@ -178,6 +179,53 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int
     }
 }
 
+
+// TMA-store epilogue of one accumulator tile for one epilogue warp: TMEM -> registers (next chunk's tcgen05.ld in flight while this
+// one is processed) -> row_scale / bias / ReLU / dropout -> swizzled smem -> TMA store.  t_base = TMEM address of the warp's lane
+// quarter and the accumulator stage, row = this thread's global row, row0 = the warp's first global row, [c_begin, c_end) = the
+// 32-column chunks this warp owns, stage0 = shared address of the warp's two 4 KiB staging buffers, sbuf = which one is next.
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap& tmC, uint32_t t_base, int row, int row0, int n0,
+                                                  int c_begin, int c_end, uint32_t stage0, int& sbuf, int lane) {
+    const float rs = (p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.0f;
+    const int per_buf = p.out_dtype == STAIR_BF16 ? 2 : 1;          // TMEM chunks per 128-byte staging row
+    uint32_t ra[32], rb[32];
+    float v[32];
+    tmem_ld32(t_base + static_cast<uint32_t>(c_begin * 32), ra);
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 2) {
+        if (n0 + c * 32 >= p.N) break;                               // warp-uniform
+        tmem_ld_wait();
+        tmem_ld32(t_base + static_cast<uint32_t>((c + 1) * 32), rb);
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+            const int cc = c + hsel;
+            if (hsel == 1) {
+                tmem_ld_wait();
+                if (cc + 1 < c_end) tmem_ld32(t_base + static_cast<uint32_t>((cc + 1) * 32), ra);
+            }
+            const int n = n0 + cc * 32;
+            const int half = per_buf == 2 ? hsel : 0;
+            if (half == 0) {                                         // about to refill a staging buffer: it must be drained
+                if (lane == 0) bulk_wait_read1();
+                __syncwarp();
+            }
+            const uint32_t buf = stage0 + static_cast<uint32_t>(sbuf) * 4096u;
+            if (n < p.N) {
+                epilogue_math(p, row, n, rs, hsel == 0 ? ra : rb, v);
+                stage_chunk(buf, lane, half, p.out_dtype, v);
+            }
+            if (half == per_buf - 1) {
+                fence_async_smem();
+                __syncwarp();
+                const int nbox = n - (per_buf == 2 ? 32 : 0);
+                if (lane == 0 && nbox < p.N) { tma_store_2d(&tmC, buf, nbox, row0); bulk_commit(); }
+                sbuf ^= 1;
+            }
+        }
+    }
+    tmem_ld_wait();
+}
+
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS + 128 * (EPI - 1), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -326,46 +374,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row = m0 + quarter * 32 + lane;
             const uint32_t t_base = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
             if (p.tma_store) {
-                // TMEM -> registers (next chunk's tcgen05.ld in flight while this one is processed) -> swizzled smem -> TMA store
-                const float rs = (p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.0f;
-                const uint32_t stage0 = smem_u32(sStage) + static_cast<uint32_t>(eset * 4 + quarter) * 8192u;
-                const int per_buf = p.out_dtype == STAIR_BF16 ? 2 : 1;          // TMEM chunks per 128-byte staging row
-                uint32_t ra[32], rb[32];
-                float v[32];
-                tmem_ld32(t_base + static_cast<uint32_t>(c_begin * 32), ra);
-#pragma unroll 1
-                for (int c = c_begin; c < c_end; c += 2) {
-                    if (n0 + c * 32 >= p.N) break;                               // warp-uniform
-                    tmem_ld_wait();
-                    tmem_ld32(t_base + static_cast<uint32_t>((c + 1) * 32), rb);
-#pragma unroll
-                    for (int hsel = 0; hsel < 2; ++hsel) {
-                        const int cc = c + hsel;
-                        if (hsel == 1) {
-                            tmem_ld_wait();
-                            if (cc + 1 < c_end) tmem_ld32(t_base + static_cast<uint32_t>((cc + 1) * 32), ra);
-                        }
-                        const int n = n0 + cc * 32;
-                        const int half = per_buf == 2 ? hsel : 0;
-                        if (half == 0) {                                         // about to refill a staging buffer: it must be drained
-                            if (lane == 0) bulk_wait_read1();
-                            __syncwarp();
-                        }
-                        const uint32_t buf = stage0 + static_cast<uint32_t>(sbuf) * 4096u;
-                        if (n < p.N) {
-                            epilogue_math(p, row, n, rs, hsel == 0 ? ra : rb, v);
-                            stage_chunk(buf, lane, half, p.out_dtype, v);
-                        }
-                        if (half == per_buf - 1) {
-                            fence_async_smem();
-                            __syncwarp();
-                            const int nbox = n - (per_buf == 2 ? 32 : 0);
-                            if (lane == 0 && nbox < p.N) { tma_store_2d(&tmC, buf, nbox, m0 + quarter * 32); bulk_commit(); }
-                            sbuf ^= 1;
-                        }
-                    }
-                }
-                tmem_ld_wait();
+                epilogue_tile_tma(p, tmC, t_base, row, m0 + quarter * 32, n0, c_begin, c_end,
+                                  smem_u32(sStage) + static_cast<uint32_t>(eset * 4 + quarter) * 8192u, sbuf, lane);
             } else {
 #pragma unroll 1
             for (int c0 = c_begin * 32; c0 < c_end * 32; c0 += 32) {
@@ -391,6 +401,163 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 2) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one cluster of two CTAs (the two SMs of a TPC) per 256 x 256 output tile.
+//
+// Why: every GEMM on this path is bound by L2 -> SM operand traffic: a 128 x 256 x 64 k-block of the single-CTA kernel
+// stages 16 KB of A + 32 KB of B per SM.  Here CTA r of the pair stages rows [m0 + 128 r, +128) of A (16 KB) and only rows
+// [n0 + 128 r, +128) of W (16 KB, half of the B tile); the leader CTA (rank 0) issues ONE tcgen05.mma.cta_group::2 of M = 256,
+// N = 256 per UMMA_K that reads both CTAs' shared memory, and each CTA's TMEM receives the 128 x 256 accumulator of its own rows:
+// 32 KB instead of 48 KB of operands per SM for the same MACs (-33 %), and half the B shared-memory reads per SM.
+//
+// Protocol (per CTA: same warp roles as the single-CTA kernel):
+//   full[s]   lives in the LEADER: count 1 (its own producer's arrive.expect_tx of BOTH CTAs' bytes); both producers' TMA loads
+//             complete_tx on it (cp.async.bulk.tensor...cta_group::2 with the leader's barrier address)
+//   empty[s]  per CTA, count 1: the leader's tcgen05.commit.cta_group::2...multicast arrives on both CTAs' copies
+//   tmem_full[a]  per CTA, count 1: multicast commit after the tile's last MMA
+//   tmem_empty[a] in the LEADER, count 2 x 4 EPI: one arrive per epilogue warp of either CTA (remote arrive for the peer)
+// Setup / teardown are cluster-synchronised: barriers are initialised before any remote arrive, TMEM (cta_group::2 alloc, issued by
+// warp 2 of both CTAs) is released only after both CTAs are done.
+// Restrictions: K-major operands, no gather, no accumulate / split-K, N % 256 == 0 (the launcher falls back to the single-CTA kernel).
+// ------------------------------------------------------------------------------------------------
+template <int STAGES, int EPI>
+struct GemmSmem2 {
+    static constexpr int BN = 256;
+    static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;                      // this CTA's half of the B tile
+    static constexpr int TILE_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+    static constexpr int STAGING_BYTES = EPI * 4 * 2 * 4096;
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int TOTAL = TILE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
+};
+
+template <int STAGES, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS + 128 * (EPI - 1), 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+    using S = GemmSmem2<STAGES, EPI>;
+    constexpr int BN = 256;
+    constexpr int B_STAGE_BYTES = S::B_STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = 512;                             // two 256-column accumulator stages
+    constexpr uint32_t IDESC = make_idesc_bf16(2 * BM, BN);         // M = 256 across the pair
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);       // same offset in both CTAs (same kernel, same static layout)
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint8_t* sStage = smem + S::TILE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES + S::STAGING_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                        // 0 = leader (issues the MMAs), 1 = peer
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int tiles_n = p.N / BN;
+    const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+    const int total_tiles = tiles_m * tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * 4 * EPI); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                             // both CTAs' barriers initialised, both TMEM allocations made
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer (both CTAs; bytes are signalled on the leader's full barrier) =====================
+            int stage = 0; uint32_t phase = 0;
+            for (int item = pair; item < total_tiles; item += npairs) {
+                const int m0 = (item / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+                const int nb = (item % tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
+                for (int seg = 0; seg < p.nseg; ++seg) {
+                    const int a_row = m0 + (p.nseg > 1 ? c_seg_a[seg] * p.a_plane_rows : 0);
+                    const int b_row = nb + (p.nseg > 1 ? c_seg_b[seg] * p.w_plane_rows : 0);
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 201);
+                        const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B_STAGE_BYTES));
+                        tma_load_2d_pair(sB + stage * B_STAGE_BYTES, &tmB, full_leader, kb * BK, b_row);
+                        tma_load_2d_pair(sA + stage * A_STAGE_BYTES, &tmA, full_leader, kb * BK, a_row);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            const int kiters = p.nseg * p.num_kb;
+            for (int item = pair; item < total_tiles; item += npairs) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.err_flag, 202);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int it = 0; it < kiters; ++it) {
+                    mbar_wait(&full_bar[stage], phase, p.err_flag, 203);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = make_umma_desc_kmajor_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
+                    const uint64_t bdesc = make_umma_desc_kmajor_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+                    umma_commit_pair(&empty_bar[stage], 3);         // frees the stage in BOTH CTAs when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(&tmem_full[acc], 3);               // accumulators complete -> both CTAs' epilogues
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (each CTA drains its own 128 rows) =====================
+        const int quarter = (warp - 4) & 3;
+        const int eset = (warp - 4) >> 2;
+        constexpr int CHUNKS = BN / 32 / EPI;
+        const int c_begin = eset * CHUNKS, c_end = c_begin + CHUNKS;
+        int acc = 0; uint32_t acc_phase = 0;
+        int sbuf = 0;
+        for (int item = pair; item < total_tiles; item += npairs) {
+            const int m0 = (item / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM, n0 = (item % tiles_n) * BN;
+            mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 204);
+            tcgen05_fence_after();
+            const int row = m0 + quarter * 32 + lane;
+            const uint32_t t_base = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
+            if (m0 + quarter * 32 < p.M)
+                epilogue_tile_tma(p, tmC, t_base, row, m0 + quarter * 32, n0, c_begin, c_end,
+                                  smem_u32(sStage) + static_cast<uint32_t>(eset * 4 + quarter) * 8192u, sbuf, lane);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {                                        // one arrive per warp on the LEADER's tmem_empty
+                if (rank == 0) mbar_arrive(&tmem_empty[acc]);
+                else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                             // the leader's MMAs read the peer's shared memory and write its TMEM
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -527,6 +694,28 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     return STAIR_OK;
 }
 
+static int pair_mode_default() {                       // STAIR_GEMM_PAIR=0|1|2 overrides the default at library load (A/B runs)
+    const char* e = getenv("STAIR_GEMM_PAIR");
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+}
+static int g_pair_mode = pair_mode_default();      // 1 (default) = CTA-pair (cta_group::2) kernel for eligible GEMMs, 0 = never, 2 = whenever legal (tests)
+
+template <int STAGES, int EPI>
+static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, cudaStream_t st) {
+    using S = GemmSmem2<STAGES, EPI>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+            return STAIR_ERR_CUDA;
+        configured = true;
+    }
+    const int tiles = ceil_div(p.M, 2 * BM) * (p.N / 256);
+    const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
+    gemm_tcgen05_pair_kernel<STAGES, EPI><<<2 * pairs, GEMM_THREADS + 128 * (EPI - 1), S::TOTAL, st>>>(ta, tb, tc, p);
+    STAIR_CHECK_LAUNCH();
+    return STAIR_OK;
+}
+
 thread_local long long g_launch_count = 0;
 
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
@@ -570,6 +759,23 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     // wide tiles when there are plenty of them.  The weight-gradient contraction (16 output tiles, K ~ 20 000 split over all SMs) is bound
     // by L2 -> SM operand traffic (every 128-column operand slice is re-read by 4 tiles: 160 MB for 40 MB of operands, ~6 TB/s); 128 x 256
     // tiles move 25 % fewer bytes but double the same-address atomics of the split-K epilogue and measured slower (g_dw_wide).
+    // CTA-pair kernel: K-major, no gather, plain store, N a multiple of 256, and at least half a wave of 256 x 256 tiles
+    {
+        const int tiles256 = ceil_div(a.M, 2 * BM) * (a.N / 256);
+        const bool legal = !a.mn_major && !gather && !a.accumulate && p.vec_ok && g_epilogue_impl == 0 && a.N % 256 == 0 && g_num_sms >= 2;
+        if (legal && (g_pair_mode == 2 || (g_pair_mode == 1 && tiles256 * 4 >= g_num_sms))) {
+            CUtensorMap ta, tb, tc;
+            int rc = make_tmap_bf16_2d(&ta, a.A, a.K, a_rows, a.lda, BK, BM);
+            if (rc) return rc;
+            rc = make_tmap_bf16_2d(&tb, a.W, a.K, w_rows, a.ldw, BK, 128);
+            if (rc) return rc;
+            rc = make_tmap_out(&tc, a.C, a.out_dtype, a.N, a.M, a.ldc);
+            if (rc) return rc;
+            p.tma_store = 1;
+            const bool epi2 = g_gemm_epi2 && p.num_kb * p.nseg <= 8;
+            return epi2 ? launch_tc_pair<5, 2>(ta, tb, tc, p, st) : launch_tc_pair<6, 1>(ta, tb, tc, p, st);
+        }
+    }
     const int bn = a.N <= 64 ? 64 : ((a.N % 256 == 0 && (tiles128 > g_wide_tiles_min * g_num_sms / 2 || (a.mn_major && g_dw_wide))) ? 256 : 128);
     CUtensorMap ta, tb;
     int rc;
@@ -601,6 +807,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
 using namespace stair;
 
 extern "C" int stair_set_gemm_impl(int impl) { g_gemm_impl = impl; return STAIR_OK; }
+extern "C" int stair_set_gemm_pair(int mode) { g_pair_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return STAIR_OK; }
 extern "C" int stair_set_gemm_epi2(int on) { g_gemm_epi2 = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_wide_min(int half_waves) { g_wide_tiles_min = half_waves < 0 ? 0 : half_waves; return STAIR_OK; }
 extern "C" int stair_set_gemm_dw_wide(int on) { g_dw_wide = on ? 1 : 0; return STAIR_OK; }

@@ -702,7 +702,7 @@ __global__ void relate_kernel(const float* __restrict__ att, const int* __restri
 
 int launch_relate(const float* att, const int* att_idx, const float* beta, int sign, float* att_out, int out_base, int n, int T, cudaStream_t st) {
     if (n <= 0) return STAIR_OK;
-    relate_kernel<<<min(blocks_for(n, 8), 148 * 8), 256, 0, st>>>(att, att_idx, beta, sign >= 0 ? 1.f : -1.f, att_out, out_base, n, T);
+    relate_kernel<<<min(blocks_for(n, 8), 148 * 8), 256, 0, st>>>(att, att_idx, beta, sign > 0 ? 1.f : (sign < 0 ? -1.f : 0.f), att_out, out_base, n, T);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -1063,10 +1063,13 @@ int launch_argmax(const float* logits, int* out, int rows, int cols, cudaStream_
 // (dead code in the reference forward; exported and parity-tested because the north star names the scans.)
 // One warp per instance; inclusive warp prefix scans over T in chunks of 32 with a running carry.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
+// The partial sums are carried in double and rounded to fp32 once per output: torch's CPU cumsum (the reference's relate_,
+// modules.py:302-304) accumulates in double too, so a run of zeros after the ReLU leaves the scan EXACTLY flat — an fp32 Kogge-Stone scan
+// associates every prefix differently and breaks such plateaus by an ulp, which moves the argmax of the mask.
+__device__ __forceinline__ double warp_incl_scan(double v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const float u = __shfl_up_sync(0xffffffffu, v, o);
+        const double u = __shfl_up_sync(0xffffffffu, v, o);
         if (lane >= o) v += u;
     }
     return v;
@@ -1074,20 +1077,20 @@ __device__ __forceinline__ float warp_incl_scan(float v, int lane) {
 
 // before[t] = sum_{u<=t} relu(a[u]) ; after[t] = sum_{u>=t} relu(a[u]) ; written to shared memory
 __device__ void scan_before_after(const float* a, int T, int lane, float* before, float* after) {
-    float carry = 0.f;
+    double carry = 0.0;
     for (int t0 = 0; t0 < T; t0 += 32) {
         const int t = t0 + lane;
-        const float v = t < T ? fmaxf(a[t], 0.f) : 0.f;
-        const float s = warp_incl_scan(v, lane) + carry;
-        if (t < T) before[t] = s;
+        const double v = t < T ? static_cast<double>(fmaxf(a[t], 0.f)) : 0.0;
+        const double s = warp_incl_scan(v, lane) + carry;
+        if (t < T) before[t] = static_cast<float>(s);
         carry = __shfl_sync(0xffffffffu, s, 31);
     }
-    carry = 0.f;
+    carry = 0.0;
     for (int t0 = 0; t0 < T; t0 += 32) {
         const int t = T - 1 - (t0 + lane);
-        const float v = t >= 0 ? fmaxf(a[t], 0.f) : 0.f;
-        const float s = warp_incl_scan(v, lane) + carry;
-        if (t >= 0) after[t] = s;
+        const double v = t >= 0 ? static_cast<double>(fmaxf(a[t], 0.f)) : 0.0;
+        const double s = warp_incl_scan(v, lane) + carry;
+        if (t >= 0) after[t] = static_cast<float>(s);
         carry = __shfl_sync(0xffffffffu, s, 31);
     }
 }

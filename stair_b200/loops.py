@@ -109,8 +109,9 @@ def train(windows, model, lr=2e-4, weight_decay=0.0, module_loss_weight=1.0, dec
     pending = []
     for window in windows:
         it = state.get('questions_seen', 0) * questions_per_iter
-        mlw = module_loss_weight if (train_module_before_iters is None or it < train_module_before_iters) else 0.0
-        dlw = decoder_loss_weight if it >= train_decoder_after_iters else 0.0
+        # the reference's counter is 1-based (global_steps += 1 before the tests): modules while g < before, decoder once g > after
+        mlw = module_loss_weight if (train_module_before_iters is None or it + 1 < train_module_before_iters) else 0.0
+        dlw = decoder_loss_weight if it + 1 > train_decoder_after_iters else 0.0
         out = step_for(mlw, dlw)(window)
         state['questions_seen'] = state.get('questions_seen', 0) + (window.B if isinstance(window, LY.NMNBatch) else len(window))
         state['optimizer'].step()

@@ -249,6 +249,10 @@ class NMNTrainStep:
     >>> out = step(list_of_data_dicts)                   # fills parameter.grad, returns losses / logits / answers
     >>> opt.step(); opt.zero_grad()
 
+    A loss weight of 0 means that loss is NOT computed for the window — the reference's iteration gates (train_module.py:349,376:
+    ``train_module_before_iters`` / ``train_decoder_after_iters``) and its ``return_res_by_step=args.module_loss_weight != 0`` — so the
+    parameters only that loss reaches keep ``grad = None`` and Adam skips them.
+
     Data-parallel (one process per GPU): pass ``process_group`` (or leave the default group initialised); every rank
     passes its own shard, ``gradient_accumulation`` defaults to the global window size, gradients are summed with NCCL
     all-reduces over the flat fp32 gradient buffer (decoder / module slots while the encoders still back-propagate, encoder slots

@@ -204,3 +204,65 @@ def test_two_epilogue_warp_sets_are_bit_identical(shape, odt):
     assert torch.equal(outs[0], outs[1])
     ref = _ref(A[:, :K], W[:, :K], bias, rs, True)
     assert (outs[1].float() - ref).abs().max().item() <= (2e-2 if odt == torch.bfloat16 else 2e-4) * max(ref.abs().max().item(), 1.0)
+
+
+PAIR_SHAPES = [(256, 256, 64), (1000, 512, 512), (333, 256, 300), (4096, 2048, 320), (130, 768, 64), (2048, 512, 1024), (4096, 2048, 4096),
+               (257, 256, 128)]
+
+
+@pytest.mark.parametrize('shape', PAIR_SHAPES)
+@pytest.mark.parametrize('odt', [torch.bfloat16, torch.float32])
+def test_cta_pair_kernel_is_bit_identical_to_the_single_cta_kernel(shape, odt):
+    """stair_set_gemm_pair: tcgen05 cta_group::2 — a 2-CTA cluster per 256 x 256 tile, M = 256 MMAs issued by the leader, the B tile split
+    across the pair.  Every accumulator element is the same k-ordered fp32 sum as in the single-CTA kernel and the epilogue code is
+    shared, so the outputs must be bit-identical (ragged M incl. a peer CTA whose rows are all past M, short and long K, bias / ReLU /
+    row scale, both output types); and both match the fp32 reference."""
+    M, N, K = shape
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp, device='cuda', dtype=torch.bfloat16)
+    W = torch.zeros(N, Kp, device='cuda', dtype=torch.bfloat16)
+    A[:, :K] = torch.randn(M, K, device='cuda', generator=g).bfloat16()
+    W[:, :K] = (torch.randn(N, K, device='cuda', generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device='cuda', generator=g)
+    rs = torch.rand(M, device='cuda', generator=g)
+    lib = L.lib()
+    outs = []
+    try:
+        for mode in (0, 2):
+            lib.stair_set_gemm_pair(mode)
+            for _ in range(2):                                   # twice: barrier phases / TMEM alloc-dealloc across launches
+                out = L.gemm(A, W, bias=bias, out_dtype=odt, act=L.ACT_RELU, row_scale=rs, K=K)
+            torch.cuda.synchronize()
+            outs.append(out.clone())
+    finally:
+        lib.stair_set_gemm_pair(1)
+    assert lib.stair_gemm_error_flag() == 0
+    assert torch.equal(outs[0], outs[1])
+    ref = _ref(A[:, :K], W[:, :K], bias, rs, True)
+    assert (outs[1].float() - ref).abs().max().item() <= (2e-2 if odt == torch.bfloat16 else 2e-4) * max(ref.abs().max().item(), 1.0)
+
+
+def test_cta_pair_kernel_split3_planes():
+    """The strict fp32 mode (three bf16 planes, six plane products into one accumulator) through the CTA-pair kernel."""
+    M, N, K = 700, 512, 512
+    g = torch.Generator(device='cuda').manual_seed(5)
+    A = torch.randn(M, K, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g) * K ** -0.5
+
+    def split(x):
+        p0 = x.bfloat16(); r = x - p0.float()
+        p1 = r.bfloat16(); r = r - p1.float()
+        return torch.cat([p0, p1, r.bfloat16()], dim=0).contiguous()
+    lib = L.lib()
+    outs = []
+    try:
+        for mode in (0, 2):
+            lib.stair_set_gemm_pair(mode)
+            outs.append(L.gemm(split(A), split(W), out_dtype=torch.float32, M=M, N=N, K=K, nplanes=3, a_plane_rows=M, w_plane_rows=N).clone())
+            torch.cuda.synchronize()
+    finally:
+        lib.stair_set_gemm_pair(1)
+    assert torch.equal(outs[0], outs[1])
+    ref = (A.double() @ W.double().t()).float()
+    assert (outs[1] - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 1e-6
