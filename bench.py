@@ -10,9 +10,14 @@ video_nmn/dataset.py:150-172), questions of 8-24 GloVe-sized words, random-init 
 inference (test_mode=True, return_res_by_step=False).  N > 1: every rank runs its own 4096 questions (weak scaling,
 configs[2]: 32768 questions at 8 GPUs) and the int32 answers are all-gathered with NCCL inside the timed step.
 
-One JSON line on stdout (rank 0): see the contract in the task statement; extra keys: roofline, cpu_baseline, phases_ms,
-parity.  The oracle (oracle/nmn_oracle.py) is used ONLY as the cpu_baseline / --impl reference timer and as the checker of
-the first 32 answers — never on the measured path.
+One JSON line on stdout (rank 0): the contract keys plus
+  roofline      dominant kernel (video input projection GEMM) against the measured bf16 peak
+  roofline_hbm  the memory-bound module kernels against the measured HBM peak, at the step's own group size and at a streaming size
+  phases_ms / host_enqueue_ms / strict (fp32 strict mode, timed) / audit / i3d (configs[4]) / train (configs[3]) / e2e (+ from_dicts)
+  parity        ALL answers of the step against the CPU oracle (bf16 and fp32 strict), attention argmax, error statistics
+  cpu_baseline  the reference's CPU path restated (oracle port) timed on the box's host cores
+The oracle (oracle/nmn_oracle.py) is used ONLY as the cpu_baseline / --impl reference timer and as the checker — never on the
+measured path.
 """
 import argparse
 import json
@@ -27,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-import numpy as np  # noqa: E402
+import numpy as np  # noqa: E402,F401
 import torch  # noqa: E402
 
 METRIC, UNIT = 'nmn_questions_per_sec', 'questions/s'
@@ -36,6 +41,8 @@ T, V = 8, 4096
 CPU_SAMPLE = 32
 TRAIN_DROPOUT = 0.25
 E2E_CHUNKS = 2
+PARITY_PER_RANK_MULTI = 512        # N > 1: questions of every rank's shard checked against the oracle (the host cores are shared by N ranks)
+ATT_CHECK_Q = 512                  # questions whose Localize attention maps are pulled back and argmax-compared
 
 
 def peaks():
@@ -43,8 +50,8 @@ def peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return {'hbm_gbs': d['hbm_gbs'], 'tf_burst': d['bf16_tflops'], 'tf_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']),
-                'src': 'measured'}
-    return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'src': 'fallback'}
+                'src': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'src': 'fallback (B200_PROFILING.md)'}
 
 
 class ClockSampler:
@@ -86,6 +93,14 @@ class ClockSampler:
 TEMPLATES = None          # None = the ten AGQA templates
 
 
+def workload_string(args, B):
+    if args.workload == 'rx':
+        return ('ModuleNet batched inference, %d mixed-program questions per GPU (10 AGQA layout templates, 2-12 modules), RX/TGIF-QA features '
+                '[8,4096], questions 8-24 words x 300, random init' % B)
+    return ('I3D stress test (BASELINE configs[4]): %d questions per GPU, layouts of >= 12 modules only (xor_between, and_between_until, '
+            'compare_between), features [64,1024], conv-mode Temporal, random init' % B)
+
+
 def build_inputs(rank, B):
     from stair_b200 import synthetic as syn, collate
     qs = syn.make_questions(B, T, V, seed=1234 + rank, with_gold=True, templates=TEMPLATES)      # gold is only read by the training leg
@@ -101,7 +116,6 @@ def cpu_reference_timer(qs, weights, cfg, min_seconds=10.0, max_passes=50, threa
     torch.set_num_threads(threads or os.cpu_count() or 1)
     model = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES, aten_lstm=True)
     sample = qs[:CPU_SAMPLE]
-    logits = None
     with torch.no_grad():
         for d in sample[:4]:
             model(d, return_res_by_step=False, test_mode=True)
@@ -109,12 +123,79 @@ def cpu_reference_timer(qs, weights, cfg, min_seconds=10.0, max_passes=50, threa
         t_all = time.perf_counter()
         while True:
             t0 = time.perf_counter()
-            logits = [model(d, return_res_by_step=False, test_mode=True)['logits'] for d in sample]
+            for d in sample:
+                model(d, return_res_by_step=False, test_mode=True)
             times.append(time.perf_counter() - t0)
             if time.perf_counter() - t_all >= min_seconds or len(times) >= max_passes:
                 break
     med = statistics.median(times)
-    return len(sample) / med, med, len(times), torch.stack(logits)
+    return len(sample) / med, med, len(times)
+
+
+def oracle_outputs(qs, weights, cfg, threads, with_attention):
+    """CPU oracle over ``qs`` (fp32, one question at a time like the reference): logits [n, A] and, for the first ``with_attention``
+    questions, every Localize attention map of the layout (list per question of [K, T] tensors in token order)."""
+    from oracle import nmn_oracle as orc
+    from stair_b200 import synthetic as syn
+    torch.set_num_threads(max(1, threads))
+    model = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES, aten_lstm=True)
+    logits, maps = [], []
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for i, d in enumerate(qs):
+            att = i < with_attention
+            out = model(d, return_res_by_step=False, return_result_of_each_step=att, test_mode=True)
+            logits.append(out['logits'])
+            if att:
+                maps.append([r for tok, (_, r) in zip(d['nmn_program_list'], out['result_of_each_step']) if tok == 'Localize'])
+    return torch.stack(logits), maps, time.perf_counter() - t0
+
+
+def parity_report(model_bf16, strict_model, qs, weights, cfg, answers_bf16, logits_bf16, threads):
+    """Answers / logits of the measured arm against the CPU oracle on the SAME questions (all of ``qs``)."""
+    n = len(qs)
+    n_att = min(ATT_CHECK_Q, n)
+    ref_logits, ref_maps, secs = oracle_outputs(qs, weights, cfg, threads, n_att)
+    ref_ans = ref_logits.argmax(1)
+    top2 = ref_logits.topk(2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    lmax = ref_logits.abs().max(1).values
+    got = answers_bf16[:n].long().cpu()
+    lg = logits_bf16[:n].float().cpu()
+    mism = got != ref_ans
+    rel = (lg - ref_logits).abs().max(1).values / lmax
+    clear = margin > 1e-2 * lmax                                   # the bar of tests/test_forward_gpu.py (3x the largest margin ever seen to flip)
+    rep = {'questions_checked': n, 'oracle_seconds': secs,
+           'bf16_answers_equal': int((~mism).sum()),
+           'bf16_answers_equal_where_margin_clear': int(((~mism) & clear).sum()), 'bf16_clear_margin': int(clear.sum()),
+           'bf16_margin_rule': 'reference top-2 logit margin > 1e-2 * max|logit|',
+           'bf16_mismatch_max_margin_rel': float((margin[mism] / lmax[mism]).max()) if bool(mism.any()) else 0.0,
+           'bf16_logit_err_rel_median': float(rel.median()), 'bf16_logit_err_rel_p99': float(rel.kthvalue(max(1, int(0.99 * n))).values),
+           'bf16_logit_err_rel_max': float(rel.max())}
+    # attention argmax of every Localize map of the first n_att questions (audit outputs of the measured model)
+    out = model_bf16(qs[:n_att], return_res_by_step=False, return_result_of_each_step=True, test_mode=True)
+    rows = eq = clear_rows = clear_eq = 0
+    worst = 0.0
+    for qi in range(n_att):
+        toks = qs[qi]['nmn_program_list']
+        mine = [r for tok, (_, r) in zip(toks, out['result_of_each_step'][qi]) if tok == 'Localize']
+        for g, w in zip(mine, ref_maps[qi]):
+            g = g.float().cpu()
+            same = g.argmax(-1) == w.argmax(-1)
+            t2 = w.topk(2, dim=-1).values
+            ok = (t2[:, 0] - t2[:, 1]) > 6e-4
+            rows += same.numel(); eq += int(same.sum()); clear_rows += int(ok.sum()); clear_eq += int((same & ok).sum())
+            if bool((~same).any()):
+                worst = max(worst, float((t2[:, 0] - t2[:, 1])[~same].max()))
+    rep.update({'localize_rows': rows, 'localize_argmax_equal': eq, 'localize_rows_margin_clear': clear_rows,
+                'localize_argmax_equal_where_margin_clear': clear_eq, 'localize_mismatch_max_margin': worst,
+                'localize_margin_rule': 'reference top-2 attention margin > 6e-4'})
+    if strict_model is not None:
+        s_out = strict_model(qs, return_res_by_step=False, test_mode=True)
+        s_ans = s_out['answers'].long().cpu()
+        rep.update({'fp32_strict_answers_equal': int((s_ans == ref_ans).sum()),
+                    'fp32_strict_max_logit_err': float((s_out['logits'].float().cpu() - ref_logits).abs().max())})
+    return rep
 
 
 def make_weights(cfg):
@@ -148,12 +229,8 @@ def run_reference(args, rank, world):
     line = {'impl': 'reference', 'metric': METRIC, 'value': qps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            # the measured arm's config (same workload, same keys), plus what one reference step is
-            'config': {'workload': ('ModuleNet batched inference, %d mixed-program questions per GPU (10 AGQA layout templates, 2-12 modules), '
-                                    'RX/TGIF-QA features [8,4096] bf16, questions 8-24 words x 300, random init, bf16 storage / fp32 accumulate'
-                                    % args.batch) if args.workload == 'rx' else
-                                   ('I3D stress test (BASELINE configs[4]): %d questions per GPU, compare / xor_between layouts (9-12 modules), '
-                                    'features [64,1024] bf16, conv-mode Temporal, random init, bf16 storage / fp32 accumulate' % args.batch),
+            # the measured arm's workload; the reference computes it in fp32 on the host (its only arithmetic type)
+            'config': {'workload': workload_string(args, args.batch) + ', fp32 on the host cores (the reference\'s arithmetic)',
                        'questions_per_gpu': args.batch, 'global_questions': args.gpus * args.batch, 'frames': T, 'video_size': V,
                        'hidden_size': cfg['hidden_size'], 'parallelism': 'reference arm: host cores of rank 0 only',
                        'reference_step': 'CPU reference path (fp32): per-question loop, eval, no_grad; one step = the first %d questions of '
@@ -164,6 +241,21 @@ def run_reference(args, rank, world):
                                        '/root/reference)' % (CPU_SAMPLE, args.steps, cores)},
             'e2e': {'value': qps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
+
+
+def device_timed(fn, steps, barrier, dev, dist, world):
+    """CUDA-event time (ms, max over ranks) of ``steps`` calls of ``fn`` on the current stream."""
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), out
 
 
 def main():
@@ -177,19 +269,21 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='stair_b200', choices=['stair_b200', 'reference'])
     ap.add_argument('--batch', type=int, default=PER_GPU_B, help='questions per GPU (default: the BASELINE config)')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU legs (cpu_baseline and the oracle parity check)')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step leg (BASELINE configs[3])')
+    ap.add_argument('--no-extras', action='store_true', help='skip the strict / i3d / roofline_hbm / e2e-from-dicts legs (quick runs)')
     ap.add_argument('--no-overlap-allreduce', action='store_true',
                     help='training leg at N > 1: one gradient all-reduce after the whole backward instead of overlapping it with BPTT (comparison)')
     ap.add_argument('--workload', default='rx', choices=['rx', 'i3d'],
                     help="rx (default, BASELINE configs[1]): T=8, V=4096, the 10 AGQA templates; i3d (configs[4] stress test): T=64, V=1024, "
-                         "conv-mode Temporal, only the >= 9-module layouts (compare, xor_between)")
+                         "conv-mode Temporal, only layouts of >= 12 modules")
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     global T, V, TEMPLATES
+    from stair_b200 import synthetic as syn
     if args.workload == 'i3d':
-        T, V, TEMPLATES = 64, 1024, ['compare', 'xor_between']
+        T, V, TEMPLATES = 64, 1024, list(syn.LONG_TEMPLATES)
     if args.impl == 'reference':
         run_reference(args, rank, world)
         return
@@ -203,7 +297,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
-    from stair_b200 import VideoNMN, synthetic as syn, _lib as L
+    from stair_b200 import VideoNMN, _lib as L
     from stair_b200.distributed import bind_to_gpu_numa_node
     numa = bind_to_gpu_numa_node(local) if world > 1 else {'numa_node': None}     # before any pinned allocation
     if world > 1:
@@ -239,20 +333,22 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        st = step_device()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, st = device_timed(step_device, args.steps, barrier, dev, dist, world)
     value = world * B * args.steps / (ms * 1e-3)
-    answers_dev = st.answers.cpu()
+    answers_dev, logits_dev = st.answers.clone(), st.logits.clone()
+    gathered_ok = None
+    if world > 1:                                                    # the gathered answers are every rank's own answers, in rank order
+        gathered_ok = bool(torch.equal(gathered[rank * B:(rank + 1) * B], answers_dev))
+
+    # host time to ENQUEUE one forward (ctypes call: ~120 cuTensorMapEncodeTiled + ~80 launches), the device idle
+    torch.cuda.synchronize()
+    enq = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        model.forward_batch(batch)
+        enq.append(time.perf_counter() - t0)
+        torch.cuda.synchronize()
+    host_enqueue_ms = 1e3 * statistics.median(enq)
 
     # ---- end to end through the public API: pinned host batch -> H2D -> forward -> answers D2H ----------------------
     # The pinned host batch is collated as E2E_CHUNKS sub-batches (bf16 features and word embeddings, the storage type of the
@@ -305,6 +401,31 @@ def main():
     e2e_value = world * B * args.steps / e2e_s
     clock_info = clocks.stop() if rank == 0 else None
 
+    # the same call from reference-schema data dicts (video_nmn/dataset.py:189-233): collate (layout compile + fp32 -> bf16 staging into
+    # pinned memory) INSIDE the timer.  This is what `model(list_of_dicts)` costs a caller who does not collate in DataLoader workers.
+    from_dicts = None
+    if not args.no_extras:
+        def step_dicts():
+            chunks = collate_chunks(qs, E2E_CHUNKS, pin_memory=True, video_dtype=torch.bfloat16, question_dtype=torch.bfloat16)
+            answers, _, _ = model.forward_pipelined(chunks)
+            return answers.cpu()
+        step_dicts()
+        barrier()
+        t0 = time.perf_counter()
+        nd = 3
+        for _ in range(nd):
+            step_dicts()
+        barrier()
+        ds = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(ds, op=dist.ReduceOp.MAX)
+        t0 = time.perf_counter()
+        collate_chunks(qs, E2E_CHUNKS, pin_memory=True, video_dtype=torch.bfloat16, question_dtype=torch.bfloat16)
+        collate_ms = 1e3 * (time.perf_counter() - t0)
+        from_dicts = {'value': world * B * nd / float(ds.item()), 'unit': UNIT, 'ms_per_step': 1e3 * float(ds.item()) / nd, 'collate_ms': collate_ms,
+                      'host_threads': os.cpu_count(),
+                      'what': 'collate_chunks(list of reference-schema dicts, fp32 tensors) + forward_pipelined + answers.cpu() per step, one process'}
+
     # ---- per-phase split and the dominant kernel (video input projection GEMM), CUDA events on the launch stream ---
     phases = [('group', L.FWD_GROUP), ('encode_video', L.FWD_ENCODE_VIDEO), ('encode_text', L.FWD_ENCODE_TEXT),
               ('modules', L.FWD_MODULES), ('decode', L.FWD_DECODE)]
@@ -329,37 +450,51 @@ def main():
         for i, (n, _) in enumerate(phases):
             ph_ms[n] += evs[i].elapsed_time(evs[i + 1]) / nrep
         gemm_ms += evs[len(phases)].elapsed_time(evs[len(phases) + 1]) / nrep
+    del xout
+
     # ---- audit mode: the same forward with every pretrain head computed (res_by_step / result_of_each_step:
     # FilterFrame [T, O] head GEMM, L2-normalised Filter / ToAction / Superlative outputs, Exists / Xor / Equals heads) -------------
     heads = model._head_modules(True, True)
     for _ in range(3):
         model.forward_batch(batch, heads)
-    barrier()
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a0.record()
-    for _ in range(nrep):
-        model.forward_batch(batch, heads)
-    a1.record()
-    barrier()
-    ta = torch.tensor([a0.elapsed_time(a1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
-    audit_ms = float(ta.item()) / nrep
+    a_ms, _ = device_timed(lambda: model.forward_batch(batch, heads), nrep, barrier, dev, dist, world)
+    audit_ms = a_ms / nrep
     audit = {'value': world * B / (audit_ms * 1e-3), 'unit': UNIT, 'ms_per_step': audit_ms, 'launches_per_step': model.last_launches,
              'what': 'forward with all pretrain heads (return_res_by_step / return_result_of_each_step device work)'}
+
+    # ---- fp32 strict mode, timed: fp32 storage, every contraction as six bf16-plane products (the mode whose answers are guaranteed
+    # bit-identical to the reference) on the same questions -------------------------------------------------------------------------
+    strict, strict_model = None, None
+    if not args.no_extras:
+        strict_model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
+        strict_model.load_state_dict(weights)
+        strict_model = strict_model.to(dev).eval()
+        for _ in range(2):
+            strict_model.forward_batch(batch)
+        ks = max(2, min(args.steps, 5))
+        s_ms, s_st = device_timed(lambda: strict_model.forward_batch(batch), ks, barrier, dev, dist, world)
+        strict = {'value': world * B * ks / (s_ms * 1e-3), 'unit': UNIT, 'ms_per_step': s_ms / ks, 'launches_per_step': strict_model.last_launches,
+                  'answers_equal_to_bf16_path': int((s_st.answers == answers_dev).sum()), 'questions': B,
+                  'what': 'precision="fp32": fp32 activations, bf16x3 split contractions (6 plane products per GEMM) on the tensor cores'}
+        strict_model.release_buffers()
 
     # ---- training step (BASELINE configs[3]): forward with history + intermediate-supervision losses + backward +
     # gradient all-reduce (N > 1) + Adam, one window = the rank's 4096 questions; device-timed, max over ranks -------------
     train = None
     if not args.no_train:
         from stair_b200.train import NMNTrainStep, FusedAdam
-        # throughput run: the reference's default training dropout (video_nmn/args.py:31); parity runs (tests) use 0 or injected masks
+        from stair_b200 import collate
+        # throughput run: the reference's default training dropout (video_nmn/args.py:31); parity runs (tests) use 0 or injected masks.
+        # The window mixes in the two layouts with a NON-root Equals / Xor so that every criterion of train_module.py:92-107 runs.
+        tmpl = None if args.workload == 'i3d' else list(syn.TEMPLATES) + ['and_equals_xor', 'compare_xor_equals']
+        tqs = qs if tmpl is None else syn.make_questions(B, T, V, seed=4321 + rank, with_gold=True, templates=tmpl)
+        tbatch = batch if tmpl is None else collate(tqs, pin_memory=True, video_dtype=torch.bfloat16, question_dtype=torch.float32).to(dev)
         tmodel = VideoNMN(dict(cfg, dropout=TRAIN_DROPOUT), pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16')
         tmodel.load_state_dict(weights)
         tmodel = tmodel.to(dev).train()
         tstep = NMNTrainStep(tmodel, overlap_allreduce=not args.no_overlap_allreduce)
         opt = FusedAdam(tmodel, lr=2e-4)
-        plan = tstep.plan(batch)
+        plan = tstep.plan(tbatch)
 
         def train_step():
             out = tstep.run(plan)
@@ -371,24 +506,15 @@ def main():
             out = train_step()
         tmodel.check_status(out['state'])
         ksteps = max(2, min(args.steps, 5))
-        barrier()
-        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0e.record()
-        for _ in range(ksteps):
-            out = train_step()
-        t1e.record()
-        barrier()
-        tms = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
-        if world > 1:
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        tms = float(tms.item())
+        tms, out = device_timed(train_step, ksteps, barrier, dev, dist, world)
         train = {'value': world * B * ksteps / (tms * 1e-3), 'unit': UNIT, 'ms_per_step': tms / ksteps, 'steps': ksteps,
                  'launches_per_step': tstep.last_launches, 'window_questions': world * B, 'loss': float(out['loss']),
                  'loss_rows': out['loss_counts'], 'dropout': TRAIN_DROPOUT,
+                 'layouts': 'the 10 AGQA templates + and_equals_xor + compare_xor_equals (supervised non-root Equals / Xor)' if tmpl else 'as the inference leg',
                  'what': 'forward with encoder history + losses (train_module.py:83-194) + backward + %sAdam (one fused multi-tensor kernel that also refreshes the bf16 weight copies); bf16 storage, fp32 gradients'
                          % ('NCCL gradient all-reduce + ' if world > 1 else '')}
         # the reference-faithful window: 32 questions per optimizer step (train_module.py gradient_accumulation = 32), latency-bound
-        plan32 = tstep.plan(qs[:32])
+        plan32 = tstep.plan(tqs[:32])
 
         def train_step32():
             o = tstep.run(plan32)
@@ -398,65 +524,114 @@ def main():
 
         for _ in range(3):
             train_step32()
-        barrier()
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record()
-        for _ in range(10):
-            train_step32()
-        w1.record()
-        barrier()
-        w32 = w0.elapsed_time(w1) / 10
-        train['window32'] = {'ms_per_step': w32, 'value': 32 / (w32 * 1e-3), 'unit': UNIT,
+        w_ms, _ = device_timed(train_step32, 10, barrier, dev, dist, world)
+        w32 = w_ms / 10
+        train['window32'] = {'ms_per_step': w32, 'value': 32 / (w32 * 1e-3), 'unit': UNIT, 'launches_per_step': tstep.last_launches,
                              'what': 'one 32-question window per optimizer step on this rank (reference accumulation window; launch-latency bound)'}
-        del tmodel, tstep, opt, plan, plan32
+        del tmodel, tstep, opt, plan, plan32, tbatch
+        torch.cuda.empty_cache()
+
+    # ---- I3D stress configuration (BASELINE configs[4]): T = 64, V = 1024, conv-mode Temporal, ONLY layouts of >= 12 modules --------
+    i3d = None
+    if not args.no_extras and args.workload == 'rx':
+        from stair_b200 import collate
+        Ti, Vi = 64, 1024
+        icfg = syn.model_config(T=Ti, V=Vi)
+        imodel = VideoNMN(icfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16')
+        imodel.load_state_dict(make_weights(icfg))
+        imodel = imodel.to(dev).eval()
+        iqs = syn.make_questions(B, Ti, Vi, seed=777 + rank, templates=list(syn.LONG_TEMPLATES))
+        ibatch = collate(iqs, pin_memory=True, video_dtype=torch.bfloat16, question_dtype=torch.float32).to(dev)
+        for _ in range(3):
+            ist = imodel.forward_batch(ibatch)
+        imodel.check_status(ist)
+        ki = max(3, min(args.steps, 10))
+        i_ms, _ = device_timed(lambda: imodel.forward_batch(ibatch), ki, barrier, dev, dist, world)
+        n_mod = [int(lay.is_module.sum()) for lay in {id(l): l for l in ibatch.layouts}.values()]
+        i3d = {'value': world * B * ki / (i_ms * 1e-3), 'unit': UNIT, 'ms_per_step': i_ms / ki, 'launches_per_step': imodel.last_launches,
+               'questions_per_gpu': B, 'frames': Ti, 'video_size': Vi, 'layouts': list(syn.LONG_TEMPLATES), 'modules_per_layout': sorted(n_mod),
+               'what': 'BASELINE configs[4]: I3D features [64, 1024], conv-mode Temporal (k = 16, 16, 33), every question a layout of >= 12 modules; '
+                       'inference, bf16 storage'}
+        del imodel, ibatch, iqs
+        torch.cuda.empty_cache()
+
+    # ---- memory-bound module kernels against the HBM roofline, at the step's own group size and at a streaming size ----------------
+    roofline_hbm = None
+    if not args.no_extras and rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, 'profiles'))
+        import module_roofline as mr
+        from stair_b200 import layout as LY
+        vid_ops = {LY.OP_OF[n] for n in ('Localize', 'Temporal', 'Filter', 'FilterFrame', 'HasItem', 'AttnVideo', 'ExistsFrame')}
+        counts = [int(c) for k, c in zip(batch.group_keys, batch.group_counts) if (int(k) // 8) % 32 in vid_ops]
+        n_step = int(statistics.median(counts)) if counts else 2048
+        names = ('cos_att', 'layernorm', 'sum_frames', 'attn_video', 'exists_frame', 'hasitem_tail', 'l2normalize')
+        roofline_hbm = {'peak_gbs': mr.hbm_peak()[0], 'peak_source': mr.hbm_peak()[1],
+                        'bytes': 'algorithmic: every input read once + every exposed output written once (SURVEY 8d), bf16 activations',
+                        'in_step': {'n': n_step, 'what': 'median instance count of the frame-sized module groups of this step; L2 flushed between '
+                                                         'repetitions; 17-34 MB per launch = launch-latency bound',
+                                    'kernels': [{k: r[k] for k in ('kernel', 'n', 'bytes', 'ms', 'frac')} for r in mr.measure(n_step, T=T, kernels=names)]},
+                        'streaming': {'n': 32768, 'what': 'inputs larger than the 126 MB L2, no flush (l2normalize: 262144 rows)',
+                                      'kernels': [{k: r[k] for k in ('kernel', 'n', 'bytes', 'ms', 'frac')} for r in mr.measure(32768, T=T, kernels=names)]}}
         torch.cuda.empty_cache()
 
     pk = peaks()
     flops = 2.0 * M * N * K
     achieved_tf = flops / (gemm_ms * 1e-3) / 1e12
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the default shape, from the committed `ncu --set full` capture
-    # (profiles/r1_gemm_xproj_ncu_summary_v3.txt); algorithmic bytes: A 268 MB + W 17 MB + C 134 MB = 419 MB
-    traffic = 398.9e6 if (args.workload == 'rx' and B == PER_GPU_B) else None
-    roofline = {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel<256,4> (video input projection [%d,%d]x[%d,%d])' % (M, K, K, N),
-                'achieved': achieved_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': achieved_tf / pk['tf_sustained'],
-                'frac_of_burst_peak': achieved_tf / pk['tf_burst'], 'peak_source': pk['src'] + ' (sustained; kernel timed inside the step loop)',
-                'traffic': traffic, 'traffic_source': 'profiles/r1_gemm_xproj_ncu_summary_v3.txt' if traffic else None, 'ms': gemm_ms,
-                'flops_per_launch': flops, 'algorithmic_bytes_per_launch': 2.0 * (M * K + N * K + M * N)}
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the default shape, from the committed `ncu --set full` capture;
+    # algorithmic bytes: A 268 MB + W 17 MB + C 134 MB = 419 MB
+    traffic_file = os.path.join(ROOT, 'profiles', 'r2_gemm_pair_ncu_traffic.json')
+    traffic, traffic_src = None, None
+    if args.workload == 'rx' and B == PER_GPU_B and os.path.exists(traffic_file):
+        tj = json.load(open(traffic_file))
+        traffic, traffic_src = tj.get('dram_bytes'), tj.get('source')
+    roofline = {'bound': 'tensor', 'kernel': 'gemm_tcgen05_pair_kernel<6,1> (video input projection [%d,%d]x[%d,%d], tcgen05 cta_group::2)' % (M, K, K, N),
+                'achieved': achieved_tf, 'peak': pk['tf_burst'], 'unit': 'TFLOP/s', 'frac': achieved_tf / pk['tf_burst'],
+                'frac_of_sustained_peak': achieved_tf / pk['tf_sustained'],
+                'peak_source': pk['src'] + ': burst bf16 (the kernel is timed alone, one launch between two events)',
+                'traffic': traffic, 'traffic_source': traffic_src, 'ms': gemm_ms,
+                'flops_per_launch': flops, 'algorithmic_bytes_per_launch': 2.0 * (M * K + N * K + M * N),
+                'step_share': gemm_ms / (ms / args.steps)}
 
-    line = None
-    if rank == 0:
-        cpu = None
-        parity = None
-        if not args.no_cpu_baseline and world == 1:
-            qps1, med1, _, _ = cpu_reference_timer(qs, weights, cfg, min_seconds=5.0, max_passes=20, threads=1)
-            qps, med, npass, ref_logits = cpu_reference_timer(qs, weights, cfg)
+    # ---- CPU legs: baseline timing (rank 0, N = 1) and the parity check of this rank's answers against the oracle -------------------
+    cpu = None
+    parity = None
+    if not args.no_cpu_baseline:
+        ncpu = os.cpu_count() or 1
+        if world == 1:
+            qps1, med1, _ = cpu_reference_timer(qs, weights, cfg, min_seconds=5.0, max_passes=20, threads=1)
+            qps, med, npass = cpu_reference_timer(qs, weights, cfg)
             cpu = {'value': qps, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
                    'single_thread': {'value': qps1, 'cores': 1, 'median_s_per_pass': med1},
                    'sample': 'first %d questions of the GPU batch, %d passes, median %.3f s/pass, torch threads=%d; oracle port with the '
                              'encoders through torch.nn.LSTM' % (CPU_SAMPLE, npass, med, torch.get_num_threads())}
-            ref_ans = ref_logits.argmax(1)
-            top2 = ref_logits.topk(2, dim=1).values
-            margin = (top2[:, 0] - top2[:, 1])
-            clear = margin > 2 * (3e-2 * ref_logits.abs().max(1).values + 2e-3)
-            got = answers_dev[:CPU_SAMPLE].long()
-            # strict mode on the same questions: answers must be bit-identical
-            strict = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
-            strict.load_state_dict(weights)
-            strict = strict.to(dev).eval()
-            s_out = strict(qs[:CPU_SAMPLE], return_res_by_step=False, test_mode=True)
-            s_ans = s_out['answers'].cpu().long()
-            parity = {'questions': CPU_SAMPLE, 'fp32_strict_answers_equal': int((s_ans == ref_ans).sum()),
-                      'fp32_strict_max_logit_err': float((s_out['logits'].cpu() - ref_logits).abs().max()),
-                      'bf16_answers_equal': int((got == ref_ans).sum()), 'bf16_clear_margin': int(clear.sum()),
-                      'bf16_answers_equal_where_margin_clear': int(((got == ref_ans) & clear).sum())}
+        n_check = B if world == 1 else min(B, PARITY_PER_RANK_MULTI)
+        mine = parity_report(model, strict_model if world == 1 else None, qs[:n_check], weights, cfg, answers_dev, logits_dev,
+                             threads=max(1, ncpu // world))
+        if world > 1:
+            keys = [k for k, v in mine.items() if isinstance(v, int) and not isinstance(v, bool)]
+            sums = torch.tensor([mine[k] for k in keys], device=dev, dtype=torch.int64)
+            dist.all_reduce(sums)
+            mx = torch.tensor([mine['bf16_mismatch_max_margin_rel'], mine['bf16_logit_err_rel_max'], mine['localize_mismatch_max_margin'],
+                               mine['oracle_seconds']], device=dev)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            ok = torch.tensor([1 if gathered_ok else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            parity = dict(mine)
+            parity.update({k: int(v) for k, v in zip(keys, sums.tolist())})
+            parity.update({'bf16_mismatch_max_margin_rel': float(mx[0]), 'bf16_logit_err_rel_max': float(mx[1]),
+                           'localize_mismatch_max_margin': float(mx[2]), 'oracle_seconds': float(mx[3]),
+                           'ranks': world, 'per_rank': n_check, 'gathered_answers_are_each_ranks_answers': bool(int(ok.item())),
+                           'what': 'every rank checks the first %d questions of ITS shard (answers as gathered) against the CPU oracle; '
+                                   'counts summed over ranks (medians / p99 are rank 0\'s)' % n_check})
+        else:
+            parity = mine
+
+    if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
                 'data': 'synthetic',
-                'config': {'workload': ('ModuleNet batched inference, %d mixed-program questions per GPU (10 AGQA layout templates, 2-12 modules), '
-                                        'RX/TGIF-QA features [8,4096] bf16, questions 8-24 words x 300, random init, bf16 storage / fp32 accumulate'
-                                        % B) if args.workload == 'rx' else
-                                       ('I3D stress test (BASELINE configs[4]): %d questions per GPU, compare / xor_between layouts (9-12 modules), '
-                                        'features [64,1024] bf16, conv-mode Temporal, random init, bf16 storage / fp32 accumulate' % B), 'questions_per_gpu': B, 'global_questions': world * B, 'frames': T, 'video_size': V,
+                'config': {'workload': workload_string(args, B) + ', bf16 storage / fp32 accumulate', 'questions_per_gpu': B,
+                           'global_questions': world * B, 'frames': T, 'video_size': V,
                            'hidden_size': cfg['hidden_size'], 'parallelism': 'question-sharded x%d, answers all-gathered (NCCL)' % world,
                            'l2': 'inputs larger than L2 (video %.0f MB per step)' % (B * T * V * 2 / 1e6)},
                 'clocks': clock_info,
@@ -464,11 +639,13 @@ def main():
                         'ms_per_step': 1e3 * e2e_s / args.steps,
                         'per_call': {'value': world * B * args.steps / percall_s, 'ms_per_step': 1e3 * percall_s / args.steps,
                                      'what': 'forward_pipelined(host chunks) + answers.cpu() per step, synchronising every step'},
+                        'from_dicts': from_dicts,
                         'host_numa_binding': numa,
                         'timer': 'wall clock between synchronize()s over all steps; VideoNMN.forward_stream: every step uploads its pinned host batch '
                                  '(%d chunks, copy stream) and reads its answers back (async D2H into pinned memory), 2 steps in flight' % E2E_CHUNKS},
-                'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
-                'roofline': roofline, 'phases_ms': ph_ms, 'audit': audit, 'train': train, 'cpu_baseline': cpu, 'parity': parity}
+                'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step, 'host_enqueue_ms': host_enqueue_ms,
+                'roofline': roofline, 'roofline_hbm': roofline_hbm, 'phases_ms': ph_ms, 'strict': strict, 'audit': audit, 'i3d': i3d, 'train': train,
+                'cpu_baseline': cpu, 'parity': parity}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

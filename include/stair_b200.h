@@ -315,6 +315,13 @@ int stair_ingest_pool_concat(const void* appearance, const void* motion, int in_
 /* I3D npy features: out[b,t,:] = feats[b, t*step, :] for t < T (dataset.py:138-141: every 2nd row, then [:max_video_length]) */
 int stair_ingest_subsample(const void* feats, int in_dtype, void* out, int out_dtype, int B, int n_frames, int T, int D, int step, void* stream);
 
+/* ---- host-side collate staging (NO GPU work; video_nmn/dataset.py:463-476 collate_fn / to_device) -------------
+ * dst rows [dst_row[i], dst_row[i] + rows[i]) <- src[i] (rows[i] x cols elements, contiguous HOST memory), converting src_dtype -> dst_dtype
+ * (fp32 -> bf16 is round-to-nearest-even, bit-identical to torch's conversion for every non-NaN value; NaN stays NaN); dst is HOST (pinned) row-major with pitch `cols`.
+ * One call stages a whole batch with `threads` host threads (<= 0: all, at most 32) instead of one torch copy per question. */
+int stair_host_collate_rows(const void* const* src /*HOST*/, const long long* rows /*HOST*/, const long long* dst_row /*HOST*/, int n, long long cols,
+                            int src_dtype, void* dst /*HOST*/, int dst_dtype, int threads);
+
 /* ---- Filter-audit head, the step right after the path (evaluate.py:65-117) ----------------------
  * out_idx[i, 0..k) = indices of the k phrase representations (reps fp32 [P, H]) most cosine-similar to query row i (row
  * row_idx[i] of q, or row i when row_idx is NULL; pitch ldq elements of `dtype`), out_sim the similarities, descending

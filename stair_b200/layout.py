@@ -11,9 +11,6 @@ dimensions are known without a device->host sync.
 """
 from __future__ import annotations
 
-import os
-from concurrent.futures import ThreadPoolExecutor
-
 import numpy as np
 import torch
 
@@ -343,26 +340,31 @@ class NMNBatch:
         return self.itab_host[o:o + size]
 
 
-def _copy_rows(pairs, min_parallel=256):
-    """dst.copy_(src) for every (dst, src) pair — dtype-converting row copies of one batch (fp32 dataset tensors -> bf16 pinned
-    staging).  Each copy is too small for ATen's intra-op parallelism (131 KB at RX), so large batches are spread over a few host
-    threads; ``copy_`` releases the GIL while it converts.  Measured in the build container (8 vCPUs): 4096 RX questions
-    0.43 s -> 0.33-0.37 s per collate; the per-call dispatch, which holds the GIL, is the rest.  Real pipelines collate in DataLoader
-    workers (INTEGRATION.md)."""
-    n = len(pairs)
-    workers = min(8, os.cpu_count() or 1)
-    if n < min_parallel or workers < 2:
-        for dst, src in pairs:
-            dst.copy_(src)
+def _stage_rows(dst, srcs, row_off):
+    """dst[row_off[i] : row_off[i] + srcs[i].shape[0]] <- srcs[i] for a whole batch (dtype-converting row copies of the dataset's fp32
+    tensors into the — usually pinned, usually bf16 — staging buffer).  One native call (``stair_host_collate_rows``, csrc/host_collate.cu:
+    a small host thread pool, no GPU work) instead of one torch copy per question: 4096 RX questions 0.35-0.45 s -> ~0.03 s.
+    Sources that are not contiguous CPU fp32 / bf16 tensors take the per-tensor torch copy."""
+    n = len(srcs)
+    if n == 0:
         return
-    step = (n + workers - 1) // workers
-
-    def work(lo):
-        for dst, src in pairs[lo:lo + step]:
-            dst.copy_(src)
-
-    with ThreadPoolExecutor(workers) as ex:
-        list(ex.map(work, range(0, n, step)))
+    cols = int(dst.shape[-1]) if dst.dim() > 1 else 1
+    width = dst[0].numel() if dst.dim() > 1 else 1                   # elements per dst row (trailing dims flattened)
+    ok = dst.is_contiguous() and dst.device.type == 'cpu' and dst.dtype in (torch.float32, torch.bfloat16)
+    if ok:
+        sd = srcs[0].dtype
+        ok = sd in (torch.float32, torch.bfloat16) and all(t.dtype == sd and t.device.type == 'cpu' and t.is_contiguous() for t in srcs)
+    if not ok or n < 16:
+        for t, r in zip(srcs, row_off):
+            dst[r:r + t.shape[0]].copy_(t)
+        return
+    import ctypes
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+    rows = (ctypes.c_longlong * n)(*[int(t.shape[0]) for t in srcs])
+    offs = (ctypes.c_longlong * n)(*[int(r) for r in row_off])
+    del cols
+    L.check(L.lib().stair_host_collate_rows(ptrs, rows, offs, L.i32(n), ctypes.c_longlong(width), L.i32(L.dtype_code(sd)), L.vp(dst.data_ptr()),
+                                            L.i32(L.dtype_code(dst.dtype)), L.i32(0)), 'stair_host_collate_rows')
 
 
 def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, merge_waves=True) -> NMNBatch:
@@ -410,7 +412,7 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
         b.T, b.V = T, V
         vdt = video_dtype or v0.dtype
         video = torch.empty((B, T, V), dtype=vdt, pin_memory=pin_memory)
-        _copy_rows([(video[i], e['video_features']) for i, e in enumerate(examples)])
+        _stage_rows(video.view(B * T, V), [e['video_features'] for e in examples], [i * T for i in range(B)])
         b.video = video
         b.video_dtype = vdt
     lens = np.array([int(e['question'].shape[0]) for e in examples], np.int64)
@@ -420,7 +422,7 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
     text = int(examples[0]['question'].shape[1])
     qdt = question_dtype or examples[0]['question'].dtype
     question = torch.empty((b.n_tok, text), dtype=qdt, pin_memory=pin_memory)
-    _copy_rows([(question[q_off[i]:q_off[i + 1]], e['question']) for i, e in enumerate(examples)])
+    _stage_rows(question, [e['question'] for e in examples], q_off[:-1].tolist())
     b.question = question
     b.text_size = text
 

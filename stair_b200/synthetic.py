@@ -109,6 +109,23 @@ EXTRA_TEMPLATES = {
 
 ALL_TEMPLATES = {**TEMPLATES, **EXTRA_TEMPLATES}
 
+# Long layouts for the I3D stress configuration (BASELINE.json configs[4]: "long program layouts (>= 12 modules)").  Not part of the golden
+# fixtures: `xor_between` (12 module calls) is the longest AGQA template above; these two chain the same AGQA sub-programs further.
+STRESS_TEMPLATES = {
+    'and_between_until': (          # 15 module calls
+        None,
+        ['And', 'Exists', 'food', 'Filter', 'Temporal', 'between', 'video', 'Localize', 'video', 'Array2', 'A', 'B', 'holding',
+         'Exists', 'Filter', 'AttnVideo', 'video', 'Relate', 'forward', 'HasItem', 'FilterFrame', 'video', 'taking', 'opening',
+         'Filter', 'Temporal', 'after', 'video', 'Localize', 'video', 'C', 'holding'],
+        list(range(32))),
+    'compare_between': (            # 12 module calls
+        None,
+        ['Compare', 'Exists', 'dish', 'Filter', 'Temporal', 'between', 'video', 'Localize', 'video', 'Array2', 'A', 'B', 'actions',
+         'Exists', 'Filter', 'video', 'cup', 'Filter', 'Temporal', 'before', 'video', 'Localize', 'video', 'Array2', 'C', 'D', 'relations'],
+        list(range(27))),
+}
+LONG_TEMPLATES = ['xor_between', 'and_between_until', 'compare_between']       # every layout has >= 12 module calls
+
 # arity table (utils/program_parser.py:16-23) restricted to the tokens the interpreter dispatches on.
 MODULE_ARITY = {
     'And': 2, 'AttnVideo': 2, 'Choose': 3, 'Compare': 2, 'Equals': 2, 'Exists': 2, 'ExistsFrame': 2, 'Filter': 2,
@@ -130,7 +147,7 @@ def make_question(rng: np.random.Generator, template: str, T: int, V: int, text_
                   answer_vocab: int = 172, with_gold: bool = False, object_types: int = 256,
                   qa_id: str | None = None):
     """One reference-schema ``data`` dict (CPU fp32 tensors)."""
-    _, tokens, idx_list = ALL_TEMPLATES[template]
+    _, tokens, idx_list = (ALL_TEMPLATES.get(template) or STRESS_TEMPLATES[template])
     L = int(rng.integers(8, 25))
     question = torch.from_numpy((rng.standard_normal((L, text_size)) * 0.4).astype(np.float32))
     video = torch.from_numpy(np.abs(rng.standard_normal((T, V))).astype(np.float32))

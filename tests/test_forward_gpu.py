@@ -3,8 +3,18 @@ unmodified reference, and against the CPU oracle on fresh seeded inputs.
 
 Bars (north star): layout grouping, argmax answers and attention argmax indices bit-exact; floating-point maps /
 logits within a stated tolerance:
-  * precision='fp32' (strict: fp32 storage, bf16x3 split contractions, fp32 accumulate): rtol 2e-4, atol 2e-5
-  * precision='bf16' (fast path: bf16 storage, fp32 accumulate): |err| <= 3e-2 * max|ref| + 2e-3 per tensor
+  * precision='fp32' (strict: fp32 storage, bf16x3 split contractions, fp32 accumulate): rtol 2e-4, atol 2e-5; every answer and every
+    attention argmax bit-identical.
+  * precision='bf16' (fast path: bf16 storage, fp32 accumulate).  Bars set from the measured full-size error (H = 512, 512 questions over
+    all 17 layouts, RX and I3D; profiles/measure_bf16_error.py -> profiles/r2_bf16_error_measured.txt), each <= 3x what was measured:
+      - every intermediate / logit tensor: |err| <= 3e-2 * max|ref| + 2e-3 (measured worst: 2.8e-2 * max|ref| on AttnVideo, i.e. 0.75 of
+        the bar; logits median 2.7e-3 * max|logit|);
+      - answers: bit-identical wherever the reference's top-2 logit margin exceeds 1e-2 * max|logit| (measured: 1018 / 1024 answers equal;
+        the 6 that differ have margins <= 3.3e-3 * max|logit| — random-init logits are near-ties), and >= 97 % equal overall;
+      - attention argmax: bit-identical wherever the reference's top-2 margin exceeds 6e-4 (maps live in [0, 0.98]; measured: 1966 / 1988
+        equal, the others have margins <= 2.2e-4);
+      - Choose (a discontinuous select on cos(k1, q) > cos(k2, q), modules.py:52): when the reference's two cosines are closer than
+        1e-2 the bf16 path may legitimately pick the other operand; such questions are excluded from the downstream comparisons.
 """
 import numpy as np
 import pytest
@@ -33,12 +43,18 @@ def _close(got, want, precision, what):
         assert err <= BF16_REL * scale + BF16_ABS, '%s: max err %g vs scale %g' % (what, err, scale)
 
 
-def _margin_ok(t, dim=-1):
-    """top-2 margin of a reference tensor along dim (argmax comparisons are only meaningful above the tolerance)."""
+ANSWER_MARGIN_REL = 1e-2       # x max|logit| of the question
+ATT_MARGIN_ABS = 6e-4
+
+
+def _margin_ok(t, dim=-1, logits=False):
+    """Where is the reference's argmax decided by more than the measured bf16 error?  (top-2 margin along dim)"""
     if t.size(dim) < 2:
         return torch.ones(t.shape[:-1], dtype=torch.bool)
     top = t.float().topk(2, dim=dim).values
-    return (top[..., 0] - top[..., 1]) > 2 * (BF16_REL * max(float(t.abs().max()), 1e-3) + BF16_ABS)
+    if logits:
+        return (top[..., 0] - top[..., 1]) > ANSWER_MARGIN_REL * t.float().abs().amax(dim)
+    return (top[..., 0] - top[..., 1]) > ATT_MARGIN_ABS
 
 
 def _model(cfg, weights, pretrain, precision):
@@ -63,7 +79,7 @@ def test_golden_every_intermediate(fx, precision):
     for qi, (data, ref, q) in enumerate(questions):
         name = q['template']
         _close(out['logits'][qi], ref['logits'], precision, '%s logits' % name)
-        if precision == 'fp32' or bool(_margin_ok(ref['logits'])):
+        if precision == 'fp32' or bool(_margin_ok(ref['logits'], logits=True)):
             assert int(out['answers'][qi]) == int(ref['logits'].argmax()), '%s answer' % name
         steps = out['result_of_each_step'][qi]
         assert len(steps) == len(ref['steps'])
@@ -123,16 +139,34 @@ def test_device_grouping_is_bit_exact(fx):
             assert lay.level[nd] == lv[lay.token_of_node[nd]]
 
 
+def _choose_flippable(oracle, data):
+    """True when the question's layout has a Choose whose two cosines (modules.py:52) the reference separates by < 1e-2: the bf16 path
+    may then select the other keyword, and everything downstream of it differs by construction."""
+    toks = data['nmn_program_list']
+    if 'Choose' not in toks:
+        return False
+    with torch.no_grad():
+        out = oracle(data, return_res_by_step=False, return_result_of_each_step=True, test_mode=True)
+    for i, t in enumerate(toks):
+        if t == 'Choose':
+            k1, k2, q = out['result_of_each_step'][i][0]
+            if abs(float(orc._cos(k1, q)) - float(orc._cos(k2, q))) < 1e-2:
+                return True
+    return False
+
+
 @pytest.mark.parametrize('shape', ['rx', 'i3d'])
 def test_full_size_against_oracle(shape):
-    """Config-1 sized check at the real dimensions (H=512): 32 questions over all 16 layouts vs the CPU oracle."""
+    """Config-1 sized check at the real dimensions (H=512): 136 questions (8 x all 17 layouts) vs the CPU oracle, every intermediate,
+    every answer, every attention argmax (bars: module docstring)."""
     T, V = (8, 4096) if shape == 'rx' else (64, 1024)
     cfg = syn.model_config(T=T, V=V)
     torch.manual_seed(0)
     ref_model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
     weights = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
-    oracle = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES)
-    qs = syn.make_questions(32, T, V, seed=99, templates=list(syn.ALL_TEMPLATES))
+    oracle = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES, aten_lstm=True)
+    n = 136
+    qs = syn.make_questions(n, T, V, seed=99, templates=list(syn.ALL_TEMPLATES))
     with torch.no_grad():
         want = [oracle(d, return_res_by_step=False, return_result_of_each_step=True, test_mode=True) for d in qs]
     for precision in ('fp32', 'bf16'):
@@ -141,18 +175,31 @@ def test_full_size_against_oracle(shape):
         model = model.cuda().eval()
         out = model(qs, return_res_by_step=False, return_result_of_each_step=True, test_mode=True)
         torch.cuda.synchronize()
-        n_checked = 0
+        n_checked = n_equal = n_att = 0
         for qi, w in enumerate(want):
+            equal = int(out['answers'][qi]) == int(w['logits'].argmax())
+            n_equal += equal
+            if precision == 'bf16' and _choose_flippable(oracle, qs[qi]):
+                continue
             _close(out['logits'][qi], w['logits'], precision, 'q%d logits' % qi)
-            if precision == 'fp32' or bool(_margin_ok(w['logits'])):
-                assert int(out['answers'][qi]) == int(w['logits'].argmax())
+            if precision == 'fp32' or bool(_margin_ok(w['logits'], logits=True)):
+                assert equal, 'q%d (%s) answer' % (qi, qs[qi]['template'])
                 n_checked += 1
             for j, ((_, got), (_, exp)) in enumerate(zip(out['result_of_each_step'][qi], w['result_of_each_step'])):
                 if isinstance(exp, str):
                     assert got == exp
-                else:
-                    _close(got, exp, precision, 'q%d step %d %s' % (qi, j, qs[qi]['nmn_program_list'][j]))
-        assert n_checked >= (32 if precision == 'fp32' else 1)
+                    continue
+                _close(got, exp, precision, 'q%d step %d %s' % (qi, j, qs[qi]['nmn_program_list'][j]))
+                if exp.dim() >= 1 and exp.size(-1) == T and exp.numel() <= 2 * T:       # attention maps: argmax index
+                    ok = _margin_ok(exp) if precision == 'bf16' else torch.ones(exp.shape[:-1], dtype=torch.bool)
+                    assert torch.equal(got.float().cpu().argmax(-1)[ok], exp.argmax(-1)[ok]), 'q%d step %d attention argmax' % (qi, j)
+                    n_att += int(ok.sum())
+        if precision == 'fp32':
+            assert n_checked == n and n_equal == n
+        else:
+            assert n_checked >= 0.3 * n, 'only %d of %d answers have a clear reference margin' % (n_checked, n)
+            assert n_equal >= 0.97 * n, 'only %d of %d bf16 answers equal the reference' % (n_equal, n)
+        assert n_att >= 0.8 * sum(t in ('Localize', 'ExistsFrame', 'HasItem', 'Relate') for d in qs for t in d['nmn_program_list'])
 
 
 @pytest.mark.parametrize('hidden,T', [(128, 8), (256, 16), (512, 8), (512, 64)])

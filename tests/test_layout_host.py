@@ -169,3 +169,27 @@ def test_wave_schedule_respects_dependencies_and_merges_groups():
     m, p = LY.collate(qs), LY.collate(qs, merge_waves=False)
     assert m.n_groups < p.n_groups and m.n_nodes == p.n_nodes
     assert np.array_equal(m.host_tab('node_q').numpy(), p.host_tab('node_q').numpy())
+
+
+def test_native_collate_staging_is_bit_identical_to_torch():
+    """stair_host_collate_rows (csrc/host_collate.cu, host threads, no GPU): the dtype-converting row copies of a whole batch == one torch
+    copy per question (video_nmn/dataset.py:463-476 collate_fn / to_device staging), for every non-NaN fp32 bit pattern."""
+    g = torch.Generator().manual_seed(0)
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (64, 1000), generator=g, dtype=torch.int64).to(torch.int32).view(torch.float32)
+    bits[0, :6] = torch.tensor([float('inf'), -float('inf'), -0.0, 1e-40, 3.4e38, -3.4e38])
+    d = torch.empty(64, 1000, dtype=torch.bfloat16)
+    LY._stage_rows(d, [bits[i:i + 1].contiguous() for i in range(64)], list(range(64)))
+    want = bits.to(torch.bfloat16)
+    ok = ~torch.isnan(bits)
+    assert torch.equal(d.view(torch.int16)[ok], want.view(torch.int16)[ok])
+    assert bool(torch.isnan(d.float()[~ok]).all())
+    back = torch.empty(64, 1000, dtype=torch.float32)
+    LY._stage_rows(back, [d[i:i + 1].contiguous() for i in range(64)], list(range(64)))
+    assert torch.equal(back.view(torch.int32)[ok], d.float().view(torch.int32)[ok])
+    # ragged rows at arbitrary offsets, and through collate itself
+    qs = syn.make_questions(40, 8, 32, seed=3, templates=list(syn.ALL_TEMPLATES))
+    b = LY.collate(qs, video_dtype=torch.bfloat16, question_dtype=torch.bfloat16)
+    assert torch.equal(b.video, torch.stack([q['video_features'] for q in qs]).to(torch.bfloat16))
+    assert torch.equal(b.question, torch.cat([q['question'] for q in qs]).to(torch.bfloat16))
+    b32 = LY.collate(qs)
+    assert torch.equal(b32.video, torch.stack([q['video_features'] for q in qs])) and b32.video.dtype == torch.float32
