@@ -82,3 +82,22 @@ def test_ingest_feeds_the_model():
     torch.cuda.synchronize()
     assert float((a['logits'] - b['logits']).abs().max()) <= 2e-5 * float(a['logits'].abs().max())
     assert torch.equal(a['answers'], b['answers'])
+
+
+def test_npy_directory_reader_on_the_device_equals_the_host_reader(tmp_path):
+    """stair_b200.agqa_data: the I3D npy reader (dataset.py:134-143) with the stride-2 / truncate reduction on the GPU
+    (stair_ingest_subsample) == the host reader, for files of several lengths."""
+    from stair_b200 import agqa_data as AD
+    rng = np.random.default_rng(1)
+    ids = []
+    for i, n in enumerate((130, 130, 40, 7, 200)):
+        vid = 'v%d' % i
+        ids.append(vid)
+        np.save(tmp_path / (vid + '.npy'), rng.standard_normal((n, 1024)).astype(np.float32))
+    host = AD.load_npy_features(str(tmp_path), ids, 64)
+    dev = AD.load_npy_features_device(str(tmp_path), ids, 64, out_dtype=torch.float32)
+    assert set(host) == set(dev)
+    for k in host:
+        assert torch.equal(dev[k].cpu(), host[k])
+    dev16 = AD.load_npy_features_device(str(tmp_path), ids[:2], 64)
+    assert dev16['v0'].dtype == torch.bfloat16 and torch.equal(dev16['v0'].cpu(), host['v0'].to(torch.bfloat16))
