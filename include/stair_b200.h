@@ -9,6 +9,16 @@
  * allocates device memory or synchronises — the caller (PyTorch's caching allocator) owns every buffer and all
  * work is enqueued on the `stream` argument (a cudaStream_t passed as void*).  Pointers are device pointers
  * unless marked HOST, and must be 16-byte aligned.  sm_100a only; there is no CPU or library fallback.
+ *
+ * What the library itself owns (and nothing else): per calling thread, 7 non-blocking side streams + 8 events on which the independent
+ * module groups of a schedule wave run concurrently (forked from and joined back into `stream`, so a call stays stream-ordered for the
+ * caller), and one pinned host int that device-side protocol time-outs report into (stair_gemm_error_flag).  stair_init() creates them
+ * for the calling thread on the current device (otherwise the first forward of the thread does), stair_shutdown() synchronises the
+ * device and destroys them.  One process (thread) per GPU is the intended use; a thread that changes its current device must call
+ * stair_shutdown() / stair_init() around the change.
+ * The stair_set_* switches below are PROCESS-GLOBAL tuning / comparison knobs read at launch time (defaults = the product path; tests and
+ * the profiles/ scripts flip them around single calls): two models in one process share them, they are not part of a model's state.
+ * Entry points are re-entrant given distinct buffers; stair_last_launch_count is per thread.
  */
 #ifndef STAIR_B200_H
 #define STAIR_B200_H
@@ -20,7 +30,7 @@
 extern "C" {
 #endif
 
-#define STAIR_ABI_VERSION 5
+#define STAIR_ABI_VERSION 6
 
 /* status codes */
 #define STAIR_OK 0
@@ -206,6 +216,8 @@ typedef struct StairTrain {
  * elements (row0 + r, c), r < rows, c < cols: keep[r*cols + c] = 1 if kept.  Restated in oracle/nmn_oracle.py dropout_keep. */
 int stair_dropout_mask_host(float p, unsigned long long seed, int site, long long row0, int rows, int cols, unsigned char* keep);
 int stair_version(void);
+int stair_init(void);        /* create the calling thread's lane streams / events and the pinned error word now (idempotent) */
+int stair_shutdown(void);    /* cudaDeviceSynchronize, then destroy them (a later call re-creates them lazily) */
 /* sizeof() of the ABI structs as compiled (0 StairModel, 1 StairGroup, 2 StairBatch, 3 StairBuffers, 4 StairItabLayout, 5 StairTrain):
  * 6 StairAdamSeg; lets a binding verify its mirror of the struct layouts. */
 int64_t stair_sizeof(int which);

@@ -404,8 +404,21 @@ inline long long group_cost(const StairGroup& g, int T) {
 }
 
 struct LaneStreams { cudaStream_t side[LANES - 1]; cudaEvent_t fork, join[LANES - 1]; bool ok = false; };
-inline LaneStreams* lane_streams() {
+// The only CUDA objects the library owns: per calling thread, LANES - 1 side streams + LANES events used to run the independent groups of
+// a schedule wave concurrently.  Created by stair_init() (or lazily by the first forward of a thread), destroyed by stair_shutdown().
+inline LaneStreams& lane_state() {
     static thread_local LaneStreams ls;
+    return ls;
+}
+inline void lane_streams_destroy() {
+    LaneStreams& ls = lane_state();
+    if (!ls.ok) return;
+    for (int l = 0; l < LANES - 1; ++l) { cudaStreamDestroy(ls.side[l]); cudaEventDestroy(ls.join[l]); }
+    cudaEventDestroy(ls.fork);
+    ls.ok = false;
+}
+inline LaneStreams* lane_streams() {
+    LaneStreams& ls = lane_state();
     if (!ls.ok) {
         for (int l = 0; l < LANES - 1; ++l) {
             if (cudaStreamCreateWithFlags(&ls.side[l], cudaStreamNonBlocking) != cudaSuccess) return nullptr;

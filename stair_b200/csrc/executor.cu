@@ -24,6 +24,17 @@ using namespace stair::ex;
 extern "C" int stair_set_lstm_impl(int impl) { g_lstm_impl = impl; return STAIR_OK; }
 extern "C" int stair_set_lanes(int lanes) { g_lanes = lanes < 1 ? 1 : (lanes > LANES ? LANES : lanes); return STAIR_OK; }
 extern "C" int stair_version(void) { return STAIR_ABI_VERSION; }
+// explicit ownership of the library's few runtime objects (see include/stair_b200.h "Conventions")
+extern "C" int stair_init(void) {
+    if (!lane_streams() || !err_flag_ptr()) return STAIR_ERR_CUDA;
+    return STAIR_OK;
+}
+extern "C" int stair_shutdown(void) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return STAIR_ERR_CUDA;
+    lane_streams_destroy();
+    err_flag_free();
+    return STAIR_OK;
+}
 extern "C" int64_t stair_sizeof(int which) {
     switch (which) {
     case 0: return sizeof(StairModel);

@@ -658,6 +658,10 @@ static int g_wide_tiles_min = 1;  // 128 x 256 tiles when there are more than th
 static int g_split_k = 1;        // 1 = split-K for accumulating GEMMs with few output tiles (weight gradients)
 static unsigned long long* g_dbg = nullptr;
 
+void err_flag_free() {
+    if (g_err_flag) { cudaFreeHost(g_err_flag); g_err_flag = nullptr; }
+}
+
 int* err_flag_ptr() {
     if (!g_err_flag) {
         if (cudaMallocHost(reinterpret_cast<void**>(&g_err_flag), sizeof(int)) != cudaSuccess) return nullptr;   // pinned, device-visible

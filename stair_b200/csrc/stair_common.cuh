@@ -173,6 +173,7 @@ struct GemmArgs {
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
 int* err_flag_ptr();      // pinned host word that device-side protocol timeouts write their code to (stair_gemm_error_flag)
+void err_flag_free();
 // true when the TMA slot-gather path can serve this (slot_rows, K) without a staging copy
 static inline bool gemm_gather_ok(int slot_rows) { return slot_rows >= 8 && slot_rows <= 128 && (128 % slot_rows) == 0; }
 

@@ -126,3 +126,21 @@ def test_returned_intermediates_survive_later_forwards():
             assert torch.equal(v[1], kept[k])
     with pytest.raises(L.StairError):
         OutputViews(model, first['state'], frozenset())
+
+
+def test_explicit_init_and_shutdown_of_the_library_runtime_objects():
+    """include/stair_b200.h "Conventions": the lane streams / events / pinned error word are the only objects the library owns;
+    stair_init() creates them, stair_shutdown() destroys them, and a later forward re-creates them lazily with identical results."""
+    from stair_b200 import _lib as L
+    lib = L.lib()
+    T, V, hid = 8, 128, 64
+    cfg = syn.model_config(T=T, V=V, hidden=hid, object_types=16)
+    torch.manual_seed(2)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().eval()
+    qs = syn.make_questions(200, T, V, seed=11, templates=list(syn.ALL_TEMPLATES), object_types=16)
+    assert lib.stair_init() == 0 and lib.stair_init() == 0                 # idempotent
+    a = model(qs, return_res_by_step=False, test_mode=True)['logits'].clone()
+    assert lib.stair_shutdown() == 0
+    b = model(qs, return_res_by_step=False, test_mode=True)['logits'].clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and lib.stair_gemm_error_flag() == 0
