@@ -17,7 +17,7 @@ inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a
 
 struct Plan {
     // encoder phase
-    long long xv_in, xv, xq_in, xq, g, c, hs;
+    long long xv_in, xv, xq_in, xq, g, c, hs, hx;
     // module / decoder phase (aliases the encoder regions; everything is stream-ordered)
     long long s0, s1, s2, pl, vp, v01, ats, a0;
     long long total;
@@ -50,6 +50,7 @@ inline void make_plan(const StairModel& m, const StairBatch& b, Plan* p) {
     p->g = take(2 * B * 4 * h * 4);
     p->c = take(2 * 2 * ((B + 127) / 128 * 128) * h * 4);     // video + text cell states (the fused kernel runs both encoders at once)
     p->hs = take(np * 2 * B * h * 2);
+    p->hx = take(lstm_ws_ok(m.precision, static_cast<int>(h), static_cast<int>(B)) ? 2 * lstm_ws_hx_bytes(static_cast<int>(B)) : 0);   // h exchange of the weight-stationary recurrence (video | text)
     const long long enc_total = o;
     // module regions
     o = 0;
@@ -183,8 +184,15 @@ inline int run_encoders(Ctx& c, int phases) {
         STAIR_TRY(launch_lstm_cell_video(c.adt, c.at<void>(c.plan.xv), g, cs, hs, c.np, c.adt, c.buf.vid, B, T, h, s, c.st));
     }
     }
+    // weight-stationary cluster recurrence (lstm_ws.cu) when eligible (h = 256): one launch per encoder, W_hh resident in shared memory
+    const bool ws = fused && lstm_ws_ok(m.precision, h, B);
+    const long long nblk128 = (B + 127) / 128;
+    char* hx = c.at<char>(c.plan.hx);
+    if (ws && (phases & STAIR_FWD_ENCODE_VIDEO))
+        STAIR_TRY(launch_lstm_ws(c.at<void>(c.plan.xv), c.buf.vid, nullptr, nullptr, T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R), cs, hx,
+                                 B, h, err_flag_ptr(), c.st));
     if (!(phases & STAIR_FWD_ENCODE_TEXT)) {
-        if (fused && (phases & STAIR_FWD_ENCODE_VIDEO))
+        if (fused && !ws && (phases & STAIR_FWD_ENCODE_VIDEO))
             return launch_lstm_fused(c.at<void>(c.plan.xv), c.buf.vid, T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R), nullptr,
                                      nullptr, nullptr, nullptr, 0, nullptr, nullptr, cs, B, h, 1, 0, err_flag_ptr(), c.st);
         return STAIR_OK;
@@ -200,6 +208,9 @@ inline int run_encoders(Ctx& c, int phases) {
         a.M = b.n_tok; a.N = 4 * H; a.K = m.text_size;
         STAIR_TRY(launch_gemm(a, c.st));
     }
+    if (ws)
+        return launch_lstm_ws(c.at<void>(c.plan.xq), c.buf.tokfeat, c.buf.qfeat, b.q_off, b.L_max, c.W(STAIR_W_TENC_WHHI_F), c.W(STAIR_W_TENC_WHHI_R),
+                              cs + 2 * nblk128 * 128 * h, hx + lstm_ws_hx_bytes(B), B, h, err_flag_ptr(), c.st);
     if (fused)
         return launch_lstm_fused(c.at<void>(c.plan.xv), c.buf.vid, T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R),
                                  c.at<void>(c.plan.xq), c.buf.tokfeat, c.buf.qfeat, b.q_off, b.L_max, c.W(STAIR_W_TENC_WHHI_F),

@@ -398,6 +398,17 @@ int run_encoders_train(Ctx& c, const StairTrain& tr) {
                                              c.T, h, s, c.st));
         }
     }
+    if (fused && lstm_ws_ok(m.precision, h, B)) {
+        // weight-stationary cluster recurrence (lstm_ws.cu), one launch per encoder, writing the same BPTT history
+        float* cs = c.at<float>(c.plan.c);
+        char* hx = c.at<char>(c.plan.hx);
+        const long long nblk128 = (B + 127) / 128;
+        STAIR_TRY(launch_lstm_ws(c.at<void>(c.plan.xv), c.buf.vid, nullptr, nullptr, c.T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R), cs, hx,
+                                 B, h, err_flag_ptr(), c.st, reinterpret_cast<bf16*>(hist.gates[0]), hist.hs[0]));
+        return launch_lstm_ws(c.at<void>(c.plan.xq), c.buf.tokfeat, c.buf.qfeat, bt.q_off, bt.L_max, c.W(STAIR_W_TENC_WHHI_F), c.W(STAIR_W_TENC_WHHI_R),
+                              cs + 2 * nblk128 * 128 * h, hx + lstm_ws_hx_bytes(B), B, h, err_flag_ptr(), c.st, reinterpret_cast<bf16*>(hist.gates[1]),
+                              hist.hs[1]);
+    }
     if (fused)
         return launch_lstm_fused(c.at<void>(c.plan.xv), c.buf.vid, c.T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R),
                                  c.at<void>(c.plan.xq), c.buf.tokfeat, c.buf.qfeat, bt.q_off, bt.L_max, c.W(STAIR_W_TENC_WHHI_F),

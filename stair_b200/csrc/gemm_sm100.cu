@@ -421,7 +421,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   tmem_empty[a] in the LEADER, count 2 x 4 EPI: one arrive per epilogue warp of either CTA (remote arrive for the peer)
 // Setup / teardown are cluster-synchronised: barriers are initialised before any remote arrive, TMEM (cta_group::2 alloc, issued by
 // warp 2 of both CTAs) is released only after both CTAs are done.
-// Restrictions: K-major operands, no gather, no accumulate / split-K, N % 256 == 0 (the launcher falls back to the single-CTA kernel).
+// Operands: K-major (every forward / dX GEMM) or MN-major (mn_major: the weight-gradient contraction dW = dZ^T . X read in place, 3-D TMA
+// boxes of 64 k-rows x 64 columns, MN-major UMMA descriptors), optionally split over K (work item = (tile, K range); partial tiles are
+// added with vector atomics by the direct-store epilogue).  Restrictions: no gather, N % 256 == 0 (the launcher falls back otherwise).
 // ------------------------------------------------------------------------------------------------
 template <int STAGES, int EPI>
 struct GemmSmem2 {
@@ -460,12 +462,13 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int tiles_n = p.N / BN;
     const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
-    const int total_tiles = tiles_m * tiles_n;
+    const int mn_tiles = tiles_m * tiles_n;
+    const int total_tiles = mn_tiles * p.ksplit;                    // work item = (output tile, K split)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+        if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * 4 * EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -485,17 +488,28 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             // ===================== TMA producer (both CTAs; bytes are signalled on the leader's full barrier) =====================
             int stage = 0; uint32_t phase = 0;
             for (int item = pair; item < total_tiles; item += npairs) {
-                const int m0 = (item / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
-                const int nb = (item % tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
+                const int tile = item % mn_tiles, ks = item / mn_tiles;
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                const int m0 = (tile / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+                const int nb = (tile % tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
                 for (int seg = 0; seg < p.nseg; ++seg) {
                     const int a_row = m0 + (p.nseg > 1 ? c_seg_a[seg] * p.a_plane_rows : 0);
                     const int b_row = nb + (p.nseg > 1 ? c_seg_b[seg] * p.w_plane_rows : 0);
-                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                    const int pa = p.nseg > 1 ? c_seg_a[seg] : 0, pb = p.nseg > 1 ? c_seg_b[seg] : 0;
+                    for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 201);
                         const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
                         if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B_STAGE_BYTES));
-                        tma_load_2d_pair(sB + stage * B_STAGE_BYTES, &tmB, full_leader, kb * BK, b_row);
-                        tma_load_2d_pair(sA + stage * A_STAGE_BYTES, &tmA, full_leader, kb * BK, a_row);
+                        if (p.mn_major) {                           // [64 k-rows][64 columns] boxes; rows past K / columns past M, N are zero-filled
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                tma_load_3d_pair(sB + stage * B_STAGE_BYTES + j * 8192, &tmB, full_leader, nb + 64 * j, kb * BK, pb);
+                                tma_load_3d_pair(sA + stage * A_STAGE_BYTES + j * 8192, &tmA, full_leader, m0 + 64 * j, kb * BK, pa);
+                            }
+                        } else {
+                            tma_load_2d_pair(sB + stage * B_STAGE_BYTES, &tmB, full_leader, kb * BK, b_row);
+                            tma_load_2d_pair(sA + stage * A_STAGE_BYTES, &tmA, full_leader, kb * BK, a_row);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -506,18 +520,27 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             // ===================== MMA issuer (leader CTA only) =====================
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            const int kiters = p.nseg * p.num_kb;
             for (int item = pair; item < total_tiles; item += npairs) {
+                const int ks = item / mn_tiles;
+                const int kiters = p.nseg * (min(p.num_kb, (ks + 1) * p.kb_per_split) - ks * p.kb_per_split);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.err_flag, 202);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
                 for (int it = 0; it < kiters; ++it) {
                     mbar_wait(&full_bar[stage], phase, p.err_flag, 203);
                     tcgen05_fence_after();
+                    if (p.mn_major) {
+                        const uint64_t adesc = make_umma_desc_mnmajor_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
+                        const uint64_t bdesc = make_umma_desc_mnmajor_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_pair(d_tmem, adesc + 128 * k, bdesc + 128 * k, IDESC | UMMA_IDESC_A_MN_MAJOR | UMMA_IDESC_B_MN_MAJOR, (it | k) != 0 ? 1u : 0u);
+                    } else {
                     const uint64_t adesc = make_umma_desc_kmajor_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
                     const uint64_t bdesc = make_umma_desc_kmajor_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit_pair(&empty_bar[stage], 3);         // frees the stage in BOTH CTAs when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -534,14 +557,25 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;
         for (int item = pair; item < total_tiles; item += npairs) {
-            const int m0 = (item / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM, n0 = (item % tiles_n) * BN;
+            const int tile = item % mn_tiles;
+            const int m0 = (tile / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 204);
             tcgen05_fence_after();
             const int row = m0 + quarter * 32 + lane;
             const uint32_t t_base = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
-            if (m0 + quarter * 32 < p.M)
-                epilogue_tile_tma(p, tmC, t_base, row, m0 + quarter * 32, n0, c_begin, c_end,
-                                  smem_u32(sStage) + static_cast<uint32_t>(eset * 4 + quarter) * 8192u, sbuf, lane);
+            if (p.tma_store) {
+                if (m0 + quarter * 32 < p.M)
+                    epilogue_tile_tma(p, tmC, t_base, row, m0 + quarter * 32, n0, c_begin, c_end,
+                                      smem_u32(sStage) + static_cast<uint32_t>(eset * 4 + quarter) * 8192u, sbuf, lane);
+            } else {                                                // accumulating / split-K outputs: direct (atomic) stores per row
+#pragma unroll 1
+                for (int c0 = c_begin * 32; c0 < c_end * 32; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(t_base + static_cast<uint32_t>(c0), v);
+                    tmem_ld_wait();
+                    if (row < p.M) epilogue_store(p, row, n0 + c0, v);
+                }
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {                                        // one arrive per warp on the LEADER's tmem_empty
@@ -550,7 +584,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (lane == 0) bulk_wait_all();
+        if (p.tma_store && lane == 0) bulk_wait_all();
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -702,6 +736,7 @@ static int pair_mode_default() {                       // STAIR_GEMM_PAIR=0|1|2 
     const char* e = getenv("STAIR_GEMM_PAIR");
     return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
 }
+static int g_pair_mn = 1;                           // 1 = the CTA-pair kernel also serves MN-major (weight-gradient) GEMMs; 0 = K-major only (comparison)
 static int g_pair_mode = pair_mode_default();      // 1 (default) = CTA-pair (cta_group::2) kernel for eligible GEMMs, 0 = never, 2 = whenever legal (tests)
 
 template <int STAGES, int EPI>
@@ -714,8 +749,20 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CU
         configured = true;
     }
     const int tiles = ceil_div(p.M, 2 * BM) * (p.N / 256);
-    const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-    gemm_tcgen05_pair_kernel<STAGES, EPI><<<2 * pairs, GEMM_THREADS + 128 * (EPI - 1), S::TOTAL, st>>>(ta, tb, tc, p);
+    const int max_pairs = g_num_sms / 2;
+    GemmParams q = p;
+    // split-K for accumulating GEMMs with few output tiles and a long contraction (weight gradients), as in launch_tc
+    if (p.accumulate && !p.bias && !p.row_scale && p.act == STAIR_ACT_NONE && g_split_k && tiles * 2 <= max_pairs && p.num_kb >= 8) {
+        int ks = max_pairs / tiles;
+        if (ks > p.num_kb / 4) ks = p.num_kb / 4;
+        if (ks > 1) {
+            q.kb_per_split = ceil_div(p.num_kb, ks);
+            q.ksplit = ceil_div(p.num_kb, q.kb_per_split);
+        }
+    }
+    const int items = tiles * q.ksplit;
+    const int pairs = items < max_pairs ? items : max_pairs;
+    gemm_tcgen05_pair_kernel<STAGES, EPI><<<2 * pairs, GEMM_THREADS + 128 * (EPI - 1), S::TOTAL, st>>>(ta, tb, tc, q);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -763,20 +810,31 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     // wide tiles when there are plenty of them.  The weight-gradient contraction (16 output tiles, K ~ 20 000 split over all SMs) is bound
     // by L2 -> SM operand traffic (every 128-column operand slice is re-read by 4 tiles: 160 MB for 40 MB of operands, ~6 TB/s); 128 x 256
     // tiles move 25 % fewer bytes but double the same-address atomics of the split-K epilogue and measured slower (g_dw_wide).
-    // CTA-pair kernel: K-major, no gather, plain store, N a multiple of 256, and at least half a wave of 256 x 256 tiles
+    // CTA-pair kernel: no gather, N a multiple of 256, and enough 256 x 256 tiles (a quarter wave) — or, for the accumulating weight-gradient
+    // contractions (few output tiles, K in the tens of thousands), enough K to split over the pairs
     {
         const int tiles256 = ceil_div(a.M, 2 * BM) * (a.N / 256);
-        const bool legal = !a.mn_major && !gather && !a.accumulate && p.vec_ok && g_epilogue_impl == 0 && a.N % 256 == 0 && g_num_sms >= 2;
-        if (legal && (g_pair_mode == 2 || (g_pair_mode == 1 && tiles256 * 4 >= g_num_sms))) {
+        const bool legal = !gather && p.vec_ok && g_epilogue_impl == 0 && a.N % 256 == 0 && g_num_sms >= 2 && (!a.mn_major || g_pair_mn);
+        const bool enough = tiles256 * 4 >= g_num_sms || (a.accumulate && !a.bias && !a.row_scale && a.act == STAIR_ACT_NONE && g_split_k && p.num_kb >= 32);
+        if (legal && (g_pair_mode == 2 || (g_pair_mode == 1 && enough))) {
             CUtensorMap ta, tb, tc;
-            int rc = make_tmap_bf16_2d(&ta, a.A, a.K, a_rows, a.lda, BK, BM);
+            int rc;
+            if (a.mn_major) {
+                rc = make_tmap_bf16_mn(&ta, a.A, a.M, a.K, a.nplanes, a.nplanes > 1 ? a.a_plane_rows : a.K, a.lda);
+                if (rc) return rc;
+                rc = make_tmap_bf16_mn(&tb, a.W, a.N, a.K, a.nplanes, a.nplanes > 1 ? a.w_plane_rows : a.K, a.ldw);
+            } else {
+                rc = make_tmap_bf16_2d(&ta, a.A, a.K, a_rows, a.lda, BK, BM);
+                if (rc) return rc;
+                rc = make_tmap_bf16_2d(&tb, a.W, a.K, w_rows, a.ldw, BK, 128);
+            }
             if (rc) return rc;
-            rc = make_tmap_bf16_2d(&tb, a.W, a.K, w_rows, a.ldw, BK, 128);
-            if (rc) return rc;
-            rc = make_tmap_out(&tc, a.C, a.out_dtype, a.N, a.M, a.ldc);
-            if (rc) return rc;
-            p.tma_store = 1;
-            const bool epi2 = g_gemm_epi2 && p.num_kb * p.nseg <= 8;
+            tc = tb;
+            if (p.tma_store) {
+                rc = make_tmap_out(&tc, a.C, a.out_dtype, a.N, a.M, a.ldc);
+                if (rc) return rc;
+            }
+            const bool epi2 = g_gemm_epi2 && p.num_kb * p.nseg <= 8 && !a.mn_major;
             return epi2 ? launch_tc_pair<5, 2>(ta, tb, tc, p, st) : launch_tc_pair<6, 1>(ta, tb, tc, p, st);
         }
     }
@@ -811,6 +869,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
 using namespace stair;
 
 extern "C" int stair_set_gemm_impl(int impl) { g_gemm_impl = impl; return STAIR_OK; }
+extern "C" int stair_set_gemm_pair_mn(int on) { g_pair_mn = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_pair(int mode) { g_pair_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return STAIR_OK; }
 extern "C" int stair_set_gemm_epi2(int on) { g_gemm_epi2 = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_wide_min(int half_waves) { g_wide_tiles_min = half_waves < 0 ? 0 : half_waves; return STAIR_OK; }

@@ -91,6 +91,14 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
                       const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st,
                       const LstmHist* hist = nullptr);
 
+// weight-stationary cluster recurrence of ONE encoder (lstm_ws.cu; bf16 path, h = 256): W_hh resident in the shared memory of a 4-CTA
+// cluster, h exchanged through `hx` (>= lstm_ws_hx_bytes(B) bytes).  q_off == nullptr: video (T = steps for every question); else text.
+// coef_h / hs_h: the BPTT history of launch_lstm_fused (null = inference).
+bool lstm_ws_ok(int precision, int h, int B);
+long long lstm_ws_hx_bytes(int B);
+int launch_lstm_ws(const void* xproj, void* out, void* final_h, const int* q_off, int steps, const void* whh_f, const void* whh_r,
+                   float* c_scratch, void* hx, int B, int h, int* err_flag, cudaStream_t st, bf16* coef_h = nullptr, bf16* hs_h = nullptr);
+
 // fused persistent BPTT of both encoders and directions (lstm_bptt.cu; bf16 path, after a fused forward with history).
 // index 0 = video, 1 = text.  gates: the forward's blocked bf16 coefficient history (c unused); dout: fp32 [rows][2h] gradient of the encoder output (dout[1] is modified: dqfeat is added to each question's last-step rows); dxb: bf16
 // [rows][8h] gate pre-activation gradients in token order (output); dc: scratch of 2 * ceil(B/64)*64 * h floats per encoder;

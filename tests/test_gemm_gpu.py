@@ -133,14 +133,18 @@ TN_CASES = [
 ]
 
 
-@pytest.mark.parametrize('impl', [0, 1], ids=['tc', 'simt'])
-@pytest.mark.parametrize('case', TN_CASES)
+@pytest.mark.parametrize('impl', [0, 1, 2], ids=['tc', 'simt', 'tc-pair'])
+@pytest.mark.parametrize('case', TN_CASES + [(256, 256, 64, 1, True), (700, 768, 5000, 1, True), (130, 512, 300, 3, False)])
 def test_gemm_tn_matches_fp32_reference(case, impl):
-    """C = A^T . W with both operands read in place as MN-major tiles (the weight-gradient contraction, no transposed copies)."""
+    """C = A^T . W with both operands read in place as MN-major tiles (the weight-gradient contraction, no transposed copies).
+    'tc' = the product dispatch (CTA-pair kernel with split-K where eligible, single-CTA kernel otherwise), 'tc-pair' = the CTA-pair
+    kernel forced wherever it is legal (N % 256 == 0; incl. ragged M whose peer CTA rows are partly or wholly past M), 'simt' = debug."""
     import ctypes
     M, N, K, planes, acc = case
     if impl == 1 and M * N * K > 3e9:
         pytest.skip('SIMT debug kernel: small cases only')
+    pair_mode = 2 if impl == 2 else 1
+    impl = 0 if impl == 2 else impl
     g = torch.Generator(device='cuda').manual_seed(M + 3 * N + 7 * K)
     lda, ldw = (M + 7) // 8 * 8, (N + 7) // 8 * 8
     prow = K + 5                                        # plane stride in rows (> K: rows past K belong to nobody)
@@ -166,12 +170,14 @@ def test_gemm_tn_matches_fp32_reference(case, impl):
     C = C0.clone()
     lib = L.lib()
     lib.stair_set_gemm_impl(impl)
+    lib.stair_set_gemm_pair(pair_mode)
     try:
         rc = lib.stair_gemm_bf16_tn(L.ptr(A), ctypes.c_longlong(lda), L.i32(prow), L.ptr(W), ctypes.c_longlong(ldw), L.i32(prow), L.i32(planes),
                                     L.ptr(C), ctypes.c_longlong(N), L.i32(M), L.i32(N), L.i32(K), L.i32(1 if acc else 0), L.stream_ptr())
         torch.cuda.synchronize()
     finally:
         lib.stair_set_gemm_impl(0)
+        lib.stair_set_gemm_pair(1)
     assert rc == 0 and lib.stair_gemm_error_flag() == 0
     want = (ref.float() + C0) if acc else ref.float()
     err = (C - want).abs().max().item()
