@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define STAIR_ABI_VERSION 6
+#define STAIR_ABI_VERSION 7
+#define STAIR_MAX_GROUP_DEPS 8
 
 /* status codes */
 #define STAIR_OK 0
@@ -147,6 +148,9 @@ typedef struct StairBatch {
     const int32_t* root_node;  /* [B] node index of token 0 */
     const StairGroup* groups;  /* HOST [n_groups] */
     const int32_t* group_tab;  /* device [4][n_groups]: node_off, out_base, out_mult, aux_base (same as `groups`) */
+    const int32_t* group_deps; /* HOST [n_groups][STAIR_MAX_GROUP_DEPS] or NULL: the groups whose outputs group g reads (-1 = unused entry; a first
+                                * entry of -2 = "every earlier group").  With it the module phase is scheduled by data dependency (a group starts as
+                                * soon as its producers are done) instead of wave by wave. */
 } StairBatch;
 
 /* Caller-owned output / scratch buffers. */
@@ -224,6 +228,9 @@ int64_t stair_sizeof(int which);
 /* concurrency of the module phase: independent groups of one schedule wave run on up to `lanes` (1..8, default 4) internal streams
  * forked from and joined back into the caller's stream (the call stays stream-ordered for the caller) */
 int stair_set_lanes(int lanes);
+/* module-phase scheduling: 1 (default) = by data dependency when StairBatch.group_deps is given (per-group events, no barrier between the
+ * schedule waves); 0 = wave by wave (fork / join around every wave) */
+int stair_set_dep_sched(int on);
 /* encoder recurrence implementation: 0 = fused persistent kernel when eligible (default), 1 = per-step GEMM + cell kernels */
 int stair_set_lstm_impl(int impl);
 /* bf16 recurrence at h = 256: 1 (default) = weight-stationary cluster kernel (csrc/lstm_ws.cu: W_hh resident in the shared memory of a 4-CTA

@@ -15,6 +15,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'stair_b200.h')
 BF16, F32 = 0, 1
 ACT_NONE, ACT_RELU = 0, 1
 FWD_ENCODE_VIDEO, FWD_ENCODE_TEXT, FWD_GROUP, FWD_MODULES, FWD_DECODE, FWD_ALL = 1, 2, 4, 8, 16, 31
+MAX_GROUP_DEPS = 8          # STAIR_MAX_GROUP_DEPS
 
 _ERRORS = {-1: 'bad argument', -2: 'CUDA error', -3: 'workspace / arena capacity exceeded',
            -4: 'invalid program layout', -5: 'unsupported configuration'}
@@ -62,7 +63,7 @@ class StairBatch(ctypes.Structure):
     _fields_ = [('B', i32), ('T', i32), ('n_tok', i32), ('L_max', i32), ('n_nodes', i32), ('n_groups', i32),
                 ('video_dtype', i32), ('question_dtype', i32), ('video', vp), ('question', vp), ('q_off', vp),
                 ('node_gid', vp), ('node_q', vp), ('node_arg', vp), ('node_span', vp), ('root_node', vp),
-                ('groups', ctypes.POINTER(StairGroup)), ('group_tab', vp)]
+                ('groups', ctypes.POINTER(StairGroup)), ('group_tab', vp), ('group_deps', vp)]
 
 
 class StairBuffers(ctypes.Structure):

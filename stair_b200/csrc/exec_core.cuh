@@ -414,7 +414,8 @@ inline long long group_cost(const StairGroup& g, int T) {
     return launches * 1000LL + static_cast<long long>(g.count) * (op_is_vid_sized(g.op) ? T : 1) / 16;
 }
 
-struct LaneStreams { cudaStream_t side[LANES - 1]; cudaEvent_t fork, join[LANES - 1]; bool ok = false; };
+constexpr int MAX_SCHED_GROUPS = 96;     // groups with their own completion event (dependency-driven scheduling); more -> wave scheduling
+struct LaneStreams { cudaStream_t side[LANES - 1]; cudaEvent_t fork, join[LANES - 1], done[MAX_SCHED_GROUPS]; bool ok = false; };
 // The only CUDA objects the library owns: per calling thread, LANES - 1 side streams + LANES events used to run the independent groups of
 // a schedule wave concurrently.  Created by stair_init() (or lazily by the first forward of a thread), destroyed by stair_shutdown().
 inline LaneStreams& lane_state() {
@@ -425,6 +426,7 @@ inline void lane_streams_destroy() {
     LaneStreams& ls = lane_state();
     if (!ls.ok) return;
     for (int l = 0; l < LANES - 1; ++l) { cudaStreamDestroy(ls.side[l]); cudaEventDestroy(ls.join[l]); }
+    for (int g = 0; g < MAX_SCHED_GROUPS; ++g) cudaEventDestroy(ls.done[g]);
     cudaEventDestroy(ls.fork);
     ls.ok = false;
 }
@@ -436,12 +438,73 @@ inline LaneStreams* lane_streams() {
             if (cudaEventCreateWithFlags(&ls.join[l], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
         if (cudaEventCreateWithFlags(&ls.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int g = 0; g < MAX_SCHED_GROUPS; ++g)
+            if (cudaEventCreateWithFlags(&ls.done[g], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         ls.ok = true;
     }
     return &ls;
 }
 
 extern int g_lanes;      // 1 = everything on the caller's stream; up to LANES
+extern int g_dep_sched;  // 1 = schedule the module groups by data dependency when the batch carries group_deps
+
+// Dependency-driven module phase.  Wave scheduling (run_modules below) joins all lanes after every schedule wave, so a wave lasts as long
+// as its slowest lane and the lanes idle in between; but a group only needs the groups whose outputs it reads.  Here every group gets
+// a completion event; a group is placed on the lane of its latest-finishing producer when that producer is the lane's tail (the chain
+// continues in stream order, no event wait) and on the least-loaded lane otherwise, waiting only for the events of its own producers.
+// The critical path becomes the longest dependency chain of the layout mix instead of the sum of the per-wave maxima.
+inline int run_modules_dep(Ctx& c, LaneStreams* ls) {
+    const int ng = c.b.n_groups;
+    const int lanes = g_lanes < LANES ? g_lanes : LANES;
+    int lane_of[MAX_SCHED_GROUPS], tail[LANES];
+    long long lane_end[LANES], finish[MAX_SCHED_GROUPS];
+    bool used[LANES];
+    for (int l = 0; l < lanes; ++l) { tail[l] = -1; lane_end[l] = 0; used[l] = false; }
+    if (cudaEventRecord(ls->fork, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
+    for (int g = 0; g < ng; ++g) {
+        const int* deps = c.b.group_deps + static_cast<long long>(g) * STAIR_MAX_GROUP_DEPS;
+        const bool all = deps[0] == -2;
+        long long ready = 0;
+        int latest = -1;
+        for (int d = 0; d < (all ? g : STAIR_MAX_GROUP_DEPS); ++d) {
+            const int pg = all ? d : deps[d];
+            if (pg < 0) break;
+            if (pg >= g) return STAIR_ERR_LAYOUT;
+            if (finish[pg] >= ready) { ready = finish[pg]; latest = pg; }
+        }
+        // lane choice: continue the producer's chain when it is its lane's tail, else the lane that is free first
+        int lane = -1;
+        if (latest >= 0 && tail[lane_of[latest]] == latest) lane = lane_of[latest];
+        else {
+            lane = 0;
+            for (int l = 1; l < lanes; ++l) if (lane_end[l] < lane_end[lane]) lane = l;
+        }
+        Ctx lc = c;
+        cudaStream_t st = lane == 0 ? c.st : ls->side[lane - 1];
+        if (lane > 0) { lc.st = st; lc.ws = c.ws + static_cast<long long>(lane) * c.plan.mod_bytes; }
+        if (lane > 0 && !used[lane]) {
+            if (cudaStreamWaitEvent(st, ls->fork, 0) != cudaSuccess) return STAIR_ERR_CUDA;
+            used[lane] = true;
+        }
+        for (int d = 0; d < (all ? g : STAIR_MAX_GROUP_DEPS); ++d) {
+            const int pg = all ? d : deps[d];
+            if (pg < 0) break;
+            if (lane_of[pg] != lane && cudaStreamWaitEvent(st, ls->done[pg], 0) != cudaSuccess) return STAIR_ERR_CUDA;
+        }
+        STAIR_TRY(run_group(lc, c.b.groups[g], g));
+        if (cudaEventRecord(ls->done[g], st) != cudaSuccess) return STAIR_ERR_CUDA;
+        lane_of[g] = lane;
+        tail[lane] = g;
+        const long long start = ready > lane_end[lane] ? ready : lane_end[lane];
+        finish[g] = lane_end[lane] = start + group_cost(c.b.groups[g], c.T);
+    }
+    for (int l = 1; l < lanes; ++l)
+        if (used[l]) {
+            if (cudaEventRecord(ls->join[l - 1], ls->side[l - 1]) != cudaSuccess) return STAIR_ERR_CUDA;
+            if (cudaStreamWaitEvent(c.st, ls->join[l - 1], 0) != cudaSuccess) return STAIR_ERR_CUDA;
+        }
+    return STAIR_OK;
+}
 
 // Groups are listed in schedule order (wave-major).  The groups of one wave are independent (they read earlier waves and write
 // disjoint arena ranges), so they are spread over up to LANES streams forked from / joined back into the caller's stream; every
@@ -450,6 +513,7 @@ extern int g_lanes;      // 1 = everything on the caller's stream; up to LANES
 inline int run_modules(Ctx& c) {
     const int ng = c.b.n_groups;
     LaneStreams* ls = g_lanes > 1 ? lane_streams() : nullptr;
+    if (ls && g_dep_sched && c.b.group_deps && ng <= MAX_SCHED_GROUPS) return run_modules_dep(c, ls);
     int gi = 0;
     while (gi < ng) {
         int gj = gi + 1;

@@ -13,6 +13,7 @@ namespace stair {
 namespace ex {
 int g_lstm_impl = 0;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
 thread_local long long t_last_launches = 0;
+int g_dep_sched = 1;         // 1 = dependency-driven module scheduling when the batch carries group_deps
 int g_lanes = 6;             // measured at B = 4096 RX: 2 / 4 / 6 / 8 lanes = 1.64 / 1.65 / 1.54 / 1.55 ms per forward
 }
 
@@ -22,6 +23,7 @@ using namespace stair;
 using namespace stair::ex;
 
 extern "C" int stair_set_lstm_impl(int impl) { g_lstm_impl = impl; return STAIR_OK; }
+extern "C" int stair_set_dep_sched(int on) { g_dep_sched = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_lanes(int lanes) { g_lanes = lanes < 1 ? 1 : (lanes > LANES ? LANES : lanes); return STAIR_OK; }
 extern "C" int stair_version(void) { return STAIR_ABI_VERSION; }
 // explicit ownership of the library's few runtime objects (see include/stair_b200.h "Conventions")

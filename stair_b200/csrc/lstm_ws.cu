@@ -26,6 +26,7 @@
 #include "tc_ptx.cuh"
 #include "train_kernels.cuh"
 #include <cstdlib>
+#include <cstdio>
 
 namespace stair {
 
@@ -412,6 +413,8 @@ int launch_lstm_ws(const void* xproj, void* out, void* final_h, const int* q_off
     STAIR_TRY(make_tmap_bf16_2d(&tw1, whh_r, h, 4ULL * h, h, 64, 256));
     STAIR_TRY(make_tmap_bf16_2d(&thx, hx, h, 4ULL * nblk * WS_ROWS, h, 64, WS_ROWS));
     const int grid = WS_NC * 2 * Gd;
+    static bool said = false;
+    if (!said && getenv("STAIR_DEBUG")) { fprintf(stderr, "lstm_ws: max resident clusters %d, clusters per direction %d, blocks %d, grid %d\n", max_clusters, Gd, nblk, grid); said = true; }
     if (hist) lstm_ws_kernel<true><<<grid, WS_THREADS, WS_SMEM, st>>>(tw0, tw1, thx, p);
     else lstm_ws_kernel<false><<<grid, WS_THREADS, WS_SMEM, st>>>(tw0, tw1, thx, p);
     STAIR_CHECK_LAUNCH();

@@ -471,6 +471,7 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
     b.group_keys, b.group_counts = keys, counts
     b.n_groups = len(keys)
     b.node_gid_host = gid
+    b.group_deps = _group_deps(gid, node_arg, len(keys))
 
     sl = b._slices()
     itab = torch.empty(sl['_total'][1], dtype=torch.int32, pin_memory=pin_memory)
@@ -484,6 +485,32 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
     if all('answer' in e for e in examples):
         b.answer = torch.tensor([int(e['answer']) for e in examples], dtype=torch.int64)
     return b
+
+
+def _group_deps(gid, node_arg, n_groups):
+    """[n_groups, MAX_GROUP_DEPS] int32: the groups whose outputs each group reads (-1 = unused; first entry -2 = more producers than fit,
+    i.e. "wait for every earlier group").  Lets the executor start a group as soon as ITS producers are done (StairBatch.group_deps)."""
+    deps = np.full((n_groups, L.MAX_GROUP_DEPS), -1, np.int32)
+    pairs = []
+    for k in range(3):
+        m = node_arg[k] >= 0
+        if m.any():
+            pairs.append(gid[m].astype(np.int64) * n_groups + gid[node_arg[k][m]])
+    if pairs:
+        uniq = np.unique(np.concatenate(pairs))
+        cons, prod = uniq // n_groups, uniq % n_groups
+        fill = np.zeros(n_groups, np.int64)
+        for c_, p_ in zip(cons.tolist(), prod.tolist()):
+            if fill[c_] < 0:
+                continue
+            if fill[c_] == L.MAX_GROUP_DEPS:
+                deps[c_, :] = -1
+                deps[c_, 0] = -2
+                fill[c_] = -1
+                continue
+            deps[c_, fill[c_]] = p_
+            fill[c_] += 1
+    return deps
 
 
 def collate_chunks(examples, n_chunks, **kw):

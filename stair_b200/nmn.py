@@ -119,6 +119,7 @@ class VideoNMN(nn.Module):
             setattr(sb, name, batch.tab_ptr(name))
         sb.groups = ctypes.cast(groups, ctypes.POINTER(L.StairGroup))
         sb.group_tab = gtab.data_ptr()
+        sb.group_deps = batch.group_deps.ctypes.data if getattr(batch, 'group_deps', None) is not None and ng else None
         lib = L.lib()
         ws_bytes = int(lib.stair_nmn_workspace_bytes(ctypes.byref(model), ctypes.byref(sb)))
         itab_ints = int(lib.stair_itab_ints(L.i32(n), L.i32(ng)))
