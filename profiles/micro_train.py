@@ -16,6 +16,8 @@ from stair_b200 import _lib as L
 L.lib().stair_set_bwd_lanes(int(os.environ.get('BWD_LANES', 4)))
 L.lib().stair_set_bptt_impl(int(os.environ.get('BPTT_IMPL', 0)))
 L.lib().stair_set_gemm_wide_min(int(os.environ.get('GEMM_WIDE_MIN', 1)))
+L.lib().stair_set_gemm_pair_mn(int(os.environ.get('PAIR_MN', 1)))       # CTA-pair kernel for the MN-major weight-gradient GEMMs
+L.lib().stair_set_gemm_pair(int(os.environ.get('PAIR', 1)))
 step, opt = NMNTrainStep(model), FusedAdam(model)
 plan = step.plan(batch)
 for i in range(steps):

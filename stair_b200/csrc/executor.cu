@@ -14,7 +14,8 @@ namespace ex {
 int g_lstm_impl = 0;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
 thread_local long long t_last_launches = 0;
 int g_dep_sched = 1;         // 1 = dependency-driven module scheduling when the batch carries group_deps
-int g_lanes = 6;             // measured at B = 4096 RX: 2 / 4 / 6 / 8 lanes = 1.64 / 1.65 / 1.54 / 1.55 ms per forward
+int g_lanes = 8;             // round 1 (wave scheduling), B = 4096 RX: 2 / 4 / 6 / 8 lanes = 1.64 / 1.65 / 1.54 / 1.55 ms per forward; round 2
+                             // (dependency scheduling): 4 / 6 / 8 lanes = 1.365 / 1.36 / 1.34 ms vs 1.41-1.43 ms wave by wave (profiles/r2_dep_sched_ab.txt)
 }
 
 }  // namespace stair

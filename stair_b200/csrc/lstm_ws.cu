@@ -73,18 +73,23 @@ __device__ __forceinline__ void ws_unpack8(const uint4& r, float (&f)[8]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(hh[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
-// wait on an mbarrier whose arrivals come from other CTAs of the cluster (acquire at cluster scope), bounded like mbar_wait
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+// wait on an mbarrier whose arrivals come from other CTAs of the cluster, bounded like mbar_wait.  The spin is RELAXED and one
+// acquire fence follows the successful try: an acquire.cluster try_wait invalidates L1 on every iteration (CCTL.IVALL, 1.2 M times per
+// launch in the first version), which is where the epilogue warps of the same SM keep the other halves of their xproj sectors.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* err_flag, int code, bool acquire = true) {
     uint32_t spins = 0;
     uint64_t t0 = 0;
     for (;;) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (ok) return;
+        if (ok) {
+            if (acquire) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            return;
+        }
         if ((++spins & 0x3FFu) == 0) {
             uint64_t now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -97,7 +102,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         }
     }
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }     // generic <-> async proxy, global state space (the h exchange buffer)
 
 template <bool HIST>
 __global__ void __cluster_dims__(WS_NC, 1, 1) __launch_bounds__(WS_THREADS, 1)
@@ -204,6 +209,28 @@ lstm_ws_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
         }
+    } else if (warp == WS_EPI_WARPS + 3) {
+        // ===================== L2 prefetcher: the chunk's input-projection columns of block-step (s, lb), one round ahead =====================
+        // xproj (402 MB at B = 4096) streams from HBM exactly once; the cell epilogue is a dependent chain per step, so an HBM miss
+        // (~0.7 us) in front of every sub-block is exposed.  This warp requests the 128 rows x 4 gates x 128 bytes of a block-step as soon
+        // as h_{s-1} of that block is complete (the same event its MMA waits for), i.e. one exchange + MMA ahead of the epilogue.
+        for (int s = 0; s < S; ++s)
+            for (int lb = 0; lb < nlb; ++lb) {
+                if (s >= s_steps[lb]) continue;
+                if (s > 0) mbar_wait_cluster(&hready[lb], static_cast<uint32_t>((s - 1) & 1), p.err_flag, 307, false);
+                const int b = g + lb * Gd;
+                for (int r = lane; r < WS_ROWS; r += 32) {
+                    const int grow = b * WS_ROWS + r;
+                    if (grow >= p.B) continue;
+                    int base, L = p.steps;
+                    if (ragged) { base = __ldg(p.q_off + grow); L = __ldg(p.q_off + grow + 1) - base; }
+                    else base = grow * p.steps;
+                    if (s >= L) continue;
+                    const bf16* xrow = p.xproj + (static_cast<long long>(base) + (dir == 0 ? s : L - 1 - s)) * 8 * h + dir * 4 * h + static_cast<int>(chunk) * 64;
+#pragma unroll
+                    for (int gte = 0; gte < 4; ++gte) asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow + gte * h));
+                }
+            }
     } else if (warp < WS_EPI_WARPS) {
         // ===================== cell epilogue: thread = (question row, 32 of the chunk's 64 units) =====================
         const int quarter = warp & 3, cg = warp >> 2;
