@@ -815,7 +815,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     {
         const int tiles256 = ceil_div(a.M, 2 * BM) * (a.N / 256);
         const bool legal = !gather && p.vec_ok && g_epilogue_impl == 0 && a.N % 256 == 0 && g_num_sms >= 2 && (!a.mn_major || g_pair_mn);
-        const bool enough = tiles256 * 4 >= g_num_sms || (a.accumulate && !a.bias && !a.row_scale && a.act == STAIR_ACT_NONE && g_split_k && p.num_kb >= 32);
+        // (split-K weight gradients with a handful of 256 x 256 output tiles stay on the single-CTA kernel unless forced: every K split adds a
+        // whole 256 KB tile with atomics, twice the atomic traffic of 128 x 128 tiles at the same SM count — measured 6.37 -> 6.55 ms per
+        // training step, profiles/r2_train_pair_ab.txt)
+        const bool enough = tiles256 * 4 >= g_num_sms;
         if (legal && (g_pair_mode == 2 || (g_pair_mode == 1 && enough))) {
             CUtensorMap ta, tb, tc;
             int rc;
