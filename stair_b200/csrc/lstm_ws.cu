@@ -39,10 +39,9 @@ constexpr int WS_W_KB_BYTES = 256 * 64 * 2;        // one k-block of the CTA's W
 constexpr int WS_A_KB_BYTES = WS_ROWS * 64 * 2;    // one k-block of a block's h tile: 16 KiB
 constexpr int WS_A_STAGES = 4;
 constexpr int WS_MAX_LB = 16;                      // local blocks per cluster
-constexpr int WS_EPI_WARPS = 8;
-constexpr int WS_THREADS = (WS_EPI_WARPS + 4) * 32;
 constexpr uint32_t WS_IDESC = make_idesc_bf16(128, 256);
 constexpr int WS_SMEM = WS_NC * WS_W_KB_BYTES + WS_A_STAGES * WS_A_KB_BYTES + 1024 /*barriers, step table*/ + 1024 /*alignment*/;
+__host__ __device__ constexpr int ws_threads(int ew) { return (ew + 4) * 32; }
 
 struct WsParams {
     const bf16* xproj;      // [rows, 8h]: W_ih x + b for both directions (fwd gates | reverse gates)
@@ -104,11 +103,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }     // generic <-> async proxy, global state space (the h exchange buffer)
 
-template <bool HIST>
-__global__ void __cluster_dims__(WS_NC, 1, 1) __launch_bounds__(WS_THREADS, 1)
+// EW = cell-epilogue warps.  The cell epilogue is a latency chain (TMEM read -> 5 transcendentals -> stores); with 8 warps (2 per
+// scheduler) it runs at 23 % of the issue slots.  The inference form processes a sub-block of 8 units GATE BY GATE (i, g -> i*g; f, o ->
+// c, h) so that at most two gates' operands are live: it fits 16 warps (4 per scheduler) in 96 registers without spilling.  The training
+// form (HIST: six coefficients per unit) keeps 8 warps and all four gates in flight.
+template <bool HIST, int EW>
+__global__ void __cluster_dims__(WS_NC, 1, 1) __launch_bounds__(ws_threads(EW), 1)
 lstm_ws_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmHX,
                const WsParams p) {
     constexpr int h = WS_H;
+    constexpr int WS_EPI_WARPS = EW;
+    constexpr int WS_THREADS = ws_threads(EW);
     const uint32_t chunk = cluster_ctarank();                      // 64-unit chunk this CTA owns
     const int cl = blockIdx.x / WS_NC, ncl = gridDim.x / WS_NC;
     const int dir = cl & 1, g = cl >> 1, Gd = ncl >> 1;            // clusters alternate directions; g-th cluster of its direction
@@ -139,7 +144,7 @@ lstm_ws_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < WS_MAX_LB) s_steps[threadIdx.x] = (ragged || threadIdx.x >= nlb) ? 0 : p.steps;
-    if (warp == 10) {
+    if (warp == WS_EPI_WARPS + 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr_smem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -235,7 +240,8 @@ lstm_ws_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__
         // ===================== cell epilogue: thread = (question row, 32 of the chunk's 64 units) =====================
         const int quarter = warp & 3, cg = warp >> 2;
         const int row = quarter * 32 + lane;
-        constexpr int SBN = 4;                                     // 8-unit sub-blocks per thread
+        constexpr int UPT = 64 / (EW / 4);                         // hidden units per thread and block-step
+        constexpr int SBN = UPT / 8;                               // 8-unit sub-blocks per thread
         const long long RB = (p.B + 127) / 128 * 4;                // 32-row blocks per (step, direction) of the BPTT history
         const long long hist_step = 2 * RB * (h >> 3);
         int acc = 0; uint32_t acc_phase = 0;
@@ -256,7 +262,62 @@ lstm_ws_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__
                 float* cblk = p.c + ((static_cast<long long>(dir) * p.nblk + b) * WS_NC + chunk) * (64LL * WS_ROWS) + row * 4;     // [unit/4][row][4]
                 bf16* hxrow = p.hx + ((dir * 2 + (s & 1)) * hx_rows + grow) * h;
                 const long long hist_rb = (static_cast<long long>(dir) * RB + (grow >> 5)) * (h >> 3);
-                const int ul0 = cg * 32;                             // first local unit of this thread
+                const int ul0 = cg * UPT;                            // first local unit of this thread
+                if constexpr (!HIST) {
+                    // ---- inference: gate-serial sub-blocks (low register footprint, 16 warps) ----
+                    (void)hist_rb; (void)hist_step;
+                    if (s > 0) {
+                        mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 306);
+                        tcgen05_fence_after();
+                    }
+#pragma unroll
+                    for (int sb = 0; sb < SBN; ++sb) {
+                        const int ul = ul0 + sb * 8;
+                        const int u0 = static_cast<int>(chunk) * 64 + ul;
+                        uint4 xi, xf, xg, xo;
+                        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+                        if (active) {
+                            xi = __ldg(reinterpret_cast<const uint4*>(xrow + u0));
+                            xg = __ldg(reinterpret_cast<const uint4*>(xrow + 2 * h + u0));
+                            xf = __ldg(reinterpret_cast<const uint4*>(xrow + h + u0));
+                            xo = __ldg(reinterpret_cast<const uint4*>(xrow + 3 * h + u0));
+                            if (s > 0) {
+                                c0 = *reinterpret_cast<const float4*>(cblk + (ul / 4) * (WS_ROWS * 4));
+                                c1 = *reinterpret_cast<const float4*>(cblk + (ul / 4 + 1) * (WS_ROWS * 4));
+                            }
+                        }
+                        const uint32_t t = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256 + ul);
+                        uint32_t ra[8], rb[8];
+                        float a[8], fx[8];
+                        if (s > 0) { ws_tmem_ld8(t, ra); ws_tmem_ld8(t + 128, rb); tmem_ld_wait(); }     // gates i and g (.sync.aligned: whole warp)
+                        if (active) {
+                            ws_unpack8(xi, fx);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) a[j] = ws_sigmoid(s > 0 ? fx[j] + __uint_as_float(ra[j]) : fx[j]);
+                            ws_unpack8(xg, fx);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) a[j] *= ws_tanh(s > 0 ? fx[j] + __uint_as_float(rb[j]) : fx[j]);
+                        }
+                        if (s > 0) { ws_tmem_ld8(t + 64, ra); ws_tmem_ld8(t + 192, rb); tmem_ld_wait(); }    // gates f and o
+                        if (active) {
+                            const float cprev[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                            float cn[8];
+                            ws_unpack8(xf, fx);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) cn[j] = fmaf(ws_sigmoid(s > 0 ? fx[j] + __uint_as_float(ra[j]) : fx[j]), cprev[j], a[j]);
+                            *reinterpret_cast<float4*>(cblk + (ul / 4) * (WS_ROWS * 4)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                            *reinterpret_cast<float4*>(cblk + (ul / 4 + 1) * (WS_ROWS * 4)) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                            ws_unpack8(xo, fx);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) a[j] = ws_sigmoid(s > 0 ? fx[j] + __uint_as_float(rb[j]) : fx[j]) * ws_tanh(cn[j]);
+                            const uint4 o0 = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+                            *reinterpret_cast<uint4*>(orow + u0) = o0;
+                            *reinterpret_cast<uint4*>(hxrow + u0) = o0;          // the next step's A operand (all four CTAs of the cluster load it)
+                            if (last) *reinterpret_cast<uint4*>(p.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0) = o0;
+                        }
+                    }
+                } else {
+                // ---- training (history): all four gates of a sub-block in flight, operands of two sub-blocks double-buffered ----
                 // operands of the first two sub-blocks are requested before waiting for the tensor core
                 uint4 xq[2][4];
                 float4 cq[2][2];
@@ -362,6 +423,7 @@ lstm_ws_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__
                         if (last) *reinterpret_cast<uint4*>(p.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0) = o0;
                     }
                 }
+                }
                 if (s > 0) {
                     tcgen05_fence_before();
                     mbar_arrive(&tmem_empty[acc]);
@@ -382,7 +444,7 @@ lstm_ws_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();                                            // no CTA exits while a peer may still arrive on its barriers
-    if (warp == 10) {
+    if (warp == WS_EPI_WARPS + 2) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
@@ -411,20 +473,20 @@ int launch_lstm_ws(const void* xproj, void* out, void* final_h, const int* q_off
     static bool configured[2] = {false, false};
     const bool hist = coef_h != nullptr;
     if (!configured[hist ? 1 : 0]) {
-        cudaError_t e = hist ? cudaFuncSetAttribute(lstm_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM)
-                             : cudaFuncSetAttribute(lstm_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
+        cudaError_t e = hist ? cudaFuncSetAttribute(lstm_ws_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM)
+                             : cudaFuncSetAttribute(lstm_ws_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
         if (e != cudaSuccess) return STAIR_ERR_CUDA;
         configured[hist ? 1 : 0] = true;
     }
     if (max_clusters < 0) {
         // clusters of four 200 KB CTAs that can be resident at once (GPC boundaries: fewer than SMs / 4)
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(WS_NC * 64); cfg.blockDim = dim3(WS_THREADS); cfg.dynamicSmemBytes = WS_SMEM;
+        cfg.gridDim = dim3(WS_NC * 64); cfg.blockDim = dim3(ws_threads(16)); cfg.dynamicSmemBytes = WS_SMEM;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = WS_NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, lstm_ws_kernel<false>, &cfg) != cudaSuccess || n < 2) { cudaGetLastError(); n = 32; }
+        if (cudaOccupancyMaxActiveClusters(&n, lstm_ws_kernel<false, 16>, &cfg) != cudaSuccess || n < 2) { cudaGetLastError(); n = 32; }
         max_clusters = n;
     }
     const int nblk = (B + WS_ROWS - 1) / WS_ROWS;
@@ -442,8 +504,8 @@ int launch_lstm_ws(const void* xproj, void* out, void* final_h, const int* q_off
     const int grid = WS_NC * 2 * Gd;
     static bool said = false;
     if (!said && getenv("STAIR_DEBUG")) { fprintf(stderr, "lstm_ws: max resident clusters %d, clusters per direction %d, blocks %d, grid %d\n", max_clusters, Gd, nblk, grid); said = true; }
-    if (hist) lstm_ws_kernel<true><<<grid, WS_THREADS, WS_SMEM, st>>>(tw0, tw1, thx, p);
-    else lstm_ws_kernel<false><<<grid, WS_THREADS, WS_SMEM, st>>>(tw0, tw1, thx, p);
+    if (hist) lstm_ws_kernel<true, 8><<<grid, ws_threads(8), WS_SMEM, st>>>(tw0, tw1, thx, p);
+    else lstm_ws_kernel<false, 16><<<grid, ws_threads(16), WS_SMEM, st>>>(tw0, tw1, thx, p);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
