@@ -1,6 +1,7 @@
-"""A/B of the two bf16 recurrence kernels at the bench shape (4096 questions, H = 512): the streaming kernel (csrc/lstm_fused.cu) vs the
-weight-stationary cluster kernel (csrc/lstm_ws.cu).  Times are whole encoder phases (input-projection GEMM + recurrence), CUDA events;
-the difference of the two columns is the recurrence itself.  Also checks that both kernels produce the same encoder outputs."""
+"""A/B of the bf16 recurrence kernels at the bench shape (4096 questions, H = 512): the streaming kernel (csrc/lstm_fused.cu) vs the
+weight-stationary cluster kernel (csrc/lstm_ws.cu; form 3 = direct global loads, form 4 = input projection staged through shared memory).
+Times are whole encoder phases (input-projection GEMM + recurrence), CUDA events; the differences between rows are the recurrence itself.
+Also checks that all kernels produce the same encoder outputs."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -29,17 +30,20 @@ def run(ph, n=10):
 
 
 outs = {}
-for ws in (0, 1):
+for name, ws, form in (('streaming (lstm_fused)', 0, 3), ('weight-stationary, form 3', 1, 3), ('weight-stationary, form 4 (smem xproj)', 1, 4)):
     lib.stair_set_lstm_ws(ws)
+    lib.stair_set_lstm_ws_form(form)
     both = run(L.FWD_ENCODE_VIDEO | L.FWD_ENCODE_TEXT)
     text = run(L.FWD_ENCODE_TEXT)
     video = run(L.FWD_ENCODE_VIDEO)
     full = run(L.FWD_ALL)
     st = model.forward_batch(batch, phases=L.FWD_ENCODE_VIDEO | L.FWD_ENCODE_TEXT)
     torch.cuda.synchronize()
-    outs[ws] = (st.vid[:B * T * 512].float().clone(), st.tokfeat[:batch.n_tok * 512].float().clone(), st.qfeat[:B * 512].float().clone())
-    print('%-28s video+text %.3f ms   text only %.3f   video only %.3f   whole forward %.3f   (GEMMs included; gemm error flag %d)'
-          % ('weight-stationary (lstm_ws)' if ws else 'streaming (lstm_fused)', both, text, video, full, lib.stair_gemm_error_flag()), flush=True)
-lib.stair_set_lstm_ws(1)
-for name, a, b in zip(('video_feat', 'token_feature', 'question_feature'), outs[0], outs[1]):
-    print('%-18s max |ws - fused| = %.3g   (max |x| %.3g)' % (name, float((a - b).abs().max()), float(a.abs().max())))
+    outs[name] = (st.vid[:B * T * 512].float().clone(), st.tokfeat[:batch.n_tok * 512].float().clone(), st.qfeat[:B * 512].float().clone())
+    print('%-40s video+text %.3f ms   text only %.3f   video only %.3f   whole forward %.3f   (GEMMs included; gemm error flag %d)'
+          % (name, both, text, video, full, lib.stair_gemm_error_flag()), flush=True)
+lib.stair_set_lstm_ws(0)
+ref = outs['streaming (lstm_fused)']
+for name, o in outs.items():
+    print('%-40s max |x - streaming|: video_feat %.3g, token_feature %.3g, question_feature %.3g'
+          % (name, *(float((a - b).abs().max()) for a, b in zip(o, ref))))
