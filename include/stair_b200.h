@@ -236,7 +236,6 @@ int stair_set_lstm_impl(int impl);
 /* bf16 recurrence at h = 256: 1 (default) = weight-stationary cluster kernel (csrc/lstm_ws.cu: W_hh resident in the shared memory of a 4-CTA
  * cluster, 128 questions per block); 0 = the streaming kernel of csrc/lstm_fused.cu (64 questions per CTA, W_hh re-read from L2 every step) */
 int stair_set_lstm_ws(int on);
-int stair_set_lstm_ws_form(int form);    /* inference form of the weight-stationary kernel: 4 (default) = input projection staged through shared memory by loader warps; 3 = direct global loads */
 
 /* ---- dense contraction (tcgen05 + TMA): C[M,N] = act(row_scale[m] * (A[M,K] . W[N,K]^T) + bias[n]) -------------
  * Replaces every nn.Linear / LSTM projection call site (video_nmn/modules.py passim, module_net.py:39-53). */

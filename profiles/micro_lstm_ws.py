@@ -1,5 +1,5 @@
 """A/B of the bf16 recurrence kernels at the bench shape (4096 questions, H = 512): the streaming kernel (csrc/lstm_fused.cu) vs the
-weight-stationary cluster kernel (csrc/lstm_ws.cu; form 3 = direct global loads, form 4 = input projection staged through shared memory).
+weight-stationary cluster kernel (csrc/lstm_ws.cu).
 Times are whole encoder phases (input-projection GEMM + recurrence), CUDA events; the differences between rows are the recurrence itself.
 Also checks that all kernels produce the same encoder outputs."""
 import sys, os
@@ -30,9 +30,8 @@ def run(ph, n=10):
 
 
 outs = {}
-for name, ws, form in (('streaming (lstm_fused)', 0, 3), ('weight-stationary, form 3', 1, 3), ('weight-stationary, form 4 (smem xproj)', 1, 4)):
+for name, ws in (('streaming (lstm_fused)', 0), ('weight-stationary (lstm_ws)', 1)):
     lib.stair_set_lstm_ws(ws)
-    lib.stair_set_lstm_ws_form(form)
     both = run(L.FWD_ENCODE_VIDEO | L.FWD_ENCODE_TEXT)
     text = run(L.FWD_ENCODE_TEXT)
     video = run(L.FWD_ENCODE_VIDEO)

@@ -101,11 +101,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         }
     }
 }
-__device__ __forceinline__ uint4 ld_shared_v4_ws(uint32_t addr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
-    return r;
-}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }     // generic <-> async proxy, global state space (the h exchange buffer)
 
 // EW = cell-epilogue warps.  The cell epilogue is a latency chain (TMEM read -> 5 transcendentals -> stores); with 8 warps (2 per
@@ -456,288 +451,6 @@ lstm_ws_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__
 }
 
 
-// ------------------------------------------------------------------------------------------------------------------------------------
-// Inference form, version 4: the input projection reaches the cell epilogue THROUGH SHARED MEMORY.
-//
-// What bounds both recurrence kernels (ncu of the forms above: tensor 16 %, MUFU 21 %, issue 23 %, but LSU wavefronts 40-48 %, the most
-// loaded unit): an epilogue thread owns one question row (its TMEM lane), so every 16-byte xproj / h access of a warp touches 32 different
-// 128-byte lines — 32 L1 wavefronts per instruction, 6 such instructions per 8 cells.  Here 4 loader warps read the block-step's xproj
-// columns row by row (a warp instruction covers 4 whole 128-byte lines: 4 wavefronts) and lay them out in shared memory piece-major
-// ([gate][8-unit piece][row][16 B], piece pitch 128 rows x 16 B + 16 B), which both their stores and the epilogue's row-per-lane reads
-// access without bank conflicts.  A block-step is two phase tiles — gates (i, g), then (f, o) — double-buffered, so the loaders run one
-// to two tiles ahead of the 16 epilogue warps, which process the gates in the same order (i, g -> i*g kept in registers; f, o -> c, h).
-// ------------------------------------------------------------------------------------------------------------------------------------
-constexpr int WS2_EW = 16;                                   // cell-epilogue warps (TMEM quarter = warp % 4, 16-unit column group = warp / 4)
-constexpr int WS2_LW = 4;                                    // loader warps
-constexpr int WS2_THREADS = (WS2_EW + 3 + WS2_LW) * 32;      // + TMA producer, MMA issuer, TMEM allocator: 23 warps
-constexpr int WS2_A_STAGES = 2;
-constexpr int WS2_PIECE_PITCH = WS_ROWS * 16 + 16;           // bytes between the [row][16 B] planes of two pieces
-constexpr int WS2_XTILE = 16 * WS2_PIECE_PITCH;              // 2 gates x 8 pieces
-constexpr int WS2_SMEM = WS_NC * WS_W_KB_BYTES + WS2_A_STAGES * WS_A_KB_BYTES + 2 * WS2_XTILE + 1024 /*barriers, step table*/ + 1024 /*alignment*/;
-static_assert(WS2_SMEM <= 232448, "shared memory budget of one CTA");
-
-__global__ void __cluster_dims__(WS_NC, 1, 1) __launch_bounds__(WS2_THREADS, 1)
-lstm_ws2_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmHX,
-                const WsParams p) {
-    constexpr int h = WS_H;
-    const uint32_t chunk = cluster_ctarank();
-    const int cl = blockIdx.x / WS_NC, ncl = gridDim.x / WS_NC;
-    const int dir = cl & 1, g = cl >> 1, Gd = ncl >> 1;
-    const bool ragged = p.q_off != nullptr;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int nlb = 0;
-    for (int b = g; b < p.nblk && nlb < WS_MAX_LB; b += Gd) ++nlb;
-
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw_addr = smem_u32(smem_raw);
-    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint8_t* sW = smem;                                            // [4 kb][256 x 64] bf16, resident
-    uint8_t* sA = smem + WS_NC * WS_W_KB_BYTES;                    // [2][128 x 64] bf16 ring of h k-blocks
-    uint8_t* sX = sA + WS2_A_STAGES * WS_A_KB_BYTES;               // [2] phase tiles of the input projection
-    uint64_t* w_full = reinterpret_cast<uint64_t*>(sX + 2 * WS2_XTILE);
-    uint64_t* a_full = w_full + 1;
-    uint64_t* a_empty = a_full + WS2_A_STAGES;
-    uint64_t* tmem_full = a_empty + WS2_A_STAGES;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* x_full = tmem_empty + 2;
-    uint64_t* x_empty = x_full + 2;
-    uint64_t* hready = x_empty + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(hready + WS_MAX_LB);
-    int* s_steps = reinterpret_cast<int*>(tmem_ptr_smem + 1);
-
-    if (threadIdx.x == 0) {
-        mbar_init(w_full, 1);
-        for (int s = 0; s < WS2_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], WS2_EW);
-            mbar_init(&x_full[a], WS2_LW); mbar_init(&x_empty[a], WS2_EW);
-        }
-        for (int lb = 0; lb < WS_MAX_LB; ++lb) mbar_init(&hready[lb], WS_NC * WS2_EW);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (threadIdx.x < WS_MAX_LB) s_steps[threadIdx.x] = (ragged || threadIdx.x >= nlb) ? 0 : p.steps;
-    if (warp == WS2_EW + 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr_smem)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    __syncthreads();
-    if (ragged) {
-        for (int i = threadIdx.x; i < nlb * WS_ROWS; i += WS2_THREADS) {
-            const int r = (g + (i / WS_ROWS) * Gd) * WS_ROWS + (i % WS_ROWS);
-            if (r < p.B) atomicMax(&s_steps[i / WS_ROWS], __ldg(p.q_off + r + 1) - __ldg(p.q_off + r));
-        }
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    int S = 0;
-    for (int lb = 0; lb < nlb; ++lb) S = max(S, s_steps[lb]);
-    const long long hx_rows = static_cast<long long>(p.nblk) * WS_ROWS;
-
-    if (warp == WS2_EW) {
-        if (lane == 0) {
-            // ===================== TMA producer =====================
-            mbar_arrive_expect_tx(w_full, WS_NC * WS_W_KB_BYTES);
-            for (int kb = 0; kb < WS_NC; ++kb) {
-                if (dir == 0) tma_load_2d(sW + kb * WS_W_KB_BYTES, &tmW0, w_full, kb * 64, static_cast<int>(chunk) * 256);
-                else tma_load_2d(sW + kb * WS_W_KB_BYTES, &tmW1, w_full, kb * 64, static_cast<int>(chunk) * 256);
-            }
-            int stage = 0; uint32_t phase = 0;
-            for (int s = 1; s < S; ++s)
-                for (int lb = 0; lb < nlb; ++lb) {
-                    if (s >= s_steps[lb]) continue;
-                    const int b = g + lb * Gd;
-                    mbar_wait_cluster(&hready[lb], static_cast<uint32_t>((s - 1) & 1), p.err_flag, 311);
-                    fence_proxy_async_all();
-                    const int row = static_cast<int>(((dir * 2 + ((s - 1) & 1)) * hx_rows) + static_cast<long long>(b) * WS_ROWS);
-                    for (int kb = 0; kb < WS_NC; ++kb) {
-                        mbar_wait(&a_empty[stage], phase ^ 1, p.err_flag, 312);
-                        mbar_arrive_expect_tx(&a_full[stage], WS_A_KB_BYTES);
-                        tma_load_2d(sA + stage * WS_A_KB_BYTES, &tmHX, &a_full[stage], kb * 64, row);
-                        if (++stage == WS2_A_STAGES) { stage = 0; phase ^= 1; }
-                    }
-                }
-        }
-    } else if (warp == WS2_EW + 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
-            mbar_wait(w_full, 0, p.err_flag, 313);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int s = 1; s < S; ++s)
-                for (int lb = 0; lb < nlb; ++lb) {
-                    if (s >= s_steps[lb]) continue;
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.err_flag, 314);
-                    tcgen05_fence_after();
-                    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
-                    for (int kb = 0; kb < WS_NC; ++kb) {
-                        mbar_wait(&a_full[stage], phase, p.err_flag, 315);
-                        tcgen05_fence_after();
-                        const uint64_t adesc = make_umma_desc_kmajor_sw128(smem_u32(sA + stage * WS_A_KB_BYTES));
-                        const uint64_t bdesc = make_umma_desc_kmajor_sw128(smem_u32(sW + kb * WS_W_KB_BYTES));
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, WS_IDESC, (kb | k) != 0 ? 1u : 0u);
-                        umma_commit(&a_empty[stage]);
-                        if (++stage == WS2_A_STAGES) { stage = 0; phase ^= 1; }
-                    }
-                    umma_commit(&tmem_full[acc]);
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                }
-        }
-    } else if (warp >= WS2_EW + 3) {
-        // ===================== loaders: xproj columns of the chunk -> piece-major shared-memory tiles =====================
-        const int tl = (warp - (WS2_EW + 3)) * 32 + lane;           // 0 .. 127
-        const int piece16 = tl & 15;                                 // (gate of the phase, 8-unit piece): 128 contiguous bytes per (row, gate)
-        const int rsub = tl >> 4;                                    // row within a group of 8
-        const uint32_t sX0 = smem_u32(sX);
-        int buf = 0; uint32_t xph = 0;
-        for (int s = 0; s < S; ++s)
-            for (int lb = 0; lb < nlb; ++lb) {
-                if (s >= s_steps[lb]) continue;
-                const int b = g + lb * Gd;
-                for (int phs = 0; phs < 2; ++phs) {
-                    const int gate = (phs == 0) ? (piece16 < 8 ? 0 : 2) : (piece16 < 8 ? 1 : 3);      // phase 0: i, g ; phase 1: f, o
-                    const int col = dir * 4 * h + gate * h + static_cast<int>(chunk) * 64 + (piece16 & 7) * 8;
-                    const uint32_t dst = sX0 + static_cast<uint32_t>(buf * WS2_XTILE + piece16 * WS2_PIECE_PITCH + rsub * 16);
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {              // two batches of 8 loads in flight per thread (16 would spill at 80 registers)
-                        uint4 v[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int row = (half * 8 + k) * 8 + rsub;
-                            const int grow = b * WS_ROWS + row;
-                            v[k] = make_uint4(0u, 0u, 0u, 0u);
-                            if (grow < p.B) {
-                                int base, L = p.steps;
-                                if (ragged) { base = __ldg(p.q_off + grow); L = __ldg(p.q_off + grow + 1) - base; }
-                                else base = grow * p.steps;
-                                if (s < L) v[k] = ld_stream_v4(p.xproj + (static_cast<long long>(base) + (dir == 0 ? s : L - 1 - s)) * 8 * h + col);
-                            }
-                        }
-                        if (half == 0) mbar_wait(&x_empty[buf], xph ^ 1, p.err_flag, 316);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) st_shared_v4(dst + static_cast<uint32_t>((half * 8 + k) * 8 * 16), v[k].x, v[k].y, v[k].z, v[k].w);
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&x_full[buf]);         // release: this warp's part of the tile is written
-                    if (++buf == 2) { buf = 0; xph ^= 1; }
-                }
-            }
-    } else if (warp < WS2_EW) {
-        // ===================== cell epilogue: thread = (question row, 16 of the chunk's 64 units) =====================
-        const int quarter = warp & 3, cg = warp >> 2;
-        const int row = quarter * 32 + lane;
-        const uint32_t sX0 = smem_u32(sX) + static_cast<uint32_t>(row * 16);
-        int acc = 0; uint32_t acc_phase = 0;
-        int buf = 0; uint32_t xph = 0;
-        for (int s = 0; s < S; ++s)
-            for (int lb = 0; lb < nlb; ++lb) {
-                if (s >= s_steps[lb]) continue;
-                const int b = g + lb * Gd;
-                const int grow = b * WS_ROWS + row;
-                const bool valid = grow < p.B;
-                int base = 0, L = p.steps;
-                if (ragged) { base = valid ? __ldg(p.q_off + grow) : 0; L = valid ? __ldg(p.q_off + grow + 1) - base : 0; }
-                else base = grow * p.steps;
-                const bool active = valid && s < L;
-                const long long tokrow = static_cast<long long>(base) + (dir == 0 ? s : L - 1 - s);
-                bf16* orow = p.out + tokrow * 2 * h + dir * h;
-                const bool last = ragged && s == L - 1;
-                float* cblk = p.c + ((static_cast<long long>(dir) * p.nblk + b) * WS_NC + chunk) * (64LL * WS_ROWS) + row * 4;     // [unit/4][row][4]
-                bf16* hxrow = p.hx + ((dir * 2 + (s & 1)) * hx_rows + grow) * h;
-                const int ul0 = cg * 16;
-                if (s > 0) {
-                    mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 317);
-                    tcgen05_fence_after();
-                }
-                const uint32_t t = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256 + ul0);
-                float a[16];
-                // ---- phase tile 0: gates i and g -> a = sigmoid(i) * tanh(g) ----
-                mbar_wait(&x_full[buf], xph, p.err_flag, 318);
-                {
-                    const uint32_t xt = sX0 + static_cast<uint32_t>(buf * WS2_XTILE);
-#pragma unroll
-                    for (int sb = 0; sb < 2; ++sb) {
-                        const uint4 xi = ld_shared_v4_ws(xt + static_cast<uint32_t>((cg * 2 + sb) * WS2_PIECE_PITCH));
-                        const uint4 xg = ld_shared_v4_ws(xt + static_cast<uint32_t>((8 + cg * 2 + sb) * WS2_PIECE_PITCH));
-                        uint32_t ra[8], rb[8];
-                        if (s > 0) { ws_tmem_ld8(t + sb * 8, ra); ws_tmem_ld8(t + 128 + sb * 8, rb); tmem_ld_wait(); }
-                        float fx[8], fy[8];
-                        ws_unpack8(xi, fx); ws_unpack8(xg, fy);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            a[sb * 8 + j] = ws_sigmoid(s > 0 ? fx[j] + __uint_as_float(ra[j]) : fx[j]) * ws_tanh(s > 0 ? fy[j] + __uint_as_float(rb[j]) : fy[j]);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&x_empty[buf]);
-                if (++buf == 2) { buf = 0; xph ^= 1; }
-                // ---- phase tile 1: gates f and o -> c, h ----
-                mbar_wait(&x_full[buf], xph, p.err_flag, 319);
-                {
-                    const uint32_t xt = sX0 + static_cast<uint32_t>(buf * WS2_XTILE);
-#pragma unroll
-                    for (int sb = 0; sb < 2; ++sb) {
-                        const int ul = ul0 + sb * 8;
-                        const int u0 = static_cast<int>(chunk) * 64 + ul;
-                        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;      // previous cell state (coalesced: [unit/4][row][4])
-                        if (active && s > 0) {
-                            c0 = *reinterpret_cast<const float4*>(cblk + (ul / 4) * (WS_ROWS * 4));
-                            c1 = *reinterpret_cast<const float4*>(cblk + (ul / 4 + 1) * (WS_ROWS * 4));
-                        }
-                        const uint4 xf = ld_shared_v4_ws(xt + static_cast<uint32_t>((cg * 2 + sb) * WS2_PIECE_PITCH));
-                        const uint4 xo = ld_shared_v4_ws(xt + static_cast<uint32_t>((8 + cg * 2 + sb) * WS2_PIECE_PITCH));
-                        uint32_t ra[8], rb[8];
-                        if (s > 0) { ws_tmem_ld8(t + 64 + sb * 8, ra); ws_tmem_ld8(t + 192 + sb * 8, rb); tmem_ld_wait(); }
-                        if (active) {
-                            float fx[8], fy[8], cn[8];
-                            ws_unpack8(xf, fx); ws_unpack8(xo, fy);
-                            const float cprev[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                cn[j] = fmaf(ws_sigmoid(s > 0 ? fx[j] + __uint_as_float(ra[j]) : fx[j]), cprev[j], a[sb * 8 + j]);
-                            *reinterpret_cast<float4*>(cblk + (ul / 4) * (WS_ROWS * 4)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                            *reinterpret_cast<float4*>(cblk + (ul / 4 + 1) * (WS_ROWS * 4)) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-                            float hn[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) hn[j] = ws_sigmoid(s > 0 ? fy[j] + __uint_as_float(rb[j]) : fy[j]) * ws_tanh(cn[j]);
-                            const uint4 o0 = make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]), pack_bf16(hn[6], hn[7]));
-                            *reinterpret_cast<uint4*>(orow + u0) = o0;
-                            *reinterpret_cast<uint4*>(hxrow + u0) = o0;
-                            if (last) *reinterpret_cast<uint4*>(p.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0) = o0;
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&x_empty[buf]);
-                if (++buf == 2) { buf = 0; xph ^= 1; }
-                if (s > 0) {
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                }
-                if (s + 1 < s_steps[lb]) {
-                    fence_proxy_async_all();
-                    __syncwarp();
-                    if (lane == 0) {
-#pragma unroll
-                        for (int r = 0; r < WS_NC; ++r) mbar_arrive_cluster(mapa_shared(smem_u32(&hready[lb]), static_cast<uint32_t>(r)));
-                    }
-                }
-            }
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == WS2_EW + 2) {
-        tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-    }
-}
-
 }  // namespace
 
 static int lstm_ws_default() {                       // STAIR_LSTM_WS=0|1 overrides the default at library load (A/B runs)
@@ -763,20 +476,19 @@ int launch_lstm_ws(const void* xproj, void* out, void* final_h, const int* q_off
     const bool hist = coef_h != nullptr;
     if (!configured[hist ? 1 : 0]) {
         cudaError_t e = hist ? cudaFuncSetAttribute(lstm_ws_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM)
-                             : (g_lstm_ws_form == 4 ? cudaFuncSetAttribute(lstm_ws2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS2_SMEM)
-                                                    : cudaFuncSetAttribute(lstm_ws_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+                             : cudaFuncSetAttribute(lstm_ws_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
         if (e != cudaSuccess) return STAIR_ERR_CUDA;
         configured[hist ? 1 : 0] = true;
     }
     if (max_clusters < 0) {
         // clusters of four 200 KB CTAs that can be resident at once (GPC boundaries: fewer than SMs / 4)
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(WS_NC * 64); cfg.blockDim = dim3(WS2_THREADS); cfg.dynamicSmemBytes = WS2_SMEM;
+        cfg.gridDim = dim3(WS_NC * 64); cfg.blockDim = dim3(ws_threads(16)); cfg.dynamicSmemBytes = WS_SMEM;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = WS_NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int n = 0;
-        if (cudaFuncSetAttribute(lstm_ws2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS2_SMEM) != cudaSuccess || cudaOccupancyMaxActiveClusters(&n, lstm_ws2_kernel, &cfg) != cudaSuccess || n < 2) { cudaGetLastError(); n = 32; }
+        if (cudaFuncSetAttribute(lstm_ws_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM) != cudaSuccess || cudaOccupancyMaxActiveClusters(&n, lstm_ws_kernel<false, 16>, &cfg) != cudaSuccess || n < 2) { cudaGetLastError(); n = 32; }
         max_clusters = n;
     }
     const int nblk = (B + WS_ROWS - 1) / WS_ROWS;
@@ -795,7 +507,6 @@ int launch_lstm_ws(const void* xproj, void* out, void* final_h, const int* q_off
     static bool said = false;
     if (!said && getenv("STAIR_DEBUG")) { fprintf(stderr, "lstm_ws: max resident clusters %d, clusters per direction %d, blocks %d, grid %d\n", max_clusters, Gd, nblk, grid); said = true; }
     if (hist) lstm_ws_kernel<true, 8><<<grid, ws_threads(8), WS_SMEM, st>>>(tw0, tw1, thx, p);
-    else if (g_lstm_ws_form == 4) lstm_ws2_kernel<<<grid, WS2_THREADS, WS2_SMEM, st>>>(tw0, tw1, thx, p);
     else lstm_ws_kernel<false, 16><<<grid, ws_threads(16), WS_SMEM, st>>>(tw0, tw1, thx, p);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
@@ -804,4 +515,3 @@ int launch_lstm_ws(const void* xproj, void* out, void* final_h, const int* q_off
 }  // namespace stair
 
 extern "C" int stair_set_lstm_ws(int on) { stair::g_lstm_ws = on ? 1 : 0; return STAIR_OK; }
-extern "C" int stair_set_lstm_ws_form(int form) { if (form != 3 && form != 4) return STAIR_ERR_ARG; stair::g_lstm_ws_form = form; return STAIR_OK; }
