@@ -30,8 +30,9 @@ def run(ph, n=10):
 
 
 outs = {}
-for name, ws in (('streaming (lstm_fused)', 0), ('weight-stationary (lstm_ws)', 1)):
+for name, ws, cg in (('streaming (lstm_fused)', 0, 4), ('streaming, 16 gate-serial warps', 0, 8), ('weight-stationary (lstm_ws)', 1, 4)):
     lib.stair_set_lstm_ws(ws)
+    lib.stair_lstm_colgroups(cg)
     both = run(L.FWD_ENCODE_VIDEO | L.FWD_ENCODE_TEXT)
     text = run(L.FWD_ENCODE_TEXT)
     video = run(L.FWD_ENCODE_VIDEO)
@@ -42,6 +43,7 @@ for name, ws in (('streaming (lstm_fused)', 0), ('weight-stationary (lstm_ws)', 
     print('%-40s video+text %.3f ms   text only %.3f   video only %.3f   whole forward %.3f   (GEMMs included; gemm error flag %d)'
           % (name, both, text, video, full, lib.stair_gemm_error_flag()), flush=True)
 lib.stair_set_lstm_ws(0)
+lib.stair_lstm_colgroups(4)
 ref = outs['streaming (lstm_fused)']
 for name, o in outs.items():
     print('%-40s max |x - streaming|: video_feat %.3g, token_feature %.3g, question_feature %.3g'

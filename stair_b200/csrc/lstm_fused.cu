@@ -275,16 +275,66 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
 #pragma unroll
                 for (int sb = 0; sb < SBN; ++sb) {
                     const int u0 = c * 64 + halfsel * (SBN * 8) + sb * 8;    // 8 hidden units u0 .. u0+7 (one 16-byte chunk of the h row)
-                    uint32_t gi[8], gf[8], gg[8], go[8];
+                    // GS (16 epilogue warps, 96 registers): the gates are taken from TMEM two at a time -- i and g first (their product is
+                    // all the cell update needs of them), then f and o into the same registers -- so that no 32-value gate set is ever live
+                    constexpr bool GS = !HIST && CG == 8;
+                    uint32_t gi[8], gf[GS ? 1 : 8], gg[8], go[GS ? 1 : 8];
+                    const uint32_t t = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                       static_cast<uint32_t>(acc * 256 + halfsel * (SBN * 8) + sb * 8);
                     if (s > 0) {                                      // tcgen05.ld / wait::ld are .sync.aligned: the whole warp, converged
-                        const uint32_t t = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                           static_cast<uint32_t>(acc * 256 + halfsel * (SBN * 8) + sb * 8);
-                        tmem_ld8(t, gi); tmem_ld8(t + 64, gf); tmem_ld8(t + 128, gg); tmem_ld8(t + 192, go);
+                        if constexpr (GS) { tmem_ld8(t, gi); tmem_ld8(t + 128, gg); }
+                        else { tmem_ld8(t, gi); tmem_ld8(t + 64, gf); tmem_ld8(t + 128, gg); tmem_ld8(t + 192, go); }
                         tmem_ld_wait();
                     }
                     const uint32_t ch = static_cast<uint32_t>(halfsel * SBN + sb);
                     const uint32_t a0 = static_cast<uint32_t>(c) * LF_KB_BYTES + rowoff + ((ch ^ sw) << 4);
-                    if (active) {
+                    if constexpr (GS) {
+                        float ig_g[8];
+                        if (active) {
+                            float fi[8], fg[8];
+                            unpack8(xq[sb][0], fi); unpack8(xq[sb][2], fg);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float pi = fi[j], pg = fg[j];
+                                if (s > 0) { pi += __uint_as_float(gi[j]); pg += __uint_as_float(gg[j]); }
+                                ig_g[j] = fast_sigmoid(pi) * fast_tanh(pg);
+                            }
+                        }
+                        if (s > 0) { tmem_ld8(t + 64, gi); tmem_ld8(t + 192, gg); tmem_ld_wait(); }      // f -> gi, o -> gg (converged again)
+                        if (active) {
+                            float ff[8], fo[8], cn[8];
+                            unpack8(xq[sb][1], ff); unpack8(xq[sb][3], fo);
+                            uint32_t hp[4];
+#pragma unroll
+                            for (int jp = 0; jp < 4; ++jp) {
+                                float hv[2];
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int j = 2 * jp + e;
+                                    float pf = ff[j], po = fo[j], cp = 0.0f;
+                                    if (s > 0) {
+                                        pf += __uint_as_float(gi[j]); po += __uint_as_float(gg[j]);
+                                        cp = j < 4 ? (&cnext[0].x)[j] : (&cnext[1].x)[j - 4];
+                                    }
+                                    const float cc = fast_sigmoid(pf) * cp + ig_g[j];
+                                    cn[j] = cc;
+                                    hv[e] = fast_sigmoid(po) * fast_tanh(cc);
+                                }
+                                hp[jp] = pack_bf16(hv[0], hv[1]);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 2; ++q)
+                                *reinterpret_cast<float4*>(c_ptr(s, u0, q)) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
+                            *reinterpret_cast<uint4*>(orow + u0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                            if (last) *reinterpret_cast<uint4*>(sq.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                            st_shared_v4(h_dst + a0, hp[0], hp[1], hp[2], hp[3]);
+                            if (DUP) st_shared_v4(h_dst + a0 + DUP, hp[0], hp[1], hp[2], hp[3]);
+                        } else {
+                            const uint4 p0 = ld_shared_v4(h_src + a0);
+                            st_shared_v4(h_dst + a0, p0.x, p0.y, p0.z, p0.w);
+                            if (DUP) st_shared_v4(h_dst + a0 + DUP, p0.x, p0.y, p0.z, p0.w);
+                        }
+                    } else if (active) {
                         float fi[8], ff[8], fg[8], fo[8], cn[8];
                         unpack8(xq[sb][0], fi); unpack8(xq[sb][1], ff); unpack8(xq[sb][2], fg); unpack8(xq[sb][3], fo);
                         const float cprev[8] = {cnext[0].x, cnext[0].y, cnext[0].z, cnext[0].w, cnext[1].x, cnext[1].y, cnext[1].z, cnext[1].w};

@@ -457,8 +457,7 @@ static int lstm_ws_default() {                       // STAIR_LSTM_WS=0|1 overri
     const char* e = getenv("STAIR_LSTM_WS");
     return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 0;
 }
-static int g_lstm_ws = lstm_ws_default();
-static int g_lstm_ws_form = 4;                  // inference form of the weight-stationary kernel: 4 = shared-memory staged xproj (lstm_ws2_kernel), 3 = direct global loads      // 1 = weight-stationary cluster kernel when eligible, 0 = lstm_fused.cu always
+static int g_lstm_ws = lstm_ws_default();      // 1 = weight-stationary cluster kernel when eligible, 0 = lstm_fused.cu always
 
 bool lstm_ws_ok(int precision, int h, int B) {
     return g_lstm_ws && precision == STAIR_BF16 && h == WS_H && B > 0;
