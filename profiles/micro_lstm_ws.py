@@ -30,8 +30,11 @@ def run(ph, n=10):
 
 
 outs = {}
-for name, ws, cg in (('streaming (lstm_fused)', 0, 4), ('streaming, 16 gate-serial warps', 0, 8), ('weight-stationary (lstm_ws)', 1, 4)):
+for name, ws, rows, cg in (('streaming (lstm_fused)', 0, 64, 4), ('streaming 64 rows, 16 gate-serial warps', 0, 64, 8),
+                           ('streaming 128 rows, 8 warps (round 1)', 0, 128, 2),
+                           ('weight-stationary (lstm_ws)', 1, 64, 4)):
     lib.stair_set_lstm_ws(ws)
+    lib.stair_lstm_rows(rows)
     lib.stair_lstm_colgroups(cg)
     both = run(L.FWD_ENCODE_VIDEO | L.FWD_ENCODE_TEXT)
     text = run(L.FWD_ENCODE_TEXT)
@@ -40,11 +43,12 @@ for name, ws, cg in (('streaming (lstm_fused)', 0, 4), ('streaming, 16 gate-seri
     st = model.forward_batch(batch, phases=L.FWD_ENCODE_VIDEO | L.FWD_ENCODE_TEXT)
     torch.cuda.synchronize()
     outs[name] = (st.vid[:B * T * 512].float().clone(), st.tokfeat[:batch.n_tok * 512].float().clone(), st.qfeat[:B * 512].float().clone())
-    print('%-40s video+text %.3f ms   text only %.3f   video only %.3f   whole forward %.3f   (GEMMs included; gemm error flag %d)'
+    print('%-42s video+text %.3f ms   text only %.3f   video only %.3f   whole forward %.3f   (GEMMs included; gemm error flag %d)'
           % (name, both, text, video, full, lib.stair_gemm_error_flag()), flush=True)
 lib.stair_set_lstm_ws(0)
+lib.stair_lstm_rows(64)
 lib.stair_lstm_colgroups(4)
 ref = outs['streaming (lstm_fused)']
 for name, o in outs.items():
-    print('%-40s max |x - streaming|: video_feat %.3g, token_feature %.3g, question_feature %.3g'
+    print('%-42s max |x - streaming|: video_feat %.3g, token_feature %.3g, question_feature %.3g'
           % (name, *(float((a - b).abs().max()) for a, b in zip(o, ref))))
