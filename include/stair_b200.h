@@ -231,6 +231,9 @@ int stair_set_lanes(int lanes);
 /* module-phase scheduling: 1 (default) = by data dependency when StairBatch.group_deps is given (per-group events, no barrier between the
  * schedule waves); 0 = wave by wave (fork / join around every wave) */
 int stair_set_dep_sched(int on);
+/* debug: timing events around every module group of the dependency-scheduled phase; read returns the number of groups (synchronises) */
+int stair_debug_timeline(int on);
+int stair_debug_timeline_read(float* t0_ms, float* t1_ms, int* lane, int* op, int* count, int* variant, int cap);
 /* encoder recurrence implementation: 0 = fused persistent kernel when eligible (default), 1 = per-step GEMM + cell kernels */
 int stair_set_lstm_impl(int impl);
 /* bf16 recurrence at h = 256: 1 (default) = weight-stationary cluster kernel (csrc/lstm_ws.cu: W_hh resident in the shared memory of a 4-CTA

@@ -445,6 +445,12 @@ inline LaneStreams* lane_streams() {
     return &ls;
 }
 
+// Debug timeline of the dependency-driven module phase (stair_debug_timeline): timing events around every group, read back by
+// stair_debug_timeline_read.  Off by default; the events perturb the schedule by a fraction of a microsecond per group.
+struct Timeline { cudaEvent_t origin, t0[MAX_SCHED_GROUPS], t1[MAX_SCHED_GROUPS]; int lane[MAX_SCHED_GROUPS], op[MAX_SCHED_GROUPS], count[MAX_SCHED_GROUPS], variant[MAX_SCHED_GROUPS]; int n = 0; bool ok = false; };
+inline Timeline& timeline_state() { static Timeline t; return t; }
+extern int g_timeline;
+
 extern int g_lanes;      // 1 = everything on the caller's stream; up to LANES
 extern int g_dep_sched;  // 1 = schedule the module groups by data dependency when the batch carries group_deps
 
@@ -461,6 +467,17 @@ inline int run_modules_dep(Ctx& c, LaneStreams* ls) {
     bool used[LANES];
     for (int l = 0; l < lanes; ++l) { tail[l] = -1; lane_end[l] = 0; used[l] = false; }
     if (cudaEventRecord(ls->fork, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
+    Timeline* tl = nullptr;
+    if (g_timeline) {
+        tl = &timeline_state();
+        if (!tl->ok) {
+            cudaEventCreate(&tl->origin);
+            for (int g = 0; g < MAX_SCHED_GROUPS; ++g) { cudaEventCreate(&tl->t0[g]); cudaEventCreate(&tl->t1[g]); }
+            tl->ok = true;
+        }
+        tl->n = ng;
+        cudaEventRecord(tl->origin, c.st);
+    }
     for (int g = 0; g < ng; ++g) {
         const int* deps = c.b.group_deps + static_cast<long long>(g) * STAIR_MAX_GROUP_DEPS;
         const bool all = deps[0] == -2;
@@ -491,7 +508,9 @@ inline int run_modules_dep(Ctx& c, LaneStreams* ls) {
             if (pg < 0) break;
             if (lane_of[pg] != lane && cudaStreamWaitEvent(st, ls->done[pg], 0) != cudaSuccess) return STAIR_ERR_CUDA;
         }
+        if (tl) { cudaEventRecord(tl->t0[g], st); tl->lane[g] = lane; tl->op[g] = c.b.groups[g].op; tl->count[g] = c.b.groups[g].count; tl->variant[g] = c.b.groups[g].variant; }
         STAIR_TRY(run_group(lc, c.b.groups[g], g));
+        if (tl) cudaEventRecord(tl->t1[g], st);
         if (cudaEventRecord(ls->done[g], st) != cudaSuccess) return STAIR_ERR_CUDA;
         lane_of[g] = lane;
         tail[lane] = g;

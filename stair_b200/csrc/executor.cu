@@ -13,6 +13,7 @@ namespace stair {
 namespace ex {
 int g_lstm_impl = 0;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
 thread_local long long t_last_launches = 0;
+int g_timeline = 0;
 int g_dep_sched = 1;         // 1 = dependency-driven module scheduling when the batch carries group_deps
 int g_lanes = 8;             // round 1 (wave scheduling), B = 4096 RX: 2 / 4 / 6 / 8 lanes = 1.64 / 1.65 / 1.54 / 1.55 ms per forward; round 2
                              // (dependency scheduling): 4 / 6 / 8 lanes = 1.365 / 1.36 / 1.34 ms vs 1.41-1.43 ms wave by wave (profiles/r2_dep_sched_ab.txt)
@@ -24,6 +25,20 @@ using namespace stair;
 using namespace stair::ex;
 
 extern "C" int stair_set_lstm_impl(int impl) { g_lstm_impl = impl; return STAIR_OK; }
+extern "C" int stair_debug_timeline(int on) { g_timeline = on ? 1 : 0; return STAIR_OK; }
+// start / end of every group of the last dependency-scheduled module phase, in ms after the phase began (device must be idle: synchronises)
+extern "C" int stair_debug_timeline_read(float* t0, float* t1, int* lane, int* op, int* count, int* variant, int cap) {
+    Timeline& tl = timeline_state();
+    if (!tl.ok) return 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return STAIR_ERR_CUDA;
+    const int n = tl.n < cap ? tl.n : cap;
+    for (int g = 0; g < n; ++g) {
+        cudaEventElapsedTime(&t0[g], tl.origin, tl.t0[g]);
+        cudaEventElapsedTime(&t1[g], tl.origin, tl.t1[g]);
+        lane[g] = tl.lane[g]; op[g] = tl.op[g]; count[g] = tl.count[g]; variant[g] = tl.variant[g];
+    }
+    return n;
+}
 extern "C" int stair_set_dep_sched(int on) { g_dep_sched = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_lanes(int lanes) { g_lanes = lanes < 1 ? 1 : (lanes > LANES ? LANES : lanes); return STAIR_OK; }
 extern "C" int stair_version(void) { return STAIR_ABI_VERSION; }

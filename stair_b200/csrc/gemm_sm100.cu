@@ -226,8 +226,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     tmem_ld_wait();
 }
 
-template <int BN, int STAGES, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS + 128 * (EPI - 1), 1)
+// OCC = CTAs per SM the kernel is built for.  OCC = 2 (BN = 128, two pipeline stages, 99 KB of shared memory, 256 TMEM columns) was written
+// for the module phase, whose GEMMs are a few microseconds of tensor work behind ~8 us of fixed latency (launch, barrier / TMEM set-up,
+// first operand fetch, epilogue drain): two resident CTAs per SM let the GEMMs of two lanes run side by side.  Measured: no gain (the phase
+// is bound by the length of its dependency chains, not by SM slots), so it is a comparison form (stair_set_gemm_small).
+template <int BN, int STAGES, int EPI, int OCC>
+__global__ void __launch_bounds__(GEMM_THREADS + 128 * (EPI - 1), OCC)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     using S = GemmSmem<BN, STAGES, EPI>;
@@ -704,12 +708,15 @@ int* err_flag_ptr() {
     return g_err_flag;
 }
 
-template <int BN, int STAGES, int EPI = 1>
+template <int BN, int STAGES, int EPI = 1, int OCC = 1>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, cudaStream_t st) {
     using S = GemmSmem<BN, STAGES, EPI>;
+    static_assert(OCC == 1 || (OCC * (S::TOTAL + 1024) <= 228 * 1024 && OCC * 2 * BN <= 512), "co-resident CTAs must share the SM's shared memory and TMEM");
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES, EPI, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+            return STAIR_ERR_CUDA;
+        if (OCC > 1 && cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES, EPI, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess)
             return STAIR_ERR_CUDA;
         configured = true;
     }
@@ -726,8 +733,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
         }
     }
     const int items = tiles * q.ksplit;
-    const int grid = items < g_num_sms ? items : g_num_sms;
-    gemm_tcgen05_kernel<BN, STAGES, EPI><<<grid, GEMM_THREADS + 128 * (EPI - 1), S::TOTAL, st>>>(ta, tb, tc, q);
+    const int grid = items < OCC * g_num_sms ? items : OCC * g_num_sms;
+    gemm_tcgen05_kernel<BN, STAGES, EPI, OCC><<<grid, GEMM_THREADS + 128 * (EPI - 1), S::TOTAL, st>>>(ta, tb, tc, q);
     STAIR_CHECK_LAUNCH();
     return STAIR_OK;
 }
@@ -768,6 +775,9 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CU
 }
 
 thread_local long long g_launch_count = 0;
+static int small_default() { const char* e = getenv("STAIR_GEMM_SMALL"); return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 0; }
+static int g_gemm_small = small_default();      // 1 = module-sized GEMMs (N <= 1024, at most a few waves of tiles) use the two-CTAs-per-SM form.  Off:
+                                                // bit-identical and no faster (1.331 vs 1.337 ms per forward, profiles/r2_module_phase_analysis.txt)
 
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0) return STAIR_OK;
@@ -812,7 +822,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     // tiles move 25 % fewer bytes but double the same-address atomics of the split-K epilogue and measured slower (g_dw_wide).
     // CTA-pair kernel: no gather, N a multiple of 256, and enough 256 x 256 tiles (a quarter wave) — or, for the accumulating weight-gradient
     // contractions (few output tiles, K in the tens of thousands), enough K to split over the pairs
-    {
+    const bool small = g_gemm_small && a.nplanes == 1 && !a.mn_major && !a.accumulate && a.N > 64 && a.N <= 1024 && tiles128 <= 8 * g_num_sms;
+    if (!small) {
         const int tiles256 = ceil_div(a.M, 2 * BM) * (a.N / 256);
         const bool legal = !gather && p.vec_ok && g_epilogue_impl == 0 && a.N % 256 == 0 && g_num_sms >= 2 && (!a.mn_major || g_pair_mn);
         // (split-K weight gradients with a handful of 256 x 256 output tiles stay on the single-CTA kernel unless forced: every K split adds a
@@ -841,7 +852,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
             return epi2 ? launch_tc_pair<5, 2>(ta, tb, tc, p, st) : launch_tc_pair<6, 1>(ta, tb, tc, p, st);
         }
     }
-    const int bn = a.N <= 64 ? 64 : ((a.N % 256 == 0 && (tiles128 > g_wide_tiles_min * g_num_sms / 2 || (a.mn_major && g_dw_wide))) ? 256 : 128);
+    const int bn = a.N <= 64 ? 64 : ((!small && a.N % 256 == 0 && (tiles128 > g_wide_tiles_min * g_num_sms / 2 || (a.mn_major && g_dw_wide))) ? 256 : 128);
     CUtensorMap ta, tb;
     int rc;
     if (a.mn_major) {
@@ -862,6 +873,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     }
     // short K loops are epilogue-bound: two epilogue warp sets, one pipeline stage fewer (see GemmSmem)
     const bool epi2 = g_gemm_epi2 && p.num_kb * p.nseg <= 8 && !a.mn_major;
+    if (small) return launch_tc<128, 2, 1, 2>(ta, tb, tc, p, st);
     if (bn == 64) return launch_tc<64, 8>(ta, tb, tc, p, st);
     if (bn == 256) return epi2 ? launch_tc<256, 3, 2>(ta, tb, tc, p, st) : launch_tc<256, 4>(ta, tb, tc, p, st);
     return epi2 ? launch_tc<128, 5, 2>(ta, tb, tc, p, st) : launch_tc<128, 6>(ta, tb, tc, p, st);
@@ -874,6 +886,7 @@ using namespace stair;
 extern "C" int stair_set_gemm_impl(int impl) { g_gemm_impl = impl; return STAIR_OK; }
 extern "C" int stair_set_gemm_pair_mn(int on) { g_pair_mn = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_pair(int mode) { g_pair_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return STAIR_OK; }
+extern "C" int stair_set_gemm_small(int on) { g_gemm_small = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_epi2(int on) { g_gemm_epi2 = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_wide_min(int half_waves) { g_wide_tiles_min = half_waves < 0 ? 0 : half_waves; return STAIR_OK; }
 extern "C" int stair_set_gemm_dw_wide(int on) { g_dw_wide = on ? 1 : 0; return STAIR_OK; }
