@@ -214,6 +214,38 @@ def grad_targets(sub, config):
     return t
 
 
+def all_parameters(root):
+    """``list(root.parameters())`` without the name bookkeeping of ``nn.Module.named_parameters`` (a 10x cheaper walk: this runs
+    several times per step to detect changed weights).  Same order, shared modules / parameters listed once.  The module tree is
+    walked once and its ``_parameters`` dicts are remembered (they are live: a replaced Parameter is seen; submodules added to an
+    existing model afterwards are not — call ``all_parameters(root, rescan=True)``)."""
+    return _walk_parameters(root, False)
+
+
+def _walk_parameters(root, rescan):
+    dicts = None if rescan else root.__dict__.get('_stair_param_dicts')
+    if dicts is None:
+        dicts, seen_m, stack = [], set(), [root]
+        while stack:
+            m = stack.pop()
+            if id(m) in seen_m:
+                continue
+            seen_m.add(id(m))
+            if m._parameters:
+                dicts.append(m._parameters)
+            stack.extend(reversed([c for c in m._modules.values() if c is not None]))
+        root.__dict__['_stair_param_dicts'] = dicts
+    out = [p for d in dicts for p in d.values() if p is not None]
+    if len(set(map(id, out))) != len(out):                  # tied parameters: list each once, first occurrence wins
+        seen, uniq = set(), []
+        for p in out:
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        out = uniq
+    return out
+
+
 class PackedWeights:
     """Device copies of the weights in the layout the kernels read, rebuilt when a parameter changes."""
 
@@ -223,13 +255,14 @@ class PackedWeights:
         self.transposed = {}
         self.want_transposed = False
         self.model_struct = None
+        self.version = 0
 
     def mark_current(self, sub, precision, device):
         """The packed copies were just rewritten from the parameters by ``stair_adam_multi`` (train.FusedAdam)."""
-        self.signature = (precision, str(device)) + tuple((p.data_ptr(), p._version) for p in sub.parameters())
+        self.signature = (precision, str(device)) + tuple((p.data_ptr(), p._version) for p in all_parameters(sub))
 
     def refresh(self, sub, config, precision, device, training=False):
-        params = [p for p in sub.parameters()]
+        params = all_parameters(sub)
         sig = (precision, str(device)) + tuple((p.data_ptr(), p._version) for p in params)
         training = training or self.want_transposed          # once a model trains, keep the transposed copies current
         if sig == self.signature and (not training or self.transposed):
@@ -263,4 +296,5 @@ class PackedWeights:
             m.w[wid] = tensors[wid].data_ptr() if wid in tensors else None
             m.wt[wid] = transposed[wid].data_ptr() if wid in transposed else None
         self.tensors, self.transposed, self.model_struct, self.signature = tensors, transposed, m, sig
+        self.version += 1                                   # generation of the packed copies (consumers cache raw pointers into them)
         return m

@@ -301,6 +301,34 @@ class NMNTrainStep:
             self._targets, self._offsets, self._flat_numel = tg, off, o
         return self._targets, self._offsets, self._flat_numel
 
+    def _grad_views(self):
+        """(sizes of the consecutive pieces of the flat buffer, [(slot id, piece index, parameter, shares-its-piece)])."""
+        if getattr(self, '_views', None) is None:
+            tg, offsets, total = self._layout()
+            regions = {}                                                     # (start, numel) -> piece index, in address order
+            for wid, (_, targets) in tg.items():
+                for prm, o in targets:
+                    regions.setdefault((offsets[wid] + o, prm.numel()), None)
+            cuts, pos = [], 0
+            for k, (start, numel) in enumerate(sorted(regions)):
+                if start < pos:
+                    raise L.StairError('overlapping gradient regions in the flat buffer')
+                if start > pos:
+                    cuts.append(start - pos)                                 # alignment gap
+                regions[(start, numel)] = len(cuts)
+                cuts.append(numel)
+                pos = start + numel
+            if pos < total:
+                cuts.append(total - pos)
+            entries, seen = [], set()
+            for wid, (_, targets) in tg.items():
+                for prm, o in targets:
+                    key = (offsets[wid] + o, prm.numel())
+                    entries.append((wid, regions[key], prm, key in seen))
+                    seen.add(key)
+            self._views = (cuts, entries)
+        return self._views
+
     def _buf(self, name, numel, dtype, device):
         t = self._cache.get(name)
         if t is None or t.numel() < numel or t.dtype != dtype or t.device != device:
@@ -485,18 +513,15 @@ class NMNTrainStep:
                 dist.all_reduce(flat, group=self.group)                    # NCCL sum over NVLink: gradients
                 dist.all_reduce(loss, group=self.group)
         if assign_grads:
-            for wid, (numel, targets) in tg.items():
-                if wid not in touched:
+            cuts, entries = self._grad_views()
+            pieces = torch.split_with_sizes(flat, cuts)                     # one call: a view per parameter region of the flat buffer
+            for wid, piece, prm, dup in entries:
+                if wid not in touched or not prm.requires_grad:
                     continue
-                used = set()
-                for prm, o in targets:
-                    if not prm.requires_grad:
-                        continue
-                    g = flat[offsets[wid] + o: offsets[wid] + o + prm.numel()].view_as(prm)
-                    if o in used:
-                        g = g.clone()                                        # the two LSTM biases of a direction share a slot
-                    used.add(o)
-                    prm.grad = g if prm.grad is None else prm.grad + g
+                g = pieces[piece].view(prm.shape)
+                if dup:
+                    g = g.clone()                                            # the two LSTM biases of a direction share a slot
+                prm.grad = g if prm.grad is None else prm.grad + g
         self.last = dict(state=st, plan=pl, flat=flat, offsets=offsets, touched=touched, train=tr, cls_rep=cls_rep)
         return {'logits': st.logits, 'answers': st.answers, 'loss_terms': loss, 'loss': loss[:8].sum(), 'loss_counts': dict(rows.counts),
                 'state': st}
@@ -560,6 +585,49 @@ class FusedAdam(torch.optim.Adam):
         super().__init__(model.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=0.0)
         self.model = model
         self._slots = None
+        self._seg, self._seg_key, self._book, self._covered = None, None, {}, set()
+
+    def _build_segments(self, slots, active, pw):
+        """ctypes segment array + per-segment (parameter, twin, bookkeeping) rows for the parameters ``active`` (indices into the slot
+        table); gradient pointers and bias corrections are filled in by ``step``."""
+        arr = (L.StairAdamSeg * len(active))()
+        rows, tile0 = [], 0
+        for j, i in enumerate(active):
+            wid, kind, prm, prm2, off, perm_wid = slots[i]
+            L.require_cuda(prm, 'parameter')
+            sg = arr[j]
+            st = self._state_of(prm)
+            book = self._book.setdefault(id(prm), {'state': st, 'k': int(st['step'])})
+            sg.p, sg.m, sg.v = prm.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr()
+            book2 = None
+            if prm2 is not None:
+                s2 = self._state_of(prm2)
+                book2 = self._book.setdefault(id(prm2), {'state': s2, 'k': int(s2['step'])})
+                sg.p2, sg.m2, sg.v2 = prm2.data_ptr(), s2['exp_avg'].data_ptr(), s2['exp_avg_sq'].data_ptr()
+            packed = pw.tensors[wid]
+            if kind == 'V':
+                sg.kind, sg.nplanes, sg.rows, sg.cols = 0, 1, 1, prm.numel()
+                sg.packed = packed.data_ptr() + 4 * off
+                ntiles = (prm.numel() + 1023) // 1024
+            else:
+                rws = prm.shape[0]
+                cols = prm.numel() // rws
+                nplanes = packed.shape[0] if packed.dim() == 3 else 1
+                n_total, ld = packed.shape[-2], packed.shape[-1]
+                row_off = off // cols
+                sg.kind, sg.nplanes, sg.rows, sg.cols = 1, nplanes, rws, cols
+                sg.packed, sg.packed_ld, sg.packed_plane = packed.data_ptr() + 2 * row_off * ld, ld, n_total * ld
+                tt = pw.transposed.get(wid)
+                if tt is not None:
+                    ld_t = tt.shape[-1]
+                    sg.packed_t, sg.packed_t_ld, sg.packed_t_plane = tt.data_ptr() + 2 * row_off, ld_t, tt.shape[-2] * ld_t
+                if perm_wid is not None and perm_wid in pw.tensors:
+                    sg.packed_perm, sg.perm_hh = pw.tensors[perm_wid].data_ptr(), cols
+                ntiles = ((rws + 63) // 64) * ((cols + 63) // 64)
+            sg.tile0 = tile0
+            tile0 += ntiles
+            rows.append((prm, prm2, book, book2))
+        return arr, rows, tile0
 
     def _slot_table(self):
         if self._slots is None:
@@ -587,7 +655,16 @@ class FusedAdam(torch.optim.Adam):
                     for prm, o in targets:
                         slots.append((wid, 'M', prm, None, o, perm_of.get(wid)))
             self._slots = slots
+            self._covered = set()
+            for _, _, prm, prm2, _, _ in slots:
+                self._covered.add(id(prm))
+                if prm2 is not None:
+                    self._covered.add(id(prm2))
         return self._slots
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._seg, self._seg_key, self._book = None, None, {}               # the cached table points at the old moment tensors
 
     def _state_of(self, p):
         s = self.state[p]
@@ -611,58 +688,40 @@ class FusedAdam(torch.optim.Adam):
         pw = model._packed
         pw.refresh(model.submodules, model.config, PRECISIONS[model.precision], dev, training=True)   # no-op when current
         lib = L.lib()
-        segs, covered, tile0 = [], set(), 0
-        for wid, kind, prm, prm2, off, perm_wid in self._slot_table():
-            covered.add(id(prm))
-            if prm2 is not None:
-                covered.add(id(prm2))
-            if prm.grad is None or (prm2 is not None and prm2.grad is None):
-                continue
-            L.require_cuda(prm, 'parameter')
-            sg = L.StairAdamSeg()
-            st = self._state_of(prm)
-            st['step'] += 1
-            k = float(st['step'])
-            sg.bc1, sg.bc2 = 1.0 - b1 ** k, 1.0 - b2 ** k
-            g = prm.grad if prm.grad.is_contiguous() else prm.grad.contiguous()
-            sg.p, sg.g, sg.m, sg.v = prm.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr()
-            keep = [g]
-            if prm2 is not None:
-                s2 = self._state_of(prm2)
-                s2['step'] += 1
-                g2 = prm2.grad if prm2.grad.is_contiguous() else prm2.grad.contiguous()
-                sg.p2, sg.g2, sg.m2, sg.v2 = prm2.data_ptr(), g2.data_ptr(), s2['exp_avg'].data_ptr(), s2['exp_avg_sq'].data_ptr()
-                keep.append(g2)
-            packed = pw.tensors[wid]
-            if kind == 'V':
-                sg.kind, sg.nplanes, sg.rows, sg.cols = 0, 1, 1, prm.numel()
-                sg.packed = packed.data_ptr() + 4 * off
-                ntiles = (prm.numel() + 1023) // 1024
-            else:
-                rows = prm.shape[0]
-                cols = prm.numel() // rows
-                nplanes = packed.shape[0] if packed.dim() == 3 else 1
-                n_total, ld = packed.shape[-2], packed.shape[-1]
-                row_off = off // cols
-                sg.kind, sg.nplanes, sg.rows, sg.cols = 1, nplanes, rows, cols
-                sg.packed, sg.packed_ld, sg.packed_plane = packed.data_ptr() + 2 * row_off * ld, ld, n_total * ld
-                tt = pw.transposed.get(wid)
-                if tt is not None:
-                    ld_t = tt.shape[-1]
-                    sg.packed_t, sg.packed_t_ld, sg.packed_t_plane = tt.data_ptr() + 2 * row_off, ld_t, tt.shape[-2] * ld_t
-                if perm_wid is not None and perm_wid in pw.tensors:
-                    sg.packed_perm, sg.perm_hh = pw.tensors[perm_wid].data_ptr(), cols
-                ntiles = ((rows + 63) // 64) * ((cols + 63) // 64)
-            sg.tile0 = tile0
-            tile0 += ntiles
-            segs.append((sg, keep))
-        if segs:
-            arr = (L.StairAdamSeg * len(segs))(*[s for s, _ in segs])
+        slots = self._slot_table()
+        active = tuple(i for i, (wid, kind, prm, prm2, off, perm_wid) in enumerate(slots)
+                       if prm.grad is not None and (prm2 is None or prm2.grad is not None))
+        if active:
+            # the segment table of this set of updated parameters: everything but the gradient pointers and the bias corrections is the
+            # same from step to step, so the ctypes array is built once per (set of parameters, generation of the weight copies) and patched
+            key = (active, pw.version)
+            if self._seg_key != key:
+                self._seg, self._seg_key = self._build_segments(slots, active, pw), key
+            arr, rows, ntiles = self._seg
+            steps, keep = [], []
+            for j, (prm, prm2, book, book2) in enumerate(rows):
+                book['k'] += 1
+                k = book['k']
+                sg = arr[j]
+                sg.bc1, sg.bc2 = 1.0 - b1 ** k, 1.0 - b2 ** k
+                g = prm.grad if prm.grad.is_contiguous() else prm.grad.contiguous()
+                sg.g = g.data_ptr()
+                keep.append(g)
+                steps.append(book['state']['step'])
+                if prm2 is not None:
+                    book2['k'] += 1
+                    g2 = prm2.grad if prm2.grad.is_contiguous() else prm2.grad.contiguous()
+                    sg.g2 = g2.data_ptr()
+                    keep.append(g2)
+                    steps.append(book2['state']['step'])
+            torch._foreach_add_(steps, 1)                                      # state[p]['step'] (torch.optim.Adam's layout), one call
             table = torch.frombuffer(bytearray(arr), dtype=torch.uint8).to(dev, non_blocking=True)
-            L.check(lib.stair_adam_multi(L.ptr(table), L.i32(len(segs)), L.i32(tile0), ctypes.c_float(lr), ctypes.c_double(b1), ctypes.c_double(b2),
-                                         ctypes.c_float(eps), L.stream_ptr()), 'stair_adam_multi')
+            L.check(lib.stair_adam_multi(L.ptr(table), L.i32(len(rows)), L.i32(ntiles), ctypes.c_float(lr), ctypes.c_double(b1),
+                                         ctypes.c_double(b2), ctypes.c_float(eps), L.stream_ptr()), 'stair_adam_multi')
+            del keep
             # the update (and the refresh of the packed copies) happened behind torch's back: keep PackedWeights' signature valid
             pw.mark_current(model.submodules, PRECISIONS[model.precision], dev)
+        covered = self._covered
         # parameters outside the weight table (none in the reference model) fall back to the per-tensor kernel + a full re-pack
         for prm in group['params']:
             if id(prm) in covered or prm.grad is None:

@@ -75,6 +75,40 @@ def test_grad_slots_cover_every_trainable_tensor_once():
     assert L.W['COUNT'] > max(tg)
 
 
+def test_fast_parameter_walk_equals_module_parameters():
+    """params.all_parameters is the per-forward replacement of nn.Module.parameters(): same tensors, same order, shared modules
+    (Superlative.localize_module is Localize, module_net.py:33) listed once."""
+    from stair_b200 import synthetic as syn
+    from stair_b200.params import all_parameters
+    cfg = syn.model_config(T=8, V=128, hidden=64, object_types=16)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES)
+    for root in (model, model.submodules):
+        assert [id(p) for p in all_parameters(root)] == [id(p) for p in root.parameters()]
+
+
+def test_flat_gradient_pieces_tile_the_buffer():
+    """NMNTrainStep hands out the gradients as views of ONE flat buffer cut by a single split_with_sizes call: the pieces must tile
+    the buffer and every parameter's piece must have its size; only the twin LSTM biases share a piece."""
+    from stair_b200 import synthetic as syn
+    from stair_b200.train import NMNTrainStep
+    cfg = syn.model_config(T=8, V=128, hidden=64, object_types=16)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES)
+    step = NMNTrainStep(model, distributed=False)
+    cuts, entries = step._grad_views()
+    _, offsets, total = step._layout()
+    assert sum(cuts) == total and all(c > 0 for c in cuts)
+    starts = np.concatenate([[0], np.cumsum(cuts)[:-1]])
+    names = {id(p): k for k, p in model.named_parameters()}
+    shared = 0
+    for wid, piece, prm, dup in entries:
+        assert cuts[piece] == prm.numel()
+        assert offsets[wid] <= starts[piece] < offsets[wid] + max(1, prm.numel()) + (1 << 30)
+        shared += int(dup)
+        if dup:
+            assert 'bias_hh' in names[id(prm)]
+    assert shared == 4                                      # b_hh of 2 encoders x 2 directions
+
+
 def test_create_attention_from_frame_interval_known_answers():
     """module_net.py:190-208 (the worked example in its comments: (0.2, 5.8) -> gold[0] = 0.8, gold[1:5] = 1, gold[5] = 0.8)."""
     from stair_b200.train import create_attention_from_frame_interval
