@@ -21,6 +21,10 @@ opt = FusedAdam(model, lr=2e-4)
 plan = step.plan(batch)
 
 real = L.lib()
+if 'BWD_LANES' in os.environ:
+    real.stair_set_bwd_lanes(int(os.environ['BWD_LANES']))
+if 'DEP' in os.environ:
+    real.stair_set_dep_sched(int(os.environ['DEP']))
 marks = []
 
 
@@ -55,6 +59,6 @@ L._lib = real
 agg = {}
 for name, e0, e1, n in marks:
     a = agg.setdefault(name, [0.0, 0, 0]); a[0] += e0.elapsed_time(e1); a[1] += 1; a[2] = n
-print('training step, B=%d: %.3f ms per step (events around the whole step)' % (B, tot0.elapsed_time(tot1) / N))
+print('training step, B=%d, bwd lanes %s, dependency scheduling %s: %.3f ms per step (events around the whole step)' % (B, os.environ.get('BWD_LANES', 'default'), os.environ.get('DEP', 'default'), tot0.elapsed_time(tot1) / N))
 for name, (ms, k, n) in agg.items():
     print('  %-32s %.3f ms per step  (%d launches)' % (name, ms / N, n))

@@ -656,7 +656,8 @@ int group_bwd(BCtx& b, int gi) {
     return STAIR_OK;
 }
 
-int g_bwd_lanes = 4;      // 1 = groups one after the other on the caller's stream; > 1 = the groups of a schedule wave on concurrent streams
+int g_bwd_lanes = 8;      // 1 = groups one after the other on the caller's stream; > 1 = concurrent streams.  Training step at B = 4096: wave by wave on
+                          // 4 / 8 lanes 6.04 / 6.06 ms, by dependency on 4 / 6 / 8 lanes 5.91 / 5.90 / 5.85 ms (profiles/r2_train_bwd_sched.txt)
 
 // Module backward: groups in reverse schedule order.  The groups of one wave are independent of each other in the backward pass too
 // (they read their own output gradients and ADD into shared gradient arenas / parameter gradients with atomics), so with
@@ -688,6 +689,59 @@ int modules_bwd(BCtx& b) {
     if (b.ws.overflow) return STAIR_ERR_CAPACITY;
     LaneStreams* ls = lane_streams();
     if (!ls) return STAIR_ERR_CUDA;
+    if (g_dep_sched && c.b.group_deps && ng <= MAX_SCHED_GROUPS) {
+        // Dependency-driven order (the mirror image of run_modules_dep): the backward of group g may start as soon as every CONSUMER of
+        // its outputs has been back-propagated (their kernels add into g's output-gradient slots), not when the whole later wave has.
+        const int* deps = c.b.group_deps;
+        int lane_of[MAX_SCHED_GROUPS], tail[LANES];
+        long long lane_end[LANES], finish[MAX_SCHED_GROUPS];
+        bool used[LANES];
+        for (int l = 0; l < max_lanes; ++l) { tail[l] = -1; lane_end[l] = 0; used[l] = false; }
+        if (cudaEventRecord(ls->fork, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
+        auto consumes = [&](int cg, int g) {                       // does group cg read an output of group g?
+            const int* d = deps + static_cast<long long>(cg) * STAIR_MAX_GROUP_DEPS;
+            if (d[0] == -2) return true;                           // "everything before me"
+            for (int k = 0; k < STAIR_MAX_GROUP_DEPS && d[k] >= 0; ++k) if (d[k] == g) return true;
+            return false;
+        };
+        for (int g = ng - 1; g >= 0; --g) {
+            long long ready = 0;
+            int latest = -1;
+            for (int cg = g + 1; cg < ng; ++cg)
+                if (consumes(cg, g) && finish[cg] >= ready) { ready = finish[cg]; latest = cg; }
+            int lane = -1;
+            if (latest >= 0 && tail[lane_of[latest]] == latest) lane = lane_of[latest];
+            else {
+                lane = 0;
+                for (int l = 1; l < max_lanes; ++l) if (lane_end[l] < lane_end[lane]) lane = l;
+            }
+            Ctx lc = c;
+            cudaStream_t st = lane == 0 ? c.st : ls->side[lane - 1];
+            if (lane > 0) { lc.st = st; lc.ws = c.ws + static_cast<long long>(lane) * c.plan.mod_bytes; }
+            if (lane > 0 && !used[lane]) {
+                if (cudaStreamWaitEvent(st, ls->fork, 0) != cudaSuccess) return STAIR_ERR_CUDA;
+                used[lane] = true;
+            }
+            for (int cg = g + 1; cg < ng; ++cg)
+                if (lane_of[cg] != lane && consumes(cg, g) && cudaStreamWaitEvent(st, ls->done[cg], 0) != cudaSuccess) return STAIR_ERR_CUDA;
+            BCtx bl{lc, b.tr, Bump(), false};
+            bl.ws.base = lane_base + lane * chunk_peak; bl.ws.cap = chunk_peak;
+            STAIR_TRY(group_bwd(bl, g));
+            if (bl.ws.overflow) return STAIR_ERR_CAPACITY;
+            if (cudaEventRecord(ls->done[g], st) != cudaSuccess) return STAIR_ERR_CUDA;
+            lane_of[g] = lane;
+            tail[lane] = g;
+            const long long start = ready > lane_end[lane] ? ready : lane_end[lane];
+            finish[g] = lane_end[lane] = start + 2 * group_cost(c.b.groups[g], c.T);
+        }
+        for (int l = 1; l < max_lanes; ++l)
+            if (used[l]) {
+                if (cudaEventRecord(ls->join[l - 1], ls->side[l - 1]) != cudaSuccess) return STAIR_ERR_CUDA;
+                if (cudaStreamWaitEvent(c.st, ls->join[l - 1], 0) != cudaSuccess) return STAIR_ERR_CUDA;
+            }
+        b.ws.off = mark;
+        return STAIR_OK;
+    }
     int gj = ng;
     while (gj > 0) {
         int gi = gj - 1;
