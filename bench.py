@@ -45,6 +45,44 @@ PARITY_PER_RANK_MULTI = 512        # N > 1: questions of every rank's shard chec
 ATT_CHECK_Q = 512                  # questions whose Localize attention maps are pulled back and argmax-compared
 
 
+def algorithmic_step_flops(batch, cfg):
+    """GEMM flops of one inference step over ``batch`` (2·M·K·N per Linear): input projections and recurrences of
+    both encoders, decoder, and every module instance of the batch's layouts."""
+    from stair_b200 import layout as LY, _lib as L
+    H, h, T, V, A = cfg['hidden_size'], cfg['hidden_size'] // 2, batch.T, cfg['video_size'], cfg['answer_vocab_length']
+    B, n_tok, txt = batch.B, batch.n_tok, cfg['text_size']
+    f = B * T * (2.0 * V * 4 * H + 2.0 * h * 4 * H) + n_tok * (2.0 * txt * 4 * H + 2.0 * h * 4 * H)          # 2 directions x 4h gates = 4H
+    f += B * (2.0 * 2 * H * 2 * H + 2.0 * 2 * H * A)
+    lin, frame = 2.0 * H * H, 2.0 * T * H * H
+    groups, _, _ = LY.build_groups(batch, frozenset())
+    names = {v: k for k, v in L.OP.items()}
+    for g in range(batch.n_groups):
+        op, var, n = names[groups[g].op], groups[g].variant, groups[g].count
+        if op == 'LOCALIZE':
+            per = 2 * frame + (var + 1) * lin
+        elif op in ('TEMPORAL', 'HASITEM'):
+            per = frame
+        elif op == 'FILTER':
+            per = 2 * frame + lin
+        elif op == 'FILTERFRAME':
+            per = 3 * frame
+        elif op == 'SUPERLATIVE':
+            kind = var >> 1
+            per = 2 * frame + (1 if kind == 0 else (2 if kind == 1 else T)) * lin + lin
+        elif op in ('COMPARE', 'EQUALS'):
+            per = 2 * lin
+        elif op == 'XOR':
+            per = 3 * lin
+        elif op == 'EXISTS':
+            per = 4 * lin
+        elif op == 'TOACTION':
+            per = 3 * lin
+        else:
+            per = 0.0
+        f += n * per
+    return f
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -591,6 +629,15 @@ def main():
                 'traffic': traffic, 'traffic_source': traffic_src, 'ms': gemm_ms,
                 'flops_per_launch': flops, 'algorithmic_bytes_per_launch': 2.0 * (M * K + N * K + M * N),
                 'step_share': gemm_ms / (ms / args.steps)}
+
+    # whole step against the tensor roof: algorithmic GEMM flops of this rank's batch (encoders, decoder, every module
+    # instance's Linears by the per-instance column of SURVEY 8a) over the device-timed step
+    step_flops = algorithmic_step_flops(batch, cfg)
+    step_tf = step_flops / (ms / args.steps * 1e-3) / 1e12
+    roofline['whole_step'] = {'flops': step_flops, 'mflop_per_question': step_flops / B / 1e6, 'achieved': step_tf, 'unit': 'TFLOP/s',
+                              'frac_of_sustained_peak': step_tf / pk['tf_sustained'], 'frac_of_burst_peak': step_tf / pk['tf_burst'],
+                              'what': 'the step is a chain of 81 launches; the recurrence (latency-bound, 0.40 ms) and the module phase '
+                                      '(0.45 ms of small GEMMs) are not tensor-bound, see DESIGN.md section 4'}
 
     # ---- CPU legs: baseline timing (rank 0, N = 1) and the parity check of this rank's answers against the oracle -------------------
     cpu = None
