@@ -144,3 +144,49 @@ def test_explicit_init_and_shutdown_of_the_library_runtime_objects():
     b = model(qs, return_res_by_step=False, test_mode=True)['logits'].clone()
     torch.cuda.synchronize()
     assert torch.equal(a, b) and lib.stair_gemm_error_flag() == 0
+
+
+def test_module_scheduling_modes_agree_and_the_timeline_hook_reports_every_group():
+    """The module phase can run wave by wave or by data dependency (StairBatch.group_deps), on 1..8 lanes: same kernels, same
+    operands, so the forward is bit-identical in every mode.  The backward adds into shared gradient slots with atomics when groups
+    run concurrently, so its gradients agree to fp32 summation-order noise.  stair_debug_timeline brackets every group with events."""
+    import ctypes
+    from stair_b200 import _lib as L
+    from stair_b200.train import NMNTrainStep
+    lib = L.lib()
+    T, V, hid = 8, 128, 64
+    cfg = dict(syn.model_config(T=T, V=V, hidden=hid, object_types=16), dropout=0.0)
+    torch.manual_seed(6)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().eval()
+    qs = syn.make_questions(300, T, V, seed=21, templates=list(syn.ALL_TEMPLATES), object_types=16, with_gold=True)
+    batch = collate(qs, video_dtype=torch.bfloat16).to('cuda')
+    try:
+        outs, grads = {}, {}
+        for dep, lanes in ((1, 8), (0, 8), (1, 3), (0, 1)):
+            lib.stair_set_dep_sched(dep); lib.stair_set_lanes(lanes); lib.stair_set_bwd_lanes(lanes)
+            outs[(dep, lanes)] = model.forward_batch(batch).logits.clone()
+            step = NMNTrainStep(model.train(), distributed=False)
+            step.run(step.plan(batch), assign_grads=False, dropout_seed=5)
+            grads[(dep, lanes)] = step.last['flat'].clone()
+            model.eval()
+        ref = outs[(1, 8)]
+        assert all(torch.equal(o, ref) for o in outs.values())
+        g0 = grads[(0, 1)]                                                   # one lane: no concurrent adds
+        for k, g in grads.items():
+            assert float((g - g0).abs().max()) <= 1e-4 * float(g0.abs().max()), k
+        # timeline hook (dependency scheduling only)
+        lib.stair_set_dep_sched(1); lib.stair_set_lanes(8)
+        lib.stair_debug_timeline(1)
+        st = model.forward_batch(batch)
+        cap = 96
+        t0 = np.zeros(cap, np.float32); t1 = np.zeros(cap, np.float32)
+        lane, op, cnt, var = (np.zeros(cap, np.int32) for _ in range(4))
+        n = lib.stair_debug_timeline_read(*(a.ctypes.data_as(ctypes.c_void_p) for a in (t0, t1, lane, op, cnt, var)), cap)
+        assert n == batch.n_groups
+        assert (t1[:n] >= t0[:n]).all() and (t0[:n] >= 0).all() and (lane[:n] >= 0).all() and (lane[:n] < 8).all()
+        from stair_b200 import layout as LY
+        groups, _, _ = LY.build_groups(batch, frozenset())
+        assert [int(c) for c in cnt[:n]] == [groups[g].count for g in range(n)] and [int(o) for o in op[:n]] == [groups[g].op for g in range(n)]
+        model.check_status(st)
+    finally:
+        lib.stair_debug_timeline(0); lib.stair_set_dep_sched(1); lib.stair_set_lanes(8); lib.stair_set_bwd_lanes(8)
