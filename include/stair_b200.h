@@ -265,6 +265,7 @@ int stair_set_gemm_wide_min(int half_waves); /* 128 x 256 tiles when a GEMM has 
 int stair_set_gemm_epi2(int on);         /* 1 (default) = two epilogue warp sets (384 threads) for GEMMs with <= 8 k-blocks; 0 = one set always */
 int stair_set_gemm_split_k(int on);      /* 1 (default) = split-K with atomic accumulation for accumulating GEMMs with few output tiles */
 int stair_set_gemm_pair(int mode);       /* CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles per 2-CTA cluster) GEMM: 1 (default) = for K-major, non-gather, non-accumulating GEMMs with N % 256 == 0 and at least a quarter wave of tiles; 0 = never; 2 = whenever legal (tests) */
+int stair_set_gemm_pair_gather(int on);     /* 1 (default): gathered-A GEMMs (frame-arena slots) may use the CTA-pair kernel */
 int stair_set_gemm_pair_mn(int on);      /* 1 (default) = the CTA-pair kernel also runs the MN-major weight-gradient contractions (split-K over the pairs); 0 = K-major GEMMs only */
 int stair_set_gemm_epilogue(int impl);  /* 0 = smem-staged TMA-store epilogue (product); 1 = direct per-row stores (comparison) */
 int stair_gemm_debug_timeline(unsigned long long* dev_buf /* 8 x u64, or NULL to disable */);

@@ -427,7 +427,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // warp 2 of both CTAs) is released only after both CTAs are done.
 // Operands: K-major (every forward / dX GEMM) or MN-major (mn_major: the weight-gradient contraction dW = dZ^T . X read in place, 3-D TMA
 // boxes of 64 k-rows x 64 columns, MN-major UMMA descriptors), optionally split over K (work item = (tile, K range); partial tiles are
-// added with vector atomics by the direct-store epilogue).  Restrictions: no gather, N % 256 == 0 (the launcher falls back otherwise).
+// added with vector atomics by the direct-store epilogue); or K-major with the A rows gathered slot by slot from the frame-feature arena
+// (each CTA's producer warp issues its own 128 rows as 3-D TMA boxes, one lane per slot).  Restriction: N % 256 == 0 (the launcher falls
+// back otherwise).
 // ------------------------------------------------------------------------------------------------
 template <int STAGES, int EPI>
 struct GemmSmem2 {
@@ -488,7 +490,35 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (p.a_slots) {
+            // ===================== TMA producer, gather mode (whole warp: lane j loads slot j of this CTA's 128 A rows) ===============
+            // K-major, one plane.  The leader expects the bytes of BOTH CTAs' valid slots (the last M tile may hold fewer, or none for the peer).
+            const int spt = BM / p.slot_rows;                       // slots per CTA tile
+            int stage = 0; uint32_t phase = 0;
+            for (int item = pair; item < total_tiles; item += npairs) {
+                const int tile = item % mn_tiles;
+                const int m_pair = (tile / tiles_n) * (2 * BM);
+                const int nb = (tile % tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
+                const int s_pair = m_pair / p.slot_rows;
+                const int nv0 = max(0, min(spt, p.num_slots - s_pair)), nv1 = max(0, min(spt, p.num_slots - s_pair - spt));
+                const int s0 = s_pair + static_cast<int>(rank) * spt, nvalid = rank == 0 ? nv0 : nv1;
+                const int my_slot = lane < nvalid ? __ldg(p.a_slots + s0 + lane) : -1;
+                const uint32_t tx_bytes = static_cast<uint32_t>((nv0 + nv1) * p.slot_rows * BK * 2) + 2 * B_STAGE_BYTES;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    uint32_t full_leader = 0;
+                    if (lane == 0) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 201);
+                        full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                        tma_load_2d_pair(sB + stage * B_STAGE_BYTES, &tmB, full_leader, kb * BK, nb);
+                    }
+                    full_leader = __shfl_sync(0xffffffffu, full_leader, 0);      // also orders the slot loads after lane 0's empty-barrier wait
+                    if (my_slot >= 0)
+                        tma_load_3d_pair(sA + stage * A_STAGE_BYTES + lane * p.slot_rows * (BK * 2), &tmA, full_leader, kb * BK, 0, my_slot);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (lane == 0) {
             // ===================== TMA producer (both CTAs; bytes are signalled on the leader's full barrier) =====================
             int stage = 0; uint32_t phase = 0;
             for (int item = pair; item < total_tiles; item += npairs) {
@@ -743,6 +773,7 @@ static int pair_mode_default() {                       // STAIR_GEMM_PAIR=0|1|2 
     const char* e = getenv("STAIR_GEMM_PAIR");
     return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
 }
+static int g_pair_gather = 1;                       // 1 = the CTA-pair kernel also serves gathered (frame-arena) A operands
 static int g_pair_mn = 1;                           // 1 = the CTA-pair kernel also serves MN-major (weight-gradient) GEMMs; 0 = K-major only (comparison)
 static int g_pair_mode = pair_mode_default();      // 1 (default) = CTA-pair (cta_group::2) kernel for eligible GEMMs, 0 = never, 2 = whenever legal (tests)
 
@@ -825,7 +856,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     const bool small = g_gemm_small && a.nplanes == 1 && !a.mn_major && !a.accumulate && a.N > 64 && a.N <= 1024 && tiles128 <= 8 * g_num_sms;
     if (!small) {
         const int tiles256 = ceil_div(a.M, 2 * BM) * (a.N / 256);
-        const bool legal = !gather && p.vec_ok && g_epilogue_impl == 0 && a.N % 256 == 0 && g_num_sms >= 2 && (!a.mn_major || g_pair_mn);
+        const bool legal = (!gather || g_pair_gather) && p.vec_ok && g_epilogue_impl == 0 && a.N % 256 == 0 && g_num_sms >= 2 && (!a.mn_major || g_pair_mn);
         // (split-K weight gradients with a handful of 256 x 256 output tiles stay on the single-CTA kernel unless forced: every K split adds a
         // whole 256 KB tile with atomics, twice the atomic traffic of 128 x 128 tiles at the same SM count — measured 6.37 -> 6.55 ms per
         // training step, profiles/r2_train_pair_ab.txt)
@@ -838,7 +869,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
                 if (rc) return rc;
                 rc = make_tmap_bf16_mn(&tb, a.W, a.N, a.K, a.nplanes, a.nplanes > 1 ? a.w_plane_rows : a.K, a.ldw);
             } else {
-                rc = make_tmap_bf16_2d(&ta, a.A, a.K, a_rows, a.lda, BK, BM);
+                rc = gather ? make_tmap_bf16_slots(&ta, a.A, a.K, a.slot_rows, a.arena_slots, a.lda)
+                            : make_tmap_bf16_2d(&ta, a.A, a.K, a_rows, a.lda, BK, BM);
                 if (rc) return rc;
                 rc = make_tmap_bf16_2d(&tb, a.W, a.K, w_rows, a.ldw, BK, 128);
             }
@@ -884,6 +916,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
 using namespace stair;
 
 extern "C" int stair_set_gemm_impl(int impl) { g_gemm_impl = impl; return STAIR_OK; }
+extern "C" int stair_set_gemm_pair_gather(int on) { g_pair_gather = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_pair_mn(int on) { g_pair_mn = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_gemm_pair(int mode) { g_pair_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return STAIR_OK; }
 extern "C" int stair_set_gemm_small(int on) { g_gemm_small = on ? 1 : 0; return STAIR_OK; }

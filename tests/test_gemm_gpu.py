@@ -272,3 +272,32 @@ def test_cta_pair_kernel_split3_planes():
     assert torch.equal(outs[0], outs[1])
     ref = (A.double() @ W.double().t()).float()
     assert (outs[1] - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize('T,n,N', [(8, 211, 512), (8, 16, 256), (8, 17, 256), (8, 4100, 512), (64, 37, 512), (16, 1000, 256), (128, 9, 256)])
+def test_cta_pair_kernel_gathers_frame_slots(T, n, N):
+    """Gathered A operand (rows of frame-arena slots, one 3-D TMA box per slot issued by each CTA of the pair for its own 128 rows) through
+    the CTA-pair kernel: bit-identical to the single-CTA gather kernel and equal to gather-then-GEMM, incl. a last M tile whose second
+    CTA holds no slot at all (n = 16, T = 8: 128 rows) or a single one (n = 17)."""
+    slots, H = 97, 512
+    g = torch.Generator(device='cuda').manual_seed(T * 1000 + n)
+    arena = torch.randn(slots, T, H, device='cuda', generator=g).bfloat16()
+    idx = torch.randint(0, slots, (n,), device='cuda', generator=g, dtype=torch.int32)
+    W = (torch.randn(N, H, device='cuda', generator=g) * H ** -0.5).bfloat16()
+    bias = torch.randn(N, device='cuda', generator=g)
+    rs = torch.rand(n * T, device='cuda', generator=g)
+    lib = L.lib()
+    outs = []
+    try:
+        for mode in (0, 2):
+            lib.stair_set_gemm_pair(mode)
+            for _ in range(2):
+                out = L.gemm_gather(arena, idx, T, W, bias=bias, out_dtype=torch.bfloat16, act=L.ACT_RELU, row_scale=rs)
+            torch.cuda.synchronize()
+            outs.append(out.clone())
+    finally:
+        lib.stair_set_gemm_pair(1)
+    assert lib.stair_gemm_error_flag() == 0
+    assert torch.equal(outs[0], outs[1])
+    ref = torch.relu((arena[idx.long()].reshape(n * T, H).float() @ W.float().t()) * rs[:, None] + bias)
+    assert (outs[1].float() - ref).abs().max().item() <= 2e-2 * max(ref.abs().max().item(), 1.0)
