@@ -230,6 +230,7 @@ int64_t stair_sizeof(int which);
 int stair_set_lanes(int lanes);
 /* module-phase scheduling: 1 (default) = by data dependency when StairBatch.group_deps is given (per-group events, no barrier between the
  * schedule waves); 0 = wave by wave (fork / join around every wave) */
+int stair_set_fuse_sum(int on);             /* 1: Filter's sum over frames runs in the epilogue of its second Linear (inference); default 0 (measured no faster) */
 int stair_set_dep_sched(int on);
 /* debug: timing events around every module group of the dependency-scheduled phase; read returns the number of groups (synchronises) */
 int stair_debug_timeline(int on);
@@ -247,6 +248,10 @@ int stair_gemm_bf16(const void* A, long long lda, int a_plane_rows, const void* 
                     int M, int N, int K, int act, int accumulate, void* stream);
 /* Same contraction with A gathered from an arena of slots: row m = slot a_slots[m / slot_rows], frame m % slot_rows.
  * Used for every module that reads [T,H] frame features of arbitrary questions (TMA 3-D boxes, no staging copy). */
+/* out[i, :] (bf16 [M / T, ld_sum]) = sum over the T consecutive rows of instance i of bf16(act(A . W^T + bias)): the frame sum of Filter
+ * (video_nmn/modules.py:374-376) taken in the GEMM epilogue; the [M, N] product itself is not written.  T in {1,2,4,...,128}, M % T == 0. */
+int stair_gemm_bf16_framesum(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* sum_out, long long ld_sum,
+                             int M, int N, int K, int act, int T, void* stream);
 int stair_gemm_bf16_gather(const void* arena, long long ld, long long arena_slots, const int32_t* a_slots, int slot_rows,
                            const void* W, long long ldw, const float* bias, const float* row_scale, void* C, long long ldc,
                            int out_dtype, int M, int N, int K, int act, void* stream);

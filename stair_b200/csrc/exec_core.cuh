@@ -9,6 +9,7 @@ namespace ex {
 
 extern thread_local long long t_last_launches;   // kernels launched by the last entry-point call on this thread
 extern int g_lstm_impl;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
+extern int g_fuse_sum;                      // 1 = Filter's frame sum in the epilogue of its second Linear (inference)
 constexpr int LANES = 8;                 // independent groups of one wave execute concurrently on up to LANES streams (main + side)
 constexpr long long ROW_CAP = 65536;     // frame rows per chunk of a VID-typed group
 constexpr long long VEC_CAP = 16384;     // instances per chunk of a VEC-typed group / decoder chunk
@@ -87,6 +88,9 @@ struct Ctx {
     // (S0/S1/S2/VP/V0/...) at act_base + k * plan.mod_bytes instead of the shared per-lane scratch, so the backward reads it back
     // instead of re-running the chunk's forward
     char* act_base = nullptr;
+    // inference entry points only (stair_nmn_forward / stair_op_forward): intermediates nobody reads afterwards may be skipped, e.g. the
+    // frame sum of Filter is taken in the epilogue of its second Linear and the [n T, H] activation is never written
+    bool inference = false;
 
     template <typename P> P* at(long long off) const { return reinterpret_cast<P*>(ws + off); }
     const void* W(int id) const { return m.w[id]; }
@@ -264,10 +268,17 @@ inline int run_chunk(Ctx& c, const StairGroup& g, int p, int n, int ob, int ab) 
         const int w = STAIR_W_FILT_REPR + 4 * g.variant;
         drop_next(c, w, pT);
         STAIR_TRY(gemm_vid(c, a0, n, H, w, w + 1, STAIR_ACT_RELU, nullptr, S0, dt, H));
-        drop_next(c, w + 2, pT);
-        STAIR_TRY(gemm_act(c, S0, n * T, H, H, w + 2, w + 3, STAIR_ACT_RELU, nullptr, S1, dt, H));
         // tensor keyword: nn.Softmax() over a size-1 dim makes the attention exactly 1.0 -> plain sum over frames
-        STAIR_TRY(launch_sum_T(dt, S1, S2, n, T, H, c.st));
+        if (c.inference && g_fuse_sum && c.np == 1 && c.drop_p == 0.0f && gemm_sum_epilogue_ok(T)) {
+            GemmArgs a;                                              // second Linear + ReLU + sum over the T frames of an instance in one kernel
+            a.A = S0; a.lda = H; a.W = c.W(w + 2); a.ldw = H; a.w_plane_rows = H; a.bias = c.Wf(w + 3); a.M = n * T; a.N = H; a.K = H;
+            a.act = STAIR_ACT_RELU; a.out_dtype = dt; a.sum_out = S2; a.ld_sum = H; a.sum_T = T;
+            STAIR_TRY(launch_gemm(a, c.st));
+        } else {
+            drop_next(c, w + 2, pT);
+            STAIR_TRY(gemm_act(c, S0, n * T, H, H, w + 2, w + 3, STAIR_ACT_RELU, nullptr, S1, dt, H));
+            STAIR_TRY(launch_sum_T(dt, S1, S2, n, T, H, c.st));
+        }
         STAIR_TRY(gemm_act(c, S2, n, H, H, STAIR_W_FILT_D_W, STAIR_W_FILT_D_B, STAIR_ACT_RELU, nullptr, vec_out, dt, H));
         if (g.head) return launch_l2norm(dt, c.buf.vec, ob, c.buf.head_vec, ab, n, H, c.st);
         return STAIR_OK;
@@ -466,7 +477,6 @@ inline int run_modules_dep(Ctx& c, LaneStreams* ls) {
     long long lane_end[LANES], finish[MAX_SCHED_GROUPS];
     bool used[LANES];
     for (int l = 0; l < lanes; ++l) { tail[l] = -1; lane_end[l] = 0; used[l] = false; }
-    if (cudaEventRecord(ls->fork, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
     Timeline* tl = nullptr;
     if (g_timeline) {
         tl = &timeline_state();
@@ -476,8 +486,9 @@ inline int run_modules_dep(Ctx& c, LaneStreams* ls) {
             tl->ok = true;
         }
         tl->n = ng;
-        cudaEventRecord(tl->origin, c.st);
+        cudaEventRecord(tl->origin, c.st);                         // before the fork: every lane starts after it
     }
+    if (cudaEventRecord(ls->fork, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
     for (int g = 0; g < ng; ++g) {
         const int* deps = c.b.group_deps + static_cast<long long>(g) * STAIR_MAX_GROUP_DEPS;
         const bool all = deps[0] == -2;

@@ -14,6 +14,10 @@ namespace ex {
 int g_lstm_impl = 0;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
 thread_local long long t_last_launches = 0;
 int g_timeline = 0;
+int g_fuse_sum = 0;                      // 1 = Filter's frame sum in the epilogue of its second Linear (inference).  Bit-identical, fewer launches (81 -> 78
+                                         // at RX, 169 -> 155 at I3D) and NOT faster: these K = 512 GEMMs are epilogue-bound, and the transposing sum costs the
+                                         // epilogue more than the separate 4-20 us pass (RX 1.354 -> 1.365-1.377 ms, I3D 5.57-5.72 -> 5.59-5.62 ms;
+                                         // profiles/r2_fused_frame_sum_ab.txt)
 int g_dep_sched = 1;         // 1 = dependency-driven module scheduling when the batch carries group_deps
 int g_lanes = 8;             // round 1 (wave scheduling), B = 4096 RX: 2 / 4 / 6 / 8 lanes = 1.64 / 1.65 / 1.54 / 1.55 ms per forward; round 2
                              // (dependency scheduling): 4 / 6 / 8 lanes = 1.365 / 1.36 / 1.34 ms vs 1.41-1.43 ms wave by wave (profiles/r2_dep_sched_ab.txt)
@@ -39,6 +43,7 @@ extern "C" int stair_debug_timeline_read(float* t0, float* t1, int* lane, int* o
     }
     return n;
 }
+extern "C" int stair_set_fuse_sum(int on) { g_fuse_sum = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_dep_sched(int on) { g_dep_sched = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_lanes(int lanes) { g_lanes = lanes < 1 ? 1 : (lanes > LANES ? LANES : lanes); return STAIR_OK; }
 extern "C" int stair_version(void) { return STAIR_ABI_VERSION; }
@@ -87,6 +92,7 @@ extern "C" int stair_nmn_forward(const StairModel* model, const StairBatch* batc
     c.ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(buf->workspace) + 1023) & ~static_cast<uintptr_t>(1023));
     if (c.ws + c.plan.total > reinterpret_cast<char*>(buf->workspace) + buf->workspace_bytes) return STAIR_ERR_CAPACITY;
     c.T = b.T; c.H = m.H; c.h = m.H / 2; c.np = m.precision == STAIR_F32 ? 3 : 1; c.adt = m.precision; c.esz = m.precision == STAIR_F32 ? 4 : 2;
+    c.inference = true;
     stair_itab_layout(b.n_nodes, b.n_groups, &c.il);
     if (buf->itab_ints < c.il.total) return STAIR_ERR_CAPACITY;
     c.perm = buf->itab + c.il.perm; c.out_slot = buf->itab + c.il.out_slot;
@@ -146,6 +152,7 @@ extern "C" int stair_op_forward(const StairModel* model, int T, const StairGroup
     c.ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(buf->workspace) + 1023) & ~static_cast<uintptr_t>(1023));
     c.T = T; c.H = m.H; c.h = m.H / 2; c.np = m.precision == STAIR_F32 ? 3 : 1; c.adt = m.precision; c.esz = m.precision == STAIR_F32 ? 4 : 2;
     c.perm = c.out_slot = c.pos_q = c.span_s = c.span_e = nullptr;
+    c.inference = true;
     c.arg0 = args; c.arg1 = args + g.count; c.arg2 = args + 2 * g.count;
     const long long before = g_launch_count;
     StairGroup g0 = g;

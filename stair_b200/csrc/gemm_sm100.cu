@@ -48,6 +48,9 @@ struct GemmParams {
     DropSpec drop;             // dropout after the activation (thresh 0 = off)
     int atomic_acc;            // fp32 accumulate with atomics even when ksplit == 1
     int mn_major;              // operands stored [k][m] / [k][n] (C = A^T . W): MN-major UMMA tiles, 3-D tensor maps {mn, k, plane}
+    bf16* sum_out;             // frame-sum epilogue (null = off): [M / sum_T, ld_sum] bf16, written INSTEAD of C
+    long long ld_sum;
+    int sum_T;
 };
 
 // plane pairs (a,b) of the 6-term bf16x3 product, smallest contributions first
@@ -226,6 +229,53 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     tmem_ld_wait();
 }
 
+// Frame-sum epilogue of one accumulator tile for one epilogue warp (GemmArgs::sum_out): the activated values are rounded to bf16 exactly as the
+// stored tile would have been, transposed through the warp's staging buffer (row = lane -> column = lane) and summed over the T consecutive
+// rows of an instance in frame order (the order of sum_T_kernel).  T <= 32: an instance lies inside the warp's 32 rows.  T = 64 / 128: the
+// instance spans 2 / 4 lane quarters; their 32-row partial sums meet in the epilogue set's shared scratch behind a named barrier (every warp
+// of the set runs this function for every tile, also for rows past M, which contribute zeros).
+__device__ __forceinline__ void epilogue_tile_sum(const GemmParams& p, uint32_t t_base, int row, int row0, int n0, int c_begin, int c_end,
+                                                  float* scratch, float* part, int quarter, int bar_id, int lane) {
+    const float rs = (p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.0f;
+    const int T = p.sum_T;
+    const int len = T < 32 ? T : 32, groups = 32 / len, span = T > 32 ? T / 32 : 1;      // span = lane quarters per instance
+    int parity = 0;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= p.N) break;                                          // warp-uniform, identical in the four warps of a set
+        uint32_t raw[32];
+        float v[32];
+        tmem_ld32(t_base + static_cast<uint32_t>(c * 32), raw);
+        tmem_ld_wait();
+        epilogue_math(p, row, n, rs, raw, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = row < p.M ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.0f;
+        __syncwarp();
+        for (int g = 0; g < groups; ++g) {
+            float s = 0.0f;
+            for (int t = 0; t < len; ++t) s += scratch[(g * len + t) * 33 + lane];
+            if (span == 1) {
+                const long long inst = (row0 + g * len) / T;
+                if (row0 + g * len < p.M && n + lane < p.N) p.sum_out[inst * p.ld_sum + n + lane] = __float2bfloat16_rn(s);
+            } else {
+                part[(parity * 4 + quarter) * 32 + lane] = s;
+            }
+        }
+        if (span > 1) {
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (quarter % span == 0) {
+                float s = 0.0f;
+                for (int q = 0; q < span; ++q) s += part[(parity * 4 + quarter + q) * 32 + lane];
+                const long long inst = row0 / T;
+                if (row0 < p.M && n + lane < p.N) p.sum_out[inst * p.ld_sum + n + lane] = __float2bfloat16_rn(s);
+            }
+            parity ^= 1;
+        }
+        __syncwarp();
+    }
+}
+
 // OCC = CTAs per SM the kernel is built for.  OCC = 2 (BN = 128, two pipeline stages, 99 KB of shared memory, 256 TMEM columns) was written
 // for the module phase, whose GEMMs are a few microseconds of tensor work behind ~8 us of fixed latency (launch, barrier / TMEM set-up,
 // first operand fetch, epilogue drain): two resident CTAs per SM let the GEMMs of two lanes run side by side.  Measured: no gain (the phase
@@ -377,7 +427,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (threadIdx.x == 128 && item == blockIdx.x) dbg_stamp(p, 3);
             const int row = m0 + quarter * 32 + lane;
             const uint32_t t_base = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
-            if (p.tma_store) {
+            if (p.sum_out) {
+                epilogue_tile_sum(p, t_base, row, m0 + quarter * 32, n0, c_begin, c_end,
+                                  reinterpret_cast<float*>(sStage + (eset * 4 + quarter) * 8192), reinterpret_cast<float*>(sStage + eset * 4 * 8192 + 4608),
+                                  quarter, 1 + eset, lane);
+            } else if (p.tma_store) {
                 epilogue_tile_tma(p, tmC, t_base, row, m0 + quarter * 32, n0, c_begin, c_end,
                                   smem_u32(sStage) + static_cast<uint32_t>(eset * 4 + quarter) * 8192u, sbuf, lane);
             } else {
@@ -597,7 +651,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             tcgen05_fence_after();
             const int row = m0 + quarter * 32 + lane;
             const uint32_t t_base = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
-            if (p.tma_store) {
+            if (p.sum_out) {
+                epilogue_tile_sum(p, t_base, row, m0 + quarter * 32, n0, c_begin, c_end,
+                                  reinterpret_cast<float*>(sStage + (eset * 4 + quarter) * 8192), reinterpret_cast<float*>(sStage + eset * 4 * 8192 + 4608),
+                                  quarter, 1 + eset, lane);
+            } else if (p.tma_store) {
                 if (m0 + quarter * 32 < p.M)
                     epilogue_tile_tma(p, tmC, t_base, row, m0 + quarter * 32, n0, c_begin, c_end,
                                       smem_u32(sStage) + static_cast<uint32_t>(eset * 4 + quarter) * 8192u, sbuf, lane);
@@ -806,6 +864,7 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CU
 }
 
 thread_local long long g_launch_count = 0;
+bool gemm_sum_epilogue_ok(int T) { return T == 1 || T == 2 || T == 4 || T == 8 || T == 16 || T == 32 || T == 64 || T == 128; }
 static int small_default() { const char* e = getenv("STAIR_GEMM_SMALL"); return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 0; }
 static int g_gemm_small = small_default();      // 1 = module-sized GEMMs (N <= 1024, at most a few waves of tiles) use the two-CTAs-per-SM form.  Off:
                                                 // bit-identical and no faster (1.331 vs 1.337 ms per forward, profiles/r2_module_phase_analysis.txt)
@@ -831,6 +890,11 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     p.vec_ok = ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.ldc * esz) % 16 == 0) ? 1 : 0;
     p.tma_store = (!a.accumulate && p.vec_ok && g_epilogue_impl == 0) ? 1 : 0;
     p.a_slots = a.a_slots; p.slot_rows = gather ? a.slot_rows : BM; p.num_slots = gather ? a.M / a.slot_rows : 0;
+    p.sum_out = reinterpret_cast<bf16*>(a.sum_out); p.ld_sum = a.ld_sum; p.sum_T = a.sum_T;
+    if (a.sum_out) {
+        if (!gemm_sum_epilogue_ok(a.sum_T) || a.M % a.sum_T || a.accumulate || a.mn_major || g_gemm_impl == 1) return STAIR_ERR_ARG;
+        p.tma_store = 0;                                           // C is never written in this mode
+    }
     p.err_flag = err_flag_ptr();
     p.dbg = g_dbg;
 
@@ -856,7 +920,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     const bool small = g_gemm_small && a.nplanes == 1 && !a.mn_major && !a.accumulate && a.N > 64 && a.N <= 1024 && tiles128 <= 8 * g_num_sms;
     if (!small) {
         const int tiles256 = ceil_div(a.M, 2 * BM) * (a.N / 256);
-        const bool legal = (!gather || g_pair_gather) && p.vec_ok && g_epilogue_impl == 0 && a.N % 256 == 0 && g_num_sms >= 2 && (!a.mn_major || g_pair_mn);
+        const bool legal = (!gather || g_pair_gather) && (p.vec_ok || a.sum_out) && g_epilogue_impl == 0 && a.N % 256 == 0 && g_num_sms >= 2 && (!a.mn_major || g_pair_mn);
         // (split-K weight gradients with a handful of 256 x 256 output tiles stay on the single-CTA kernel unless forced: every K split adds a
         // whole 256 KB tile with atomics, twice the atomic traffic of 128 x 128 tiles at the same SM count — measured 6.37 -> 6.55 ms per
         // training step, profiles/r2_train_pair_ab.txt)
@@ -947,6 +1011,15 @@ extern "C" int stair_gemm_bf16_tn(const void* A, long long lda, int a_plane_rows
     GemmArgs a;
     a.A = A; a.lda = lda; a.a_plane_rows = a_plane_rows; a.W = W; a.ldw = ldw; a.w_plane_rows = w_plane_rows; a.nplanes = nplanes;
     a.C = C; a.ldc = ldc; a.out_dtype = STAIR_F32; a.M = M; a.N = N; a.K = K; a.accumulate = accumulate; a.mn_major = 1;
+    return launch_gemm(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// sum_out[i, :] = sum over the T rows of instance i of bf16(act(A . W^T + bias))  (GemmArgs::sum_out: Filter's frame sum as a GEMM epilogue)
+extern "C" int stair_gemm_bf16_framesum(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* sum_out, long long ld_sum,
+                                        int M, int N, int K, int act, int T, void* stream) {
+    GemmArgs a;
+    a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.w_plane_rows = N; a.bias = bias; a.M = M; a.N = N; a.K = K; a.act = act;
+    a.out_dtype = STAIR_BF16; a.sum_out = sum_out; a.ld_sum = ld_sum; a.sum_T = T;
     return launch_gemm(a, reinterpret_cast<cudaStream_t>(stream));
 }
 

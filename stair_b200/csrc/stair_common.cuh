@@ -170,7 +170,13 @@ struct GemmArgs {
     int mn_major = 0;
     int atomic_acc = 0;             // accumulate with atomics even without split-K (concurrent launches adding into the same C)
     DropSpec drop;                  // applied after the activation (training forward only)
+    // frame-sum epilogue (Filter aggregation, modules.py:374-376, folded into the producing GEMM): instead of C, the kernel writes
+    // sum_out[i][n] = sum_t bf16(act(...))[i * sum_T + t][n] (bf16 [M / sum_T, ld_sum]); sum_T divides 128 or is a multiple of 32 that divides 128
+    void* sum_out = nullptr;
+    long long ld_sum = 0;
+    int sum_T = 0;
 };
+bool gemm_sum_epilogue_ok(int T);
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
 int* err_flag_ptr();      // pinned host word that device-side protocol timeouts write their code to (stair_gemm_error_flag)
 void err_flag_free();

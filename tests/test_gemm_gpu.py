@@ -301,3 +301,38 @@ def test_cta_pair_kernel_gathers_frame_slots(T, n, N):
     assert torch.equal(outs[0], outs[1])
     ref = torch.relu((arena[idx.long()].reshape(n * T, H).float() @ W.float().t()) * rs[:, None] + bias)
     assert (outs[1].float() - ref).abs().max().item() <= 2e-2 * max(ref.abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize('T,n,N,K', [(8, 409, 512, 512), (8, 16, 256, 512), (8, 17, 512, 64), (16, 100, 512, 512), (32, 33, 256, 512),
+                                      (64, 37, 512, 512), (64, 2, 512, 512), (128, 9, 256, 512), (8, 3000, 512, 512), (4, 77, 192, 320)])
+@pytest.mark.parametrize('pair', [0, 2])
+def test_frame_sum_epilogue(T, n, N, K, pair):
+    """GemmArgs::sum_out — Filter's sum over the T frames of an instance (modules.py:374-376) inside the GEMM epilogue: equals the two-kernel
+    path (GEMM with bf16 output, then a frame-ordered fp32 sum rounded to bf16) bit for bit when an instance lies inside one lane quarter
+    (T <= 32) and to one bf16 ulp when its 32-row partial sums are combined (T = 64, 128); single-CTA and CTA-pair kernels."""
+    g = torch.Generator(device='cuda').manual_seed(T * 7 + n)
+    M = n * T
+    A = torch.randn(M, K, device='cuda', generator=g).bfloat16()
+    W = (torch.randn(N, K, device='cuda', generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device='cuda', generator=g)
+    lib = L.lib()
+    out = torch.full((n, N), float('nan'), device='cuda', dtype=torch.bfloat16)
+    try:
+        lib.stair_set_gemm_pair(pair)
+        for _ in range(2):
+            L.check(lib.stair_gemm_bf16_framesum(L.ptr(A), L.i64(K), L.ptr(W), L.i64(K), L.ptr(bias), L.ptr(out), L.i64(N), L.i32(M), L.i32(N), L.i32(K),
+                                                 L.i32(L.ACT_RELU), L.i32(T), L.stream_ptr()), 'stair_gemm_bf16_framesum')
+        full = L.gemm(A, W, bias=bias, out_dtype=torch.bfloat16, act=L.ACT_RELU)
+        torch.cuda.synchronize()
+    finally:
+        lib.stair_set_gemm_pair(1)
+    assert lib.stair_gemm_error_flag() == 0
+    x = full.float().view(n, T, N)
+    ref = torch.zeros(n, N, device='cuda')
+    for t in range(T):                                               # frame order, fp32
+        ref = ref + x[:, t]
+    ref = ref.bfloat16()
+    if T <= 32:
+        assert torch.equal(out, ref)
+    else:
+        assert (out.float() - ref.float()).abs().max().item() <= 2 ** -7 * ref.float().abs().max().item()
