@@ -151,6 +151,39 @@ inline int gemm_vec_rows(Ctx& c, const int* idx, int rps, int n, int N, int wid,
     return gemm_planes(c, pl, K, M, M, N, K, wid, bid, act, nullptr, C, cdt, ldc);
 }
 
+constexpr int MAX_SCHED_GROUPS = 96;     // groups with their own completion event (dependency-driven scheduling); more -> wave scheduling
+struct LaneStreams { cudaStream_t side[LANES - 1]; cudaEvent_t fork, join[LANES - 1], done[MAX_SCHED_GROUPS]; bool ok = false; };
+// The only CUDA objects the library owns: per calling thread, LANES - 1 side streams + LANES events used to run the independent groups of
+// a schedule wave concurrently.  Created by stair_init() (or lazily by the first forward of a thread), destroyed by stair_shutdown().
+inline LaneStreams& lane_state() {
+    static thread_local LaneStreams ls;
+    return ls;
+}
+inline void lane_streams_destroy() {
+    LaneStreams& ls = lane_state();
+    if (!ls.ok) return;
+    for (int l = 0; l < LANES - 1; ++l) { cudaStreamDestroy(ls.side[l]); cudaEventDestroy(ls.join[l]); }
+    for (int g = 0; g < MAX_SCHED_GROUPS; ++g) cudaEventDestroy(ls.done[g]);
+    cudaEventDestroy(ls.fork);
+    ls.ok = false;
+}
+inline LaneStreams* lane_streams() {
+    LaneStreams& ls = lane_state();
+    if (!ls.ok) {
+        for (int l = 0; l < LANES - 1; ++l) {
+            if (cudaStreamCreateWithFlags(&ls.side[l], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&ls.join[l], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&ls.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int g = 0; g < MAX_SCHED_GROUPS; ++g)
+            if (cudaEventCreateWithFlags(&ls.done[g], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ls.ok = true;
+    }
+    return &ls;
+}
+
+extern int g_lanes;      // 1 = everything on the caller's stream; up to LANES
+
 // ---- encoders (module_net.py:147-163) --------------------------------------------------------------------------
 inline int run_encoders(Ctx& c, int phases) {
     const StairModel& m = c.m; const StairBatch& b = c.b;
@@ -160,6 +193,18 @@ inline int run_encoders(Ctx& c, int phases) {
     float* g = c.at<float>(c.plan.g);
     float* cs = c.at<float>(c.plan.c);
     bf16* hs = c.at<bf16>(c.plan.hs);
+    // The fp32 -> bf16 staging of the packed question tokens (HBM-bound, ~24 us at B = 4096) only depends on the inputs: with both encoders
+    // requested it runs on a side lane underneath the video projection GEMM (whose 200 KB CTAs leave the SMs' thread slots free).
+    bool text_staged = false;
+    if ((phases & STAIR_FWD_ENCODE_VIDEO) && (phases & STAIR_FWD_ENCODE_TEXT) && c.inference && g_lanes > 2) {
+        if (LaneStreams* ls = lane_streams()) {
+            if (cudaEventRecord(ls->join[2], c.st) != cudaSuccess || cudaStreamWaitEvent(ls->side[1], ls->join[2], 0) != cudaSuccess) return STAIR_ERR_CUDA;
+            STAIR_TRY(launch_stage_rows(b.question_dtype, b.question, m.text_size, nullptr, 1, 1, c.at<bf16>(c.plan.xq_in), m.text_ld, b.n_tok, c.np, b.n_tok,
+                                        m.text_size, ls->side[1]));
+            if (cudaEventRecord(ls->join[1], ls->side[1]) != cudaSuccess) return STAIR_ERR_CUDA;
+            text_staged = true;
+        }
+    }
     // video input projection: [B*T, V] x [V, 8h] for both directions at once
     if (phases & STAIR_FWD_ENCODE_VIDEO) {
         const bf16* A; long long lda, apr;
@@ -204,8 +249,9 @@ inline int run_encoders(Ctx& c, int phases) {
     // text input projection over the packed tokens of all questions
     {
         bf16* in = c.at<bf16>(c.plan.xq_in);
-        STAIR_TRY(launch_stage_rows(b.question_dtype, b.question, m.text_size, nullptr, 1, 1, in, m.text_ld, b.n_tok, c.np, b.n_tok,
-                                    m.text_size, c.st));
+        if (text_staged) { if (cudaStreamWaitEvent(c.st, lane_streams()->join[1], 0) != cudaSuccess) return STAIR_ERR_CUDA; }
+        else STAIR_TRY(launch_stage_rows(b.question_dtype, b.question, m.text_size, nullptr, 1, 1, in, m.text_ld, b.n_tok, c.np, b.n_tok,
+                                         m.text_size, c.st));
         GemmArgs a;
         a.A = in; a.lda = m.text_ld; a.a_plane_rows = b.n_tok; a.nplanes = c.np; a.W = c.W(STAIR_W_TENC_WIH); a.ldw = m.text_ld;
         a.w_plane_rows = 4 * H; a.bias = c.Wf(STAIR_W_TENC_B); a.C = c.at<void>(c.plan.xq); a.ldc = 4 * H; a.out_dtype = c.adt;
@@ -425,44 +471,12 @@ inline long long group_cost(const StairGroup& g, int T) {
     return launches * 1000LL + static_cast<long long>(g.count) * (op_is_vid_sized(g.op) ? T : 1) / 16;
 }
 
-constexpr int MAX_SCHED_GROUPS = 96;     // groups with their own completion event (dependency-driven scheduling); more -> wave scheduling
-struct LaneStreams { cudaStream_t side[LANES - 1]; cudaEvent_t fork, join[LANES - 1], done[MAX_SCHED_GROUPS]; bool ok = false; };
-// The only CUDA objects the library owns: per calling thread, LANES - 1 side streams + LANES events used to run the independent groups of
-// a schedule wave concurrently.  Created by stair_init() (or lazily by the first forward of a thread), destroyed by stair_shutdown().
-inline LaneStreams& lane_state() {
-    static thread_local LaneStreams ls;
-    return ls;
-}
-inline void lane_streams_destroy() {
-    LaneStreams& ls = lane_state();
-    if (!ls.ok) return;
-    for (int l = 0; l < LANES - 1; ++l) { cudaStreamDestroy(ls.side[l]); cudaEventDestroy(ls.join[l]); }
-    for (int g = 0; g < MAX_SCHED_GROUPS; ++g) cudaEventDestroy(ls.done[g]);
-    cudaEventDestroy(ls.fork);
-    ls.ok = false;
-}
-inline LaneStreams* lane_streams() {
-    LaneStreams& ls = lane_state();
-    if (!ls.ok) {
-        for (int l = 0; l < LANES - 1; ++l) {
-            if (cudaStreamCreateWithFlags(&ls.side[l], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-            if (cudaEventCreateWithFlags(&ls.join[l], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        }
-        if (cudaEventCreateWithFlags(&ls.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        for (int g = 0; g < MAX_SCHED_GROUPS; ++g)
-            if (cudaEventCreateWithFlags(&ls.done[g], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        ls.ok = true;
-    }
-    return &ls;
-}
-
 // Debug timeline of the dependency-driven module phase (stair_debug_timeline): timing events around every group, read back by
 // stair_debug_timeline_read.  Off by default; the events perturb the schedule by a fraction of a microsecond per group.
 struct Timeline { cudaEvent_t origin, t0[MAX_SCHED_GROUPS], t1[MAX_SCHED_GROUPS]; int lane[MAX_SCHED_GROUPS], op[MAX_SCHED_GROUPS], count[MAX_SCHED_GROUPS], variant[MAX_SCHED_GROUPS]; int n = 0; bool ok = false; };
 inline Timeline& timeline_state() { static Timeline t; return t; }
 extern int g_timeline;
 
-extern int g_lanes;      // 1 = everything on the caller's stream; up to LANES
 extern int g_dep_sched;  // 1 = schedule the module groups by data dependency when the batch carries group_deps
 
 // Dependency-driven module phase.  Wave scheduling (run_modules below) joins all lanes after every schedule wave, so a wave lasts as long
