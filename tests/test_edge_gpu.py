@@ -190,3 +190,29 @@ def test_module_scheduling_modes_agree_and_the_timeline_hook_reports_every_group
         model.check_status(st)
     finally:
         lib.stair_debug_timeline(0); lib.stair_set_dep_sched(1); lib.stair_set_lanes(8); lib.stair_set_bwd_lanes(8)
+
+
+@pytest.mark.parametrize('T,V', [(8, 256), (64, 128)])
+def test_optional_kernel_forms_do_not_change_the_forward(T, V):
+    """Comparison switches of the C ABI (include/stair_b200.h): the frame sum of Filter inside the GEMM epilogue (stair_set_fuse_sum), the
+    gathered-A form of the CTA-pair GEMM (stair_set_gemm_pair_gather), the two-CTAs-per-SM GEMM (stair_set_gemm_small) and the
+    weight-stationary recurrence (stair_set_lstm_ws) compute the same values as the product configuration: logits bit-identical."""
+    from stair_b200 import _lib as L
+    lib = L.lib()
+    cfg = syn.model_config(T=T, V=V, hidden=512, object_types=16)
+    torch.manual_seed(9)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().eval()
+    qs = syn.make_questions(1500, T, V, seed=5, templates=list(syn.ALL_TEMPLATES), object_types=16)
+    batch = collate(qs, video_dtype=torch.bfloat16).to('cuda')
+    ref = model.forward_batch(batch).logits.clone()
+    switches = (('stair_set_fuse_sum', 1, 0), ('stair_set_gemm_pair_gather', 0, 1), ('stair_set_gemm_small', 1, 0), ('stair_set_lstm_ws', 1, 0),
+                ('stair_set_gemm_pair', 2, 1), ('stair_set_gemm_pair', 0, 1))
+    for name, on, default in switches:
+        try:
+            getattr(lib, name)(on)
+            out = model.forward_batch(batch).logits.clone()
+            torch.cuda.synchronize()
+        finally:
+            getattr(lib, name)(default)
+        assert lib.stair_gemm_error_flag() == 0
+        assert torch.equal(out, ref), (name, on, float((out - ref).abs().max()))
