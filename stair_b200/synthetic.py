@@ -209,6 +209,131 @@ def make_questions(n: int, T: int, V: int, seed: int = 1234, templates=None, tex
                           qa_id='syn-%d' % i) for i in range(n)]
 
 
+# ---- random well-typed layouts (fuzzing beyond the probed templates) ---------------------------------------------------------
+# Value types of the reference interpreter's stack (video_nmn/modules.py signatures):
+#   VID [T,H] frame features, VEC [H], VEC2 [2,H] (Array2), ATT1 [T] (ExistsFrame / HasItem / Relate), ATTK [K,T] (Localize, K = 1 | 2)
+def random_layout(rng: np.random.Generator, max_modules: int = 12):
+    """A random NMN prefix program the reference interpreter accepts: (tokens, idx_list).  Top-down over the operators' argument
+    types with a budget of module calls; leaves are 'video' and content words ('w<i>', which get question spans)."""
+    budget = [int(rng.integers(2, max_modules + 1))]
+    n_words = [0]
+
+    def word():
+        n_words[0] += 1
+        return ['w%d' % n_words[0]]
+
+    def pick(options):
+        return options[int(rng.integers(0, len(options)))]
+
+    def spend():
+        if budget[0] <= 0:
+            return False
+        budget[0] -= 1
+        return True
+
+    def vec(depth=0):
+        if depth > 5 or not spend():
+            return word()
+        kind = pick(['Filter', 'Filter', 'Exists', 'ToAction', 'Compare', 'Equals', 'Xor', 'And', 'Choose', 'Superlative', 'word'])
+        if kind == 'word':
+            budget[0] += 1
+            return word()
+        if kind == 'Filter':
+            kw = pick([None, 'actions', 'objects', 'relations'])
+            return ['Filter'] + vid(depth + 1) + ([kw] if kw else vec_leafy(depth + 1))
+        if kind == 'Exists':
+            return ['Exists'] + vec_leafy(depth + 1) + vec(depth + 1)
+        if kind == 'ToAction':
+            return ['ToAction'] + vec(depth + 1) + vec_leafy(depth + 1)
+        if kind in ('Compare', 'Equals', 'Xor', 'And'):
+            return [kind] + vec(depth + 1) + vec(depth + 1)
+        if kind == 'Choose':
+            return ['Choose'] + vec_leafy(depth + 1) + vec_leafy(depth + 1) + vec(depth + 1)
+        actions = pick(['vec', 'vec2', 'vid'])
+        a = vec_leafy(depth + 1) if actions == 'vec' else (vec2(depth + 1) if actions == 'vec2' else vid(depth + 1))
+        return ['Superlative', pick(['max', 'min'])] + a + vid(depth + 1)
+
+    def vec_leafy(depth):                                   # keyword-like operand: usually a phrase, sometimes a computed vector
+        return word() if rng.random() < 0.8 else vec(depth)
+
+    def vec2(depth):
+        if not spend():
+            budget[0] += 0
+        return ['Array2'] + vec_leafy(depth + 1) + vec_leafy(depth + 1)
+
+    def vid(depth=0):
+        if depth > 5 or rng.random() < 0.35 or not spend():
+            return ['video']
+        kind = pick(['Temporal', 'Temporal', 'FilterFrame', 'AttnVideo'])
+        if kind == 'Temporal':
+            return ['Temporal', pick(['while', 'before', 'after', 'between'])] + vid(depth + 1) + attk(depth + 1)
+        if kind == 'FilterFrame':
+            kw = pick([None, 'relations', 'actions'])
+            return ['FilterFrame'] + vid(depth + 1) + ([kw] if kw else vec_leafy(depth + 1))
+        return ['AttnVideo'] + vid(depth + 1) + att1(depth + 1)
+
+    def attk(depth):
+        spend()
+        return ['Localize'] + vid(depth + 1) + (vec_leafy(depth + 1) if rng.random() < 0.7 else vec2(depth + 1))
+
+    def att1(depth):
+        spend()
+        kind = pick(['HasItem', 'ExistsFrame', 'ExistsFrame', 'Relate', 'And', 'XorFrame'] if depth < 5 else ['HasItem', 'ExistsFrame'])
+        if kind == 'HasItem':
+            return ['HasItem'] + vid(depth + 1)
+        if kind == 'ExistsFrame':
+            return ['ExistsFrame'] + vec_leafy(depth + 1) + vid(depth + 1)
+        if kind == 'Relate':
+            return ['Relate', pick(['forward', 'backward'])] + att1(depth + 1)
+        return [kind] + att1(depth + 1) + att1(depth + 1)
+
+    budget[0] -= 1
+    root = pick(['Filter', 'Exists', 'Compare', 'Equals', 'Xor', 'And', 'Choose', 'ToAction', 'Superlative'])
+    if root == 'Filter':
+        kw = pick([None, 'actions', 'objects', 'relations'])
+        tokens = ['Filter'] + vid(1) + ([kw] if kw else word())
+    elif root == 'Exists':
+        tokens = ['Exists'] + word() + vec(1)
+    elif root == 'ToAction':
+        tokens = ['ToAction'] + vec(1) + word()
+    elif root == 'Choose':
+        tokens = ['Choose'] + word() + word() + vec(1)
+    elif root == 'Superlative':
+        tokens = ['Superlative', pick(['max', 'min'])] + (word() if rng.random() < 0.5 else vid(1)) + vid(1)
+    else:
+        tokens = [root] + vec(1) + vec(1)
+    idx_list, k = [], 0
+    for t in tokens:
+        if t in WORDS_TO_KEEP and t not in ('actions', 'objects', 'relations'):
+            idx_list.append(None)
+        else:
+            idx_list.append(k)
+            k += 1
+    return tokens, idx_list
+
+
+def make_random_questions(n: int, T: int, V: int, seed: int = 99, max_modules: int = 12, text_size: int = 300, answer_vocab: int = 172,
+                          distinct: int | None = None):
+    """``n`` questions over ``distinct`` (default n) random well-typed layouts; reference data-dict schema."""
+    rng = np.random.default_rng(seed)
+    layouts = [random_layout(rng, max_modules) for _ in range(distinct or n)]
+    out = []
+    for i in range(n):
+        tokens, idx_list = layouts[i % len(layouts)]
+        L = int(rng.integers(8, 25))
+        spans = {}
+        for j in _content_positions(tokens):
+            w = int(rng.integers(1, 4))
+            s0 = int(rng.integers(0, L - w + 1))
+            spans[j] = (s0, s0 + w)
+        out.append({'question': torch.from_numpy((rng.standard_normal((L, text_size)) * 0.4).astype(np.float32)),
+                    'video_features': torch.from_numpy(np.abs(rng.standard_normal((T, V))).astype(np.float32)),
+                    'prog_str_to_question_tokens': spans, 'nmn_program_list': list(tokens), 'nmn_program_idx': list(idx_list),
+                    'answer': torch.tensor(int(rng.integers(0, answer_vocab - 1))), 'qa_id': 'rnd-%d' % i,
+                    'question_raw': ' '.join(tokens), 'template': 'random'})
+    return out
+
+
 def model_config(T: int = 8, V: int = 4096, hidden: int = 512, text_size: int = 300, dropout: float = 0.0,
                  answer_vocab: int = 172, object_types: int = 256):
     """Mirrors the dict built at train_module.py:304-310."""

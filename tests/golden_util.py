@@ -53,3 +53,16 @@ def load(name):
                                         for j, n in enumerate(names)]
         questions.append((data, ref, q))
     return cfg, weights, questions, meta, grads
+
+
+def load_random(name):
+    """(cfg, weights, questions, reference logits [n, A]) of the random-layout fixture (tests/golden/make_random_golden.py): the seeded
+    questions are regenerated and their token lists are checked against the ones the reference outputs were recorded for."""
+    cfg, weights, _, meta, _ = load(name)
+    rmeta = json.load(open(os.path.join(GOLDEN_DIR, 'random_layouts.json')))[name]
+    logits = torch.from_numpy(np.load(os.path.join(GOLDEN_DIR, 'random_layouts.npz'))[name + '/logits'])
+    qs = syn.make_random_questions(rmeta['n'], cfg['max_video_length'], cfg['video_size'], seed=rmeta['seed'], text_size=cfg['text_size'],
+                                   answer_vocab=cfg['answer_vocab_length'])
+    assert [d['nmn_program_list'] for d in qs] == rmeta['tokens'], \
+        'synthetic.random_layout changed: regenerate tests/golden/random_layouts.* with make_random_golden.py'
+    return cfg, weights, qs, logits, meta

@@ -279,3 +279,24 @@ def test_streaming_forward_equals_plain_forward():
     one = collate(sets[0], pin_memory=True, video_dtype=torch.bfloat16, question_dtype=torch.bfloat16)
     got = list(model.forward_stream([one], device_hook=lambda a: a + 1))
     assert torch.equal(got[0], want[0] + 1)
+
+
+@pytest.mark.parametrize('name', ['rx_small', 'i3d_small'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_random_layouts_match_the_reference(name, precision):
+    """Fuzzing beyond the templates: 150 random well-typed layouts per configuration (every operator, up to 17 module calls; 200+ distinct
+    (level, operator, variant) groups in one batch, i.e. more than the dependency scheduler's event table -> wave scheduling) in ONE batch
+    against the unmodified reference's logits (tests/golden/random_layouts.npz)."""
+    cfg, weights, qs, want, meta = gu.load_random(name)
+    model = _model(cfg, weights, meta['pretrain_modules'], precision)
+    out = model(qs, return_res_by_step=False, test_mode=True)
+    torch.cuda.synchronize()
+    model.check_status(out['state'])
+    _close(out['logits'], want, precision, 'random layouts (%s)' % name)
+    got_ans = out['answers'].cpu().long()
+    ok = _margin_ok(want, logits=True) if precision == 'bf16' else torch.ones(len(qs), dtype=torch.bool)
+    assert torch.equal(got_ans[ok], want.argmax(1)[ok])
+    if precision == 'fp32':
+        # the same questions one at a time and in two halves: batching must not matter
+        halves = torch.cat([model(qs[:61], return_res_by_step=False, test_mode=True)['logits'], model(qs[61:], return_res_by_step=False, test_mode=True)['logits']])
+        assert torch.equal(halves, out['logits'])

@@ -143,3 +143,15 @@ def test_aten_lstm_variant_equals_loop(fx):
             lb = b(data, return_res_by_step=False, test_mode=True)['logits']
         torch.testing.assert_close(la, lb, **TOL)
         torch.testing.assert_close(lb, ref['logits'], **TOL)
+
+
+@pytest.mark.parametrize('name', ['rx_small', 'i3d_small'])
+def test_oracle_matches_the_reference_on_random_layouts(name):
+    """150 random well-typed layouts per configuration (all 18 operators, up to 17 module calls, compositions none of the probed AGQA
+    templates contain): the oracle's logits equal the unmodified reference's (tests/golden/make_random_golden.py)."""
+    cfg, weights, qs, want, meta = gu.load_random(name)
+    oracle = orc.OracleNMN(cfg, weights, meta['pretrain_modules'])
+    with torch.no_grad():
+        got = torch.stack([oracle(d, return_res_by_step=False, test_mode=True)['logits'] for d in qs])
+    torch.testing.assert_close(got, want, **TOL)
+    assert torch.equal(got.argmax(1), want.argmax(1))
