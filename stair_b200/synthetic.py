@@ -167,6 +167,15 @@ def make_question(rng: np.random.Generator, template: str, T: int, V: int, text_
     return data
 
 
+def _subtree_end(tokens, i):
+    """Index one past the prefix-order subtree rooted at token i (arity table of utils/program_parser.py:16-23)."""
+    need = 1
+    while need:
+        need += MODULE_ARITY.get(tokens[i], 0) - 1
+        i += 1
+    return i
+
+
 def make_gold(rng, tokens, idx_list, T, text_size, object_types):
     """Random intermediate supervision with the value types ``CriterionByModule`` expects
     (train_module.py:83-194): bool / (s,e) / [(s,e)..] / {name:(s,e)} / [(class, glove[n_w,text])...]."""
@@ -179,8 +188,8 @@ def make_gold(rng, tokens, idx_list, T, text_size, object_types):
         if tok in ('Exists', 'Xor', 'Equals'):
             gold[idx] = bool(rng.integers(0, 2))
         elif tok == 'Localize':
-            # K = 2 iff the keyword argument is an Array2 (token right after the feat argument subtree)
-            k = 2 if tokens[i + 1] == 'video' and tokens[i + 2] == 'Array2' else 1
+            # K = 2 iff the keyword argument (the token right after the feat argument's subtree) is an Array2
+            k = 2 if tokens[_subtree_end(tokens, i + 1)] == 'Array2' else 1
             gold[idx] = tuple(interval() for _ in range(k))
         elif tok in ('Temporal', 'ExistsFrame'):
             gold[idx] = interval()
@@ -313,8 +322,9 @@ def random_layout(rng: np.random.Generator, max_modules: int = 12):
 
 
 def make_random_questions(n: int, T: int, V: int, seed: int = 99, max_modules: int = 12, text_size: int = 300, answer_vocab: int = 172,
-                          distinct: int | None = None):
-    """``n`` questions over ``distinct`` (default n) random well-typed layouts; reference data-dict schema."""
+                          distinct: int | None = None, with_gold: bool = False, object_types: int = 256):
+    """``n`` questions over ``distinct`` (default n) random well-typed layouts; reference data-dict schema (``with_gold``: random
+    intermediate supervision for every supervisable non-root module, as ``make_gold``)."""
     rng = np.random.default_rng(seed)
     layouts = [random_layout(rng, max_modules) for _ in range(distinct or n)]
     out = []
@@ -331,6 +341,8 @@ def make_random_questions(n: int, T: int, V: int, seed: int = 99, max_modules: i
                     'prog_str_to_question_tokens': spans, 'nmn_program_list': list(tokens), 'nmn_program_idx': list(idx_list),
                     'answer': torch.tensor(int(rng.integers(0, answer_vocab - 1))), 'qa_id': 'rnd-%d' % i,
                     'question_raw': ' '.join(tokens), 'template': 'random'})
+        if with_gold:
+            out[-1]['sg_res_by_step'] = make_gold(rng, tokens, idx_list, T, text_size, object_types)
     return out
 
 

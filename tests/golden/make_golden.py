@@ -83,6 +83,59 @@ def gold_to_json(gold):
     return out
 
 
+def reference_window(model, crit, args, batch):
+    """One gradient-accumulation window with the reference criterion and the loop semantics of train_module.py:341-412 (losses scaled by
+    weight / gradient_accumulation, window-level contrastive negatives) followed by ``backward()``.  Returns (loss, logs, FilterFrame losses)."""
+    model.zero_grad()
+    batch_loss, logs = 0., {m: [] for m in crit.criterions}
+    class_reps, neg_reps = {}, {}
+    ff_losses = []
+    for it, data in enumerate(batch):
+        out = model(data, return_res_by_step=True)
+        gold_by_step = out['sg_res_by_step']
+        example_loss = 0.
+        for step, (module, res) in out['res_by_step'].items():       # train_module.py:350-373
+            if module == 'FilterFrame' and step in gold_by_step:
+                ff_losses.append([it, int(step), float(crit(module, res, gold_by_step[step]))])
+            if step not in gold_by_step or module in args.modules_no_intermediate_train or module not in crit.criterions:
+                continue
+            sg = gold_by_step[step]
+            if sg is None:
+                continue
+            if module in ['Filter', 'Superlative', 'ToAction']:
+                for cname, crep in sg:
+                    class_reps.setdefault(cname, []).append((it, module, res))
+                    neg_reps[cname] = crep
+            else:
+                loss = crit(module, res, sg)
+                logs[module].append(float(loss))
+                example_loss = example_loss + loss * args.module_loss_weight / args.gradient_accumulation
+        loss = crit('decoder', out['logits'], data['answer'])           # :376-380
+        logs['decoder'].append(float(loss))
+        batch_loss = batch_loss + example_loss + loss * args.decoder_loss_weight / args.gradient_accumulation
+    for cname, vals in class_reps.items():                              # :388-406
+        for _, module, res in vals:
+            pos = neg_reps[cname]
+            neg = [v for k, v in neg_reps.items() if k != cname]
+            gold = torch.cat([pos.unsqueeze(0), torch.stack(neg)]) if neg else pos.unsqueeze(0)
+            loss = crit(module, res, gold)
+            logs[module].append(float(loss))
+            batch_loss = batch_loss + loss * args.module_loss_weight / args.gradient_accumulation
+    batch_loss.backward()
+    return batch_loss, logs, ff_losses
+
+
+def make_criterion(object_types, ga):
+    with tempfile.NamedTemporaryFile('w', suffix='.json', delete=False) as f:
+        json.dump({'obj_%d' % i: i for i in range(object_types)}, f)
+    args = types.SimpleNamespace(word2id_filename=f.name, module_loss_weight=1.0, decoder_loss_weight=1.0,
+                                 gradient_accumulation=ga, modules_no_intermediate_train=['FilterFrame'])
+    with contextlib.redirect_stdout(io.StringIO()):
+        crit = ref_train.CriterionByModule(args)
+    os.unlink(f.name)
+    return crit, args
+
+
 def run_config(name, c):
     cfg = syn.model_config(T=c['T'], V=c['V'], hidden=c['hidden'], text_size=c['text_size'],
                            answer_vocab=c['answer_vocab'], object_types=c['object_types'])
@@ -129,49 +182,8 @@ def run_config(name, c):
         meta['questions'].append(q)
 
     # ---- one gradient-accumulation window, reference criterion + loop semantics ---------------------
-    with tempfile.NamedTemporaryFile('w', suffix='.json', delete=False) as f:
-        json.dump({'obj_%d' % i: i for i in range(c['object_types'])}, f)
-    args = types.SimpleNamespace(word2id_filename=f.name, module_loss_weight=1.0, decoder_loss_weight=1.0,
-                                 gradient_accumulation=len(batch), modules_no_intermediate_train=['FilterFrame'])
-    with contextlib.redirect_stdout(io.StringIO()):
-        crit = ref_train.CriterionByModule(args)
-    os.unlink(f.name)
-    model.zero_grad()
-    batch_loss, logs = 0., {m: [] for m in crit.criterions}
-    class_reps, neg_reps = {}, {}
-    ff_losses = []
-    for it, data in enumerate(batch):
-        out = model(data, return_res_by_step=True)
-        gold_by_step = out['sg_res_by_step']
-        example_loss = 0.
-        for step, (module, res) in out['res_by_step'].items():       # train_module.py:350-373
-            if module == 'FilterFrame' and step in gold_by_step:
-                ff_losses.append([it, int(step), float(crit(module, res, gold_by_step[step]))])
-            if step not in gold_by_step or module in args.modules_no_intermediate_train or module not in crit.criterions:
-                continue
-            sg = gold_by_step[step]
-            if sg is None:
-                continue
-            if module in ['Filter', 'Superlative', 'ToAction']:
-                for cname, crep in sg:
-                    class_reps.setdefault(cname, []).append((it, module, res))
-                    neg_reps[cname] = crep
-            else:
-                loss = crit(module, res, sg)
-                logs[module].append(float(loss))
-                example_loss = example_loss + loss * args.module_loss_weight / args.gradient_accumulation
-        loss = crit('decoder', out['logits'], data['answer'])           # :376-380
-        logs['decoder'].append(float(loss))
-        batch_loss = batch_loss + example_loss + loss * args.decoder_loss_weight / args.gradient_accumulation
-    for cname, vals in class_reps.items():                              # :388-406
-        for _, module, res in vals:
-            pos = neg_reps[cname]
-            neg = [v for k, v in neg_reps.items() if k != cname]
-            gold = torch.cat([pos.unsqueeze(0), torch.stack(neg)]) if neg else pos.unsqueeze(0)
-            loss = crit(module, res, gold)
-            logs[module].append(float(loss))
-            batch_loss = batch_loss + loss * args.module_loss_weight / args.gradient_accumulation
-    batch_loss.backward()
+    crit, args = make_criterion(c['object_types'], len(batch))
+    batch_loss, logs, ff_losses = reference_window(model, crit, args, batch)
     meta['window'] = {'loss': float(batch_loss), 'logs': logs, 'filterframe_losses': ff_losses}
     seen = set()
     for k, p in model.named_parameters():

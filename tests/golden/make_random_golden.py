@@ -30,9 +30,12 @@ from video_nmn.module_net import VideoNMN  # noqa: E402  (reference)
 
 from stair_b200 import synthetic as syn  # noqa: E402
 from tests import golden_util as gu  # noqa: E402
+from tests.golden import make_golden as mg  # noqa: E402  (reference_window / make_criterion: the reference criterion + window loop)
 
 N_LAYOUTS = 150
 SEEDS = {'rx_small': 20250, 'i3d_small': 20251}
+N_TRAIN = 40                                  # questions of the random-layout training window (with intermediate supervision)
+TRAIN_SEEDS = {'rx_small': 30250, 'i3d_small': 30251}
 
 
 def main():
@@ -52,6 +55,24 @@ def main():
         store[name + '/logits'] = np.stack(logits).astype(np.float32)
         meta[name] = {'seed': seed, 'n': N_LAYOUTS, 'tokens': [d['nmn_program_list'] for d in qs],
                       'modules': [sum(1 for t in d['nmn_program_list'] if t in syn.MODULE_ARITY) for d in qs]}
+        # ---- one accumulation window of random layouts with gold for every supervisable non-root module: reference losses + gradients ----
+        tq = syn.make_random_questions(N_TRAIN, cfg['max_video_length'], cfg['video_size'], seed=TRAIN_SEEDS[name], text_size=cfg['text_size'],
+                                       answer_vocab=cfg['answer_vocab_length'], with_gold=True, object_types=cfg['object_types'])
+        crit, args = mg.make_criterion(cfg['object_types'], len(tq))
+        model.train()                                                   # dropout is 0 in these configs; train() as in train_module.py:341
+        loss, logs, _ = mg.reference_window(model, crit, args, tq)
+        model.eval()
+        seen = set()
+        for k, p in model.named_parameters():
+            if id(p) in seen:
+                continue
+            seen.add(id(p))
+            if p.grad is not None:
+                store[name + '/g/' + k] = p.grad.numpy().copy()
+        meta[name]['train'] = {'seed': TRAIN_SEEDS[name], 'n': N_TRAIN, 'loss': float(loss), 'logs': logs,
+                               'tokens': [d['nmn_program_list'] for d in tq],
+                               'params_without_grad': [k for k, p in model.named_parameters() if p.grad is None]}
+        print(name, 'training window of', N_TRAIN, 'random layouts: loss %.6f' % float(loss), {m: len(v) for m, v in logs.items() if v})
         print(name, 'layouts', N_LAYOUTS, 'modules per layout: max %d mean %.1f' % (max(meta[name]['modules']), np.mean(meta[name]['modules'])),
               'distinct operators', len({t for d in qs for t in d['nmn_program_list'] if t in syn.MODULE_ARITY}))
     np.savez_compressed(os.path.join(HERE, 'random_layouts.npz'), **store)

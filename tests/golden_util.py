@@ -66,3 +66,18 @@ def load_random(name):
     assert [d['nmn_program_list'] for d in qs] == rmeta['tokens'], \
         'synthetic.random_layout changed: regenerate tests/golden/random_layouts.* with make_random_golden.py'
     return cfg, weights, qs, logits, meta
+
+
+def load_random_train(name):
+    """(cfg, weights, window questions with gold, {'loss', 'logs', 'params_without_grad'}, reference gradients, meta) of the random-layout
+    TRAINING window of tests/golden/make_random_golden.py."""
+    cfg, weights, _, meta, _ = load(name)
+    tm = json.load(open(os.path.join(GOLDEN_DIR, 'random_layouts.json')))[name]['train']
+    npz = np.load(os.path.join(GOLDEN_DIR, 'random_layouts.npz'))
+    pre = name + '/g/'
+    grads = {k[len(pre):]: torch.from_numpy(npz[k]) for k in npz.files if k.startswith(pre)}
+    qs = syn.make_random_questions(tm['n'], cfg['max_video_length'], cfg['video_size'], seed=tm['seed'], text_size=cfg['text_size'],
+                                   answer_vocab=cfg['answer_vocab_length'], with_gold=True, object_types=cfg['object_types'])
+    assert [d['nmn_program_list'] for d in qs] == tm['tokens'], \
+        'synthetic.random_layout changed: regenerate tests/golden/random_layouts.* with make_random_golden.py'
+    return cfg, weights, qs, tm, grads, meta

@@ -155,3 +155,30 @@ def test_oracle_matches_the_reference_on_random_layouts(name):
         got = torch.stack([oracle(d, return_res_by_step=False, test_mode=True)['logits'] for d in qs])
     torch.testing.assert_close(got, want, **TOL)
     assert torch.equal(got.argmax(1), want.argmax(1))
+
+
+@pytest.mark.parametrize('name', ['rx_small', 'i3d_small'])
+def test_oracle_window_on_random_layouts(name):
+    """Row L on random layouts: a 40-question window with supervision on every supervisable non-root module (all nine criteria fire) —
+    the oracle's window loss, per-criterion logs and autograd gradients equal the reference's (make_random_golden.py)."""
+    cfg, weights, qs, tm, grads, meta = gu.load_random_train(name)
+    w = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
+    for k in list(w):
+        if k.startswith('submodules.Superlative.localize_module.'):
+            w[k] = w[k.replace('Superlative.localize_module', 'Localize')]
+    model = orc.OracleNMN(cfg, w, meta['pretrain_modules'])
+    crit = orc.OracleCriterion({'obj_%d' % i: i for i in range(cfg['object_types'])})
+    total, logs, _ = orc.window_loss(model, crit, qs)
+    assert abs(float(total) - tm['loss']) < 2e-5 * abs(tm['loss'])
+    for mname, vals in tm['logs'].items():
+        assert len(vals) == len(logs[mname]), mname
+        for a, b in zip(sorted(vals), sorted(logs[mname])):
+            assert abs(a - b) <= 2e-5 * max(1.0, abs(a)), mname
+    total.backward()
+    for k, g in grads.items():
+        got = w[k].grad
+        assert got is not None, k
+        assert float((got - g).abs().max()) <= 1e-4 * max(float(g.abs().max()), 1e-6) + 1e-7, k
+    for k in tm['params_without_grad']:
+        if k in w and not k.startswith('submodules.Superlative.localize_module.'):
+            assert w[k].grad is None or float(w[k].grad.abs().max()) == 0.0, k

@@ -651,3 +651,20 @@ def test_bf16_gradients_of_a_large_window_are_tight():
         with open(rep, 'a') as fh:
             fh.write('== large window 510 (bf16)\n%s\nworst tensor l2rel %.3e, ALL gradients l2rel %.3e\n' % ('\n'.join(lines), worst, glob))
     assert worst <= BF16_LARGE_TENSOR_L2 and glob <= BF16_LARGE_GLOBAL_L2, 'worst tensor %.3e, global %.3e\n%s' % (worst, glob, '\n'.join(lines))
+
+
+@pytest.mark.parametrize('name', ['rx_small', 'i3d_small'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_random_layout_window_loss_and_gradients(name, precision):
+    """Row L beyond the templates: a window of 40 random well-typed layouts with supervision on every supervisable non-root module
+    (all nine criteria fire; tests/golden/make_random_golden.py) — window loss and every parameter gradient against the unmodified
+    reference's ``backward()``."""
+    cfg, weights, qs, tm, grads, meta = gu.load_random_train(name)
+    model = _model(cfg, weights, meta['pretrain_modules'], precision)
+    step = NMNTrainStep(model)
+    out = step(qs)
+    torch.cuda.synchronize()
+    model.check_status(out['state'])
+    assert abs(float(out['loss']) - tm['loss']) <= LOSS_TOL[precision] * abs(tm['loss']), (float(out['loss']), tm['loss'])
+    bad = _compare_grads(model, grads, tm['params_without_grad'], precision, 'random layouts ' + name)
+    assert not bad, '\n'.join(bad)
