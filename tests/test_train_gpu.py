@@ -114,14 +114,20 @@ def test_span_to_attention_known_answers(fx):
 
 
 @pytest.mark.parametrize('shape', ['rx', 'i3d'])
-def test_full_size_window_against_oracle_autograd(shape):
-    """One 32-question window (all 16 layouts twice) at the real dimensions (H=512): CUDA backward vs the oracle's autograd."""
+@pytest.mark.parametrize('layouts', ['templates', 'random'])
+def test_full_size_window_against_oracle_autograd(shape, layouts):
+    """One 32-question window at the real dimensions (H=512): CUDA backward vs the oracle's autograd — the layout templates, or 32 random
+    well-typed layouts with supervision on every supervisable module (the oracle's window is pinned to the reference on such windows by
+    tests/test_oracle_golden.py::test_oracle_window_on_random_layouts)."""
     T, V = (8, 4096) if shape == 'rx' else (64, 1024)
     cfg = syn.model_config(T=T, V=V)
     torch.manual_seed(0)
     ref_model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
     weights = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
-    qs = syn.make_questions(32, T, V, seed=321, templates=list(syn.ALL_TEMPLATES), with_gold=True)
+    if layouts == 'templates':
+        qs = syn.make_questions(32, T, V, seed=321, templates=list(syn.ALL_TEMPLATES), with_gold=True)
+    else:
+        qs = syn.make_random_questions(32, T, V, seed=5151, with_gold=True)
     w = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
     for k in list(w):
         if k.startswith('submodules.Superlative.localize_module.'):
@@ -138,7 +144,7 @@ def test_full_size_window_against_oracle_autograd(shape):
         torch.cuda.synchronize()
         model.check_status(out['state'])
         assert abs(float(out['loss']) - float(total)) <= LOSS_TOL[precision] * abs(float(total))
-        bad = _compare_grads(model, ref_grads, no_grad, precision, 'oracle ' + shape)
+        bad = _compare_grads(model, ref_grads, no_grad, precision, 'oracle %s %s' % (shape, layouts))
         assert not bad, '\n'.join(bad)
 
 
