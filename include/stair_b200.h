@@ -10,9 +10,9 @@
  * work is enqueued on the `stream` argument (a cudaStream_t passed as void*).  Pointers are device pointers
  * unless marked HOST, and must be 16-byte aligned.  sm_100a only; there is no CPU or library fallback.
  *
- * What the library itself owns (and nothing else): per calling thread, 7 non-blocking side streams + 8 events on which the independent
- * module groups of a schedule wave run concurrently (forked from and joined back into `stream`, so a call stays stream-ordered for the
- * caller), and one pinned host int that device-side protocol time-outs report into (stair_gemm_error_flag).  stair_init() creates them
+ * What the library itself owns (and nothing else): per calling thread, 7 non-blocking side streams + 104 events (one fork, one join per
+ * lane, one completion event per module group) on which independent module groups run concurrently in dependency order (forked from and
+ * joined back into `stream`, so a call stays stream-ordered for the caller), and one pinned host int that device-side protocol time-outs report into (stair_gemm_error_flag).  stair_init() creates them
  * for the calling thread on the current device (otherwise the first forward of the thread does), stair_shutdown() synchronises the
  * device and destroys them.  One process (thread) per GPU is the intended use; a thread that changes its current device must call
  * stair_shutdown() / stair_init() around the change.
