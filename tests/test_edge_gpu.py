@@ -216,3 +216,31 @@ def test_optional_kernel_forms_do_not_change_the_forward(T, V):
             getattr(lib, name)(default)
         assert lib.stair_gemm_error_flag() == 0
         assert torch.equal(out, ref), (name, on, float((out - ref).abs().max()))
+
+
+@pytest.mark.parametrize('T', [16, 32, 128])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_other_frame_counts_against_oracle(T, precision):
+    """Frame counts other than the two benchmark configurations: T = 16 / 32 (Linear(T, T) relate, modules.py:271-277) and T = 128
+    (Conv1d relate with k = 32, 32, 65, modules.py:255-266; one instance spans a whole 128-row GEMM tile) — templates and random layouts
+    against the CPU oracle."""
+    V, hid = 96, 128
+    cfg = syn.model_config(T=T, V=V, hidden=hid, object_types=16)
+    torch.manual_seed(T)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision=precision)
+    weights = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    qs = syn.make_questions(34, T, V, seed=T, templates=list(syn.ALL_TEMPLATES), object_types=16) + syn.make_random_questions(40, T, V, seed=T + 1)
+    oracle = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES)
+    with torch.no_grad():
+        want = torch.stack([oracle(d, return_res_by_step=False, test_mode=True)['logits'] for d in qs])
+    model = model.cuda().eval()
+    out = model(qs, return_res_by_step=False, test_mode=True)
+    torch.cuda.synchronize()
+    model.check_status(out['state'])
+    got = out['logits'].cpu()
+    scale = max(1.0, float(want.abs().max()))
+    if precision == 'fp32':
+        assert float((got - want).abs().max()) <= 2e-4 * scale
+        assert torch.equal(out['answers'].cpu().long(), want.argmax(1))
+    else:
+        assert float((got - want).abs().max()) <= 3e-2 * float(want.abs().max()) + 2e-3
