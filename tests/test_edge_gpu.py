@@ -244,3 +244,34 @@ def test_other_frame_counts_against_oracle(T, precision):
         assert torch.equal(out['answers'].cpu().long(), want.argmax(1))
     else:
         assert float((got - want).abs().max()) <= 3e-2 * float(want.abs().max()) + 2e-3
+
+
+@pytest.mark.parametrize('dims', [dict(V=100, text_size=52, answer_vocab=37, hidden=384), dict(V=200, text_size=768, answer_vocab=1000, hidden=256),
+                                  dict(V=4096, text_size=300, answer_vocab=172, hidden=320)])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_other_model_dimensions_against_oracle(dims, precision):
+    """Model dimensions other than the benchmark's: feature / embedding sizes that are not multiples of 8 (staged operands instead of direct
+    TMA), a BERT-sized text embedding, small and large answer vocabularies, hidden sizes 256 / 320 / 384 (h = 160 is not a fused-recurrence
+    size: per-step LSTM path; 384 is not a multiple of 256: no CTA-pair GEMM) — templates and random layouts against the CPU oracle."""
+    T = 8
+    cfg = syn.model_config(T=T, V=dims['V'], hidden=dims['hidden'], text_size=dims['text_size'], answer_vocab=dims['answer_vocab'], object_types=16)
+    torch.manual_seed(dims['V'])
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision=precision)
+    weights = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    kw = dict(text_size=dims['text_size'], answer_vocab=dims['answer_vocab'])
+    qs = syn.make_questions(34, T, dims['V'], seed=1, templates=list(syn.ALL_TEMPLATES), object_types=16, **kw) + \
+        syn.make_random_questions(30, T, dims['V'], seed=2, **kw)
+    oracle = orc.OracleNMN(cfg, weights, syn.PRETRAIN_MODULES)
+    with torch.no_grad():
+        want = torch.stack([oracle(d, return_res_by_step=False, test_mode=True)['logits'] for d in qs])
+    model = model.cuda().eval()
+    out = model(qs, return_res_by_step=False, test_mode=True)
+    torch.cuda.synchronize()
+    model.check_status(out['state'])
+    got = out['logits'].cpu()
+    assert got.shape == want.shape
+    if precision == 'fp32':
+        assert float((got - want).abs().max()) <= 2e-4 * max(1.0, float(want.abs().max()))
+        assert torch.equal(out['answers'].cpu().long(), want.argmax(1))
+    else:
+        assert float((got - want).abs().max()) <= 3e-2 * float(want.abs().max()) + 2e-3
