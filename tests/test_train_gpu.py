@@ -113,21 +113,23 @@ def test_span_to_attention_known_answers(fx):
         assert max(abs(float(a) - b) for a, b in zip(got, case['out'])) < 1e-6
 
 
-@pytest.mark.parametrize('shape', ['rx', 'i3d'])
+@pytest.mark.parametrize('shape', ['rx', 'i3d', 'odd'])
 @pytest.mark.parametrize('layouts', ['templates', 'random'])
 def test_full_size_window_against_oracle_autograd(shape, layouts):
     """One 32-question window at the real dimensions (H=512): CUDA backward vs the oracle's autograd — the layout templates, or 32 random
     well-typed layouts with supervision on every supervisable module (the oracle's window is pinned to the reference on such windows by
     tests/test_oracle_golden.py::test_oracle_window_on_random_layouts)."""
-    T, V = (8, 4096) if shape == 'rx' else (64, 1024)
-    cfg = syn.model_config(T=T, V=V)
+    # 'odd': T = 16, unaligned feature / embedding sizes, hidden 384 (no CTA-pair GEMM, h = 192 recurrence), a 37-word answer vocabulary
+    T, V = {'rx': (8, 4096), 'i3d': (64, 1024), 'odd': (16, 100)}[shape]
+    kw = dict(text_size=52, answer_vocab=37) if shape == 'odd' else {}
+    cfg = syn.model_config(T=T, V=V, hidden=384, **kw) if shape == 'odd' else syn.model_config(T=T, V=V)
     torch.manual_seed(0)
     ref_model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='fp32')
     weights = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
     if layouts == 'templates':
-        qs = syn.make_questions(32, T, V, seed=321, templates=list(syn.ALL_TEMPLATES), with_gold=True)
+        qs = syn.make_questions(32, T, V, seed=321, templates=list(syn.ALL_TEMPLATES), with_gold=True, **kw)
     else:
-        qs = syn.make_random_questions(32, T, V, seed=5151, with_gold=True)
+        qs = syn.make_random_questions(32, T, V, seed=5151, with_gold=True, **kw)
     w = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
     for k in list(w):
         if k.startswith('submodules.Superlative.localize_module.'):
