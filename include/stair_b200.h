@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define STAIR_ABI_VERSION 7
+#define STAIR_ABI_VERSION 8
 #define STAIR_MAX_GROUP_DEPS 8
 
 /* status codes */
@@ -214,6 +214,14 @@ typedef struct StairTrain {
      * gold / rowsum) on the [T, O] head of supervised FilterFrame nodes.  ff_gold [n_ff][T][O] is the normalised gold, ff_w the weight
      * per element (module_loss_weight / (ga T O)); dhead_ff has the shape of StairBuffers.head_ff.  loss[7] receives the sum. */
     int32_t n_ff; const int32_t* ff_node; const float* ff_gold; const float* ff_w; float* dhead_ff; int64_t dhead_ff_elems;
+    /* External gradient seeds (all NULL = the built-in criteria above).  When `ext_dlogits` is set the backward skips its own losses and
+     * starts from the caller's gradients with respect to what the forward exposed — the reference's `loss.backward()` on `logits` and on the
+     * `res_by_step` tensors (module_net.py:107-113,140-145) with ANY torch loss (stair_b200/train.py DifferentiableNMN binds this as a
+     * torch.autograd.Function):  ext_dlogits [B, A];  ext_datt [att_rows, T] (Localize / ExistsFrame maps and Temporal's stashed gate live in
+     * the ATT arena);  ext_dhead_small [small rows, 2] (Linear heads of Exists / Xor / Equals);  ext_dhead_vec [hvec rows, H] (L2Normalize
+     * heads of Filter / ToAction / Superlative);  ext_dhead_ff [ff rows, T, O] (FilterFrame head).  fp32, shapes of the forward buffers;
+     * any of the last four may be NULL (= zero). */
+    const float* ext_dlogits; const float* ext_datt; const float* ext_dhead_small; const float* ext_dhead_vec; const float* ext_dhead_ff;
 } StairTrain;
 
 /* Host evaluation (no GPU work) of the dropout mask of site `site` (a STAIR_W_* id of the Linear the Dropout follows) for the
@@ -225,7 +233,7 @@ int stair_shutdown(void);    /* cudaDeviceSynchronize, then destroy them (a late
 /* sizeof() of the ABI structs as compiled (0 StairModel, 1 StairGroup, 2 StairBatch, 3 StairBuffers, 4 StairItabLayout, 5 StairTrain):
  * 6 StairAdamSeg; lets a binding verify its mirror of the struct layouts. */
 int64_t stair_sizeof(int which);
-/* concurrency of the module phase: independent groups of one schedule wave run on up to `lanes` (1..8, default 4) internal streams
+/* concurrency of the module phase: independent groups run on up to `lanes` (1..8, default 8) internal streams
  * forked from and joined back into the caller's stream (the call stays stream-ordered for the caller) */
 int stair_set_lanes(int lanes);
 /* module-phase scheduling: 1 (default) = by data dependency when StairBatch.group_deps is given (per-group events, no barrier between the
@@ -237,8 +245,9 @@ int stair_debug_timeline(int on);
 int stair_debug_timeline_read(float* t0_ms, float* t1_ms, int* lane, int* op, int* count, int* variant, int cap);
 /* encoder recurrence implementation: 0 = fused persistent kernel when eligible (default), 1 = per-step GEMM + cell kernels */
 int stair_set_lstm_impl(int impl);
-/* bf16 recurrence at h = 256: 1 (default) = weight-stationary cluster kernel (csrc/lstm_ws.cu: W_hh resident in the shared memory of a 4-CTA
- * cluster, 128 questions per block); 0 = the streaming kernel of csrc/lstm_fused.cu (64 questions per CTA, W_hh re-read from L2 every step) */
+/* bf16 recurrence at h = 256: 1 = weight-stationary cluster kernel (csrc/lstm_ws.cu: W_hh resident in the shared memory of a 4-CTA cluster,
+ * 128 questions per block; bit-identical, measured no faster); 0 (default; env STAIR_LSTM_WS overrides) = the streaming kernel of
+ * csrc/lstm_fused.cu (64 questions per CTA, W_hh re-read from L2 every step) */
 int stair_set_lstm_ws(int on);
 
 /* ---- dense contraction (tcgen05 + TMA): C[M,N] = act(row_scale[m] * (A[M,K] . W[N,K]^T) + bias[n]) -------------

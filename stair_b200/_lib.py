@@ -87,7 +87,8 @@ class StairTrain(ctypes.Structure):
                 ('dvid', vp), ('dvec', vp), ('datt', vp), ('dtokfeat', vp), ('dqfeat', vp), ('dlogits', vp),
                 ('saved', vp), ('saved_bytes', i64), ('workspace', vp), ('workspace_bytes', i64),
                 ('dropout_p', ctypes.c_float), ('dropout_seed', ctypes.c_uint64), ('act_saved', vp), ('act_saved_bytes', i64),
-                ('n_ff', i32), ('ff_node', vp), ('ff_gold', vp), ('ff_w', vp), ('dhead_ff', vp), ('dhead_ff_elems', i64)]
+                ('n_ff', i32), ('ff_node', vp), ('ff_gold', vp), ('ff_w', vp), ('dhead_ff', vp), ('dhead_ff_elems', i64),
+                ('ext_dlogits', vp), ('ext_datt', vp), ('ext_dhead_small', vp), ('ext_dhead_vec', vp), ('ext_dhead_ff', vp)]
 
 
 class StairAdamSeg(ctypes.Structure):

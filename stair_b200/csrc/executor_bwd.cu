@@ -223,7 +223,7 @@ int chunk_bwd(BCtx& b, const StairGroup& g, int p, int n, int ob, int ab) {
     case STAIR_OP_FILTERFRAME: {
         const int w = STAIR_W_FF_REPR + 4 * g.variant;
         const float* gate = g.variant == 0 ? c.at<float>(c.plan.a0) : nullptr;
-        if (g.head && tr.n_ff > 0 && ab >= 0) {                   // criterion_filterframe: through pretrain_head = Linear(H, O) into d(vid_out)
+        if (g.head && (tr.n_ff > 0 || tr.ext_dhead_ff) && tr.dhead_ff && ab >= 0) {      // criterion_filterframe (or an external seed): through pretrain_head = Linear(H, O) into d(vid_out)
             const int O = c.m.O;
             float* dHd = tr.dhead_ff + static_cast<long long>(ab) * T * O;
             float* dOut2 = b.ws.take<float>(static_cast<long long>(M) * H);
@@ -613,6 +613,43 @@ int losses(BCtx& b) {
     return STAIR_OK;
 }
 
+// StairTrain.ext_*: the caller's gradients with respect to logits / attention maps / head outputs replace the built-in criteria (the
+// gradient arenas were just zeroed).  Head outputs are back-propagated through their pretrain heads into the VEC gradient arena here;
+// the FilterFrame head is handled by the FilterFrame group's backward (dhead_ff).
+int external_seeds(BCtx& b) {
+    Ctx& c = b.c;
+    const StairTrain& tr = b.tr;
+    const long long T = c.T, H = c.H;
+    if (!b.dry) {
+        cudaError_t e = cudaMemcpyAsync(tr.dlogits, tr.ext_dlogits, sizeof(float) * c.b.B * c.m.A, cudaMemcpyDeviceToDevice, c.st);
+        if (e == cudaSuccess && tr.ext_datt) e = cudaMemcpyAsync(tr.datt, tr.ext_datt, sizeof(float) * c.buf.att_rows * T, cudaMemcpyDeviceToDevice, c.st);
+        if (e == cudaSuccess && tr.ext_dhead_ff) {
+            if (!tr.dhead_ff) return STAIR_ERR_ARG;
+            e = cudaMemcpyAsync(tr.dhead_ff, tr.ext_dhead_ff, sizeof(float) * tr.dhead_ff_elems, cudaMemcpyDeviceToDevice, c.st);
+        }
+        if (e != cudaSuccess) return STAIR_ERR_CUDA;
+    }
+    for (int gi = 0; gi < c.b.n_groups; ++gi) {
+        const StairGroup& g = c.b.groups[gi];
+        if (!g.head || g.aux_base < 0) continue;
+        int wslot = -1, nout = 0;
+        switch (g.op) {
+        case STAIR_OP_EQUALS: wslot = STAIR_W_EQUALS_HEAD_W; nout = 1; break;
+        case STAIR_OP_XOR: wslot = STAIR_W_XOR_HEAD_W; nout = 2; break;
+        case STAIR_OP_EXISTS: wslot = STAIR_W_EXISTS_HEAD_W; nout = 2; break;
+        case STAIR_OP_FILTER: case STAIR_OP_TOACTION: case STAIR_OP_SUPERLATIVE:
+            if (tr.ext_dhead_vec) RUN(launch_l2norm_bwd(c.adt, c.buf.vec, g.out_base, tr.ext_dhead_vec, g.aux_base, tr.dvec, g.count, static_cast<int>(H), c.st));
+            continue;
+        default: continue;
+        }
+        if (!tr.ext_dhead_small) continue;
+        if (!c.Wf(wslot)) return STAIR_ERR_ARG;
+        RUN(launch_small_head_bwd(c.adt, c.buf.vec, g.out_base, c.Wf(wslot), nout, tr.ext_dhead_small, g.aux_base, tr.dvec, G(b, wslot), G(b, wslot + 1),
+                                  g.count, static_cast<int>(H), c.st));
+    }
+    return STAIR_OK;
+}
+
 int decoder_bwd(BCtx& b) {
     Ctx& c = b.c;
     const StairTrain& tr = b.tr;
@@ -807,10 +844,11 @@ int run_backward(BCtx& b, int phases = STAIR_BWD_ALL) {
         if (e == cudaSuccess) e = cudaMemsetAsync(tr.dtokfeat, 0, sizeof(float) * c.b.n_tok * H, c.st);
         if (e == cudaSuccess) e = cudaMemsetAsync(tr.dqfeat, 0, sizeof(float) * c.b.B * H, c.st);
         if (e == cudaSuccess) e = cudaMemsetAsync(tr.loss, 0, sizeof(float) * 8, c.st);
-        if (e == cudaSuccess && tr.n_ff > 0 && tr.dhead_ff) e = cudaMemsetAsync(tr.dhead_ff, 0, sizeof(float) * tr.dhead_ff_elems, c.st);
+        if (e == cudaSuccess && (tr.n_ff > 0 || tr.ext_dhead_ff) && tr.dhead_ff) e = cudaMemsetAsync(tr.dhead_ff, 0, sizeof(float) * tr.dhead_ff_elems, c.st);
         if (e != cudaSuccess) return STAIR_ERR_CUDA;
     }
-    STAIR_TRY(losses(b));
+    if (tr.ext_dlogits) STAIR_TRY(external_seeds(b));
+    else STAIR_TRY(losses(b));
     STAIR_TRY(decoder_bwd(b));
     STAIR_TRY(modules_bwd(b));
     if (phases & STAIR_BWD_ENCODERS) STAIR_TRY(encoders_bwd(b));

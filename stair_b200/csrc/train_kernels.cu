@@ -1315,6 +1315,66 @@ __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restr
         reinterpret_cast<float4*>(dst)[i] = a;
     }
 }
+__device__ __forceinline__ float to_float(float x) { return x; }
+__device__ __forceinline__ float to_float(bf16 x) { return __bfloat162float(x); }
+
+// ---- pretrain-head backward for external gradient seeds (StairTrain.ext_dhead_small / ext_dhead_vec) --------------------------------
+template <typename AT>
+__global__ void small_head_bwd_kernel(const AT* __restrict__ vec, int row_base, const float* __restrict__ w, int nout, const float* __restrict__ dout,
+                                      int out_base, float* __restrict__ dvec, float* __restrict__ dW, float* __restrict__ db, int n, int H) {
+    const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * warps + (threadIdx.x >> 5); i < n; i += gridDim.x * warps) {
+        const AT* x = vec + static_cast<long long>(row_base + i) * H;
+        float* dx = dvec + static_cast<long long>(row_base + i) * H;
+        for (int o = 0; o < nout; ++o) {
+            const float g = dout[static_cast<long long>(out_base + i) * 2 + o];
+            if (g == 0.0f) continue;
+            for (int c = lane; c < H; c += 32) {
+                atomicAdd(dx + c, g * __ldg(w + o * H + c));
+                if (dW) atomicAdd(dW + o * H + c, g * to_float(x[c]));
+            }
+            if (db && lane == 0) atomicAdd(db + o, g);
+        }
+    }
+}
+
+int launch_small_head_bwd(int dt, const void* vec, int row_base, const float* w, int nout, const float* dout, int out_base, float* dvec, float* dW,
+                          float* db, int n, int H, cudaStream_t st) {
+    if (n <= 0) return STAIR_OK;
+    if (nout > 2) return STAIR_ERR_ARG;
+    DISPATCH_DT(dt, AT, (small_head_bwd_kernel<AT><<<nblocks(n, 8, 148 * 8), 256, 0, st>>>(reinterpret_cast<const AT*>(vec), row_base, w, nout, dout,
+                                                                                                    out_base, dvec, dW, db, n, H)));
+    STAIR_CHECK_LAUNCH();
+    return STAIR_OK;
+}
+
+template <typename AT>
+__global__ void l2norm_bwd_kernel(const AT* __restrict__ vec, int row_base, const float* __restrict__ dout, int out_base, float* __restrict__ dvec, int n, int H) {
+    const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * warps + (threadIdx.x >> 5); i < n; i += gridDim.x * warps) {
+        const AT* x = vec + static_cast<long long>(row_base + i) * H;
+        const float* g = dout + static_cast<long long>(out_base + i) * H;
+        float ss = 0.f, xg = 0.f;
+        for (int c = lane; c < H; c += 32) { const float xv = to_float(x[c]); ss += xv * xv; xg += xv * g[c]; }
+        ss = warp_sum(ss); xg = warp_sum(xg);
+        const float nrm = sqrtf(ss);
+        float* dx = dvec + static_cast<long long>(row_base + i) * H;
+        if (nrm > 1e-12f) {                                    // y = x / |x| :  dx = (g - y (y.g)) / |x|
+            const float inv = 1.0f / nrm, k = xg * inv * inv;
+            for (int c = lane; c < H; c += 32) atomicAdd(dx + c, (g[c] - to_float(x[c]) * k) * inv);
+        } else {                                               // F.normalize clamps the norm at eps: y = x / eps
+            for (int c = lane; c < H; c += 32) atomicAdd(dx + c, g[c] * 1e12f);
+        }
+    }
+}
+
+int launch_l2norm_bwd(int dt, const void* vec, int row_base, const float* dout, int out_base, float* dvec, int n, int H, cudaStream_t st) {
+    if (n <= 0) return STAIR_OK;
+    DISPATCH_DT(dt, AT, (l2norm_bwd_kernel<AT><<<nblocks(n, 8, 148 * 8), 256, 0, st>>>(reinterpret_cast<const AT*>(vec), row_base, dout, out_base, dvec, n, H)));
+    STAIR_CHECK_LAUNCH();
+    return STAIR_OK;
+}
+
 int launch_add_inplace(float* dst, const float* src, long long n, cudaStream_t st) {
     if (n <= 0) return STAIR_OK;
     if (n % 4) return STAIR_ERR_ARG;

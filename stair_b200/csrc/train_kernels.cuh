@@ -57,6 +57,12 @@ extern int g_loss_con_impl;      // 0 = shared-memory kernel when n_cls <= 64, H
 // criterion_filterframe: BCELoss(softmax_O(head row), gold row) per (node, frame); writes d head (not accumulated) and adds to loss[7]
 int launch_loss_ff(const float* head, float* dhead, const int* aux_slot, const int* node, const float* gold, const float* w, float* loss,
                    int n, int T, int O, cudaStream_t st);
+// Backward of the pretrain heads for EXTERNAL gradient seeds (StairTrain.ext_*): Linear(H, nout <= 2) heads of Equals / Xor / Exists
+// (dvec[row] += W^T g, dW += g x^T, db += g) and the L2Normalize heads of Filter / ToAction / Superlative (dvec[row] += (g - y (y.g)) / |x|).
+// vec rows row_base .. row_base + n, seeds dout[(out_base + i) * 2 + o] / dout[(out_base + i) * H ..].
+int launch_small_head_bwd(int dt, const void* vec, int row_base, const float* w, int nout, const float* dout, int out_base, float* dvec, float* dW,
+                          float* db, int n, int H, cudaStream_t st);
+int launch_l2norm_bwd(int dt, const void* vec, int row_base, const float* dout, int out_base, float* dvec, int n, int H, cudaStream_t st);
 int launch_add_inplace(float* dst, const float* src, long long n, cudaStream_t st);     // dst += src (n a multiple of 4, 16-byte aligned)
 int launch_loss_dec(const float* logits, const int* answer, float w, float* dlogits, float* loss, int B, int A, cudaStream_t st);
 

@@ -91,9 +91,10 @@ class VideoNMN(nn.Module):
         return frozenset(m for m in self.pretrain_modules if m in LY.HEAD_KIND)
 
     # ---- the batched forward ---------------------------------------------------------------------------------------
-    def prepare(self, batch: LY.NMNBatch, head_modules=frozenset(), training=False):
+    def prepare(self, batch: LY.NMNBatch, head_modules=frozenset(), training=False, private=False):
         """Allocate (grow-only cache) the arenas / tables of one call and fill the C-ABI structs.
-        Returns (state, StairModel, StairBatch, StairBuffers)."""
+        Returns (state, StairModel, StairBatch, StairBuffers).  ``private``: fresh buffers owned by the returned state instead of the
+        model's cache (several forwards whose results must stay alive at once, e.g. retained autograd graphs)."""
         if batch.device is None or batch.device.type != 'cuda':
             raise L.StairError('batch is not on a CUDA device: call batch.to("cuda") — stair_b200 has no CPU fallback')
         dev = batch.device
@@ -123,19 +124,24 @@ class VideoNMN(nn.Module):
         lib = L.lib()
         ws_bytes = int(lib.stair_nmn_workspace_bytes(ctypes.byref(model), ctypes.byref(sb)))
         itab_ints = int(lib.stair_itab_ints(L.i32(n), L.i32(ng)))
-        st.vid = self._buf('vid', sizes['vid'] * T * H, adt, dev)
-        st.vec = self._buf('vec', sizes['vec'] * H, adt, dev)
-        st.att = self._buf('att', sizes['att'] * T, torch.float32, dev)
-        st.tokfeat = self._buf('tokfeat', batch.n_tok * H, adt, dev)
-        st.qfeat = self._buf('qfeat', B * H, adt, dev)
+        _cached = self._buf
+        if private:
+            def _cached(name, numel, dtype, device):
+                return torch.empty(max(int(numel), 1), dtype=dtype, device=device)
+        self_buf = _cached
+        st.vid = self_buf('vid', sizes['vid'] * T * H, adt, dev)
+        st.vec = self_buf('vec', sizes['vec'] * H, adt, dev)
+        st.att = self_buf('att', sizes['att'] * T, torch.float32, dev)
+        st.tokfeat = self_buf('tokfeat', batch.n_tok * H, adt, dev)
+        st.qfeat = self_buf('qfeat', B * H, adt, dev)
         st.logits = torch.empty((B, A), dtype=torch.float32, device=dev)
         st.answers = torch.empty(B, dtype=torch.int32, device=dev)
-        st.head_small = self._buf('head_small', sizes['small'] * 2, torch.float32, dev)
-        st.head_vec = self._buf('head_vec', sizes['hvec'] * H, torch.float32, dev)
-        st.head_ff = self._buf('head_ff', sizes['ff'] * T * O, torch.float32, dev)
-        st.itab = self._buf('itab', itab_ints, torch.int32, dev)
+        st.head_small = self_buf('head_small', sizes['small'] * 2, torch.float32, dev)
+        st.head_vec = self_buf('head_vec', sizes['hvec'] * H, torch.float32, dev)
+        st.head_ff = self_buf('head_ff', sizes['ff'] * T * O, torch.float32, dev)
+        st.itab = self_buf('itab', itab_ints, torch.int32, dev)
         st.status = torch.zeros(4, dtype=torch.int32, device=dev)
-        ws = self._buf('workspace', ws_bytes, torch.uint8, dev)
+        ws = self_buf('workspace', ws_bytes, torch.uint8, dev)
         bufs = L.StairBuffers()
         bufs.vid, bufs.vid_slots = st.vid.data_ptr(), sizes['vid']
         bufs.vec, bufs.vec_rows = st.vec.data_ptr(), sizes['vec']
@@ -146,7 +152,7 @@ class VideoNMN(nn.Module):
         bufs.itab, bufs.itab_ints = st.itab.data_ptr(), st.itab.numel()
         bufs.workspace, bufs.workspace_bytes = ws.data_ptr(), ws.numel()
         bufs.status = st.status.data_ptr()
-        st.keepalive = (gtab, model, sb, bufs)
+        st.keepalive = (gtab, model, sb, bufs, ws)
         il = L.StairItabLayout()
         lib.stair_itab_layout(L.i32(n), L.i32(ng), ctypes.byref(il))
         st.itab_layout = il

@@ -733,3 +733,211 @@ class FusedAdam(torch.optim.Adam):
                                         L.stream_ptr()), 'stair_adam_step')
             torch.autograd.graph.increment_version(prm)
         return None
+
+
+# ---- differentiable forward: the reference's own training loop on top of the CUDA path ------------------------------------------------
+class _NMNFunction(torch.autograd.Function):
+    """``stair_nmn_forward_train`` / ``stair_nmn_backward`` as ONE autograd node: inputs are the model's parameters, outputs the logits, the
+    attention arena and the three pretrain-head buffers of a batch; the backward seeds the CUDA backward with the caller's gradients
+    (``StairTrain.ext_*``) instead of the built-in criteria."""
+
+    @staticmethod
+    def forward(ctx, owner, batch, dropout_seed, *params):
+        model = owner.model
+        cfg = model.config
+        lib = L.lib()
+        dev = batch.device
+        ctx.set_materialize_grads(False)                          # unused outputs arrive as None in backward (no zero tensors, no head work)
+        heads = frozenset(m for m in model.pretrain_modules if m in LY.HEAD_KIND) if cfg['have_pretrain_head'] else frozenset()
+        st, ms, sb, bufs = model.prepare(batch, heads, training=True, private=True)
+        T, H, A = batch.T, cfg['hidden_size'], cfg['answer_vocab_length']
+        tr = L.StairTrain()
+        tr.dropout_p = float(cfg.get('dropout', 0.0) or 0.0) if model.training else 0.0
+        tr.dropout_seed = int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
+        keep = {}
+
+        def buf(name, numel, dtype):
+            keep[name] = torch.empty(max(int(numel), 1), dtype=dtype, device=dev)
+            return keep[name]
+
+        saved = buf('saved', int(lib.stair_train_saved_bytes(ctypes.byref(ms), ctypes.byref(sb))), torch.uint8)
+        tr.saved, tr.saved_bytes = saved.data_ptr(), saved.numel()
+        act_bytes = int(lib.stair_train_act_bytes(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs)))
+        if 0 < act_bytes <= owner.save_activations_budget:
+            act = buf('act', act_bytes, torch.uint8)
+            tr.act_saved, tr.act_saved_bytes = act.data_ptr(), act.numel()
+        if st.head_ff.numel() > 1:                               # FilterFrame heads present: their gradient buffer takes part in the workspace plan
+            dh = buf('dhead_ff', st.head_ff.numel(), torch.float32)
+            tr.dhead_ff, tr.dhead_ff_elems = dh.data_ptr(), st.sizes['ff'] * T * (cfg.get('object_types', 0) or 0)
+        dummy = buf('ext_probe', 4, torch.float32)
+        tr.ext_dlogits = dummy.data_ptr()                         # external-seed mode from the start (workspace planning depends on it)
+        ws_bytes = int(lib.stair_train_workspace_bytes(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr)))
+        if ws_bytes < 0:
+            raise L.StairError('stair_train_workspace_bytes failed (unsupported configuration)')
+        ws = buf('train_ws', ws_bytes + 256, torch.uint8)
+        tr.workspace, tr.workspace_bytes = ws.data_ptr(), ws.numel()
+        loss = buf('loss', 8, torch.float32)
+        tr.loss = loss.data_ptr()
+        L.check(lib.stair_nmn_forward_train(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), L.stream_ptr()),
+                'stair_nmn_forward_train')
+        ctx.owner, ctx.batch, ctx.state, ctx.structs, ctx.keep, ctx.params = owner, batch, st, (ms, sb, bufs, tr), keep, params
+        owner._last_state = st
+        O = cfg.get('object_types', 0) or 0
+        sizes = st.sizes
+        outs = (st.logits.clone(),
+                st.att[:sizes['att'] * T].clone().view(-1, T),
+                st.head_small[:sizes['small'] * 2].clone().view(-1, 2),
+                st.head_vec[:sizes['hvec'] * H].clone().view(-1, H),
+                st.head_ff[:sizes['ff'] * T * O].clone().view(-1, T, max(O, 1)))
+        return outs
+
+    @staticmethod
+    def backward(ctx, dlogits, datt, dsmall, dhvec, dhff):
+        owner, batch, st = ctx.owner, ctx.batch, ctx.state
+        ms, sb, bufs, tr = ctx.structs
+        model = owner.model
+        cfg = model.config
+        dev = batch.device
+        lib = L.lib()
+        T, H, A = batch.T, cfg['hidden_size'], cfg['answer_vocab_length']
+        tg, offsets, flat_numel = owner._step._layout()
+        flat = torch.zeros(flat_numel, dtype=torch.float32, device=dev)
+        for wid in range(L.W_COUNT):
+            tr.grad[wid] = flat.data_ptr() + 4 * offsets[wid] if wid in offsets else None
+
+        def seed(g, numel):
+            if g is None:
+                return None
+            g = g.detach().to(torch.float32).contiguous()
+            if g.numel() != numel:
+                raise L.StairError('gradient seed has %d elements, expected %d' % (g.numel(), numel))
+            return g
+
+        sizes = st.sizes
+        O = cfg.get('object_types', 0) or 0
+        gl = seed(dlogits, batch.B * A)
+        if gl is None:
+            gl = torch.zeros(batch.B * A, dtype=torch.float32, device=dev)
+        ga_, gs, gv, gf = seed(datt, sizes['att'] * T), seed(dsmall, sizes['small'] * 2), seed(dhvec, sizes['hvec'] * H), seed(dhff, sizes['ff'] * T * max(O, 1))
+        if sizes['ff'] == 0 or not tr.dhead_ff:
+            gf = None
+        tr.ext_dlogits = gl.data_ptr()
+        tr.ext_datt = ga_.data_ptr() if ga_ is not None and ga_.numel() else None
+        tr.ext_dhead_small = gs.data_ptr() if gs is not None and gs.numel() else None
+        tr.ext_dhead_vec = gv.data_ptr() if gv is not None and gv.numel() else None
+        tr.ext_dhead_ff = gf.data_ptr() if gf is not None and gf.numel() else None
+        arenas = [torch.empty(max(n, 1), dtype=torch.float32, device=dev) for n in
+                  (sizes['vid'] * T * H, sizes['vec'] * H, sizes['att'] * T, batch.n_tok * H, batch.B * H, batch.B * A)]
+        tr.dvid, tr.dvec, tr.datt, tr.dtokfeat, tr.dqfeat, tr.dlogits = (t.data_ptr() for t in arenas)
+        L.check(lib.stair_nmn_backward(ctypes.byref(ms), ctypes.byref(sb), ctypes.byref(bufs), ctypes.byref(tr), L.stream_ptr()), 'stair_nmn_backward')
+        # which parameters the graph reaches (everything the batch's layouts execute, the encoders and — when logits were used — the decoder;
+        # head Linears only when their outputs received a gradient): the others get None, like parameters outside an autograd graph
+        touched = touched_slots(batch, LossRows(), False, decoder_active=True)
+        if dlogits is None:
+            touched -= {L.W['DEC0_W'], L.W['DEC0_B'], L.W['DEC1_W'], L.W['DEC1_B']}
+        if gs is not None:
+            for name, op in (('EQUALS_HEAD', 'Equals'), ('XOR_HEAD', 'Xor'), ('EXISTS_HEAD', 'Exists')):
+                if any(op in lay.tokens for lay in batch.layouts):
+                    touched |= {L.W[name + '_W'], L.W[name + '_B']}
+        if gf is not None:
+            touched |= {L.W['FF_HEAD_W'], L.W['FF_HEAD_B']}
+        by_param = {}
+        cuts, entries = owner._step._grad_views()
+        pieces = torch.split_with_sizes(flat, cuts)
+        for wid, piece, prm, dup in entries:
+            if wid in touched:
+                g = pieces[piece].view(prm.shape)
+                by_param[id(prm)] = g.clone() if dup else g
+        ctx.keep['backward'] = (flat, arenas, gl, ga_, gs, gv, gf)
+        return (None, None, None) + tuple(by_param.get(id(p)) if p.requires_grad else None for p in ctx.params)
+
+
+class DifferentiableNMN:
+    """``model(data, return_res_by_step=True)`` of the reference with autograd history: ``logits`` and every ``res_by_step`` tensor
+    (``pretrain_head`` outputs, module_net.py:107-113) are differentiable with respect to the model's parameters, so the reference's own
+    training loop runs unchanged on the CUDA path — any torch criterion on them (``train_module.CriterionByModule``), ``loss.backward()``
+    (once per window over several retained calls, train_module.py:408), ``optimizer.step()``:
+
+    >>> net = DifferentiableNMN(model.train())
+    >>> out = net(data)                                  # one data dict (reference shapes) or a list of them (batched shapes)
+    >>> loss = criterion('decoder', out['logits'], data['answer']) + sum(criterion(m, r, out['sg_res_by_step'][k]) ...)
+    >>> loss.backward(); optimizer.step()
+
+    Forward and backward are the kernels of ``NMNTrainStep`` (forward with history, CUDA backward); only the loss gradients come from
+    autograd (``StairTrain.ext_*`` seeds).  Every call owns its buffers, so several calls can be alive until ``backward``.
+    ``NMNTrainStep`` (built-in criteria, one launch sequence per window) is the fast path; this is the compatible one."""
+
+    def __init__(self, model, dropout_seed=None, save_activations_budget=24 << 30):
+        if not model.config['have_pretrain_head']:
+            raise L.StairError('DifferentiableNMN exposes the pretrain_head outputs: it needs have_pretrain_head')
+        self.model = model
+        self.save_activations_budget = int(save_activations_budget)
+        self.dropout_seed = int(torch.initial_seed() if dropout_seed is None else dropout_seed) & 0xFFFFFFFFFFFFFFFF
+        self.calls = 0
+        self._step = NMNTrainStep(model, distributed=False)
+        from .params import all_parameters
+        self._params = all_parameters(model)
+
+    def __call__(self, data, return_res_by_step=True):
+        from .nmn import OutputViews
+        model = self.model
+        single = isinstance(data, dict)
+        batch = data if isinstance(data, LY.NMNBatch) else LY.collate([data] if single else list(data))
+        dev = next(model.parameters()).device
+        if dev.type != 'cuda':
+            raise L.StairError('VideoNMN parameters are on %s: stair_b200 runs only on CUDA (sm_100a) devices' % dev)
+        if batch.device is None:
+            batch.to(dev)
+        seed = (self.dropout_seed + 0x9E3779B97F4A7C15 * self.calls) & 0xFFFFFFFFFFFFFFFF
+        self.calls += 1
+        logits, att, small, hvec, hff = _NMNFunction.apply(self, batch, seed, *self._params)
+        st = self._last_state
+        self._last_state = None
+        model.check_status(st)
+        ret = {'logits': logits, 'answers': logits.detach().argmax(1).to(torch.int32), 'state': st}
+        if return_res_by_step:
+            views = _DiffViews(model, st, att, small, hvec, hff)
+            ret['res_by_step'] = [views.res_by_step(q) for q in range(batch.B)]
+        else:
+            ret['res_by_step'] = [dict() for _ in range(batch.B)]
+        ret['sg_res_by_step'] = model._encode_gold(batch)
+        if single:
+            ret['logits'], ret['answers'] = ret['logits'][0], ret['answers'][0]
+            ret['res_by_step'], ret['sg_res_by_step'] = ret['res_by_step'][0], ret['sg_res_by_step'][0]
+        return ret
+
+
+def _make_diff_views():
+    from .nmn import OutputViews
+
+    class DiffViews(OutputViews):
+        """``res_by_step`` views over the DIFFERENTIABLE buffers of one ``_NMNFunction`` call (attention arena + head outputs)."""
+
+        def __init__(self, model, st, att, small, hvec, hff):
+            self.model, self.st, self.heads = model, st, None
+            b, il = st.batch, st.itab_layout
+            itab = st.itab.cpu().numpy()
+            n = b.n_nodes
+            self.out_slot = itab[il.out_slot:il.out_slot + n].copy()
+            self.aux_slot = itab[il.aux_slot:il.aux_slot + n].copy()
+            self.att, self.head_small, self.head_vec = att, small, hvec
+            self.head_ff = hff if (model.config.get('object_types', 0) or 0) else None
+            self.vid = self.vec = None
+            self._last_temporal = None
+
+        def node_output(self, q, nd):
+            lay = self.st.batch.layouts[q]
+            if lay.out_type[nd] in (LY.VID, LY.VEC, LY.VEC2):
+                raise L.StairError('only attention maps and pretrain_head outputs are differentiable outputs of DifferentiableNMN')
+            return super().node_output(q, nd)
+
+    return DiffViews
+
+
+def _DiffViews(*args):
+    global _DIFF_VIEWS
+    try:
+        cls = _DIFF_VIEWS
+    except NameError:
+        cls = _DIFF_VIEWS = _make_diff_views()
+    return cls(*args)

@@ -676,3 +676,49 @@ def test_random_layout_window_loss_and_gradients(name, precision):
     assert abs(float(out['loss']) - tm['loss']) <= LOSS_TOL[precision] * abs(tm['loss']), (float(out['loss']), tm['loss'])
     bad = _compare_grads(model, grads, tm['params_without_grad'], precision, 'random layouts ' + name)
     assert not bad, '\n'.join(bad)
+
+
+def _to_cpu(x):
+    if isinstance(x, torch.Tensor):
+        return x.cpu()                                           # differentiable device transfer
+    if isinstance(x, (list, tuple)):
+        return type(x)(_to_cpu(v) for v in x)
+    if isinstance(x, dict):
+        return {k: _to_cpu(v) for k, v in x.items()}
+    return x
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('batched', [False, True])
+def test_reference_training_loop_through_autograd(fx, precision, batched):
+    """The reference's OWN loop on the CUDA path (train_module.py:341-408): ``DifferentiableNMN`` returns logits / res_by_step with autograd
+    history, a torch criterion (the oracle's restatement of CriterionByModule, on the CPU) scores them, ONE ``backward()`` per window runs
+    through the retained per-question graphs into the CUDA backward (external gradient seeds).  Parameter gradients == the unmodified
+    reference's (golden fixtures).  ``batched``: the same window through one call (the questions' slices of the batched outputs)."""
+    from stair_b200.train import DifferentiableNMN
+    name, (cfg, weights, questions, meta, grads) = fx
+    model = _model(cfg, weights, meta['pretrain_modules'], precision)
+    net = DifferentiableNMN(model)
+    crit = orc.OracleCriterion({'obj_%d' % i: i for i in range(cfg['object_types'])})
+    batch = [d for d, _, _ in questions]
+
+    class PerQuestion:
+        def forward(self, data, return_res_by_step=True):
+            return _to_cpu({k: v for k, v in net(data, return_res_by_step=return_res_by_step).items() if k != 'state'})
+
+    class Batched:
+        def __init__(self):
+            self.out = _to_cpu({k: v for k, v in net(batch).items() if k != 'state'})
+            self._q = 0
+
+        def forward(self, data, return_res_by_step=True):
+            q = self._q
+            return {'logits': self.out['logits'][q], 'res_by_step': self.out['res_by_step'][q], 'sg_res_by_step': self.out['sg_res_by_step'][q]}
+
+    total, logs, _ = orc.window_loss(Batched() if batched else PerQuestion(), crit, batch)
+    want = meta['window']['loss']
+    assert abs(float(total) - want) <= LOSS_TOL[precision] * abs(want), 'window loss %g vs reference %g' % (float(total), want)
+    total.backward()
+    torch.cuda.synchronize()
+    bad = _compare_grads(model, grads, meta['params_without_grad'], precision, 'autograd loop %s %s' % (name, 'batched' if batched else 'per question'))
+    assert not bad, '\n'.join(bad)
