@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define STAIR_ABI_VERSION 8
+#define STAIR_ABI_VERSION 9
 #define STAIR_MAX_GROUP_DEPS 8
 
 /* status codes */
@@ -151,6 +151,12 @@ typedef struct StairBatch {
     const int32_t* group_deps; /* HOST [n_groups][STAIR_MAX_GROUP_DEPS] or NULL: the groups whose outputs group g reads (-1 = unused entry; a first
                                 * entry of -2 = "every earlier group").  With it the module phase is scheduled by data dependency (a group starts as
                                 * soon as its producers are done) instead of wave by wave. */
+    /* Optional length-sorted schedule of the inference text recurrence (all three or none; stair_b200.layout.collate fills them):
+     * q_order [B] = the question ids in descending question length (a permutation of 0..B-1), q_soff [B+1] = token offsets in THAT order,
+     * tok_src [n_tok] = the token row (batch order) of every sorted row: tok_src[q_soff[p] + s] = q_off[q_order[p]] + s.  Scheduling data
+     * only: the outputs keep the batch's order and do not depend on it.  NULL: the library sorts on the device itself (two small kernels
+     * in front of the text staging) unless stair_set_text_sort(0). */
+    const int32_t* q_order; const int32_t* q_soff; const int32_t* tok_src;
 } StairBatch;
 
 /* Caller-owned output / scratch buffers. */
@@ -238,10 +244,18 @@ int64_t stair_sizeof(int which);
 int stair_set_lanes(int lanes);
 /* module-phase scheduling: 1 (default) = by data dependency when StairBatch.group_deps is given (per-group events, no barrier between the
  * schedule waves); 0 = wave by wave (fork / join around every wave) */
+/* 1 (default): the inference text recurrence runs over the questions in descending length (StairBatch.q_order / q_soff / tok_src, or a
+ * counting sort on the device when those are NULL): the text projection's input is staged in that order, every 64-question block stops at
+ * its own longest question and the longest blocks start first.  Outputs (token_feature / question_feature rows) keep the batch's order
+ * and are bit-identical to 0 = batch order. */
+int stair_set_text_sort(int on);
 int stair_set_fuse_sum(int on);             /* 1: Filter's sum over frames runs in the epilogue of its second Linear (inference); default 0 (measured no faster) */
 int stair_set_dep_sched(int on);
 /* debug: timing events around every module group of the dependency-scheduled phase; read returns the number of groups (synchronises) */
 int stair_debug_timeline(int on);
+/* with stair_debug_timeline(1): ms from the start of the last forward to [1] video projection, [2] text projection, [3] recurrence, [4] grouping
+ * join, [5] module phase, [6] decoder complete on the caller's stream (ms[0] = 0); returns the number of marks written (synchronises) */
+int stair_debug_phase_marks(float* ms, int cap);
 int stair_debug_timeline_read(float* t0_ms, float* t1_ms, int* lane, int* op, int* count, int* variant, int cap);
 /* encoder recurrence implementation: 0 = fused persistent kernel when eligible (default), 1 = per-step GEMM + cell kernels */
 int stair_set_lstm_impl(int impl);

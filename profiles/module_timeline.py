@@ -15,6 +15,8 @@ model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').c
 qs = syn.make_questions(B, T, V, seed=1234)
 batch = collate(qs, video_dtype=torch.bfloat16).to('cuda')
 lib = L.lib()
+if 'TEXT_SORT' in os.environ:
+    lib.stair_set_text_sort(int(os.environ['TEXT_SORT']))
 ph = L.FWD_ALL if mode == 'full' else L.FWD_MODULES
 for _ in range(5):
     model.forward_batch(batch, phases=L.FWD_ALL)

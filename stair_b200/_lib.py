@@ -63,7 +63,8 @@ class StairBatch(ctypes.Structure):
     _fields_ = [('B', i32), ('T', i32), ('n_tok', i32), ('L_max', i32), ('n_nodes', i32), ('n_groups', i32),
                 ('video_dtype', i32), ('question_dtype', i32), ('video', vp), ('question', vp), ('q_off', vp),
                 ('node_gid', vp), ('node_q', vp), ('node_arg', vp), ('node_span', vp), ('root_node', vp),
-                ('groups', ctypes.POINTER(StairGroup)), ('group_tab', vp), ('group_deps', vp)]
+                ('groups', ctypes.POINTER(StairGroup)), ('group_tab', vp), ('group_deps', vp),
+                ('q_order', vp), ('q_soff', vp), ('tok_src', vp)]
 
 
 class StairBuffers(ctypes.Structure):

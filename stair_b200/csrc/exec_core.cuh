@@ -9,6 +9,7 @@ namespace ex {
 
 extern thread_local long long t_last_launches;   // kernels launched by the last entry-point call on this thread
 extern int g_lstm_impl;                     // 0 = fused persistent recurrence when eligible, 1 = per-step GEMM + cell kernels
+extern int g_text_sort;                     // 1 = inference text recurrence over length-sorted questions (default)
 extern int g_fuse_sum;                      // 1 = Filter's frame sum in the epilogue of its second Linear (inference)
 constexpr int LANES = 8;                 // independent groups of one wave execute concurrently on up to LANES streams (main + side)
 constexpr long long ROW_CAP = 65536;     // frame rows per chunk of a VID-typed group
@@ -18,7 +19,7 @@ inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a
 
 struct Plan {
     // encoder phase
-    long long xv_in, xv, xq_in, xq, g, c, hs, hx;
+    long long xv_in, xv, xq_in, xq, g, c, hs, hx, tsort;
     // module / decoder phase (aliases the encoder regions; everything is stream-ordered)
     long long s0, s1, s2, pl, vp, v01, ats, a0;
     long long total;
@@ -52,6 +53,7 @@ inline void make_plan(const StairModel& m, const StairBatch& b, Plan* p) {
     p->c = take(2 * 2 * ((B + 127) / 128 * 128) * h * 4);     // video + text cell states (the fused kernel runs both encoders at once)
     p->hs = take(np * 2 * B * h * 2);
     p->hx = take(lstm_ws_ok(m.precision, static_cast<int>(h), static_cast<int>(B)) ? 2 * lstm_ws_hx_bytes(static_cast<int>(B)) : 0);   // h exchange of the weight-stationary recurrence (video | text)
+    p->tsort = take((2LL * B + 1 + b.n_tok) * 4);               // length-sorted text schedule: order [B] | soff [B+1] | tok_src [n_tok]
     const long long enc_total = o;
     // module regions
     o = 0;
@@ -183,6 +185,17 @@ inline LaneStreams* lane_streams() {
 }
 
 extern int g_lanes;      // 1 = everything on the caller's stream; up to LANES
+extern int g_timeline;
+// Debug marks on the caller's stream (stair_debug_timeline(1)): 0 forward start, 1 after the video projection, 2 after the text projection,
+// 3 after the recurrence, 4 after the grouping join, 5 after the module phase, 6 after the decoder (stair_debug_phase_marks reads them)
+struct PhaseMarks { cudaEvent_t ev[8]; bool ok = false; };
+inline PhaseMarks& phase_marks() { static PhaseMarks p; return p; }
+inline void phase_mark(cudaStream_t st, int i) {
+    if (!g_timeline) return;
+    PhaseMarks& pm = phase_marks();
+    if (!pm.ok) { for (int k = 0; k < 8; ++k) cudaEventCreate(&pm.ev[k]); pm.ok = true; }
+    cudaEventRecord(pm.ev[i], st);
+}
 
 // ---- encoders (module_net.py:147-163) --------------------------------------------------------------------------
 inline int run_encoders(Ctx& c, int phases) {
@@ -196,10 +209,25 @@ inline int run_encoders(Ctx& c, int phases) {
     // The fp32 -> bf16 staging of the packed question tokens (HBM-bound, ~24 us at B = 4096) only depends on the inputs: with both encoders
     // requested it runs on a side lane underneath the video projection GEMM (whose 200 KB CTAs leave the SMs' thread slots free).
     bool text_staged = false;
+    const bool fused = lstm_fused_ok(m.precision, h) && g_lstm_impl == 0 && c.W(STAIR_W_VENC_WHHI_F) && c.W(STAIR_W_TENC_WHHI_F);
+    const bool ws = fused && lstm_ws_ok(m.precision, h, B);
+    // Inference: the text recurrence runs over the questions in descending length (a 64-question block stops at its own longest question
+    // instead of the batch's).  The sort only permutes which block computes a question; the projection input is staged in that order
+    // (gather by tok_src) so that a block's input rows stay contiguous.  Outputs keep the batch's token order.
+    const bool tsort = (phases & STAIR_FWD_ENCODE_TEXT) && c.inference && fused && !ws && g_text_sort && text_sort_ok(b.L_max) && b.n_tok > 0;
+    const bool tsort_given = tsort && b.q_order && b.q_soff && b.tok_src;      // the caller's schedule (collate); else a device counting sort
+    const int* t_order = !tsort ? nullptr : (tsort_given ? b.q_order : c.at<int>(c.plan.tsort));
+    const int* t_soff = !tsort ? nullptr : (tsort_given ? b.q_soff : t_order + B);
+    const int* t_src = !tsort ? nullptr : (tsort_given ? b.tok_src : t_soff + B + 1);
+    auto device_sort = [&](cudaStream_t st) {
+        int* o = c.at<int>(c.plan.tsort);
+        return launch_text_sort(b.q_off, B, b.L_max, o, o + B, o + 2 * B + 1, st);
+    };
     if ((phases & STAIR_FWD_ENCODE_VIDEO) && (phases & STAIR_FWD_ENCODE_TEXT) && c.inference && g_lanes > 2) {
         if (LaneStreams* ls = lane_streams()) {
             if (cudaEventRecord(ls->join[2], c.st) != cudaSuccess || cudaStreamWaitEvent(ls->side[1], ls->join[2], 0) != cudaSuccess) return STAIR_ERR_CUDA;
-            STAIR_TRY(launch_stage_rows(b.question_dtype, b.question, m.text_size, nullptr, 1, 1, c.at<bf16>(c.plan.xq_in), m.text_ld, b.n_tok, c.np, b.n_tok,
+            if (tsort && !tsort_given) STAIR_TRY(device_sort(ls->side[1]));
+            STAIR_TRY(launch_stage_rows(b.question_dtype, b.question, m.text_size, t_src, 1, 1, c.at<bf16>(c.plan.xq_in), m.text_ld, b.n_tok, c.np, b.n_tok,
                                         m.text_size, ls->side[1]));
             if (cudaEventRecord(ls->join[1], ls->side[1]) != cudaSuccess) return STAIR_ERR_CUDA;
             text_staged = true;
@@ -220,8 +248,8 @@ inline int run_encoders(Ctx& c, int phases) {
         a.w_plane_rows = 4 * H; a.bias = c.Wf(STAIR_W_VENC_B); a.C = c.at<void>(c.plan.xv); a.ldc = 4 * H; a.out_dtype = c.adt;
         a.M = static_cast<int>(rows_v); a.N = 4 * H; a.K = m.V;
         STAIR_TRY(launch_gemm(a, c.st));
+        phase_mark(c.st, 1);
     }
-    const bool fused = lstm_fused_ok(m.precision, h) && g_lstm_impl == 0 && c.W(STAIR_W_VENC_WHHI_F) && c.W(STAIR_W_TENC_WHHI_F);
     if ((phases & STAIR_FWD_ENCODE_VIDEO) && !fused) {
     if (cudaMemsetAsync(cs, 0, sizeof(float) * 2 * B * h, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
     for (int s = 0; s < T; ++s) {
@@ -234,7 +262,6 @@ inline int run_encoders(Ctx& c, int phases) {
     }
     }
     // weight-stationary cluster recurrence (lstm_ws.cu) when eligible (h = 256): one launch per encoder, W_hh resident in shared memory
-    const bool ws = fused && lstm_ws_ok(m.precision, h, B);
     const long long nblk128 = (B + 127) / 128;
     char* hx = c.at<char>(c.plan.hx);
     if (ws && (phases & STAIR_FWD_ENCODE_VIDEO))
@@ -250,13 +277,16 @@ inline int run_encoders(Ctx& c, int phases) {
     {
         bf16* in = c.at<bf16>(c.plan.xq_in);
         if (text_staged) { if (cudaStreamWaitEvent(c.st, lane_streams()->join[1], 0) != cudaSuccess) return STAIR_ERR_CUDA; }
-        else STAIR_TRY(launch_stage_rows(b.question_dtype, b.question, m.text_size, nullptr, 1, 1, in, m.text_ld, b.n_tok, c.np, b.n_tok,
-                                         m.text_size, c.st));
+        else {
+            if (tsort && !tsort_given) STAIR_TRY(device_sort(c.st));
+            STAIR_TRY(launch_stage_rows(b.question_dtype, b.question, m.text_size, t_src, 1, 1, in, m.text_ld, b.n_tok, c.np, b.n_tok, m.text_size, c.st));
+        }
         GemmArgs a;
         a.A = in; a.lda = m.text_ld; a.a_plane_rows = b.n_tok; a.nplanes = c.np; a.W = c.W(STAIR_W_TENC_WIH); a.ldw = m.text_ld;
         a.w_plane_rows = 4 * H; a.bias = c.Wf(STAIR_W_TENC_B); a.C = c.at<void>(c.plan.xq); a.ldc = 4 * H; a.out_dtype = c.adt;
         a.M = b.n_tok; a.N = 4 * H; a.K = m.text_size;
         STAIR_TRY(launch_gemm(a, c.st));
+        phase_mark(c.st, 2);
     }
     if (ws)
         return launch_lstm_ws(c.at<void>(c.plan.xq), c.buf.tokfeat, c.buf.qfeat, b.q_off, b.L_max, c.W(STAIR_W_TENC_WHHI_F), c.W(STAIR_W_TENC_WHHI_R),
@@ -264,7 +294,8 @@ inline int run_encoders(Ctx& c, int phases) {
     if (fused)
         return launch_lstm_fused(c.at<void>(c.plan.xv), c.buf.vid, T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R),
                                  c.at<void>(c.plan.xq), c.buf.tokfeat, c.buf.qfeat, b.q_off, b.L_max, c.W(STAIR_W_TENC_WHHI_F),
-                                 c.W(STAIR_W_TENC_WHHI_R), cs, B, h, (phases & STAIR_FWD_ENCODE_VIDEO) ? 1 : 0, 1, err_flag_ptr(), c.st);
+                                 c.W(STAIR_W_TENC_WHHI_R), cs, B, h, (phases & STAIR_FWD_ENCODE_VIDEO) ? 1 : 0, 1, err_flag_ptr(), c.st, nullptr,
+                                 t_order, t_soff);
     if (cudaMemsetAsync(cs, 0, sizeof(float) * 2 * B * h, c.st) != cudaSuccess) return STAIR_ERR_CUDA;
     for (int s = 0; s < b.L_max; ++s) {
         if (s > 0)

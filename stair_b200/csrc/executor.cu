@@ -8,6 +8,7 @@
 //
 // Scratch is carved from the caller's workspace by `Plan` (same arithmetic in stair_nmn_workspace_bytes).
 #include "exec_core.cuh"
+#include <cstdlib>
 
 namespace stair {
 namespace ex {
@@ -18,6 +19,11 @@ int g_fuse_sum = 0;                      // 1 = Filter's frame sum in the epilog
                                          // at RX, 169 -> 155 at I3D) and NOT faster: these K = 512 GEMMs are epilogue-bound, and the transposing sum costs the
                                          // epilogue more than the separate 4-20 us pass (RX 1.354 -> 1.365-1.377 ms, I3D 5.57-5.72 -> 5.59-5.62 ms;
                                          // profiles/r2_fused_frame_sum_ab.txt)
+static int text_sort_default() {             // STAIR_TEXT_SORT=0|1 overrides the default at library load (A/B runs)
+    const char* e = getenv("STAIR_TEXT_SORT");
+    return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 1;
+}
+int g_text_sort = text_sort_default();         // 1 = inference text recurrence over length-sorted questions (bit-identical outputs; run_encoders)
 int g_dep_sched = 1;         // 1 = dependency-driven module scheduling when the batch carries group_deps
 int g_lanes = 8;             // round 1 (wave scheduling), B = 4096 RX: 2 / 4 / 6 / 8 lanes = 1.64 / 1.65 / 1.54 / 1.55 ms per forward; round 2
                              // (dependency scheduling): 4 / 6 / 8 lanes = 1.365 / 1.36 / 1.34 ms vs 1.41-1.43 ms wave by wave (profiles/r2_dep_sched_ab.txt)
@@ -43,7 +49,18 @@ extern "C" int stair_debug_timeline_read(float* t0, float* t1, int* lane, int* o
     }
     return n;
 }
+// ms from the start of the last forward (with stair_debug_timeline(1)) to: [0] = 0, [1] video projection done, [2] text projection done,
+// [3] recurrence done, [4] grouping joined, [5] module phase done, [6] decoder done (synchronises; a mark the call did not pass is stale)
+extern "C" int stair_debug_phase_marks(float* ms, int cap) {
+    PhaseMarks& pm = phase_marks();
+    if (!pm.ok) return 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return STAIR_ERR_CUDA;
+    const int n = cap < 7 ? cap : 7;
+    for (int i = 0; i < n; ++i) if (cudaEventElapsedTime(&ms[i], pm.ev[0], pm.ev[i]) != cudaSuccess) ms[i] = -1.0f;
+    return n;
+}
 extern "C" int stair_set_fuse_sum(int on) { g_fuse_sum = on ? 1 : 0; return STAIR_OK; }
+extern "C" int stair_set_text_sort(int on) { g_text_sort = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_dep_sched(int on) { g_dep_sched = on ? 1 : 0; return STAIR_OK; }
 extern "C" int stair_set_lanes(int lanes) { g_lanes = lanes < 1 ? 1 : (lanes > LANES ? LANES : lanes); return STAIR_OK; }
 extern "C" int stair_version(void) { return STAIR_ABI_VERSION; }
@@ -103,6 +120,7 @@ extern "C" int stair_nmn_forward(const StairModel* model, const StairBatch* batc
     // while the input projections execute, and is joined before the first module group
     const bool enc = (phases & (STAIR_FWD_ENCODE_VIDEO | STAIR_FWD_ENCODE_TEXT)) != 0;
     LaneStreams* ls = ((phases & STAIR_FWD_GROUP) && enc && g_lanes > 1) ? lane_streams() : nullptr;
+    phase_mark(c.st, 0);
     if (phases & STAIR_FWD_GROUP) {
         if (ls) {
             if (cudaEventRecord(ls->fork, c.st) != cudaSuccess || cudaStreamWaitEvent(ls->side[0], ls->fork, 0) != cudaSuccess) return STAIR_ERR_CUDA;
@@ -113,9 +131,13 @@ extern "C" int stair_nmn_forward(const StairModel* model, const StairBatch* batc
         }
     }
     if (enc) STAIR_TRY(run_encoders(c, phases));
+    phase_mark(c.st, 3);
     if (ls && cudaStreamWaitEvent(c.st, ls->join[0], 0) != cudaSuccess) return STAIR_ERR_CUDA;
+    phase_mark(c.st, 4);
     if (phases & STAIR_FWD_MODULES) STAIR_TRY(run_modules(c));
+    phase_mark(c.st, 5);
     if (phases & STAIR_FWD_DECODE) STAIR_TRY(run_decoder(c));
+    phase_mark(c.st, 6);
     t_last_launches = g_launch_count - before;
     return STAIR_OK;
 }

@@ -89,7 +89,11 @@ struct LstmHist { float* gates[2]; float* c[2]; bf16* hs[2]; long long hs_dir[2]
 int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh_v_f, const void* whh_v_r,
                       const void* xproj_t, void* tokfeat, void* qfeat, const int* q_off, int L_max, const void* whh_t_f,
                       const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st,
-                      const LstmHist* hist = nullptr);
+                      const LstmHist* hist = nullptr, const int* text_order = nullptr, const int* text_soff = nullptr);
+// length-sorted text schedule of the inference recurrence: order [B] = question ids in descending length, soff [B+1] = token offsets in that
+// order, tok_src [n_tok] = source token row of every sorted row (the staging gather of the text projection's A operand)
+bool text_sort_ok(int L_max);
+int launch_text_sort(const int* q_off, int B, int L_max, int* order, int* soff, int* tok_src, cudaStream_t st);
 
 // weight-stationary cluster recurrence of ONE encoder (lstm_ws.cu; bf16 path, h = 256): W_hh resident in the shared memory of a 4-CTA
 // cluster, h exchanged through `hx` (>= lstm_ws_hx_bytes(B) bytes).  q_off == nullptr: video (T = steps for every question); else text.

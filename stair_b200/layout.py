@@ -304,7 +304,7 @@ class NMNBatch:
         B, n = self.B, self.n_nodes
         o, out = 0, {}
         for name, size in (('q_off', B + 1), ('node_gid', n), ('node_q', n), ('node_arg', 3 * n), ('node_span', 2 * n),
-                           ('root_node', B)):
+                           ('root_node', B), ('q_order', B), ('q_soff', B + 1), ('tok_src', self.n_tok)):
             out[name] = (o, size)
             o += (size + 3) // 4 * 4
         out['_total'] = (0, o)
@@ -476,8 +476,10 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
     sl = b._slices()
     itab = torch.empty(sl['_total'][1], dtype=torch.int32, pin_memory=pin_memory)
     it = itab.numpy()
+    q_order, q_soff, tok_src = length_sorted_schedule(q_off)
     for name, arr in (('q_off', q_off), ('node_gid', gid), ('node_q', node_q), ('node_arg', node_arg.reshape(-1)),
-                      ('node_span', node_span.reshape(-1)), ('root_node', root)):
+                      ('node_span', node_span.reshape(-1)), ('root_node', root), ('q_order', q_order), ('q_soff', q_soff),
+                      ('tok_src', tok_src)):
         o, size = sl[name]
         it[o:o + size] = arr
     b.itab_host = itab
@@ -485,6 +487,22 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
     if all('answer' in e for e in examples):
         b.answer = torch.tensor([int(e['answer']) for e in examples], dtype=torch.int64)
     return b
+
+
+def length_sorted_schedule(q_off):
+    """Schedule of the inference text recurrence (StairBatch.q_order / q_soff / tok_src): the questions in descending length (stable), the
+    token offsets in that order and the batch-order token row of every sorted row.  A 64-question block of the recurrence then stops at
+    its own longest question instead of the batch's (csrc/lstm_fused.cu); the outputs keep the batch's order."""
+    q_off = np.asarray(q_off, np.int64)
+    lens = np.diff(q_off)
+    order = np.argsort(-lens, kind='stable')
+    soff = np.zeros(len(q_off), np.int64)
+    np.cumsum(lens[order], out=soff[1:])
+    n_tok = int(q_off[-1])
+    # row r of the sorted layout belongs to sorted position p = searchsorted(soff, r): its source row is q_off[order[p]] + (r - soff[p])
+    shift = np.repeat(q_off[:-1][order] - soff[:-1], lens[order])
+    tok_src = np.arange(n_tok, dtype=np.int64) + shift
+    return order.astype(np.int32), soff.astype(np.int32), tok_src.astype(np.int32)
 
 
 def _group_deps(gid, node_arg, n_groups):

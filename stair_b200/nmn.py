@@ -116,8 +116,10 @@ class VideoNMN(nn.Module):
         sb.B, sb.T, sb.n_tok, sb.L_max, sb.n_nodes, sb.n_groups = B, T, batch.n_tok, batch.L_max, n, ng
         sb.video_dtype, sb.question_dtype = L.dtype_code(batch.video_dev.dtype), L.dtype_code(batch.question_dev.dtype)
         sb.video, sb.question = batch.video_dev.data_ptr(), batch.question_dev.data_ptr()
-        for name in ('q_off', 'node_gid', 'node_q', 'node_arg', 'node_span', 'root_node'):
+        for name in ('q_off', 'node_gid', 'node_q', 'node_arg', 'node_span', 'root_node', 'q_order', 'q_soff', 'tok_src'):
             setattr(sb, name, batch.tab_ptr(name))
+        if getattr(self, 'device_text_sort', False):             # leave the length-sorted text schedule to the library's device sort
+            sb.q_order = sb.q_soff = sb.tok_src = None
         sb.groups = ctypes.cast(groups, ctypes.POINTER(L.StairGroup))
         sb.group_tab = gtab.data_ptr()
         sb.group_deps = batch.group_deps.ctypes.data if getattr(batch, 'group_deps', None) is not None and ng else None

@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), 'missing export %s' % n
-    assert lib.stair_version() == 8
+    assert lib.stair_version() == 9
 
 
 def test_host_only_entry_points():

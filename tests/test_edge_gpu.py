@@ -196,7 +196,7 @@ def test_module_scheduling_modes_agree_and_the_timeline_hook_reports_every_group
 def test_optional_kernel_forms_do_not_change_the_forward(T, V):
     """Comparison switches of the C ABI (include/stair_b200.h): the frame sum of Filter inside the GEMM epilogue (stair_set_fuse_sum), the
     gathered-A form of the CTA-pair GEMM (stair_set_gemm_pair_gather), the two-CTAs-per-SM GEMM (stair_set_gemm_small) and the
-    weight-stationary recurrence (stair_set_lstm_ws) compute the same values as the product configuration: logits bit-identical."""
+    weight-stationary recurrence (stair_set_lstm_ws), the text recurrence in batch order instead of length-sorted (stair_set_text_sort) compute the same values as the product configuration: logits bit-identical."""
     from stair_b200 import _lib as L
     lib = L.lib()
     cfg = syn.model_config(T=T, V=V, hidden=512, object_types=16)
@@ -206,7 +206,7 @@ def test_optional_kernel_forms_do_not_change_the_forward(T, V):
     batch = collate(qs, video_dtype=torch.bfloat16).to('cuda')
     ref = model.forward_batch(batch).logits.clone()
     switches = (('stair_set_fuse_sum', 1, 0), ('stair_set_gemm_pair_gather', 0, 1), ('stair_set_gemm_small', 1, 0), ('stair_set_lstm_ws', 1, 0),
-                ('stair_set_gemm_pair', 2, 1), ('stair_set_gemm_pair', 0, 1))
+                ('stair_set_gemm_pair', 2, 1), ('stair_set_gemm_pair', 0, 1), ('stair_set_text_sort', 0, 1))
     for name, on, default in switches:
         try:
             getattr(lib, name)(on)
@@ -216,6 +216,49 @@ def test_optional_kernel_forms_do_not_change_the_forward(T, V):
             getattr(lib, name)(default)
         assert lib.stair_gemm_error_flag() == 0
         assert torch.equal(out, ref), (name, on, float((out - ref).abs().max()))
+
+
+_LAUNCHES = {}
+
+
+def outs_launches(model, on, device_sort, outs):
+    """The device sort adds exactly two launches to the forward; the other two modes launch the same kernels."""
+    _LAUNCHES.setdefault(id(model), model.last_launches)
+    return _LAUNCHES[id(model)] + (2 if (on and device_sort) else 0)
+
+
+@pytest.mark.parametrize('B', [1, 63, 333, 1100])
+def test_length_sorted_text_recurrence_is_bit_identical_to_batch_order(B):
+    """The inference text recurrence runs over length-sorted questions (stair_set_text_sort, default on; csrc/lstm_fused.cu
+    text_sort_kernel; schedule from collate or from the library's device sort): token_feature, question_feature and the logits equal the batch-order run bit for bit — lengths 1 .. 40 incl. many
+    equal ones, batches that do not fill a 64-question block, and the text-only phase (encode_question)."""
+    from stair_b200 import _lib as L
+    lib = L.lib()
+    T, V = 8, 128
+    cfg = syn.model_config(T=T, V=V, hidden=256, object_types=16)
+    torch.manual_seed(B)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().eval()
+    rng = np.random.default_rng(B)
+    qs = syn.make_questions(B, T, V, seed=B, templates=list(syn.ALL_TEMPLATES), object_types=16)
+    qs = [_with_length(d, int(rng.integers(1, 41)), rng) if i % 3 else d for i, d in enumerate(qs)]
+    batch = collate(qs, video_dtype=torch.bfloat16).to('cuda')
+    outs = []
+    for on, device_sort in ((1, False), (0, False), (1, True)):      # collate's schedule | batch order | the library's device counting sort
+        try:
+            lib.stair_set_text_sort(on)
+            model.device_text_sort = device_sort
+            st = model.forward_batch(batch)
+            torch.cuda.synchronize()
+            model.check_status(st)
+            outs.append((st.logits.clone(), st.tokfeat[:batch.n_tok * 256].clone(), st.qfeat[:B * 256].clone()))
+            assert model.last_launches == outs_launches(model, on, device_sort, outs)
+        finally:
+            lib.stair_set_text_sort(1)
+            model.device_text_sort = False
+    for a, b in ((outs[0], outs[1]), (outs[0], outs[2])):
+        for x, y, name in zip(a, b, ('logits', 'token_feature', 'question_feature')):
+            assert torch.equal(x, y), (name, float((x.float() - y.float()).abs().max()))
+    assert float(outs[0][2].float().abs().max()) > 0
 
 
 @pytest.mark.parametrize('T', [16, 32, 128])

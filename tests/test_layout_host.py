@@ -193,3 +193,24 @@ def test_native_collate_staging_is_bit_identical_to_torch():
     assert torch.equal(b.question, torch.cat([q['question'] for q in qs]).to(torch.bfloat16))
     b32 = LY.collate(qs)
     assert torch.equal(b32.video, torch.stack([q['video_features'] for q in qs])) and b32.video.dtype == torch.float32
+
+
+def test_length_sorted_text_schedule():
+    """layout.length_sorted_schedule (StairBatch.q_order / q_soff / tok_src): a permutation in descending length, offsets in that order and
+    the batch-order row of every sorted token row — and collate stores it in the packed integer table."""
+    from stair_b200.layout import length_sorted_schedule
+    rng = np.random.default_rng(3)
+    for B in (1, 2, 65, 700):
+        lens = rng.integers(1, 41, size=B)
+        q_off = np.concatenate([[0], np.cumsum(lens)])
+        order, soff, tok_src = length_sorted_schedule(q_off)
+        assert sorted(order.tolist()) == list(range(B))
+        assert (np.diff(lens[order]) <= 0).all()
+        assert soff[0] == 0 and soff[-1] == q_off[-1] and (np.diff(soff) == lens[order]).all()
+        for p in range(B):
+            q = order[p]
+            assert (tok_src[soff[p]:soff[p + 1]] == np.arange(q_off[q], q_off[q + 1])).all()
+    qs = syn.make_questions(23, 8, 32, seed=4)
+    b = LY.collate(qs)
+    order, soff, tok_src = length_sorted_schedule(b.host_tab('q_off').numpy())
+    assert (b.host_tab('q_order').numpy() == order).all() and (b.host_tab('q_soff').numpy() == soff).all() and (b.host_tab('tok_src').numpy() == tok_src).all()
