@@ -346,6 +346,15 @@ bool fused_history(const Ctx& c) {
     return lstm_fused_ok(c.m.precision, c.h) && g_lstm_impl == 0 && c.W(STAIR_W_VENC_WHHI_F) && c.W(STAIR_W_TENC_WHHI_F);
 }
 
+// true when the training forward, its history and the BPTT run the text encoder over length-sorted questions (the schedule of
+// StairBatch.q_order / q_soff / tok_src; fused forward + persistent fused BPTT only — both read the history by grid row).  The forward and
+// the backward of a step must see the same switches (stair_set_text_sort / stair_set_bptt_impl / stair_set_lstm_impl).
+bool train_text_sorted(const Ctx& c) {
+    const StairModel& m = c.m;
+    return g_text_sort && c.b.q_order && c.b.q_soff && c.b.tok_src && fused_history(c) && !lstm_ws_ok(m.precision, c.h, c.b.B) && g_bptt_impl == 0 &&
+           lstm_bptt_fused_ok(m.precision, c.h) && m.wt[STAIR_W_VENC_WHH_F] && m.wt[STAIR_W_VENC_WHH_R] && m.wt[STAIR_W_TENC_WHH_F] && m.wt[STAIR_W_TENC_WHH_R];
+}
+
 int run_encoders_train(Ctx& c, const StairTrain& tr) {
     const StairModel& m = c.m; const StairBatch& bt = c.b;
     const int B = bt.B, H = c.H, h = c.h;
@@ -355,6 +364,7 @@ int run_encoders_train(Ctx& c, const StairTrain& tr) {
     float* g = c.at<float>(c.plan.g);
     // bf16 path: both recurrences run in the persistent fused kernel (csrc/lstm_fused.cu), which writes the BPTT history itself
     const bool fused = fused_history(c);
+    const bool tsort = train_text_sorted(c);
     LstmHist hist;
     for (int e = 0; e < 2; ++e) {
         const EncIO io = enc_io(c, e);
@@ -363,7 +373,8 @@ int run_encoders_train(Ctx& c, const StairTrain& tr) {
         GemmArgs a;
         if (direct) { a.A = io.xin; a.lda = io.Kin; a.a_plane_rows = 0; }
         else {
-            STAIR_TRY(launch_stage_rows(io.xin_dt, io.xin, io.Kin, nullptr, 1, 1, in, io.Kin_ld, io.rows, c.np, io.rows, io.Kin, c.st));
+            STAIR_TRY(launch_stage_rows(io.xin_dt, io.xin, io.Kin, (e == 1 && tsort) ? bt.tok_src : nullptr, 1, 1, in, io.Kin_ld, io.rows, c.np, io.rows,
+                                        io.Kin, c.st));
             a.A = in; a.lda = io.Kin_ld; a.a_plane_rows = static_cast<int>(io.rows);
         }
         a.nplanes = c.np; a.W = c.W(io.wih); a.ldw = io.Kin_ld; a.w_plane_rows = 4 * H; a.bias = c.Wf(io.bias); a.C = io.xproj; a.ldc = 4 * H;
@@ -412,7 +423,8 @@ int run_encoders_train(Ctx& c, const StairTrain& tr) {
     if (fused)
         return launch_lstm_fused(c.at<void>(c.plan.xv), c.buf.vid, c.T, c.W(STAIR_W_VENC_WHHI_F), c.W(STAIR_W_VENC_WHHI_R),
                                  c.at<void>(c.plan.xq), c.buf.tokfeat, c.buf.qfeat, bt.q_off, bt.L_max, c.W(STAIR_W_TENC_WHHI_F),
-                                 c.W(STAIR_W_TENC_WHHI_R), c.at<float>(c.plan.c), B, h, 1, 1, err_flag_ptr(), c.st, &hist);
+                                 c.W(STAIR_W_TENC_WHHI_R), c.at<float>(c.plan.c), B, h, 1, 1, err_flag_ptr(), c.st, &hist, tsort ? bt.q_order : nullptr,
+                                 tsort ? bt.q_soff : nullptr);
     return STAIR_OK;
 }
 
@@ -497,7 +509,8 @@ int encoder_bwd(BCtx& b, int e, int dir_lane, bf16* dxb_done = nullptr) {
                 const bf16* xin_p = reinterpret_cast<const bf16*>(io.xin);
                 if (!direct) {
                     bf16* in = b.ws.take<bf16>(io.rows * io.Kin_ld);
-                    RUN(launch_stage_rows(io.xin_dt, io.xin, io.Kin, nullptr, 1, 1, in, io.Kin_ld, io.rows, 1, io.rows, io.Kin, c.st));
+                    const int* src = (e == 1 && dxb_done && train_text_sorted(c)) ? bt.tok_src : nullptr;      // the gate gradients' row order
+                    RUN(launch_stage_rows(io.xin_dt, io.xin, io.Kin, src, 1, 1, in, io.Kin_ld, io.rows, 1, io.rows, io.Kin, c.st));
                     xin_p = in;
                 }
                 GemmArgs a;
@@ -564,7 +577,8 @@ int encoders_bwd(BCtx& b) {
             a.whhT[2 * e] = m.wt[io.whh_f]; a.whhT[2 * e + 1] = m.wt[io.whh_r];
         }
         a.dqfeat = b.tr.dqfeat;
-        RUN(launch_lstm_bptt_fused(a, B, h, c.T, c.b.L_max, c.b.q_off, err_flag_ptr(), c.st));
+        const bool tsort = train_text_sorted(c);
+        RUN(launch_lstm_bptt_fused(a, B, h, c.T, c.b.L_max, c.b.q_off, err_flag_ptr(), c.st, tsort ? c.b.q_order : nullptr, tsort ? c.b.q_soff : nullptr));
     }
     const long long mark = b.ws.off;
     // video (e = 0): side stream 2 (+ side stream 3 for its reverse-direction GEMMs); workspace [mark, video peak)

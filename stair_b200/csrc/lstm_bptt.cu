@@ -43,6 +43,8 @@ struct BpttSeq {
     bf16* dxb;              // [rows][8h] gate pre-activation gradients, token order
     float* dc;              // running dc scratch [2][nblk][h][64]
     const int* q_off;       // text: [B+1]; video: null
+    const int* order;       // text (optional): length-sorted schedule of the fused forward (lstm_fused.cu LstmSeq::order / soff): grid row r is
+    const int* soff;        //   question order[r]; dxb rows (and the coefficient history, by grid row) in sorted order, dout rows in batch order
     int steps, B, h;
 };
 struct BpttParams { BpttSeq seq[2]; int* err_flag; };
@@ -108,7 +110,8 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
     __syncthreads();
     if (ragged && threadIdx.x < LB_ROWS) {
         const int r = row0 + threadIdx.x;
-        if (r < sq.B) atomicMax(s_steps, __ldg(sq.q_off + r + 1) - __ldg(sq.q_off + r));
+        const int* off = sq.soff ? sq.soff : sq.q_off;
+        if (r < sq.B) atomicMax(s_steps, __ldg(off + r + 1) - __ldg(off + r));
     }
     fence_async_smem();
     tcgen05_fence_before();
@@ -174,17 +177,20 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
         // and L2 (dc): the operands of iteration k+1 are requested before iteration k is processed (two register stages), so the
         // recurrence waits on the tensor core, not on memory.
         const int row = (quarter & 1) * 32 + lane;
-        const int grow = row0 + row;
-        const bool valid = grow < sq.B;
-        int base = 0, L = sq.steps;
-        if (ragged) { base = valid ? __ldg(sq.q_off + grow) : 0; L = valid ? __ldg(sq.q_off + grow + 1) - base : 0; }
-        else base = grow * sq.steps;
+        const int pos = row0 + row;                                 // grid row; carries question order[pos] when the text is length-sorted
+        const bool valid = pos < sq.B;
+        const int grow = (valid && sq.order) ? __ldg(sq.order + pos) : pos;
+        int base = 0, xbase = 0, L = sq.steps;                      // first dout row (batch order) / first dxb row (schedule order)
+        if (ragged) {
+            base = valid ? __ldg(sq.q_off + grow) : 0; L = valid ? __ldg(sq.q_off + grow + 1) - base : 0;
+            xbase = (valid && sq.soff) ? __ldg(sq.soff + pos) : base;
+        } else xbase = base = grow * sq.steps;
         if (!valid) L = 0;
         constexpr uint32_t DUP = 64u * 128u;                       // byte offset of the copy of a row in the dG operand (row + 64)
         const int nblk = (sq.B + LB_ROWS - 1) / LB_ROWS;
         float* dcblk = sq.dc + (static_cast<long long>(dir) * nblk + blockIdx.x) * (static_cast<long long>(h) * LB_ROWS) + row * 4;   // [unit/4][row][4]
         const long long RB = (sq.B + 127) / 128 * 4;
-        const long long hist_rb = (static_cast<long long>(dir) * RB + (grow >> 5)) * (h >> 3);
+        const long long hist_rb = (static_cast<long long>(dir) * RB + (pos >> 5)) * (h >> 3);
         const long long hist_step = 2 * RB * (h >> 3);
         const uint32_t sA0 = smem_u32(sA);
         const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
@@ -237,7 +243,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
                     *reinterpret_cast<float4*>(dcblk + (u0 / 4) * (LB_ROWS * 4)) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
                     *reinterpret_cast<float4*>(dcblk + (u0 / 4 + 1) * (LB_ROWS * 4)) = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
                 }
-                bf16* xrow = sq.dxb + (static_cast<long long>(base) + (dir == 0 ? s : L - 1 - s)) * 8 * h + dir * 4 * h + u0;
+                bf16* xrow = sq.dxb + (static_cast<long long>(xbase) + (dir == 0 ? s : L - 1 - s)) * 8 * h + dir * 4 * h + u0;
                 // gate by gate: multiply, pack, store (token-order row + shared-memory operand) — short live ranges
                 auto emit = [&](int g, const float (&x)[8], const uint4& co) {
                     uint4 v;
@@ -318,21 +324,29 @@ __global__ void add_qfeat_grad_kernel(float* __restrict__ dtok, const float* __r
 bool lstm_bptt_fused_ok(int precision, int h) { return precision == STAIR_BF16 && h >= 64 && h <= 256 && (h % 64) == 0; }
 
 // index 0 = video encoder (T steps), 1 = text encoder (ragged, L_max steps).  whhT_* = transposed W_hh copies [h][4h] (StairModel.wt).
-int launch_lstm_bptt_fused(const LstmBptt& a, int B, int h, int T, int L_max, const int* q_off, int* err_flag, cudaStream_t st) {
+int launch_lstm_bptt_fused(const LstmBptt& a, int B, int h, int T, int L_max, const int* q_off, int* err_flag, cudaStream_t st,
+                           const int* text_order, const int* text_soff) {
     if (B <= 0) return STAIR_OK;
+    if (!text_order || !text_soff) text_order = text_soff = nullptr;
     BpttParams p;
     p.err_flag = err_flag;
-    for (int e = 0; e < 2; ++e) {
-        BpttSeq& s = p.seq[e];
+    // length-sorted text: the text blocks come first in the grid (longest first), the short video blocks fill in behind them (lstm_fused.cu)
+    const int first = text_order ? 1 : 0;
+    const void* whhT[4];
+    for (int i = 0; i < 2; ++i) {
+        const int e = i == 0 ? first : 1 - first;
+        BpttSeq& s = p.seq[i];
         s.coef_h = reinterpret_cast<const bf16*>(a.gates[e]); s.dout = a.dout[e]; s.dxb = a.dxb[e];
         s.dc = a.dc[e]; s.q_off = e == 1 ? q_off : nullptr; s.steps = e == 0 ? T : L_max; s.B = B; s.h = h;
+        s.order = e == 1 ? text_order : nullptr; s.soff = e == 1 ? text_soff : nullptr;
+        whhT[2 * i] = a.whhT[2 * e]; whhT[2 * i + 1] = a.whhT[2 * e + 1];
     }
     if (a.dqfeat) {
         add_qfeat_grad_kernel<<<static_cast<int>((static_cast<long long>(B) * 2 * h + 255) / 256), 256, 0, st>>>(a.dout[1], a.dqfeat, q_off, B, h);
         STAIR_CHECK_LAUNCH();
     }
     CUtensorMap tm[4];
-    for (int i = 0; i < 4; ++i) STAIR_TRY(make_tmap_bf16_2d(&tm[i], a.whhT[i], 4ULL * h, h, 4ULL * h, 64, 256));
+    for (int i = 0; i < 4; ++i) STAIR_TRY(make_tmap_bf16_2d(&tm[i], whhT[i], 4ULL * h, h, 4ULL * h, 64, 256));
     const int smem = 2 * LB_A_BYTES + LB_STAGES * LB_W_STAGE_BYTES + 256 + 1024;
     static int configured = 0;
     if (configured < smem) {

@@ -245,7 +245,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
         const int nblk = (sq.B + VROWS - 1) / VROWS;
         float* cblk = sq.c + (static_cast<long long>(dir) * nblk + blockIdx.x) * (static_cast<long long>(h) * VROWS) + row * 4;
         const long long RB = (sq.B + 127) / 128 * 4;                                      // 32-row blocks per (step, direction)
-        const long long hist_rb = (static_cast<long long>(dir) * RB + (grow >> 5)) * (h >> 3);      // + step * 2 * RB * (h/8); then + unit/8
+        const long long hist_rb = (static_cast<long long>(dir) * RB + (pos >> 5)) * (h >> 3);       // + step * 2 * RB * (h/8); then + unit/8 (by grid row)
         const long long hist_step = 2 * RB * (h >> 3);
         auto c_ptr = [&](int, int unit, int q) -> float* { return cblk + (unit / 4 + q) * (VROWS * 4); };     // q-th float4 of 8 units
         const uint32_t sH0 = smem_u32(sH);
@@ -423,8 +423,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                         o0.x = hp[0]; o0.y = hp[1]; o0.z = hp[2]; o0.w = hp[3];
                         *reinterpret_cast<uint4*>(orow + u0) = o0;
                         // h_s is the *previous* state of the next step's token: stored at that token's row ([rows][2h], zero where a direction
-                        // starts), so dW_hh = dGates^T . h_prev is one contraction over token rows with both operands in token order
-                        if (HIST && s + 1 < L) *reinterpret_cast<uint4*>(sq.hs_h + (tokrow + (dir == 0 ? 1 : -1)) * 2 * h + dir * h + u0) = o0;
+                        // starts), so dW_hh = dGates^T . h_prev is one contraction over token rows with both operands in the same (schedule) order
+                        if (HIST && s + 1 < L) *reinterpret_cast<uint4*>(sq.hs_h + (static_cast<long long>(xbase) + tstep + (dir == 0 ? 1 : -1)) * 2 * h + dir * h + u0) = o0;
                         if (last) *reinterpret_cast<uint4*>(sq.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0) = o0;
                         st_shared_v4(h_dst + a0, o0.x, o0.y, o0.z, o0.w);
                         if (DUP) st_shared_v4(h_dst + a0 + DUP, o0.x, o0.y, o0.z, o0.w);
@@ -509,7 +509,7 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
                       const void* whh_t_r, float* c_scratch, int B, int h, int run_video, int run_text, int* err_flag, cudaStream_t st,
                       const LstmHist* hist, const int* text_order, const int* text_soff) {
     if (B <= 0 || (!run_video && !run_text)) return STAIR_OK;
-    if (hist || !text_order || !text_soff) text_order = text_soff = nullptr;      // the BPTT history is laid out in batch order
+    if (!text_order || !text_soff) text_order = text_soff = nullptr;      // (training: the history, hs_h and the BPTT follow the same schedule)
     LstmFusedParams p;
     p.err_flag = err_flag;
     p.dbg = g_lstm_dbg;

@@ -111,7 +111,9 @@ struct LstmBptt {
     const float* gates[2]; const float* c[2]; float* dout[2]; const float* dqfeat; bf16* dxb[2]; float* dc[2]; const void* whhT[4];
 };
 bool lstm_bptt_fused_ok(int precision, int h);
-int launch_lstm_bptt_fused(const LstmBptt& a, int B, int h, int T, int L_max, const int* q_off, int* err_flag, cudaStream_t st);
+// text_order / text_soff: the length-sorted schedule the fused forward ran with (null = batch order): dxb[1] rows are then in schedule order
+int launch_lstm_bptt_fused(const LstmBptt& a, int B, int h, int T, int L_max, const int* q_off, int* err_flag, cudaStream_t st,
+                           const int* text_order = nullptr, const int* text_soff = nullptr);
 
 // ---- layout grouping (layout_group.cu) ----------------------------------------------------------------------------
 int launch_group_layouts(const StairBatch& b, int32_t* itab, int32_t* status, cudaStream_t st);

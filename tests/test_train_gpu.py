@@ -493,6 +493,39 @@ def test_persistent_bptt_matches_stepwise_bptt(hidden, n_q):
             assert l2 <= 5e-3, '%s: relative L2 %g' % (k, l2)
 
 
+@pytest.mark.parametrize('hidden,n_q', [(128, 150), (512, 333)])
+def test_length_sorted_training_recurrence_matches_batch_order(hidden, n_q):
+    """stair_set_text_sort(1) (default): the training forward with history, the history itself and the persistent BPTT run the text
+    encoder over length-sorted questions (StairBatch.q_order / q_soff / tok_src; csrc/lstm_fused.cu, lstm_bptt.cu, executor_bwd.cu
+    train_text_sorted) == batch order: same loss (the forward is bit-identical), gradients equal up to the fp32 summation order of the
+    weight-gradient contractions over token rows."""
+    from stair_b200 import _lib as L
+    cfg = syn.model_config(T=8, V=256, hidden=hidden, object_types=16)
+    torch.manual_seed(23)
+    model = VideoNMN(cfg, pretrain_modules=syn.PRETRAIN_MODULES, precision='bf16').cuda().train()
+    qs = syn.make_questions(n_q, 8, 256, seed=37, templates=list(syn.ALL_TEMPLATES), with_gold=True, object_types=16)
+    res = {}
+    try:
+        for on in (0, 1):
+            L.lib().stair_set_text_sort(on)
+            for prm in model.parameters():
+                prm.grad = None
+            out = NMNTrainStep(model)(qs)
+            torch.cuda.synchronize()
+            model.check_status(out['state'])
+            res[on] = (float(out['loss']), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    finally:
+        L.lib().stair_set_text_sort(1)
+    (l0, g0), (l1, g1) = res[0], res[1]
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)                    # (the loss rows are summed with atomics)
+    assert g0.keys() == g1.keys()
+    for k in g0:
+        l2 = float((g0[k] - g1[k]).norm()) / max(float(g0[k].norm()), 1e-30)
+        # run-to-run noise of the atomically accumulated gradients ~1e-6; the encoder weight gradients sum ~10^4 bf16 x bf16 products per
+        # element over token rows in a different order (heavy cancellation): measured 8e-5
+        assert l2 <= (5e-4 if 'encoder' in k else 2e-5), '%s: relative L2 %g' % (k, l2)
+
+
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_shared_memory_contrastive_loss_matches_register_kernel(precision):
     """stair_set_loss_con_impl(0) (product for windows of <= 64 classes): class matrix staged in shared memory, lane = class for the
