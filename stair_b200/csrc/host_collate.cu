@@ -5,6 +5,9 @@
 #include "stair_common.cuh"
 
 #include <atomic>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -20,13 +23,57 @@ inline uint16_t f32_to_bf16(uint32_t u) {
     return static_cast<uint16_t>((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
 }
 
+// Vector forms of the same conversion (same bits as f32_to_bf16 for every input), chosen at run time: the library is built on one machine
+// and runs on another.  The scalar loop converts ~0.3 G elements/s per thread (the NaN branch keeps it scalar); these are memory-bound.
+#if defined(__x86_64__) && defined(__GNUC__)
+#define STAIR_X86_DISPATCH 1
+__attribute__((target("avx512f,avx512bw"))) void f32_to_bf16_avx512(const uint32_t* s, uint16_t* d, long long n) {
+    const __m512i absmask = _mm512_set1_epi32(0x7fffffff), inf = _mm512_set1_epi32(0x7f800000), bias = _mm512_set1_epi32(0x7fff),
+                  one = _mm512_set1_epi32(1), qnan = _mm512_set1_epi32(0x7FC0);
+    long long i = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m512i v = _mm512_loadu_si512(s + i);
+        const __mmask16 nan = _mm512_cmpgt_epu32_mask(_mm512_and_si512(v, absmask), inf);
+        __m512i r = _mm512_srli_epi32(_mm512_add_epi32(_mm512_add_epi32(v, bias), _mm512_and_si512(_mm512_srli_epi32(v, 16), one)), 16);
+        r = _mm512_mask_mov_epi32(r, nan, qnan);
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(d + i), _mm512_cvtepi32_epi16(r));
+    }
+    for (; i < n; ++i) d[i] = f32_to_bf16(s[i]);
+}
+__attribute__((target("avx2"))) void f32_to_bf16_avx2(const uint32_t* s, uint16_t* d, long long n) {
+    const __m256i absmask = _mm256_set1_epi32(0x7fffffff), inf = _mm256_set1_epi32(0x7f800000), bias = _mm256_set1_epi32(0x7fff),
+                  one = _mm256_set1_epi32(1), qnan = _mm256_set1_epi32(0x7FC0);
+    long long i = 0;
+    for (; i + 16 <= n; i += 16) {
+        __m256i r[2];
+        for (int k = 0; k < 2; ++k) {
+            const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 8 * k));
+            const __m256i nan = _mm256_cmpgt_epi32(_mm256_and_si256(v, absmask), inf);      // both sides non-negative: the signed compare is exact
+            const __m256i x = _mm256_srli_epi32(_mm256_add_epi32(_mm256_add_epi32(v, bias), _mm256_and_si256(_mm256_srli_epi32(v, 16), one)), 16);
+            r[k] = _mm256_blendv_epi8(x, qnan, nan);
+        }
+        // packus works per 128-bit lane: [r0.lo r1.lo | r0.hi r1.hi] -> permute the 64-bit quarters back into element order
+        const __m256i pk = _mm256_permute4x64_epi64(_mm256_packus_epi32(r[0], r[1]), 0xD8);
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(d + i), pk);
+    }
+    for (; i < n; ++i) d[i] = f32_to_bf16(s[i]);
+}
+#endif
+
+void f32_to_bf16_n(const uint32_t* s, uint16_t* d, long long n) {
+#ifdef STAIR_X86_DISPATCH
+    static const int level = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+    if (level == 2) return f32_to_bf16_avx512(s, d, n);
+    if (level == 1) return f32_to_bf16_avx2(s, d, n);
+#endif
+    for (long long i = 0; i < n; ++i) d[i] = f32_to_bf16(s[i]);
+}
+
 void convert_block(const void* src, int src_dtype, void* dst, int dst_dtype, long long n) {
     if (src_dtype == dst_dtype) {
         std::memcpy(dst, src, static_cast<size_t>(n) * (src_dtype == STAIR_F32 ? 4 : 2));
     } else if (src_dtype == STAIR_F32) {                     // fp32 -> bf16
-        const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
-        uint16_t* d = reinterpret_cast<uint16_t*>(dst);
-        for (long long i = 0; i < n; ++i) d[i] = f32_to_bf16(s[i]);
+        f32_to_bf16_n(reinterpret_cast<const uint32_t*>(src), reinterpret_cast<uint16_t*>(dst), n);
     } else {                                                 // bf16 -> fp32
         const uint16_t* s = reinterpret_cast<const uint16_t*>(src);
         uint32_t* d = reinterpret_cast<uint32_t*>(dst);
