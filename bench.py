@@ -636,8 +636,8 @@ def main():
     step_tf = step_flops / (ms / args.steps * 1e-3) / 1e12
     roofline['whole_step'] = {'flops': step_flops, 'mflop_per_question': step_flops / B / 1e6, 'achieved': step_tf, 'unit': 'TFLOP/s',
                               'frac_of_sustained_peak': step_tf / pk['tf_sustained'], 'frac_of_burst_peak': step_tf / pk['tf_burst'],
-                              'what': 'the step is a chain of 81 launches; the recurrence (latency-bound, 0.40 ms) and the module phase '
-                                      '(0.45 ms of small GEMMs) are not tensor-bound, see DESIGN.md section 4'}
+                              'what': 'the step is a chain of 81 launches; the recurrence (latency-bound, 0.33 ms) and the module phase '
+                                      '(0.44 ms of small GEMMs) are not tensor-bound, see DESIGN.md section 4'}
 
     # ---- CPU legs: baseline timing (rank 0, N = 1) and the parity check of this rank's answers against the oracle -------------------
     cpu = None
