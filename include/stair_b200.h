@@ -8,7 +8,8 @@
  * Conventions: every function returns 0 (STAIR_OK) or a negative STAIR_ERR_* code; nothing throws, exits,
  * allocates device memory or synchronises — the caller (PyTorch's caching allocator) owns every buffer and all
  * work is enqueued on the `stream` argument (a cudaStream_t passed as void*).  Pointers are device pointers
- * unless marked HOST, and must be 16-byte aligned.  sm_100a only; there is no CPU or library fallback.
+ * unless marked HOST, and must be 16-byte aligned (32-byte: the StairBuffers arenas vid / tokfeat / qfeat, the workspace and
+ * StairTrain.saved, which the recurrence kernels access with 256-bit loads / stores).  sm_100a only; there is no CPU or library fallback.
  *
  * What the library itself owns (and nothing else): per calling thread, 7 non-blocking side streams + 104 events (one fork, one join per
  * lane, one completion event per module group) on which independent module groups run concurrently in dependency order (forked from and

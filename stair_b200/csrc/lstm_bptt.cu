@@ -331,7 +331,7 @@ int launch_lstm_bptt_fused(const LstmBptt& a, int B, int h, int T, int L_max, co
     BpttParams p;
     p.err_flag = err_flag;
     // length-sorted text: the text blocks come first in the grid (longest first), the short video blocks fill in behind them (lstm_fused.cu)
-    const int first = text_order ? 1 : 0;
+    const int first = (text_order && L_max > T) ? 1 : 0;          // (more frames than words: the video blocks are the long ones and stay first)
     const void* whhT[4];
     for (int i = 0; i < 2; ++i) {
         const int e = i == 0 ? first : 1 - first;

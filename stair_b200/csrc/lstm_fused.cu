@@ -76,6 +76,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr) : "memory");
 }
+// 32-byte global accesses (sm_100 LDG/STG .256): one request per gate for a thread's 16 units instead of two — every lane of the cell
+// epilogue addresses its own question's row, so each access is its own LSU wavefront, and the wavefronts are the kernel's most loaded unit
+__device__ __forceinline__ void ldg256_nc(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
@@ -252,6 +262,23 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
         const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
         const uint32_t sw = static_cast<uint32_t>(row & 7);
         int acc = 0; uint32_t acc_phase = 0;
+        constexpr bool GS_CHUNK_C = !HIST && CG == 8;                // the 16-warp comparison form loads the cell state per chunk
+        float4 cnext[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};     // cell state of the next sub-block's 8 units
+        // ROLL: the input-projection pieces of a sub-block (4 gates x 16 bytes) are requested one sub-block ahead, across chunk and step
+        // boundaries, into two alternating register sets (the sub-block loop is unrolled and SBN is even, so the alternation is static).
+        // Requested per chunk right before the wait for the tensor core — which is short, the cell epilogue being the slower side — their
+        // HBM latency was exposed: 28 % of the epilogue warps' samples sat on the first use (ncu source page, r3_lstm_sorted_ncu_summary.txt).
+        constexpr bool WIDE = SBN % 2 == 0;       // 32-byte input-projection loads / output stores for pairs of sub-blocks
+        constexpr bool ROLL = false;      // measured SLOWER (forward 1.26 -> 1.345 ms): see the comment above the per-chunk loads
+        uint4 xroll[2][4];
+        auto x_row = [&](int step) -> const bf16* {
+            return sq.xproj + (static_cast<long long>(xbase) + (dir == 0 ? step : L - 1 - step)) * 8 * h + dir * 4 * h;
+        };
+        if (ROLL && valid && L > 0) {
+            const bf16* xr = x_row(0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) xroll[0][g] = __ldg(reinterpret_cast<const uint4*>(xr + g * h + halfsel * (SBN * 8)));
+        }
         for (int s = 0; s < S; ++s) {
             const bool active = valid && s < L;
             const int tstep = dir == 0 ? s : L - 1 - s;
@@ -264,16 +291,24 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
             for (int c = 0; c < NC; ++c) {
                 // all global operands of this chunk (input projection, previous cell state) are requested before waiting for the
                 // tensor core, so their latency overlaps the MMA of this chunk instead of serialising 4x per chunk
-                uint4 xq[SBN][4];
-                float4 cnext[2];                                      // cell state of the next 8 units (L2-resident, one sub-block ahead)
+                uint4 xq[ROLL ? 1 : SBN][4];
                 if (active) {
+                    if constexpr (!ROLL && WIDE) {
 #pragma unroll
-                    for (int sb = 0; sb < SBN; ++sb) {
-                        const int u0 = c * 64 + halfsel * (SBN * 8) + sb * 8;
+                        for (int sb = 0; sb < SBN; sb += 2) {          // a pair of sub-blocks = 16 units = one 32-byte sector per gate
+                            const int u0 = c * 64 + halfsel * (SBN * 8) + sb * 8;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) xq[sb][g] = __ldg(reinterpret_cast<const uint4*>(xrow + g * h + u0));      // L1-allocating: the next sub-block reads the other half of the sector (no-allocate measured 1.6x slower)
+                            for (int g = 0; g < 4; ++g) ldg256_nc(xrow + g * h + u0, xq[sb][g], xq[sb + 1][g]);
+                        }
+                    } else if constexpr (!ROLL) {
+#pragma unroll
+                        for (int sb = 0; sb < SBN; ++sb) {
+                            const int u0 = c * 64 + halfsel * (SBN * 8) + sb * 8;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) xq[sb][g] = __ldg(reinterpret_cast<const uint4*>(xrow + g * h + u0));      // L1-allocating: the next sub-block reads the other half of the sector (no-allocate measured 1.6x slower)
+                        }
                     }
-                    if (s > 0) {
+                    if (GS_CHUNK_C && s > 0) {
 #pragma unroll
                         for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(c_ptr(s - 1, c * 64 + halfsel * (SBN * 8), q));
                     }
@@ -282,6 +317,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                     mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 205);
                     tcgen05_fence_after();
                 }
+                uint4 o_even = make_uint4(0, 0, 0, 0);                  // packed h of the even sub-block of a pair (WIDE)
 #pragma unroll
                 for (int sb = 0; sb < SBN; ++sb) {
                     const int u0 = c * 64 + halfsel * (SBN * 8) + sb * 8;    // 8 hidden units u0 .. u0+7 (one 16-byte chunk of the h row)
@@ -346,11 +382,34 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                         }
                     } else if (active) {
                         float fi[8], ff[8], fg[8], fo[8], cn[8];
-                        unpack8(xq[sb][0], fi); unpack8(xq[sb][1], ff); unpack8(xq[sb][2], fg); unpack8(xq[sb][3], fo);
-                        const float cprev[8] = {cnext[0].x, cnext[0].y, cnext[0].z, cnext[0].w, cnext[1].x, cnext[1].y, cnext[1].z, cnext[1].w};
-                        if (s > 0 && sb < SBN - 1) {
+                        if constexpr (ROLL) {
+                            unpack8(xroll[sb & 1][0], fi); unpack8(xroll[sb & 1][1], ff); unpack8(xroll[sb & 1][2], fg); unpack8(xroll[sb & 1][3], fo);
+                            // next sub-block in processing order: same chunk, next chunk, or the first one of this row's next step
+                            const bool last_sb = sb == SBN - 1, last_chunk = c == NC - 1;
+                            const bool wrap = last_sb && last_chunk;
+                            if (!wrap || s + 1 < L) {
+                                const bf16* xr = wrap ? x_row(s + 1) : xrow;
+                                const int nu0 = !last_sb ? u0 + 8 : (!last_chunk ? (c + 1) * 64 + halfsel * (SBN * 8) : halfsel * (SBN * 8));
 #pragma unroll
-                            for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(c_ptr(s - 1, u0 + 8, q));
+                                for (int g = 0; g < 4; ++g) xroll[(sb + 1) & 1][g] = __ldg(reinterpret_cast<const uint4*>(xr + g * h + nu0));
+                            }
+                        } else {
+                            unpack8(xq[sb][0], fi); unpack8(xq[sb][1], ff); unpack8(xq[sb][2], fg); unpack8(xq[sb][3], fo);
+                        }
+                        const float cprev[8] = {cnext[0].x, cnext[0].y, cnext[0].z, cnext[0].w, cnext[1].x, cnext[1].y, cnext[1].z, cnext[1].w};
+                        // rolling prefetch of the cell state, one sub-block ahead ACROSS chunk and step boundaries: the state of the next
+                        // sub-block in processing order was written by this thread at least a chunk ago (the first sub-block of the next step:
+                        // in this step's first chunk).  Requested at the start of a chunk (right before the wait for the tensor core, which is
+                        // short because the cell epilogue is the slower side) the L2 round trip was the kernel's largest single stall
+                        // (ncu source page: 27 % of the epilogue warps' samples on the first use of this load).
+                        {
+                            const bool last_sb = sb == SBN - 1, last_chunk = c == NC - 1;
+                            const int nu0 = !last_sb ? u0 + 8 : (!last_chunk ? (c + 1) * 64 + halfsel * (SBN * 8) : halfsel * (SBN * 8));
+                            const bool need = (last_sb && last_chunk) ? (s + 1 < S && NC * SBN > 1) : (s > 0);     // (a single sub-block per step: after its store, below)
+                            if (need) {
+#pragma unroll
+                                for (int q = 0; q < 2; ++q) cnext[q] = *reinterpret_cast<const float4*>(c_ptr(s, nu0, q));
+                            }
                         }
                         uint32_t hp[4];                               // h of the 8 units as bf16 pairs
                         if constexpr (HIST) {
@@ -419,13 +478,25 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                                 *reinterpret_cast<float4*>(c_ptr(s, u0, q)) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
                             hp[0] = pack_bf16(hn[0], hn[1]); hp[1] = pack_bf16(hn[2], hn[3]); hp[2] = pack_bf16(hn[4], hn[5]); hp[3] = pack_bf16(hn[6], hn[7]);
                         }
+                        if (SBN == 1 && NC == 1 && s + 1 < S) {              // the only sub-block of the step: its new state was just stored
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) cnext[q] = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
+                        }
                         uint4 o0;
                         o0.x = hp[0]; o0.y = hp[1]; o0.z = hp[2]; o0.w = hp[3];
+                        if constexpr (WIDE) {                         // outputs of a pair of sub-blocks leave as 32-byte stores
+                            if (sb & 1) {
+                                stg256(orow + u0 - 8, o_even, o0);
+                                if (HIST && s + 1 < L) stg256(sq.hs_h + (static_cast<long long>(xbase) + tstep + (dir == 0 ? 1 : -1)) * 2 * h + dir * h + u0 - 8, o_even, o0);
+                                if (last) stg256(sq.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0 - 8, o_even, o0);
+                            } else o_even = o0;
+                        } else {
                         *reinterpret_cast<uint4*>(orow + u0) = o0;
                         // h_s is the *previous* state of the next step's token: stored at that token's row ([rows][2h], zero where a direction
                         // starts), so dW_hh = dGates^T . h_prev is one contraction over token rows with both operands in the same (schedule) order
                         if (HIST && s + 1 < L) *reinterpret_cast<uint4*>(sq.hs_h + (static_cast<long long>(xbase) + tstep + (dir == 0 ? 1 : -1)) * 2 * h + dir * h + u0) = o0;
                         if (last) *reinterpret_cast<uint4*>(sq.final_h + static_cast<long long>(grow) * 2 * h + dir * h + u0) = o0;
+                        }
                         st_shared_v4(h_dst + a0, o0.x, o0.y, o0.z, o0.w);
                         if (DUP) st_shared_v4(h_dst + a0 + DUP, o0.x, o0.y, o0.z, o0.w);
                     } else {
@@ -510,6 +581,10 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
                       const LstmHist* hist, const int* text_order, const int* text_soff) {
     if (B <= 0 || (!run_video && !run_text)) return STAIR_OK;
     if (!text_order || !text_soff) text_order = text_soff = nullptr;      // (training: the history, hs_h and the BPTT follow the same schedule)
+    {   // the cell epilogue reads the projections and writes its outputs with 32-byte accesses
+        const void* al[] = {xproj_v, vid_out, xproj_t, tokfeat, qfeat, hist ? hist->hs[0] : nullptr, hist ? hist->hs[1] : nullptr};
+        for (const void* q : al) if (reinterpret_cast<uintptr_t>(q) & 31) return STAIR_ERR_ARG;
+    }
     LstmFusedParams p;
     p.err_flag = err_flag;
     p.dbg = g_lstm_dbg;
@@ -527,9 +602,11 @@ int launch_lstm_fused(const void* xproj_v, void* vid_out, int T, const void* whh
     // Block dispatch follows the linear block index (x, then y, then z = sequence).  Batch order: video first, the text blocks (all L_max
     // steps long) fill the SMs the video blocks free.  Length-sorted text: text first, longest blocks first (x = 0), and the short video
     // blocks fill in behind the text blocks as those finish (longest-processing-time order: 0.40 -> 0.30 ms makespan at B = 4096).
-    if (run_text && text_order) { p.seq[nseq] = t; w[2 * nseq] = whh_t_f; w[2 * nseq + 1] = whh_t_r; ++nseq; }
+    // With more frames than words (I3D: T = 64) the video blocks are the long ones and stay first.
+    const bool text_first = text_order && L_max > T;
+    if (run_text && text_first) { p.seq[nseq] = t; w[2 * nseq] = whh_t_f; w[2 * nseq + 1] = whh_t_r; ++nseq; }
     if (run_video) { p.seq[nseq] = v; w[2 * nseq] = whh_v_f; w[2 * nseq + 1] = whh_v_r; ++nseq; }
-    if (run_text && !text_order) { p.seq[nseq] = t; w[2 * nseq] = whh_t_f; w[2 * nseq + 1] = whh_t_r; ++nseq; }
+    if (run_text && !text_first) { p.seq[nseq] = t; w[2 * nseq] = whh_t_f; w[2 * nseq + 1] = whh_t_r; ++nseq; }
     if (nseq == 1) { p.seq[1] = p.seq[0]; w[2] = w[0]; w[3] = w[1]; }
     CUtensorMap tm[4];
     for (int i = 0; i < 4; ++i) STAIR_TRY(make_tmap_bf16_2d(&tm[i], w[i], h, 4ULL * h, h, 64, 256));
