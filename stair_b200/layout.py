@@ -353,7 +353,8 @@ def _stage_rows(dst, srcs, row_off):
     ok = dst.is_contiguous() and dst.device.type == 'cpu' and dst.dtype in (torch.float32, torch.bfloat16)
     if ok:
         sd = srcs[0].dtype
-        ok = sd in (torch.float32, torch.bfloat16) and all(t.dtype == sd and t.device.type == 'cpu' and t.is_contiguous() for t in srcs)
+        cpu = torch.device('cpu')
+        ok = sd in (torch.float32, torch.bfloat16) and all([t.dtype == sd and t.device == cpu and t.is_contiguous() for t in srcs])
     if not ok or n < 16:
         for t, r in zip(srcs, row_off):
             dst[r:r + t.shape[0]].copy_(t)
@@ -452,19 +453,37 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
             glob = np.where(a[None, :] >= 0, a[None, :] + starts[:, None], a[None, :])
             node_arg[k, pos] = glob.reshape(-1).astype(np.int32)
         root[qs] = (starts + lay.root).astype(np.int32)
-    # word spans (per question data; module_net.py:128-129).  A missing entry raises KeyError like the reference.
-    for qi, (lay, e) in enumerate(zip(layouts, examples)):
-        if lay.word_nodes:
-            spans = e['prog_str_to_question_tokens']
-            base = node_start[qi]
-            for nd in lay.word_nodes:
-                s, t = spans[lay.token_of_node[nd]]
-                if s is None and t is None:
-                    s, t = -1, -1
-                elif s is None or t is None or s < 0 or t < 0:
-                    Lq = int(lens[qi])                            # python slice semantics of token_feature[s:t]
-                    s, t, _ = slice(s, t).indices(Lq)
-                node_span[0, base + nd], node_span[1, base + nd] = s, t
+    # word spans (per question data; module_net.py:128-129).  A missing entry raises KeyError like the reference.  Questions of one layout
+    # have the same word nodes: their (start, end) pairs are fetched with one itemgetter call per question and written with one numpy
+    # assignment per layout; None / negative entries (python slice semantics of token_feature[s:t]) take the per-element path.
+    from operator import itemgetter
+    for lay, qidx in by_layout.values():
+        if not lay.word_nodes:
+            continue
+        wn = list(lay.word_nodes)
+        keys_w = [lay.token_of_node[nd] for nd in wn]
+        get = itemgetter(*keys_w) if len(keys_w) > 1 else (lambda d, k=keys_w[0]: (d[k],))
+        rows = [get(examples[qi]['prog_str_to_question_tokens']) for qi in qidx]
+        qarr = np.asarray(qidx, np.int64)
+        pos = node_start[qarr][:, None] + np.asarray(wn, np.int64)[None, :]
+        try:
+            arr = np.array(rows, dtype=np.int64)                  # [questions, word nodes, 2]; a None inside raises TypeError
+            if arr.shape != (len(qidx), len(wn), 2):
+                raise ValueError
+        except (TypeError, ValueError):
+            arr = None
+        if arr is not None and not (arr < 0).any():
+            node_span[0, pos] = arr[:, :, 0]
+            node_span[1, pos] = arr[:, :, 1]
+            continue
+        for i, qi in enumerate(qidx):
+            for j in range(len(wn)):
+                s_, t_ = rows[i][j]
+                if s_ is None and t_ is None:
+                    s_, t_ = -1, -1
+                elif s_ is None or t_ is None or s_ < 0 or t_ < 0:
+                    s_, t_, _ = slice(s_, t_).indices(int(lens[qi]))
+                node_span[0, pos[i, j]], node_span[1, pos[i, j]] = s_, t_
     keys = np.unique(node_key)
     gid = np.searchsorted(keys, node_key).astype(np.int32)
     counts = np.bincount(gid, minlength=len(keys))

@@ -214,3 +214,41 @@ def test_length_sorted_text_schedule():
     b = LY.collate(qs)
     order, soff, tok_src = length_sorted_schedule(b.host_tab('q_off').numpy())
     assert (b.host_tab('q_order').numpy() == order).all() and (b.host_tab('q_soff').numpy() == soff).all() and (b.host_tab('tok_src').numpy() == tok_src).all()
+
+
+def test_collate_word_spans_fast_and_slow_paths_agree():
+    """collate writes the word spans of all questions of one layout in one assignment; (None, None), one-sided None and negative spans
+    (python slice semantics of ``token_feature[s:t]``, module_net.py:128-129) take the per-element path — both == a per-question
+    restatement, for batches that mix them."""
+    rng = np.random.default_rng(5)
+    qs = syn.make_questions(120, 8, 16, seed=6, templates=list(syn.ALL_TEMPLATES))
+    for i, d in enumerate(qs):
+        sp = dict(d['prog_str_to_question_tokens'])
+        Lq = int(d['question'].shape[0])
+        for k in list(sp):
+            r = rng.integers(0, 8)
+            if i % 3 == 0 and r == 0:
+                sp[k] = (None, None)
+            elif i % 3 == 0 and r == 1:
+                sp[k] = (None, int(rng.integers(1, Lq + 1)))
+            elif i % 3 == 0 and r == 2:
+                sp[k] = (int(rng.integers(-Lq, 0)), None)
+            elif i % 3 == 0 and r == 3:
+                sp[k] = (-2, -1)
+        d['prog_str_to_question_tokens'] = sp
+    b = LY.collate(qs)
+    span = b.host_tab('node_span').numpy().reshape(2, -1)
+    for qi, (lay, d) in enumerate(zip(b.layouts, qs)):
+        Lq = int(d['question'].shape[0])
+        for nd in lay.word_nodes:
+            s_, t_ = d['prog_str_to_question_tokens'][lay.token_of_node[nd]]
+            if s_ is None and t_ is None:
+                want = (-1, -1)
+            else:
+                want = slice(s_, t_).indices(Lq)[:2] if (s_ is None or t_ is None or s_ < 0 or t_ < 0) else (s_, t_)
+            got = (int(span[0, b.node_start[qi] + nd]), int(span[1, b.node_start[qi] + nd]))
+            assert got == tuple(want), (qi, nd, got, want)
+    others = np.ones(b.n_nodes, bool)
+    for qi, lay in enumerate(b.layouts):
+        others[b.node_start[qi] + np.asarray(lay.word_nodes, np.int64)] = False
+    assert (span[:, others] == -1).all()
