@@ -264,21 +264,10 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
         int acc = 0; uint32_t acc_phase = 0;
         constexpr bool GS_CHUNK_C = !HIST && CG == 8;                // the 16-warp comparison form loads the cell state per chunk
         float4 cnext[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};     // cell state of the next sub-block's 8 units
-        // ROLL: the input-projection pieces of a sub-block (4 gates x 16 bytes) are requested one sub-block ahead, across chunk and step
-        // boundaries, into two alternating register sets (the sub-block loop is unrolled and SBN is even, so the alternation is static).
-        // Requested per chunk right before the wait for the tensor core — which is short, the cell epilogue being the slower side — their
-        // HBM latency was exposed: 28 % of the epilogue warps' samples sat on the first use (ncu source page, r3_lstm_sorted_ncu_summary.txt).
+        // (Requesting the input-projection pieces one sub-block ahead as well — two alternating register sets — measured SLOWER, 1.26 ->
+        // 1.345 ms per forward: a thread's two sub-blocks share 32-byte sectors and separate requests double the L2 traffic.  They are
+        // requested per chunk, as one 32-byte load per gate: profiles/r3_lstm_sorted_ncu_summary.txt.)
         constexpr bool WIDE = SBN % 2 == 0;       // 32-byte input-projection loads / output stores for pairs of sub-blocks
-        constexpr bool ROLL = false;      // measured SLOWER (forward 1.26 -> 1.345 ms): see the comment above the per-chunk loads
-        uint4 xroll[2][4];
-        auto x_row = [&](int step) -> const bf16* {
-            return sq.xproj + (static_cast<long long>(xbase) + (dir == 0 ? step : L - 1 - step)) * 8 * h + dir * 4 * h;
-        };
-        if (ROLL && valid && L > 0) {
-            const bf16* xr = x_row(0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) xroll[0][g] = __ldg(reinterpret_cast<const uint4*>(xr + g * h + halfsel * (SBN * 8)));
-        }
         for (int s = 0; s < S; ++s) {
             const bool active = valid && s < L;
             const int tstep = dir == 0 ? s : L - 1 - s;
@@ -291,16 +280,16 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
             for (int c = 0; c < NC; ++c) {
                 // all global operands of this chunk (input projection, previous cell state) are requested before waiting for the
                 // tensor core, so their latency overlaps the MMA of this chunk instead of serialising 4x per chunk
-                uint4 xq[ROLL ? 1 : SBN][4];
+                uint4 xq[SBN][4];
                 if (active) {
-                    if constexpr (!ROLL && WIDE) {
+                    if constexpr (WIDE) {
 #pragma unroll
                         for (int sb = 0; sb < SBN; sb += 2) {          // a pair of sub-blocks = 16 units = one 32-byte sector per gate
                             const int u0 = c * 64 + halfsel * (SBN * 8) + sb * 8;
 #pragma unroll
                             for (int g = 0; g < 4; ++g) ldg256_nc(xrow + g * h + u0, xq[sb][g], xq[sb + 1][g]);
                         }
-                    } else if constexpr (!ROLL) {
+                    } else {
 #pragma unroll
                         for (int sb = 0; sb < SBN; ++sb) {
                             const int u0 = c * 64 + halfsel * (SBN * 8) + sb * 8;
@@ -382,20 +371,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constan
                         }
                     } else if (active) {
                         float fi[8], ff[8], fg[8], fo[8], cn[8];
-                        if constexpr (ROLL) {
-                            unpack8(xroll[sb & 1][0], fi); unpack8(xroll[sb & 1][1], ff); unpack8(xroll[sb & 1][2], fg); unpack8(xroll[sb & 1][3], fo);
-                            // next sub-block in processing order: same chunk, next chunk, or the first one of this row's next step
-                            const bool last_sb = sb == SBN - 1, last_chunk = c == NC - 1;
-                            const bool wrap = last_sb && last_chunk;
-                            if (!wrap || s + 1 < L) {
-                                const bf16* xr = wrap ? x_row(s + 1) : xrow;
-                                const int nu0 = !last_sb ? u0 + 8 : (!last_chunk ? (c + 1) * 64 + halfsel * (SBN * 8) : halfsel * (SBN * 8));
-#pragma unroll
-                                for (int g = 0; g < 4; ++g) xroll[(sb + 1) & 1][g] = __ldg(reinterpret_cast<const uint4*>(xr + g * h + nu0));
-                            }
-                        } else {
-                            unpack8(xq[sb][0], fi); unpack8(xq[sb][1], ff); unpack8(xq[sb][2], fg); unpack8(xq[sb][3], fo);
-                        }
+                        unpack8(xq[sb][0], fi); unpack8(xq[sb][1], ff); unpack8(xq[sb][2], fg); unpack8(xq[sb][3], fo);
                         const float cprev[8] = {cnext[0].x, cnext[0].y, cnext[0].z, cnext[0].w, cnext[1].x, cnext[1].y, cnext[1].z, cnext[1].w};
                         // rolling prefetch of the cell state, one sub-block ahead ACROSS chunk and step boundaries: the state of the next
                         // sub-block in processing order was written by this thread at least a chunk ago (the first sub-block of the next step:
