@@ -83,6 +83,39 @@ def all_gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tens
     return torch.cat([out[r * mx:r * mx + sizes[r]] for r in range(world)])
 
 
+class AnswerGather:
+    """NCCL all-gather of every step's answers, ``depth`` steps deep: step k's gather runs on NCCL's stream while step k+1 computes, and
+    the compute stream only waits for a gather when its buffer comes round again (or at ``finish``).  A synchronous gather makes every step
+    a rendez-vous of all ranks — each step then lasts as long as ITS slowest rank, which at 8 ranks costs more than the 131 KB collective
+    itself; one step of slack absorbs that jitter.  Equal shard sizes (``n_local`` answers per rank)."""
+
+    def __init__(self, n_local: int, device, group=None, depth: int = 2, dtype=torch.int32):
+        self.group, self.depth = group, max(1, int(depth))
+        world = dist.get_world_size(group)
+        self.bufs = [torch.empty(world * n_local, dtype=dtype, device=device) for _ in range(self.depth)]
+        self.pending = []                                        # (work, buffer, input kept alive), oldest first
+        self.k = 0
+
+    def submit(self, answers: torch.Tensor) -> torch.Tensor:
+        """Start gathering ``answers`` (this rank's [n_local]); returns the buffer the result lands in (valid after ``finish`` or after
+        ``depth`` further submits)."""
+        if len(self.pending) >= self.depth:
+            self.pending.pop(0)[0].wait()                        # stream-side wait: the buffer about to be reused is complete
+        buf = self.bufs[self.k % self.depth]
+        self.k += 1
+        work = dist.all_gather_into_tensor(buf, answers.contiguous(), group=self.group, async_op=True)
+        self.pending.append((work, buf, answers))
+        return buf
+
+    def finish(self):
+        """Make the current stream wait for every outstanding gather; returns the most recent result (None before the first submit)."""
+        last = self.pending[-1][1] if self.pending else (self.bufs[(self.k - 1) % self.depth] if self.k else None)
+        for work, _, _ in self.pending:
+            work.wait()
+        self.pending.clear()
+        return last
+
+
 class ShardedNMN:
     """Batch-sharded inference: ``model`` is a (replicated) ``stair_b200.VideoNMN`` on this rank's GPU."""
 

@@ -68,3 +68,39 @@ def test_numa_binding_helper_is_tolerant(tmp_path):
     assert _parse_cpulist('') == set()
     info = bind_to_gpu_numa_node(0, sysfs=str(tmp_path))
     assert info['bound_cpus'] == 0 and info['numa_node'] is None
+
+
+def _gather_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        n = 6
+        g = D.AnswerGather(n, 'cpu', depth=2)
+        assert g.finish() is None
+        ok, bufs = True, []
+        for step in range(5):                                            # five steps through two buffers: results checked one step late
+            local = torch.arange(n, dtype=torch.int32) + 100 * rank + 1000 * step
+            bufs.append((step, g.submit(local)))
+        last = g.finish()
+        want = torch.cat([torch.arange(n, dtype=torch.int32) + 100 * r + 1000 * 4 for r in range(world)])
+        ok = ok and torch.equal(last, want) and last is bufs[-1][1]
+        prev = bufs[-2][1]                                                # step 3's result sits in the other buffer
+        ok = ok and torch.equal(prev, torch.cat([torch.arange(n, dtype=torch.int32) + 100 * r + 1000 * 3 for r in range(world)]))
+        out_q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pipelined_answer_gather_world2_gloo():
+    """distributed.AnswerGather (the bench's per-step NCCL gather, one step behind the compute): order and contents over gloo."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
