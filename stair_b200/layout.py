@@ -457,6 +457,7 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
     # have the same word nodes: their (start, end) pairs are fetched with one itemgetter call per question and written with one numpy
     # assignment per layout; None / negative entries (python slice semantics of token_feature[s:t]) take the per-element path.
     from operator import itemgetter
+    from itertools import chain
     for lay, qidx in by_layout.values():
         if not lay.word_nodes:
             continue
@@ -466,9 +467,10 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
         rows = [get(examples[qi]['prog_str_to_question_tokens']) for qi in qidx]
         qarr = np.asarray(qidx, np.int64)
         pos = node_start[qarr][:, None] + np.asarray(wn, np.int64)[None, :]
-        try:
-            arr = np.array(rows, dtype=np.int64)                  # [questions, word nodes, 2]; a None inside raises TypeError
-            if arr.shape != (len(qidx), len(wn), 2):
+        try:                                                      # [questions, word nodes, 2]; a None inside raises TypeError
+            flat = chain.from_iterable(chain.from_iterable(rows))
+            arr = np.fromiter(flat, dtype=np.int64, count=len(qidx) * len(wn) * 2).reshape(len(qidx), len(wn), 2)
+            if next(flat, None) is not None:
                 raise ValueError
         except (TypeError, ValueError):
             arr = None
@@ -503,8 +505,9 @@ def collate(examples, pin_memory=False, video_dtype=None, question_dtype=None, m
         it[o:o + size] = arr
     b.itab_host = itab
     b.answer = None
-    if all('answer' in e for e in examples):
-        b.answer = torch.tensor([int(e['answer']) for e in examples], dtype=torch.int64)
+    ans = [e.get('answer') for e in examples]
+    if not any([a is None for a in ans]):                        # (identity test: `None in ans` would call Tensor.__eq__ per element)
+        b.answer = torch.tensor([a.item() if isinstance(a, torch.Tensor) else int(a) for a in ans], dtype=torch.int64)
     return b
 
 
