@@ -152,11 +152,13 @@ typedef struct StairBatch {
     const int32_t* group_deps; /* HOST [n_groups][STAIR_MAX_GROUP_DEPS] or NULL: the groups whose outputs group g reads (-1 = unused entry; a first
                                 * entry of -2 = "every earlier group").  With it the module phase is scheduled by data dependency (a group starts as
                                 * soon as its producers are done) instead of wave by wave. */
-    /* Optional length-sorted schedule of the inference text recurrence (all three or none; stair_b200.layout.collate fills them):
+    /* Optional length-sorted schedule of the text recurrence — inference and, with the fused forward + persistent BPTT, the training
+     * step, whose forward and backward calls must then see the same three arrays (all three or none; stair_b200.layout.collate fills them):
      * q_order [B] = the question ids in descending question length (a permutation of 0..B-1), q_soff [B+1] = token offsets in THAT order,
      * tok_src [n_tok] = the token row (batch order) of every sorted row: tok_src[q_soff[p] + s] = q_off[q_order[p]] + s.  Scheduling data
-     * only: the outputs keep the batch's order and do not depend on it.  NULL: the library sorts on the device itself (two small kernels
-     * in front of the text staging) unless stair_set_text_sort(0). */
+     * only: the outputs keep the batch's order and do not depend on it (training: gradients equal up to fp32 summation order).  NULL:
+     * inference sorts on the device itself (two small kernels in front of the text staging) unless stair_set_text_sort(0); training
+     * keeps batch order. */
     const int32_t* q_order; const int32_t* q_soff; const int32_t* tok_src;
 } StairBatch;
 
